@@ -1,0 +1,135 @@
+"""TEST INFRASTRUCTURE (oracle) - drives the UNMODIFIED reference (`isls` at HEAD) from outside.
+
+Only usable where the reference tree exists (this build container: /root/reference, or $ISLS_REFERENCE).
+It is used solely by tests/golden/make_golden.py to produce the committed golden vectors and by the
+container-only cross-check tests; nothing on the GPU box imports it (the reference does not travel).
+
+The reference is imported read-only and patched from outside, never edited:
+  S0  stub `matplotlib` package on sys.path (base.py:4, sls_base.py:4, utils.py:6-8 import it at module level)
+  S1  obj.C = obj.Sw, obj.D = obj.Su            (isls_base.py:152-158 / isls.py:426-438 use C, D; base.py:18-19
+                                                 defines Sw, Su)
+  S2  ADMM(threshold=...) -> ADMM(tol=...)       (isls.py:480-486 passes `threshold`, admm.py:6-8 takes `tol`)
+  S3  always log=True                            (isls.py:489-490 index the return tuple assuming the log entry)
+  S4  quadratic via-point cost as cost_function  (isls_base.py:113-117 falls back to an undefined compute_cost)
+"""
+import contextlib
+import io
+import os
+import sys
+import warnings
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE_ROOT = os.environ.get("ISLS_REFERENCE", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "isls"))
+
+
+_mod = {}
+
+
+def load():
+    """Import the reference package (once) and return (isls_module, isls.isls module)."""
+    if _mod:
+        return _mod["pkg"], _mod["isls"]
+    if not available():
+        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+    stubs = os.path.join(_HERE, "stubs")
+    for p in (REFERENCE_ROOT, stubs):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import isls as pkg                      # noqa: E402
+        import isls.isls as isls_mod            # noqa: E402
+    orig_admm = isls_mod.ADMM
+
+    def admm_accepting_threshold(*a, threshold=None, **k):          # shim S2
+        if threshold is not None:
+            k["tol"] = threshold
+        return orig_admm(*a, **k)
+
+    isls_mod.ADMM = admm_accepting_threshold
+    _mod.update(pkg=pkg, isls=isls_mod, orig_admm=orig_admm)
+    return pkg, isls_mod
+
+
+@contextlib.contextmanager
+def quiet():
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        yield
+
+
+def quadratic_cost(Q_dense, xd, R_dense):
+    """sum (x-xd)' Q (x-xd) + u' R u over the flattened horizon, batched over a leading axis
+    (same expression as sls_base.py:25-44)."""
+    def cost(x, u):
+        single = (x.ndim == 2)
+        xf = x.reshape(1, -1) if single else x.reshape(x.shape[0], -1)
+        uf = u.reshape(1, -1) if single else u.reshape(u.shape[0], -1)
+        dx = xf - xd
+        c = np.sum(dx * (Q_dense @ dx.T).T, axis=-1) + np.sum(uf * (R_dense @ uf.T).T, axis=-1)
+        return c[0] if single else c
+    return cost
+
+
+def make_isls(model, N, zs, Qs, seq, u_std):
+    """iSLS object with forward model, quadratic via-point cost and shims S1/S4 applied."""
+    pkg, _ = load()
+    with quiet():
+        s = pkg.iSLS(model.n, model.m, N)
+        s.C, s.D = s.Sw, s.Su                                        # shim S1
+        s.forward_model = model.f
+        s.set_quadratic_cost(zs, Qs, seq, u_std)
+        Qd = s.Q.toarray()
+        Rd = s.R.toarray()
+        s.cost_function = quadratic_cost(Qd, s.xd, Rd)               # shim S4
+    return s
+
+
+def get_Cs_quadratic(s):
+    """Analytic get_Cs for the via-point cost: c=[2Q_t(x-z_t); 2R u], C=blkdiag(2Q_t, 2R)
+    (what isls.py:263-271 computes inline in the `Cts is None` branch)."""
+    n, m, N = s.x_dim, s.u_dim, s.N
+
+    def get_Cs(x, u):
+        c = np.zeros((N, n + m))
+        C = np.zeros((N, n + m, n + m))
+        for t in range(N):
+            Q = s.Qs[s.seq[t]]
+            c[t, :n] = 2 * Q @ (x[t] - s.zs[s.seq[t]])
+            c[t, n:] = 2 * s.Rt @ u[t]
+            C[t, :n, :n] = 2 * Q
+            C[t, n:, n:] = 2 * s.Rt
+        return c, C
+    return get_Cs
+
+
+def init_nominal(s, x0, u0):
+    with quiet():
+        x_nom, u_nom = s.rollout_batch(np.asarray(x0)[None], np.asarray(u0)[None])
+        s.reset()
+        s.nominal_values = x_nom[0], u_nom[0]
+
+
+def run_ilqr_admm(s, model, project_x=False, project_u=False, rho_x=None, rho_u=None, max_iter=20,
+                  max_admm_iter=20, max_line_search_iter=20, alpha=1.0, tol=1e-3):
+    """Shimmed HEAD `iSLS.ilqr_admm` (isls.py:379-501). Returns dict(x, u, cost_log, admm_log)."""
+    with quiet():
+        log = s.ilqr_admm(model.get_AB, project_x=project_x, project_u=project_u, rho_x=rho_x, rho_u=rho_u,
+                          max_iter=max_iter, max_admm_iter=max_admm_iter,
+                          max_line_search_iter=max_line_search_iter, alpha=alpha, tol=tol, log=True)  # S3
+    return dict(x=s.x_nom.copy(), u=s.u_nom.copy(), cost_log=np.array(s.cost_log, dtype=np.float64),
+                admm_log=np.array(log, dtype=np.float64))
+
+
+def run_ilqr_dp(s, model, max_iter=100, max_line_search_iter=25, tol_fun=1e-5):
+    """HEAD `iSLS.solve(method='dp')` (isls.py:54-132) with the analytic get_Cs."""
+    with quiet():
+        s.solve(model.get_AB, get_Cs_quadratic(s), method="dp", max_iter=max_iter,
+                max_line_search_iter=max_line_search_iter, tol_fun=tol_fun)
+    return dict(x=s.x_nom.copy(), u=s.u_nom.copy(), cost_log=np.array(s.cost_log, dtype=np.float64))

@@ -1,0 +1,544 @@
+"""TEST INFRASTRUCTURE (oracle) - numpy restatement of the reference's iLQR / iLQR-ADMM / LQT-ADMM hot path.
+
+This is the checker, never the product: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs may import it.  The CUDA path must not (and does not) route through it.
+
+Parity status: PINNED.  tests/test_oracle_vs_reference.py (container only, needs /root/reference) runs the
+unmodified reference (oracle/ref_shim.py) side by side with this file, and tests/golden/*.npz hold
+reference-generated vectors (made by tests/golden/make_golden.py) that this file is checked against
+everywhere (including the GPU box, where the reference does not exist).
+
+What is restated (reference file:line -> function here):
+  isls/isls_base.py:10-11   alpha grid 10**linspace(0,-5,50)                     -> alphas()
+  isls/sls_base.py:25-44    quadratic via-point cost (no 1/2)                    -> quad_cost()
+  isls/isls.py:135-154      open-loop rollout for all candidates                 -> rollout_open()
+  isls/isls.py:310-334      closed-loop rollout u=K(x-x^)+a k+u^                 -> rollout_closed()
+  isls/isls.py:229-308      Riccati recursion K_t,k_t (dposv on Quu)             -> backward_pass()
+  isls/sls.py:85-166        the same with ADMM regularisers + Quu/Qux logs       -> backward_pass(logs=True)
+  isls/sls.py:168-202       feed-forward-only recursion (constant K)             -> ff_pass()
+  isls/isls.py:336-374      iterate_once_dp: line search, NaN->1e5, accept test  -> ilqr_dp()
+  isls/isls.py:54-132       iLQR outer loop and its stop rules                   -> ilqr_dp()
+  isls/isls.py:379-501      ilqr_admm outer loop, f_argmin, warm start, stops    -> ilqr_admm()
+  isls/admm.py:6-106        ADMM driver: z-projection, scaled dual, residuals    -> (inlined in ilqr_admm / lqt_admm_dp)
+  isls/projections.py:7-11  project_bound = np.clip                              -> np.clip
+  isls/sls.py:298-317       ADMM_LQT_DP (Riccati once, ff-pass per iteration)    -> lqt_admm_dp()
+  isls/base.py:55-79        rho expansion (diagonal rho only)    -> problem dict rho_x / rho_u
+
+The reference's `ilqr_admm` solves the inner LQ problem in dense batch least-squares form
+(isls.py:436-465).  The recipe used here is the Riccati form of the same minimiser (SURVEY.md 8c'): one K-pass
+per linearisation, one ff-pass + linear rollout per ADMM iteration giving the identical delta_u*, including the
+batch form's treatment of the last control (u_{N-1} does not influence any state, so
+delta_u_{N-1} = -Cuu^-1 cu_{N-1}).  It is checked against the unmodified reference in the container tests.
+
+Everything is batched over a leading problem axis (the reference solves one problem; B=1 reproduces it).
+Per-problem early exit is handled by compacting the still-active problems, so each problem sees exactly the
+iteration sequence the reference would run for it alone.
+"""
+import numpy as np
+
+from . import models as _models
+
+# status bits (mirrored by include/isls_b200.h)
+ST_CONVERGED_COST = 1      # |cost - prev_cost| < tol   (isls.py:125, isls.py:493)
+ST_LINESEARCH_FAIL = 2     # forward pass failed         (isls.py:128)
+ST_MAX_ITER = 4            # budget exhausted            (isls.py:131)
+ST_OSCILLATING = 8         # mean-of-4 test              (isls.py:497)
+ST_NON_PD = 16             # Quu not positive definite   (LinAlgError at isls.py:296)
+ST_NAN_COST = 32           # NaN cost seen in line search (isls.py:362)
+
+ADMM_CONVERGED = 1         # admm.py:72
+ADMM_STALLED = 2           # admm.py:80
+ADMM_MAXIT = 3             # admm.py:93
+
+
+def alphas(L):
+    """isls_base.py:10-11."""
+    return (10.0 ** np.linspace(0.0, -5.0, 50))[:L]
+
+
+# --------------------------------------------------------------------------------------------------- cost
+def _zs_b(p, B):
+    zs = np.asarray(p["zs"], dtype=np.float64)
+    if zs.ndim == 2:
+        zs = np.broadcast_to(zs, (B,) + zs.shape)
+    return zs
+
+
+def quad_cost(p, zs, x, u):
+    """sum_t (x_t-z_t)'Q_t(x_t-z_t) + u_std * sum u^2  (sls_base.py:25-44 with block-diagonal Q from
+    utils.py:101-115 and R = u_std I, base.py:86-89).  x[B,L,N,n], u[B,L,N,m], zs[B,k,n] -> [B,L]."""
+    seq = p["seq"]
+    Qd = p["Qdiag"][seq]                       # [N,n]
+    xd = zs[:, seq]                            # [B,N,n]
+    dx = x - xd[:, None]
+    c = np.sum(dx * dx * Qd, axis=(-1, -2))
+    c = c + p["u_std"] * np.sum(u * u, axis=(-1, -2))
+    return c
+
+
+# ------------------------------------------------------------------------------------------------ rollouts
+def rollout_open(model, x0, u):
+    """isls.py:135-154.  x0[B,n], u[B,L,N,m] -> x[B,L,N,n]."""
+    B, L, N, m = u.shape
+    x = np.broadcast_to(x0[:, None, :], (B, L, x0.shape[-1])).copy()
+    xs = np.empty((B, L, N, x0.shape[-1]))
+    for t in range(N):
+        xs[:, :, t] = x
+        x = model.f(x, u[:, :, t])
+    return xs
+
+
+def rollout_closed(model, x_nom, u_nom, K, k_cand):
+    """isls.py:310-334.  x_nom[B,N,n], u_nom[B,N,m], K[B,N,m,n], k_cand[B,L,N,m]."""
+    B, L, N, m = k_cand.shape
+    n = x_nom.shape[-1]
+    x = np.broadcast_to(x_nom[:, None, 0, :], (B, L, n)).copy()
+    xs = np.empty((B, L, N, n))
+    us = np.empty((B, L, N, m))
+    for t in range(N):
+        dx = x - x_nom[:, None, t]
+        u = np.einsum("bij,blj->bli", K[:, t], dx) + k_cand[:, :, t] + u_nom[:, None, t]
+        us[:, :, t] = u
+        xs[:, :, t] = x
+        x = model.f(x, u)
+    return xs, us
+
+
+# ------------------------------------------------------------------------------------------------- Riccati
+def _T(a):
+    return np.swapaxes(a, -1, -2)
+
+
+def backward_pass(A, Bm, cx, cu, Cxx, Cuu, Cux=None, logs=False):
+    """Riccati recursion of isls.py:229-308 (general `Cts` branch), batched.
+
+    A[B,N,n,n], Bm[B,N,n,m], cx[B,N,n], cu[B,N,m], Cxx[B,N,n,n], Cuu[B,N,m,m] (leading B may be 1 for the
+    cost terms), Cux[B,N,m,n] or None.  Returns K[B,N,m,n], k[B,N,m], non_pd[B] (+ Quu, Quu_inv, Qux logs as in
+    sls.py:117-120,159-162).  K[N-1] = k[N-1] = 0 (isls.py:245-246, 261).
+    """
+    Bsz, N, n, m = Bm.shape
+    K = np.zeros((Bsz, N, m, n))
+    k = np.zeros((Bsz, N, m))
+    non_pd = np.zeros(Bsz, dtype=bool)
+    V = np.broadcast_to(Cxx[:, -1], (Bsz, n, n)).copy()           # isls.py:257
+    v = np.broadcast_to(cx[:, -1], (Bsz, n)).copy()               # isls.py:258
+    if logs:
+        Quu_log = np.zeros((Bsz, N, m, m))
+        Quu_inv_log = np.zeros((Bsz, N, m, m))
+        Qux_log = np.zeros((Bsz, N, m, n))
+    for t in range(N - 2, -1, -1):
+        At, Bt = A[:, t], Bm[:, t]
+        qx = cx[:, t] + np.einsum("bji,bj->bi", At, v)            # isls.py:285
+        qu = cu[:, t] + np.einsum("bji,bj->bi", Bt, v)            # isls.py:286
+        VA = V @ At
+        Qxx = Cxx[:, t] + _T(At) @ VA                             # isls.py:288
+        Qux = _T(Bt) @ VA                                         # isls.py:289
+        if Cux is not None:
+            Qux = Qux + Cux[:, t]
+        Quu = Cuu[:, t] + _T(Bt) @ (V @ Bt)                       # isls.py:290
+        # dposv (isls.py:296) raises for non-PD Quu: flag those problems and keep them finite
+        ev = np.linalg.eigvalsh(0.5 * (Quu + _T(Quu)))
+        bad = ~(ev.min(axis=-1) > 0.0)
+        non_pd |= bad
+        Quu_s = np.where(bad[:, None, None], np.eye(m), Quu)
+        rhs = np.concatenate([Qux, qu[:, :, None]], axis=-1)
+        sol = -np.linalg.solve(Quu_s, rhs)
+        Kt, kt = sol[:, :, :-1], sol[:, :, -1]
+        V = Qxx + _T(Kt) @ Quu @ Kt + _T(Qux) @ Kt + _T(Kt) @ Qux                       # isls.py:300
+        v = (qx + np.einsum("bji,bj->bi", Kt, qu) + np.einsum("bji,bj->bi", Kt, np.einsum("bij,bj->bi", Quu, kt))
+             + np.einsum("bji,bj->bi", Qux, kt))                                         # isls.py:302
+        K[:, t], k[:, t] = Kt, kt
+        if logs:
+            Quu_log[:, t], Qux_log[:, t] = Quu, Qux
+            Quu_inv_log[:, t] = np.linalg.inv(Quu_s)
+    if logs:
+        return K, k, non_pd, Quu_log, Quu_inv_log, Qux_log
+    return K, k, non_pd
+
+
+def ff_pass(A, Bm, cx, cu, K, Quu, Quu_inv, Qux):
+    """Feed-forward-only recursion of sls.py:168-202 (time-varying A,B).  Returns k[B,N,m] with k[N-1]=0."""
+    Bsz, N, n, m = Bm.shape
+    k = np.zeros((Bsz, N, m))
+    v = cx[:, -1].copy()
+    for t in range(N - 2, -1, -1):
+        qx = cx[:, t] + np.einsum("bji,bj->bi", A[:, t], v)                              # sls.py:196
+        qu = cu[:, t] + np.einsum("bji,bj->bi", Bm[:, t], v)                             # sls.py:197
+        kt = -np.einsum("bij,bj->bi", Quu_inv[:, t], qu)                                 # sls.py:198
+        v = (qx + np.einsum("bji,bj->bi", Qux[:, t], kt) + np.einsum("bji,bj->bi", K[:, t], qu)
+             + np.einsum("bji,bj->bi", K[:, t], np.einsum("bij,bj->bi", Quu[:, t], kt)))   # sls.py:199
+        k[:, t] = kt
+    return k
+
+
+def linear_rollout(A, Bm, K, k, dx0=None):
+    """du_t = K_t dx_t + k_t ; dx_{t+1} = A_t dx_t + B_t du_t  (the closed form of l_side_inv @ rhs,
+    isls.py:465, in Riccati form)."""
+    Bsz, N, n, m = Bm.shape
+    dx = np.zeros((Bsz, n)) if dx0 is None else dx0.copy()
+    du = np.zeros((Bsz, N, m))
+    dxs = np.zeros((Bsz, N, n))
+    for t in range(N):
+        dxs[:, t] = dx
+        du[:, t] = np.einsum("bij,bj->bi", K[:, t], dx) + k[:, t]
+        if t < N - 1:
+            dx = np.einsum("bij,bj->bi", A[:, t], dx) + np.einsum("bij,bj->bi", Bm[:, t], du[:, t])
+    return dxs, du
+
+
+# ------------------------------------------------------------------------------------------ problem helpers
+def _model_of(p):
+    if p["model"] == "double_integrator":
+        return _models.make_model("double_integrator", nb_dim=p["m"], dt=p["dt"])
+    return _models.make_model(p["model"], dt=p["dt"])
+
+
+def _diag_embed(d):
+    out = np.zeros(d.shape + (d.shape[-1],))
+    i = np.arange(d.shape[-1])
+    out[..., i, i] = d
+    return out
+
+
+def _bounds(p, key, N, dim):
+    lo, hi = p.get("lo_" + key), p.get("hi_" + key)
+    if lo is None and hi is None:
+        return None
+    lo = np.full((N, dim), -np.inf) if lo is None else np.broadcast_to(np.asarray(lo, float), (N, dim))
+    hi = np.full((N, dim), np.inf) if hi is None else np.broadcast_to(np.asarray(hi, float), (N, dim))
+    return lo, hi
+
+
+def initial_rollout(p):
+    """What the reference user does before calling a solver (notebooks, e.g. Car/...control constraints cell 11):
+    roll the initial control guess out from x0 and set it as the nominal trajectory."""
+    model = _model_of(p)
+    x0 = np.asarray(p["x0"], dtype=np.float64)
+    B = x0.shape[0]
+    u0 = np.asarray(p["u0"], dtype=np.float64)
+    u_nom = np.broadcast_to(u0, (B,) + u0.shape[-2:]).copy()
+    x_nom = rollout_open(model, x0, u_nom[:, None])[:, 0]
+    return x_nom, u_nom
+
+
+# -------------------------------------------------------------------------------------------- plain iLQR (DP)
+def ilqr_dp(p, max_iter=100, L=25, tol_fun=1e-5, fixed_budget=False):
+    """iSLS.solve(method='dp') for the quadratic via-point cost (isls.py:54-132 + 336-374)."""
+    model = _model_of(p)
+    N, n, m = p["N"], p["n"], p["m"]
+    x_nom, u_nom = initial_rollout(p)
+    B = x_nom.shape[0]
+    zs = _zs_b(p, B)
+    seq = p["seq"]
+    Qd = p["Qdiag"][seq]
+    al = alphas(L)
+    cost = quad_cost(p, zs, x_nom[:, None], u_nom[:, None])[:, 0]
+    cost_log = np.full((B, max_iter + 1), np.nan)
+    cost_log[:, 0] = cost
+    n_log = np.ones(B, dtype=np.int64)
+    status = np.zeros(B, dtype=np.int32)
+    iters = np.zeros(B, dtype=np.int32)
+    alpha_idx = np.full((B, max_iter), -1, dtype=np.int32)
+    active = np.ones(B, dtype=bool)
+    Cxx = _diag_embed(2.0 * Qd)[None]
+    Cuu = _diag_embed(np.full((N, m), 2.0 * p["u_std"]))[None]
+    K_out = np.zeros((B, N, m, n))
+    k_out = np.zeros((B, N, m))
+    for it in range(max_iter):
+        idx = np.nonzero(active)[0]
+        if idx.size == 0:
+            break
+        xn, un = x_nom[idx], u_nom[idx]
+        A, Bm = model.get_AB(xn, un)
+        cx = 2.0 * Qd * (xn - zs[idx][:, seq])
+        cu = 2.0 * p["u_std"] * un
+        K, k, non_pd = backward_pass(A, Bm, cx, cu, Cxx, Cuu)
+        K_out[idx], k_out[idx] = K, k
+        k_cand = k[:, None] * al[None, :, None, None]                         # isls.py:357
+        xs, us = rollout_closed(model, xn, un, K, k_cand)
+        costs = quad_cost(p, zs[idx], xs, us)
+        nan = np.isnan(costs)
+        costs = np.where(nan, 1e5, costs)                                     # isls.py:362
+        ind = np.argmin(costs, axis=1)
+        best = costs[np.arange(idx.size), ind]
+        ok = (best - cost[idx]) < 0.0                                         # isls.py:365-367
+        ok &= ~non_pd
+        iters[idx] += 1
+        alpha_idx[idx, it] = np.where(ok, ind, -1)
+        acc = idx[ok]
+        x_nom[acc] = xs[ok, ind[ok]]
+        u_nom[acc] = us[ok, ind[ok]]
+        # nominal_values setter re-evaluates the cost (isls_base.py:80-85)
+        newc = quad_cost(p, zs[acc], x_nom[acc][:, None], u_nom[acc][:, None])[:, 0]
+        cost[acc] = newc
+        cost_log[acc, n_log[acc]] = newc
+        n_log[acc] += 1
+        status[idx[non_pd]] |= ST_NON_PD
+        status[idx[nan.any(axis=1)]] |= ST_NAN_COST
+        if not fixed_budget:
+            for j, b in enumerate(idx):
+                nl = n_log[b]
+                small = nl >= 2 and abs(cost_log[b, nl - 1] - cost_log[b, nl - 2]) < tol_fun   # isls.py:125
+                if small:
+                    status[b] |= ST_CONVERGED_COST
+                    active[b] = False
+                elif not ok[j]:                                               # isls.py:128
+                    status[b] |= ST_LINESEARCH_FAIL
+                    active[b] = False
+    status[active] |= ST_MAX_ITER
+    return dict(x=x_nom, u=u_nom, cost=cost, cost_log=cost_log, n_log=n_log, status=status, iters=iters,
+                alpha_idx=alpha_idx, K=K_out, k=k_out)
+
+
+# ----------------------------------------------------------------------------------------------- iLQR-ADMM
+def ilqr_admm(p, fixed_budget=False, outer_tol=1e-3, keep_trace=False):
+    """Riccati-form restatement of iSLS.ilqr_admm (isls.py:379-501) + ADMM (admm.py:6-106) with box projections.
+
+    p : problem dict (oracle/problems.py).  Returns final nominal (x,u), cost_log, per-problem iteration
+    counts, ADMM residual logs, final z / lambda and the clip masks of the last projection.
+    """
+    model = _model_of(p)
+    N, n, m = p["N"], p["n"], p["m"]
+    I_o, I_a, L, tol, relax = p["I_o"], p["I_a"], p["L"], p["tol"], p.get("alpha", 1.0)
+    x_nom, u_nom = initial_rollout(p)
+    B = x_nom.shape[0]
+    zs = _zs_b(p, B)
+    seq = p["seq"]
+    Qd = p["Qdiag"][seq]                                                      # [N,n]
+    R = p["u_std"]
+    bx, bu = _bounds(p, "x", N, n), _bounds(p, "u", N, m)
+    proj_x, proj_u = bx is not None, bu is not None
+    rho_x = np.broadcast_to(np.asarray(p["rho_x"], float), (N, n)) if proj_x else np.zeros((N, n))
+    rho_u = np.broadcast_to(np.asarray(p["rho_u"], float), (N, m)) if proj_u else np.zeros((N, m))
+    al = alphas(L)
+
+    cost = quad_cost(p, zs, x_nom[:, None], u_nom[:, None])[:, 0]
+    cost_log = np.full((B, I_o + 1), np.nan)
+    cost_log[:, 0] = cost
+    n_log = np.ones(B, dtype=np.int64)
+    status = np.zeros(B, dtype=np.int32)
+    outer_iters = np.zeros(B, dtype=np.int32)
+    admm_iters = np.zeros((B, I_o), dtype=np.int32)
+    admm_exit = np.zeros((B, I_o), dtype=np.int32)
+    res_log = np.full((B, I_o, I_a, 2), np.nan)
+    alpha_idx = np.full((B, I_o, I_a), -1, dtype=np.int32)
+    z_x, z_u = np.zeros((B, N, n)), np.zeros((B, N, m))
+    lam_x, lam_u = np.zeros((B, N, n)), np.zeros((B, N, m))
+    mask_x = np.zeros((B, N, n), dtype=np.int8)      # -1 clipped at lo, +1 clipped at hi (last projection)
+    mask_u = np.zeros((B, N, m), dtype=np.int8)
+    trace = [] if keep_trace else None
+    active = np.ones(B, dtype=bool)
+
+    Cxx = _diag_embed(2.0 * (Qd + rho_x))[None]                               # recipe step 1
+    Cuu = _diag_embed(2.0 * (R + rho_u))[None]
+    Cuu_last = 2.0 * (R + rho_u[-1])
+
+    for j in range(I_o):
+        idx = np.nonzero(active)[0]
+        if idx.size == 0:
+            break
+        xn, un = x_nom[idx].copy(), u_nom[idx].copy()
+        prev_cost = cost[idx].copy()
+        A, Bm = model.get_AB(xn, un)                                          # isls.py:424
+        zero_cx = np.zeros((1, N, n))
+        zero_cu = np.zeros((1, N, m))
+        K, _, non_pd, Quu, Quu_inv, Qux = backward_pass(A, Bm, zero_cx, zero_cu, Cxx, Cuu, logs=True)
+        status[idx[non_pd]] |= ST_NON_PD
+        zs_i = zs[idx][:, seq]                                                # [b,N,n]
+        zx, zu = z_x[idx].copy(), z_u[idx].copy()                             # warm start (isls.py:489-490)
+        lx, lu = np.zeros_like(zx), np.zeros_like(zu)                         # lambda reset (isls.py:414-415)
+        prim = np.full(idx.size, 1e6)
+        dual = np.full(idx.size, 1e6)
+        x_last, u_last = xn.copy(), un.copy()
+        a_active = np.ones(idx.size, dtype=bool)
+        for a in range(I_a):
+            ia = np.nonzero(a_active)[0]
+            if ia.size == 0:
+                break
+            g = idx[ia]
+            reg_x, reg_u = zx[ia] - lx[ia], zu[ia] - lu[ia]                   # admm.py:32-33
+            # ---- f_argmin (isls.py:456-478) in Riccati form
+            cx = 2.0 * Qd * (xn[ia] - zs_i[ia]) + 2.0 * rho_x * (xn[ia] - reg_x)
+            cu = 2.0 * R * un[ia] + 2.0 * rho_u * (un[ia] - reg_u)
+            k = ff_pass(A[ia], Bm[ia], cx, cu, K[ia], Quu[ia], Quu_inv[ia], Qux[ia])
+            k[:, -1] = -cu[:, -1] / Cuu_last                                  # batch-form last control
+            _, du = linear_rollout(A[ia], Bm[ia], K[ia], k)
+            u_cand = un[ia][:, None] + al[None, :, None, None] * du[:, None]  # isls.py:468
+            x_cand = rollout_open(model, xn[ia][:, 0], u_cand)                # isls.py:469
+            costs = quad_cost(p, zs[g], x_cand, u_cand)                       # isls.py:470
+            if proj_x:
+                dxr = x_cand - reg_x[:, None]
+                costs = costs + np.sum(dxr * dxr * rho_x, axis=(-1, -2))      # isls.py:471-473 (diagonal Qr)
+            if proj_u:
+                dur = u_cand - reg_u[:, None]
+                costs = costs + np.sum(dur * dur * rho_u, axis=(-1, -2))      # isls.py:474-476
+            # np.argmin returns the first NaN if any (isls.py:477) - keep numpy semantics
+            ind = np.argmin(costs, axis=1)
+            ar = np.arange(ia.size)
+            xx, xu = x_cand[ar, ind], u_cand[ar, ind]
+            alpha_idx[g, j, a] = ind
+            status[g[np.isnan(costs).any(axis=1)]] |= ST_NAN_COST
+            x_last[ia], u_last[ia] = xx, xu
+            # ---- ADMM update (admm.py:43-69)
+            pprim, pdual = prim[ia].copy(), dual[ia].copy()
+            pr = np.zeros(ia.size)
+            dr = np.zeros(ia.size)
+            if proj_x:
+                zprev = zx[ia]
+                pre = relax * xx + (1.0 - relax) * zprev + lx[ia]
+                znew = np.clip(pre, bx[0], bx[1])                             # projections.py:7-11
+                mask_x[g] = (pre > bx[1]).astype(np.int8) - (pre < bx[0]).astype(np.int8)
+                r = xx - znew
+                lx[ia] = lx[ia] + r
+                zx[ia] = znew
+                pr = pr + np.sqrt(np.sum(r * r, axis=(-1, -2)))
+                dz = znew - zprev
+                dr = dr + np.sqrt(np.sum(dz * dz, axis=(-1, -2)))
+            if proj_u:
+                zprev = zu[ia]
+                pre = relax * xu + (1.0 - relax) * zprev + lu[ia]
+                znew = np.clip(pre, bu[0], bu[1])
+                mask_u[g] = (pre > bu[1]).astype(np.int8) - (pre < bu[0]).astype(np.int8)
+                r = xu - znew
+                lu[ia] = lu[ia] + r
+                zu[ia] = znew
+                pr = pr + np.sqrt(np.sum(r * r, axis=(-1, -2)))
+                dz = znew - zprev
+                dr = dr + np.sqrt(np.sum(dz * dz, axis=(-1, -2)))
+            prim[ia], dual[ia] = pr, dr
+            res_log[g, j, a, 0], res_log[g, j, a, 1] = pr, dr
+            admm_iters[g, j] = a + 1
+            if keep_trace:
+                trace.append(dict(j=j, a=a, g=g.copy(), du=du.copy(), costs=costs.copy(), ind=ind.copy(),
+                                  reg_x=reg_x.copy(), reg_u=reg_u.copy(), x=xx.copy(), u=xu.copy(),
+                                  z_x=zx[ia].copy(), z_u=zu[ia].copy(), lam_x=lx[ia].copy(), lam_u=lu[ia].copy()))
+            if not fixed_budget:
+                conv = (pr < tol) & (dr < tol)                                # admm.py:72
+                pch = np.abs(pprim - pr) / (pprim + 1e-30)                    # admm.py:78-79
+                dch = np.abs(pdual - dr) / (pdual + 1e-30)
+                stall = (~conv) & (pch < tol) & (dch < tol)                   # admm.py:80
+                admm_exit[g[conv], j] = ADMM_CONVERGED
+                admm_exit[g[stall], j] = ADMM_STALLED
+                a_active[ia[conv | stall]] = False
+        admm_exit[idx[a_active], j] = ADMM_MAXIT
+        # ---- after ADMM (isls.py:488-499)
+        x_nom[idx], u_nom[idx] = x_last, u_last                              # nominal <- last primal iterate
+        newc = quad_cost(p, zs[idx], x_last[:, None], u_last[:, None])[:, 0]
+        cost[idx] = newc
+        cost_log[idx, n_log[idx]] = newc
+        n_log[idx] += 1
+        z_x[idx], z_u[idx] = zx, zu
+        lam_x[idx], lam_u[idx] = lx, lu
+        outer_iters[idx] = j + 1
+        if not fixed_budget:
+            for q, b in enumerate(idx):
+                if abs(newc[q] - prev_cost[q]) < outer_tol:                   # isls.py:493
+                    status[b] |= ST_CONVERGED_COST
+                    active[b] = False
+                    continue
+                nl = n_log[b]
+                last4 = cost_log[b, max(0, nl - 4):nl]
+                prev4 = cost_log[b, max(0, nl - 8):max(0, nl - 4)]
+                if prev4.size and abs(np.mean(last4) - np.mean(prev4)) < outer_tol:   # isls.py:497
+                    status[b] |= ST_OSCILLATING
+                    active[b] = False
+    status[active] |= ST_MAX_ITER
+    out = dict(x=x_nom, u=u_nom, cost=cost, cost_log=cost_log, n_log=n_log, status=status,
+               outer_iters=outer_iters, admm_iters=admm_iters, admm_exit=admm_exit, res_log=res_log,
+               alpha_idx=alpha_idx, z_x=z_x, z_u=z_u, lam_x=lam_x, lam_u=lam_u, mask_x=mask_x, mask_u=mask_u)
+    if keep_trace:
+        out["trace"] = trace
+    return out
+
+
+# ------------------------------------------------------------------------------------- LQT-ADMM with Riccati
+def lqt_admm_dp(p, fixed_budget=False):
+    """SLS.ADMM_LQT_DP (sls.py:298-317): linear dynamics, one Riccati pass (sls.py:85-166), then per ADMM
+    iteration the feed-forward recursion (sls.py:168-202) + closed-loop linear rollout
+    (sls_base.py:76-89) + projection / dual update (admm.py).  Budget p['I_a'] iterations, tolerance p['tol']."""
+    model = _model_of(p)
+    N, n, m = p["N"], p["n"], p["m"]
+    I_a, tol, relax = p["I_a"], p["tol"], p.get("alpha", 1.0)
+    x0 = np.asarray(p["x0"], dtype=np.float64)
+    B = x0.shape[0]
+    zs = _zs_b(p, B)
+    seq = p["seq"]
+    Qd = p["Qdiag"][seq]
+    R = p["u_std"]
+    bx, bu = _bounds(p, "x", N, n), _bounds(p, "u", N, m)
+    proj_x, proj_u = bx is not None, bu is not None
+    rho_x = np.broadcast_to(np.asarray(p["rho_x"], float), (N, n)) if proj_x else np.zeros((N, n))
+    rho_u = np.broadcast_to(np.asarray(p["rho_u"], float), (N, m)) if proj_u else np.zeros((N, m))
+    A1, B1 = model.A, model.B
+    A = np.broadcast_to(A1, (1, N, n, n))
+    Bm = np.broadcast_to(B1, (1, N, n, m))
+    Cxx = _diag_embed(2.0 * (Qd + rho_x))[None]
+    Cuu = _diag_embed(2.0 * (R + rho_u))[None]
+    K, _, non_pd, Quu, Quu_inv, Qux = backward_pass(A, Bm, np.zeros((1, N, n)), np.zeros((1, N, m)), Cxx, Cuu,
+                                                    logs=True)
+    Ab = np.broadcast_to(A, (B, N, n, n))
+    Bb = np.broadcast_to(Bm, (B, N, n, m))
+    Kb = np.broadcast_to(K, (B, N, m, n))
+    Quub, Quuib, Quxb = (np.broadcast_to(a, (B,) + a.shape[1:]) for a in (Quu, Quu_inv, Qux))
+    zs_i = zs[:, seq]
+    zx, zu = np.zeros((B, N, n)), np.zeros((B, N, m))
+    lx, lu = np.zeros((B, N, n)), np.zeros((B, N, m))
+    x_last, u_last = np.zeros((B, N, n)), np.zeros((B, N, m))
+    k_last = np.zeros((B, N, m))
+    prim, dual = np.full(B, 1e6), np.full(B, 1e6)
+    res_log = np.full((B, I_a, 2), np.nan)
+    iters = np.zeros(B, dtype=np.int32)
+    exit_code = np.zeros(B, dtype=np.int32)
+    mask_x = np.zeros((B, N, n), dtype=np.int8)
+    mask_u = np.zeros((B, N, m), dtype=np.int8)
+    a_active = np.ones(B, dtype=bool)
+    for a in range(I_a):
+        ia = np.nonzero(a_active)[0]
+        if ia.size == 0:
+            break
+        reg_x, reg_u = zx[ia] - lx[ia], zu[ia] - lu[ia]
+        cx = -2.0 * Qd * zs_i[ia] - 2.0 * rho_x * reg_x                        # sls.py:187-193
+        cu = -2.0 * rho_u * reg_u
+        k = ff_pass(Ab[ia], Bb[ia], cx, cu, Kb[ia], Quub[ia], Quuib[ia], Quxb[ia])
+        xs, us = linear_rollout(Ab[ia], Bb[ia], Kb[ia], k, dx0=x0[ia])         # sls_base.py:76-89
+        x_last[ia], u_last[ia], k_last[ia] = xs, us, k
+        pprim, pdual = prim[ia].copy(), dual[ia].copy()
+        pr, dr = np.zeros(ia.size), np.zeros(ia.size)
+        if proj_x:
+            zprev = zx[ia]
+            pre = relax * xs + (1.0 - relax) * zprev + lx[ia]
+            znew = np.clip(pre, bx[0], bx[1])
+            mask_x[ia] = (pre > bx[1]).astype(np.int8) - (pre < bx[0]).astype(np.int8)
+            r = xs - znew
+            lx[ia] = lx[ia] + r
+            zx[ia] = znew
+            pr = pr + np.sqrt(np.sum(r * r, axis=(-1, -2)))
+            dz = znew - zprev
+            dr = dr + np.sqrt(np.sum(dz * dz, axis=(-1, -2)))
+        if proj_u:
+            zprev = zu[ia]
+            pre = relax * us + (1.0 - relax) * zprev + lu[ia]
+            znew = np.clip(pre, bu[0], bu[1])
+            mask_u[ia] = (pre > bu[1]).astype(np.int8) - (pre < bu[0]).astype(np.int8)
+            r = us - znew
+            lu[ia] = lu[ia] + r
+            zu[ia] = znew
+            pr = pr + np.sqrt(np.sum(r * r, axis=(-1, -2)))
+            dz = znew - zprev
+            dr = dr + np.sqrt(np.sum(dz * dz, axis=(-1, -2)))
+        prim[ia], dual[ia] = pr, dr
+        res_log[ia, a, 0], res_log[ia, a, 1] = pr, dr
+        iters[ia] = a + 1
+        if not fixed_budget:
+            conv = (pr < tol) & (dr < tol)
+            pch = np.abs(pprim - pr) / (pprim + 1e-30)
+            dch = np.abs(pdual - dr) / (pdual + 1e-30)
+            stall = (~conv) & (pch < tol) & (dch < tol)
+            exit_code[ia[conv]] = ADMM_CONVERGED
+            exit_code[ia[stall]] = ADMM_STALLED
+            a_active[ia[conv | stall]] = False
+    exit_code[a_active] = ADMM_MAXIT
+    cost = quad_cost(p, zs, x_last[:, None], u_last[:, None])[:, 0]
+    return dict(x=x_last, u=u_last, K=np.broadcast_to(K, (B, N, m, n)).copy(), k=k_last, cost=cost, iters=iters,
+                exit_code=exit_code, res_log=res_log, z_x=zx, z_u=zu, lam_x=lx, lam_u=lu, mask_x=mask_x,
+                mask_u=mask_u, non_pd=np.broadcast_to(non_pd, (B,)).copy())
