@@ -1,0 +1,148 @@
+// Device-side dynamics models registered behind the reference's forward_model / get_AB plugin slots.
+//
+// Every model provides
+//   n, m          state / control dimension
+//   NJ            number of trajectory-dependent Jacobian scalars cached per time step
+//   am(i,j), bm(i,j)   compile-time sparsity class of A[i][j], B[i][j]: MZ (structural 0), MO (structural 1),
+//                      MV (value held in the dense array).  The small-matrix helpers skip MZ terms and turn MO
+//                      terms into plain adds, so one generic Riccati/ff/rollout code path is specialised per model
+//                      by full unrolling.
+//   step(x,u,xn,dt)    x_{t+1} = f(x_t,u_t)                 (reference: forward_model callable)
+//   jac(x,u,J,dt)      the NJ scalars at (x_t,u_t)          (reference: get_AB callable)
+//   expand(J,A,B,dt)   fill the MV entries of dense A, B
+//
+// Formulas (cited in oracle/models.py as well):
+//   car   notebooks/Car/Iterative LQR with control constraints.ipynb cell 6
+//   arm3  notebooks/3DoF robot/State and control bound constraints.ipynb cells 9-10, closed-form planar 3R
+//         FK / Jacobian for urdfs/3dof_robot.urdf:73-102 (unit links)
+//   double integrator   isls/utils.py:266-276, isls/sls_base.py:49-53
+#pragma once
+
+enum { MZ = 0, MO = 1, MV = 2 };
+
+#define ISLS_TWO_PI 6.283185307179586476925286766559
+
+// numpy's np.mod(a, 2*pi) for float64: r = fmod(a,b); if r != 0 and sign differs from b: r += b
+__device__ __forceinline__ double mod_two_pi(double a) {
+  if (a >= 0.0 && a < ISLS_TWO_PI) return a;      // common case: exact, no fmod
+  double r = fmod(a, ISLS_TWO_PI);
+  if (r < 0.0) r += ISLS_TWO_PI;
+  else if (r == 0.0) r = 0.0;                     // copysign(0, b) = +0
+  return r;
+}
+
+struct CarModel {
+  static constexpr int n = 4, m = 2, NJ = 6, NJA = 6;
+  __host__ __device__ static constexpr int am(int i, int j) {
+    return i == j ? MO : ((i <= 1 && j >= 2) || (i == 2 && j == 3)) ? MV : MZ;
+  }
+  __host__ __device__ static constexpr int bm(int i, int j) {
+    return ((i == 2 && j == 0) || (i == 3 && j == 1)) ? MV : MZ;
+  }
+  __device__ __forceinline__ static void step(const double (&x)[n], const double (&u)[m], double (&xn)[n],
+                                              double dt) {
+    double s, c;
+    sincos(x[2], &s, &c);
+    const double dv = dt * x[3];
+    xn[0] = x[0] + dv * c;
+    xn[1] = x[1] + dv * s;
+    xn[2] = mod_two_pi(x[2] + dv * u[0]);
+    xn[3] = x[3] + dt * u[1];
+  }
+  __device__ __forceinline__ static void jac(const double (&x)[n], const double (&u)[m], double (&J)[NJ],
+                                             double dt) {
+    double s, c;
+    sincos(x[2], &s, &c);
+    const double dv = dt * x[3];
+    J[0] = dv * -s;      // A[0][2]
+    J[1] = dv * c;       // A[1][2]
+    J[2] = dt * c;       // A[0][3]
+    J[3] = dt * s;       // A[1][3]
+    J[4] = dt * u[0];    // A[2][3]
+    J[5] = dv;           // B[2][0]
+  }
+  __device__ __forceinline__ static void expand(const double (&J)[NJ], double (&A)[n][n], double (&B)[n][m],
+                                                double dt) {
+    A[0][2] = J[0]; A[1][2] = J[1]; A[0][3] = J[2]; A[1][3] = J[3]; A[2][3] = J[4];
+    B[2][0] = J[5]; B[3][1] = dt;
+  }
+};
+
+struct Arm3Model {
+  static constexpr int n = 9, m = 3, NJ = 6, NJA = 6;
+  __host__ __device__ static constexpr int am(int i, int j) {
+    return i < 6 ? (i == j ? MO : (i < 3 && j == i + 3) ? MV : MZ)
+                 : (i < 8 && j < 6) ? MV : MZ;           // rows 6,7 = [J, J dt, 0]; row 8 (p_z) is zero
+  }
+  __host__ __device__ static constexpr int bm(int i, int j) {
+    return i < 3 ? (i == j ? MV : MZ) : i < 6 ? (j == i - 3 ? MV : MZ) : i < 8 ? MV : MZ;
+  }
+  __device__ __forceinline__ static void qnext(const double (&x)[n], const double (&u)[m], double (&q)[3],
+                                               double dt) {
+    const double h = dt * dt;
+#pragma unroll
+    for (int i = 0; i < 3; i++) q[i] = (x[i] + x[3 + i] * dt) + (0.5 * u[i]) * h;
+  }
+  __device__ __forceinline__ static void step(const double (&x)[n], const double (&u)[m], double (&xn)[n],
+                                              double dt) {
+    double q[3];
+    qnext(x, u, q, dt);
+    const double a1 = q[0], a2 = a1 + q[1], a3 = a2 + q[2];
+    double s1, c1, s2, c2, s3, c3;
+    sincos(a1, &s1, &c1); sincos(a2, &s2, &c2); sincos(a3, &s3, &c3);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { xn[i] = q[i]; xn[3 + i] = x[3 + i] + u[i] * dt; }
+    xn[6] = (c1 + c2) + c3;
+    xn[7] = (s1 + s2) + s3;
+    xn[8] = 0.0;
+  }
+  __device__ __forceinline__ static void jac(const double (&x)[n], const double (&u)[m], double (&J)[NJ],
+                                             double dt) {
+    double q[3];
+    qnext(x, u, q, dt);
+    const double a1 = q[0], a2 = a1 + q[1], a3 = a2 + q[2];
+    double s1, c1, s2, c2, s3, c3;
+    sincos(a1, &s1, &c1); sincos(a2, &s2, &c2); sincos(a3, &s3, &c3);
+    J[0] = -((s1 + s2) + s3); J[1] = -(s2 + s3); J[2] = -s3;
+    J[3] = (c1 + c2) + c3;    J[4] = c2 + c3;    J[5] = c3;
+  }
+  __device__ __forceinline__ static void expand(const double (&J)[NJ], double (&A)[n][n], double (&B)[n][m],
+                                                double dt) {
+    const double h = 0.5 * (dt * dt);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { A[i][i + 3] = dt; B[i][i] = h; B[3 + i][i] = dt; }
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        A[6 + r][c] = J[3 * r + c];
+        A[6 + r][3 + c] = J[3 * r + c] * dt;
+        B[6 + r][c] = h * J[3 * r + c];        // numpy: 0.5 * J * dt**2 -> (0.5*J)*(dt*dt); scaling by 0.5 is exact
+      }
+  }
+};
+
+template <int D>
+struct DoubleIntModel {
+  static constexpr int n = 2 * D, m = D, NJ = 0, NJA = 1;
+  __host__ __device__ static constexpr int am(int i, int j) { return i == j ? MO : (i < D && j == i + D) ? MV : MZ; }
+  __host__ __device__ static constexpr int bm(int i, int j) {
+    return (i < D && j == i) ? MV : (i >= D && j == i - D) ? MV : MZ;
+  }
+  __device__ __forceinline__ static void step(const double (&x)[n], const double (&u)[m], double (&xn)[n],
+                                              double dt) {
+    const double h = dt * dt / 2.0;               // utils.py:266-276: dt**2 / factorial(2)
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      xn[i] = (x[i] + dt * x[D + i]) + h * u[i];
+      xn[D + i] = x[D + i] + dt * u[i];
+    }
+  }
+  __device__ __forceinline__ static void jac(const double (&)[n], const double (&)[m], double (&)[1], double) {}
+  __device__ __forceinline__ static void expand(const double (&)[1], double (&A)[n][n], double (&B)[n][m],
+                                                double dt) {
+    const double h = dt * dt / 2.0;
+#pragma unroll
+    for (int i = 0; i < D; i++) { A[i][i + D] = dt; B[i][i] = h; B[D + i][i] = dt; }
+  }
+};

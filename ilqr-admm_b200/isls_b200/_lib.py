@@ -1,0 +1,80 @@
+"""ctypes binding of libisls_b200.so (the C-ABI declared in include/isls_b200.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libisls_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+
+
+class ProblemDesc(C.Structure):
+    _fields_ = [("model_id", C.c_int32), ("n", C.c_int32), ("m", C.c_int32), ("N", C.c_int32),
+                ("n_via", C.c_int32), ("L", C.c_int32), ("dt", C.c_double), ("u_std", C.c_double),
+                ("Qdiag", C.c_void_p), ("seq", C.c_void_p), ("alphas", C.c_void_p),
+                ("rho_x", C.c_void_p), ("lo_x", C.c_void_p), ("hi_x", C.c_void_p),
+                ("rho_u", C.c_void_p), ("lo_u", C.c_void_p), ("hi_u", C.c_void_p)]
+
+
+class SolveOpts(C.Structure):
+    _fields_ = [("max_outer", C.c_int32), ("max_admm", C.c_int32), ("tol", C.c_double), ("outer_tol", C.c_double),
+                ("relax", C.c_double), ("fixed_budget", C.c_int32), ("last_stage_dp", C.c_int32)]
+
+
+OUT_FIELDS = ["x", "u", "cost", "cost_log", "n_log", "status", "outer_iters", "admm_iters", "admm_exit", "res_log",
+              "alpha_idx", "z_x", "z_u", "lam_x", "lam_u", "K", "k", "mask_x", "mask_u"]
+
+
+class SolveOut(C.Structure):
+    _fields_ = [(f, C.c_void_p) for f in OUT_FIELDS]
+
+
+EXPORTS = ["isls_version", "isls_last_error_string", "isls_model_id", "isls_model_supported", "isls_plan_create",
+           "isls_plan_destroy", "isls_workspace_bytes", "isls_ilqr_admm_solve_f64", "isls_ilqr_solve_f64",
+           "isls_lqt_admm_dp_f64", "isls_riccati_f64", "isls_rollout_linesearch_f64", "isls_admm_project_dual_f64",
+           "isls_measure_fp64_tflops"]
+
+_lib = None
+
+
+class IslsError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libisls_b200.so (once).  Raises if it has not been built - there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IslsError("libisls_b200.so not found at %s - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.isls_last_error_string.restype = C.c_char_p
+    L.isls_model_id.argtypes = [C.c_char_p]
+    L.isls_model_supported.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    L.isls_plan_create.argtypes = [C.POINTER(ProblemDesc), C.POINTER(C.c_void_p)]
+    L.isls_plan_destroy.argtypes = [C.c_void_p]
+    L.isls_workspace_bytes.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_size_t)]
+    solve_args = [C.c_void_p, C.POINTER(SolveOpts), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_size_t, C.POINTER(SolveOut), C.c_void_p]
+    L.isls_ilqr_admm_solve_f64.argtypes = solve_args
+    L.isls_ilqr_solve_f64.argtypes = solve_args
+    L.isls_lqt_admm_dp_f64.argtypes = [C.c_void_p, C.POINTER(SolveOpts), C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_size_t, C.POINTER(SolveOut), C.c_void_p]
+    L.isls_riccati_f64.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 8
+    L.isls_rollout_linesearch_f64.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 11 + [C.c_size_t, C.c_void_p]
+    L.isls_admm_project_dual_f64.argtypes = [C.c_int64, C.c_int64, C.c_double] + [C.c_void_p] * 9
+    L.isls_measure_fp64_tflops.argtypes = [C.POINTER(C.c_double), C.c_void_p]
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().isls_last_error_string()
+        raise IslsError("%s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else "?"))

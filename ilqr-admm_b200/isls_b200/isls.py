@@ -1,0 +1,273 @@
+"""iSLS - batched, device-resident mirror of the reference's `isls.iSLS` hot path (isls/isls.py, isls/isls_base.py,
+isls/base.py).  Same constructor, properties and method names/keywords (HEAD and the legacy spellings used by the
+notebooks and README), plus an optional leading problem axis B on every array.  All arithmetic runs in
+libisls_b200.so; there is no CPU fallback.
+"""
+import numpy as np
+import torch
+
+from . import solver as S
+from ._lib import IslsError
+from .projections import Bound
+from .utils import diag_of
+
+_MODEL_NAMES = ("car", "arm3", "double_integrator")
+
+
+class iSLS:
+    def __init__(self, x_dim, u_dim, N, batch=None, device="cuda:0"):
+        """iSLS(x_dim, u_dim, N) (isls/isls.py:9,52); `batch` adds the problem axis (None = one problem)."""
+        self.x_dim, self.u_dim, self.N = int(x_dim), int(u_dim), int(N)
+        self.batch = batch
+        self.nb = 1 if batch is None else int(batch)
+        self.device = device
+        self.alphas = S.alphas(50)                       # isls_base.py:10-11
+        self._model = None
+        self._model_kw = {}
+        self.A = self.B = None
+        self.reset()
+        self.zs = self.Qs = self.seq = self.Rt = None
+        self._plan_cache = {}
+
+    # ------------------------------------------------------------------ plugin slots
+    @property
+    def forward_model(self):
+        return self._model
+
+    @forward_model.setter
+    def forward_model(self, spec):
+        """Name of a registered device model ("car", "arm3", "double_integrator"), optionally (name, {"dt": ..})
+        (slot: isls/isls_base.py:106-111)."""
+        if isinstance(spec, (tuple, list)):
+            name, kw = spec[0], dict(spec[1])
+        else:
+            name, kw = spec, {}
+        if callable(name) and hasattr(name, "isls_model"):
+            name, kw = name.isls_model, dict(getattr(name, "isls_model_kw", {}))
+        if not isinstance(name, str) or name not in _MODEL_NAMES:
+            raise TypeError("forward_model must name a registered device model %s; Python callables cannot run "
+                            "inside the kernels and there is no CPU fallback" % (_MODEL_NAMES,))
+        self._model, self._model_kw = name, kw
+        self._plan_cache.clear()
+
+    @property
+    def cost_function(self):
+        return "quadratic_viapoint"
+
+    @cost_function.setter
+    def cost_function(self, f):
+        if f not in (None, "quadratic_viapoint"):
+            raise TypeError("only the quadratic via-point cost (set_quadratic_cost) is available on the device")
+
+    def _check_get_AB(self, get_AB):
+        if get_AB is None:
+            return
+        name = getattr(get_AB, "isls_model", get_AB)
+        if name != self._model:
+            raise TypeError("get_AB must be None or the name of the device model set as forward_model (%r); "
+                            "Jacobians are evaluated by the device model" % (self._model,))
+
+    # ------------------------------------------------------------------ cost
+    def set_quadratic_cost(self, zs, Qs, seq, u_std):
+        """isls/base.py:81-89.  zs [k,n] or [B,k,n]; Qs [k,n,n] (diagonal) or [k,n] diagonals."""
+        zs = np.asarray(zs, dtype=np.float64)
+        Qs = np.asarray(Qs, dtype=np.float64)
+        self.zs = zs
+        self.Qs = Qs
+        self.Qdiag = diag_of(Qs, "Qs") if Qs.ndim == 3 else Qs
+        self.seq = np.asarray(seq, dtype=np.int32)
+        self.u_std = float(u_std)
+        self.Rt = np.eye(self.u_dim) * u_std
+        self._plan_cache.clear()
+
+    set_cost_variables = set_quadratic_cost          # legacy name (README.md:24-39)
+
+    def compute_Rr_Qr(self, rho_x, rho_u, dp=True):
+        """isls/base.py:55-79, returned as per-step DIAGONALS Qr[N,n], Rr[N,m] (None stays None)."""
+        def ex(rho, dim):
+            if rho is None:
+                return None
+            r = np.asarray(rho, dtype=np.float64)
+            if r.ndim == 0:
+                return np.full((self.N, dim), float(r))
+            if r.ndim >= 2 and r.shape[-1] == r.shape[-2] == dim and not (r.ndim == 2 and r.shape[0] == self.N
+                                                                           and self.N != dim):
+                r = diag_of(r, "rho")
+            return np.ascontiguousarray(np.broadcast_to(r, (self.N, dim)))
+        return ex(rho_x, self.x_dim), ex(rho_u, self.u_dim)
+
+    # ------------------------------------------------------------------ nominal trajectory
+    @property
+    def nominal_values(self):
+        return self.x_nom, self.u_nom
+
+    @nominal_values.setter
+    def nominal_values(self, value):
+        """(x_nom, u_nom) (isls/isls_base.py:80-85).  Only x_nom[..., 0, :] and u_nom are used: the solvers re-roll
+        the model out from the initial state, exactly what the reference's rollouts do."""
+        x_nom, u_nom = value
+        x_nom = torch.as_tensor(np.asarray(x_nom) if not isinstance(x_nom, torch.Tensor) else x_nom)
+        u_nom = torch.as_tensor(np.asarray(u_nom) if not isinstance(u_nom, torch.Tensor) else u_nom)
+        self.set_initial(x_nom[..., 0, :], u_nom)
+
+    def set_initial(self, x0, u_init):
+        """x0 [n] / [B,n], u_init [N,m] / [B,N,m] (host or device)."""
+        x0 = torch.as_tensor(np.asarray(x0, dtype=np.float64)) if not isinstance(x0, torch.Tensor) else x0
+        u_init = (torch.as_tensor(np.asarray(u_init, dtype=np.float64)) if not isinstance(u_init, torch.Tensor)
+                  else u_init)
+        self._x0 = x0.reshape(-1, self.x_dim).expand(self.nb, self.x_dim)
+        self._u_init = u_init.expand(self.nb, self.N, self.u_dim)
+
+    def reset(self):
+        """isls/isls_base.py:160-175."""
+        self.x_nom = self.u_nom = None
+        self.cost = None
+        self.cost_log = None
+        self._K = self._k = None
+        self.status = None
+        self.last = None
+
+    @property
+    def K(self):
+        return self._K
+
+    @property
+    def k(self):
+        return self._k
+
+    # ------------------------------------------------------------------ plumbing
+    def _dt(self):
+        return float(self._model_kw.get("dt", 0.01))
+
+    def _zs_b(self):
+        zs = torch.as_tensor(self.zs)
+        return zs.expand(self.nb, zs.shape[-2], self.x_dim)
+
+    def _solver(self, L, rho_x, bx, rho_u, bu, max_outer, max_admm, want_gains=False, want_masks=False):
+        if self._model is None or self.zs is None:
+            raise IslsError("set forward_model and set_quadratic_cost first")
+        key = (L, None if rho_x is None else rho_x.tobytes(), None if bx is None else (bx[0].tobytes(), bx[1].tobytes()),
+               None if rho_u is None else rho_u.tobytes(), None if bu is None else (bu[0].tobytes(), bu[1].tobytes()),
+               max_outer, max_admm, want_gains, want_masks)
+        if key not in self._plan_cache:
+            plan = S.Plan(self._model, self.N, self.x_dim, self.u_dim, self._dt(), self.Qdiag, self.seq, self.u_std,
+                          L, rho_x=rho_x, lo_x=None if bx is None else bx[0], hi_x=None if bx is None else bx[1],
+                          rho_u=rho_u, lo_u=None if bu is None else bu[0], hi_u=None if bu is None else bu[1])
+            self._plan_cache.clear()
+            self._plan_cache[key] = S.BatchSolver(plan, self.nb, self.device, max_outer=max_outer, max_admm=max_admm,
+                                                  want_gains=want_gains, want_masks=want_masks)
+        return self._plan_cache[key]
+
+    def _publish(self, out):
+        sq = (lambda t: t[0]) if self.batch is None else (lambda t: t)
+        self.x_nom, self.u_nom = sq(out.x), sq(out.u)
+        self.cost = sq(out.cost)
+        self.cost_log = sq(out.cost_log)
+        self.status = sq(out.status)
+        if "K" in out:
+            self._K, self._k = sq(out.K), sq(out.k)
+        self.last = out
+
+    # ------------------------------------------------------------------ solvers
+    def solve(self, get_AB=None, get_Cs=None, is_dynamics_linear=False, is_cost_quadratic=False, method="dp",
+              max_iter=100, max_line_search_iter=25, tol_fun=1e-5, tol_grad=1e-4, verbose=False, fixed_budget=False):
+        """iLQR with the Riccati backward pass and closed-loop line search (isls/isls.py:54-132, method='dp')."""
+        if method != "dp":
+            raise NotImplementedError("device path implements method='dp' (the dense batch form is the same minimiser)")
+        self._check_get_AB(get_AB)
+        sv = self._solver(max_line_search_iter, None, None, None, None, max_iter, 1, want_gains=True)
+        sv.set_inputs(self._x0, self._u_init, self._zs_b())
+        out = sv.ilqr(tol_fun=tol_fun, fixed_budget=fixed_budget)
+        self._publish(out)
+        if verbose:
+            self._report(out)
+        return out
+
+    def solve_ilqr(self, get_AB=None, max_ilqr_iter=100, max_line_search_iter=25, dp=True, verbose=False, **kw):
+        """Legacy spelling used by the notebooks (Car/Iterative LQR with state constraints.ipynb cell 13)."""
+        return self.solve(get_AB, method="dp", max_iter=max_ilqr_iter, max_line_search_iter=max_line_search_iter,
+                          verbose=verbose, **kw)
+
+    def ilqr_admm(self, get_AB=None, get_Cs=None, project_x=False, project_u=False, max_iter=20,
+                  max_line_search_iter=20, max_admm_iter=20, rho_x=None, rho_u=None, alpha=1, tol=1e-3, verbose=False,
+                  log=False, k_max=None, max_line_search=None, threshold=None, fixed_budget=False, want_masks=False):
+        """iLQR-ADMM with box state / control bounds (isls/isls.py:379-501 + isls/admm.py:6-106).
+        project_x / project_u: `Bound` descriptors (isls_b200.projections).  Legacy keywords k_max,
+        max_line_search, threshold map to max_iter, max_line_search_iter, tol."""
+        if k_max is not None:
+            max_iter = k_max
+        if max_line_search is not None:
+            max_line_search_iter = max_line_search
+        if threshold is not None:
+            tol = threshold
+        self._check_get_AB(get_AB)
+        if get_Cs is not None:
+            raise NotImplementedError("only the quadratic via-point cost is available on the device")
+        for nm, pr in (("project_x", project_x), ("project_u", project_u)):
+            if pr and not isinstance(pr, Bound):
+                raise TypeError("%s must be an isls_b200.projections.Bound (box bounds); Python callables cannot run "
+                                "inside the kernels" % nm)
+        Qr, Rr = self.compute_Rr_Qr(rho_x if project_x else None, rho_u if project_u else None)
+        if project_x and Qr is None or project_u and Rr is None:
+            raise ValueError("rho_x / rho_u is required for a projected variable")
+        bx = project_x.expand(self.N, self.x_dim) if project_x else None
+        bu = project_u.expand(self.N, self.u_dim) if project_u else None
+        sv = self._solver(max_line_search_iter, Qr, bx, Rr, bu, max_iter, max_admm_iter, want_masks=want_masks)
+        sv.set_inputs(self._x0, self._u_init, self._zs_b())
+        out = sv.ilqr_admm(tol=tol, relax=float(alpha), fixed_budget=fixed_budget)
+        self._publish(out)
+        if verbose:
+            self._report(out)
+        return out.res_log if log else out
+
+    def _report(self, out):
+        st = out.status.cpu().numpy()
+        it = out.outer_iters.cpu().numpy()
+        for b in range(min(self.nb, 8)):
+            msg = []
+            if st[b] & S.ST_CONVERGED_COST:
+                msg.append("Cost change is too low, cannot improve anymore at iteration %d." % it[b])
+            if st[b] & S.ST_OSCILLATING:
+                msg.append("Cost is oscillating at iteration %d" % it[b])
+            if st[b] & S.ST_LINESEARCH_FAIL:
+                msg.append("Forward pass failed, cannot improve anymore at iteration %d." % it[b])
+            if st[b] & S.ST_MAX_ITER:
+                msg.append("Maximum iterations reached.")
+            print("problem", b, "iLQR cost:", float(out.cost[b]), " ".join(msg))
+
+    # ------------------------------------------------------------------ stage-level API
+    def backward_pass_DP(self, Cts, cts):
+        """K, k = backward_pass_DP(Cts, cts) with self.A, self.nb set (isls/isls.py:229-308)."""
+        dev = self.device
+        t = lambda a: torch.as_tensor(a, dtype=torch.float64).to(dev)
+        A, Bm, C, c = t(self.A), t(self.B), t(Cts), t(cts)
+        single = A.ndim == 3
+        if single:
+            A, Bm, C, c = A[None], Bm[None], C[None], c[None]
+        K, k, bad = S.riccati(A, Bm, c, C)
+        if bool(bad.any()):
+            raise np.linalg.LinAlgError("Quu is not positive definite")       # what dposv raises, isls.py:296
+        return (K[0], k[0]) if single else (K, k)
+
+    @property
+    def AB(self):
+        return [self.A, self.B]
+
+    @AB.setter
+    def AB(self, value):
+        self.A, self.B = value[0], value[1]
+
+    def rollout_batch(self, x_nom, u_nom):
+        """Open-loop rollout from x_nom[0] for every control sequence in u_nom [nb,N,m] (isls/isls.py:135-154)."""
+        x_nom = torch.as_tensor(np.asarray(x_nom)) if not isinstance(x_nom, torch.Tensor) else x_nom
+        u_nom = torch.as_tensor(np.asarray(u_nom)) if not isinstance(u_nom, torch.Tensor) else u_nom
+        nb = u_nom.shape[0]
+        plan = S.Plan(self._model, self.N, self.x_dim, self.u_dim, self._dt(),
+                      np.zeros((1, self.x_dim)) if self.zs is None else self.Qdiag,
+                      np.zeros(self.N, dtype=np.int32) if self.zs is None else self.seq,
+                      0.0 if self.zs is None else self.u_std, 1)
+        sv = S.BatchSolver(plan, nb, self.device, logs=False)
+        zs = torch.zeros(nb, plan.n_via, self.x_dim, dtype=torch.float64)
+        xn = x_nom.reshape(-1, self.N, self.x_dim)[:1].expand(nb, self.N, self.x_dim)
+        _, _, xb, ub = sv.linesearch(xn, u_nom, torch.zeros_like(u_nom), zs)
+        return xb, ub

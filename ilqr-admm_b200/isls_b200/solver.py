@@ -1,0 +1,253 @@
+"""Thin host layer over the C-ABI: plans, workspaces and batched solves on torch CUDA tensors.
+
+torch is used only as the buffer carrier (allocation, streams, host<->device copies); all arithmetic of the hot
+path runs in libisls_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+MODEL_DIMS = {"car": (4, 2), "arm3": (9, 3)}
+
+ST_CONVERGED_COST, ST_LINESEARCH_FAIL, ST_MAX_ITER, ST_OSCILLATING, ST_NON_PD, ST_NAN_COST = 1, 2, 4, 8, 16, 32
+ADMM_CONVERGED, ADMM_STALLED, ADMM_MAXIT = 1, 2, 3
+
+
+def alphas(L):
+    """Line-search step sizes of the reference (isls/isls_base.py:10-11)."""
+    return (10.0 ** np.linspace(0.0, -5.0, 50))[:L].copy()
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if shape is not None:
+        a = np.ascontiguousarray(np.broadcast_to(a, shape))
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _dptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Plan:
+    """Problem description shared by a batch (isls_problem_desc): model, horizon, quadratic via-point cost,
+    diagonal ADMM penalties and box bounds."""
+
+    def __init__(self, model, N, n, m, dt, Qdiag, seq, u_std, L, rho_x=None, lo_x=None, hi_x=None, rho_u=None,
+                 lo_u=None, hi_u=None):
+        L_ = _lib.lib()
+        mid = L_.isls_model_id(model.encode())
+        _lib.check(0 if mid >= 0 else mid, "isls_model_id(%r)" % model)
+        _lib.check(L_.isls_model_supported(mid, n, m), "isls_model_supported(%s, n=%d, m=%d)" % (model, n, m))
+        self.model, self.N, self.n, self.m, self.dt, self.L = model, int(N), int(n), int(m), float(dt), int(L)
+        Qdiag = _f64(Qdiag)
+        self.n_via = Qdiag.shape[0]
+        keep = dict(Qdiag=Qdiag.reshape(self.n_via, n), seq=np.ascontiguousarray(seq, dtype=np.int32),
+                    alphas=alphas(L))
+        self.proj_x = rho_x is not None
+        self.proj_u = rho_u is not None
+        if self.proj_x:
+            keep.update(rho_x=_f64(rho_x, (N, n)), lo_x=_f64(-np.inf if lo_x is None else lo_x, (N, n)),
+                        hi_x=_f64(np.inf if hi_x is None else hi_x, (N, n)))
+        if self.proj_u:
+            keep.update(rho_u=_f64(rho_u, (N, m)), lo_u=_f64(-np.inf if lo_u is None else lo_u, (N, m)),
+                        hi_u=_f64(np.inf if hi_u is None else hi_u, (N, m)))
+        assert keep["seq"].shape == (N,)
+        d = _lib.ProblemDesc(model_id=mid, n=n, m=m, N=N, n_via=self.n_via, L=L, dt=dt, u_std=float(u_std))
+        for k in ("Qdiag", "seq", "alphas", "rho_x", "lo_x", "hi_x", "rho_u", "lo_u", "hi_u"):
+            setattr(d, k, _ptr(keep.get(k)))
+        self._keep = keep
+        h = C.c_void_p()
+        _lib.check(L_.isls_plan_create(C.byref(d), C.byref(h)), "isls_plan_create")
+        self.handle = h
+
+    def workspace_bytes(self, B):
+        sz = C.c_size_t()
+        _lib.check(_lib.lib().isls_workspace_bytes(self.handle, int(B), C.byref(sz)), "isls_workspace_bytes")
+        return sz.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.lib().isls_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Result(dict):
+    __getattr__ = dict.__getitem__
+
+
+class BatchSolver:
+    """Owns the workspace and the result buffers for a fixed (plan, B); solves are enqueued on the current
+    torch stream.  Inputs may be host (numpy / pinned torch) or device tensors."""
+
+    def __init__(self, plan, B, device="cuda:0", max_outer=20, max_admm=20, logs=True, want_gains=False,
+                 want_masks=False):
+        if not torch.cuda.is_available():
+            raise _lib.IslsError("isls_b200 needs a CUDA device (there is no CPU path)")
+        self.plan, self.B, self.device = plan, int(B), torch.device(device)
+        self.max_outer, self.max_admm = int(max_outer), int(max_admm)
+        p, dev = plan, self.device
+        with torch.cuda.device(dev):
+            self.ws = torch.empty(plan.workspace_bytes(B) + 256, dtype=torch.uint8, device=dev)
+        off = (-self.ws.data_ptr()) % 256
+        self._ws_ptr, self._ws_bytes = self.ws.data_ptr() + off, self.ws.numel() - off
+        f64 = dict(dtype=torch.float64, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        B_, N, n, m = self.B, p.N, p.n, p.m
+        o = Result(x=torch.empty(B_, N, n, **f64), u=torch.empty(B_, N, m, **f64), cost=torch.empty(B_, **f64),
+                   cost_log=torch.empty(B_, self.max_outer + 1, **f64), n_log=torch.empty(B_, **i32),
+                   status=torch.empty(B_, **i32), outer_iters=torch.empty(B_, **i32))
+        if logs:
+            o.update(admm_iters=torch.empty(B_, self.max_outer, **i32),
+                     admm_exit=torch.empty(B_, self.max_outer, **i32),
+                     res_log=torch.empty(B_, self.max_outer, max(self.max_admm, 1), 2, **f64),
+                     alpha_idx=torch.empty(B_, self.max_outer, max(self.max_admm, 1), **i32),
+                     z_x=torch.empty(B_, N, n, **f64), z_u=torch.empty(B_, N, m, **f64),
+                     lam_x=torch.empty(B_, N, n, **f64), lam_u=torch.empty(B_, N, m, **f64))
+        if want_gains:
+            o.update(K=torch.empty(B_, N, m, n, **f64), k=torch.empty(B_, N, m, **f64))
+        if want_masks:
+            o.update(mask_x=torch.zeros(B_, N, n, dtype=torch.int8, device=dev),
+                     mask_u=torch.zeros(B_, N, m, dtype=torch.int8, device=dev))
+        self.out = o
+        self._cout = _lib.SolveOut()
+        for f in _lib.OUT_FIELDS:
+            setattr(self._cout, f, _dptr(o.get(f)))
+        # device staging buffers for the inputs
+        self.x0 = torch.empty(B_, n, **f64)
+        self.u_init = torch.empty(B_, N, m, **f64)
+        self.zs = torch.empty(B_, p.n_via, n, **f64)
+
+    # ---- input staging (host -> device copies happen here when host arrays are given)
+    def _stage(self, dst, src, name):
+        if isinstance(src, torch.Tensor):
+            t = src
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(src, dtype=np.float64)))
+        if t.dtype != torch.float64:
+            t = t.to(torch.float64)
+        if t.shape != dst.shape:
+            t = t.expand(dst.shape)
+        dst.copy_(t, non_blocking=True)
+
+    def set_inputs(self, x0, u_init, zs):
+        self._stage(self.x0, x0, "x0")
+        self._stage(self.u_init, u_init, "u_init")
+        self._stage(self.zs, zs, "zs")
+
+    def _opts(self, tol, outer_tol, relax, fixed_budget, last_stage_dp, max_outer=None, max_admm=None):
+        return _lib.SolveOpts(max_outer=self.max_outer if max_outer is None else max_outer,
+                              max_admm=self.max_admm if max_admm is None else max_admm, tol=tol,
+                              outer_tol=outer_tol, relax=relax, fixed_budget=int(fixed_budget),
+                              last_stage_dp=int(last_stage_dp))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def ilqr_admm(self, tol=1e-3, outer_tol=1e-3, relax=1.0, fixed_budget=False, last_stage_dp=False):
+        o = self._opts(tol, outer_tol, relax, fixed_budget, last_stage_dp)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().isls_ilqr_admm_solve_f64(self.plan.handle, C.byref(o), self.B, _dptr(self.x0),
+                                                     _dptr(self.u_init), _dptr(self.zs), C.c_void_p(self._ws_ptr),
+                                                     self._ws_bytes, C.byref(self._cout), self._stream())
+        _lib.check(rc, "isls_ilqr_admm_solve_f64")
+        return self.out
+
+    def ilqr(self, tol_fun=1e-5, fixed_budget=False):
+        o = self._opts(tol_fun, 0.0, 1.0, fixed_budget, True)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().isls_ilqr_solve_f64(self.plan.handle, C.byref(o), self.B, _dptr(self.x0),
+                                                _dptr(self.u_init), _dptr(self.zs), C.c_void_p(self._ws_ptr),
+                                                self._ws_bytes, C.byref(self._cout), self._stream())
+        _lib.check(rc, "isls_ilqr_solve_f64")
+        return self.out
+
+    def lqt_admm_dp(self, tol=1e-3, relax=1.0, fixed_budget=False):
+        o = self._opts(tol, 0.0, relax, fixed_budget, True, max_outer=1)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().isls_lqt_admm_dp_f64(self.plan.handle, C.byref(o), self.B, _dptr(self.x0),
+                                                 _dptr(self.zs), C.c_void_p(self._ws_ptr), self._ws_bytes,
+                                                 C.byref(self._cout), self._stream())
+        _lib.check(rc, "isls_lqt_admm_dp_f64")
+        return self.out
+
+    def linesearch(self, x_nom, u_nom, du, zs, reg_x=None, reg_u=None):
+        """Stage-level: open-loop line search + argmin (isls_rollout_linesearch_f64)."""
+        p, dev = self.plan, self.device
+        f64 = dict(dtype=torch.float64, device=dev)
+
+        def dv(a, shape):
+            if a is None:
+                return None
+            t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+            return t.to(dev).expand(shape).contiguous()
+        B_, N, n, m = self.B, p.N, p.n, p.m
+        x_nom, u_nom, du = dv(x_nom, (B_, N, n)), dv(u_nom, (B_, N, m)), dv(du, (B_, N, m))
+        zs, reg_x, reg_u = dv(zs, (B_, p.n_via, n)), dv(reg_x, (B_, N, n)), dv(reg_u, (B_, N, m))
+        costs = torch.empty(B_, p.L, **f64)
+        best = torch.empty(B_, dtype=torch.int32, device=dev)
+        xb, ub = torch.empty(B_, N, n, **f64), torch.empty(B_, N, m, **f64)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().isls_rollout_linesearch_f64(p.handle, B_, _dptr(x_nom), _dptr(u_nom), _dptr(du),
+                                                        _dptr(zs), _dptr(reg_x), _dptr(reg_u), _dptr(costs),
+                                                        _dptr(best), _dptr(xb), _dptr(ub), C.c_void_p(self._ws_ptr),
+                                                        self._ws_bytes, self._stream())
+        _lib.check(rc, "isls_rollout_linesearch_f64")
+        return costs, best, xb, ub
+
+
+def riccati(A, Bm, c, Cm):
+    """Stage-level generic-operator Riccati pass (isls_riccati_f64; iSLS.backward_pass_DP, isls/isls.py:229-308).
+    A[B,N,n,n], Bm[B,N,n,m], c[B,N,n+m], Cm[B,N,n+m,n+m] (CUDA float64) -> K[B,N,m,n], k[B,N,m], non_pd[B]."""
+    B_, N, n, m = Bm.shape
+    dev = A.device
+    A, Bm, c, Cm = (t.contiguous() for t in (A, Bm, c, Cm))
+    K = torch.empty(B_, N, m, n, dtype=torch.float64, device=dev)
+    k = torch.empty(B_, N, m, dtype=torch.float64, device=dev)
+    bad = torch.empty(B_, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().isls_riccati_f64(n, m, N, B_, _dptr(A), _dptr(Bm), _dptr(c), _dptr(Cm), _dptr(K), _dptr(k),
+                                         _dptr(bad), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "isls_riccati_f64")
+    return K, k, bad
+
+
+def admm_project_dual(x, z, lam, lo, hi, relax=1.0, want_mask=False):
+    """Stage-level ADMM z-projection + scaled dual update on flat [B,len] CUDA tensors, in place on z, lam
+    (isls_admm_project_dual_f64; isls/admm.py:43-69 with project_bound).  Returns (prim_sq[B], dual_sq[B], mask)."""
+    B_, ln = x.shape
+    dev = x.device
+    prim = torch.zeros(B_, dtype=torch.float64, device=dev)
+    dual = torch.zeros(B_, dtype=torch.float64, device=dev)
+    mask = torch.empty(B_, ln, dtype=torch.int8, device=dev) if want_mask else None
+    lo = lo.to(dev).expand(ln).contiguous()
+    hi = hi.to(dev).expand(ln).contiguous()
+    assert x.is_contiguous() and z.is_contiguous() and lam.is_contiguous()
+    with torch.cuda.device(dev):
+        rc = _lib.lib().isls_admm_project_dual_f64(B_, ln, float(relax), _dptr(x), _dptr(z), _dptr(lam), _dptr(lo),
+                                                   _dptr(hi), _dptr(prim), _dptr(dual), _dptr(mask),
+                                                   C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "isls_admm_project_dual_f64")
+    return prim, dual, mask
+
+
+def measure_fp64_tflops(device="cuda:0"):
+    v = C.c_double()
+    with torch.cuda.device(device):
+        rc = _lib.lib().isls_measure_fp64_tflops(C.byref(v),
+                                                 C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+    _lib.check(rc, "isls_measure_fp64_tflops")
+    return v.value

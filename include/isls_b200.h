@@ -1,0 +1,179 @@
+/* isls_b200.h - C-ABI of the B200-native batched iLQR-ADMM hot path (libisls_b200.so).
+ *
+ * The reference (chenjianxing1/iLQR-ADMM, package `isls`) is pure Python: its "FFI" for this path is the Python
+ * class surface.  Each entry point below names the reference interface it replaces (file:line in the
+ * reference tree).  The host-side mirror of that surface (ilqr-admm_b200/isls_b200: iSLS, SLS, ADMM) binds these
+ * functions with ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types.  All numeric arrays are IEEE FP64 (`double`) or `int32_t`.
+ *   - "dev" pointers are DEVICE pointers owned by the caller; "host" pointers are small host arrays that are
+ *     copied when a plan is created.  Natural (reference) layouts: row-major [B, N, dim] etc.
+ *   - the library never allocates device memory on the solve path: the caller provides a workspace of
+ *     isls_workspace_bytes() bytes (256-byte aligned).  Plans own a small constant block (created / destroyed
+ *     explicitly).
+ *   - every solve call only ENQUEUES work on `stream` (a cudaStream_t passed as void*) and returns.
+ *   - return value: 0 ok; <0 invalid argument / unsupported (see ISLS_E_*); >0 a cudaError_t.
+ *     isls_last_error_string() describes the last failure on the calling thread.
+ *   - per-problem conditions are reported in `status[B]` bit-fields (ISLS_ST_*), never as return codes.
+ */
+#ifndef ISLS_B200_H
+#define ISLS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISLS_VERSION 100
+
+/* return codes */
+#define ISLS_OK 0
+#define ISLS_E_INVALID (-1)      /* bad argument (NULL pointer, non-positive size, ...) */
+#define ISLS_E_UNSUPPORTED (-2)  /* unknown model / unsupported (n, m) */
+#define ISLS_E_WORKSPACE (-3)    /* workspace too small or misaligned */
+
+/* device-side dynamics models, registered by name behind the reference's forward_model / get_AB plugin slots
+ * (isls/isls_base.py:106-111 forward_model; get_AB argument of isls/isls.py:54, isls/isls.py:379) */
+#define ISLS_MODEL_DOUBLE_INTEGRATOR 0   /* isls/utils.py:266-276 + isls/sls_base.py:49-53; n=2d, m=d, d in {1,2,3} */
+#define ISLS_MODEL_CAR 1                 /* notebooks/Car/Iterative LQR with control constraints.ipynb cell 6; n=4,m=2 */
+#define ISLS_MODEL_ARM3 2                /* notebooks/3DoF robot/State and control bound constraints.ipynb cells 9-10; n=9,m=3 */
+
+/* per-problem status bits */
+#define ISLS_ST_CONVERGED_COST 1   /* |cost-prev| < tol            isls/isls.py:125, isls/isls.py:493 */
+#define ISLS_ST_LINESEARCH_FAIL 2  /* forward pass failed           isls/isls.py:128 */
+#define ISLS_ST_MAX_ITER 4         /* iteration budget exhausted    isls/isls.py:131 */
+#define ISLS_ST_OSCILLATING 8      /* mean-of-4 oscillation test    isls/isls.py:497 */
+#define ISLS_ST_NON_PD 16          /* Quu not positive definite (the reference raises LinAlgError, isls/isls.py:296) */
+#define ISLS_ST_NAN_COST 32        /* NaN cost in the line search   isls/isls.py:362 */
+
+/* ADMM exit codes (admm_exit[B, max_outer]) */
+#define ISLS_ADMM_CONVERGED 1      /* isls/admm.py:72 */
+#define ISLS_ADMM_STALLED 2        /* isls/admm.py:80 */
+#define ISLS_ADMM_MAXIT 3          /* isls/admm.py:93 */
+
+/* Problem description shared by all problems of a batch: dynamics model, horizon, quadratic via-point cost
+ * (isls/base.py:81-89 set_quadratic_cost), diagonal ADMM penalties (isls/base.py:55-79 compute_Rr_Qr, diagonal
+ * rho only - see SURVEY D10) and box bounds (isls/projections.py:7-11 project_bound).  All pointers are HOST
+ * pointers, copied by isls_plan_create. */
+typedef struct isls_problem_desc {
+  int32_t model_id;      /* ISLS_MODEL_* */
+  int32_t n, m, N;       /* x_dim, u_dim, horizon (N states x_0..x_{N-1}, N controls) */
+  int32_t n_via;         /* number of via-points k (rows of zs / Qdiag) */
+  int32_t L;             /* number of line-search candidates (<= 50, isls/isls_base.py:10-11) */
+  double dt;             /* model time step */
+  double u_std;          /* R = u_std * I (isls/base.py:86) */
+  const double *Qdiag;   /* [n_via, n] diagonals of Qs */
+  const int32_t *seq;    /* [N] via-point index per time step */
+  const double *alphas;  /* [L] step sizes, 10**linspace(0,-5,50)[:L] */
+  const double *rho_x;   /* [N, n] diagonal of Qr per step, or NULL: no state projection */
+  const double *lo_x, *hi_x; /* [N, n] box bounds on the state (+-inf = free), required iff rho_x != NULL */
+  const double *rho_u;   /* [N, m] or NULL: no control projection */
+  const double *lo_u, *hi_u; /* [N, m] */
+} isls_problem_desc;
+
+typedef struct isls_plan isls_plan;   /* opaque */
+
+/* iteration budgets and tolerances: keyword arguments of iSLS.ilqr_admm (isls/isls.py:379-381) and
+ * iSLS.solve (isls/isls.py:54-55) */
+typedef struct isls_solve_opts {
+  int32_t max_outer;       /* max_iter */
+  int32_t max_admm;        /* max_admm_iter (ignored by isls_ilqr_solve_f64) */
+  double tol;              /* ADMM residual tolerance `tol` (admm.py:72-85) / tol_fun for plain iLQR */
+  double outer_tol;        /* hard-coded 1e-3 in isls/isls.py:493,497 */
+  double relax;            /* ADMM relaxation alpha (admm.py:46) */
+  int32_t fixed_budget;    /* 1: ignore every stop test (deterministic work, used by the benchmark) */
+  int32_t last_stage_dp;   /* 0: batch-form last control du_{N-1} = -Cuu^-1 cu (isls/isls.py:441-465);
+                              1: DP form K[N-1]=k[N-1]=0 (isls/isls.py:245-246) */
+} isls_solve_opts;
+
+/* Results, natural layouts, DEVICE pointers.  Optional outputs may be NULL. */
+typedef struct isls_solve_out {
+  double *x;            /* [B, N, n] final nominal states            (iSLS.x_nom) */
+  double *u;            /* [B, N, m] final nominal controls          (iSLS.u_nom) */
+  double *cost;         /* [B] final cost                            (iSLS.cost) */
+  double *cost_log;     /* [B, max_outer+1], NaN padded              (iSLS.cost_log) */
+  int32_t *n_log;       /* [B] valid entries of cost_log */
+  int32_t *status;      /* [B] ISLS_ST_* */
+  int32_t *outer_iters; /* [B] */
+  int32_t *admm_iters;  /* [B, max_outer] optional */
+  int32_t *admm_exit;   /* [B, max_outer] optional */
+  double *res_log;      /* [B, max_outer, max_admm, 2] optional: (primal, dual) residual norms (ADMM `logs`) */
+  int32_t *alpha_idx;   /* [B, max_outer, max_admm] optional: chosen line-search index (-1: rejected) */
+  double *z_x, *z_u;    /* [B, N, n], [B, N, m] optional: final ADMM z (warm-start state, isls.py:489-490) */
+  double *lam_x, *lam_u;/* optional: final scaled duals */
+  double *K;            /* [B, N, m, n] optional: feedback gains of the last backward pass */
+  double *k;            /* [B, N, m] optional: feed-forward gains of the last backward pass */
+  int8_t *mask_x, *mask_u; /* [B, N, dim] optional: clip mask of the last projection (-1 at lo, +1 at hi) */
+} isls_solve_out;
+
+int isls_version(void);
+const char *isls_last_error_string(void);
+
+/* name -> ISLS_MODEL_* (or ISLS_E_UNSUPPORTED).  Names: "double_integrator", "car", "arm3". */
+int isls_model_id(const char *name);
+/* 0 if the (model, n, m) combination has a compiled kernel */
+int isls_model_supported(int32_t model_id, int32_t n, int32_t m);
+
+int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan);
+int isls_plan_destroy(isls_plan *plan);
+
+/* bytes of caller-owned device workspace needed to solve B problems with this plan */
+int isls_workspace_bytes(const isls_plan *plan, int64_t B, size_t *bytes);
+
+/* iSLS.ilqr_admm (isls/isls.py:379-501) with ADMM (isls/admm.py:6-106) and project_bound
+ * (isls/projections.py:7-11) for a batch of B independent problems.
+ *   x0_dev [B, n]; u_init_dev [B, N, m]; zs_dev [B, n_via, n] via-point targets per problem. */
+int isls_ilqr_admm_solve_f64(const isls_plan *plan, const isls_solve_opts *opts, int64_t B,
+                             const double *x0_dev, const double *u_init_dev, const double *zs_dev,
+                             void *workspace_dev, size_t workspace_bytes, const isls_solve_out *out, void *stream);
+
+/* iSLS.solve(method='dp') (isls/isls.py:54-132, 229-374): unconstrained iLQR with closed-loop line search. */
+int isls_ilqr_solve_f64(const isls_plan *plan, const isls_solve_opts *opts, int64_t B,
+                        const double *x0_dev, const double *u_init_dev, const double *zs_dev,
+                        void *workspace_dev, size_t workspace_bytes, const isls_solve_out *out, void *stream);
+
+/* SLS.ADMM_LQT_DP (isls/sls.py:298-317; solve_dp 85-166, solve_dp_ff 168-202): linear dynamics
+ * (double integrator), opts->max_admm iterations, single "outer" pass.  out->cost_log gets [B,2]. */
+int isls_lqt_admm_dp_f64(const isls_plan *plan, const isls_solve_opts *opts, int64_t B,
+                         const double *x0_dev, const double *zs_dev,
+                         void *workspace_dev, size_t workspace_bytes, const isls_solve_out *out, void *stream);
+
+/* ---- stage-level entry points (teacher-forced parity tests; also usable on their own) ---- */
+
+/* iSLS.backward_pass_DP(Cts, cts) (isls/isls.py:229-308), generic-operator variant: dense operators from HBM.
+ *   A_dev [B,N,n,n], B_dev [B,N,n,m], c_dev [B,N,n+m], C_dev [B,N,n+m,n+m] -> K_dev [B,N,m,n], k_dev [B,N,m],
+ *   non_pd_dev [B] (int32, optional).  Supported (n,m): (2,1) (4,2) (6,3) (9,3). */
+int isls_riccati_f64(int32_t n, int32_t m, int32_t N, int64_t B, const double *A_dev, const double *B_dev,
+                     const double *c_dev, const double *C_dev, double *K_dev, double *k_dev, int32_t *non_pd_dev,
+                     void *stream);
+
+/* iSLS.rollout_batch + cost evaluation + argmin (isls/isls.py:135-154, 468-477): open-loop line search from
+ * x_nom[:,0] over candidates u_nom + alpha_l * du with the ADMM penalty terms.
+ *   x_nom_dev [B,N,n] (only x_nom[:,0] is used, like the reference), u_nom_dev [B,N,m], du_dev [B,N,m],
+ *   reg_x_dev [B,N,n] / reg_u_dev [B,N,m] (z - lambda; may be NULL when the plan has no such projection)
+ *   -> costs_dev [B,L], best_dev [B] (int32), x_best_dev [B,N,n], u_best_dev [B,N,m]. */
+int isls_rollout_linesearch_f64(const isls_plan *plan, int64_t B, const double *x_nom_dev, const double *u_nom_dev,
+                                const double *du_dev, const double *zs_dev, const double *reg_x_dev,
+                                const double *reg_u_dev, double *costs_dev, int32_t *best_dev, double *x_best_dev,
+                                double *u_best_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* One ADMM z-projection + scaled-dual update (isls/admm.py:43-69) with project_bound, elementwise on flat
+ * [B, len] arrays with per-element bounds lo/hi [len] (device):
+ *   z <- clip(relax*x + (1-relax)*z + lam, lo, hi); lam <- lam + x - z;
+ *   prim_sq[B] += sum (x-z)^2, dual_sq[B] += sum (z-z_prev)^2, mask[B,len] (optional) = -1/0/+1.
+ * Bit-exact with numpy on the same inputs (no FMA contraction). */
+int isls_admm_project_dual_f64(int64_t B, int64_t len, double relax, const double *x_dev, double *z_dev,
+                               double *lam_dev, const double *lo_dev, const double *hi_dev, double *prim_sq_dev,
+                               double *dual_sq_dev, int8_t *mask_dev, void *stream);
+
+/* ---- measurement helpers (bench.py roofline denominators; not part of the reference surface) ---- */
+/* dependent-free DFMA throughput of the whole GPU in TFLOP/s (FMA = 2 flop), measured with CUDA events */
+int isls_measure_fp64_tflops(double *tflops, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISLS_B200_H */

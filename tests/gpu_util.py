@@ -1,0 +1,55 @@
+"""Helpers shared by the GPU parity tests: run an oracle problem dict (oracle/problems.py) through the public
+isls_b200 API."""
+import numpy as np
+
+from isls_b200 import Bound, SLS, iSLS
+
+
+def make_isls(p, device="cuda:0"):
+    B = p["x0"].shape[0]
+    s = iSLS(p["n"], p["m"], p["N"], batch=B, device=device)
+    kw = {"dt": p["dt"]}
+    s.forward_model = (p["model"], kw)
+    s.set_quadratic_cost(p["zs"], p["Qdiag"], p["seq"], p["u_std"])
+    s.set_initial(p["x0"], p["u0"])
+    return s
+
+
+def run_ilqr_admm(p, fixed_budget=False, want_masks=True, device="cuda:0"):
+    s = make_isls(p, device)
+    kw = {}
+    if p.get("lo_x") is not None:
+        kw.update(project_x=Bound(p["lo_x"], p["hi_x"]), rho_x=p["rho_x"])
+    if p.get("lo_u") is not None:
+        kw.update(project_u=Bound(p["lo_u"], p["hi_u"]), rho_u=p["rho_u"])
+    out = s.ilqr_admm(max_iter=p["I_o"], max_admm_iter=p["I_a"], max_line_search_iter=p["L"], tol=p["tol"],
+                      alpha=p.get("alpha", 1.0), fixed_budget=fixed_budget, want_masks=want_masks, **kw)
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def run_ilqr_dp(p, max_iter, L, tol_fun=1e-5, fixed_budget=False, device="cuda:0"):
+    s = make_isls(p, device)
+    out = s.solve(p["model"], max_iter=max_iter, max_line_search_iter=L, tol_fun=tol_fun, fixed_budget=fixed_budget)
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def run_lqt_admm_dp(p, fixed_budget=False, device="cuda:0"):
+    from isls_b200 import get_double_integrator_AB
+    B = p["x0"].shape[0]
+    s = SLS(p["n"], p["m"], p["N"], batch=B, device=device)
+    s.AB = get_double_integrator_AB(p["m"], 2, p["dt"])
+    s.set_quadratic_cost(p["zs"], p["Qdiag"], p["seq"], p["u_std"])
+    kw = {}
+    if p.get("lo_x") is not None:
+        kw.update(project_x=Bound(p["lo_x"], p["hi_x"]), rho_x=p["rho_x"])
+    if p.get("lo_u") is not None:
+        kw.update(project_u=Bound(p["lo_u"], p["hi_u"]), rho_u=p["rho_u"])
+    s.ADMM_LQT_DP(p["x0"], max_iter=p["I_a"], tol=p["tol"], alpha=p.get("alpha", 1.0), fixed_budget=fixed_budget,
+                  want_masks=True, **kw)
+    return {k: v.cpu().numpy() for k, v in s.last.items()}
+
+
+def rel_logs(a, b):
+    m = ~np.isnan(b)
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "cost_log lengths differ"
+    return np.max(np.abs(a[m] - b[m]) / np.maximum(np.abs(b[m]), 1e-300))
