@@ -41,6 +41,25 @@ static int cuda_fail(cudaError_t e, const char *what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
   } while (0)
 
+// ---------------------------------------------------------------------------------------- per-kernel event timing
+// Optional (bench.py roofline): when enabled on the calling thread, every kernel launch of a solve is bracketed by
+// a CUDA event pair on the launching stream; isls_profile_collect() synchronises and sums per kernel class.
+struct ProfRec { int kc; cudaEvent_t e0, e1; };
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec> g_prof;
+struct ProfScope {
+  cudaStream_t s; int idx;
+  ProfScope(int kc, cudaStream_t s_) : s(s_), idx(-1) {
+    if (!g_prof_on) return;
+    ProfRec r; r.kc = kc;
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, s);
+    g_prof.push_back(r); idx = (int)g_prof.size() - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(g_prof[idx].e1, s); }
+};
+#define LAUNCH(kc, stream, ...) do { ProfScope ps__(kc, stream); __VA_ARGS__; } while (0)
+
 // ------------------------------------------------------------------------------------------------ device context
 struct Dev {
   int N, n_via, L, proj_x, proj_u, T;
@@ -1488,17 +1507,17 @@ extern "C" int isls_ilqr_admm_solve_f64(const isls_plan *plan, const isls_solve_
   cudaStream_t s = (cudaStream_t)stream;
   return dispatch_model(plan, [&](auto model) -> int {
     using M = decltype(model);
-    k_init<M><<<tp_grid(d), tp_block(), 0, s>>>(d, x0, u_init, zs);
+    LAUNCH(ISLS_KC_INIT, s, (k_init<M><<<tp_grid(d), tp_block(), 0, s>>>(d, x0, u_init, zs)));
     for (int j = 0; j < d.max_outer; j++) {
-      k_kpass<M><<<tp_grid(d), tp_block(), 0, s>>>(d);
+      LAUNCH(ISLS_KC_KPASS, s, (k_kpass<M><<<tp_grid(d), tp_block(), 0, s>>>(d)));
       for (int a = 0; a < d.max_admm; a++) {
-        k_ff<M><<<tp_grid(d), tp_block(), 0, s>>>(d);
-        launch_linesearch<M>(d, false, s);
-        k_admm<M><<<tp_grid(d), tp_block(), 0, s>>>(d, j, a);
+        LAUNCH(ISLS_KC_FF, s, (k_ff<M><<<tp_grid(d), tp_block(), 0, s>>>(d)));
+        LAUNCH(ISLS_KC_LINESEARCH, s, launch_linesearch<M>(d, false, s));
+        LAUNCH(ISLS_KC_ADMM, s, (k_admm<M><<<tp_grid(d), tp_block(), 0, s>>>(d, j, a)));
       }
-      k_outer_end<M><<<tp_grid(d), tp_block(), 0, s>>>(d, j);
+      LAUNCH(ISLS_KC_OUTER_END, s, (k_outer_end<M><<<tp_grid(d), tp_block(), 0, s>>>(d, j)));
     }
-    k_finalize<M><<<tp_grid(d), tp_block(), 0, s>>>(d);
+    LAUNCH(ISLS_KC_FINALIZE, s, (k_finalize<M><<<tp_grid(d), tp_block(), 0, s>>>(d)));
     CK(cudaGetLastError());
     return ISLS_OK;
   });
@@ -1520,13 +1539,13 @@ extern "C" int isls_ilqr_solve_f64(const isls_plan *plan, const isls_solve_opts 
   cudaStream_t s = (cudaStream_t)stream;
   return dispatch_model(plan, [&](auto model) -> int {
     using M = decltype(model);
-    k_init<M><<<tp_grid(d), tp_block(), 0, s>>>(d, x0, u_init, zs);
+    LAUNCH(ISLS_KC_INIT, s, (k_init<M><<<tp_grid(d), tp_block(), 0, s>>>(d, x0, u_init, zs)));
     for (int j = 0; j < d.max_outer; j++) {
-      k_backward_full<M><<<tp_grid(d), tp_block(), 0, s>>>(d);
-      launch_linesearch<M>(d, true, s);
-      k_accept_closed<M><<<tp_grid(d), tp_block(), 0, s>>>(d, j);
+      LAUNCH(ISLS_KC_BACKWARD_FULL, s, (k_backward_full<M><<<tp_grid(d), tp_block(), 0, s>>>(d)));
+      LAUNCH(ISLS_KC_LINESEARCH, s, launch_linesearch<M>(d, true, s));
+      LAUNCH(ISLS_KC_ACCEPT, s, (k_accept_closed<M><<<tp_grid(d), tp_block(), 0, s>>>(d, j)));
     }
-    k_finalize<M><<<tp_grid(d), tp_block(), 0, s>>>(d);
+    LAUNCH(ISLS_KC_FINALIZE, s, (k_finalize<M><<<tp_grid(d), tp_block(), 0, s>>>(d)));
     CK(cudaGetLastError());
     return ISLS_OK;
   });
@@ -1574,7 +1593,7 @@ extern "C" int isls_lqt_admm_dp_f64(const isls_plan *plan, const isls_solve_opts
     k_kpass<M><<<1, dim3(TILE, 1), 0, s>>>(d1);
     // the K-pass reset (lambda = 0, reg = z) touched tile 0 only with zeros: state stays zero
     k_pack_zs<M><<<tp_grid(d), tp_block(), 0, s>>>(d, zs);
-    k_lqt_admm<M><<<tp_grid(d), tp_block(), 0, s>>>(d, x0);
+    LAUNCH(ISLS_KC_LQT, s, (k_lqt_admm<M><<<tp_grid(d), tp_block(), 0, s>>>(d, x0)));
     k_copy_primal<M><<<tp_grid(d), tp_block(), 0, s>>>(d);
     Dev df = d;
     df.out.K = nullptr;          // gains are shared: unpacked by k_lqt_unpack_K
@@ -1629,6 +1648,27 @@ extern "C" int isls_admm_project_dual_f64(int64_t B, int64_t len, double relax, 
   if (B <= 0 || len <= 0 || !x || !z || !lam || !lo || !hi) return fail(ISLS_E_INVALID, "NULL argument or bad size");
   k_admm_flat<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(len, relax, x, z, lam, lo, hi, prim_sq, dual_sq, mask);
   CK(cudaGetLastError());
+  return ISLS_OK;
+}
+
+extern "C" int isls_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return ISLS_OK;
+}
+
+extern "C" int isls_profile_collect(double *ms_sum, int64_t *launches) {
+  if (!ms_sum || !launches) return fail(ISLS_E_INVALID, "NULL argument");
+  for (int i = 0; i < ISLS_KC_COUNT; i++) { ms_sum[i] = 0.0; launches[i] = 0; }
+  for (auto &r : g_prof) {
+    CK(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    ms_sum[r.kc] += ms;
+    launches[r.kc] += 1;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
   return ISLS_OK;
 }
 

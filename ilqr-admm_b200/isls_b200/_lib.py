@@ -36,7 +36,10 @@ class SolveOut(C.Structure):
 EXPORTS = ["isls_version", "isls_last_error_string", "isls_model_id", "isls_model_supported", "isls_plan_create",
            "isls_plan_destroy", "isls_workspace_bytes", "isls_ilqr_admm_solve_f64", "isls_ilqr_solve_f64",
            "isls_lqt_admm_dp_f64", "isls_riccati_f64", "isls_rollout_linesearch_f64", "isls_admm_project_dual_f64",
-           "isls_measure_fp64_tflops"]
+           "isls_measure_fp64_tflops", "isls_profile_enable", "isls_profile_collect"]
+
+KERNEL_CLASSES = ["init", "kpass", "ff", "linesearch", "admm", "outer_end", "finalize", "backward_full", "accept",
+                  "lqt"]
 
 _lib = None
 
@@ -70,6 +73,8 @@ def lib():
     L.isls_rollout_linesearch_f64.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 11 + [C.c_size_t, C.c_void_p]
     L.isls_admm_project_dual_f64.argtypes = [C.c_int64, C.c_int64, C.c_double] + [C.c_void_p] * 9
     L.isls_measure_fp64_tflops.argtypes = [C.POINTER(C.c_double), C.c_void_p]
+    L.isls_profile_enable.argtypes = [C.c_int]
+    L.isls_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     _lib = L
     return L
 

@@ -126,6 +126,7 @@ class BatchSolver:
         self._cout = _lib.SolveOut()
         for f in _lib.OUT_FIELDS:
             setattr(self._cout, f, _dptr(o.get(f)))
+        self.h2d_bytes = 0
         # device staging buffers for the inputs
         self.x0 = torch.empty(B_, n, **f64)
         self.u_init = torch.empty(B_, N, m, **f64)
@@ -139,9 +140,15 @@ class BatchSolver:
             t = torch.from_numpy(np.ascontiguousarray(np.asarray(src, dtype=np.float64)))
         if t.dtype != torch.float64:
             t = t.to(torch.float64)
-        if t.shape != dst.shape:
-            t = t.expand(dst.shape)
-        dst.copy_(t, non_blocking=True)
+        if t.device != dst.device:
+            # host -> device: move the bytes that exist (un-expanded storage), broadcast on the device
+            base = t
+            if any(st == 0 for st in t.stride()) and t.numel() > 0:
+                idx = tuple(slice(0, 1) if st == 0 else slice(None) for st in t.stride())
+                base = t[idx]
+            self.h2d_bytes += base.numel() * 8
+            t = base.to(dst.device, non_blocking=True)
+        dst.copy_(t.expand(dst.shape), non_blocking=True)
 
     def set_inputs(self, x0, u_init, zs):
         self._stage(self.x0, x0, "x0")
@@ -251,3 +258,16 @@ def measure_fp64_tflops(device="cuda:0"):
                                                  C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
     _lib.check(rc, "isls_measure_fp64_tflops")
     return v.value
+
+
+def profile_enable(on):
+    _lib.check(_lib.lib().isls_profile_enable(int(bool(on))), "isls_profile_enable")
+
+
+def profile_collect():
+    """-> {kernel class: (total ms, launches)} since the last collect (per-kernel CUDA-event timing)."""
+    n = len(_lib.KERNEL_CLASSES)
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    _lib.check(_lib.lib().isls_profile_collect(ms, cnt), "isls_profile_collect")
+    return {k: (ms[i], cnt[i]) for i, k in enumerate(_lib.KERNEL_CLASSES) if cnt[i]}

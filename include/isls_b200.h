@@ -170,6 +170,23 @@ int isls_admm_project_dual_f64(int64_t B, int64_t len, double relax, const doubl
                                double *dual_sq_dev, int8_t *mask_dev, void *stream);
 
 /* ---- measurement helpers (bench.py roofline denominators; not part of the reference surface) ---- */
+/* kernel classes for per-kernel CUDA-event timing */
+#define ISLS_KC_INIT 0
+#define ISLS_KC_KPASS 1
+#define ISLS_KC_FF 2
+#define ISLS_KC_LINESEARCH 3
+#define ISLS_KC_ADMM 4
+#define ISLS_KC_OUTER_END 5
+#define ISLS_KC_FINALIZE 6
+#define ISLS_KC_BACKWARD_FULL 7
+#define ISLS_KC_ACCEPT 8
+#define ISLS_KC_LQT 9
+#define ISLS_KC_COUNT 10
+/* thread-local switch: when on, every kernel launch of a solve is bracketed by a CUDA event pair on the
+ * launching stream (adds a few microseconds per launch; use for per-kernel durations, not for throughput) */
+int isls_profile_enable(int on);
+/* synchronises, sums elapsed milliseconds and launch counts per kernel class ([ISLS_KC_COUNT] each), resets */
+int isls_profile_collect(double *ms_sum, int64_t *launches);
 /* dependent-free DFMA throughput of the whole GPU in TFLOP/s (FMA = 2 flop), measured with CUDA events */
 int isls_measure_fp64_tflops(double *tflops, void *stream);
 

@@ -1,103 +1,10 @@
-"""TEST INFRASTRUCTURE (oracle side) - seeded synthetic problem batches C1..C5 of SURVEY.md 8(d).
+"""Problem data lives with the product (ilqr-admm_b200/isls_b200/configs.py: numpy arrays only, no solver logic);
+this shim lets oracle-side code keep importing `oracle.problems`."""
+import os
+import sys
 
-The same arrays are fed to the oracle, to the reference shim (golden generation) and to the CUDA path, so this
-module contains no solver logic - only problem data (numpy).  bench.py / tests import it to build inputs.
-
-A problem batch is a plain dict:
-  model      "car" | "arm3" | "double_integrator",  dt
-  N, n, m
-  zs[k,n], Qdiag[k,n], seq[N] int32, u_std     quadratic via-point cost (base.py:81-89)
-  x0[B,n], u0[N,m]                              initial state per problem, shared initial control guess
-  lo_u/hi_u[N,m], lo_x/hi_x[N,n] or None        box bounds (+-inf = unconstrained element)
-  rho_u[N,m] or None, rho_x[N,n] or None        diagonal ADMM penalty weights (compute_Rr_Qr, base.py:55-79)
-  I_o, I_a, L, tol, alpha                       budgets / tolerances (isls.py:379-381 keywords)
-"""
-import numpy as np
-
-INF = np.inf
-
-
-def _seed(idx):
-    return 1234 + idx
-
-
-def car_batch(B, N=100, dt=0.1, seed=_seed(2), I_o=20, I_a=5, L=20, tol=1e-3, stress=False):
-    """C2 / C5: simple kinematic car, control bounds |u|<=0.5, rho_u = 10
-    (weights: notebooks/Car/Iterative LQR with control constraints.ipynb cells 8, 18, 20)."""
-    rng = np.random.default_rng(seed)
-    n, m = 4, 2
-    x0 = np.zeros((B, n))
-    x0[:, 0] = rng.uniform(-2, 2, B)
-    x0[:, 1] = rng.uniform(-2, 2, B)
-    if stress:     # notebook-like distribution: dt=0.03, target theta 0, theta0 in [0, 2pi): hits the mod wrap
-        x0[:, 2] = rng.uniform(0, 2 * np.pi, B)
-        target = np.zeros(n)
-    else:
-        x0[:, 2] = rng.uniform(np.pi / 2, 3 * np.pi / 2, B)
-        target = np.array([0.0, 0.0, np.pi, 0.0])
-    zs = np.stack([np.zeros(n), target])
-    Qdiag = np.stack([np.zeros(n), np.full(n, 1e2)])
-    seq = np.zeros(N, dtype=np.int32)
-    seq[-1] = 1
-    return dict(name="car", model="car", dt=(0.03 if stress else dt), N=N, n=n, m=m, zs=zs, Qdiag=Qdiag, seq=seq,
-                u_std=1e-2, x0=x0, u0=np.zeros((N, m)),
-                lo_u=np.full((N, m), -0.5), hi_u=np.full((N, m), 0.5), lo_x=None, hi_x=None,
-                rho_u=np.full((N, m), 1e1), rho_x=None, I_o=I_o, I_a=I_a, L=L, tol=tol, alpha=1.0)
-
-
-def arm_batch(B, N=100, dt=0.01, seed=_seed(3), I_o=20, I_a=10, L=5, tol=1e-4):
-    """C3: planar 3-DoF arm with state and control bounds
-    (notebooks/3DoF robot/State and control bound constraints.ipynb cells 12, 15, 22-24)."""
-    from .models import Arm3
-    rng = np.random.default_rng(seed)
-    n, m = 9, 3
-    q0 = np.array([np.pi / 3, -np.pi / 2, -np.pi / 4]) + rng.normal(0.0, 0.1, (B, 3))
-    x0 = Arm3(dt).state_from_q(q0)
-    target = np.array([0, 0, 0, 0, 0, 0, 1.5, 1.0, 0.0])
-    zs = np.stack([np.zeros(n), target])
-    Qdiag = np.stack([np.zeros(n), np.array([0, 0, 0, 1e6, 1e6, 1e6, 0, 1e6, 0.0])])
-    seq = np.zeros(N, dtype=np.int32)
-    seq[-1] = 1
-    lo_x = np.full((N, n), -INF)
-    hi_x = np.full((N, n), INF)
-    lo_x[:, 3:6], hi_x[:, 3:6] = -1.5, 1.5
-    lo_x[-1, 6], hi_x[-1, 6] = 0.5, 1.0
-    rho_x = np.zeros((N, n))
-    rho_x[:, 3:6] = 1e-2
-    rho_x[-1, 6] = 1e1
-    return dict(name="arm3", model="arm3", dt=dt, N=N, n=n, m=m, zs=zs, Qdiag=Qdiag, seq=seq, u_std=1e-4,
-                x0=x0, u0=np.ones((N, m)),
-                lo_u=np.full((N, m), -6.0), hi_u=np.full((N, m), 6.0), lo_x=lo_x, hi_x=hi_x,
-                rho_u=np.full((N, m), 1e-3), rho_x=rho_x, I_o=I_o, I_a=I_a, L=L, tol=tol, alpha=1.0)
-
-
-def di_batch(B=1, N=50, seed=_seed(1), max_iter=2000, tol=1e-4, batched_targets=False):
-    """C1: LQT-ADMM double integrator (n=4, m=2), state + control bounds
-    (structure of notebooks/Double integrator/LQR and SLS with state bounds.ipynb)."""
-    rng = np.random.default_rng(seed)
-    n, m = 4, 2
-    dt = 1.0 / N
-    target = np.array([0.5, 0.4, 0.0, 0.0])
-    zs = np.stack([np.zeros(n), target])
-    Qdiag = np.stack([np.zeros(n), np.full(n, 1e3)])
-    seq = np.zeros(N, dtype=np.int32)
-    seq[-1] = 1
-    x0 = np.zeros((B, n))
-    if B > 1:
-        x0[:, :2] = rng.normal(0.0, 0.02, (B, 2))
-    lo_x = np.full((N, n), -INF)
-    hi_x = np.full((N, n), INF)
-    lo_x[:, 2:], hi_x[:, 2:] = -0.6, 0.6
-    rho_x = np.zeros((N, n))
-    rho_x[:, 2:] = 1.0
-    return dict(name="double_integrator", model="double_integrator", dt=dt, N=N, n=n, m=m, zs=zs, Qdiag=Qdiag,
-                seq=seq, u_std=1e-4, x0=x0, u0=np.zeros((N, m)),
-                lo_u=np.full((N, m), -3.0), hi_u=np.full((N, m), 3.0), lo_x=lo_x, hi_x=hi_x,
-                rho_u=np.full((N, m), 1e-2), rho_x=rho_x, I_o=1, I_a=max_iter, L=1, tol=tol, alpha=1.0)
-
-
-def subset(p, idx):
-    """Same problem data restricted to problems `idx` (array of indices)."""
-    q = dict(p)
-    q["x0"] = p["x0"][idx].copy()
-    return q
+_PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ilqr-admm_b200")
+if _PKG not in sys.path:
+    sys.path.insert(0, _PKG)
+from isls_b200.configs import *          # noqa: F401,F403,E402
+from isls_b200.configs import _seed      # noqa: F401,E402
