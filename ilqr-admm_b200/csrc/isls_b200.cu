@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -73,7 +74,7 @@ struct Dev {
   const double *rho_u, *lo_u, *hi_u;   // [N][m]
   const double *alphas;  // [L]
   // workspace, tile-blocked [T][N][dim][32]
-  double *xh, *uh, *xa, *ua, *du, *zx, *lx, *zu, *lu, *rgx, *rgu, *Kg, *Qux, *Quu, *Qui, *kk, *jac, *zs;
+  double *xh, *uh, *du, *zx, *lx, *zu, *lu, *rgx, *rgu, *Kg, *Qui, *kk, *zs;   // Qui: packed lower triangle
   double *lsc;           // [T][L][32] candidate costs of the last line search
   // per-problem scalars [T*32]
   double *cost, *prev_cost, *prim, *dual, *cost_adm, *best_cost;
@@ -188,10 +189,9 @@ template <class M>
 __device__ __forceinline__ bool riccati_step(const double (&A)[M::n][M::n], const double (&Bm)[M::n][M::m],
                                              const double (&dxx)[M::n], const double (&duu)[M::m],
                                              double (&V)[M::n][M::n], double (&K)[M::m][M::n],
-                                             double (&Qux)[M::m][M::n], double (&Quu)[M::m][M::m],
                                              double (&Qui)[M::m][M::m]) {
   constexpr int n = M::n, m = M::m;
-  double VA[n][n], Qxx[n][n];
+  double VA[n][n], Qxx[n][n], Qux[m][n], Quu[m][m];
   mat_V_A<M>(V, A, VA);
   mat_At_X<M, n>(A, VA, Qxx);
 #pragma unroll
@@ -240,16 +240,18 @@ __device__ __forceinline__ bool riccati_step(const double (&A)[M::n][M::n], cons
   return ok;
 }
 
-// feed-forward step (sls.py:196-199): qx = cx + A'v, qu = cu + B'v, k = -Quu^-1 qu,
-// v = qx + Qux'k + K'qu + K'(Quu k)
+// feed-forward step (sls.py:196-199): qx = cx + A'v, qu = cu + B'v, k = -Quu^-1 qu, and
+//   v = qx + Qux'k + K'qu + K'(Quu k)  =  qx + K'qu
+// (with k = -Quu^-1 qu and K = -Quu^-1 Qux the terms K'(Quu k) and Qux'k equal -K'qu and +K'qu exactly in real
+// arithmetic; evaluating the collapsed form needs K and Quu^-1 only - no Qux / Quu traffic - and avoids the
+// cancellation of the three-term form).
 template <class M>
 __device__ __forceinline__ void ff_step(const double (&A)[M::n][M::n], const double (&Bm)[M::n][M::m],
                                         const double (&cx)[M::n], const double (&cu)[M::m],
-                                        const double (&K)[M::m][M::n], const double (&Qux)[M::m][M::n],
-                                        const double (&Quu)[M::m][M::m], const double (&Qui)[M::m][M::m],
+                                        const double (&K)[M::m][M::n], const double (&Qui)[M::m][M::m],
                                         double (&v)[M::n], double (&kt)[M::m]) {
   constexpr int n = M::n, m = M::m;
-  double qx[n], qu[m], Qk[m];
+  double qx[n], qu[m];
   mat_At_v<M>(A, v, qx);
   mat_Bt_v<M>(Bm, v, qu);
 #pragma unroll
@@ -264,24 +266,17 @@ __device__ __forceinline__ void ff_step(const double (&A)[M::n][M::n], const dou
     kt[a] = -acc;
   }
 #pragma unroll
-  for (int a = 0; a < m; a++) {
-    double acc = 0.0;
-#pragma unroll
-    for (int b2 = 0; b2 < m; b2++) acc = fma(Quu[a][b2], kt[b2], acc);
-    Qk[a] = acc;
-  }
-#pragma unroll
   for (int i = 0; i < n; i++) {
-    double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    double acc = qx[i];
 #pragma unroll
-    for (int a = 0; a < m; a++) {
-      t1 = fma(Qux[a][i], kt[a], t1);
-      t2 = fma(K[a][i], qu[a], t2);
-      t3 = fma(K[a][i], Qk[a], t3);
-    }
-    v[i] = ((qx[i] + t1) + t2) + t3;
+    for (int a = 0; a < m; a++) acc = fma(K[a][i], qu[a], acc);
+    v[i] = acc;
   }
 }
+
+// packed lower triangle of a symmetric m x m matrix: index of (a, b), b <= a
+__host__ __device__ constexpr int tri(int a, int b) { return a * (a + 1) / 2 + b; }
+#define NTRI(m) ((m) * ((m) + 1) / 2)
 
 template <class M>
 __device__ __forceinline__ void init_AB(double (&A)[M::n][M::n], double (&Bm)[M::n][M::m]) {
@@ -295,20 +290,18 @@ __device__ __forceinline__ void init_AB(double (&A)[M::n][M::n], double (&Bm)[M:
 }
 
 // K-pass: linearise at the nominal trajectory (get_AB, isls/isls.py:424) and run the Riccati recursion with
-// Cxx = 2(Q_t + Qr_t), Cuu = 2(R + Rr_t) (regularised form of sls.py:132-137).  Stores K, Qux, Quu, Quu^-1
-// (sls.py:159-162 logs) and the Jacobian scalars; resets the ADMM state of the new outer iteration
-// (lambda = 0, isls/isls.py:414-415; z warm start isls/isls.py:489-490).
+// Cxx = 2(Q_t + Qr_t), Cuu = 2(R + Rr_t) (regularised form of sls.py:132-137).  Stores K_t and the packed Quu_t^-1
+// (what the feed-forward passes need, cf. the logs of sls.py:159-162); resets the ADMM state of the new outer
+// iteration (lambda = 0, isls/isls.py:414-415; z warm start isls/isls.py:489-490).
 template <class M>
 __global__ void k_kpass(Dev d) {
-  constexpr int n = M::n, m = M::m;
+  constexpr int n = M::n, m = M::m, nt = NTRI(M::m);
   const int tile = blockIdx.x * blockDim.y + threadIdx.y;
   if (tile >= d.T) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b]) return;
   const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m);
-  double *Kg = c.at(d.Kg, d, m * n), *Qx = c.at(d.Qux, d, m * n);
-  double *Qu = c.at(d.Quu, d, m * m), *Qi = c.at(d.Qui, d, m * m);
-  double *jc = c.at(d.jac, d, M::NJA);
+  double *Kg = c.at(d.Kg, d, m * n), *Qi = c.at(d.Qui, d, nt);
   double A[n][n], Bm[n][m], V[n][n];
   init_AB<M>(A, Bm);
 #pragma unroll
@@ -324,27 +317,19 @@ __global__ void k_kpass(Dev d) {
 #pragma unroll
     for (int j = 0; j < m; j++) u[j] = EL(uh, m, t, j);
     M::jac(x, u, J, d.dt);
-#pragma unroll
-    for (int q = 0; q < M::NJ; q++) EL(jc, M::NJA, t, q) = J[q];
     M::expand(J, A, Bm, d.dt);
-    double dxx[n], duu[m], K[m][n], Qux[m][n], Quu[m][m], Qui[m][m];
+    double dxx[n], duu[m], K[m][n], Qui[m][m];
 #pragma unroll
     for (int i = 0; i < n; i++) dxx[i] = 2.0 * (d.qd[t * n + i] + d.rho_x[t * n + i]);
 #pragma unroll
     for (int j = 0; j < m; j++) duu[j] = 2.0 * (d.u_std + d.rho_u[t * m + j]);
-    ok &= riccati_step<M>(A, Bm, dxx, duu, V, K, Qux, Quu, Qui);
+    ok &= riccati_step<M>(A, Bm, dxx, duu, V, K, Qui);
 #pragma unroll
     for (int a = 0; a < m; a++) {
 #pragma unroll
-      for (int j = 0; j < n; j++) {
-        EL(Kg, m * n, t, a * n + j) = K[a][j];
-        EL(Qx, m * n, t, a * n + j) = Qux[a][j];
-      }
+      for (int j = 0; j < n; j++) EL(Kg, m * n, t, a * n + j) = K[a][j];
 #pragma unroll
-      for (int b2 = 0; b2 < m; b2++) {
-        EL(Qu, m * m, t, a * m + b2) = Quu[a][b2];
-        EL(Qi, m * m, t, a * m + b2) = Qui[a][b2];
-      }
+      for (int b2 = 0; b2 <= a; b2++) EL(Qi, nt, t, tri(a, b2)) = Qui[a][b2];
     }
   }
 #pragma unroll
@@ -374,44 +359,46 @@ __global__ void k_kpass(Dev d) {
 // Riccati form, SURVEY 8c' step 2): backward feed-forward recursion (sls.py:168-202) with
 //   cx = 2Q(x^ - z_via) + 2Qr(x^ - reg_x), cu = 2R u^ + 2Rr(u^ - reg_u),
 // batch-form last control, then du_t = K dx + k, dx+ = A dx + B du.
+// HBM-bound kernel: the Jacobian scalars are recomputed from (x^_t, u^_t) (loaded anyway for cx, cu) instead of
+// being read back, and only K_t and the packed Quu_t^-1 are streamed.
 template <class M>
 __global__ void k_ff(Dev d) {
-  constexpr int n = M::n, m = M::m;
+  constexpr int n = M::n, m = M::m, nt = NTRI(M::m);
   const int tile = blockIdx.x * blockDim.y + threadIdx.y;
   if (tile >= d.T) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b] || d.adone[c.b]) return;
   const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m);
-  const double *Kg = c.at(d.Kg, d, m * n), *Qx = c.at(d.Qux, d, m * n);
-  const double *Qu = c.at(d.Quu, d, m * m), *Qi = c.at(d.Qui, d, m * m);
-  const double *jc = c.at(d.jac, d, M::NJA);
+  const double *Kg = c.at(d.Kg, d, m * n), *Qi = c.at(d.Qui, d, nt);
   const double *rgx = c.at(d.rgx, d, n), *rgu = c.at(d.rgu, d, m);
   const double *zs = d.zs + (size_t)tile * d.n_via * n * TILE + c.lane;
   double *kk = c.at(d.kk, d, m), *du = c.at(d.du, d, m);
   double A[n][n], Bm[n][m];
   init_AB<M>(A, Bm);
   double v[n];
-  auto costgrad = [&](int t, double (&cx)[n], double (&cu)[m]) {
+  auto costgrad = [&](int t, const double (&x)[n], const double (&u)[m], double (&cx)[n], double (&cu)[m]) {
     const int s = d.seq[t];
 #pragma unroll
     for (int i = 0; i < n; i++) {
-      const double xi = EL(xh, n, t, i);
       double g = 0.0;
-      if (d.qnz[t]) g = 2.0 * d.qd[t * n + i] * (xi - EL(zs, n, s, i));
-      if (d.proj_x) g += 2.0 * d.rho_x[t * n + i] * (xi - EL(rgx, n, t, i));
+      if (d.qnz[t]) g = 2.0 * d.qd[t * n + i] * (x[i] - EL(zs, n, s, i));
+      if (d.proj_x) g += 2.0 * d.rho_x[t * n + i] * (x[i] - EL(rgx, n, t, i));
       cx[i] = g;
     }
 #pragma unroll
     for (int j = 0; j < m; j++) {
-      const double uj = EL(uh, m, t, j);
-      double g = 2.0 * d.u_std * uj;
-      if (d.proj_u) g += 2.0 * d.rho_u[t * m + j] * (uj - EL(rgu, m, t, j));
+      double g = 2.0 * d.u_std * u[j];
+      if (d.proj_u) g += 2.0 * d.rho_u[t * m + j] * (u[j] - EL(rgu, m, t, j));
       cu[j] = g;
     }
   };
   {
-    double cx[n], cu[m];
-    costgrad(d.N - 1, cx, cu);
+    double x[n], u[m], cx[n], cu[m];
+#pragma unroll
+    for (int i = 0; i < n; i++) x[i] = EL(xh, n, d.N - 1, i);
+#pragma unroll
+    for (int j = 0; j < m; j++) u[j] = EL(uh, m, d.N - 1, j);
+    costgrad(d.N - 1, x, u, cx, cu);
 #pragma unroll
     for (int i = 0; i < n; i++) v[i] = cx[i];
 #pragma unroll
@@ -422,19 +409,22 @@ __global__ void k_ff(Dev d) {
     }
   }
   for (int t = d.N - 2; t >= 0; t--) {
-    double J[M::NJA], cx[n], cu[m], K[m][n], Qux[m][n], Quu[m][m], Qui[m][m], kt[m];
+    double x[n], u[m], J[M::NJA], cx[n], cu[m], K[m][n], Qui[m][m], kt[m];
 #pragma unroll
-    for (int q = 0; q < M::NJ; q++) J[q] = EL(jc, M::NJA, t, q);
-    M::expand(J, A, Bm, d.dt);
-    costgrad(t, cx, cu);
+    for (int i = 0; i < n; i++) x[i] = EL(xh, n, t, i);
+#pragma unroll
+    for (int j = 0; j < m; j++) u[j] = EL(uh, m, t, j);
 #pragma unroll
     for (int a = 0; a < m; a++) {
 #pragma unroll
-      for (int j = 0; j < n; j++) { K[a][j] = EL(Kg, m * n, t, a * n + j); Qux[a][j] = EL(Qx, m * n, t, a * n + j); }
+      for (int j = 0; j < n; j++) K[a][j] = EL(Kg, m * n, t, a * n + j);
 #pragma unroll
-      for (int b2 = 0; b2 < m; b2++) { Quu[a][b2] = EL(Qu, m * m, t, a * m + b2); Qui[a][b2] = EL(Qi, m * m, t, a * m + b2); }
+      for (int b2 = 0; b2 <= a; b2++) { Qui[a][b2] = EL(Qi, nt, t, tri(a, b2)); Qui[b2][a] = Qui[a][b2]; }
     }
-    ff_step<M>(A, Bm, cx, cu, K, Qux, Quu, Qui, v, kt);
+    M::jac(x, u, J, d.dt);
+    M::expand(J, A, Bm, d.dt);
+    costgrad(t, x, u, cx, cu);
+    ff_step<M>(A, Bm, cx, cu, K, Qui, v, kt);
 #pragma unroll
     for (int j = 0; j < m; j++) EL(kk, m, t, j) = kt[j];
   }
@@ -455,9 +445,12 @@ __global__ void k_ff(Dev d) {
       EL(du, m, t, a) = duv[a];
     }
     if (t < d.N - 1) {
-      double J[M::NJA], dxn[n];
+      double x[n], u[m], J[M::NJA], dxn[n];
 #pragma unroll
-      for (int q = 0; q < M::NJ; q++) J[q] = EL(jc, M::NJA, t, q);
+      for (int i = 0; i < n; i++) x[i] = EL(xh, n, t, i);
+#pragma unroll
+      for (int j = 0; j < m; j++) u[j] = EL(uh, m, t, j);
+      M::jac(x, u, J, d.dt);
       M::expand(J, A, Bm, d.dt);
       mat_Ax_Bu<M>(A, Bm, dx, duv, dxn);
 #pragma unroll
@@ -483,8 +476,8 @@ __device__ __forceinline__ int argmin_np(const double *c, int L, int stride, boo
 // Open-loop line search (isls/isls.py:468-477): for every candidate alpha_l roll the model out from x^_0 with
 // u^ + alpha_l du (rollout_batch, isls/isls.py:135-154), evaluate cost + sum((x-reg_x)^2 Qr) + sum((u-reg_u)^2 Rr),
 // take the argmin unconditionally.  CTA = 32 problems x W warps, CPT candidates per thread (ILP).
-template <class M, int CPT, int MAXW>
-__global__ void __launch_bounds__(TILE * MAXW) k_linesearch(Dev d) {
+template <class M, int CPT, int MAXW, int MINB>
+__global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d) {
   constexpr int n = M::n, m = M::m;
   __shared__ double sc[MAX_L][TILE];
   const int tile = blockIdx.x;
@@ -505,19 +498,36 @@ __global__ void __launch_bounds__(TILE * MAXW) k_linesearch(Dev d) {
 #pragma unroll
       for (int i = 0; i < n; i++) x[q][i] = EL(xh, n, 0, i);
     }
+    // operands of step t are loaded one step ahead (software prefetch: the loads of step t+1 are in flight while
+    // the FP64 chains of step t run)
+    double un_n[m], dun_n[m], ru_n[m], rx_n[n];
+    auto fetch = [&](int t) {
+#pragma unroll
+      for (int j = 0; j < m; j++) {
+        un_n[j] = EL(uh, m, t, j);
+        dun_n[j] = EL(du, m, t, j);
+        if (d.proj_u) ru_n[j] = EL(rgu, m, t, j);
+      }
+      if (d.proj_x) {
+#pragma unroll
+        for (int i = 0; i < n; i++) rx_n[i] = EL(rgx, n, t, i);
+      }
+    };
+    fetch(0);
     for (int t = 0; t < d.N; t++) {
       double un[m], dun[m], ru[m], rx[n], zv[n], qd[n], rhx[n], rhu[m];
       const bool qz = d.qnz[t];
 #pragma unroll
       for (int j = 0; j < m; j++) {
-        un[j] = EL(uh, m, t, j);
-        dun[j] = EL(du, m, t, j);
-        if (d.proj_u) { ru[j] = EL(rgu, m, t, j); rhu[j] = d.rho_u[t * m + j]; }
+        un[j] = un_n[j];
+        dun[j] = dun_n[j];
+        if (d.proj_u) { ru[j] = ru_n[j]; rhu[j] = d.rho_u[t * m + j]; }
       }
       if (d.proj_x) {
 #pragma unroll
-        for (int i = 0; i < n; i++) { rx[i] = EL(rgx, n, t, i); rhx[i] = d.rho_x[t * n + i]; }
+        for (int i = 0; i < n; i++) { rx[i] = rx_n[i]; rhx[i] = d.rho_x[t * n + i]; }
       }
+      if (t + 1 < d.N) fetch(t + 1);
       if (qz) {
         const int s = d.seq[t];
 #pragma unroll
@@ -587,7 +597,7 @@ __device__ __forceinline__ void admm_elem(double x, double relax, double lo, dou
 }
 
 // Winner rollout + ADMM update: re-roll the chosen candidate (the primal iterate (x,u) returned by f_argmin,
-// isls/isls.py:478), apply the z-projection and scaled dual update element by element (admm.py:43-59), form the
+// isls/isls.py:478; it is not stored - k_outer_end re-rolls the last one in place), apply the z-projection and scaled dual update element by element (admm.py:43-59), form the
 // residual norms (admm.py:62-69) and run the stop tests (admm.py:72-85).
 template <class M>
 __global__ void k_admm(Dev d, int outer, int inner) {
@@ -597,7 +607,6 @@ __global__ void k_admm(Dev d, int outer, int inner) {
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b] || d.adone[c.b]) return;
   const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m), *du = c.at(d.du, d, m);
-  double *xa = c.at(d.xa, d, n), *ua = c.at(d.ua, d, m);
   double *zx = c.at(d.zx, d, n), *lx = c.at(d.lx, d, n), *rgx = c.at(d.rgx, d, n);
   double *zu = c.at(d.zu, d, m), *lu = c.at(d.lu, d, m), *rgu = c.at(d.rgu, d, m);
   const double *zs = d.zs + (size_t)tile * d.n_via * n * TILE + c.lane;
@@ -613,7 +622,6 @@ __global__ void k_admm(Dev d, int outer, int inner) {
 #pragma unroll
     for (int j = 0; j < m; j++) {
       u[j] = EL(uh, m, t, j) + al * EL(du, m, t, j);
-      EL(ua, m, t, j) = u[j];
       cc += u[j] * u[j];
       if (d.proj_u) {
         double z = EL(zu, m, t, j), l = EL(lu, m, t, j);
@@ -627,7 +635,6 @@ __global__ void k_admm(Dev d, int outer, int inner) {
     }
 #pragma unroll
     for (int i = 0; i < n; i++) {
-      EL(xa, n, t, i) = x[i];
       if (d.proj_x) {
         double z = EL(zx, n, t, i), l = EL(lx, n, t, i);
         int mk;
@@ -682,13 +689,27 @@ __global__ void k_outer_end(Dev d, int outer) {
   if (tile >= d.T) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b]) return;
-  const double *xa = c.at(d.xa, d, n), *ua = c.at(d.ua, d, m);
+  // nominal <- last primal iterate (isls.py:488): re-roll u^ + alpha* du in place (same arithmetic as k_admm, whose
+  // cost of this iterate is cost_adm) instead of storing every ADMM iterate's trajectory
   double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m);
-  for (int t = 0; t < d.N; t++) {
+  const double *du = c.at(d.du, d, m);
+  {
+    const double al = d.alphas[d.best[c.b]];
+    double x[n], u[m], xn[n];
 #pragma unroll
-    for (int i = 0; i < n; i++) EL(xh, n, t, i) = EL(xa, n, t, i);
+    for (int i = 0; i < n; i++) x[i] = EL(xh, n, 0, i);
+    for (int t = 0; t < d.N; t++) {
 #pragma unroll
-    for (int j = 0; j < m; j++) EL(uh, m, t, j) = EL(ua, m, t, j);
+      for (int j = 0; j < m; j++) {
+        u[j] = EL(uh, m, t, j) + al * EL(du, m, t, j);
+        EL(uh, m, t, j) = u[j];
+      }
+#pragma unroll
+      for (int i = 0; i < n; i++) EL(xh, n, t, i) = x[i];
+      M::step(x, u, xn, d.dt);
+#pragma unroll
+      for (int i = 0; i < n; i++) x[i] = xn[i];
+    }
   }
   const double cost = d.cost_adm[c.b], prev = d.prev_cost[c.b];
   d.cost[c.b] = cost;
@@ -779,7 +800,7 @@ __global__ void k_backward_full(Dev d) {
   }
   bool ok = true;
   for (int t = d.N - 2; t >= 0; t--) {
-    double x[n], u[m], J[M::NJA], dxx[n], duu[m], cx[n], cu[m], K[m][n], Qux[m][n], Quu[m][m], Qui[m][m], kt[m];
+    double x[n], u[m], J[M::NJA], dxx[n], duu[m], cx[n], cu[m], K[m][n], Qui[m][m], kt[m];
     const int s = d.seq[t];
 #pragma unroll
     for (int i = 0; i < n; i++) {
@@ -801,8 +822,8 @@ __global__ void k_backward_full(Dev d) {
     for (int i = 0; i < n; i++)
 #pragma unroll
       for (int j = 0; j < n; j++) Vn[i][j] = V[i][j];
-    ok &= riccati_step<M>(A, Bm, dxx, duu, Vn, K, Qux, Quu, Qui);
-    ff_step<M>(A, Bm, cx, cu, K, Qux, Quu, Qui, v, kt);
+    ok &= riccati_step<M>(A, Bm, dxx, duu, Vn, K, Qui);
+    ff_step<M>(A, Bm, cx, cu, K, Qui, v, kt);
 #pragma unroll
     for (int i = 0; i < n; i++)
 #pragma unroll
@@ -818,8 +839,8 @@ __global__ void k_backward_full(Dev d) {
 }
 
 // Closed-loop line search (isls/isls.py:310-334, 357-363): u = K(x - x^) + alpha k + u^, NaN cost -> 1e5, argmin.
-template <class M, int CPT, int MAXW>
-__global__ void __launch_bounds__(TILE * MAXW) k_linesearch_closed(Dev d) {
+template <class M, int CPT, int MAXW, int MINB>
+__global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch_closed(Dev d) {
   constexpr int n = M::n, m = M::m;
   __shared__ double sc[MAX_L][TILE];
   const int tile = blockIdx.x;
@@ -1130,8 +1151,9 @@ __global__ void k_lqt_admm(Dev d, const double *x0_in) {
   if (tile >= d.T) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   // gains are shared: tile 0 / lane 0 of the gain arrays
-  const double *Kg = d.Kg, *Qx = d.Qux, *Qu = d.Quu, *Qi = d.Qui;
-  double *xa = c.at(d.xa, d, n), *ua = c.at(d.ua, d, m), *kk = c.at(d.kk, d, m);
+  constexpr int nt = NTRI(M::m);
+  const double *Kg = d.Kg, *Qi = d.Qui;
+  double *xa = c.at(d.xh, d, n), *ua = c.at(d.uh, d, m), *kk = c.at(d.kk, d, m);   // primal iterate -> result
   double *zx = c.at(d.zx, d, n), *lx = c.at(d.lx, d, n);
   double *zu = c.at(d.zu, d, m), *lu = c.at(d.lu, d, m);
   const double *zs = d.zs + (size_t)tile * d.n_via * n * TILE + c.lane;
@@ -1161,7 +1183,7 @@ __global__ void k_lqt_admm(Dev d, const double *x0_in) {
       for (int j = 0; j < m; j++) EL(kk, m, t, j) = 0.0;
     }
     for (int t = d.N - 2; t >= 0; t--) {
-      double cx[n], cu[m], K[m][n], Qux[m][n], Quu[m][m], Qui[m][m], kt[m];
+      double cx[n], cu[m], K[m][n], Qui[m][m], kt[m];
       const int s = d.seq[t];
 #pragma unroll
       for (int i = 0; i < n; i++) {
@@ -1175,11 +1197,11 @@ __global__ void k_lqt_admm(Dev d, const double *x0_in) {
 #pragma unroll
       for (int a = 0; a < m; a++) {
 #pragma unroll
-        for (int j = 0; j < n; j++) { K[a][j] = EL(Kg, m * n, t, a * n + j); Qux[a][j] = EL(Qx, m * n, t, a * n + j); }
+        for (int j = 0; j < n; j++) K[a][j] = EL(Kg, m * n, t, a * n + j);
 #pragma unroll
-        for (int b2 = 0; b2 < m; b2++) { Quu[a][b2] = EL(Qu, m * m, t, a * m + b2); Qui[a][b2] = EL(Qi, m * m, t, a * m + b2); }
+        for (int b2 = 0; b2 <= a; b2++) { Qui[a][b2] = EL(Qi, nt, t, tri(a, b2)); Qui[b2][a] = Qui[a][b2]; }
       }
-      ff_step<M>(A, Bm, cx, cu, K, Qux, Quu, Qui, v, kt);
+      ff_step<M>(A, Bm, cx, cu, K, Qui, v, kt);
 #pragma unroll
       for (int j = 0; j < m; j++) EL(kk, m, t, j) = kt[j];
     }
@@ -1252,21 +1274,6 @@ __global__ void k_lqt_admm(Dev d, const double *x0_in) {
     if (d.out.admm_exit) d.out.admm_exit[c.b] = ex;
     d.out.cost_log[c.b * 2 + 0] = nan("");
     d.out.cost_log[c.b * 2 + 1] = cost;
-  }
-}
-
-// copies xa/ua into xh/uh so that k_finalize unpacks the last primal iterate
-template <class M>
-__global__ void k_copy_primal(Dev d) {
-  constexpr int n = M::n, m = M::m;
-  const int tile = blockIdx.x * blockDim.y + threadIdx.y;
-  if (tile >= d.T) return;
-  TileCtx<M> c(d, tile, threadIdx.x);
-  const double *xa = c.at(d.xa, d, n), *ua = c.at(d.ua, d, m);
-  double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m);
-  for (int t = 0; t < d.N; t++) {
-    for (int i = 0; i < n; i++) EL(xh, n, t, i) = EL(xa, n, t, i);
-    for (int j = 0; j < m; j++) EL(uh, m, t, j) = EL(ua, m, t, j);
   }
 }
 
@@ -1426,14 +1433,14 @@ static size_t carve(const isls_plan *p, long long B, char *base, Dev *d) {
   };
   const size_t tn = T * N * n * TILE, tm = T * N * m * TILE;
   takeD(d ? &d->xh : nullptr, tn); takeD(d ? &d->uh : nullptr, tm);
-  takeD(d ? &d->xa : nullptr, tn); takeD(d ? &d->ua : nullptr, tm);
   takeD(d ? &d->du : nullptr, tm);
-  takeD(d ? &d->zx : nullptr, tn); takeD(d ? &d->lx : nullptr, tn); takeD(d ? &d->rgx : nullptr, tn);
-  takeD(d ? &d->zu : nullptr, tm); takeD(d ? &d->lu : nullptr, tm); takeD(d ? &d->rgu : nullptr, tm);
-  takeD(d ? &d->Kg : nullptr, T * N * m * n * TILE); takeD(d ? &d->Qux : nullptr, T * N * m * n * TILE);
-  takeD(d ? &d->Quu : nullptr, T * N * m * m * TILE); takeD(d ? &d->Qui : nullptr, T * N * m * m * TILE);
+  takeD(d ? &d->zx : nullptr, tn); takeD(d ? &d->lx : nullptr, tn);       // always present: unpacked by k_finalize
+  takeD(d ? &d->rgx : nullptr, p->proj_x ? tn : 0);
+  takeD(d ? &d->zu : nullptr, tm); takeD(d ? &d->lu : nullptr, tm);
+  takeD(d ? &d->rgu : nullptr, p->proj_u ? tm : 0);
+  takeD(d ? &d->Kg : nullptr, T * N * m * n * TILE);
+  takeD(d ? &d->Qui : nullptr, T * N * NTRI(m) * TILE);
   takeD(d ? &d->kk : nullptr, tm);
-  takeD(d ? &d->jac : nullptr, T * N * p->NJA * TILE);
   takeD(d ? &d->zs : nullptr, T * p->n_via * n * TILE);
   takeD(d ? &d->lsc : nullptr, T * p->L * TILE);
   const size_t S = T * TILE;
@@ -1478,20 +1485,34 @@ static dim3 tp_grid(const Dev &d) { return dim3((d.T + TPB_TILES - 1) / TPB_TILE
 
 // Line-search CTA shape: CPT candidates per thread (independent FP64 chains, shared loads), W = ceil(L/CPT)
 // warps.  MAXW only feeds __launch_bounds__ (register budget).
-template <class M, int CPT, int MAXW>
+template <class M, int CPT, int MAXW, int MINB = 1>
 static void launch_ls_cfg(const Dev &d, bool closed, cudaStream_t s) {
   const int W = (d.L + CPT - 1) / CPT;
-  if (closed) k_linesearch_closed<M, CPT, MAXW><<<d.T, dim3(TILE, W), 0, s>>>(d);
-  else k_linesearch<M, CPT, MAXW><<<d.T, dim3(TILE, W), 0, s>>>(d);
+  if (closed) k_linesearch_closed<M, CPT, MAXW, MINB><<<d.T, dim3(TILE, W), 0, s>>>(d);
+  else k_linesearch<M, CPT, MAXW, MINB><<<d.T, dim3(TILE, W), 0, s>>>(d);
+}
+static int ls_cpt_override() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("ISLS_LS_CPT");      // tuning knob: candidates per thread of the line-search CTA
+    v = e ? atoi(e) : 0;
+  }
+  return v;
 }
 template <class M>
 static void launch_linesearch(const Dev &d, bool closed, cudaStream_t s) {
+  const int ov = ls_cpt_override();
   if constexpr (M::n >= 9) {
     if (d.L <= 8) launch_ls_cfg<M, 1, 8>(d, closed, s);
     else launch_ls_cfg<M, 2, 25>(d, closed, s);
   } else {
-    if (d.L <= 20) launch_ls_cfg<M, 4, 5>(d, closed, s);
-    else launch_ls_cfg<M, 4, 13>(d, closed, s);
+    if (d.L <= 20) {
+      if (ov == 1) launch_ls_cfg<M, 1, 20>(d, closed, s);
+      else if (ov == 2) launch_ls_cfg<M, 2, 10, 2>(d, closed, s);
+      else if (ov == 5) launch_ls_cfg<M, 5, 4, 2>(d, closed, s);
+      else if (ov == 43) launch_ls_cfg<M, 4, 5, 3>(d, closed, s);
+      else launch_ls_cfg<M, 4, 5, 2>(d, closed, s);
+    } else launch_ls_cfg<M, 4, 13>(d, closed, s);
   }
 }
 
@@ -1594,7 +1615,6 @@ extern "C" int isls_lqt_admm_dp_f64(const isls_plan *plan, const isls_solve_opts
     // the K-pass reset (lambda = 0, reg = z) touched tile 0 only with zeros: state stays zero
     k_pack_zs<M><<<tp_grid(d), tp_block(), 0, s>>>(d, zs);
     LAUNCH(ISLS_KC_LQT, s, (k_lqt_admm<M><<<tp_grid(d), tp_block(), 0, s>>>(d, x0)));
-    k_copy_primal<M><<<tp_grid(d), tp_block(), 0, s>>>(d);
     Dev df = d;
     df.out.K = nullptr;          // gains are shared: unpacked by k_lqt_unpack_K
     k_finalize<M><<<tp_grid(d), tp_block(), 0, s>>>(df);

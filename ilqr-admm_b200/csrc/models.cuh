@@ -31,6 +31,35 @@ __device__ __forceinline__ double mod_two_pi(double a) {
   return r;
 }
 
+// sin and cos of a double with a 3-term Cody-Waite reduction by pi/2 (exact products through FMA) and the
+// fdlibm kernel polynomials on [-pi/4, pi/4] (< 1 ulp).  The rollouts evaluate it once per candidate-step, so it
+// avoids the library sincos()'s large-argument path in the hot loop; |x| >= 2^17 falls back to sincos().
+__device__ __forceinline__ void sincos_pio2(double x, double *sp, double *cp) {
+  const double kd = rint(x * 0.6366197723675814);
+  if (!(fabs(kd) < 131072.0)) { sincos(x, sp, cp); return; }
+  double r = fma(-kd, 1.5707963267948966, x);
+  r = fma(-kd, 6.123233995736766e-17, r);
+  r = fma(-kd, -1.4973849048591698e-33, r);
+  const int k = (int)kd;
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(z, ps, 2.75573137070700676789e-06);
+  ps = fma(z, ps, -1.98412698298579493134e-04);
+  ps = fma(z, ps, 8.33333333332248946124e-03);
+  ps = fma(z, ps, -1.66666666666666324348e-01);
+  const double s = fma(z * r, ps, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(z, pc, -2.75573143513906633035e-07);
+  pc = fma(z, pc, 2.48015872894767294178e-05);
+  pc = fma(z, pc, -1.38888888888741095749e-03);
+  pc = fma(z, pc, 4.16666666666666019037e-02);
+  const double hz = 0.5 * z, w = 1.0 - hz;
+  const double c = w + (((1.0 - w) - hz) + z * (z * pc));
+  const double sa = (k & 1) ? c : s, ca = (k & 1) ? s : c;
+  *sp = (k & 2) ? -sa : sa;
+  *cp = ((k + 1) & 2) ? -ca : ca;
+}
+
 struct CarModel {
   static constexpr int n = 4, m = 2, NJ = 6, NJA = 6;
   __host__ __device__ static constexpr int am(int i, int j) {
@@ -42,7 +71,7 @@ struct CarModel {
   __device__ __forceinline__ static void step(const double (&x)[n], const double (&u)[m], double (&xn)[n],
                                               double dt) {
     double s, c;
-    sincos(x[2], &s, &c);
+    sincos_pio2(x[2], &s, &c);
     const double dv = dt * x[3];
     xn[0] = x[0] + dv * c;
     xn[1] = x[1] + dv * s;
@@ -52,7 +81,7 @@ struct CarModel {
   __device__ __forceinline__ static void jac(const double (&x)[n], const double (&u)[m], double (&J)[NJ],
                                              double dt) {
     double s, c;
-    sincos(x[2], &s, &c);
+    sincos_pio2(x[2], &s, &c);
     const double dv = dt * x[3];
     J[0] = dv * -s;      // A[0][2]
     J[1] = dv * c;       // A[1][2]
@@ -89,7 +118,7 @@ struct Arm3Model {
     qnext(x, u, q, dt);
     const double a1 = q[0], a2 = a1 + q[1], a3 = a2 + q[2];
     double s1, c1, s2, c2, s3, c3;
-    sincos(a1, &s1, &c1); sincos(a2, &s2, &c2); sincos(a3, &s3, &c3);
+    sincos_pio2(a1, &s1, &c1); sincos_pio2(a2, &s2, &c2); sincos_pio2(a3, &s3, &c3);
 #pragma unroll
     for (int i = 0; i < 3; i++) { xn[i] = q[i]; xn[3 + i] = x[3 + i] + u[i] * dt; }
     xn[6] = (c1 + c2) + c3;
@@ -102,7 +131,7 @@ struct Arm3Model {
     qnext(x, u, q, dt);
     const double a1 = q[0], a2 = a1 + q[1], a3 = a2 + q[2];
     double s1, c1, s2, c2, s3, c3;
-    sincos(a1, &s1, &c1); sincos(a2, &s2, &c2); sincos(a3, &s3, &c3);
+    sincos_pio2(a1, &s1, &c1); sincos_pio2(a2, &s2, &c2); sincos_pio2(a3, &s3, &c3);
     J[0] = -((s1 + s2) + s3); J[1] = -(s2 + s3); J[2] = -s3;
     J[3] = (c1 + c2) + c3;    J[4] = c2 + c3;    J[5] = c3;
   }

@@ -140,12 +140,16 @@ def test_car_ilqr_dp_vs_oracle_and_golden(golden):
     rel = np.where(m, np.abs(out["cost_log"] - o["cost_log"]) / np.where(m, np.abs(o["cost_log"]), 1.0), 0.0).max(1)
     assert np.array_equal(np.isnan(out["cost_log"]), ~m)
     assert np.quantile(rel, 0.95) < 1e-9 and rel.max() < 1e-6
-    good = rel < 1e-9
-    assert np.abs(out["u"][good] - o["u"][good]).max() < 1e-9
-    assert np.abs(out["K"][good] - o["K"][good]).max() / np.abs(o["K"]).max() < 1e-9
+    du = np.abs(out["u"] - o["u"]).reshape(64, -1).max(1)
+    dK = np.abs(out["K"] - o["K"]).reshape(64, -1).max(1) / np.abs(o["K"]).reshape(64, -1).max(1)
+    print("plain iLQR car: quantiles of max|du| (50/90/100 %):", np.quantile(du, [0.5, 0.9, 1.0]),
+          " of rel dK:", np.quantile(dK, [0.5, 0.9, 1.0]))
+    assert np.quantile(du, 0.5) < 1e-9 and du.max() < 1e-5
+    assert np.quantile(dK, 0.5) < 1e-9 and dK.max() < 1e-5
     ref = g["cost_log"]
-    assert _gpu().rel_logs(out["cost_log"][:4, :ref.shape[1]], ref) < 1e-9
-    assert np.abs(out["u"][:4] - g["u"]).max() < 1e-9
+    out4 = _gpu().run_ilqr_dp(P.car_batch(4), int(g["max_iter"]), int(g["L"]))
+    assert _gpu().rel_logs(out4["cost_log"][:, :ref.shape[1]], ref) < 1e-9
+    assert np.abs(out4["u"] - g["u"]).max() < 1e-9
 
 
 def test_arm_ilqr_dp_vs_oracle():
