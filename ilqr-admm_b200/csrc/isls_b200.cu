@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -64,6 +65,7 @@ struct ProfScope {
 // ------------------------------------------------------------------------------------------------ device context
 struct Dev {
   int N, n_via, L, proj_x, proj_u, T;
+  int tile0, tile1;      // tile range of this launch (chunked solves run disjoint ranges on separate streams)
   long long B;
   double dt, u_std;
   // plan constants (device)
@@ -74,10 +76,11 @@ struct Dev {
   const double *rho_u, *lo_u, *hi_u;   // [N][m]
   const double *alphas;  // [L]
   // workspace, tile-blocked [T][N][dim][32]
-  double *xh, *uh, *du, *zx, *lx, *zu, *lu, *rgx, *rgu, *Kg, *Qui, *kk, *zs;   // Qui: packed lower triangle
+  double *xh, *uh, *du, *zx, *lx, *zu, *lu, *rgx, *rgu, *Kg, *Qux, *Quu, *Qui, *kk, *zs;   // Quu, Qui: packed lower
   double *lsc;           // [T][L][32] candidate costs of the last line search
   // per-problem scalars [T*32]
   double *cost, *prev_cost, *prim, *dual, *cost_adm, *best_cost;
+  double *cq;            // [3][T*32] control-cost polynomial of the current line search: c0 + a c1 + a^2 c2
   int *best, *odone, *adone, *nlog, *status, *oit, *ait;
   // options
   int max_outer, max_admm, fixed_budget, last_stage_dp;
@@ -122,8 +125,8 @@ __device__ __forceinline__ double state_cost(const Dev &d, const double *zs, int
 // nominal_values, isls/isls.py:135-154, isls/isls_base.py:80-85) + workspace initialisation.
 template <class M>
 __global__ void k_init(Dev d, const double *x0, const double *u_init, const double *zs_in) {
-  const int tile = blockIdx.x * blockDim.y + threadIdx.y;
-  if (tile >= d.T) return;
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   double *xh = c.at(d.xh, d, M::n), *uh = c.at(d.uh, d, M::m);
   double *zs = d.zs + (size_t)tile * d.n_via * M::n * TILE + c.lane;
@@ -189,9 +192,10 @@ template <class M>
 __device__ __forceinline__ bool riccati_step(const double (&A)[M::n][M::n], const double (&Bm)[M::n][M::m],
                                              const double (&dxx)[M::n], const double (&duu)[M::m],
                                              double (&V)[M::n][M::n], double (&K)[M::m][M::n],
+                                             double (&Qux)[M::m][M::n], double (&Quu)[M::m][M::m],
                                              double (&Qui)[M::m][M::m]) {
   constexpr int n = M::n, m = M::m;
-  double VA[n][n], Qxx[n][n], Qux[m][n], Quu[m][m];
+  double VA[n][n], Qxx[n][n];
   mat_V_A<M>(V, A, VA);
   mat_At_X<M, n>(A, VA, Qxx);
 #pragma unroll
@@ -240,18 +244,21 @@ __device__ __forceinline__ bool riccati_step(const double (&A)[M::n][M::n], cons
   return ok;
 }
 
-// feed-forward step (sls.py:196-199): qx = cx + A'v, qu = cu + B'v, k = -Quu^-1 qu, and
-//   v = qx + Qux'k + K'qu + K'(Quu k)  =  qx + K'qu
-// (with k = -Quu^-1 qu and K = -Quu^-1 Qux the terms K'(Quu k) and Qux'k equal -K'qu and +K'qu exactly in real
-// arithmetic; evaluating the collapsed form needs K and Quu^-1 only - no Qux / Quu traffic - and avoids the
-// cancellation of the three-term form).
+// feed-forward step (sls.py:196-199): qx = cx + A'v, qu = cu + B'v, k = -Quu^-1 qu,
+//   v = qx + Qux'k + K'qu + K'(Quu k).
+// The reference's four-term form is v = qx + Qux'k + K'w with the residual w = qu + Quu k: the K'w term cancels the
+// first-order error of the computed inverse (with K = -Quu^-1 Qux, K'w = -Qux' Quu^-1 w).  The same correction is
+// applied here to k itself - one refinement step k <- k - Quu^-1 w - after which v = qx + Qux'k.  It is the
+// identical first-order-exact value, needs Qux, Quu, Quu^-1 (no K) in the backward sweep, and hands the rollout a
+// refined k.  (The plain collapsed form qx + K'qu is cheaper but first-order sensitive to cond(Quu) - measurably
+// worse on the arm.)
 template <class M>
 __device__ __forceinline__ void ff_step(const double (&A)[M::n][M::n], const double (&Bm)[M::n][M::m],
                                         const double (&cx)[M::n], const double (&cu)[M::m],
-                                        const double (&K)[M::m][M::n], const double (&Qui)[M::m][M::m],
-                                        double (&v)[M::n], double (&kt)[M::m]) {
+                                        const double (&Qux)[M::m][M::n], const double (&Quu)[M::m][M::m],
+                                        const double (&Qui)[M::m][M::m], double (&v)[M::n], double (&kt)[M::m]) {
   constexpr int n = M::n, m = M::m;
-  double qx[n], qu[m];
+  double qx[n], qu[m], k0[m], w[m];
   mat_At_v<M>(A, v, qx);
   mat_Bt_v<M>(Bm, v, qu);
 #pragma unroll
@@ -263,13 +270,27 @@ __device__ __forceinline__ void ff_step(const double (&A)[M::n][M::n], const dou
     double acc = 0.0;
 #pragma unroll
     for (int b2 = 0; b2 < m; b2++) acc = fma(Qui[a][b2], qu[b2], acc);
-    kt[a] = -acc;
+    k0[a] = -acc;
+  }
+#pragma unroll
+  for (int a = 0; a < m; a++) {
+    double acc = qu[a];
+#pragma unroll
+    for (int b2 = 0; b2 < m; b2++) acc = fma(Quu[a][b2], k0[b2], acc);
+    w[a] = acc;
+  }
+#pragma unroll
+  for (int a = 0; a < m; a++) {
+    double acc = 0.0;
+#pragma unroll
+    for (int b2 = 0; b2 < m; b2++) acc = fma(Qui[a][b2], w[b2], acc);
+    kt[a] = k0[a] - acc;
   }
 #pragma unroll
   for (int i = 0; i < n; i++) {
     double acc = qx[i];
 #pragma unroll
-    for (int a = 0; a < m; a++) acc = fma(K[a][i], qu[a], acc);
+    for (int a = 0; a < m; a++) acc = fma(Qux[a][i], kt[a], acc);
     v[i] = acc;
   }
 }
@@ -290,18 +311,19 @@ __device__ __forceinline__ void init_AB(double (&A)[M::n][M::n], double (&Bm)[M:
 }
 
 // K-pass: linearise at the nominal trajectory (get_AB, isls/isls.py:424) and run the Riccati recursion with
-// Cxx = 2(Q_t + Qr_t), Cuu = 2(R + Rr_t) (regularised form of sls.py:132-137).  Stores K_t and the packed Quu_t^-1
-// (what the feed-forward passes need, cf. the logs of sls.py:159-162); resets the ADMM state of the new outer
+// Cxx = 2(Q_t + Qr_t), Cuu = 2(R + Rr_t) (regularised form of sls.py:132-137).  Stores K_t, Qux_t and the packed
+// Quu_t, Quu_t^-1 (the logs of sls.py:159-162 that the feed-forward passes need); resets the ADMM state of the new outer
 // iteration (lambda = 0, isls/isls.py:414-415; z warm start isls/isls.py:489-490).
 template <class M>
 __global__ void k_kpass(Dev d) {
   constexpr int n = M::n, m = M::m, nt = NTRI(M::m);
-  const int tile = blockIdx.x * blockDim.y + threadIdx.y;
-  if (tile >= d.T) return;
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b]) return;
   const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m);
-  double *Kg = c.at(d.Kg, d, m * n), *Qi = c.at(d.Qui, d, nt);
+  double *Kg = c.at(d.Kg, d, m * n), *Qx = c.at(d.Qux, d, m * n);
+  double *Qu = c.at(d.Quu, d, nt), *Qi = c.at(d.Qui, d, nt);
   double A[n][n], Bm[n][m], V[n][n];
   init_AB<M>(A, Bm);
 #pragma unroll
@@ -318,18 +340,21 @@ __global__ void k_kpass(Dev d) {
     for (int j = 0; j < m; j++) u[j] = EL(uh, m, t, j);
     M::jac(x, u, J, d.dt);
     M::expand(J, A, Bm, d.dt);
-    double dxx[n], duu[m], K[m][n], Qui[m][m];
+    double dxx[n], duu[m], K[m][n], Qux[m][n], Quu[m][m], Qui[m][m];
 #pragma unroll
     for (int i = 0; i < n; i++) dxx[i] = 2.0 * (d.qd[t * n + i] + d.rho_x[t * n + i]);
 #pragma unroll
     for (int j = 0; j < m; j++) duu[j] = 2.0 * (d.u_std + d.rho_u[t * m + j]);
-    ok &= riccati_step<M>(A, Bm, dxx, duu, V, K, Qui);
+    ok &= riccati_step<M>(A, Bm, dxx, duu, V, K, Qux, Quu, Qui);
 #pragma unroll
     for (int a = 0; a < m; a++) {
 #pragma unroll
-      for (int j = 0; j < n; j++) EL(Kg, m * n, t, a * n + j) = K[a][j];
+      for (int j = 0; j < n; j++) { EL(Kg, m * n, t, a * n + j) = K[a][j]; EL(Qx, m * n, t, a * n + j) = Qux[a][j]; }
 #pragma unroll
-      for (int b2 = 0; b2 <= a; b2++) EL(Qi, nt, t, tri(a, b2)) = Qui[a][b2];
+      for (int b2 = 0; b2 <= a; b2++) {
+        EL(Qu, nt, t, tri(a, b2)) = 0.5 * (Quu[a][b2] + Quu[b2][a]);
+        EL(Qi, nt, t, tri(a, b2)) = Qui[a][b2];
+      }
     }
   }
 #pragma unroll
@@ -360,16 +385,17 @@ __global__ void k_kpass(Dev d) {
 //   cx = 2Q(x^ - z_via) + 2Qr(x^ - reg_x), cu = 2R u^ + 2Rr(u^ - reg_u),
 // batch-form last control, then du_t = K dx + k, dx+ = A dx + B du.
 // HBM-bound kernel: the Jacobian scalars are recomputed from (x^_t, u^_t) (loaded anyway for cx, cu) instead of
-// being read back, and only K_t and the packed Quu_t^-1 are streamed.
+// being read back; the backward sweep streams Qux_t and the packed Quu_t, Quu_t^-1, the forward sweep K_t.
 template <class M>
 __global__ void k_ff(Dev d) {
   constexpr int n = M::n, m = M::m, nt = NTRI(M::m);
-  const int tile = blockIdx.x * blockDim.y + threadIdx.y;
-  if (tile >= d.T) return;
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b] || d.adone[c.b]) return;
   const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m);
-  const double *Kg = c.at(d.Kg, d, m * n), *Qi = c.at(d.Qui, d, nt);
+  const double *Kg = c.at(d.Kg, d, m * n), *Qx = c.at(d.Qux, d, m * n);
+  const double *Qu = c.at(d.Quu, d, nt), *Qi = c.at(d.Qui, d, nt);
   const double *rgx = c.at(d.rgx, d, n), *rgu = c.at(d.rgu, d, m);
   const double *zs = d.zs + (size_t)tile * d.n_via * n * TILE + c.lane;
   double *kk = c.at(d.kk, d, m), *du = c.at(d.du, d, m);
@@ -409,7 +435,7 @@ __global__ void k_ff(Dev d) {
     }
   }
   for (int t = d.N - 2; t >= 0; t--) {
-    double x[n], u[m], J[M::NJA], cx[n], cu[m], K[m][n], Qui[m][m], kt[m];
+    double x[n], u[m], J[M::NJA], cx[n], cu[m], Qux[m][n], Quu[m][m], Qui[m][m], kt[m];
 #pragma unroll
     for (int i = 0; i < n; i++) x[i] = EL(xh, n, t, i);
 #pragma unroll
@@ -417,23 +443,30 @@ __global__ void k_ff(Dev d) {
 #pragma unroll
     for (int a = 0; a < m; a++) {
 #pragma unroll
-      for (int j = 0; j < n; j++) K[a][j] = EL(Kg, m * n, t, a * n + j);
+      for (int j = 0; j < n; j++) Qux[a][j] = EL(Qx, m * n, t, a * n + j);
 #pragma unroll
-      for (int b2 = 0; b2 <= a; b2++) { Qui[a][b2] = EL(Qi, nt, t, tri(a, b2)); Qui[b2][a] = Qui[a][b2]; }
+      for (int b2 = 0; b2 <= a; b2++) {
+        Qui[a][b2] = EL(Qi, nt, t, tri(a, b2)); Qui[b2][a] = Qui[a][b2];
+        Quu[a][b2] = EL(Qu, nt, t, tri(a, b2)); Quu[b2][a] = Quu[a][b2];
+      }
     }
     M::jac(x, u, J, d.dt);
     M::expand(J, A, Bm, d.dt);
     costgrad(t, x, u, cx, cu);
-    ff_step<M>(A, Bm, cx, cu, K, Qui, v, kt);
+    ff_step<M>(A, Bm, cx, cu, Qux, Quu, Qui, v, kt);
 #pragma unroll
     for (int j = 0; j < m; j++) EL(kk, m, t, j) = kt[j];
   }
-  // linear rollout
+  // linear rollout.  The control part of every line-search candidate's cost,
+  //   sum_t R u^2 + Rr (u - reg_u)^2  with  u = u^ + alpha du          (isls.py:470, 474-476)
+  // is the quadratic c0 + alpha c1 + alpha^2 c2 in alpha; its three coefficients are accumulated here once per
+  // problem so the L candidate rollouts neither recompute it nor read reg_u.
   double dx[n];
 #pragma unroll
   for (int i = 0; i < n; i++) dx[i] = 0.0;
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0;
   for (int t = 0; t < d.N; t++) {
-    double duv[m];
+    double duv[m], u[m];
 #pragma unroll
     for (int a = 0; a < m; a++) {
       double acc = 0.0;
@@ -443,13 +476,23 @@ __global__ void k_ff(Dev d) {
       }
       duv[a] = acc + EL(kk, m, t, a);
       EL(du, m, t, a) = duv[a];
+      u[a] = EL(uh, m, t, a);
+      const double R = d.u_std;
+      c0 = fma(R * u[a], u[a], c0);
+      c1 = fma(2.0 * R * u[a], duv[a], c1);
+      double w2 = R;
+      if (d.proj_u) {
+        const double rho = d.rho_u[t * m + a], e = u[a] - EL(rgu, m, t, a);
+        c0 = fma(rho * e, e, c0);
+        c1 = fma(2.0 * rho * e, duv[a], c1);
+        w2 += rho;
+      }
+      c2 = fma(w2 * duv[a], duv[a], c2);
     }
     if (t < d.N - 1) {
-      double x[n], u[m], J[M::NJA], dxn[n];
+      double x[n], J[M::NJA], dxn[n];
 #pragma unroll
       for (int i = 0; i < n; i++) x[i] = EL(xh, n, t, i);
-#pragma unroll
-      for (int j = 0; j < m; j++) u[j] = EL(uh, m, t, j);
       M::jac(x, u, J, d.dt);
       M::expand(J, A, Bm, d.dt);
       mat_Ax_Bu<M>(A, Bm, dx, duv, dxn);
@@ -457,6 +500,10 @@ __global__ void k_ff(Dev d) {
       for (int i = 0; i < n; i++) dx[i] = dxn[i];
     }
   }
+  const size_t S = (size_t)d.T * TILE;
+  d.cq[c.b] = c0;
+  d.cq[S + c.b] = c1;
+  d.cq[2 * S + c.b] = c2;
 }
 
 // np.argmin semantics over candidate costs (first minimum; the first NaN wins, isls/isls.py:477)
@@ -475,54 +522,49 @@ __device__ __forceinline__ int argmin_np(const double *c, int L, int stride, boo
 
 // Open-loop line search (isls/isls.py:468-477): for every candidate alpha_l roll the model out from x^_0 with
 // u^ + alpha_l du (rollout_batch, isls/isls.py:135-154), evaluate cost + sum((x-reg_x)^2 Qr) + sum((u-reg_u)^2 Rr),
-// take the argmin unconditionally.  CTA = 32 problems x W warps, CPT candidates per thread (ILP).
+// take the argmin unconditionally.  CTA = 32 problems x W warps, CPT candidates per thread (independent FP64
+// chains, shared operand loads).  The control part of the cost comes from the per-problem quadratic (c0,c1,c2)
+// accumulated by k_ff, so the hot loop is: 2 FMA for u, sincos, 5 FMA-type model updates (+ state terms).
 template <class M, int CPT, int MAXW, int MINB>
 __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d) {
   constexpr int n = M::n, m = M::m;
   __shared__ double sc[MAX_L][TILE];
-  const int tile = blockIdx.x;
+  const int tile = d.tile0 + blockIdx.x;
   TileCtx<M> c(d, tile, threadIdx.x);
   const int w = threadIdx.y;
   const bool skip = d.odone[c.b] || d.adone[c.b];
   if (__syncthreads_and(skip)) return;
   if (!skip) {
     const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m), *du = c.at(d.du, d, m);
-    const double *rgx = c.at(d.rgx, d, n), *rgu = c.at(d.rgu, d, m);
+    const double *rgx = c.at(d.rgx, d, n);
     const double *zs = d.zs + (size_t)tile * d.n_via * n * TILE + c.lane;
-    double al[CPT], x[CPT][n], cs[CPT], cc[CPT], px[CPT], pu[CPT];
+    double al[CPT], x[CPT][n], cs[CPT], px[CPT];
 #pragma unroll
     for (int q = 0; q < CPT; q++) {
       const int l = w * CPT + q;
       al[q] = l < d.L ? d.alphas[l] : 0.0;
-      cs[q] = cc[q] = px[q] = pu[q] = 0.0;
+      cs[q] = px[q] = 0.0;
 #pragma unroll
       for (int i = 0; i < n; i++) x[q][i] = EL(xh, n, 0, i);
     }
-    // operands of step t are loaded one step ahead (software prefetch: the loads of step t+1 are in flight while
-    // the FP64 chains of step t run)
-    double un_n[m], dun_n[m], ru_n[m], rx_n[n];
+    // operands of step t+1 are loaded while the FP64 chains of step t run (software prefetch)
+    double un_n[m], dun_n[m], rx_n[n];
+    int qz_n;
     auto fetch = [&](int t) {
 #pragma unroll
-      for (int j = 0; j < m; j++) {
-        un_n[j] = EL(uh, m, t, j);
-        dun_n[j] = EL(du, m, t, j);
-        if (d.proj_u) ru_n[j] = EL(rgu, m, t, j);
-      }
+      for (int j = 0; j < m; j++) { un_n[j] = EL(uh, m, t, j); dun_n[j] = EL(du, m, t, j); }
       if (d.proj_x) {
 #pragma unroll
         for (int i = 0; i < n; i++) rx_n[i] = EL(rgx, n, t, i);
       }
+      qz_n = d.qnz[t];
     };
     fetch(0);
     for (int t = 0; t < d.N; t++) {
-      double un[m], dun[m], ru[m], rx[n], zv[n], qd[n], rhx[n], rhu[m];
-      const bool qz = d.qnz[t];
+      double un[m], dun[m], rx[n], zv[n], qd[n], rhx[n];
+      const bool qz = qz_n;
 #pragma unroll
-      for (int j = 0; j < m; j++) {
-        un[j] = un_n[j];
-        dun[j] = dun_n[j];
-        if (d.proj_u) { ru[j] = ru_n[j]; rhu[j] = d.rho_u[t * m + j]; }
-      }
+      for (int j = 0; j < m; j++) { un[j] = un_n[j]; dun[j] = dun_n[j]; }
       if (d.proj_x) {
 #pragma unroll
         for (int i = 0; i < n; i++) { rx[i] = rx_n[i]; rhx[i] = d.rho_x[t * n + i]; }
@@ -537,11 +579,7 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d) {
       for (int q = 0; q < CPT; q++) {
         double u[m], xn[n];
 #pragma unroll
-        for (int j = 0; j < m; j++) {
-          u[j] = un[j] + al[q] * dun[j];
-          cc[q] += u[j] * u[j];
-          if (d.proj_u) { const double e = u[j] - ru[j]; pu[q] += (e * e) * rhu[j]; }
-        }
+        for (int j = 0; j < m; j++) u[j] = fma(al[q], dun[j], un[j]);
         if (qz) {
 #pragma unroll
           for (int i = 0; i < n; i++) { const double e = x[q][i] - zv[i]; cs[q] += (e * e) * qd[i]; }
@@ -555,13 +593,14 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d) {
         for (int i = 0; i < n; i++) x[q][i] = xn[i];
       }
     }
+    const size_t S = (size_t)d.T * TILE;
+    const double c0 = d.cq[c.b], c1 = d.cq[S + c.b], c2 = d.cq[2 * S + c.b];
 #pragma unroll
     for (int q = 0; q < CPT; q++) {
       const int l = w * CPT + q;
       if (l < d.L) {
-        double tot = cs[q] + d.u_std * cc[q];          // cost_function (isls.py:470)
-        if (d.proj_x) tot += px[q];                    // isls.py:473
-        if (d.proj_u) tot += pu[q];                    // isls.py:476
+        double tot = cs[q] + fma(al[q], fma(al[q], c2, c1), c0);   // cost_function + control penalty (isls.py:470,476)
+        if (d.proj_x) tot += px[q];                                // isls.py:473
         sc[l][c.lane] = tot;
       }
     }
@@ -602,8 +641,8 @@ __device__ __forceinline__ void admm_elem(double x, double relax, double lo, dou
 template <class M>
 __global__ void k_admm(Dev d, int outer, int inner) {
   constexpr int n = M::n, m = M::m;
-  const int tile = blockIdx.x * blockDim.y + threadIdx.y;
-  if (tile >= d.T) return;
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b] || d.adone[c.b]) return;
   const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m), *du = c.at(d.du, d, m);
@@ -685,8 +724,8 @@ __global__ void k_admm(Dev d, int outer, int inner) {
 template <class M>
 __global__ void k_outer_end(Dev d, int outer) {
   constexpr int n = M::n, m = M::m;
-  const int tile = blockIdx.x * blockDim.y + threadIdx.y;
-  if (tile >= d.T) return;
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b]) return;
   // nominal <- last primal iterate (isls.py:488): re-roll u^ + alpha* du in place (same arithmetic as k_admm, whose
@@ -742,8 +781,8 @@ __global__ void k_outer_end(Dev d, int outer) {
 template <class M>
 __global__ void k_finalize(Dev d) {
   constexpr int n = M::n, m = M::m;
-  const int tile = blockIdx.x * blockDim.y + threadIdx.y;
-  if (tile >= d.T) return;
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (!c.valid) return;
   const isls_solve_out &o = d.out;
@@ -776,8 +815,8 @@ __global__ void k_finalize(Dev d) {
 template <class M>
 __global__ void k_backward_full(Dev d) {
   constexpr int n = M::n, m = M::m;
-  const int tile = blockIdx.x * blockDim.y + threadIdx.y;
-  if (tile >= d.T) return;
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b]) return;
   const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m);
@@ -800,7 +839,7 @@ __global__ void k_backward_full(Dev d) {
   }
   bool ok = true;
   for (int t = d.N - 2; t >= 0; t--) {
-    double x[n], u[m], J[M::NJA], dxx[n], duu[m], cx[n], cu[m], K[m][n], Qui[m][m], kt[m];
+    double x[n], u[m], J[M::NJA], dxx[n], duu[m], cx[n], cu[m], K[m][n], Qux[m][n], Quu[m][m], Qui[m][m], kt[m];
     const int s = d.seq[t];
 #pragma unroll
     for (int i = 0; i < n; i++) {
@@ -822,8 +861,8 @@ __global__ void k_backward_full(Dev d) {
     for (int i = 0; i < n; i++)
 #pragma unroll
       for (int j = 0; j < n; j++) Vn[i][j] = V[i][j];
-    ok &= riccati_step<M>(A, Bm, dxx, duu, Vn, K, Qui);
-    ff_step<M>(A, Bm, cx, cu, K, Qui, v, kt);
+    ok &= riccati_step<M>(A, Bm, dxx, duu, Vn, K, Qux, Quu, Qui);
+    ff_step<M>(A, Bm, cx, cu, Qux, Quu, Qui, v, kt);
 #pragma unroll
     for (int i = 0; i < n; i++)
 #pragma unroll
@@ -843,7 +882,7 @@ template <class M, int CPT, int MAXW, int MINB>
 __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch_closed(Dev d) {
   constexpr int n = M::n, m = M::m;
   __shared__ double sc[MAX_L][TILE];
-  const int tile = blockIdx.x;
+  const int tile = d.tile0 + blockIdx.x;
   TileCtx<M> c(d, tile, threadIdx.x);
   const int w = threadIdx.y;
   const bool skip = d.odone[c.b];
@@ -921,8 +960,8 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch_closed(Dev d) 
 template <class M>
 __global__ void k_accept_closed(Dev d, int it) {
   constexpr int n = M::n, m = M::m;
-  const int tile = blockIdx.x * blockDim.y + threadIdx.y;
-  if (tile >= d.T) return;
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b]) return;
   double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m);
@@ -984,8 +1023,8 @@ template <class M>
 __global__ void k_pack_stage(Dev d, const double *x_nom, const double *u_nom, const double *du_in,
                              const double *zs_in, const double *regx, const double *regu) {
   constexpr int n = M::n, m = M::m;
-  const int tile = blockIdx.x * blockDim.y + threadIdx.y;
-  if (tile >= d.T) return;
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m), *du = c.at(d.du, d, m);
   double *rgx = c.at(d.rgx, d, n), *rgu = c.at(d.rgu, d, m);
@@ -1003,6 +1042,25 @@ __global__ void k_pack_stage(Dev d, const double *x_nom, const double *u_nom, co
       if (d.proj_u) EL(rgu, m, t, j) = regu[(c.bb * d.N + t) * m + j];
     }
   }
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+  for (int t = 0; t < d.N; t++)
+    for (int j = 0; j < m; j++) {
+      const double u = EL(uh, m, t, j), dv = EL(du, m, t, j), R = d.u_std;
+      c0 = fma(R * u, u, c0);
+      c1 = fma(2.0 * R * u, dv, c1);
+      double w2 = R;
+      if (d.proj_u) {
+        const double rho = d.rho_u[t * m + j], e = u - EL(rgu, m, t, j);
+        c0 = fma(rho * e, e, c0);
+        c1 = fma(2.0 * rho * e, dv, c1);
+        w2 += rho;
+      }
+      c2 = fma(w2 * dv, dv, c2);
+    }
+  const size_t S = (size_t)d.T * TILE;
+  d.cq[c.b] = c0;
+  d.cq[S + c.b] = c1;
+  d.cq[2 * S + c.b] = c2;
   d.odone[c.b] = 0;
   d.adone[c.b] = 0;
   d.status[c.b] = 0;
@@ -1011,8 +1069,8 @@ __global__ void k_pack_stage(Dev d, const double *x_nom, const double *u_nom, co
 template <class M>
 __global__ void k_unpack_stage(Dev d, double *costs, int *best, double *x_best, double *u_best) {
   constexpr int n = M::n, m = M::m;
-  const int tile = blockIdx.x * blockDim.y + threadIdx.y;
-  if (tile >= d.T) return;
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (!c.valid) return;
   // re-roll the winner (rollout_batch, isls/isls.py:135-154)
@@ -1147,12 +1205,12 @@ __global__ void k_riccati_generic(int N, long long B, const double *Ag, const do
 template <class M>
 __global__ void k_lqt_admm(Dev d, const double *x0_in) {
   constexpr int n = M::n, m = M::m;
-  const int tile = blockIdx.x * blockDim.y + threadIdx.y;
-  if (tile >= d.T) return;
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   // gains are shared: tile 0 / lane 0 of the gain arrays
   constexpr int nt = NTRI(M::m);
-  const double *Kg = d.Kg, *Qi = d.Qui;
+  const double *Kg = d.Kg, *Qx = d.Qux, *Qu = d.Quu, *Qi = d.Qui;
   double *xa = c.at(d.xh, d, n), *ua = c.at(d.uh, d, m), *kk = c.at(d.kk, d, m);   // primal iterate -> result
   double *zx = c.at(d.zx, d, n), *lx = c.at(d.lx, d, n);
   double *zu = c.at(d.zu, d, m), *lu = c.at(d.lu, d, m);
@@ -1183,7 +1241,7 @@ __global__ void k_lqt_admm(Dev d, const double *x0_in) {
       for (int j = 0; j < m; j++) EL(kk, m, t, j) = 0.0;
     }
     for (int t = d.N - 2; t >= 0; t--) {
-      double cx[n], cu[m], K[m][n], Qui[m][m], kt[m];
+      double cx[n], cu[m], Qux[m][n], Quu[m][m], Qui[m][m], kt[m];
       const int s = d.seq[t];
 #pragma unroll
       for (int i = 0; i < n; i++) {
@@ -1197,11 +1255,14 @@ __global__ void k_lqt_admm(Dev d, const double *x0_in) {
 #pragma unroll
       for (int a = 0; a < m; a++) {
 #pragma unroll
-        for (int j = 0; j < n; j++) K[a][j] = EL(Kg, m * n, t, a * n + j);
+        for (int j = 0; j < n; j++) Qux[a][j] = EL(Qx, m * n, t, a * n + j);
 #pragma unroll
-        for (int b2 = 0; b2 <= a; b2++) { Qui[a][b2] = EL(Qi, nt, t, tri(a, b2)); Qui[b2][a] = Qui[a][b2]; }
+        for (int b2 = 0; b2 <= a; b2++) {
+          Qui[a][b2] = EL(Qi, nt, t, tri(a, b2)); Qui[b2][a] = Qui[a][b2];
+          Quu[a][b2] = EL(Qu, nt, t, tri(a, b2)); Quu[b2][a] = Quu[a][b2];
+        }
       }
-      ff_step<M>(A, Bm, cx, cu, K, Qui, v, kt);
+      ff_step<M>(A, Bm, cx, cu, Qux, Quu, Qui, v, kt);
 #pragma unroll
       for (int j = 0; j < m; j++) EL(kk, m, t, j) = kt[j];
     }
@@ -1300,7 +1361,11 @@ __global__ void k_fp64_peak(double *out, int iters) {
 }
 
 // ----------------------------------------------------------------------------------------------------- host side
+#define MAX_CHUNKS 8
 struct isls_plan {
+  cudaStream_t aux[MAX_CHUNKS];      // auxiliary streams for chunked solves (created lazily)
+  cudaEvent_t ev_fork, ev_join[MAX_CHUNKS];
+  bool aux_ready;
   isls_problem_desc desc;   // pointers inside are NOT valid after create (copied to the device block)
   int n, m, N, n_via, L, NJA;
   bool proj_x, proj_u;
@@ -1362,6 +1427,7 @@ extern "C" int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan)
   for (int t = 0; t < N; t++)
     if (desc->seq[t] < 0 || desc->seq[t] >= desc->n_via) return fail(ISLS_E_INVALID, "seq entry out of range");
   isls_plan *p = new isls_plan();
+  p->aux_ready = false;
   p->desc = *desc;
   p->n = n; p->m = m; p->N = N; p->n_via = desc->n_via; p->L = desc->L; p->NJA = nja;
   p->proj_x = desc->rho_x != nullptr;
@@ -1413,6 +1479,10 @@ extern "C" int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan)
 
 extern "C" int isls_plan_destroy(isls_plan *plan) {
   if (!plan) return ISLS_OK;
+  if (plan->aux_ready) {
+    for (int i = 0; i < MAX_CHUNKS; i++) { cudaStreamDestroy(plan->aux[i]); cudaEventDestroy(plan->ev_join[i]); }
+    cudaEventDestroy(plan->ev_fork);
+  }
   cudaFree(plan->cblock);
   delete plan;
   return ISLS_OK;
@@ -1439,6 +1509,8 @@ static size_t carve(const isls_plan *p, long long B, char *base, Dev *d) {
   takeD(d ? &d->zu : nullptr, tm); takeD(d ? &d->lu : nullptr, tm);
   takeD(d ? &d->rgu : nullptr, p->proj_u ? tm : 0);
   takeD(d ? &d->Kg : nullptr, T * N * m * n * TILE);
+  takeD(d ? &d->Qux : nullptr, T * N * m * n * TILE);
+  takeD(d ? &d->Quu : nullptr, T * N * NTRI(m) * TILE);
   takeD(d ? &d->Qui : nullptr, T * N * NTRI(m) * TILE);
   takeD(d ? &d->kk : nullptr, tm);
   takeD(d ? &d->zs : nullptr, T * p->n_via * n * TILE);
@@ -1446,6 +1518,7 @@ static size_t carve(const isls_plan *p, long long B, char *base, Dev *d) {
   const size_t S = T * TILE;
   takeD(d ? &d->cost : nullptr, S); takeD(d ? &d->prev_cost : nullptr, S); takeD(d ? &d->prim : nullptr, S);
   takeD(d ? &d->dual : nullptr, S); takeD(d ? &d->cost_adm : nullptr, S); takeD(d ? &d->best_cost : nullptr, S);
+  takeD(d ? &d->cq : nullptr, 3 * S);
   takeI(d ? &d->best : nullptr, S); takeI(d ? &d->odone : nullptr, S); takeI(d ? &d->adone : nullptr, S);
   takeI(d ? &d->nlog : nullptr, S); takeI(d ? &d->status : nullptr, S); takeI(d ? &d->oit : nullptr, S);
   takeI(d ? &d->ait : nullptr, S);
@@ -1466,6 +1539,8 @@ static int setup(const isls_plan *plan, const isls_solve_opts *o, int64_t B, voi
   *d = plan->base;
   d->B = B;
   d->T = (int)((B + TILE - 1) / TILE);
+  d->tile0 = 0;
+  d->tile1 = d->T;
   carve(plan, B, (char *)ws, d);
   if (o) {
     if (o->max_outer < 1 || o->max_admm < 0) return fail(ISLS_E_INVALID, "bad iteration budgets");
@@ -1481,15 +1556,24 @@ static int setup(const isls_plan *plan, const isls_solve_opts *o, int64_t B, voi
 
 #define TPB_TILES 2   // tiles (warps) per CTA for the one-thread-per-problem kernels
 static dim3 tp_block() { return dim3(TILE, TPB_TILES); }
-static dim3 tp_grid(const Dev &d) { return dim3((d.T + TPB_TILES - 1) / TPB_TILES); }
+static dim3 tp_grid(const Dev &d) { return dim3((d.tile1 - d.tile0 + TPB_TILES - 1) / TPB_TILES); }
 
 // Line-search CTA shape: CPT candidates per thread (independent FP64 chains, shared loads), W = ceil(L/CPT)
 // warps.  MAXW only feeds __launch_bounds__ (register budget).
 template <class M, int CPT, int MAXW, int MINB = 1>
 static void launch_ls_cfg(const Dev &d, bool closed, cudaStream_t s) {
   const int W = (d.L + CPT - 1) / CPT;
-  if (closed) k_linesearch_closed<M, CPT, MAXW, MINB><<<d.T, dim3(TILE, W), 0, s>>>(d);
-  else k_linesearch<M, CPT, MAXW, MINB><<<d.T, dim3(TILE, W), 0, s>>>(d);
+  if (closed) k_linesearch_closed<M, CPT, MAXW, MINB><<<d.tile1 - d.tile0, dim3(TILE, W), 0, s>>>(d);
+  else k_linesearch<M, CPT, MAXW, MINB><<<d.tile1 - d.tile0, dim3(TILE, W), 0, s>>>(d);
+}
+static int solve_chunks() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("ISLS_CHUNKS");      // number of concurrently running batch chunks (streams)
+    v = e ? atoi(e) : 1;
+    if (v < 1) v = 1;
+  }
+  return v;
 }
 static int ls_cpt_override() {
   static int v = -1;
@@ -1528,17 +1612,44 @@ extern "C" int isls_ilqr_admm_solve_f64(const isls_plan *plan, const isls_solve_
   cudaStream_t s = (cudaStream_t)stream;
   return dispatch_model(plan, [&](auto model) -> int {
     using M = decltype(model);
-    LAUNCH(ISLS_KC_INIT, s, (k_init<M><<<tp_grid(d), tp_block(), 0, s>>>(d, x0, u_init, zs)));
-    for (int j = 0; j < d.max_outer; j++) {
-      LAUNCH(ISLS_KC_KPASS, s, (k_kpass<M><<<tp_grid(d), tp_block(), 0, s>>>(d)));
-      for (int a = 0; a < d.max_admm; a++) {
-        LAUNCH(ISLS_KC_FF, s, (k_ff<M><<<tp_grid(d), tp_block(), 0, s>>>(d)));
-        LAUNCH(ISLS_KC_LINESEARCH, s, launch_linesearch<M>(d, false, s));
-        LAUNCH(ISLS_KC_ADMM, s, (k_admm<M><<<tp_grid(d), tp_block(), 0, s>>>(d, j, a)));
+    // Problems are independent, so the batch is cut into `chunks` disjoint tile ranges that run the same kernel
+    // sequence on separate streams (forked from / joined to the caller's stream): the HBM-bound recursions of one
+    // chunk overlap the FP64-bound line search of another.
+    int chunks = solve_chunks();
+    if (g_prof_on) chunks = 1;                       // per-kernel event timing wants serialised launches
+    chunks = std::max(1, std::min(std::min(chunks, MAX_CHUNKS), d.T));
+    isls_plan *pl = const_cast<isls_plan *>(plan);
+    if (chunks > 1 && !pl->aux_ready) {
+      for (int i = 0; i < MAX_CHUNKS; i++) {
+        CK(cudaStreamCreateWithFlags(&pl->aux[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&pl->ev_join[i], cudaEventDisableTiming));
       }
-      LAUNCH(ISLS_KC_OUTER_END, s, (k_outer_end<M><<<tp_grid(d), tp_block(), 0, s>>>(d, j)));
+      CK(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+      pl->aux_ready = true;
     }
-    LAUNCH(ISLS_KC_FINALIZE, s, (k_finalize<M><<<tp_grid(d), tp_block(), 0, s>>>(d)));
+    if (chunks > 1) CK(cudaEventRecord(pl->ev_fork, s));
+    for (int ch = 0; ch < chunks; ch++) {
+      Dev dc = d;
+      dc.tile0 = (int)((long long)d.T * ch / chunks);
+      dc.tile1 = (int)((long long)d.T * (ch + 1) / chunks);
+      cudaStream_t cs = ch == 0 ? s : pl->aux[ch];
+      if (ch > 0) CK(cudaStreamWaitEvent(cs, pl->ev_fork, 0));
+      LAUNCH(ISLS_KC_INIT, cs, (k_init<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, x0, u_init, zs)));
+      for (int j = 0; j < d.max_outer; j++) {
+        LAUNCH(ISLS_KC_KPASS, cs, (k_kpass<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc)));
+        for (int a = 0; a < d.max_admm; a++) {
+          LAUNCH(ISLS_KC_FF, cs, (k_ff<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc)));
+          LAUNCH(ISLS_KC_LINESEARCH, cs, launch_linesearch<M>(dc, false, cs));
+          LAUNCH(ISLS_KC_ADMM, cs, (k_admm<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, j, a)));
+        }
+        LAUNCH(ISLS_KC_OUTER_END, cs, (k_outer_end<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, j)));
+      }
+      LAUNCH(ISLS_KC_FINALIZE, cs, (k_finalize<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc)));
+      if (ch > 0) {
+        CK(cudaEventRecord(pl->ev_join[ch], cs));
+        CK(cudaStreamWaitEvent(s, pl->ev_join[ch], 0));
+      }
+    }
     CK(cudaGetLastError());
     return ISLS_OK;
   });
@@ -1574,8 +1685,8 @@ extern "C" int isls_ilqr_solve_f64(const isls_plan *plan, const isls_solve_opts 
 
 template <class M>
 __global__ void k_pack_zs(Dev d, const double *zs_in) {
-  const int tile = blockIdx.x * blockDim.y + threadIdx.y;
-  if (tile >= d.T) return;
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   double *zs = d.zs + (size_t)tile * d.n_via * M::n * TILE + c.lane;
   for (int k = 0; k < d.n_via; k++)
@@ -1610,6 +1721,7 @@ extern "C" int isls_lqt_admm_dp_f64(const isls_plan *plan, const isls_solve_opts
     // shared gains: K-pass on tile 0 only (linear model: the Jacobian does not depend on the trajectory)
     Dev d1 = d;
     d1.T = 1;
+    d1.tile1 = 1;
     d1.B = 1;
     k_kpass<M><<<1, dim3(TILE, 1), 0, s>>>(d1);
     // the K-pass reset (lambda = 0, reg = z) touched tile 0 only with zeros: state stays zero
