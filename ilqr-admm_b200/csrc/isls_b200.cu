@@ -560,6 +560,7 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d) {
       qz_n = d.qnz[t];
     };
     fetch(0);
+#pragma unroll 2
     for (int t = 0; t < d.N; t++) {
       double un[m], dun[m], rx[n], zv[n], qd[n], rhx[n];
       const bool qz = qz_n;
@@ -575,19 +576,23 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d) {
 #pragma unroll
         for (int i = 0; i < n; i++) { zv[i] = EL(zs, n, s, i); qd[i] = d.qd[t * n + i]; }
       }
+      if (qz) {
+#pragma unroll
+        for (int q = 0; q < CPT; q++)
+#pragma unroll
+          for (int i = 0; i < n; i++) { const double e = x[q][i] - zv[i]; cs[q] += (e * e) * qd[i]; }
+      }
+      if (d.proj_x) {
+#pragma unroll
+        for (int q = 0; q < CPT; q++)
+#pragma unroll
+          for (int i = 0; i < n; i++) { const double e = x[q][i] - rx[i]; px[q] += (e * e) * rhx[i]; }
+      }
 #pragma unroll
       for (int q = 0; q < CPT; q++) {
         double u[m], xn[n];
 #pragma unroll
         for (int j = 0; j < m; j++) u[j] = fma(al[q], dun[j], un[j]);
-        if (qz) {
-#pragma unroll
-          for (int i = 0; i < n; i++) { const double e = x[q][i] - zv[i]; cs[q] += (e * e) * qd[i]; }
-        }
-        if (d.proj_x) {
-#pragma unroll
-          for (int i = 0; i < n; i++) { const double e = x[q][i] - rx[i]; px[q] += (e * e) * rhx[i]; }
-        }
         M::step(x[q], u, xn, d.dt);
 #pragma unroll
         for (int i = 0; i < n; i++) x[q][i] = xn[i];
@@ -1594,8 +1599,9 @@ static void launch_linesearch(const Dev &d, bool closed, cudaStream_t s) {
       if (ov == 1) launch_ls_cfg<M, 1, 20>(d, closed, s);
       else if (ov == 2) launch_ls_cfg<M, 2, 10, 2>(d, closed, s);
       else if (ov == 5) launch_ls_cfg<M, 5, 4, 2>(d, closed, s);
-      else if (ov == 43) launch_ls_cfg<M, 4, 5, 3>(d, closed, s);
-      else launch_ls_cfg<M, 4, 5, 2>(d, closed, s);
+      else if (ov == 42) launch_ls_cfg<M, 4, 5, 2>(d, closed, s);
+      else if (ov == 44) launch_ls_cfg<M, 4, 5, 4>(d, closed, s);
+      else launch_ls_cfg<M, 4, 5, 3>(d, closed, s);      // 4 chains/thread, 5 warps, 3 CTAs/SM (128 regs)
     } else launch_ls_cfg<M, 4, 13>(d, closed, s);
   }
 }

@@ -22,37 +22,51 @@ enum { MZ = 0, MO = 1, MV = 2 };
 
 #define ISLS_TWO_PI 6.283185307179586476925286766559
 
-// numpy's np.mod(a, 2*pi) for float64: r = fmod(a,b); if r != 0 and sign differs from b: r += b
-__device__ __forceinline__ double mod_two_pi(double a) {
-  if (a >= 0.0 && a < ISLS_TWO_PI) return a;      // common case: exact, no fmod
+__device__ __noinline__ double mod_two_pi_slow(double a) {
   double r = fmod(a, ISLS_TWO_PI);
   if (r < 0.0) r += ISLS_TWO_PI;
   else if (r == 0.0) r = 0.0;                     // copysign(0, b) = +0
   return r;
 }
+// numpy's np.mod(a, 2*pi) for float64: r = fmod(a,b); if r != 0 and sign differs from b: r += b
+__device__ __forceinline__ double mod_two_pi(double a) {
+  if (a >= 0.0 && a < ISLS_TWO_PI) return a;      // common case: exact, no fmod
+  return mod_two_pi_slow(a);
+}
 
 // sin and cos of a double with a 3-term Cody-Waite reduction by pi/2 (exact products through FMA) and the
-// fdlibm kernel polynomials on [-pi/4, pi/4] (< 1 ulp).  The rollouts evaluate it once per candidate-step, so it
-// avoids the library sincos()'s large-argument path in the hot loop; |x| >= 2^17 falls back to sincos().
+// fdlibm kernel polynomials on [-pi/4, pi/4] (< 1 ulp).  The rollouts evaluate it once per candidate-step.  The
+// coefficients live in constant memory so every DFMA takes its coefficient as a constant-bank operand (literal
+// doubles cost two UMOV each per use - measured 25 % of the line-search instruction stream); |x| >= 2^17 takes the
+// out-of-line library path.
+__constant__ double kSC[16] = {
+    0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17, -1.4973849048591698e-33,
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+
+__device__ __noinline__ void sincos_slow(double x, double *sp, double *cp) { sincos(x, sp, cp); }
+
 __device__ __forceinline__ void sincos_pio2(double x, double *sp, double *cp) {
-  const double kd = rint(x * 0.6366197723675814);
-  if (!(fabs(kd) < 131072.0)) { sincos(x, sp, cp); return; }
-  double r = fma(-kd, 1.5707963267948966, x);
-  r = fma(-kd, 6.123233995736766e-17, r);
-  r = fma(-kd, -1.4973849048591698e-33, r);
+  const double kd = rint(x * kSC[0]);
+  if (!(fabs(kd) < 131072.0)) { sincos_slow(x, sp, cp); return; }
+  double r = fma(-kd, kSC[1], x);
+  r = fma(-kd, kSC[2], r);
+  r = fma(-kd, kSC[3], r);
   const int k = (int)kd;
   const double z = r * r;
-  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-  ps = fma(z, ps, 2.75573137070700676789e-06);
-  ps = fma(z, ps, -1.98412698298579493134e-04);
-  ps = fma(z, ps, 8.33333333332248946124e-03);
-  ps = fma(z, ps, -1.66666666666666324348e-01);
+  double ps = fma(z, kSC[4], kSC[5]);
+  ps = fma(z, ps, kSC[6]);
+  ps = fma(z, ps, kSC[7]);
+  ps = fma(z, ps, kSC[8]);
+  ps = fma(z, ps, kSC[9]);
   const double s = fma(z * r, ps, r);
-  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-  pc = fma(z, pc, -2.75573143513906633035e-07);
-  pc = fma(z, pc, 2.48015872894767294178e-05);
-  pc = fma(z, pc, -1.38888888888741095749e-03);
-  pc = fma(z, pc, 4.16666666666666019037e-02);
+  double pc = fma(z, kSC[10], kSC[11]);
+  pc = fma(z, pc, kSC[12]);
+  pc = fma(z, pc, kSC[13]);
+  pc = fma(z, pc, kSC[14]);
+  pc = fma(z, pc, kSC[15]);
   const double hz = 0.5 * z, w = 1.0 - hz;
   const double c = w + (((1.0 - w) - hz) + z * (z * pc));
   const double sa = (k & 1) ? c : s, ca = (k & 1) ? s : c;
