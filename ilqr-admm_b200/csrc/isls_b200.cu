@@ -539,11 +539,13 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d) {
     const double *rgx = c.at(d.rgx, d, n);
     const double *zs = d.zs + (size_t)tile * d.n_via * n * TILE + c.lane;
     double al[CPT], x[CPT][n], cs[CPT], px[CPT];
+    bool bad[CPT];
 #pragma unroll
     for (int q = 0; q < CPT; q++) {
       const int l = w * CPT + q;
       al[q] = l < d.L ? d.alphas[l] : 0.0;
       cs[q] = px[q] = 0.0;
+      bad[q] = false;
 #pragma unroll
       for (int i = 0; i < n; i++) x[q][i] = EL(xh, n, 0, i);
     }
@@ -588,14 +590,39 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d) {
 #pragma unroll
           for (int i = 0; i < n; i++) { const double e = x[q][i] - rx[i]; px[q] += (e * e) * rhx[i]; }
       }
+      // branch-free model steps: the CPT independent chains interleave in one basic block; an argument outside the
+      // fast range of sincos / mod only raises the candidate's sticky flag (its rollout is redone exactly below)
 #pragma unroll
       for (int q = 0; q < CPT; q++) {
         double u[m], xn[n];
 #pragma unroll
         for (int j = 0; j < m; j++) u[j] = fma(al[q], dun[j], un[j]);
-        M::step(x[q], u, xn, d.dt);
+        M::step_fast(x[q], u, xn, d.dt, bad[q]);
 #pragma unroll
         for (int i = 0; i < n; i++) x[q][i] = xn[i];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < CPT; q++) {
+      if (bad[q]) {          // rare: exact re-rollout of this candidate (library sincos / fmod paths)
+        double xe[n], u[m], xn[n];
+        double cse = 0.0, pxe = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; i++) xe[i] = EL(xh, n, 0, i);
+        for (int t = 0; t < d.N; t++) {
+#pragma unroll
+          for (int j = 0; j < m; j++) u[j] = fma(al[q], EL(du, m, t, j), EL(uh, m, t, j));
+          cse += state_cost<M>(d, zs, t, xe);
+          if (d.proj_x) {
+#pragma unroll
+            for (int i = 0; i < n; i++) { const double e = xe[i] - EL(rgx, n, t, i); pxe += (e * e) * d.rho_x[t * n + i]; }
+          }
+          M::step(xe, u, xn, d.dt);
+#pragma unroll
+          for (int i = 0; i < n; i++) xe[i] = xn[i];
+        }
+        cs[q] = cse;
+        px[q] = pxe;
       }
     }
     const size_t S = (size_t)d.T * TILE;

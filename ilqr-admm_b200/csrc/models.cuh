@@ -28,10 +28,20 @@ __device__ __noinline__ double mod_two_pi_slow(double a) {
   else if (r == 0.0) r = 0.0;                     // copysign(0, b) = +0
   return r;
 }
-// numpy's np.mod(a, 2*pi) for float64: r = fmod(a,b); if r != 0 and sign differs from b: r += b
+// numpy's np.mod(a, 2*pi) for float64: r = fmod(a,b); if r != 0 and sign differs from b: r += b.
+// Branch-free on [-2pi, 4pi) where it is exact by construction: [0,2pi) -> a; [2pi,4pi) -> a - 2pi (exact,
+// Sterbenz) = fmod; [-2pi,0) -> fmod gives a, then a + 2pi (one rounding, as numpy).  Outside: `bad`.
+__device__ __forceinline__ double mod_two_pi_core(double a, bool &bad) {
+  double r = a;
+  r = (a >= ISLS_TWO_PI) ? a - ISLS_TWO_PI : r;
+  r = (a < 0.0) ? a + ISLS_TWO_PI : r;
+  bad |= !(a >= -ISLS_TWO_PI && a < 2.0 * ISLS_TWO_PI);
+  return r;
+}
 __device__ __forceinline__ double mod_two_pi(double a) {
-  if (a >= 0.0 && a < ISLS_TWO_PI) return a;      // common case: exact, no fmod
-  return mod_two_pi_slow(a);
+  bool bad = false;
+  const double r = mod_two_pi_core(a, bad);
+  return bad ? mod_two_pi_slow(a) : r;
 }
 
 // sin and cos of a double with a 3-term Cody-Waite reduction by pi/2 (exact products through FMA) and the
@@ -48,9 +58,11 @@ __constant__ double kSC[16] = {
 
 __device__ __noinline__ void sincos_slow(double x, double *sp, double *cp) { sincos(x, sp, cp); }
 
-__device__ __forceinline__ void sincos_pio2(double x, double *sp, double *cp) {
+// branch-free core: `bad` is OR-ed with "argument outside the fast range" (results are then garbage and the caller
+// must redo with sincos_slow); no branch, so several independent evaluations schedule into one basic block.
+__device__ __forceinline__ void sincos_core(double x, double *sp, double *cp, bool &bad) {
   const double kd = rint(x * kSC[0]);
-  if (!(fabs(kd) < 131072.0)) { sincos_slow(x, sp, cp); return; }
+  bad |= !(fabs(kd) < 131072.0);
   double r = fma(-kd, kSC[1], x);
   r = fma(-kd, kSC[2], r);
   r = fma(-kd, kSC[3], r);
@@ -74,6 +86,12 @@ __device__ __forceinline__ void sincos_pio2(double x, double *sp, double *cp) {
   *cp = ((k + 1) & 2) ? -ca : ca;
 }
 
+__device__ __forceinline__ void sincos_pio2(double x, double *sp, double *cp) {
+  bool bad = false;
+  sincos_core(x, sp, cp, bad);
+  if (bad) sincos_slow(x, sp, cp);
+}
+
 struct CarModel {
   static constexpr int n = 4, m = 2, NJ = 6, NJA = 6;
   __host__ __device__ static constexpr int am(int i, int j) {
@@ -82,15 +100,26 @@ struct CarModel {
   __host__ __device__ static constexpr int bm(int i, int j) {
     return ((i == 2 && j == 0) || (i == 3 && j == 1)) ? MV : MZ;
   }
+  // branch-free step; `bad` is OR-ed when an argument left the fast range (then xn is invalid: redo with step())
+  __device__ __forceinline__ static void step_fast(const double (&x)[n], const double (&u)[m], double (&xn)[n],
+                                                   double dt, bool &bad) {
+    double s, c;
+    sincos_core(x[2], &s, &c, bad);
+    const double dv = dt * x[3];
+    xn[0] = fma(dv, c, x[0]);
+    xn[1] = fma(dv, s, x[1]);
+    xn[2] = mod_two_pi_core(fma(dv, u[0], x[2]), bad);
+    xn[3] = fma(dt, u[1], x[3]);
+  }
   __device__ __forceinline__ static void step(const double (&x)[n], const double (&u)[m], double (&xn)[n],
                                               double dt) {
     double s, c;
     sincos_pio2(x[2], &s, &c);
     const double dv = dt * x[3];
-    xn[0] = x[0] + dv * c;
-    xn[1] = x[1] + dv * s;
-    xn[2] = mod_two_pi(x[2] + dv * u[0]);
-    xn[3] = x[3] + dt * u[1];
+    xn[0] = fma(dv, c, x[0]);
+    xn[1] = fma(dv, s, x[1]);
+    xn[2] = mod_two_pi(fma(dv, u[0], x[2]));
+    xn[3] = fma(dt, u[1], x[3]);
   }
   __device__ __forceinline__ static void jac(const double (&x)[n], const double (&u)[m], double (&J)[NJ],
                                              double dt) {
@@ -124,7 +153,20 @@ struct Arm3Model {
                                                double dt) {
     const double h = dt * dt;
 #pragma unroll
-    for (int i = 0; i < 3; i++) q[i] = (x[i] + x[3 + i] * dt) + (0.5 * u[i]) * h;
+    for (int i = 0; i < 3; i++) q[i] = fma(0.5 * u[i], h, fma(x[3 + i], dt, x[i]));
+  }
+  __device__ __forceinline__ static void step_fast(const double (&x)[n], const double (&u)[m], double (&xn)[n],
+                                                   double dt, bool &bad) {
+    double q[3];
+    qnext(x, u, q, dt);
+    const double a1 = q[0], a2 = a1 + q[1], a3 = a2 + q[2];
+    double s1, c1, s2, c2, s3, c3;
+    sincos_core(a1, &s1, &c1, bad); sincos_core(a2, &s2, &c2, bad); sincos_core(a3, &s3, &c3, bad);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { xn[i] = q[i]; xn[3 + i] = fma(u[i], dt, x[3 + i]); }
+    xn[6] = (c1 + c2) + c3;
+    xn[7] = (s1 + s2) + s3;
+    xn[8] = 0.0;
   }
   __device__ __forceinline__ static void step(const double (&x)[n], const double (&u)[m], double (&xn)[n],
                                               double dt) {
@@ -134,7 +176,7 @@ struct Arm3Model {
     double s1, c1, s2, c2, s3, c3;
     sincos_pio2(a1, &s1, &c1); sincos_pio2(a2, &s2, &c2); sincos_pio2(a3, &s3, &c3);
 #pragma unroll
-    for (int i = 0; i < 3; i++) { xn[i] = q[i]; xn[3 + i] = x[3 + i] + u[i] * dt; }
+    for (int i = 0; i < 3; i++) { xn[i] = q[i]; xn[3 + i] = fma(u[i], dt, x[3 + i]); }
     xn[6] = (c1 + c2) + c3;
     xn[7] = (s1 + s2) + s3;
     xn[8] = 0.0;
@@ -181,6 +223,8 @@ struct DoubleIntModel {
       xn[D + i] = x[D + i] + dt * u[i];
     }
   }
+  __device__ __forceinline__ static void step_fast(const double (&x)[n], const double (&u)[m], double (&xn)[n],
+                                                   double dt, bool &) { step(x, u, xn, dt); }
   __device__ __forceinline__ static void jac(const double (&)[n], const double (&)[m], double (&)[1], double) {}
   __device__ __forceinline__ static void expand(const double (&)[1], double (&A)[n][n], double (&B)[n][m],
                                                 double dt) {
