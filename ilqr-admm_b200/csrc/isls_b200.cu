@@ -28,20 +28,19 @@
 #define TILE 32
 #define MAX_L 50
 
+#include "common.cuh"
+
 static thread_local std::string g_err;
-static int fail(int code, const std::string &msg) {
+int isls_fail(int code, const std::string &msg) {
   g_err = msg;
   return code;
 }
-static int cuda_fail(cudaError_t e, const char *what) {
+int isls_cuda_fail(cudaError_t e, const char *what) {
   g_err = std::string(what) + ": " + cudaGetErrorString(e);
   return (int)e;
 }
-#define CK(call)                                   \
-  do {                                             \
-    cudaError_t e__ = (call);                      \
-    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
-  } while (0)
+static int fail(int code, const std::string &msg) { return isls_fail(code, msg); }
+static int cuda_fail(cudaError_t e, const char *what) { return isls_cuda_fail(e, what); }
 
 // ---------------------------------------------------------------------------------------- per-kernel event timing
 // Optional (bench.py roofline): when enabled on the calling thread, every kernel launch of a solve is bracketed by

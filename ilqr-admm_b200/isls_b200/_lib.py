@@ -29,6 +29,13 @@ OUT_FIELDS = ["x", "u", "cost", "cost_log", "n_log", "status", "outer_iters", "a
               "alpha_idx", "z_x", "z_u", "lam_x", "lam_u", "K", "k", "mask_x", "mask_u"]
 
 
+class SlsAdmmOpts(C.Structure):
+    _fields_ = [("max_iter", C.c_int32), ("rho_u", C.c_double), ("alpha", C.c_double), ("tol", C.c_double),
+                ("fixed_budget", C.c_int32), ("n_cones", C.c_int32), ("cone_rows", C.c_int32), ("As", C.c_void_p),
+                ("bs", C.c_void_p), ("inner_rho", C.c_double), ("inner_max_iter", C.c_int32),
+                ("inner_threshold", C.c_double)]
+
+
 class SolveOut(C.Structure):
     _fields_ = [(f, C.c_void_p) for f in OUT_FIELDS]
 
@@ -36,7 +43,9 @@ class SolveOut(C.Structure):
 EXPORTS = ["isls_version", "isls_last_error_string", "isls_model_id", "isls_model_supported", "isls_plan_create",
            "isls_plan_destroy", "isls_workspace_bytes", "isls_ilqr_admm_solve_f64", "isls_ilqr_solve_f64",
            "isls_lqt_admm_dp_f64", "isls_riccati_f64", "isls_rollout_linesearch_f64", "isls_admm_project_dual_f64",
-           "isls_measure_fp64_tflops", "isls_profile_enable", "isls_profile_collect"]
+           "isls_measure_fp64_tflops", "isls_profile_enable", "isls_profile_collect",
+           "isls_sls_plan_create", "isls_sls_plan_destroy", "isls_sls_operators", "isls_sls_solve_f64",
+           "isls_sls_admm_f64", "isls_sls_controller_f64"]
 
 KERNEL_CLASSES = ["init", "kpass", "ff", "linesearch", "admm", "outer_end", "finalize", "backward_full", "accept",
                   "lqt"]
@@ -73,6 +82,14 @@ def lib():
     L.isls_rollout_linesearch_f64.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 11 + [C.c_size_t, C.c_void_p]
     L.isls_admm_project_dual_f64.argtypes = [C.c_int64, C.c_int64, C.c_double] + [C.c_void_p] * 9
     L.isls_measure_fp64_tflops.argtypes = [C.POINTER(C.c_double), C.c_void_p]
+    L.isls_sls_plan_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_double, C.POINTER(C.c_void_p), C.c_void_p]
+    L.isls_sls_plan_destroy.argtypes = [C.c_void_p]
+    L.isls_sls_operators.argtypes = [C.c_void_p] * 5
+    L.isls_sls_solve_f64.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.isls_sls_admm_f64.argtypes = [C.c_void_p, C.POINTER(SlsAdmmOpts), C.c_int64] + [C.c_void_p] * 8
+    L.isls_sls_controller_f64.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
     L.isls_profile_enable.argtypes = [C.c_int]
     L.isls_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     _lib = L

@@ -38,3 +38,17 @@ class Bound:
 
 def bound(lo=-np.inf, hi=np.inf):
     return Bound(lo, hi)
+
+
+class SetConvexSOC:
+    """Row-wise projection onto the intersection of second-order cones {A_i x + b_i in SOC}: the device counterpart of
+    `lambda y: project_set_convex(y, As, bs, projections=[project_soc_unit]*P, rho=.., max_iter=.., threshold=..)`
+    (isls/projections.py:289-374 with 118-162), e.g. the chance-constrained control bounds of
+    notebooks/Double integrator/LQR and SLS with control bounds.ipynb cell 15.  As: list of [c+1, c], bs: list of
+    [c+1]."""
+
+    def __init__(self, As, bs, rho=1.0, max_iter=200, threshold=1e-4):
+        self.As = np.ascontiguousarray(np.stack([np.asarray(a, dtype=np.float64) for a in As]))
+        self.bs = np.ascontiguousarray(np.stack([np.asarray(b, dtype=np.float64) for b in bs]))
+        assert self.As.ndim == 3 and self.bs.shape == self.As.shape[:2]
+        self.rho, self.max_iter, self.threshold = float(rho), int(max_iter), float(threshold)

@@ -4,7 +4,10 @@ import torch
 
 from . import solver as S
 from ._lib import IslsError
-from .projections import Bound
+import ctypes as C
+
+from . import _lib
+from .projections import Bound, SetConvexSOC
 from .utils import diag_of, get_double_integrator_AB
 
 
@@ -19,6 +22,7 @@ class SLS:
         self._dt = None
         self.zs = None
         self.last = None
+        self._sls_plan = None
 
     @property
     def AB(self):
@@ -30,13 +34,15 @@ class SLS:
         (isls/utils.py:266-276): A, B must be get_double_integrator_AB(u_dim, 2, dt) for some dt."""
         A, Bm = np.asarray(value[0], dtype=np.float64), np.asarray(value[1], dtype=np.float64)
         d = self.u_dim
-        if A.shape != (2 * d, 2 * d) or Bm.shape != (2 * d, d) or self.x_dim != 2 * d:
-            raise NotImplementedError("device LQT path supports the double integrator (x_dim = 2 u_dim)")
-        dt = float(A[0, d])
-        A2, B2 = get_double_integrator_AB(d, 2, dt)
-        if not (np.array_equal(A, A2) and np.array_equal(Bm, B2)):
-            raise NotImplementedError("A, B are not a double integrator; no device model registered for them")
-        self.A, self.B, self._dt = A, Bm, dt
+        if A.shape != (self.x_dim, self.x_dim) or Bm.shape != (self.x_dim, d):
+            raise ValueError("device SLS path needs constant A [x_dim, x_dim], B [x_dim, u_dim]")
+        self.A, self.B, self._dt = A, Bm, None
+        self._sls_plan = None
+        if self.x_dim == 2 * d:                      # registered device model for the LQT-ADMM (DP) kernels
+            dt = float(A[0, d])
+            A2, B2 = get_double_integrator_AB(d, 2, dt)
+            if np.array_equal(A, A2) and np.array_equal(Bm, B2):
+                self._dt = dt
 
     def set_quadratic_cost(self, zs, Qs, seq, u_std):
         """isls/base.py:81-89."""
@@ -45,6 +51,7 @@ class SLS:
         self.Qdiag = diag_of(Qs, "Qs") if Qs.ndim == 3 else Qs
         self.seq = np.asarray(seq, dtype=np.int32)
         self.u_std = float(u_std)
+        self._sls_plan = None
 
     set_cost_variables = set_quadratic_cost
 
@@ -62,8 +69,11 @@ class SLS:
                     tol=1e-3, verbose=False, log=False, fixed_budget=False, want_masks=False):
         """LQT-ADMM with dynamic programming (isls/sls.py:298-317): Riccati pass once, then ff-pass + rollout +
         projection/dual update per iteration, all inside one kernel.  Returns (x, u, K, k[, logs])."""
-        if self._dt is None or self.zs is None:
+        if self.A is None or self.zs is None:
             raise IslsError("set AB and set_quadratic_cost first")
+        if self._dt is None:
+            raise NotImplementedError("ADMM_LQT_DP on the device needs A, B = get_double_integrator_AB(u_dim, 2, dt) "
+                                      "(the registered linear model)")
         for nm, pr in (("project_x", project_x), ("project_u", project_u)):
             if pr and not isinstance(pr, Bound):
                 raise TypeError("%s must be an isls_b200.projections.Bound" % nm)
@@ -90,3 +100,143 @@ class SLS:
         if log:
             ret += (sq(out.res_log[:, 0]),)
         return ret
+
+    # ------------------------------------------------------------------ SLS (system level synthesis) path
+    def _plan(self):
+        """Shared operators Sw, Su, L^-1, PHI_U on the device (isls_sls_plan_create)."""
+        if self.A is None or self.zs is None:
+            raise IslsError("set AB and set_quadratic_cost first")
+        if self._sls_plan is None:
+            L_ = _lib.lib()
+            Qt = np.ascontiguousarray(self.Qdiag[self.seq])                      # [N, n] per-step diagonal of Q
+            A = np.ascontiguousarray(self.A)
+            Bm = np.ascontiguousarray(self.B)
+            h = C.c_void_p()
+            with torch.cuda.device(self.device):
+                rc = L_.isls_sls_plan_create(self.x_dim, self.u_dim, self.N, A.ctypes.data, Bm.ctypes.data,
+                                             Qt.ctypes.data, self.u_std, C.byref(h),
+                                             C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+            _lib.check(rc, "isls_sls_plan_create")
+            self._sls_plan = _SlsPlan(h, self)
+        return self._sls_plan
+
+    def _xd(self):
+        """xd = find_mus(zs, seq) (isls/utils.py:95-99) per problem: [B, N n] on the device."""
+        zs = np.asarray(self.zs, dtype=np.float64)
+        if zs.ndim == 2:
+            zs = zs[None]
+        xd = zs[:, self.seq].reshape(zs.shape[0], -1)
+        xd = np.ascontiguousarray(np.broadcast_to(xd, (self.nb, self.N * self.x_dim)))
+        return torch.from_numpy(xd).to(self.device)
+
+    @property
+    def Sw(self):
+        return self._plan().Sw
+
+    @property
+    def Su(self):
+        return self._plan().Su
+
+    def solve_sls(self, verbose=False):
+        """PHI_U, du = solve_sls() (isls/sls.py:205-233).  PHI_U [N m, N n] is shared by the batch; du [B, N m]."""
+        pl = self._plan()
+        xd = self._xd()
+        du = torch.empty(self.nb, self.N * self.u_dim, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().isls_sls_solve_f64(pl.handle, self.nb, C.c_void_p(xd.data_ptr()),
+                                               C.c_void_p(du.data_ptr()),
+                                               C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        _lib.check(rc, "isls_sls_solve_f64")
+        return pl.PHI_U, (du[0] if self.batch is None else du)
+
+    def ADMM_SLS(self, project_x=False, project_u=False, max_iter=5000, rho_x=0., rho_u=0., alpha=1., tol=1e-3,
+                 verbose=False, log=False, fixed_budget=False):
+        """SLS-ADMM with robust (chance-constrained) control bounds w.r.t. the initial position
+        (isls/sls.py:319-454).  project_u: `SetConvexSOC`; returns (du, phi_u[, logs])."""
+        if project_x:
+            raise NotImplementedError("device ADMM_SLS implements the control-side projection (project_u)")
+        if not isinstance(project_u, SetConvexSOC):
+            raise TypeError("project_u must be an isls_b200.projections.SetConvexSOC")
+        pl = self._plan()
+        dev = self.device
+        B_, Nm, Nn, c = self.nb, self.N * self.u_dim, self.N * self.x_dim, self.x_dim // 2 + 1
+        As, bs = project_u.As, project_u.bs
+        if As.shape[1:] != (c + 1, c):
+            raise ValueError("cone matrices must be [%d, %d] (1 + x_dim/2 columns)" % (c + 1, c))
+        xd = self._xd()
+        f64 = dict(dtype=torch.float64, device=dev)
+        du = torch.empty(B_, Nm, **f64)
+        phic = torch.empty(B_, Nm, c - 1, **f64)
+        logs = torch.full((B_, int(max_iter), 2), float("nan"), **f64)
+        iters = torch.empty(B_, dtype=torch.int32, device=dev)
+        exits = torch.empty(B_, dtype=torch.int32, device=dev)
+        inner = torch.empty(B_, dtype=torch.int64, device=dev)
+        o = _lib.SlsAdmmOpts(max_iter=int(max_iter), rho_u=float(rho_u), alpha=float(alpha), tol=float(tol),
+                             fixed_budget=int(fixed_budget), n_cones=As.shape[0], cone_rows=c + 1,
+                             As=As.ctypes.data, bs=bs.ctypes.data, inner_rho=project_u.rho,
+                             inner_max_iter=project_u.max_iter, inner_threshold=project_u.threshold)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        with torch.cuda.device(dev):
+            rc = _lib.lib().isls_sls_admm_f64(pl.handle, C.byref(o), B_, p(xd), p(du), p(phic), p(logs), p(iters),
+                                              p(exits), p(inner),
+                                              C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(rc, "isls_sls_admm_f64")
+        self.last = S.Result(du=du, phi_cols=phic, logs=logs, iters=iters, exit_code=exits, inner_total=inner)
+        phi_u = torch.cat([phic, pl.PHI_U[None, :, c - 1:].expand(B_, Nm, Nn - (c - 1))], dim=-1)   # sls.py:450
+        if verbose:
+            it, ex = iters.cpu().numpy(), exits.cpu().numpy()
+            for b in range(min(B_, 8)):
+                msg = {1: "ADMM converged at iteration %d !", 2: "ADMM can't improve anymore at iteration %d !",
+                       3: "ADMM: Max iteration reached. (%d)"}[int(ex[b])] % (it[b] - 1)
+                print("problem", b, msg, "residual", logs[b, it[b] - 1].tolist())
+        sq = (lambda t: t[0]) if self.batch is None else (lambda t: t)
+        ret = (sq(du), sq(phi_u))
+        if log:
+            ret += (sq(logs),)
+        return ret
+
+    def controller(self, PHI_U, du):
+        """K, k = controller(PHI_U, du) (isls/sls.py:235-242); PHI_U [N m, N n] or [B, N m, N n], du [N m] / [B, N m]."""
+        pl = self._plan()
+        dev = self.device
+        Nm, Nn = self.N * self.u_dim, self.N * self.x_dim
+        PHI_U = torch.as_tensor(PHI_U, dtype=torch.float64).to(dev)
+        du = torch.as_tensor(du, dtype=torch.float64).to(dev)
+        single = PHI_U.ndim == 2 and du.ndim == 1
+        du = du.reshape(-1, Nm).contiguous()
+        B_ = du.shape[0]
+        PHI = PHI_U.reshape(-1, Nm, Nn).expand(B_, Nm, Nn).contiguous()
+        f64 = dict(dtype=torch.float64, device=dev)
+        K = torch.empty(B_, Nm, Nn, **f64)
+        k = torch.empty(B_, Nm, **f64)
+        ws = torch.empty(B_ * Nn * Nn, **f64)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        with torch.cuda.device(dev):
+            rc = _lib.lib().isls_sls_controller_f64(pl.handle, B_, Nn, p(PHI), p(du), p(ws), ws.numel() * 8, p(K),
+                                                    p(k), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(rc, "isls_sls_controller_f64")
+        return (K[0], k[0]) if single else (K, k)
+
+
+class _SlsPlan:
+    """Owner of an isls_sls_plan handle + caller-owned copies of its shared device operators."""
+
+    def __init__(self, handle, owner):
+        self.handle = handle
+        dev = owner.device
+        Nn, Nm = owner.N * owner.x_dim, owner.N * owner.u_dim
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.Sw, self.Su, self.PHI_U = torch.empty(Nn, Nn, **f64), torch.empty(Nn, Nm, **f64), torch.empty(Nm, Nn, **f64)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().isls_sls_operators(handle, C.c_void_p(self.Sw.data_ptr()), C.c_void_p(self.Su.data_ptr()),
+                                               C.c_void_p(self.PHI_U.data_ptr()),
+                                               C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(rc, "isls_sls_operators")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().isls_sls_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

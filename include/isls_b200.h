@@ -169,6 +169,52 @@ int isls_admm_project_dual_f64(int64_t B, int64_t len, double relax, const doubl
                                double *lam_dev, const double *lo_dev, const double *hi_dev, double *prim_sq_dev,
                                double *dual_sq_dev, int8_t *mask_dev, void *stream);
 
+/* ---- SLS path (north-star item 4, BASELINE config 4): linear time-invariant dynamics, diagonal Q ---- */
+typedef struct isls_sls_plan isls_sls_plan;   /* opaque: Sw, Su, Su'Q, L = Su'QSu + R, L^-1, PHI_U on the device */
+
+/* Builds the operators shared by a batch (same A, B, Q, R; per-problem targets xd):
+ *   Sw, Su                         Base.AB setter            isls/base.py:98-119
+ *   L = Su'Q Su + R, L^-1          SLS.solve_sls             isls/sls.py:216-219 (compute_inverses, base.py:44-50)
+ *   PHI_U (block lower triangular) SLS.solve_sls             isls/sls.py:225-229
+ * A_host [n,n], B_host [n,m], Qdiag_t_host [N,n] (per-step diagonal of Q) are HOST arrays.  Synchronises. */
+int isls_sls_plan_create(int32_t n, int32_t m, int32_t N, const double *A_host, const double *B_host,
+                         const double *Qdiag_t_host, double u_std, isls_sls_plan **plan, void *stream);
+int isls_sls_plan_destroy(isls_sls_plan *plan);
+/* copies the shared operators into caller-owned device buffers (any may be NULL):
+ * Sw [N n, N n], Su [N n, N m], PHI_U [N m, N n], row-major */
+int isls_sls_operators(const isls_sls_plan *plan, double *Sw_dev, double *Su_dev, double *PHI_U_dev, void *stream);
+
+/* SLS.solve_sls feed-forward part (isls/sls.py:221): du[b] = L^-1 Su'Q xd[b].  xd_dev [B, N n] -> du_dev [B, N m] */
+int isls_sls_solve_f64(const isls_sls_plan *plan, int64_t B, const double *xd_dev, double *du_dev, void *stream);
+
+/* SLS.ADMM_SLS (isls/sls.py:319-454) with project_u = row-wise project_set_convex(.., [project_soc_unit]*P)
+ * (isls/projections.py:289-374, 140-162) and no state projection: robust control bounds w.r.t. the initial position. */
+typedef struct isls_sls_admm_opts {
+  int32_t max_iter;        /* ADMM_SLS max_iter */
+  double rho_u, alpha, tol;
+  int32_t fixed_budget;    /* 1: ignore the stop tests */
+  int32_t n_cones;         /* P: number of cones per row (<= 4) */
+  int32_t cone_rows;       /* rows of each A_i = c + 1 with c = 1 + x_dim/2 columns (c <= 4) */
+  const double *As;        /* host [P, cone_rows, c] */
+  const double *bs;        /* host [P, cone_rows] */
+  double inner_rho;        /* project_set_convex rho */
+  int32_t inner_max_iter;  /* project_set_convex max_iter */
+  double inner_threshold;  /* project_set_convex threshold */
+} isls_sls_admm_opts;
+/* xd_dev [B, N n] -> du_dev [B, N m] (= x_u[:,0]), phi_cols_dev [B, N m, c-1] (= x_u[:,1:c]; the full PHI_U of a
+ * problem is [phi_cols | shared PHI_U[:, c-1:]], sls.py:450), logs_dev [B, max_iter, 2] (optional), iters_dev [B],
+ * exit_dev [B] (ISLS_ADMM_*), inner_total_dev [B] int64 (optional: total inner projection iterations). */
+int isls_sls_admm_f64(isls_sls_plan *plan, const isls_sls_admm_opts *opts, int64_t B, const double *xd_dev,
+                      double *du_dev, double *phi_cols_dev, double *logs_dev, int32_t *iters_dev, int32_t *exit_dev,
+                      int64_t *inner_total_dev, void *stream);
+
+/* SLS.controller (isls/sls.py:235-242): K = PHI_U PHI_X^-1, k = (I - K Su) du per problem, with
+ * PHI_U[b] = [phi_cols_dev[b] (first n_first_cols columns) | shared PHI_U (rest)].
+ * workspace: B * (N n)^2 doubles.  K_dev [B, N m, N n], k_dev [B, N m]. */
+int isls_sls_controller_f64(const isls_sls_plan *plan, int64_t B, int32_t n_first_cols, const double *phi_cols_dev,
+                            const double *du_dev, void *workspace_dev, size_t workspace_bytes, double *K_dev,
+                            double *k_dev, void *stream);
+
 /* ---- measurement helpers (bench.py roofline denominators; not part of the reference surface) ---- */
 /* kernel classes for per-kernel CUDA-event timing */
 #define ISLS_KC_INIT 0

@@ -542,3 +542,170 @@ def lqt_admm_dp(p, fixed_budget=False):
     return dict(x=x_last, u=u_last, K=np.broadcast_to(K, (B, N, m, n)).copy(), k=k_last, cost=cost, iters=iters,
                 exit_code=exit_code, res_log=res_log, z_x=zx, z_u=zu, lam_x=lx, lam_u=lu, mask_x=mask_x,
                 mask_u=mask_u, non_pd=np.broadcast_to(non_pd, (B,)).copy())
+
+
+# ================================================================================ SLS path (item 4, config 4)
+def build_Sw_Su(A, Bm, N):
+    """Base.AB setter (isls/base.py:98-119): Sw = (I - Z A)^-1 (lower block triangular, blocks A^(i-j)),
+    Su blocks A^(i-j-1) B for i > j.  Built with the reference's backward block recursion."""
+    n, m = Bm.shape
+    Sw = np.kron(np.triu(np.ones((N, N))).T, np.eye(n))           # base.py:18
+    Su = np.zeros((n * N, N * m))                                 # base.py:19
+    for i in range(N - 1, 0, -1):
+        Su[i * n:, (i - 1) * m:i * m] = Sw[i * n:, i * n:(i + 1) * n] @ Bm       # base.py:115-116
+        Sw[i * n:, (i - 1) * n:i * n] = Sw[i * n:, i * n:(i + 1) * n] @ A        # base.py:118-119
+    return Sw, Su
+
+
+def trailing_inverses(L, m, N):
+    """Base.compute_inverses (isls/base.py:44-50): inverses of all trailing principal sub-matrices L[i m:, i m:],
+    i = 0..N, each obtained from the previous by the rank-2m Woodbury down-date of isls/base.py:32-42, which is the
+    Schur-complement identity  D^-1 = S - r p^-1 q  for  inv([[a,b],[c,D]]) = [[p,q],[r,S]]."""
+    invs = [np.linalg.inv(L)]
+    for i in range(N):
+        Ai = invs[i]
+        p, q, r, S = Ai[:m, :m], Ai[:m, m:], Ai[m:, :m], Ai[m:, m:]
+        invs.append(S - r @ np.linalg.solve(p, q))
+    return invs
+
+
+def project_soc_unit_batch(z, t):
+    """isls/projections.py:140-162 verbatim semantics (incl. SURVEY D9: every row with t < 0 is zeroed)."""
+    z_norm = np.linalg.norm(z, axis=-1)
+    z_ = z.copy()
+    t_ = t.copy()
+    cond1 = np.logical_or(z_norm <= -t, t < 0)
+    cond2 = np.logical_or(z_norm > t, z_norm > -t)
+    cond3 = z_norm <= t
+    tmp = (z_norm + t_) / 2
+    z_[cond2] = tmp[cond2, None] * z[cond2] / (z_norm[cond2, None] + 1e-30)
+    t_[cond2] = tmp[cond2].copy()
+    z_[cond1] = 0.
+    t_[cond1] = 0.
+    z_[cond3] = z[cond3]
+    t_[cond3] = t[cond3]
+    return z_, t_
+
+
+def project_set_convex_soc(x0, As, bs, rho=1.0, max_iter=200, threshold=1e-4):
+    """isls/projections.py:289-374 with projections = [project_soc_unit] * len(As): inner ADMM onto the
+    intersection of {A_i x + b_i in SOC}; x0 [rows, c].  Returns (x [rows, c], inner iterations)."""
+    P = len(As)
+    x0 = np.asarray(x0)
+    rows = x0.shape[0]
+    x = x0.T.copy()
+    z = [As[i] @ x + bs[i][:, None] for i in range(P)]
+    lmb = [zz * 0 for zz in z]
+    l_side_add = sum(As[i].T @ As[i] for i in range(P))
+    l_side_inv = np.linalg.inv(np.eye(x0.shape[-1]) + rho * l_side_add)
+    prim_n = np.ones((P, rows)) * 1e5
+    dual_n = np.ones((P, rows)) * 1e5
+    prim_, dual_ = 1e5, 1e5
+    its = 0
+    for j in range(max_iter):
+        its = j + 1
+        r_side = sum(As[i].T @ (-bs[i][:, None] + z[i] - lmb[i]) for i in range(P))
+        x = l_side_inv @ (x0.T + rho * r_side)
+        z_prev = list(z)
+        pprim, pdual = prim_, dual_
+        for i in range(P):
+            Ax_b = As[i] @ x + bs[i][:, None]
+            y = (Ax_b + lmb[i]).T
+            zz, tt = project_soc_unit_batch(y[:, :-1], y[:, -1])
+            z[i] = np.concatenate([zz, tt[:, None]], axis=1).T
+            prim_res = Ax_b - z[i]
+            dual_res = rho * As[i].T @ (z[i] - z_prev[i])
+            lmb[i] = lmb[i] + prim_res
+            prim_n[i] = np.linalg.norm(prim_res, axis=0)
+            dual_n[i] = np.linalg.norm(dual_res, axis=0)
+        prim_, dual_ = np.max(prim_n), np.max(dual_n)
+        if prim_ < threshold and dual_ < threshold:
+            break
+        if j < max_iter - 1:
+            pch = np.abs(pprim - prim_) / (pprim + 1e-30)
+            dch = np.abs(pdual - dual_) / (pdual + 1e-30)
+            if pch < 1e-5 and dch < 1e-5:
+                break
+    return x.T, its
+
+
+def sls_solve(A, Bm, N, Qdiag_t, xd, u_std):
+    """SLS.solve_sls (isls/sls.py:205-233).  Qdiag_t [N, n] per-step diagonal of Q, xd [N n] (one problem) or
+    [B, N n].  Returns PHI_U [N m, N n] (shared), du [B, N m], plus the operators reused by admm_sls."""
+    n, m = Bm.shape
+    Sw, Su = build_Sw_Su(A, Bm, N)
+    q = Qdiag_t.reshape(-1)
+    DTQ = Su.T * q[None, :]                                        # Su' Q with block-diagonal (here diagonal) Q
+    L = DTQ @ Su + u_std * np.eye(N * m)
+    invs = trailing_inverses(L, m, N)
+    xd2 = np.atleast_2d(xd)
+    du = (invs[0] @ DTQ @ xd2.T).T                                 # sls.py:221
+    r_side = -DTQ @ Sw                                             # sls.py:225
+    PHI_U = np.zeros((N * m, N * n))
+    for i in range(N):
+        PHI_U[i * m:, i * n:(i + 1) * n] = invs[i] @ r_side[i * m:, i * n:(i + 1) * n]     # sls.py:228-229
+    return dict(PHI_U=PHI_U, du=du, Sw=Sw, Su=Su, DTQ=DTQ, L=L)
+
+
+def admm_sls(A, Bm, N, Qdiag_t, xd, u_std, As, bs, rho_u, max_iter=5000, alpha=1.0, tol=1e-3, inner_rho=1.0,
+             inner_max_iter=200, inner_threshold=1e-4, fixed_budget=False):
+    """SLS.ADMM_SLS (isls/sls.py:319-454) with project_u = project_set_convex(.., [project_soc_unit]*P) row-wise and
+    no state projection.  One problem per row of xd [B, N n].  Returns du [B, N m], phi_u [B, N m, N n], logs."""
+    n, m = Bm.shape
+    c = n // 2 + 1
+    base = sls_solve(A, Bm, N, Qdiag_t, xd, u_std)
+    Sw, Su, DTQ = base["Sw"], base["Su"], base["DTQ"]
+    Sx = Sw[:, :n // 2]
+    l_side = base["L"] + rho_u * np.eye(N * m)                     # sls.py:339-349 (Rr = rho_u I)
+    l_inv = trailing_inverses(l_side, m, N)[0]                     # sls.py:352, 367
+    r_fb = -DTQ @ Sx
+    xd2 = np.atleast_2d(xd)
+    B = xd2.shape[0]
+    du_out = np.zeros((B, N * m))
+    phi_out = np.zeros((B, N * m, N * n))
+    logs, iters, exits, inner_total = [], np.zeros(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int64)
+    for b in range(B):
+        r_side = np.concatenate([(DTQ @ xd2[b])[:, None], r_fb], axis=-1)
+        z_u = np.zeros((N * m, c))
+        lmb = np.zeros((N * m, c))
+        prim = dual = 1e6
+        lg = []
+        ex = ADMM_MAXIT
+        for j in range(max_iter):
+            reg_u = z_u - lmb
+            x_u = l_inv @ (r_side + rho_u * reg_u)                 # sls.py:372-380
+            pprim, pdual = prim, dual
+            z_prev = z_u.copy()
+            z_u, it_in = project_set_convex_soc(alpha * x_u + (1 - alpha) * z_u + lmb, As, bs, rho=inner_rho,
+                                                max_iter=inner_max_iter, threshold=inner_threshold)
+            inner_total[b] += it_in
+            pr = x_u - z_u
+            lmb = lmb + pr
+            dual = np.linalg.norm(rho_u * (z_u - z_prev))          # sls.py:417 (Frobenius, Rr = rho_u I)
+            prim = np.linalg.norm(rho_u * pr)
+            lg.append((prim, dual))
+            iters[b] = j + 1
+            if fixed_budget:
+                continue
+            if prim < tol and dual < tol:
+                ex = ADMM_CONVERGED
+                break
+            pch = abs(pprim - prim) / (pprim + 1e-30)
+            dch = abs(pdual - dual) / (pdual + 1e-30)
+            if pch < 1e-2 and dch < 1e-2:                          # sls.py:429
+                ex = ADMM_STALLED
+                break
+        exits[b] = ex
+        du_out[b] = x_u[:, 0]
+        phi_out[b] = np.concatenate([x_u[:, 1:c], base["PHI_U"][:, c - 1:]], axis=-1)   # sls.py:449-450
+        logs.append(np.array(lg))
+    return dict(du=du_out, phi_u=phi_out, logs=logs, iters=iters, exit_code=exits, inner_total=inner_total,
+                PHI_U=base["PHI_U"], du0=base["du"], Sw=Sw, Su=Su)
+
+
+def sls_controller(Sw, Su, PHI_U, du):
+    """SLS.controller (isls/sls.py:235-242): PHI_X = Sw + Su PHI_U; K = PHI_U PHI_X^-1; k = (I - K Su) du."""
+    PHI_X = Sw + Su @ PHI_U
+    K = PHI_U @ np.linalg.inv(PHI_X)
+    k = (np.eye(Su.shape[-1]) - K @ Su) @ du
+    return K, k

@@ -154,3 +154,58 @@ if __name__ == "__main__":
     pd = P.di_batch(3)
     golden_lqt_admm_dp(pd, "di_lqt_admm_dp")
     golden_notebook_pins()
+    golden_sls()
+
+
+def golden_sls(name="sls_admm"):
+    """SLS.solve_sls / ADMM_SLS / controller of the unmodified reference on (a) the notebook problem
+    'LQR and SLS with control bounds' (n=2, m=1, N=100; known printout: "can't improve anymore at iteration 25",
+    residual 8.50e-13 3.77e-01) and (b) a C4-style problem (n=4, m=2, N=50, dt=1/50) for 3 targets."""
+    from scipy.stats import norm
+    pkg, _ = S.load()
+    from isls.utils import get_double_integrator_AB
+    from isls.projections import project_set_convex, project_soc_unit
+    out = {}
+
+    def cones(pos_dim, upper, lower, var_x0=0.01, p=0.95):
+        mu = np.zeros(pos_dim + 1); mu[0] = 1.0
+        sigma = np.zeros(pos_dim + 1); sigma[1:] = var_x0
+        psi = norm.ppf(p)
+        Au = np.diag(np.sqrt(sigma)); bu = np.zeros(pos_dim + 1)
+        A_ = [np.concatenate([Au, (-mu / psi)[None]], 0), np.concatenate([Au, (mu / psi)[None]], 0)]
+        b_ = [np.append(bu, upper / psi), np.append(bu, -lower / psi)]
+        return A_, b_
+
+    def run(tag, pos_dim, N, dt, Qf, u_std, targets, bound):
+        n, m = 2 * pos_dim, pos_dim
+        A, B = get_double_integrator_AB(pos_dim, nb_deriv=2, dt=dt)
+        A_, b_ = cones(pos_dim, bound, -bound)
+        proj = lambda y: project_set_convex(y, A_, b_, projections=[project_soc_unit] * 2, rho=1e1, max_iter=100,
+                                            threshold=1e-3)
+        res = dict(du0=[], du=[], phic=[], iters=[], last=[], logs=[], u_cl=[])
+        for tg in targets:
+            with S.quiet():
+                sls = pkg.SLS(n, m, N); sls.AB = [A, B]
+                zs = np.stack([np.zeros(n), np.concatenate([tg, np.zeros(pos_dim)])])
+                Qs = np.stack([np.zeros((n, n)), np.eye(n) * Qf])
+                seq = np.zeros(N, dtype=np.int32); seq[-1] = 1
+                sls.set_quadratic_cost(zs, Qs, seq, u_std)
+                PHI0, du0 = sls.solve_sls()
+                du, PHI, log = sls.ADMM_SLS(project_u=proj, max_iter=50, rho_u=1e2, alpha=1., tol=1e-3, log=True)
+                K, k = sls.controller(PHI, du)
+                # closed-loop controls for a few initial positions (well-conditioned function of the controller)
+                x0s = np.zeros((3, n)); x0s[:, :pos_dim] = np.array([[0.05], [-0.1], [0.12]])[:, :1]
+                _, u_cl = sls.get_trajectory_sls(x0s, K, k)
+            res["du0"].append(du0); res["du"].append(du); res["phic"].append(PHI[:, :pos_dim])
+            res["iters"].append(len(log)); res["last"].append(np.array(log)[-1]); res["u_cl"].append(u_cl)
+            lg = np.full((50, 2), np.nan); lg[:len(log)] = np.array(log); res["logs"].append(lg)
+            print(tag, tg, len(log), np.array(log)[-1])
+        out[tag + "_PHI0"] = PHI0
+        out[tag + "_A_"] = np.stack(A_); out[tag + "_b_"] = np.stack(b_)
+        out[tag + "_targets"] = np.stack(targets)
+        for kk, v in res.items():
+            out[tag + "_" + kk] = np.stack(v)
+
+    run("nb", 1, 100, 0.01, 1e6, 1e-2, [np.array([1.0])], 5.0)
+    run("c4", 2, 50, 1.0 / 50, 1e6, 1e-2, [np.array([1.0, 1.0]), np.array([0.7, 0.9]), np.array([0.6, 0.65])], 5.0)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)

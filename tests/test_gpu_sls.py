@@ -1,0 +1,178 @@
+"""GPU parity tests of the SLS path (north-star item 4 / BASELINE config 4): SLS.solve_sls, ADMM_SLS with SOC
+chance constraints, controller - CUDA path through the public API against the oracle and the reference goldens."""
+import numpy as np
+import pytest
+
+from oracle import models as M, restated as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(g, tag, pos_dim, N, dt, Qf=1e6):
+    n, m = 2 * pos_dim, pos_dim
+    A, B = M.double_integrator_AB(pos_dim, 2, dt)
+    tg = g[tag + "_targets"]
+    return n, m, A, B, tg, [a for a in g[tag + "_A_"]], [b for b in g[tag + "_b_"]]
+
+
+def _make_sls(n, m, N, A, B, targets, Qf=1e6, u_std=1e-2):
+    from isls_b200 import SLS
+    pos = n // 2
+    Bn = len(targets)
+    s = SLS(n, m, N, batch=Bn)
+    s.AB = [A, B]
+    zs = np.zeros((Bn, 2, n))
+    zs[:, 1, :pos] = targets
+    Qs = np.stack([np.zeros((n, n)), np.eye(n) * Qf])
+    seq = np.zeros(N, dtype=np.int32); seq[-1] = 1
+    s.set_quadratic_cost(zs, Qs, seq, u_std)
+    return s
+
+
+def _closed_loop(A, B, K, k, x0s, N):
+    """SLSBase.get_trajectory_sls (sls_base.py:91-105) without noise: u_t = (K x_hist + k)[t]."""
+    n, m = B.shape
+    us = np.zeros((len(x0s), N, m))
+    for b, x0 in enumerate(x0s):
+        xv = np.zeros(N * n)
+        x = x0.copy()
+        for t in range(N):
+            xv[t * n:(t + 1) * n] = x
+            u = (K @ xv + k)[t * m:(t + 1) * m]
+            us[b, t] = u
+            x = A @ x + B @ u
+    return us
+
+
+def test_dgemm_and_operators_vs_numpy():
+    """Sw, Su and PHI_U (reverse-Cholesky + DMMA products) against the oracle's restatement of base.py:98-119 and
+    sls.py:205-233."""
+    import torch
+    for pos_dim, N, dt in ((1, 100, 0.01), (2, 50, 0.02), (3, 37, 0.05)):
+        n, m = 2 * pos_dim, pos_dim
+        A, B = M.double_integrator_AB(pos_dim, 2, dt)
+        s = _make_sls(n, m, N, A, B, np.ones((2, pos_dim)))
+        PHI, du = s.solve_sls()
+        Qt = np.zeros((N, n)); Qt[-1] = 1e6
+        xd = np.zeros((2, N, n)); xd[:, -1, :pos_dim] = 1.0
+        o = R.sls_solve(A, B, N, Qt, xd.reshape(2, -1), 1e-2)
+        assert np.abs(s.Sw.cpu().numpy() - o["Sw"]).max() < 1e-12
+        assert np.abs(s.Su.cpu().numpy() - o["Su"]).max() < 1e-12
+        PHI = PHI.cpu().numpy()
+        # cond(L) ~ 1e10: the oracle's explicit-inverse down-date chain is itself only ~1e-6 accurate here
+        assert np.abs(PHI - o["PHI_U"]).max() / np.abs(o["PHI_U"]).max() < 1e-5
+        # block-lower-triangular structure is exact
+        for i in range(N):
+            assert np.all(PHI[:i * m, i * n:(i + 1) * n] == 0.0)
+        assert np.abs(du.cpu().numpy() - o["du"]).max() / np.abs(o["du"]).max() < 1e-7
+
+
+def test_phi_u_against_high_precision():
+    """Who is right on the ill-conditioned solve: PHI_U block columns against a long-double solve of the same
+    trailing systems - the reverse-Cholesky path must be at least as accurate as the reference's down-date chain."""
+    pos_dim, N, dt = 1, 60, 0.01
+    n, m = 2, 1
+    A, B = M.double_integrator_AB(pos_dim, 2, dt)
+    s = _make_sls(n, m, N, A, B, np.ones((1, 1)))
+    PHI = s.solve_sls()[0].cpu().numpy()
+    Qt = np.zeros((N, n)); Qt[-1] = 1e6
+    o = R.sls_solve(A, B, N, Qt, np.zeros(N * n), 1e-2)
+    L = o["L"].astype(np.longdouble)
+    r = (-o["DTQ"] @ o["Sw"]).astype(np.longdouble)
+
+    def solve_ld(Mx, rhs):                      # Gaussian elimination with partial pivoting in long double
+        Mx, rhs = Mx.copy(), rhs.copy()
+        k = Mx.shape[0]
+        for c in range(k):
+            p = c + np.argmax(np.abs(Mx[c:, c]))
+            Mx[[c, p]], rhs[[c, p]] = Mx[[p, c]], rhs[[p, c]]
+            f = Mx[c + 1:, c] / Mx[c, c]
+            Mx[c + 1:] -= f[:, None] * Mx[c]
+            rhs[c + 1:] -= f[:, None] * rhs[c]
+        x = np.zeros_like(rhs)
+        for c in range(k - 1, -1, -1):
+            x[c] = (rhs[c] - Mx[c, c + 1:] @ x[c + 1:]) / Mx[c, c]
+        return x
+    err_gpu = err_ref = 0.0
+    for i in (0, 7, 31, 55):
+        exact = solve_ld(L[i * m:, i * m:], r[i * m:, i * n:(i + 1) * n]).astype(np.float64)
+        sc = np.abs(exact).max()
+        err_gpu = max(err_gpu, np.abs(PHI[i * m:, i * n:(i + 1) * n] - exact).max() / sc)
+        err_ref = max(err_ref, np.abs(o["PHI_U"][i * m:, i * n:(i + 1) * n] - exact).max() / sc)
+    print("PHI_U relative error vs long double: cuda %.2e, numpy down-date chain %.2e" % (err_gpu, err_ref))
+    assert err_gpu < 1e-7 and err_gpu < 10 * err_ref + 1e-12
+
+
+@pytest.mark.parametrize("tag,pos_dim,N,dt", [("nb", 1, 100, 0.01), ("c4", 2, 50, 1.0 / 50)])
+def test_admm_sls_vs_reference_golden_and_oracle(golden, tag, pos_dim, N, dt):
+    from isls_b200 import SetConvexSOC
+    g = golden("sls_admm")
+    n, m, A, B, tg, A_, b_ = _case(g, tag, pos_dim, N, dt)
+    s = _make_sls(n, m, N, A, B, tg)
+    proj = SetConvexSOC(A_, b_, rho=1e1, max_iter=100, threshold=1e-3)
+    du, phi_u, logs = s.ADMM_SLS(project_u=proj, max_iter=50, rho_u=1e2, alpha=1.0, tol=1e-3, log=True)
+    du, phi_u, logs = du.cpu().numpy(), phi_u.cpu().numpy(), logs.cpu().numpy()
+    iters = s.last.iters.cpu().numpy()
+    assert np.array_equal(iters, g[tag + "_iters"]), "ADMM_SLS iteration counts differ from the reference"
+    c = pos_dim + 1
+    for b in range(len(tg)):
+        it = iters[b]
+        assert np.allclose(logs[b, :it], g[tag + "_logs"][b, :it], rtol=1e-5, atol=1e-14)
+    # d_u and the robust columns: cond(L + rho I) ~ 1e4..1e8 -> 1e-7 relative to the reference's explicit inverse
+    assert np.abs(du - g[tag + "_du"]).max() / np.abs(g[tag + "_du"]).max() < 1e-7
+    assert np.abs(phi_u[:, :, :c - 1] - g[tag + "_phic"]).max() / np.abs(g[tag + "_phic"]).max() < 1e-7
+    # oracle on the same inputs incl. exit codes and inner iteration totals
+    Qt = np.zeros((N, n)); Qt[-1] = 1e6
+    xd = np.zeros((len(tg), N, n)); xd[:, -1, :pos_dim] = tg
+    o = R.admm_sls(A, B, N, Qt, xd.reshape(len(tg), -1), 1e-2, A_, b_, 1e2, max_iter=50, alpha=1.0, tol=1e-3,
+                   inner_rho=1e1, inner_max_iter=100, inner_threshold=1e-3)
+    assert np.array_equal(s.last.exit_code.cpu().numpy(), o["exit_code"])
+    assert np.array_equal(s.last.inner_total.cpu().numpy(), o["inner_total"])
+    # controller: closed-loop controls from sampled initial positions (sls_base.py:91-105) vs the reference's
+    K, k = s.controller(phi_u, du)
+    K, k = K.cpu().numpy(), k.cpu().numpy()
+    x0s = np.zeros((3, n)); x0s[:, :pos_dim] = np.array([[0.05], [-0.1], [0.12]])
+    for b in range(len(tg)):
+        u_cl = _closed_loop(A, B, K[b], k[b], x0s, N)
+        ref = g[tag + "_u_cl"][b]
+        assert np.abs(u_cl - ref).max() / np.abs(ref).max() < 1e-6
+        # K is causal: block (t, s) vanishes for s > t
+        for t in range(0, N, 7):
+            assert np.all(K[b][t * m:(t + 1) * m, (t + 1) * n:] == 0.0)
+
+
+def test_admm_sls_config4_batch_properties():
+    """BASELINE config 4 size: 1,024 problems (n=4, m=2, N=50), per-problem targets U[0.6, 1.0]: agreement of a
+    subsample with the oracle, determinism, and the chance constraint |d_u| + psi * ||sigma Phi|| <= bound."""
+    from scipy.stats import norm
+    from isls_b200 import SetConvexSOC
+    pos_dim, N, dt, Bn = 2, 50, 1.0 / 50, 1024
+    n, m = 4, 2
+    A, B = M.double_integrator_AB(pos_dim, 2, dt)
+    rng = np.random.default_rng(1234 + 4)
+    tg = rng.uniform(0.6, 1.0, (Bn, 2))
+    mu = np.zeros(3); mu[0] = 1.0
+    sigma = np.array([0.0, 0.01, 0.01]); psi = norm.ppf(0.95)
+    Au = np.diag(np.sqrt(sigma))
+    A_ = [np.concatenate([Au, (-mu / psi)[None]], 0), np.concatenate([Au, (mu / psi)[None]], 0)]
+    b_ = [np.append(np.zeros(3), 5.0 / psi), np.append(np.zeros(3), 5.0 / psi)]
+    s = _make_sls(n, m, N, A, B, tg)
+    proj = SetConvexSOC(A_, b_, rho=1e1, max_iter=100, threshold=1e-3)
+    du, phi_u, logs = s.ADMM_SLS(project_u=proj, max_iter=50, rho_u=1e2, alpha=1.0, tol=1e-3, log=True)
+    it1 = s.last.iters.cpu().numpy().copy()
+    du2, phi2, _ = s.ADMM_SLS(project_u=proj, max_iter=50, rho_u=1e2, alpha=1.0, tol=1e-3, log=True)
+    assert np.array_equal(du.cpu().numpy(), du2.cpu().numpy()) and np.array_equal(it1, s.last.iters.cpu().numpy())
+    du, phi_u = du.cpu().numpy(), phi_u.cpu().numpy()
+    idx = rng.choice(Bn, 6, replace=False)
+    Qt = np.zeros((N, n)); Qt[-1] = 1e6
+    xd = np.zeros((len(idx), N, n)); xd[:, -1, :pos_dim] = tg[idx]
+    o = R.admm_sls(A, B, N, Qt, xd.reshape(len(idx), -1), 1e-2, A_, b_, 1e2, max_iter=50, alpha=1.0, tol=1e-3,
+                   inner_rho=1e1, inner_max_iter=100, inner_threshold=1e-3)
+    assert np.array_equal(it1[idx], o["iters"])
+    assert np.abs(du[idx] - o["du"]).max() / np.abs(o["du"]).max() < 1e-7
+    assert np.abs(phi_u[idx, :, :2] - o["phi_u"][:, :, :2]).max() / np.abs(o["phi_u"][:, :, :2]).max() < 1e-7
+    # converged problems satisfy the chance constraint up to the ADMM tolerance
+    conv = s.last.exit_code.cpu().numpy() == 1
+    lhs = np.abs(du) + psi * np.sqrt(0.01) * np.linalg.norm(phi_u[:, :, :2], axis=-1)
+    if conv.any():
+        assert lhs[conv].max() < 5.0 + 5e-2

@@ -113,3 +113,36 @@ def test_notebook_pins(golden):
     assert int(o["iters"][0]) == int(g["di_admm_dp_iters"])
     assert np.abs(o["u"][0] - g["di_admm_dp_u"]).max() < 1e-9
     assert np.abs(o["x"][0] - g["di_admm_dp_x"]).max() < 1e-9
+
+
+def _sls_case(g, tag, pos_dim, N, dt, u_std=1e-2, Qf=1e6):
+    from oracle import models as M
+    n, m = 2 * pos_dim, pos_dim
+    A, B = M.double_integrator_AB(pos_dim, 2, dt)
+    Qt = np.zeros((N, n)); Qt[-1] = Qf
+    tg = g[tag + "_targets"]
+    xd = np.zeros((len(tg), N, n)); xd[:, -1, :pos_dim] = tg
+    return A, B, Qt, xd.reshape(len(tg), -1), [a for a in g[tag + "_A_"]], [b for b in g[tag + "_b_"]]
+
+
+def test_sls_admm_matches_reference(golden):
+    """SLS.solve_sls + ADMM_SLS (SOC chance constraints): iteration counts, residual logs, d_u and the robust
+    Phi_u columns against the unmodified reference; includes the notebook printout 'can't improve anymore at
+    iteration 25', residual 8.50e-13 3.77e-01."""
+    g = golden("sls_admm")
+    for tag, pos_dim, N, dt in (("nb", 1, 100, 0.01), ("c4", 2, 50, 1.0 / 50)):
+        A, B, Qt, xd, A_, b_ = _sls_case(g, tag, pos_dim, N, dt)
+        o = R.admm_sls(A, B, N, Qt, xd, 1e-2, A_, b_, 1e2, max_iter=50, alpha=1.0, tol=1e-3, inner_rho=1e1,
+                       inner_max_iter=100, inner_threshold=1e-3)
+        assert np.array_equal(o["iters"], g[tag + "_iters"])
+        for b in range(len(xd)):
+            it = o["iters"][b]
+            assert np.allclose(o["logs"][b], g[tag + "_logs"][b, :it], rtol=1e-6, atol=1e-15)
+        assert np.abs(o["du0"] - g[tag + "_du0"]).max() < 1e-9
+        assert np.abs(o["du"] - g[tag + "_du"]).max() < 1e-9
+        c = pos_dim + 1
+        assert np.abs(o["phi_u"][:, :, :c - 1] - g[tag + "_phic"]).max() < 1e-9
+        # shared feedback part: the reference's Woodbury down-date chain (base.py:32-50) on cond(L) ~ 1e10 limits
+        # agreement of PHI_U to ~1e-6 relative
+        assert np.abs(o["PHI_U"] - g[tag + "_PHI0"]).max() / np.abs(g[tag + "_PHI0"]).max() < 1e-5
+    assert int(g["nb_iters"][0]) == 26 and "%.2e %.2e" % tuple(g["nb_last"][0]) == "8.50e-13 3.77e-01"
