@@ -195,12 +195,12 @@ def run_b200(a):
     h_zs = torch.from_numpy(p["zs"]).pin_memory()
     h_out = {k: torch.empty(sv.out[k].shape, dtype=sv.out[k].dtype).pin_memory()
              for k in ("x", "u", "cost", "status", "cost_log")}
-    gathered = [torch.empty(B, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+    from isls_b200.sharding import gather_scalars
 
     def solve():
         out = sv.ilqr_admm(tol=p["tol"], fixed_budget=fixed)
         if world > 1:                                       # NCCL only gathers per-problem result scalars
-            dist.all_gather(gathered, out.cost)
+            gather_scalars(out.cost, B * world)
         return out
 
     def step_e2e():

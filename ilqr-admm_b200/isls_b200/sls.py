@@ -127,7 +127,7 @@ class SLS:
             zs = zs[None]
         xd = zs[:, self.seq].reshape(zs.shape[0], -1)
         xd = np.ascontiguousarray(np.broadcast_to(xd, (self.nb, self.N * self.x_dim)))
-        return torch.from_numpy(xd).to(self.device)
+        return torch.from_numpy(xd.copy()).to(self.device)
 
     @property
     def Sw(self):
