@@ -386,12 +386,9 @@ __global__ void k_kpass(Dev d) {
 // HBM-bound kernel: the Jacobian scalars are recomputed from (x^_t, u^_t) (loaded anyway for cx, cu) instead of
 // being read back; the backward sweep streams Qux_t and the packed Quu_t, Quu_t^-1, the forward sweep K_t.
 template <class M>
-__global__ void k_ff(Dev d) {
+__device__ __forceinline__ void ff_body(const Dev &d, const TileCtx<M> &c) {
   constexpr int n = M::n, m = M::m, nt = NTRI(M::m);
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
-  if (tile >= d.tile1) return;
-  TileCtx<M> c(d, tile, threadIdx.x);
-  if (d.odone[c.b] || d.adone[c.b]) return;
+  const int tile = c.tile;
   const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m);
   const double *Kg = c.at(d.Kg, d, m * n), *Qx = c.at(d.Qux, d, m * n);
   const double *Qu = c.at(d.Quu, d, nt), *Qi = c.at(d.Qui, d, nt);
@@ -505,6 +502,15 @@ __global__ void k_ff(Dev d) {
   d.cq[2 * S + c.b] = c2;
 }
 
+template <class M>
+__global__ void k_ff(Dev d) {
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
+  TileCtx<M> c(d, tile, threadIdx.x);
+  if (d.odone[c.b] || d.adone[c.b]) return;
+  ff_body<M>(d, c);
+}
+
 // np.argmin semantics over candidate costs (first minimum; the first NaN wins, isls/isls.py:477)
 __device__ __forceinline__ int argmin_np(const double *c, int L, int stride, bool *has_nan) {
   double best = c[0];
@@ -524,8 +530,14 @@ __device__ __forceinline__ int argmin_np(const double *c, int L, int stride, boo
 // take the argmin unconditionally.  CTA = 32 problems x W warps, CPT candidates per thread (independent FP64
 // chains, shared operand loads).  The control part of the cost comes from the per-problem quadratic (c0,c1,c2)
 // accumulated by k_ff, so the hot loop is: 2 FMA for u, sincos, 5 FMA-type model updates (+ state terms).
+template <class M>
+__device__ __forceinline__ void admm_body(const Dev &d, const TileCtx<M> &c, int outer, int inner);
+
+// fuse bit 1: warp 0 first runs the ff-pass + linear rollout of its tile (ff_body); fuse bit 2: warp 0 finishes with
+// the winner rollout + ADMM update (admm_body).  The single-warp HBM-bound phases of one CTA overlap the FP64-bound
+// candidate rollouts of the other CTAs resident on the SM.
 template <class M, int CPT, int MAXW, int MINB>
-__global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d) {
+__global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fuse, int outer, int inner) {
   constexpr int n = M::n, m = M::m;
   __shared__ double sc[MAX_L][TILE];
   const int tile = d.tile0 + blockIdx.x;
@@ -533,6 +545,10 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d) {
   const int w = threadIdx.y;
   const bool skip = d.odone[c.b] || d.adone[c.b];
   if (__syncthreads_and(skip)) return;
+  if (fuse & 1) {
+    if (w == 0 && !skip) ff_body<M>(d, c);
+    __syncthreads();
+  }
   if (!skip) {
     const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m), *du = c.at(d.du, d, m);
     const double *rgx = c.at(d.rgx, d, n);
@@ -647,6 +663,7 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d) {
       double *o = d.lsc + (size_t)tile * d.L * TILE + c.lane;
       for (int l = 0; l < d.L; l++) o[(size_t)l * TILE] = sc[l][c.lane];
     }
+    if (fuse & 2) admm_body<M>(d, c, outer, inner);
   }
 }
 
@@ -670,12 +687,9 @@ __device__ __forceinline__ void admm_elem(double x, double relax, double lo, dou
 // isls/isls.py:478; it is not stored - k_outer_end re-rolls the last one in place), apply the z-projection and scaled dual update element by element (admm.py:43-59), form the
 // residual norms (admm.py:62-69) and run the stop tests (admm.py:72-85).
 template <class M>
-__global__ void k_admm(Dev d, int outer, int inner) {
+__device__ __forceinline__ void admm_body(const Dev &d, const TileCtx<M> &c, int outer, int inner) {
   constexpr int n = M::n, m = M::m;
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
-  if (tile >= d.tile1) return;
-  TileCtx<M> c(d, tile, threadIdx.x);
-  if (d.odone[c.b] || d.adone[c.b]) return;
+  const int tile = c.tile;
   const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m), *du = c.at(d.du, d, m);
   double *zx = c.at(d.zx, d, n), *lx = c.at(d.lx, d, n), *rgx = c.at(d.rgx, d, n);
   double *zu = c.at(d.zu, d, m), *lu = c.at(d.lu, d, m), *rgu = c.at(d.rgu, d, m);
@@ -749,6 +763,15 @@ __global__ void k_admm(Dev d, int outer, int inner) {
     d.adone[c.b] = 1;
     if (c.valid && d.out.admm_exit) d.out.admm_exit[c.b * d.max_outer + outer] = ex;
   }
+}
+
+template <class M>
+__global__ void k_admm(Dev d, int outer, int inner) {
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
+  TileCtx<M> c(d, tile, threadIdx.x);
+  if (d.odone[c.b] || d.adone[c.b]) return;
+  admm_body<M>(d, c, outer, inner);
 }
 
 // After ADMM (isls/isls.py:488-499): nominal <- last primal iterate, cost log, outer stop tests.
@@ -1591,11 +1614,12 @@ static dim3 tp_grid(const Dev &d) { return dim3((d.tile1 - d.tile0 + TPB_TILES -
 
 // Line-search CTA shape: CPT candidates per thread (independent FP64 chains, shared loads), W = ceil(L/CPT)
 // warps.  MAXW only feeds __launch_bounds__ (register budget).
+struct LsFuse { int fuse, outer, inner; };
 template <class M, int CPT, int MAXW, int MINB = 1>
-static void launch_ls_cfg(const Dev &d, bool closed, cudaStream_t s) {
+static void launch_ls_cfg(const Dev &d, bool closed, cudaStream_t s, LsFuse f) {
   const int W = (d.L + CPT - 1) / CPT;
   if (closed) k_linesearch_closed<M, CPT, MAXW, MINB><<<d.tile1 - d.tile0, dim3(TILE, W), 0, s>>>(d);
-  else k_linesearch<M, CPT, MAXW, MINB><<<d.tile1 - d.tile0, dim3(TILE, W), 0, s>>>(d);
+  else k_linesearch<M, CPT, MAXW, MINB><<<d.tile1 - d.tile0, dim3(TILE, W), 0, s>>>(d, f.fuse, f.outer, f.inner);
 }
 static int solve_chunks() {
   static int v = -1;
@@ -1603,6 +1627,14 @@ static int solve_chunks() {
     const char *e = getenv("ISLS_CHUNKS");      // number of concurrently running batch chunks (streams)
     v = e ? atoi(e) : 1;
     if (v < 1) v = 1;
+  }
+  return v;
+}
+static int solve_fuse() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("ISLS_FUSE");        // bit 1: ff-pass fused into the line-search CTA, bit 2: ADMM update
+    v = e ? atoi(e) : 0;
   }
   return v;
 }
@@ -1615,20 +1647,20 @@ static int ls_cpt_override() {
   return v;
 }
 template <class M>
-static void launch_linesearch(const Dev &d, bool closed, cudaStream_t s) {
+static void launch_linesearch(const Dev &d, bool closed, cudaStream_t s, LsFuse f = LsFuse{0, 0, 0}) {
   const int ov = ls_cpt_override();
   if constexpr (M::n >= 9) {
-    if (d.L <= 8) launch_ls_cfg<M, 1, 8>(d, closed, s);
-    else launch_ls_cfg<M, 2, 25>(d, closed, s);
+    if (d.L <= 8) launch_ls_cfg<M, 1, 8>(d, closed, s, f);
+    else launch_ls_cfg<M, 2, 25>(d, closed, s, f);
   } else {
     if (d.L <= 20) {
-      if (ov == 1) launch_ls_cfg<M, 1, 20>(d, closed, s);
-      else if (ov == 2) launch_ls_cfg<M, 2, 10, 2>(d, closed, s);
-      else if (ov == 5) launch_ls_cfg<M, 5, 4, 2>(d, closed, s);
-      else if (ov == 42) launch_ls_cfg<M, 4, 5, 2>(d, closed, s);
-      else if (ov == 44) launch_ls_cfg<M, 4, 5, 4>(d, closed, s);
-      else launch_ls_cfg<M, 4, 5, 3>(d, closed, s);      // 4 chains/thread, 5 warps, 3 CTAs/SM (128 regs)
-    } else launch_ls_cfg<M, 4, 13>(d, closed, s);
+      if (ov == 1) launch_ls_cfg<M, 1, 20>(d, closed, s, f);
+      else if (ov == 2) launch_ls_cfg<M, 2, 10, 2>(d, closed, s, f);
+      else if (ov == 5) launch_ls_cfg<M, 5, 4, 2>(d, closed, s, f);
+      else if (ov == 42) launch_ls_cfg<M, 4, 5, 2>(d, closed, s, f);
+      else if (ov == 44) launch_ls_cfg<M, 4, 5, 4>(d, closed, s, f);
+      else launch_ls_cfg<M, 4, 5, 3>(d, closed, s, f);      // 4 chains/thread, 5 warps, 3 CTAs/SM (128 regs)
+    } else launch_ls_cfg<M, 4, 13>(d, closed, s, f);
   }
 }
 
@@ -1670,9 +1702,10 @@ extern "C" int isls_ilqr_admm_solve_f64(const isls_plan *plan, const isls_solve_
       for (int j = 0; j < d.max_outer; j++) {
         LAUNCH(ISLS_KC_KPASS, cs, (k_kpass<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc)));
         for (int a = 0; a < d.max_admm; a++) {
-          LAUNCH(ISLS_KC_FF, cs, (k_ff<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc)));
-          LAUNCH(ISLS_KC_LINESEARCH, cs, launch_linesearch<M>(dc, false, cs));
-          LAUNCH(ISLS_KC_ADMM, cs, (k_admm<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, j, a)));
+          const int fuse = solve_fuse();
+          if (!(fuse & 1)) LAUNCH(ISLS_KC_FF, cs, (k_ff<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc)));
+          LAUNCH(ISLS_KC_LINESEARCH, cs, launch_linesearch<M>(dc, false, cs, LsFuse{fuse, j, a}));
+          if (!(fuse & 2)) LAUNCH(ISLS_KC_ADMM, cs, (k_admm<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, j, a)));
         }
         LAUNCH(ISLS_KC_OUTER_END, cs, (k_outer_end<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, j)));
       }
