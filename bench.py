@@ -252,7 +252,7 @@ def run_b200(a):
     if rank == 0:
         fp64_peak = S.measure_fp64_tflops(dev)
         S.profile_enable(True)
-        solve()
+        sv.ilqr_admm(tol=p["tol"], fixed_budget=fixed)      # rank-0-only pass: no collective in here
         prof = S.profile_collect()
         S.profile_enable(False)
         tot = sum(v[0] for v in prof.values())
