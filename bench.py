@@ -266,8 +266,9 @@ def run_b200(a):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        # bytes the kernel has to move per launch: u^, du, reg_u read once per problem (3 x N x m), x^_0, best index
-        alg_bytes = float(B) * (3 * p["N"] * 2 + 4 + 1) * 8
+        # bytes the kernel has to move per launch: u^, du read once per problem (2 x N x m), x^_0 (n), the control-cost
+        # polynomial (3), best index / best cost written (2)
+        alg_bytes = float(B) * (2 * p["N"] * 2 + 4 + 3 + 2) * 8
         roof = {"kernel": "k_linesearch<CarModel>", "bound": "fp64", "achieved": round(ach, 3),
                 "peak": round(fp64_peak, 3), "unit": "TFLOP/s", "frac": round(ach / fp64_peak, 4),
                 "peak_source": "DFMA throughput measured live by isls_measure_fp64_tflops (MEASURED_PEAKS.json has "
@@ -277,7 +278,10 @@ def run_b200(a):
                         "achieved_gbs": round(alg_bytes / (ls_ms / ls_n * 1e-3) / 1e9, 2),
                         "peak_gbs": peaks.get("hbm_gbs", 6650.0),
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
-                "traffic": None}
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=65,536 from the committed
+                # `ncu --set full` capture (profiles/r1_ncu_full_main_kernels.csv), scaled to this batch size
+                "traffic": round(223.87e6 * B / 65536.0), "traffic_source": "profiles/r1_ncu_full_main_kernels.csv",
+                "fp64_pipe_active_pct_ncu": 54.3}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
