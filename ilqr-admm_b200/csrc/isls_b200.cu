@@ -1657,9 +1657,16 @@ static void launch_linesearch(const Dev &d, bool closed, cudaStream_t s, LsFuse 
       if (ov == 1) launch_ls_cfg<M, 1, 20>(d, closed, s, f);
       else if (ov == 2) launch_ls_cfg<M, 2, 10, 2>(d, closed, s, f);
       else if (ov == 5) launch_ls_cfg<M, 5, 4, 2>(d, closed, s, f);
+      else if (ov == 73) launch_ls_cfg<M, 7, 3, 3>(d, closed, s, f);
+      else if (ov == 74) launch_ls_cfg<M, 7, 3, 4>(d, closed, s, f);
+      else if (ov == 75) launch_ls_cfg<M, 7, 3, 5>(d, closed, s, f);
+      else if (ov == 43) launch_ls_cfg<M, 4, 5, 3>(d, closed, s, f);
+      else if (ov == 54) launch_ls_cfg<M, 5, 4, 4>(d, closed, s, f);
+      else if (ov == 103) launch_ls_cfg<M, 10, 2, 3>(d, closed, s, f);
+      else if (ov == 104) launch_ls_cfg<M, 10, 2, 4>(d, closed, s, f);
       else if (ov == 42) launch_ls_cfg<M, 4, 5, 2>(d, closed, s, f);
       else if (ov == 44) launch_ls_cfg<M, 4, 5, 4>(d, closed, s, f);
-      else launch_ls_cfg<M, 4, 5, 3>(d, closed, s, f);      // 4 chains/thread, 5 warps, 3 CTAs/SM (128 regs)
+      else launch_ls_cfg<M, 5, 4, 3>(d, closed, s, f);      // 5 chains/thread, 4 warps, 3 CTAs/SM (168 regs, no spills)
     } else launch_ls_cfg<M, 4, 13>(d, closed, s, f);
   }
 }
