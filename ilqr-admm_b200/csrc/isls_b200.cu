@@ -79,7 +79,8 @@ struct Dev {
   double *lsc;           // [T][L][32] candidate costs of the last line search
   // per-problem scalars [T*32]
   double *cost, *prev_cost, *prim, *dual, *cost_adm, *best_cost;
-  double *cq;            // [3][T*32] control-cost polynomial of the current line search: c0 + a c1 + a^2 c2
+  double *cq;            // [6][T*32] control-cost polynomials of the current line search: rows 0-2 cost + ADMM
+                         // penalty c0 + a c1 + a^2 c2, rows 3-5 the R-only part (cost of the winner without penalty)
   int *best, *odone, *adone, *nlog, *status, *oit, *ait;
   // options
   int max_outer, max_admm, fixed_budget, last_stage_dp;
@@ -460,7 +461,7 @@ __device__ __forceinline__ void ff_body(const Dev &d, const TileCtx<M> &c) {
   double dx[n];
 #pragma unroll
   for (int i = 0; i < n; i++) dx[i] = 0.0;
-  double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0;
   for (int t = 0; t < d.N; t++) {
     double duv[m], u[m];
 #pragma unroll
@@ -473,17 +474,15 @@ __device__ __forceinline__ void ff_body(const Dev &d, const TileCtx<M> &c) {
       duv[a] = acc + EL(kk, m, t, a);
       EL(du, m, t, a) = duv[a];
       u[a] = EL(uh, m, t, a);
-      const double R = d.u_std;
-      c0 = fma(R * u[a], u[a], c0);
-      c1 = fma(2.0 * R * u[a], duv[a], c1);
-      double w2 = R;
-      if (d.proj_u) {
+      r0 = fma(u[a], u[a], r0);                 // R-only part (scaled by u_std after the loop)
+      r1 = fma(u[a], duv[a], r1);
+      r2 = fma(duv[a], duv[a], r2);
+      if (d.proj_u) {                           // ADMM penalty part
         const double rho = d.rho_u[t * m + a], e = u[a] - EL(rgu, m, t, a);
         c0 = fma(rho * e, e, c0);
         c1 = fma(2.0 * rho * e, duv[a], c1);
-        w2 += rho;
+        c2 = fma(rho * duv[a], duv[a], c2);
       }
-      c2 = fma(w2 * duv[a], duv[a], c2);
     }
     if (t < d.N - 1) {
       double x[n], J[M::NJA], dxn[n];
@@ -497,9 +496,15 @@ __device__ __forceinline__ void ff_body(const Dev &d, const TileCtx<M> &c) {
     }
   }
   const size_t S = (size_t)d.T * TILE;
-  d.cq[c.b] = c0;
-  d.cq[S + c.b] = c1;
-  d.cq[2 * S + c.b] = c2;
+  r0 *= d.u_std;                       // R sum u^2, 2R sum u du, R sum du^2  (R = u_std I)
+  r1 *= 2.0 * d.u_std;
+  r2 *= d.u_std;
+  d.cq[c.b] = c0 + r0;
+  d.cq[S + c.b] = c1 + r1;
+  d.cq[2 * S + c.b] = c2 + r2;
+  d.cq[3 * S + c.b] = r0;
+  d.cq[4 * S + c.b] = r1;
+  d.cq[5 * S + c.b] = r2;
 }
 
 template <class M>
@@ -530,8 +535,27 @@ __device__ __forceinline__ int argmin_np(const double *c, int L, int stride, boo
 // take the argmin unconditionally.  CTA = 32 problems x W warps, CPT candidates per thread (independent FP64
 // chains, shared operand loads).  The control part of the cost comes from the per-problem quadratic (c0,c1,c2)
 // accumulated by k_ff, so the hot loop is: 2 FMA for u, sincos, 5 FMA-type model updates (+ state terms).
+// z <- clip(relax*x + (1-relax)*z + lam); r = x - z; lam += r   (isls/admm.py:43-59, projections.py:7-11).
+// Written with explicit round-to-nearest intrinsics (no FMA contraction) so it is bit-identical to numpy on
+// the same inputs.
+__device__ __forceinline__ void admm_elem(double x, double relax, double lo, double hi, double &z, double &lam,
+                                          double &rsq, double &dsq, int &mask) {
+  const double pre = __dadd_rn(__dadd_rn(__dmul_rn(relax, x), __dmul_rn(__dsub_rn(1.0, relax), z)), lam);
+  const double zn = fmin(fmax(pre, lo), hi);
+  mask = (pre > hi) - (pre < lo);
+  const double r = __dsub_rn(x, zn);
+  const double dz = __dsub_rn(zn, z);
+  lam = __dadd_rn(lam, r);
+  z = zn;
+  rsq = fma(r, r, rsq);
+  dsq = fma(dz, dz, dsq);
+}
+
 template <class M>
 __device__ __forceinline__ void admm_body(const Dev &d, const TileCtx<M> &c, int outer, int inner);
+template <class M>
+__device__ __forceinline__ void admm_finish(const Dev &d, const TileCtx<M> &c, int outer, int inner, int bi,
+                                            double prim, double dual);
 
 // fuse bit 1: warp 0 first runs the ff-pass + linear rollout of its tile (ff_body); fuse bit 2: warp 0 finishes with
 // the winner rollout + ADMM update (admm_body).  The single-warp HBM-bound phases of one CTA overlap the FP64-bound
@@ -540,6 +564,9 @@ template <class M, int CPT, int MAXW, int MINB>
 __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fuse, int outer, int inner) {
   constexpr int n = M::n, m = M::m;
   __shared__ double sc[MAX_L][TILE];
+  __shared__ double scs[MAX_L][TILE];        // state-cost part of every candidate (cost of the winner w/o penalty)
+  __shared__ double sred[2][MAXW][TILE];     // residual partial sums of the fused ADMM update
+  __shared__ int sbest[TILE];
   const int tile = d.tile0 + blockIdx.x;
   TileCtx<M> c(d, tile, threadIdx.x);
   const int w = threadIdx.y;
@@ -649,6 +676,7 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
         double tot = cs[q] + fma(al[q], fma(al[q], c2, c1), c0);   // cost_function + control penalty (isls.py:470,476)
         if (d.proj_x) tot += px[q];                                // isls.py:473
         sc[l][c.lane] = tot;
+        scs[l][c.lane] = cs[q];
       }
     }
   }
@@ -658,6 +686,7 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
     const int idx = argmin_np(&sc[0][c.lane], d.L, TILE, &has_nan);
     d.best[c.b] = idx;
     d.best_cost[c.b] = sc[idx][c.lane];
+    sbest[c.lane] = idx;
     if (has_nan) d.status[c.b] |= ISLS_ST_NAN_COST;
     if (d.lsc) {
       double *o = d.lsc + (size_t)tile * d.L * TILE + c.lane;
@@ -665,22 +694,65 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
     }
     if (fuse & 2) admm_body<M>(d, c, outer, inner);
   }
-}
-
-// z <- clip(relax*x + (1-relax)*z + lam); r = x - z; lam += r   (isls/admm.py:43-59, projections.py:7-11).
-// Written with explicit round-to-nearest intrinsics (no FMA contraction) so it is bit-identical to numpy on
-// the same inputs.
-__device__ __forceinline__ void admm_elem(double x, double relax, double lo, double hi, double &z, double &lam,
-                                          double &rsq, double &dsq, int &mask) {
-  const double pre = __dadd_rn(__dadd_rn(__dmul_rn(relax, x), __dmul_rn(__dsub_rn(1.0, relax), z)), lam);
-  const double zn = fmin(fmax(pre, lo), hi);
-  mask = (pre > hi) - (pre < lo);
-  const double r = __dsub_rn(x, zn);
-  const double dz = __dsub_rn(zn, z);
-  lam = __dadd_rn(lam, r);
-  z = zn;
-  rsq = fma(r, r, rsq);
-  dsq = fma(dz, dz, dsq);
+  if (!(fuse & 4)) return;
+  // ---- fused ADMM update for control-only projections (admm.py:43-97): z_u, lambda_u and reg_u depend on the winner
+  // only through u = u^ + alpha* du, so the whole CTA streams the tile's N x m elements (warp w takes t = w, w+W, ..)
+  // instead of a separate trajectory-per-thread kernel re-rolling the model.  Residual sums: fixed-order reduction.
+  __syncthreads();
+  const int W = blockDim.y;
+  double pru = 0.0, dru = 0.0;
+  if (!skip) {
+    const double *uh = c.at(d.uh, d, m), *du = c.at(d.du, d, m);
+    double *zu = c.at(d.zu, d, m), *lu = c.at(d.lu, d, m), *rgu = c.at(d.rgu, d, m);
+    const double al = d.alphas[sbest[c.lane]];
+    int8_t *mku = (d.out.mask_u && c.valid) ? d.out.mask_u + c.b * d.N * m : nullptr;
+    constexpr int UB = 7;                       // time steps in flight per thread (all loads issued before use)
+    for (int t0 = w; t0 < d.N; t0 += W * UB) {
+      double uv[UB][m], zv[UB][m], lv[UB][m], lo[UB][m], hi[UB][m];
+#pragma unroll
+      for (int q = 0; q < UB; q++) {
+        const int t = t0 + q * W;
+        if (t < d.N) {
+#pragma unroll
+          for (int j = 0; j < m; j++) {
+            uv[q][j] = fma(al, EL(du, m, t, j), EL(uh, m, t, j));        // identical to the candidate's u
+            zv[q][j] = EL(zu, m, t, j);
+            lv[q][j] = EL(lu, m, t, j);
+            lo[q][j] = d.lo_u[t * m + j];
+            hi[q][j] = d.hi_u[t * m + j];
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < UB; q++) {
+        const int t = t0 + q * W;
+        if (t < d.N) {
+#pragma unroll
+          for (int j = 0; j < m; j++) {
+            int mk;
+            admm_elem(uv[q][j], d.relax, lo[q][j], hi[q][j], zv[q][j], lv[q][j], pru, dru, mk);
+            EL(zu, m, t, j) = zv[q][j];
+            EL(lu, m, t, j) = lv[q][j];
+            EL(rgu, m, t, j) = __dsub_rn(zv[q][j], lv[q][j]);
+            if (mku) mku[t * m + j] = (int8_t)mk;
+          }
+        }
+      }
+    }
+  }
+  sred[0][w][c.lane] = pru;
+  sred[1][w][c.lane] = dru;
+  __syncthreads();
+  if (w == 0 && !skip) {
+    double ps = 0.0, ds = 0.0;
+    for (int q = 0; q < W; q++) { ps += sred[0][q][c.lane]; ds += sred[1][q][c.lane]; }
+    const int bi = sbest[c.lane];
+    const double al = d.alphas[bi];
+    const size_t S = (size_t)d.T * TILE;
+    // cost of the winner without penalties: state part of its rollout + R-only control polynomial
+    d.cost_adm[c.b] = scs[bi][c.lane] + fma(al, fma(al, d.cq[5 * S + c.b], d.cq[4 * S + c.b]), d.cq[3 * S + c.b]);
+    admm_finish<M>(d, c, outer, inner, bi, sqrt(ps), sqrt(ds));
+  }
 }
 
 // Winner rollout + ADMM update: re-roll the chosen candidate (the primal iterate (x,u) returned by f_argmin,
@@ -735,7 +807,13 @@ __device__ __forceinline__ void admm_body(const Dev &d, const TileCtx<M> &c, int
     for (int i = 0; i < n; i++) x[i] = xn[i];
   }
   d.cost_adm[c.b] = cs + d.u_std * cc;
-  const double prim = sqrt(prx) + sqrt(pru), dual = sqrt(drx) + sqrt(dru);   // admm.py:62-69
+  admm_finish<M>(d, c, outer, inner, bi, sqrt(prx) + sqrt(pru), sqrt(drx) + sqrt(dru));   // admm.py:62-69
+}
+
+// residual log + ADMM stop tests (admm.py:62-97) of one problem after its z / lambda update
+template <class M>
+__device__ __forceinline__ void admm_finish(const Dev &d, const TileCtx<M> &c, int outer, int inner, int bi,
+                                            double prim, double dual) {
   const double pprim = d.prim[c.b], pdual = d.dual[c.b];
   d.prim[c.b] = prim;
   d.dual[c.b] = dual;
@@ -1096,25 +1174,30 @@ __global__ void k_pack_stage(Dev d, const double *x_nom, const double *u_nom, co
       if (d.proj_u) EL(rgu, m, t, j) = regu[(c.bb * d.N + t) * m + j];
     }
   }
-  double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0;
   for (int t = 0; t < d.N; t++)
     for (int j = 0; j < m; j++) {
-      const double u = EL(uh, m, t, j), dv = EL(du, m, t, j), R = d.u_std;
-      c0 = fma(R * u, u, c0);
-      c1 = fma(2.0 * R * u, dv, c1);
-      double w2 = R;
+      const double u = EL(uh, m, t, j), dv = EL(du, m, t, j);
+      r0 = fma(u, u, r0);
+      r1 = fma(u, dv, r1);
+      r2 = fma(dv, dv, r2);
       if (d.proj_u) {
         const double rho = d.rho_u[t * m + j], e = u - EL(rgu, m, t, j);
         c0 = fma(rho * e, e, c0);
         c1 = fma(2.0 * rho * e, dv, c1);
-        w2 += rho;
+        c2 = fma(rho * dv, dv, c2);
       }
-      c2 = fma(w2 * dv, dv, c2);
     }
   const size_t S = (size_t)d.T * TILE;
-  d.cq[c.b] = c0;
-  d.cq[S + c.b] = c1;
-  d.cq[2 * S + c.b] = c2;
+  r0 *= d.u_std;
+  r1 *= 2.0 * d.u_std;
+  r2 *= d.u_std;
+  d.cq[c.b] = c0 + r0;
+  d.cq[S + c.b] = c1 + r1;
+  d.cq[2 * S + c.b] = c2 + r2;
+  d.cq[3 * S + c.b] = r0;
+  d.cq[4 * S + c.b] = r1;
+  d.cq[5 * S + c.b] = r2;
   d.odone[c.b] = 0;
   d.adone[c.b] = 0;
   d.status[c.b] = 0;
@@ -1572,7 +1655,7 @@ static size_t carve(const isls_plan *p, long long B, char *base, Dev *d) {
   const size_t S = T * TILE;
   takeD(d ? &d->cost : nullptr, S); takeD(d ? &d->prev_cost : nullptr, S); takeD(d ? &d->prim : nullptr, S);
   takeD(d ? &d->dual : nullptr, S); takeD(d ? &d->cost_adm : nullptr, S); takeD(d ? &d->best_cost : nullptr, S);
-  takeD(d ? &d->cq : nullptr, 3 * S);
+  takeD(d ? &d->cq : nullptr, 6 * S);
   takeI(d ? &d->best : nullptr, S); takeI(d ? &d->odone : nullptr, S); takeI(d ? &d->adone : nullptr, S);
   takeI(d ? &d->nlog : nullptr, S); takeI(d ? &d->status : nullptr, S); takeI(d ? &d->oit : nullptr, S);
   takeI(d ? &d->ait : nullptr, S);
@@ -1636,6 +1719,11 @@ static int solve_fuse() {
     const char *e = getenv("ISLS_FUSE");        // bit 1: ff-pass fused into the line-search CTA, bit 2: ADMM update
     v = e ? atoi(e) : 0;
   }
+  return v;
+}
+static int no_fused_update() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("ISLS_NO_FUSED_UPDATE"); v = e ? atoi(e) : 0; }
   return v;
 }
 static int ls_cpt_override() {
@@ -1709,10 +1797,11 @@ extern "C" int isls_ilqr_admm_solve_f64(const isls_plan *plan, const isls_solve_
       for (int j = 0; j < d.max_outer; j++) {
         LAUNCH(ISLS_KC_KPASS, cs, (k_kpass<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc)));
         for (int a = 0; a < d.max_admm; a++) {
-          const int fuse = solve_fuse();
+          int fuse = solve_fuse();
+          if (!(fuse & 2) && !d.proj_x && d.proj_u && !no_fused_update()) fuse |= 4;   // streaming ADMM epilogue
           if (!(fuse & 1)) LAUNCH(ISLS_KC_FF, cs, (k_ff<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc)));
           LAUNCH(ISLS_KC_LINESEARCH, cs, launch_linesearch<M>(dc, false, cs, LsFuse{fuse, j, a}));
-          if (!(fuse & 2)) LAUNCH(ISLS_KC_ADMM, cs, (k_admm<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, j, a)));
+          if (!(fuse & 6)) LAUNCH(ISLS_KC_ADMM, cs, (k_admm<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, j, a)));
         }
         LAUNCH(ISLS_KC_OUTER_END, cs, (k_outer_end<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, j)));
       }
