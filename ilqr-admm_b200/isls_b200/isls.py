@@ -159,6 +159,9 @@ class iSLS:
         return self._plan_cache[key]
 
     def _publish(self, out):
+        # the solver state persists like the reference's (x_nom, u_nom): a following call continues from here
+        self._x0 = out.x[:, 0].clone()
+        self._u_init = out.u.clone()
         sq = (lambda t: t[0]) if self.batch is None else (lambda t: t)
         self.x_nom, self.u_nom = sq(out.x), sq(out.u)
         self.cost = sq(out.cost)
@@ -182,6 +185,14 @@ class iSLS:
         if verbose:
             self._report(out)
         return out
+
+    def iterate_once_dp(self, max_line_search=15, verbose=False, **kwargs):
+        """One iLQR iteration from the current nominal trajectory: backward pass, closed-loop line search, accept iff
+        the cost decreases (isls/isls.py:336-374).  Returns (fp_success [B] bool, K, k)."""
+        out = self.solve(method="dp", max_iter=1, max_line_search_iter=max_line_search, verbose=verbose,
+                         fixed_budget=True)
+        ok = out.alpha_idx[:, 0, 0] >= 0
+        return (bool(ok[0]) if self.batch is None else ok), self._K, self._k
 
     def solve_ilqr(self, get_AB=None, max_ilqr_iter=100, max_line_search_iter=25, dp=True, verbose=False, **kw):
         """Legacy spelling used by the notebooks (Car/Iterative LQR with state constraints.ipynb cell 13)."""

@@ -65,18 +65,7 @@ class SLS:
             r = diag_of(r, "rho")
         return np.ascontiguousarray(np.broadcast_to(r, (self.N, dim)))
 
-    def ADMM_LQT_DP(self, x0, project_x=False, project_u=False, max_iter=2000, rho_x=None, rho_u=None, alpha=1.0,
-                    tol=1e-3, verbose=False, log=False, fixed_budget=False, want_masks=False):
-        """LQT-ADMM with dynamic programming (isls/sls.py:298-317): Riccati pass once, then ff-pass + rollout +
-        projection/dual update per iteration, all inside one kernel.  Returns (x, u, K, k[, logs])."""
-        if self.A is None or self.zs is None:
-            raise IslsError("set AB and set_quadratic_cost first")
-        if self._dt is None:
-            raise NotImplementedError("ADMM_LQT_DP on the device needs A, B = get_double_integrator_AB(u_dim, 2, dt) "
-                                      "(the registered linear model)")
-        for nm, pr in (("project_x", project_x), ("project_u", project_u)):
-            if pr and not isinstance(pr, Bound):
-                raise TypeError("%s must be an isls_b200.projections.Bound" % nm)
+    def _lqt(self, x0, project_x, project_u, max_iter, rho_x, rho_u, alpha, tol, fixed_budget, want_masks):
         bx = project_x.expand(self.N, self.x_dim) if project_x else None
         bu = project_u.expand(self.N, self.u_dim) if project_u else None
         plan = S.Plan("double_integrator", self.N, self.x_dim, self.u_dim, self._dt, self.Qdiag, self.seq, self.u_std,
@@ -93,6 +82,62 @@ class SLS:
                       zs.expand(self.nb, zs.shape[-2], self.x_dim))
         out = sv.lqt_admm_dp(tol=tol, relax=float(alpha), fixed_budget=fixed_budget)
         self.last = out
+        return out
+
+    def _check_lqt(self):
+        if self.A is None or self.zs is None:
+            raise IslsError("set AB and set_quadratic_cost first")
+        if self._dt is None:
+            raise NotImplementedError("the LQT (DP) kernels need A, B = get_double_integrator_AB(u_dim, 2, dt) "
+                                      "(the registered linear model)")
+
+    def solve_dp(self, Qr=None, Rr=None, ur=None, xr=None, return_Qs=False, x0=None):
+        """K, k of the unconstrained LQT problem by the Riccati recursion (isls/sls.py:85-166).  The regularised
+        variant (Qr, Rr, xr, ur) is internal to ADMM_LQT_DP on the device."""
+        if Qr is not None or Rr is not None or return_Qs:
+            raise NotImplementedError("regularised solve_dp is internal to ADMM_LQT_DP on the device path")
+        self._check_lqt()
+        out = self._lqt(np.zeros(self.x_dim) if x0 is None else x0, False, False, 1, None, None, 1.0, 0.0, True, False)
+        sq = (lambda t: t[0]) if self.batch is None else (lambda t: t)
+        return sq(out.K), sq(out.k)
+
+    def solve(self, x0=None, method="dp", verbose=False):
+        """x, u of the LQT problem from x0 (isls/sls.py:40-60; method 'dp': Riccati gains + closed-loop rollout,
+        sls_base.py:76-89)."""
+        if method != "dp":
+            raise NotImplementedError("device path implements method='dp'")
+        self._check_lqt()
+        out = self._lqt(np.zeros(self.x_dim) if x0 is None else x0, False, False, 1, None, None, 1.0, 0.0, True, False)
+        if self.batch is None:
+            return out.x[0].reshape(-1), out.u[0].reshape(-1)
+        return out.x.reshape(self.nb, -1), out.u.reshape(self.nb, -1)
+
+    def compute_cost(self, x, u=None):
+        """sum (x-xd)'Q(x-xd) + u'Ru, batched over leading axes (isls/sls_base.py:25-44).  Convenience only
+        (elementwise torch ops on the caller's tensors; the solvers evaluate costs inside their kernels)."""
+        x = torch.as_tensor(x, dtype=torch.float64)
+        dev = x.device
+        Qt = torch.as_tensor(np.ascontiguousarray(self.Qdiag[self.seq]).reshape(-1), device=dev)
+        zs = np.asarray(self.zs, dtype=np.float64)
+        xd = zs[..., self.seq, :].reshape(*zs.shape[:-2], -1)
+        xd = torch.as_tensor(np.ascontiguousarray(xd), device=dev)
+        dx = x.reshape(*x.shape[:-2], -1) - xd if x.shape[-1] == self.x_dim and x.ndim >= 2 else x - xd
+        c = (dx * dx * Qt).sum(-1)
+        if u is not None:
+            u = torch.as_tensor(u, dtype=torch.float64, device=dev)
+            uf = u.reshape(*u.shape[:-2], -1) if u.shape[-1] == self.u_dim and u.ndim >= 2 else u
+            c = c + self.u_std * (uf * uf).sum(-1)
+        return c
+
+    def ADMM_LQT_DP(self, x0, project_x=False, project_u=False, max_iter=2000, rho_x=None, rho_u=None, alpha=1.0,
+                    tol=1e-3, verbose=False, log=False, fixed_budget=False, want_masks=False):
+        """LQT-ADMM with dynamic programming (isls/sls.py:298-317): Riccati pass once, then ff-pass + rollout +
+        projection/dual update per iteration, all inside one kernel.  Returns (x, u, K, k[, logs])."""
+        self._check_lqt()
+        for nm, pr in (("project_x", project_x), ("project_u", project_u)):
+            if pr and not isinstance(pr, Bound):
+                raise TypeError("%s must be an isls_b200.projections.Bound" % nm)
+        out = self._lqt(x0, project_x, project_u, max_iter, rho_x, rho_u, alpha, tol, fixed_budget, want_masks)
         sq = (lambda t: t[0]) if self.batch is None else (lambda t: t)
         ret = (sq(out.x).reshape(*out.x.shape[:-2], -1) if self.batch is not None else out.x[0].reshape(-1),
                sq(out.u).reshape(*out.u.shape[:-2], -1) if self.batch is not None else out.u[0].reshape(-1),

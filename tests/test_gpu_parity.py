@@ -307,3 +307,44 @@ def test_full_size_properties():
     o = R.ilqr_admm(P.subset(p, idx), fixed_budget=True)
     assert _gpu().rel_logs(a["cost_log"][idx], o["cost_log"]) < 1e-9
     assert np.abs(a["u"][idx] - o["u"]).max() < 1e-9
+
+
+def test_api_surface_lqt_and_continuation(golden):
+    """Remaining pieces of the reference surface on the hot path: SLS.solve / solve_dp / compute_cost, state
+    persistence of iSLS between calls and iterate_once_dp (isls.py:336-374)."""
+    import torch
+    from isls_b200 import SLS, get_double_integrator_AB
+    from oracle import models as M
+    p = P.di_batch(4)
+    p["x0"][:, :2] = np.array([[0.0, 0.0], [0.01, -0.02], [0.03, 0.0], [-0.02, 0.02]])
+    s = SLS(4, 2, p["N"], batch=4)
+    s.AB = get_double_integrator_AB(2, 2, p["dt"])
+    s.set_quadratic_cost(p["zs"], p["Qdiag"], p["seq"], p["u_std"])
+    x, u = s.solve(p["x0"], method="dp")
+    K, k = s.solve_dp(x0=p["x0"])
+    # oracle: unregularised Riccati + closed-loop rollout
+    N, n, m = p["N"], 4, 2
+    A, B = M.double_integrator_AB(2, 2, p["dt"])
+    Qd = p["Qdiag"][p["seq"]]
+    Ab, Bb = np.broadcast_to(A, (1, N, n, n)), np.broadcast_to(B, (1, N, n, m))
+    zs_t = p["zs"][p["seq"]]
+    Ko, ko, _ = R.backward_pass(Ab, Bb, (-2.0 * Qd * zs_t)[None], np.zeros((1, N, m)),
+                                R._diag_embed(2.0 * Qd)[None], R._diag_embed(np.full((N, m), 2.0 * p["u_std"]))[None])
+    assert np.abs(K.cpu().numpy() - Ko).max() / np.abs(Ko).max() < 1e-9
+    xs, us = R.linear_rollout(np.broadcast_to(Ab, (4, N, n, n)), np.broadcast_to(Bb, (4, N, n, m)),
+                              np.broadcast_to(Ko, (4, N, m, n)), np.broadcast_to(ko, (4, N, m)), dx0=p["x0"])
+    assert np.abs(x.cpu().numpy().reshape(4, N, n) - xs).max() < 1e-9
+    assert np.abs(u.cpu().numpy().reshape(4, N, m) - us).max() < 1e-8
+    c = s.compute_cost(x.reshape(4, N, n), u.reshape(4, N, m)).cpu().numpy()
+    co = R.quad_cost(p, R._zs_b(p, 4), xs[:, None], us[:, None])[:, 0]
+    assert np.abs(c - co).max() / np.abs(co).max() < 1e-9
+    # iSLS: two calls of max_iter=3 continue where the first stopped == one call of max_iter=6 (fixed budget)
+    pc = P.car_batch(32)
+    s1 = _gpu().make_isls(pc)
+    s1.solve("car", max_iter=3, max_line_search_iter=20, fixed_budget=True)
+    s1.solve("car", max_iter=3, max_line_search_iter=20, fixed_budget=True)
+    s2 = _gpu().make_isls(pc)
+    s2.solve("car", max_iter=6, max_line_search_iter=20, fixed_budget=True)
+    assert torch.equal(s1.u_nom, s2.u_nom) and torch.equal(s1.cost, s2.cost)
+    ok, K1, k1 = s2.iterate_once_dp(max_line_search=20)
+    assert ok.dtype == torch.bool and K1.shape == (32, pc["N"], 2, 4)
