@@ -362,15 +362,35 @@ __global__ void k_kpass(Dev d) {
   // reset ADMM state for this outer iteration
   if (d.proj_x) {
     double *zx = c.at(d.zx, d, n), *lx = c.at(d.lx, d, n), *rg = c.at(d.rgx, d, n);
-    for (int t = 0; t < d.N; t++)
+    for (int t0 = 0; t0 < d.N; t0 += 4) {            // 4 steps of loads in flight before the first store
+      double zv[4][n];
 #pragma unroll
-      for (int i = 0; i < n; i++) { EL(lx, n, t, i) = 0.0; EL(rg, n, t, i) = EL(zx, n, t, i); }
+      for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int i = 0; i < n; i++) zv[q][i] = (t0 + q < d.N) ? EL(zx, n, t0 + q, i) : 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (t0 + q < d.N) {
+#pragma unroll
+          for (int i = 0; i < n; i++) { EL(lx, n, t0 + q, i) = 0.0; EL(rg, n, t0 + q, i) = zv[q][i]; }
+        }
+    }
   }
   if (d.proj_u) {
     double *zu = c.at(d.zu, d, m), *lu = c.at(d.lu, d, m), *rg = c.at(d.rgu, d, m);
-    for (int t = 0; t < d.N; t++)
+    for (int t0 = 0; t0 < d.N; t0 += 8) {
+      double zv[8][m];
 #pragma unroll
-      for (int j = 0; j < m; j++) { EL(lu, m, t, j) = 0.0; EL(rg, m, t, j) = EL(zu, m, t, j); }
+      for (int q = 0; q < 8; q++)
+#pragma unroll
+        for (int j = 0; j < m; j++) zv[q][j] = (t0 + q < d.N) ? EL(zu, m, t0 + q, j) : 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        if (t0 + q < d.N) {
+#pragma unroll
+          for (int j = 0; j < m; j++) { EL(lu, m, t0 + q, j) = 0.0; EL(rg, m, t0 + q, j) = zv[q][j]; }
+        }
+    }
   }
   if (!ok) d.status[c.b] |= ISLS_ST_NON_PD;
   d.prev_cost[c.b] = d.cost[c.b];
@@ -463,31 +483,39 @@ __device__ __forceinline__ void ff_body(const Dev &d, const TileCtx<M> &c) {
   for (int i = 0; i < n; i++) dx[i] = 0.0;
   double c0 = 0.0, c1 = 0.0, c2 = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0;
   for (int t = 0; t < d.N; t++) {
-    double duv[m], u[m];
+    // every load of the step is issued before its first store (see admm_body)
+    double duv[m], u[m], K[m][n], kv[m], ru[m], x[n];
+#pragma unroll
+    for (int a = 0; a < m; a++) {
+#pragma unroll
+      for (int j = 0; j < n; j++) K[a][j] = EL(Kg, m * n, t, a * n + j);
+      kv[a] = EL(kk, m, t, a);
+      u[a] = EL(uh, m, t, a);
+      ru[a] = d.proj_u ? EL(rgu, m, t, a) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < n; i++) x[i] = EL(xh, n, t, i);
 #pragma unroll
     for (int a = 0; a < m; a++) {
       double acc = 0.0;
       if (t < d.N - 1) {
 #pragma unroll
-        for (int j = 0; j < n; j++) acc = fma(EL(Kg, m * n, t, a * n + j), dx[j], acc);
+        for (int j = 0; j < n; j++) acc = fma(K[a][j], dx[j], acc);
       }
-      duv[a] = acc + EL(kk, m, t, a);
+      duv[a] = acc + kv[a];
       EL(du, m, t, a) = duv[a];
-      u[a] = EL(uh, m, t, a);
       r0 = fma(u[a], u[a], r0);                 // R-only part (scaled by u_std after the loop)
       r1 = fma(u[a], duv[a], r1);
       r2 = fma(duv[a], duv[a], r2);
       if (d.proj_u) {                           // ADMM penalty part
-        const double rho = d.rho_u[t * m + a], e = u[a] - EL(rgu, m, t, a);
+        const double rho = d.rho_u[t * m + a], e = u[a] - ru[a];
         c0 = fma(rho * e, e, c0);
         c1 = fma(2.0 * rho * e, duv[a], c1);
         c2 = fma(rho * duv[a], duv[a], c2);
       }
     }
     if (t < d.N - 1) {
-      double x[n], J[M::NJA], dxn[n];
-#pragma unroll
-      for (int i = 0; i < n; i++) x[i] = EL(xh, n, t, i);
+      double J[M::NJA], dxn[n];
       M::jac(x, u, J, d.dt);
       M::expand(J, A, Bm, d.dt);
       mat_Ax_Bu<M>(A, Bm, dx, duv, dxn);
@@ -514,6 +542,232 @@ __global__ void k_ff(Dev d) {
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b] || d.adone[c.b]) return;
   ff_body<M>(d, c);
+}
+
+// ---- cp.async (LDGSTS) staging: each thread streams ITS OWN operands of the next STAGES-1 time steps into a private
+// slice of shared memory, so several steps of loads are in flight per warp without holding registers.  Used for the
+// ff-pass when the batch is too small to hide the per-step memory round trip with resident warps alone (at 65,536
+// problems the plain kernel is bandwidth-bound and staging is neutral; at 4,096 - 16,384 it is latency-bound).
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int Npend>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(Npend) : "memory"); }
+
+template <class M, int STAGES>
+__global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
+  constexpr int n = M::n, m = M::m, nt = NTRI(M::m);
+  constexpr int SB = n + m + m * n + 2 * nt + m + n;      // backward slots: x^, u^, Qux, Quu, Quu^-1, reg_u, reg_x
+  constexpr int SF = m * n + m + m + m + n;               // forward slots:  K, k, u^, reg_u, x^
+  constexpr int SL = SB > SF ? SB : SF;
+  extern __shared__ double smem_ff[];
+  const int tile = d.tile0 + blockIdx.x;
+  if (tile >= d.tile1) return;
+  TileCtx<M> c(d, tile, threadIdx.x);
+  if (d.odone[c.b] || d.adone[c.b]) return;
+  const int tid = threadIdx.x;
+  auto slot = [&](int stage, int k) -> double * { return smem_ff + ((size_t)stage * SL + k) * TILE + tid; };
+  const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m);
+  const double *Kg = c.at(d.Kg, d, m * n), *Qx = c.at(d.Qux, d, m * n);
+  const double *Qu = c.at(d.Quu, d, nt), *Qi = c.at(d.Qui, d, nt);
+  const double *rgx = c.at(d.rgx, d, n), *rgu = c.at(d.rgu, d, m);
+  const double *zs = d.zs + (size_t)tile * d.n_via * n * TILE + c.lane;
+  double *kk = c.at(d.kk, d, m), *du = c.at(d.du, d, m);
+  const int N = d.N;
+  double A[n][n], Bm[n][m];
+  init_AB<M>(A, Bm);
+  double v[n];
+  auto costgrad = [&](int t, const double (&x)[n], const double (&u)[m], const double (&rx)[n],
+                      const double (&ru)[m], double (&cx)[n], double (&cu)[m]) {
+    const int s = d.seq[t];
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+      double g = 0.0;
+      if (d.qnz[t]) g = 2.0 * d.qd[t * n + i] * (x[i] - EL(zs, n, s, i));
+      if (d.proj_x) g += 2.0 * d.rho_x[t * n + i] * (x[i] - rx[i]);
+      cx[i] = g;
+    }
+#pragma unroll
+    for (int j = 0; j < m; j++) {
+      double g = 2.0 * d.u_std * u[j];
+      if (d.proj_u) g += 2.0 * d.rho_u[t * m + j] * (u[j] - ru[j]);
+      cu[j] = g;
+    }
+  };
+  auto issue_b = [&](int t, int stage) {
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < n; i++) cp_async8(slot(stage, k++), &EL(xh, n, t, i));
+#pragma unroll
+    for (int j = 0; j < m; j++) cp_async8(slot(stage, k++), &EL(uh, m, t, j));
+#pragma unroll
+    for (int q = 0; q < m * n; q++) cp_async8(slot(stage, k++), &EL(Qx, m * n, t, q));
+#pragma unroll
+    for (int q = 0; q < nt; q++) cp_async8(slot(stage, k++), &EL(Qu, nt, t, q));
+#pragma unroll
+    for (int q = 0; q < nt; q++) cp_async8(slot(stage, k++), &EL(Qi, nt, t, q));
+    if (d.proj_u) {
+#pragma unroll
+      for (int j = 0; j < m; j++) cp_async8(slot(stage, k + j), &EL(rgu, m, t, j));
+    }
+    k += m;
+    if (d.proj_x) {
+#pragma unroll
+      for (int i = 0; i < n; i++) cp_async8(slot(stage, k + i), &EL(rgx, n, t, i));
+    }
+  };
+  {   // terminal step N-1 (plain loads)
+    double x[n], u[m], rx[n], ru[m], cx[n], cu[m];
+#pragma unroll
+    for (int i = 0; i < n; i++) { x[i] = EL(xh, n, N - 1, i); rx[i] = d.proj_x ? EL(rgx, n, N - 1, i) : 0.0; }
+#pragma unroll
+    for (int j = 0; j < m; j++) { u[j] = EL(uh, m, N - 1, j); ru[j] = d.proj_u ? EL(rgu, m, N - 1, j) : 0.0; }
+    costgrad(N - 1, x, u, rx, ru, cx, cu);
+#pragma unroll
+    for (int i = 0; i < n; i++) v[i] = cx[i];
+#pragma unroll
+    for (int j = 0; j < m; j++) {
+      const double cuu = 2.0 * (d.u_std + d.rho_u[(N - 1) * m + j]);
+      EL(kk, m, N - 1, j) = d.last_stage_dp ? 0.0 : -cu[j] / cuu;
+    }
+  }
+  // ---- backward sweep, STAGES deep
+  int t_issue = N - 2;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (t_issue >= 0) issue_b(t_issue, (N - 2 - t_issue) % STAGES);
+    cp_async_commit();
+    t_issue--;
+  }
+  for (int t = N - 2; t >= 0; t--) {
+    if (t_issue >= 0) issue_b(t_issue, (N - 2 - t_issue) % STAGES);
+    cp_async_commit();
+    t_issue--;
+    cp_async_wait<STAGES - 1>();
+    const int st = (N - 2 - t) % STAGES;
+    double x[n], u[m], rx[n], ru[m], J[M::NJA], cx[n], cu[m], Qux[m][n], Quu[m][m], Qui[m][m], kt[m];
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < n; i++) x[i] = *slot(st, k++);
+#pragma unroll
+    for (int j = 0; j < m; j++) u[j] = *slot(st, k++);
+#pragma unroll
+    for (int a = 0; a < m; a++)
+#pragma unroll
+      for (int j = 0; j < n; j++) Qux[a][j] = *slot(st, k++);
+#pragma unroll
+    for (int a = 0; a < m; a++)
+#pragma unroll
+      for (int b2 = 0; b2 <= a; b2++) { Quu[a][b2] = *slot(st, k + tri(a, b2)); Quu[b2][a] = Quu[a][b2]; }
+    k += nt;
+#pragma unroll
+    for (int a = 0; a < m; a++)
+#pragma unroll
+      for (int b2 = 0; b2 <= a; b2++) { Qui[a][b2] = *slot(st, k + tri(a, b2)); Qui[b2][a] = Qui[a][b2]; }
+    k += nt;
+#pragma unroll
+    for (int j = 0; j < m; j++) ru[j] = d.proj_u ? *slot(st, k + j) : 0.0;
+    k += m;
+#pragma unroll
+    for (int i = 0; i < n; i++) rx[i] = d.proj_x ? *slot(st, k + i) : 0.0;
+    M::jac(x, u, J, d.dt);
+    M::expand(J, A, Bm, d.dt);
+    costgrad(t, x, u, rx, ru, cx, cu);
+    ff_step<M>(A, Bm, cx, cu, Qux, Quu, Qui, v, kt);
+#pragma unroll
+    for (int j = 0; j < m; j++) EL(kk, m, t, j) = kt[j];
+  }
+  cp_async_wait<0>();
+  // ---- forward sweep (linear rollout + control-cost polynomials), STAGES deep
+  auto issue_f = [&](int t, int stage) {
+    int k = 0;
+#pragma unroll
+    for (int q = 0; q < m * n; q++) cp_async8(slot(stage, k++), &EL(Kg, m * n, t, q));
+#pragma unroll
+    for (int j = 0; j < m; j++) cp_async8(slot(stage, k++), &EL(kk, m, t, j));
+#pragma unroll
+    for (int j = 0; j < m; j++) cp_async8(slot(stage, k++), &EL(uh, m, t, j));
+    if (d.proj_u) {
+#pragma unroll
+      for (int j = 0; j < m; j++) cp_async8(slot(stage, k + j), &EL(rgu, m, t, j));
+    }
+    k += m;
+#pragma unroll
+    for (int i = 0; i < n; i++) cp_async8(slot(stage, k++), &EL(xh, n, t, i));
+  };
+  double dx[n];
+#pragma unroll
+  for (int i = 0; i < n; i++) dx[i] = 0.0;
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0;
+  t_issue = 0;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (t_issue < N) issue_f(t_issue, t_issue % STAGES);
+    cp_async_commit();
+    t_issue++;
+  }
+  for (int t = 0; t < N; t++) {
+    if (t_issue < N) issue_f(t_issue, t_issue % STAGES);
+    cp_async_commit();
+    t_issue++;
+    cp_async_wait<STAGES - 1>();
+    const int st = t % STAGES;
+    double duv[m], u[m], K[m][n], kv[m], ru[m], x[n];
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < m; a++)
+#pragma unroll
+      for (int j = 0; j < n; j++) K[a][j] = *slot(st, k++);
+#pragma unroll
+    for (int j = 0; j < m; j++) kv[j] = *slot(st, k++);
+#pragma unroll
+    for (int j = 0; j < m; j++) u[j] = *slot(st, k++);
+#pragma unroll
+    for (int j = 0; j < m; j++) ru[j] = d.proj_u ? *slot(st, k + j) : 0.0;
+    k += m;
+#pragma unroll
+    for (int i = 0; i < n; i++) x[i] = *slot(st, k++);
+#pragma unroll
+    for (int a = 0; a < m; a++) {
+      double acc = 0.0;
+      if (t < N - 1) {
+#pragma unroll
+        for (int j = 0; j < n; j++) acc = fma(K[a][j], dx[j], acc);
+      }
+      duv[a] = acc + kv[a];
+      EL(du, m, t, a) = duv[a];
+      r0 = fma(u[a], u[a], r0);
+      r1 = fma(u[a], duv[a], r1);
+      r2 = fma(duv[a], duv[a], r2);
+      if (d.proj_u) {
+        const double rho = d.rho_u[t * m + a], e = u[a] - ru[a];
+        c0 = fma(rho * e, e, c0);
+        c1 = fma(2.0 * rho * e, duv[a], c1);
+        c2 = fma(rho * duv[a], duv[a], c2);
+      }
+    }
+    if (t < N - 1) {
+      double J[M::NJA], dxn[n];
+      M::jac(x, u, J, d.dt);
+      M::expand(J, A, Bm, d.dt);
+      mat_Ax_Bu<M>(A, Bm, dx, duv, dxn);
+#pragma unroll
+      for (int i = 0; i < n; i++) dx[i] = dxn[i];
+    }
+  }
+  cp_async_wait<0>();
+  const size_t S = (size_t)d.T * TILE;
+  r0 *= d.u_std;
+  r1 *= 2.0 * d.u_std;
+  r2 *= d.u_std;
+  d.cq[c.b] = c0 + r0;
+  d.cq[S + c.b] = c1 + r1;
+  d.cq[2 * S + c.b] = c2 + r2;
+  d.cq[3 * S + c.b] = r0;
+  d.cq[4 * S + c.b] = r1;
+  d.cq[5 * S + c.b] = r2;
 }
 
 // np.argmin semantics over candidate costs (first minimum; the first NaN wins, isls/isls.py:477)
@@ -775,29 +1029,38 @@ __device__ __forceinline__ void admm_body(const Dev &d, const TileCtx<M> &c, int
   int8_t *mkx = (d.out.mask_x && c.valid) ? d.out.mask_x + c.b * d.N * n : nullptr;
   int8_t *mku = (d.out.mask_u && c.valid) ? d.out.mask_u + c.b * d.N * m : nullptr;
   for (int t = 0; t < d.N; t++) {
+    // all loads of the step are issued before the first store (the stores may alias as far as the compiler knows,
+    // which would otherwise serialise one memory round trip per element)
+    double zuv[m], luv[m], lou[m], hiu[m], zxv[n], lxv[n], lox[n], hix[n];
 #pragma unroll
     for (int j = 0; j < m; j++) {
-      u[j] = EL(uh, m, t, j) + al * EL(du, m, t, j);
+      u[j] = fma(al, EL(du, m, t, j), EL(uh, m, t, j));
+      if (d.proj_u) { zuv[j] = EL(zu, m, t, j); luv[j] = EL(lu, m, t, j); lou[j] = d.lo_u[t * m + j]; hiu[j] = d.hi_u[t * m + j]; }
+    }
+    if (d.proj_x) {
+#pragma unroll
+      for (int i = 0; i < n; i++) { zxv[i] = EL(zx, n, t, i); lxv[i] = EL(lx, n, t, i); lox[i] = d.lo_x[t * n + i]; hix[i] = d.hi_x[t * n + i]; }
+    }
+#pragma unroll
+    for (int j = 0; j < m; j++) {
       cc += u[j] * u[j];
       if (d.proj_u) {
-        double z = EL(zu, m, t, j), l = EL(lu, m, t, j);
         int mk;
-        admm_elem(u[j], d.relax, d.lo_u[t * m + j], d.hi_u[t * m + j], z, l, pru, dru, mk);
-        EL(zu, m, t, j) = z;
-        EL(lu, m, t, j) = l;
-        EL(rgu, m, t, j) = __dsub_rn(z, l);          // reg = z - lambda for the next f_argmin (admm.py:32-33)
+        admm_elem(u[j], d.relax, lou[j], hiu[j], zuv[j], luv[j], pru, dru, mk);
+        EL(zu, m, t, j) = zuv[j];
+        EL(lu, m, t, j) = luv[j];
+        EL(rgu, m, t, j) = __dsub_rn(zuv[j], luv[j]);   // reg = z - lambda for the next f_argmin (admm.py:32-33)
         if (mku) mku[t * m + j] = (int8_t)mk;
       }
     }
+    if (d.proj_x) {
 #pragma unroll
-    for (int i = 0; i < n; i++) {
-      if (d.proj_x) {
-        double z = EL(zx, n, t, i), l = EL(lx, n, t, i);
+      for (int i = 0; i < n; i++) {
         int mk;
-        admm_elem(x[i], d.relax, d.lo_x[t * n + i], d.hi_x[t * n + i], z, l, prx, drx, mk);
-        EL(zx, n, t, i) = z;
-        EL(lx, n, t, i) = l;
-        EL(rgx, n, t, i) = __dsub_rn(z, l);
+        admm_elem(x[i], d.relax, lox[i], hix[i], zxv[i], lxv[i], prx, drx, mk);
+        EL(zx, n, t, i) = zxv[i];
+        EL(lx, n, t, i) = lxv[i];
+        EL(rgx, n, t, i) = __dsub_rn(zxv[i], lxv[i]);
         if (mkx) mkx[t * n + i] = (int8_t)mk;
       }
     }
@@ -1409,20 +1672,32 @@ __global__ void k_lqt_admm(Dev d, const double *x0_in) {
     for (int i = 0; i < n; i++) x[i] = x0[i];
     double cs = 0.0, cc = 0.0, prx = 0.0, pru = 0.0, drx = 0.0, dru = 0.0;
     for (int t = 0; t < d.N; t++) {
+      // loads of the step first, then stores (see admm_body)
+      double zuv[m], luv[m], kv[m], zxv[n], lxv[n], Kt[m][n];
+#pragma unroll
+      for (int j = 0; j < m; j++) {
+#pragma unroll
+        for (int i = 0; i < n; i++) Kt[j][i] = EL(Kg, m * n, t, j * n + i);
+        kv[j] = EL(kk, m, t, j);
+        if (d.proj_u) { zuv[j] = EL(zu, m, t, j); luv[j] = EL(lu, m, t, j); }
+      }
+      if (d.proj_x) {
+#pragma unroll
+        for (int i = 0; i < n; i++) { zxv[i] = EL(zx, n, t, i); lxv[i] = EL(lx, n, t, i); }
+      }
 #pragma unroll
       for (int j = 0; j < m; j++) {
         double acc = 0.0;
 #pragma unroll
-        for (int i = 0; i < n; i++) acc = fma(EL(Kg, m * n, t, j * n + i), x[i], acc);
-        u[j] = acc + EL(kk, m, t, j);
+        for (int i = 0; i < n; i++) acc = fma(Kt[j][i], x[i], acc);
+        u[j] = acc + kv[j];
         EL(ua, m, t, j) = u[j];
         cc += u[j] * u[j];
         if (d.proj_u) {
-          double z = EL(zu, m, t, j), l = EL(lu, m, t, j);
           int mk;
-          admm_elem(u[j], d.relax, d.lo_u[t * m + j], d.hi_u[t * m + j], z, l, pru, dru, mk);
-          EL(zu, m, t, j) = z;
-          EL(lu, m, t, j) = l;
+          admm_elem(u[j], d.relax, d.lo_u[t * m + j], d.hi_u[t * m + j], zuv[j], luv[j], pru, dru, mk);
+          EL(zu, m, t, j) = zuv[j];
+          EL(lu, m, t, j) = luv[j];
           if (mku) mku[t * m + j] = (int8_t)mk;
         }
       }
@@ -1430,11 +1705,10 @@ __global__ void k_lqt_admm(Dev d, const double *x0_in) {
       for (int i = 0; i < n; i++) {
         EL(xa, n, t, i) = x[i];
         if (d.proj_x) {
-          double z = EL(zx, n, t, i), l = EL(lx, n, t, i);
           int mk;
-          admm_elem(x[i], d.relax, d.lo_x[t * n + i], d.hi_x[t * n + i], z, l, prx, drx, mk);
-          EL(zx, n, t, i) = z;
-          EL(lx, n, t, i) = l;
+          admm_elem(x[i], d.relax, d.lo_x[t * n + i], d.hi_x[t * n + i], zxv[i], lxv[i], prx, drx, mk);
+          EL(zx, n, t, i) = zxv[i];
+          EL(lx, n, t, i) = lxv[i];
           if (mkx) mkx[t * n + i] = (int8_t)mk;
         }
       }
@@ -1695,6 +1969,36 @@ static int setup(const isls_plan *plan, const isls_solve_opts *o, int64_t B, voi
 static dim3 tp_block() { return dim3(TILE, TPB_TILES); }
 static dim3 tp_grid(const Dev &d) { return dim3((d.tile1 - d.tile0 + TPB_TILES - 1) / TPB_TILES); }
 
+// ff-pass launcher: plain kernel for large batches (bandwidth-bound), cp.async-staged kernel for small ones
+template <class M>
+static int launch_ff(const Dev &d, cudaStream_t s) {
+  static int mode = -2;
+  if (mode == -2) {
+    const char *e = getenv("ISLS_FF_STAGES");         // -1 auto (default), 0 plain, 2/4 forced pipeline depth
+    mode = e ? atoi(e) : -1;
+  }
+  constexpr int n = M::n, m = M::m, nt = NTRI(M::m);
+  constexpr int SB = n + m + m * n + 2 * nt + m + n, SF = m * n + 3 * m + n, SL = SB > SF ? SB : SF;
+  const int tiles = d.tile1 - d.tile0;
+  int stages = mode;
+  if (stages < 0) stages = (tiles < 1536 && (size_t)4 * SL * TILE * sizeof(double) <= 32 * 1024) ? 4 : 0;
+  if (stages == 4) {
+    const size_t smem = (size_t)4 * SL * TILE * sizeof(double);
+    static bool set4 = false;
+    if (!set4) { CK(cudaFuncSetAttribute(k_ff_staged<M, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set4 = true; }
+    k_ff_staged<M, 4><<<tiles, TILE, smem, s>>>(d);
+  } else if (stages == 2) {
+    const size_t smem = (size_t)2 * SL * TILE * sizeof(double);
+    static bool set2 = false;
+    if (!set2) { CK(cudaFuncSetAttribute(k_ff_staged<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set2 = true; }
+    k_ff_staged<M, 2><<<tiles, TILE, smem, s>>>(d);
+  } else {
+    k_ff<M><<<tp_grid(d), tp_block(), 0, s>>>(d);
+  }
+  return 0;
+}
+
+
 // Line-search CTA shape: CPT candidates per thread (independent FP64 chains, shared loads), W = ceil(L/CPT)
 // warps.  MAXW only feeds __launch_bounds__ (register budget).
 struct LsFuse { int fuse, outer, inner; };
@@ -1799,7 +2103,7 @@ extern "C" int isls_ilqr_admm_solve_f64(const isls_plan *plan, const isls_solve_
         for (int a = 0; a < d.max_admm; a++) {
           int fuse = solve_fuse();
           if (!(fuse & 2) && !d.proj_x && d.proj_u && !no_fused_update()) fuse |= 4;   // streaming ADMM epilogue
-          if (!(fuse & 1)) LAUNCH(ISLS_KC_FF, cs, (k_ff<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc)));
+          if (!(fuse & 1)) LAUNCH(ISLS_KC_FF, cs, launch_ff<M>(dc, cs));
           LAUNCH(ISLS_KC_LINESEARCH, cs, launch_linesearch<M>(dc, false, cs, LsFuse{fuse, j, a}));
           if (!(fuse & 6)) LAUNCH(ISLS_KC_ADMM, cs, (k_admm<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, j, a)));
         }
