@@ -332,12 +332,23 @@ __global__ void k_kpass(Dev d) {
     for (int j = 0; j < n; j++)
       V[i][j] = (i == j) ? 2.0 * (d.qd[(d.N - 1) * n + i] + d.rho_x[(d.N - 1) * n + i]) : 0.0;   // isls.py:257
   bool ok = true;
+  double xn_[n], un_[m];                   // operands of the next step, loaded while this step's Riccati update runs
+#pragma unroll
+  for (int i = 0; i < n; i++) xn_[i] = EL(xh, n, d.N - 2, i);
+#pragma unroll
+  for (int j = 0; j < m; j++) un_[j] = EL(uh, m, d.N - 2, j);
   for (int t = d.N - 2; t >= 0; t--) {
     double x[n], u[m], J[M::NJA];
 #pragma unroll
-    for (int i = 0; i < n; i++) x[i] = EL(xh, n, t, i);
+    for (int i = 0; i < n; i++) x[i] = xn_[i];
 #pragma unroll
-    for (int j = 0; j < m; j++) u[j] = EL(uh, m, t, j);
+    for (int j = 0; j < m; j++) u[j] = un_[j];
+    if (t > 0) {
+#pragma unroll
+      for (int i = 0; i < n; i++) xn_[i] = EL(xh, n, t - 1, i);
+#pragma unroll
+      for (int j = 0; j < m; j++) un_[j] = EL(uh, m, t - 1, j);
+    }
     M::jac(x, u, J, d.dt);
     M::expand(J, A, Bm, d.dt);
     double dxx[n], duu[m], K[m][n], Qux[m][n], Quu[m][m], Qui[m][m];
@@ -1132,17 +1143,26 @@ __global__ void k_outer_end(Dev d, int outer) {
     double x[n], u[m], xn[n];
 #pragma unroll
     for (int i = 0; i < n; i++) x[i] = EL(xh, n, 0, i);
-    for (int t = 0; t < d.N; t++) {
+    for (int t0 = 0; t0 < d.N; t0 += 4) {          // 4 steps of loads in flight before the first store
+      double uv[4][m];
 #pragma unroll
-      for (int j = 0; j < m; j++) {
-        u[j] = EL(uh, m, t, j) + al * EL(du, m, t, j);
-        EL(uh, m, t, j) = u[j];
+      for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int j = 0; j < m; j++)
+          uv[q][j] = (t0 + q < d.N) ? fma(al, EL(du, m, t0 + q, j), EL(uh, m, t0 + q, j)) : 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int t = t0 + q;
+        if (t < d.N) {
+#pragma unroll
+          for (int j = 0; j < m; j++) { u[j] = uv[q][j]; EL(uh, m, t, j) = u[j]; }
+#pragma unroll
+          for (int i = 0; i < n; i++) EL(xh, n, t, i) = x[i];
+          M::step(x, u, xn, d.dt);
+#pragma unroll
+          for (int i = 0; i < n; i++) x[i] = xn[i];
+        }
       }
-#pragma unroll
-      for (int i = 0; i < n; i++) EL(xh, n, t, i) = x[i];
-      M::step(x, u, xn, d.dt);
-#pragma unroll
-      for (int i = 0; i < n; i++) x[i] = xn[i];
     }
   }
   const double cost = d.cost_adm[c.b], prev = d.prev_cost[c.b];
@@ -2005,8 +2025,18 @@ struct LsFuse { int fuse, outer, inner; };
 template <class M, int CPT, int MAXW, int MINB = 1>
 static void launch_ls_cfg(const Dev &d, bool closed, cudaStream_t s, LsFuse f) {
   const int W = (d.L + CPT - 1) / CPT;
+  // optional dynamic shared-memory padding caps the CTAs per SM (experiments with concurrent HBM-bound kernels)
+  static int pad_kb = -1;
+  if (pad_kb < 0) { const char *e = getenv("ISLS_LS_PAD_KB"); pad_kb = e ? atoi(e) : 0; }
+  const size_t pad = (size_t)pad_kb * 1024;
   if (closed) k_linesearch_closed<M, CPT, MAXW, MINB><<<d.tile1 - d.tile0, dim3(TILE, W), 0, s>>>(d);
-  else k_linesearch<M, CPT, MAXW, MINB><<<d.tile1 - d.tile0, dim3(TILE, W), 0, s>>>(d, f.fuse, f.outer, f.inner);
+  else {
+    if (pad) {
+      static bool set = false;
+      if (!set) { cudaFuncSetAttribute(k_linesearch<M, CPT, MAXW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad); set = true; }
+    }
+    k_linesearch<M, CPT, MAXW, MINB><<<d.tile1 - d.tile0, dim3(TILE, W), pad, s>>>(d, f.fuse, f.outer, f.inner);
+  }
 }
 static int solve_chunks() {
   static int v = -1;
