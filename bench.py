@@ -269,10 +269,10 @@ def run_b200(a):
         fused_update = "admm" not in prof          # the streaming ADMM z/lambda update runs as the kernel's epilogue
         # bytes the kernel has to move per launch: u^, du read once per problem (2 x N x m), x^_0 (n), the control-cost
         # polynomial (3), best index / best cost written (2)
-        alg_bytes = float(B) * (2 * p["N"] * 2 + 4 + 3 + 2) * 8
-        # two-phase bound of the fused kernel: FP64 phase at the DFMA peak + streaming ADMM epilogue (u^, du, z, lambda
-        # read; z, lambda, reg written = 14 doubles per problem-step) at the measured HBM peak
-        epi_bytes = float(B) * p["N"] * 2 * 7 * 8 if fused_update else 0.0
+        alg_bytes = float(B) * (2 * p["N"] * 2 + 4 + 6 + 2) * 8
+        # two-phase bound of the fused kernel: FP64 phase at the DFMA peak + streaming ADMM epilogue (z, lambda read;
+        # z, lambda, reg written = 5 doubles per control element; u^, du are re-read from cache) at the measured HBM peak
+        epi_bytes = float(B) * p["N"] * 2 * 5 * 8 if fused_update else 0.0
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         t_bound = flops / (fp64_peak * 1e12) + epi_bytes / (hbm_peak * 1e9)
         roof = {"kernel": "k_linesearch<CarModel,5,4,3>" + (" + fused ADMM z/lambda epilogue" if fused_update else ""),
@@ -281,17 +281,25 @@ def run_b200(a):
                 "peak_source": "DFMA throughput measured live by isls_measure_fp64_tflops (MEASURED_PEAKS.json has "
                                "no FP64 figure)",
                 "algorithmic_flop_per_launch": flops, "flop_per_candidate_step": FLOP_PER_CAND_STEP_CAR,
-                "hbm": {"algorithmic_bytes_per_launch": alg_bytes,
-                        "achieved_gbs": round(alg_bytes / (ls_ms / ls_n * 1e-3) / 1e9, 2),
+                "hbm": {"algorithmic_bytes_per_launch": alg_bytes + epi_bytes,
+                        "achieved_gbs": round((alg_bytes + epi_bytes) / (ls_ms / ls_n * 1e-3) / 1e9, 2),
                         "peak_gbs": peaks.get("hbm_gbs", 6650.0),
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=65,536 from the committed
                 # `ncu --set full` capture (profiles/r1_ncu_full_main_kernels.csv), scaled to this batch size
-                "traffic": round(223.87e6 * B / 65536.0), "traffic_source": "profiles/r1_ncu_full_main_kernels.csv",
+                "traffic": round(755.0e6 * B / 65536.0), "traffic_source": "profiles/r1_ncu_full_main_kernels.csv",
                 "two_phase": {"epilogue_bytes_per_launch": epi_bytes, "bound_ms": round(t_bound * 1e3, 4),
                               "measured_ms": round(ls_ms / ls_n, 4),
                               "frac": round(t_bound / (ls_ms / ls_n * 1e-3), 4)}}
 
+    if rank == 0 and roof is not None and "ff" in prof:
+        # second-largest kernel (HBM-bound): ff-pass + linear rollout, 44 doubles per problem-step
+        ff_ms, ff_n = prof["ff"]
+        ff_bytes = float(B) * p["N"] * 44 * 8
+        roof["second_kernel"] = {"kernel": "k_ff<CarModel>", "bound": "hbm",
+                                 "achieved": round(ff_bytes / (ff_ms / ff_n * 1e-3) / 1e9, 1), "peak": hbm_peak,
+                                 "unit": "GB/s", "frac": round(ff_bytes / (ff_ms / ff_n * 1e-3) / 1e9 / hbm_peak, 4),
+                                 "algorithmic_bytes_per_launch": ff_bytes, "traffic": round(2171.1e6 * B / 65536.0)}
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
