@@ -348,3 +348,67 @@ def test_api_surface_lqt_and_continuation(golden):
     assert torch.equal(s1.u_nom, s2.u_nom) and torch.equal(s1.cost, s2.cost)
     ok, K1, k1 = s2.iterate_once_dp(max_line_search=20)
     assert ok.dtype == torch.bool and K1.shape == (32, pc["N"], 2, 4)
+
+
+def test_edge_cases_small_sizes_relaxation_and_state_bounds():
+    """Edge cases the reference's semantics define: minimal horizon / single candidate / single problem, ADMM
+    relaxation alpha != 1 (un-relaxed dual update, admm.py:48-52), state AND control bounds on the car (the
+    trajectory-per-thread k_admm path), infinite bounds (no projection effect)."""
+    g = _gpu()
+    # (a) N = 3, L = 1, B = 1
+    p = P.car_batch(1, N=3, I_o=3, I_a=2, L=1)
+    out, o = g.run_ilqr_admm(p), R.ilqr_admm(p)
+    assert np.array_equal(out["n_log"], o["n_log"]) and g.rel_logs(out["cost_log"], o["cost_log"]) < 1e-10
+    assert np.abs(out["u"] - o["u"]).max() < 1e-10
+    # (b) relaxation alpha = 1.6
+    p = P.car_batch(40, I_o=8)
+    p["alpha"] = 1.6
+    out, o = g.run_ilqr_admm(p), R.ilqr_admm(p)
+    assert np.array_equal(out["n_log"], o["n_log"]) and np.array_equal(out["alpha_idx"], o["alpha_idx"])
+    assert g.rel_logs(out["cost_log"], o["cost_log"]) < 1e-9
+    assert np.abs(out["lam_u"] - o["lam_u"]).max() < 1e-9 and np.array_equal(out["mask_u"], o["mask_u"])
+    # (c) car with a speed limit (state bound on v) + control bounds: exercises k_admm and the x penalty terms
+    p = P.car_batch(48, I_o=10)
+    N = p["N"]
+    lo_x, hi_x = np.full((N, 4), -np.inf), np.full((N, 4), np.inf)
+    lo_x[:, 3], hi_x[:, 3] = -0.8, 0.8
+    rho_x = np.zeros((N, 4)); rho_x[:, 3] = 5.0
+    p.update(lo_x=lo_x, hi_x=hi_x, rho_x=rho_x)
+    out, o = g.run_ilqr_admm(p), R.ilqr_admm(p)
+    assert np.array_equal(out["n_log"], o["n_log"]) and np.array_equal(out["admm_iters"], o["admm_iters"])
+    same = np.all(out["alpha_idx"].reshape(48, -1) == o["alpha_idx"].reshape(48, -1), axis=1)
+    assert same.mean() > 0.95
+    assert g.rel_logs(out["cost_log"][same], o["cost_log"][same]) < 1e-9
+    assert np.abs(out["z_x"][same] - o["z_x"][same]).max() < 1e-9
+    assert np.array_equal(out["mask_x"][same], o["mask_x"][same]) and np.array_equal(out["mask_u"][same], o["mask_u"][same])
+    assert np.abs(out["z_x"][:, :, 3]).max() <= 0.8
+    # (d) infinite bounds: projection is the identity, lambda stays 0, z = primal iterate
+    p = P.car_batch(8, I_o=3)
+    p["lo_u"][:], p["hi_u"][:] = -np.inf, np.inf
+    out = g.run_ilqr_admm(p, fixed_budget=True)
+    assert np.all(out["lam_u"] == 0.0) and np.array_equal(out["z_u"], out["u"]) and np.all(out["mask_u"] == 0)
+
+
+def test_status_flags_nan_and_non_pd():
+    """Per-problem failure reporting: a NaN initial state poisons that problem only (np.argmin picks the first NaN,
+    isls.py:477 / NaN -> 1e5 in plain iLQR, isls.py:362); a non-PD Quu (the reference raises LinAlgError,
+    isls.py:296) sets ISLS_ST_NON_PD and the problem stops with 'forward pass failed'."""
+    g = _gpu()
+    p = P.car_batch(34, I_o=3)
+    p["x0"][5, 0] = np.nan
+    out = g.run_ilqr_admm(p, fixed_budget=True)
+    assert out["status"][5] & 32 and np.isnan(out["cost"][5])
+    ok = np.ones(34, bool); ok[5] = False
+    assert not np.isnan(out["cost"][ok]).any() and not (out["status"][ok] & 32).any()
+    q = P.subset(p, np.arange(34)[ok])
+    ref = g.run_ilqr_admm(q, fixed_budget=True)
+    assert np.array_equal(out["u"][ok], ref["u"])                    # neighbours in the tile are untouched
+    assert np.all(out["alpha_idx"][5] == 0)                          # first NaN wins the argmin
+    # plain iLQR: NaN costs become 1e5 -> the step is rejected (cost is NaN, dcost < 0 is False)
+    o2 = g.run_ilqr_dp(p, 3, 10)
+    assert o2["status"][5] & 32 and o2["status"][5] & 2
+    # non-PD: negative control weight
+    p = P.car_batch(6, I_o=2)
+    p["u_std"] = -5.0
+    o3 = g.run_ilqr_dp(p, 2, 10)
+    assert np.all(o3["status"] & 16) and np.all(o3["status"] & 2) and np.all(o3["n_log"] == 1)
