@@ -48,7 +48,7 @@ EXPORTS = ["isls_version", "isls_last_error_string", "isls_model_id", "isls_mode
            "isls_sls_admm_f64", "isls_sls_controller_f64"]
 
 KERNEL_CLASSES = ["init", "kpass", "ff", "linesearch", "admm", "outer_end", "finalize", "backward_full", "accept",
-                  "lqt"]
+                  "lqt", "compact"]
 
 _lib = None
 

@@ -227,7 +227,8 @@ int isls_sls_controller_f64(const isls_sls_plan *plan, int64_t B, int32_t n_firs
 #define ISLS_KC_BACKWARD_FULL 7
 #define ISLS_KC_ACCEPT 8
 #define ISLS_KC_LQT 9
-#define ISLS_KC_COUNT 10
+#define ISLS_KC_COMPACT 10
+#define ISLS_KC_COUNT 11
 /* thread-local switch: when on, every kernel launch of a solve is bracketed by a CUDA event pair on the
  * launching stream (adds a few microseconds per launch; use for per-kernel durations, not for throughput) */
 int isls_profile_enable(int on);
