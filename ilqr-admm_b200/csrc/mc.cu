@@ -1,0 +1,120 @@
+// Monte-Carlo closed-loop evaluation of a controller over a batch of sampled initial states:
+//   SLSBase / iSLSBase.get_trajectory_batch  (open loop us)              isls/sls_base.py:62-74,  isls/isls_base.py:45-58
+//   SLSBase / iSLSBase.get_trajectory_dp     (u_t = K_t x_t + k_t)       isls/sls_base.py:76-89,  isls/isls_base.py:60-71
+//   SLSBase / iSLSBase.get_trajectory_sls    (history feedback
+//        u_t = sum_{s<=t} K[t,s] (x_s - x^_s) + k_t + u^_t)              isls/sls_base.py:91-105, isls/isls_base.py:28-43
+// One sample per thread, the controller is shared by the batch (every lane reads the same gain -> broadcast loads).
+// Process noise w ~ N(0, noise_scale) per state and step comes from a counter-based generator (Philox-4x32-10 +
+// Box-Muller), so a run is reproducible from (seed, sample, step) - the reference uses the unseeded global numpy
+// generator, i.e. only its statistics are defined.
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/isls_b200.h"
+#include "common.cuh"
+#include "models.cuh"
+
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                           uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// two standard normals from one Philox block (53-bit uniforms, Box-Muller)
+__device__ __forceinline__ void normal2(unsigned long long seed, unsigned long long sample, uint32_t step, uint32_t pair,
+                                        double &g0, double &g1) {
+  uint32_t r[4];
+  philox4x32((uint32_t)sample, (uint32_t)(sample >> 32), step, pair, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  const double u0 = ((((unsigned long long)r[0] << 21) ^ (unsigned long long)(r[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+  const double u1 = ((((unsigned long long)r[2] << 21) ^ (unsigned long long)(r[3] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+  const double rad = sqrt(-2.0 * log(u0));
+  double s, c;
+  sincos(6.283185307179586476925286766559 * u1, &s, &c);
+  g0 = rad * c;
+  g1 = rad * s;
+}
+
+#define MC_MAX_HIST 4608      // doubles of per-thread state history (N * n), local memory
+
+template <class M>
+__global__ void k_mc_rollout(int mode, int N, long long B, double dt, const double *x0, const double *K, const double *k,
+                             const double *x_nom, const double *u_nom, double noise, unsigned long long seed,
+                             double *x_out, double *u_out) {
+  constexpr int n = M::n, m = M::m;
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double x[n], u[m], xn[n];
+  double hist[MC_MAX_HIST];             // (x_s - x^_s) history for the SLS feedback (mode 2 only)
+#pragma unroll
+  for (int i = 0; i < n; i++) x[i] = x0[b * n + i];
+  for (int t = 0; t < N; t++) {
+    if (mode == 0) {
+#pragma unroll
+      for (int j = 0; j < m; j++) u[j] = k[t * m + j];
+    } else if (mode == 1) {
+#pragma unroll
+      for (int j = 0; j < m; j++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; i++) acc = fma(K[(size_t)(t * m + j) * n + i], x[i], acc);
+        u[j] = acc + k[t * m + j];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < n; i++) hist[t * n + i] = x[i] - (x_nom ? x_nom[t * n + i] : 0.0);
+#pragma unroll
+      for (int j = 0; j < m; j++) {
+        const double *row = K + (size_t)(t * m + j) * N * n;
+        double acc = 0.0;
+        for (int q = 0; q < (t + 1) * n; q++) acc = fma(row[q], hist[q], acc);   // K is causal: columns > t are zero
+        u[j] = (acc + k[t * m + j]) + (u_nom ? u_nom[t * m + j] : 0.0);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < n; i++) x_out[((size_t)b * N + t) * n + i] = x[i];
+#pragma unroll
+    for (int j = 0; j < m; j++) u_out[((size_t)b * N + t) * m + j] = u[j];
+    M::step(x, u, xn, dt);
+    if (noise != 0.0) {
+#pragma unroll
+      for (int i = 0; i < n; i += 2) {
+        double g0, g1;
+        normal2(seed, (unsigned long long)b, (uint32_t)t, (uint32_t)(i >> 1), g0, g1);
+        xn[i] += noise * g0;
+        if (i + 1 < n) xn[i + 1] += noise * g1;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < n; i++) x[i] = xn[i];
+  }
+}
+
+extern "C" int isls_mc_rollout_f64(int32_t model_id, int32_t n, int32_t m, int32_t N, double dt, int32_t mode,
+                                   int64_t B, const double *x0_dev, const double *K_dev, const double *k_dev,
+                                   const double *x_nom_dev, const double *u_nom_dev, double noise_scale, uint64_t seed,
+                                   double *x_out_dev, double *u_out_dev, void *stream) {
+  if (B <= 0 || N < 1 || !x0_dev || !k_dev || !x_out_dev || !u_out_dev) return isls_fail(ISLS_E_INVALID, "NULL argument or bad size");
+  if (mode < 0 || mode > 2) return isls_fail(ISLS_E_INVALID, "mode must be 0 (open loop), 1 (dp) or 2 (sls)");
+  if (mode >= 1 && !K_dev) return isls_fail(ISLS_E_INVALID, "K_dev is NULL");
+  if (mode == 2 && (long long)N * n > MC_MAX_HIST) return isls_fail(ISLS_E_UNSUPPORTED, "N * x_dim too large for the SLS history");
+  if (isls_model_supported(model_id, n, m)) return isls_fail(ISLS_E_UNSUPPORTED, "unsupported (model, n, m)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((B + 127) / 128);
+#define GO(MODEL) k_mc_rollout<MODEL><<<grid, 128, 0, s>>>(mode, N, B, dt, x0_dev, K_dev, k_dev, x_nom_dev, u_nom_dev, \
+                                                          noise_scale, seed, x_out_dev, u_out_dev)
+  if (model_id == ISLS_MODEL_CAR) GO(CarModel);
+  else if (model_id == ISLS_MODEL_ARM3) GO(Arm3Model);
+  else if (m == 1) GO(DoubleIntModel<1>);
+  else if (m == 2) GO(DoubleIntModel<2>);
+  else GO(DoubleIntModel<3>);
+#undef GO
+  CK(cudaGetLastError());
+  return ISLS_OK;
+}

@@ -22,7 +22,7 @@ enum { MZ = 0, MO = 1, MV = 2 };
 
 #define ISLS_TWO_PI 6.283185307179586476925286766559
 
-__device__ __noinline__ double mod_two_pi_slow(double a) {
+static __device__ __noinline__ double mod_two_pi_slow(double a) {
   double r = fmod(a, ISLS_TWO_PI);
   if (r < 0.0) r += ISLS_TWO_PI;
   else if (r == 0.0) r = 0.0;                     // copysign(0, b) = +0
@@ -49,14 +49,14 @@ __device__ __forceinline__ double mod_two_pi(double a) {
 // coefficients live in constant memory so every DFMA takes its coefficient as a constant-bank operand (literal
 // doubles cost two UMOV each per use - measured 25 % of the line-search instruction stream); |x| >= 2^17 takes the
 // out-of-line library path.
-__constant__ double kSC[16] = {
+static __constant__ double kSC[16] = {
     0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17, -1.4973849048591698e-33,
     1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
     -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
     -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
     2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
 
-__device__ __noinline__ void sincos_slow(double x, double *sp, double *cp) { sincos(x, sp, cp); }
+static __device__ __noinline__ void sincos_slow(double x, double *sp, double *cp) { sincos(x, sp, cp); }
 
 // branch-free core: `bad` is OR-ed with "argument outside the fast range" (results are then garbage and the caller
 // must redo with sincos_slow); no branch, so several independent evaluations schedule into one basic block.

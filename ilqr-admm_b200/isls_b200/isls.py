@@ -282,3 +282,7 @@ class iSLS:
         xn = x_nom.reshape(-1, self.N, self.x_dim)[:1].expand(nb, self.N, self.x_dim)
         _, _, xb, ub = sv.linesearch(xn, u_nom, torch.zeros_like(u_nom), zs)
         return xb, ub
+
+
+from .sls import _mc_api      # noqa: E402
+iSLS.get_trajectory_batch, iSLS.get_trajectory_dp, iSLS.get_trajectory_sls = _mc_api(True)

@@ -263,6 +263,39 @@ class SLS:
         return (K[0], k[0]) if single else (K, k)
 
 
+def _mc_api(cls_is_nonlinear):
+    """get_trajectory_batch / dp / sls (isls/sls_base.py:62-105, isls/isls_base.py:28-71) on the device."""
+    def _args(self):
+        if cls_is_nonlinear:
+            return self._model, self.x_dim, self.u_dim, self.N, self._dt()
+        if self._dt is None:
+            raise NotImplementedError("device rollouts need the registered double-integrator model")
+        return "double_integrator", self.x_dim, self.u_dim, self.N, self._dt
+
+    def _ret(x0, xs, us):
+        single = (np.ndim(x0) == 1) if not isinstance(x0, torch.Tensor) else (x0.ndim == 1)
+        return (xs[0], us[0]) if single else (xs, us)
+
+    def get_trajectory_batch(self, x0, us, noise_scale=0, seed=0):
+        xs, uo = S.mc_rollout(*_args(self), "batch", x0, None, us, noise_scale=noise_scale, seed=seed, device=self.device)
+        return _ret(x0, xs, uo)
+
+    def get_trajectory_dp(self, x0, K, k, noise_scale=0, seed=0):
+        xs, uo = S.mc_rollout(*_args(self), "dp", x0, K, k, noise_scale=noise_scale, seed=seed, device=self.device)
+        return _ret(x0, xs, uo)
+
+    def get_trajectory_sls(self, x0, K, k, noise_scale=0, seed=0):
+        xn = un = None
+        if cls_is_nonlinear:                       # iSLSBase feeds back on (x - x_nom) and adds u_nom
+            xn, un = self.x_nom, self.u_nom
+            if xn is not None and xn.ndim == 3:
+                raise NotImplementedError("get_trajectory_sls evaluates ONE controller: construct iSLS without `batch`")
+        xs, uo = S.mc_rollout(*_args(self), "sls", x0, K, k, x_nom=xn, u_nom=un, noise_scale=noise_scale, seed=seed,
+                              device=self.device)
+        return _ret(x0, xs, uo)
+    return get_trajectory_batch, get_trajectory_dp, get_trajectory_sls
+
+
 class _SlsPlan:
     """Owner of an isls_sls_plan handle + caller-owned copies of its shared device operators."""
 
@@ -285,3 +318,6 @@ class _SlsPlan:
                 self.handle = None
         except Exception:
             pass
+
+
+SLS.get_trajectory_batch, SLS.get_trajectory_dp, SLS.get_trajectory_sls = _mc_api(False)

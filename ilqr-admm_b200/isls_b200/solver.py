@@ -271,3 +271,30 @@ def profile_collect():
     cnt = (C.c_int64 * n)()
     _lib.check(_lib.lib().isls_profile_collect(ms, cnt), "isls_profile_collect")
     return {k: (ms[i], cnt[i]) for i, k in enumerate(_lib.KERNEL_CLASSES) if cnt[i]}
+
+
+def mc_rollout(model, n, m, N, dt, mode, x0, K, k, x_nom=None, u_nom=None, noise_scale=0.0, seed=0, device="cuda:0"):
+    """Monte-Carlo closed-loop rollouts of one controller over the rows of x0 (isls_mc_rollout_f64).
+    mode: "batch" (open loop, k = us[N,m]), "dp" (K[N,m,n], k[N,m]), "sls" (K[N m, N n], k[N m])."""
+    L_ = _lib.lib()
+    mid = L_.isls_model_id(model.encode())
+    _lib.check(0 if mid >= 0 else mid, "isls_model_id(%r)" % model)
+    dev = torch.device(device)
+
+    def dv(a):
+        if a is None:
+            return None
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64)))
+        return t.to(dev, dtype=torch.float64).contiguous()
+    x0, K, k, x_nom, u_nom = dv(x0), dv(K), dv(k), dv(x_nom), dv(u_nom)
+    x0 = x0.reshape(-1, n)
+    B_ = x0.shape[0]
+    xs = torch.empty(B_, N, n, dtype=torch.float64, device=dev)
+    us = torch.empty(B_, N, m, dtype=torch.float64, device=dev)
+    md = {"batch": 0, "dp": 1, "sls": 2}[mode]
+    with torch.cuda.device(dev):
+        rc = L_.isls_mc_rollout_f64(mid, n, m, N, float(dt), md, B_, _dptr(x0), _dptr(K), _dptr(k), _dptr(x_nom),
+                                    _dptr(u_nom), float(noise_scale), int(seed), _dptr(xs), _dptr(us),
+                                    C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "isls_mc_rollout_f64")
+    return xs, us

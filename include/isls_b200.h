@@ -215,6 +215,18 @@ int isls_sls_controller_f64(const isls_sls_plan *plan, int64_t B, int32_t n_firs
                             const double *du_dev, void *workspace_dev, size_t workspace_bytes, double *K_dev,
                             double *k_dev, void *stream);
 
+/* ---- Monte-Carlo closed-loop evaluation of one controller over B sampled initial states ----
+ * mode 0: get_trajectory_batch  u_t = us[t]                         (k_dev = us [N, m])
+ * mode 1: get_trajectory_dp     u_t = K_t x_t + k_t                 (K_dev [N, m, n], k_dev [N, m])
+ * mode 2: get_trajectory_sls    u_t = sum_s K[t,s](x_s - x^_s) + k_t + u^_t   (K_dev [N m, N n], k_dev [N m];
+ *                                x_nom_dev [N, n] / u_nom_dev [N, m] optional: iSLSBase subtracts the nominal)
+ * isls/sls_base.py:62-105, isls/isls_base.py:28-71.  x_{t+1} = f(x_t, u_t) + w, w ~ N(0, noise_scale) from a
+ * counter-based generator keyed by (seed, sample, step).  x0_dev [B, n] -> x_out_dev [B, N, n], u_out_dev [B, N, m]. */
+int isls_mc_rollout_f64(int32_t model_id, int32_t n, int32_t m, int32_t N, double dt, int32_t mode, int64_t B,
+                        const double *x0_dev, const double *K_dev, const double *k_dev, const double *x_nom_dev,
+                        const double *u_nom_dev, double noise_scale, uint64_t seed, double *x_out_dev,
+                        double *u_out_dev, void *stream);
+
 /* ---- measurement helpers (bench.py roofline denominators; not part of the reference surface) ---- */
 /* kernel classes for per-kernel CUDA-event timing */
 #define ISLS_KC_INIT 0

@@ -709,3 +709,25 @@ def sls_controller(Sw, Su, PHI_U, du):
     K = PHI_U @ np.linalg.inv(PHI_X)
     k = (np.eye(Su.shape[-1]) - K @ Su) @ du
     return K, k
+
+
+# ============================================================================ Monte-Carlo closed-loop evaluation
+def mc_rollout(model, mode, x0, K, k, N, x_nom=None, u_nom=None):
+    """Noise-free restatement of get_trajectory_batch / dp / sls (isls/sls_base.py:62-105, isls/isls_base.py:28-71).
+    x0 [B, n]; returns x [B, N, n], u [B, N, m]."""
+    B, n = x0.shape
+    m = model.m
+    xs, us = np.zeros((B, N, n)), np.zeros((B, N, m))
+    x = x0.copy()
+    xv = np.zeros((B, N * n))
+    for t in range(N):
+        if mode == "batch":
+            u = np.broadcast_to(k[t], (B, m))
+        elif mode == "dp":
+            u = x @ K[t].T + k[t]
+        else:
+            xv[:, t * n:(t + 1) * n] = x - (0.0 if x_nom is None else x_nom[t])
+            u = (xv @ K.T + k)[:, t * m:(t + 1) * m] + (0.0 if u_nom is None else u_nom[t])
+        xs[:, t], us[:, t] = x, u
+        x = model.f(x, u)
+    return xs, us

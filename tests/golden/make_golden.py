@@ -155,6 +155,7 @@ if __name__ == "__main__":
     golden_lqt_admm_dp(pd, "di_lqt_admm_dp")
     golden_notebook_pins()
     golden_sls()
+    golden_mc()
 
 
 def golden_sls(name="sls_admm"):
@@ -209,3 +210,47 @@ def golden_sls(name="sls_admm"):
     run("nb", 1, 100, 0.01, 1e6, 1e-2, [np.array([1.0])], 5.0)
     run("c4", 2, 50, 1.0 / 50, 1e6, 1e-2, [np.array([1.0, 1.0]), np.array([0.7, 0.9]), np.array([0.6, 0.65])], 5.0)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
+def golden_mc(name="mc_rollouts"):
+    """get_trajectory_dp / get_trajectory_sls / get_trajectory_batch of the unmodified reference (noise_scale = 0) for
+    (a) SLS with the double integrator (sls_base.py:62-105) and (b) iSLS with the car (isls_base.py:28-71)."""
+    pkg, _ = S.load()
+    from isls.utils import get_double_integrator_AB
+    rng = np.random.default_rng(99)
+    out = {}
+    with S.quiet():
+        n, m, N = 4, 2, 30
+        A, B = get_double_integrator_AB(2, nb_deriv=2, dt=0.05)
+        sls = pkg.SLS(n, m, N); sls.AB = [A, B]
+        K = rng.normal(0, 0.3, (N, m, n)); k = rng.normal(0, 0.5, (N, m))
+        Ks = np.tril(np.ones((N, N)))[:, None, :, None] * rng.normal(0, 0.05, (N, m, N, n))
+        Ks = Ks.reshape(N * m, N * n); ks = rng.normal(0, 0.5, N * m)
+        x0 = rng.normal(0, 1.0, (7, n)); us = rng.normal(0, 1.0, (N, m))
+        out.update(di_K=K, di_k=k, di_Ks=Ks, di_ks=ks, di_x0=x0, di_us=us)
+        out["di_dp_x"], out["di_dp_u"] = sls.get_trajectory_dp(x0, K, k)
+        out["di_sls_x"], out["di_sls_u"] = sls.get_trajectory_sls(x0, Ks, ks)
+        out["di_batch_x"], out["di_batch_u"] = sls.get_trajectory_batch(x0, us)
+        # iSLS + car: nominal trajectory needed by get_trajectory_sls
+        model = M.make_model("car", dt=0.1)
+        N2 = 25
+        s = pkg.iSLS(4, 2, N2); s.forward_model = model.f
+        u_nom = rng.normal(0, 0.2, (N2, 2)); x0n = np.array([0.5, -0.3, 1.0, 0.4])
+        x_nom, _ = s.rollout_batch(x0n[None], u_nom[None])
+        s.x_nom, s.u_nom = x_nom[0], u_nom
+        Kc = rng.normal(0, 0.2, (N2, 2, 4)); kc = rng.normal(0, 0.3, (N2, 2))
+        Kcs = (np.tril(np.ones((N2, N2)))[:, None, :, None] * rng.normal(0, 0.03, (N2, 2, N2, 4))).reshape(N2 * 2, N2 * 4)
+        kcs = rng.normal(0, 0.1, N2 * 2)
+        x0c = x0n + rng.normal(0, 0.2, (6, 4))
+        out.update(car_x_nom=x_nom[0], car_u_nom=u_nom, car_K=Kc, car_k=kc, car_Ks=Kcs, car_ks=kcs, car_x0=x0c)
+        # NOTE isls_base.py:39-42 / 68-71 return element [0] when x0.ndim == 2 (SURVEY D12): call per sample
+        xs, uu = [], []
+        for r in x0c:
+            a, b = s.get_trajectory_dp(r[None], Kc, kc); xs.append(a); uu.append(b)
+        out["car_dp_x"], out["car_dp_u"] = np.stack(xs), np.stack(uu)
+        xs, uu = [], []
+        for r in x0c:
+            a, b = s.get_trajectory_sls(r[None], Kcs, kcs); xs.append(a); uu.append(b)
+        out["car_sls_x"], out["car_sls_u"] = np.stack(xs), np.stack(uu)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items() if k.endswith("_x")})

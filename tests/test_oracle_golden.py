@@ -146,3 +146,18 @@ def test_sls_admm_matches_reference(golden):
         # agreement of PHI_U to ~1e-6 relative
         assert np.abs(o["PHI_U"] - g[tag + "_PHI0"]).max() / np.abs(g[tag + "_PHI0"]).max() < 1e-5
     assert int(g["nb_iters"][0]) == 26 and "%.2e %.2e" % tuple(g["nb_last"][0]) == "8.50e-13 3.77e-01"
+
+
+def test_mc_rollouts_match_reference(golden):
+    """get_trajectory_batch / dp / sls (noise-free) of SLS (double integrator) and iSLS (car) vs the reference."""
+    from oracle import models as M
+    g = golden("mc_rollouts")
+    di = M.make_model("double_integrator", nb_dim=2, dt=0.05)
+    for mode, K, k in (("dp", g["di_K"], g["di_k"]), ("sls", g["di_Ks"], g["di_ks"]), ("batch", None, g["di_us"])):
+        x, u = R.mc_rollout(di, mode, g["di_x0"], K, k, 30)
+        assert np.abs(x - g["di_%s_x" % mode]).max() < 1e-12 and np.abs(u - g["di_%s_u" % mode]).max() < 1e-12
+    car = M.make_model("car", dt=0.1)
+    x, u = R.mc_rollout(car, "dp", g["car_x0"], g["car_K"], g["car_k"], 25)
+    assert np.abs(x - g["car_dp_x"]).max() < 1e-12 and np.abs(u - g["car_dp_u"]).max() < 1e-12
+    x, u = R.mc_rollout(car, "sls", g["car_x0"], g["car_Ks"], g["car_ks"], 25, g["car_x_nom"], g["car_u_nom"])
+    assert np.abs(x - g["car_sls_x"]).max() < 1e-12 and np.abs(u - g["car_sls_u"]).max() < 1e-12
