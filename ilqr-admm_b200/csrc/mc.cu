@@ -118,3 +118,74 @@ extern "C" int isls_mc_rollout_f64(int32_t model_id, int32_t n, int32_t m, int32
   CK(cudaGetLastError());
   return ISLS_OK;
 }
+
+// --------------------------------------------------------------------------- batched row projections
+// Device counterparts of the `_batch` projections of isls/projections.py, one row per thread (dim <= 16):
+//   kind 0 bound      np.clip(x, lo[dim], hi[dim])                                          projections.py:7-11
+//   kind 1 linear     l <= a'x <= u                (a = p0[dim])                             projections.py:30-43
+//   kind 2 quadratic  l <= 0.5 |x - c|^2 <= u      (c = p0[dim] or NULL)                     projections.py:86-104
+//   kind 3 soc_unit   |z| <= t with x = [z, t], numpy batch semantics            projections.py:140-162
+//   kind 4 square     l <= |x - c|_inf <= u        (c = p0[dim] or NULL)                     projections.py:252-272
+//   kind 5 unit_ball  |x| <= 1                                                               projections.py:232-240
+#define PROJ_MAXD 16
+__global__ void k_project_rows(int kind, long long rows, int dim, const double *x, const double *p0, const double *p1,
+                               double l, double u, double *out) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  double v[PROJ_MAXD], z[PROJ_MAXD];
+  for (int i = 0; i < dim; i++) v[i] = x[r * dim + i];
+  if (kind == 0) {
+    for (int i = 0; i < dim; i++) z[i] = fmin(fmax(v[i], p0[i]), p1[i]);
+  } else if (kind == 1) {
+    double ax = 0.0, aa = 0.0;
+    for (int i = 0; i < dim; i++) { ax += v[i] * p0[i]; aa += p0[i] * p0[i]; }
+    aa += 1e-30;
+    double mu = 0.0;
+    if (ax > u) mu = ax - u;
+    if (ax < l) mu = ax - l;
+    for (int i = 0; i < dim; i++) z[i] = (mu != 0.0) ? v[i] - mu * (p0[i] / aa) : v[i];
+  } else if (kind == 2) {
+    double ss = 0.0;
+    for (int i = 0; i < dim; i++) { if (p0) v[i] -= p0[i]; ss += v[i] * v[i]; }
+    const double val = 0.5 * ss, nrm = sqrt(ss);
+    for (int i = 0; i < dim; i++) z[i] = v[i];
+    if (val > u) for (int i = 0; i < dim; i++) z[i] = v[i] * sqrt(2.0 * u) / nrm;
+    if (l > val) for (int i = 0; i < dim; i++) z[i] = v[i] * sqrt(2.0 * l) / nrm;
+    if (p0) for (int i = 0; i < dim; i++) z[i] += p0[i];
+  } else if (kind == 3) {
+    const int d = dim - 1;
+    double ss = 0.0;
+    for (int i = 0; i < d; i++) ss += v[i] * v[i];
+    const double zn = sqrt(ss), t = v[d];
+    const bool c1 = (zn <= -t) || (t < 0.0), c2 = (zn > t) || (zn > -t), c3 = zn <= t;
+    for (int i = 0; i < dim; i++) z[i] = v[i];
+    if (c2) { const double tmp = (zn + t) / 2.0; for (int i = 0; i < d; i++) z[i] = tmp * v[i] / (zn + 1e-30); z[d] = tmp; }
+    if (c1) for (int i = 0; i < dim; i++) z[i] = 0.0;
+    if (c3) for (int i = 0; i < dim; i++) z[i] = v[i];
+  } else if (kind == 4) {
+    int j = 0;
+    double mx = -1.0;
+    for (int i = 0; i < dim; i++) { if (p0) v[i] -= p0[i]; const double a = fabs(v[i]); if (a > mx) { mx = a; j = i; } }
+    for (int i = 0; i < dim; i++) z[i] = v[i];
+    if (mx < l) z[j] = l * ((v[j] > 0.0) - (v[j] < 0.0));
+    for (int i = 0; i < dim; i++) { z[i] = fmax(fmin(z[i], u), -u); if (p0) z[i] += p0[i]; }
+  } else {
+    double ss = 0.0;
+    for (int i = 0; i < dim; i++) ss += v[i] * v[i];
+    const double nrm = sqrt(ss);
+    for (int i = 0; i < dim; i++) z[i] = (nrm <= 1.0) ? v[i] : v[i] / nrm;
+  }
+  for (int i = 0; i < dim; i++) out[r * dim + i] = z[i];
+}
+
+extern "C" int isls_project_rows_f64(int32_t kind, int64_t rows, int32_t dim, const double *x_dev, const double *p0_dev,
+                                     const double *p1_dev, double l, double u, double *out_dev, void *stream) {
+  if (rows <= 0 || dim < 1 || dim > PROJ_MAXD || !x_dev || !out_dev) return isls_fail(ISLS_E_INVALID, "bad size or NULL argument");
+  if (kind < 0 || kind > 5) return isls_fail(ISLS_E_UNSUPPORTED, "unknown projection kind");
+  if ((kind == 0 && (!p0_dev || !p1_dev)) || (kind == 1 && !p0_dev)) return isls_fail(ISLS_E_INVALID, "missing parameter array");
+  if (kind == 3 && dim < 2) return isls_fail(ISLS_E_INVALID, "soc_unit needs dim >= 2");
+  k_project_rows<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(kind, rows, dim, x_dev, p0_dev, p1_dev, l, u,
+                                                                                   out_dev);
+  CK(cudaGetLastError());
+  return ISLS_OK;
+}

@@ -45,7 +45,7 @@ EXPORTS = ["isls_version", "isls_last_error_string", "isls_model_id", "isls_mode
            "isls_lqt_admm_dp_f64", "isls_riccati_f64", "isls_rollout_linesearch_f64", "isls_admm_project_dual_f64",
            "isls_measure_fp64_tflops", "isls_profile_enable", "isls_profile_collect",
            "isls_sls_plan_create", "isls_sls_plan_destroy", "isls_sls_operators", "isls_sls_solve_f64",
-           "isls_sls_admm_f64", "isls_sls_controller_f64", "isls_mc_rollout_f64"]
+           "isls_sls_admm_f64", "isls_sls_controller_f64", "isls_mc_rollout_f64", "isls_project_rows_f64"]
 
 KERNEL_CLASSES = ["init", "kpass", "ff", "linesearch", "admm", "outer_end", "finalize", "backward_full", "accept",
                   "lqt", "compact"]
@@ -93,6 +93,8 @@ def lib():
     L.isls_mc_rollout_f64.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int64,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                       C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.isls_project_rows_f64.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                        C.c_double, C.c_void_p, C.c_void_p]
     L.isls_profile_enable.argtypes = [C.c_int]
     L.isls_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     _lib = L

@@ -52,3 +52,59 @@ class SetConvexSOC:
         self.bs = np.ascontiguousarray(np.stack([np.asarray(b, dtype=np.float64) for b in bs]))
         assert self.As.ndim == 3 and self.bs.shape == self.As.shape[:2]
         self.rho, self.max_iter, self.threshold = float(rho), int(max_iter), float(threshold)
+
+
+# ---------------------------------------------------------------- batched row projections on the device (CUDA tensors)
+def _rows(kind, x, p0=None, p1=None, l=0.0, u=0.0):
+    import ctypes as C
+    from . import _lib
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float64 and x.ndim == 2):
+        raise TypeError("device projections take a CUDA float64 tensor [rows, dim]")
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    t = lambda a: None if a is None else torch.as_tensor(np.asarray(a, dtype=np.float64) if not isinstance(a, torch.Tensor)
+                                                         else a, dtype=torch.float64).to(x.device).expand(x.shape[1]).contiguous()
+    p0, p1 = t(p0), t(p1)
+    ptr = lambda a: None if a is None else C.c_void_p(a.data_ptr())
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().isls_project_rows_f64(kind, x.shape[0], x.shape[1], ptr(x), ptr(p0), ptr(p1), float(l), float(u),
+                                              ptr(out), C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    _lib.check(rc, "isls_project_rows_f64")
+    return out
+
+
+def project_bound_batch(x, l, u):
+    """isls/projections.py:7-11 on rows of a CUDA tensor (per-component bounds)."""
+    return _rows(0, x, l, u)
+
+
+def project_linear_batch(x, a, l, u):
+    """isls/projections.py:30-43."""
+    return _rows(1, x, a, None, l, u)
+
+
+def project_quadratic_batch(x, l, u, center=None):
+    """isls/projections.py:86-104; `center` c evaluates project_quadratic(x - c, l, u) + c (obstacle notebooks)."""
+    return _rows(2, x, center, None, l, u)
+
+
+def project_quadratic_b_batch(x, b, l, u):
+    """isls/projections.py:106-115: l <= 0.5 x'x + b'x <= u."""
+    b = np.asarray(b, dtype=np.float64)
+    const = 0.5 * float(b @ b)
+    return _rows(2, x, -b, None, l + const, u + const)
+
+
+def project_soc_unit_batch(x):
+    """isls/projections.py:140-162 on rows [z, t] (numpy batch semantics incl. SURVEY D9)."""
+    return _rows(3, x)
+
+
+def project_square_batch(x, l, u, center=None):
+    """isls/projections.py:252-272 (`center`: project_square_c)."""
+    return _rows(4, x, center, None, l, u)
+
+
+def project_unit_ball_batch(x):
+    """isls/projections.py:232-240 row-wise."""
+    return _rows(5, x)

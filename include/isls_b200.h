@@ -227,6 +227,17 @@ int isls_mc_rollout_f64(int32_t model_id, int32_t n, int32_t m, int32_t N, doubl
                         const double *u_nom_dev, double noise_scale, uint64_t seed, double *x_out_dev,
                         double *u_out_dev, void *stream);
 
+/* ---- batched row projections: device counterparts of the `_batch` functions of isls/projections.py (8f #2) ----
+ * x_dev [rows, dim] -> out_dev [rows, dim] (dim <= 16), one row per thread.
+ *   kind 0 bound      np.clip(x, p0 = lo[dim], p1 = hi[dim])                     isls/projections.py:7-11
+ *   kind 1 linear     l <= a'x <= u, a = p0[dim]                                  isls/projections.py:30-43
+ *   kind 2 quadratic  l <= 0.5 |x - c|^2 <= u, c = p0[dim] or NULL                isls/projections.py:86-104
+ *   kind 3 soc_unit   |x[:-1]| <= x[-1], numpy batch semantics                    isls/projections.py:140-162
+ *   kind 4 square     l <= |x - c|_inf <= u, c = p0[dim] or NULL                  isls/projections.py:252-272
+ *   kind 5 unit_ball  |x| <= 1                                                    isls/projections.py:232-240 */
+int isls_project_rows_f64(int32_t kind, int64_t rows, int32_t dim, const double *x_dev, const double *p0_dev,
+                          const double *p1_dev, double l, double u, double *out_dev, void *stream);
+
 /* ---- measurement helpers (bench.py roofline denominators; not part of the reference surface) ---- */
 /* kernel classes for per-kernel CUDA-event timing */
 #define ISLS_KC_INIT 0

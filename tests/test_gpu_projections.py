@@ -1,0 +1,65 @@
+"""GPU: batched row projections against the reference's own functions restated inline
+(isls/projections.py) on random rows incl. the boundary cases (inside / outside / zero rows / t < 0 for the SOC)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_linear(x, a, l, u):                     # projections.py:30-43
+    aTx = np.sum(x * a, axis=-1)
+    aTa = np.sum(a * a, axis=-1) + 1e-30
+    z = x.copy()
+    c1, c2 = aTx > u, aTx < l
+    z[c1] = z[c1] - (aTx - u)[c1, None] * (a / aTa)
+    z[c2] = z[c2] - (aTx - l)[c2, None] * (a / aTa)
+    return z
+
+
+def _ref_quadratic(x, l, u):                     # projections.py:86-104
+    z = x.copy()
+    val = 0.5 * np.sum(x * x, axis=-1)
+    c1, c2 = val > u, l > val
+    z[c1] = x[c1] * np.sqrt(2 * u) / np.linalg.norm(x[c1], axis=-1)[:, None]
+    z[c2] = x[c2] * np.sqrt(2 * l) / np.linalg.norm(x[c2], axis=-1)[:, None]
+    return z
+
+
+def _ref_square(x, l, u):                        # projections.py:252-262
+    z = x.copy()
+    j = np.argmax(np.abs(x), axis=-1)
+    cond = np.where(np.linalg.norm(x, ord=np.inf, axis=-1) < l)
+    z[(cond, j[cond])] = l * np.sign(x[(cond, j[cond])])
+    return np.maximum(np.minimum(z, u), -u)
+
+
+def test_row_projections_vs_numpy():
+    import torch
+    from isls_b200 import projections as Pj
+    from oracle import restated as R
+    rng = np.random.default_rng(11)
+    for dim in (2, 3, 5):
+        x = rng.normal(0, 1.5, (4000, dim))
+        x[::17] *= 0.05
+        td = torch.as_tensor(x, device="cuda:0")
+        g = lambda t: t.cpu().numpy()
+        lo, hi = rng.normal(-1, 0.3, dim), rng.normal(1, 0.3, dim)
+        assert np.array_equal(g(Pj.project_bound_batch(td, lo, hi)), np.clip(x, lo, hi))
+        a = rng.normal(0, 1, dim)
+        assert np.abs(g(Pj.project_linear_batch(td, a, -0.4, 0.7)) - _ref_linear(x, a, -0.4, 0.7)).max() < 1e-14
+        assert np.abs(g(Pj.project_quadratic_batch(td, 0.3, 2.0)) - _ref_quadratic(x, 0.3, 2.0)).max() < 1e-14
+        c = rng.normal(0, 0.5, dim)
+        assert np.abs(g(Pj.project_quadratic_batch(td, 0.3, 2.0, center=c)) - (_ref_quadratic(x - c, 0.3, 2.0) + c)).max() < 1e-14
+        b = rng.normal(0, 0.5, dim)
+        k = 0.5 * b @ b
+        assert np.abs(g(Pj.project_quadratic_b_batch(td, b, 0.3, 2.0)) - (_ref_quadratic(x + b, 0.3 + k, 2.0 + k) - b)).max() < 1e-14
+        assert np.abs(g(Pj.project_square_batch(td, 0.4, 1.2)) - _ref_square(x, 0.4, 1.2)).max() < 1e-15
+        assert np.abs(g(Pj.project_square_batch(td, 0.4, 1.2, center=c)) - (_ref_square(x - c, 0.4, 1.2) + c)).max() < 1e-15
+        zz, tt = R.project_soc_unit_batch(x[:, :-1], x[:, -1])
+        assert np.abs(g(Pj.project_soc_unit_batch(td)) - np.concatenate([zz, tt[:, None]], 1)).max() < 1e-15
+        nrm = np.linalg.norm(x, axis=-1, keepdims=True)
+        assert np.abs(g(Pj.project_unit_ball_batch(td)) - np.where(nrm <= 1, x, x / nrm)).max() < 1e-15
+    # SOC batch semantics: [3, 0, -1] -> [0, 0, 0]
+    out = Pj.project_soc_unit_batch(torch.tensor([[3.0, 0.0, -1.0], [0.5, 0.0, 1.0], [3.0, 0.0, 1.0]], device="cuda:0",
+                                                 dtype=torch.float64)).cpu().numpy()
+    assert np.array_equal(out[0], [0, 0, 0]) and np.array_equal(out[1], [0.5, 0, 1.0]) and np.allclose(out[2], [2, 0, 2])
