@@ -836,14 +836,54 @@ template <class M>
 __device__ __forceinline__ void admm_finish(const Dev &d, const TileCtx<M> &c, int outer, int inner, int bi,
                                             double prim, double dual);
 
-// fuse bit 1: warp 0 first runs the ff-pass + linear rollout of its tile (ff_body); fuse bit 2: warp 0 finishes with
-// the winner rollout + ADMM update (admm_body).  The single-warp HBM-bound phases of one CTA overlap the FP64-bound
-// candidate rollouts of the other CTAs resident on the SM.
-template <class M, int CPT, int MAXW, int MINB>
+// ---- 1-D bulk async copies (TMA engine, cp.async.bulk) with mbarrier completion: the line search stages the next
+// chunks of its per-step operands (u^, du, reg_x of the tile: contiguous in the tile-blocked layout) in shared memory
+// while the FP64 chains run.  (A register software prefetch did not survive ptxas: it sank the copy of the prefetched
+// registers to right behind the loads, exposing the full memory latency every step - 22 % of all stall samples sat
+// on that one MOV, profiles/r2_linesearch_schedule.md.)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
+// `fuse` != 0: the CTA finishes with the streaming ADMM z / lambda / reg update of the winner (control-only
+// projections).  PX = the plan has a state projection (compile-time, so the control-only kernel carries no penalty
+// accumulators or reg_x operands).  Every thread of the CTA runs the rollout loop (it contains CTA barriers); lanes
+// whose problem is finished compute on stale data and are masked at the writes.
+template <class M, int CPT, int MAXW, int MINB, bool PX>
 __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fuse, int outer, int inner) {
   constexpr int n = M::n, m = M::m;
-  __shared__ double sc[MAX_L][TILE];
-  __shared__ double scs[MAX_L][TILE];        // state-cost part of every candidate (cost of the winner w/o penalty)
+  constexpr int LMAX = CPT * MAXW;                            // candidates this CTA shape can hold (>= d.L)
+  constexpr int ROWS = 2 * m + (PX ? n : 0);                  // staged doubles per lane and step
+  constexpr int STAGE_BYTES = LMAX > 32 ? 4096 : 12288;       // keeps the static shared memory under 48 KB
+  constexpr int TC_ = STAGE_BYTES / (ROWS * TILE * 8);        // steps per chunk
+  constexpr int TC = TC_ > 10 ? 10 : (TC_ < 1 ? 1 : TC_);
+  constexpr int NST = 2;                                      // chunks in flight
+  __shared__ __align__(128) double su[NST][TC][m][TILE];      // u^
+  __shared__ __align__(128) double sd[NST][TC][m][TILE];      // du
+  __shared__ __align__(128) double sr[NST][PX ? TC : 1][PX ? n : 1][TILE];   // reg_x
+  __shared__ unsigned long long fullbar[NST];
+  __shared__ double sc[LMAX][TILE];
+  __shared__ double scs[LMAX][TILE];         // state-cost part of every candidate (cost of the winner w/o penalty)
   __shared__ double sred[2][MAXW][TILE];     // residual partial sums of the fused ADMM update
   __shared__ int sbest[TILE];
   const int tile = d.tile0 + blockIdx.x;
@@ -851,11 +891,30 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
   const int w = threadIdx.y;
   const bool skip = d.odone[c.b] || d.adone[c.b];
   if (__syncthreads_and(skip)) return;
-  if (fuse & 1) {
-    if (w == 0 && !skip) ff_body<M>(d, c);
+  {
+    const bool leader = threadIdx.x == 0 && w == 0;
+    const int nchunks = (d.N + TC - 1) / TC;
+    const double *uh_t = d.uh + (size_t)tile * d.N * m * TILE, *du_t = d.du + (size_t)tile * d.N * m * TILE;
+    const double *rg_t = PX ? d.rgx + (size_t)tile * d.N * n * TILE : nullptr;
+    auto issue = [&](int ch) {                                // leader only
+      const int st = ch % NST, t0 = ch * TC, cnt = min(TC, d.N - t0);
+      const unsigned bu = (unsigned)(cnt * m * TILE * sizeof(double)), bx = (unsigned)(cnt * n * TILE * sizeof(double));
+      mbar_expect_tx(&fullbar[st], 2 * bu + (PX ? bx : 0u));
+      bulk_g2s(&su[st][0][0][0], uh_t + (size_t)t0 * m * TILE, bu, &fullbar[st]);
+      bulk_g2s(&sd[st][0][0][0], du_t + (size_t)t0 * m * TILE, bu, &fullbar[st]);
+      if (PX) bulk_g2s(&sr[st][0][0][0], rg_t + (size_t)t0 * n * TILE, bx, &fullbar[st]);
+    };
+    if (leader) {
+#pragma unroll
+      for (int i = 0; i < NST; i++) mbar_init(&fullbar[i], 1);
+      mbar_fence_init();
+    }
     __syncthreads();
-  }
-  if (!skip) {
+    if (leader) {
+#pragma unroll
+      for (int i = 0; i < NST; i++)
+        if (i < nchunks) issue(i);
+    }
     const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m), *du = c.at(d.du, d, m);
     const double *rgx = c.at(d.rgx, d, n);
     const double *zs = d.zs + (size_t)tile * d.n_via * n * TILE + c.lane;
@@ -866,66 +925,58 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
       const int l = w * CPT + q;
       al[q] = l < d.L ? d.alphas[l] : 0.0;
       cs[q] = px[q] = 0.0;
-      bad[q] = false;
 #pragma unroll
       for (int i = 0; i < n; i++) x[q][i] = EL(xh, n, 0, i);
+      bad[q] = !M::fast_state(x[q]);
     }
-    // operands of step t+1 are loaded while the FP64 chains of step t run (software prefetch)
-    double un_n[m], dun_n[m], rx_n[n];
-    int qz_n;
-    auto fetch = [&](int t) {
+    for (int ch = 0; ch < nchunks; ch++) {
+      const int st = ch % NST, t0 = ch * TC, cnt = min(TC, d.N - t0);
+      unsigned qmask = 0;                                     // steps of this chunk that carry a state cost
 #pragma unroll
-      for (int j = 0; j < m; j++) { un_n[j] = EL(uh, m, t, j); dun_n[j] = EL(du, m, t, j); }
-      if (d.proj_x) {
-#pragma unroll
-        for (int i = 0; i < n; i++) rx_n[i] = EL(rgx, n, t, i);
-      }
-      qz_n = d.qnz[t];
-    };
-    fetch(0);
+      for (int tt = 0; tt < TC; tt++)
+        if (tt < cnt && d.qnz[t0 + tt]) qmask |= 1u << tt;
+      mbar_wait(&fullbar[st], (unsigned)((ch / NST) & 1));
 #pragma unroll 2
-    for (int t = 0; t < d.N; t++) {
-      double un[m], dun[m], rx[n], zv[n], qd[n], rhx[n];
-      const bool qz = qz_n;
+      for (int tt = 0; tt < cnt; tt++) {
+        const int t = t0 + tt;
+        double un[m], dun[m], rx[n], zv[n], qd[n], rhx[n];
+        const bool qz = (qmask >> tt) & 1u;
 #pragma unroll
-      for (int j = 0; j < m; j++) { un[j] = un_n[j]; dun[j] = dun_n[j]; }
-      if (d.proj_x) {
+        for (int j = 0; j < m; j++) { un[j] = su[st][tt][j][c.lane]; dun[j] = sd[st][tt][j][c.lane]; }
+        if (PX) {
 #pragma unroll
-        for (int i = 0; i < n; i++) { rx[i] = rx_n[i]; rhx[i] = d.rho_x[t * n + i]; }
+          for (int i = 0; i < n; i++) { rx[i] = sr[st][tt][i][c.lane]; rhx[i] = d.rho_x[t * n + i]; }
+        }
+        if (qz) {
+          const int s = d.seq[t];
+#pragma unroll
+          for (int i = 0; i < n; i++) { zv[i] = EL(zs, n, s, i); qd[i] = d.qd[t * n + i]; }
+#pragma unroll
+          for (int q = 0; q < CPT; q++)
+#pragma unroll
+            for (int i = 0; i < n; i++) { const double e = x[q][i] - zv[i]; cs[q] += (e * e) * qd[i]; }
+        }
+        if (PX) {
+#pragma unroll
+          for (int q = 0; q < CPT; q++)
+#pragma unroll
+            for (int i = 0; i < n; i++) { const double e = x[q][i] - rx[i]; px[q] += (e * e) * rhx[i]; }
+        }
+        // branch-free model steps, written stage by stage across the CPT chains (models.cuh: steps_fast); an argument
+        // outside the fast range of sincos / mod only raises the candidate's sticky flag (its rollout is redone below)
+        double u[CPT][m];
+#pragma unroll
+        for (int j = 0; j < m; j++)
+#pragma unroll
+          for (int q = 0; q < CPT; q++) u[q][j] = fma(al[q], dun[j], un[j]);
+        M::template steps_fast<CPT>(x, u, d.dt, bad);
       }
-      if (t + 1 < d.N) fetch(t + 1);
-      if (qz) {
-        const int s = d.seq[t];
-#pragma unroll
-        for (int i = 0; i < n; i++) { zv[i] = EL(zs, n, s, i); qd[i] = d.qd[t * n + i]; }
-      }
-      if (qz) {
-#pragma unroll
-        for (int q = 0; q < CPT; q++)
-#pragma unroll
-          for (int i = 0; i < n; i++) { const double e = x[q][i] - zv[i]; cs[q] += (e * e) * qd[i]; }
-      }
-      if (d.proj_x) {
-#pragma unroll
-        for (int q = 0; q < CPT; q++)
-#pragma unroll
-          for (int i = 0; i < n; i++) { const double e = x[q][i] - rx[i]; px[q] += (e * e) * rhx[i]; }
-      }
-      // branch-free model steps: the CPT independent chains interleave in one basic block; an argument outside the
-      // fast range of sincos / mod only raises the candidate's sticky flag (its rollout is redone exactly below)
-#pragma unroll
-      for (int q = 0; q < CPT; q++) {
-        double u[m], xn[n];
-#pragma unroll
-        for (int j = 0; j < m; j++) u[j] = fma(al[q], dun[j], un[j]);
-        M::step_fast(x[q], u, xn, d.dt, bad[q]);
-#pragma unroll
-        for (int i = 0; i < n; i++) x[q][i] = xn[i];
-      }
+      __syncthreads();                                        // every warp is done with stage `st`
+      if (leader && ch + NST < nchunks) issue(ch + NST);
     }
 #pragma unroll
     for (int q = 0; q < CPT; q++) {
-      if (bad[q]) {          // rare: exact re-rollout of this candidate (library sincos / fmod paths)
+      if (bad[q] && !skip) {   // rare: exact re-rollout of this candidate (library sincos / fmod paths)
         double xe[n], u[m], xn[n];
         double cse = 0.0, pxe = 0.0;
 #pragma unroll
@@ -934,7 +985,7 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
 #pragma unroll
           for (int j = 0; j < m; j++) u[j] = fma(al[q], EL(du, m, t, j), EL(uh, m, t, j));
           cse += state_cost<M>(d, zs, t, xe);
-          if (d.proj_x) {
+          if (PX) {
 #pragma unroll
             for (int i = 0; i < n; i++) { const double e = xe[i] - EL(rgx, n, t, i); pxe += (e * e) * d.rho_x[t * n + i]; }
           }
@@ -951,9 +1002,9 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
 #pragma unroll
     for (int q = 0; q < CPT; q++) {
       const int l = w * CPT + q;
-      if (l < d.L) {
+      if (l < d.L && !skip) {
         double tot = cs[q] + fma(al[q], fma(al[q], c2, c1), c0);   // cost_function + control penalty (isls.py:470,476)
-        if (d.proj_x) tot += px[q];                                // isls.py:473
+        if (PX) tot += px[q];                                      // isls.py:473
         sc[l][c.lane] = tot;
         scs[l][c.lane] = cs[q];
       }
@@ -971,9 +1022,8 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
       double *o = d.lsc + (size_t)tile * d.L * TILE + c.lane;
       for (int l = 0; l < d.L; l++) o[(size_t)l * TILE] = sc[l][c.lane];
     }
-    if (fuse & 2) admm_body<M>(d, c, outer, inner);
   }
-  if (!(fuse & 4)) return;
+  if (!fuse) return;
   // ---- fused ADMM update for control-only projections (admm.py:43-97): z_u, lambda_u and reg_u depend on the winner
   // only through u = u^ + alpha* du, so the whole CTA streams the tile's N x m elements (warp w takes t = w, w+W, ..)
   // instead of a separate trajectory-per-thread kernel re-rolling the model.  Residual sums: fixed-order reduction.
@@ -1921,11 +1971,13 @@ template <typename F>
 static int dispatch_model(const isls_plan *p, F &&f) {
   switch (p->desc.model_id) {
     case ISLS_MODEL_CAR: return f(CarModel{});
+#ifndef ISLS_DEV_ONLY_CAR               // development builds (SASS inspection) instantiate one model only
     case ISLS_MODEL_ARM3: return f(Arm3Model{});
     case ISLS_MODEL_DOUBLE_INTEGRATOR:
       if (p->m == 1) return f(DoubleIntModel<1>{});
       if (p->m == 2) return f(DoubleIntModel<2>{});
       if (p->m == 3) return f(DoubleIntModel<3>{});
+#endif
   }
   return fail(ISLS_E_UNSUPPORTED, "unsupported model");
 }
@@ -2143,9 +2195,14 @@ static void launch_ls_cfg(const Dev &d, bool closed, cudaStream_t s, LsFuse f) {
   else {
     if (pad) {
       static bool set = false;
-      if (!set) { cudaFuncSetAttribute(k_linesearch<M, CPT, MAXW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad); set = true; }
+      if (!set) {
+        cudaFuncSetAttribute(k_linesearch<M, CPT, MAXW, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+        cudaFuncSetAttribute(k_linesearch<M, CPT, MAXW, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+        set = true;
+      }
     }
-    k_linesearch<M, CPT, MAXW, MINB><<<d.tile1 - d.tile0, dim3(TILE, W), pad, s>>>(d, f.fuse, f.outer, f.inner);
+    if (d.proj_x) k_linesearch<M, CPT, MAXW, MINB, true><<<d.tile1 - d.tile0, dim3(TILE, W), pad, s>>>(d, f.fuse, f.outer, f.inner);
+    else k_linesearch<M, CPT, MAXW, MINB, false><<<d.tile1 - d.tile0, dim3(TILE, W), pad, s>>>(d, f.fuse, f.outer, f.inner);
   }
 }
 static int solve_chunks() {
@@ -2154,14 +2211,6 @@ static int solve_chunks() {
     const char *e = getenv("ISLS_CHUNKS");      // number of concurrently running batch chunks (streams)
     v = e ? atoi(e) : 1;
     if (v < 1) v = 1;
-  }
-  return v;
-}
-static int solve_fuse() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("ISLS_FUSE");        // bit 1: ff-pass fused into the line-search CTA, bit 2: ADMM update
-    v = e ? atoi(e) : 0;
   }
   return v;
 }
@@ -2191,19 +2240,9 @@ static void launch_linesearch(const Dev &d, bool closed, cudaStream_t s, LsFuse 
     else launch_ls_cfg<M, 2, 25>(d, closed, s, f);
   } else {
     if (d.L <= 20) {
-      if (ov == 1) launch_ls_cfg<M, 1, 20>(d, closed, s, f);
-      else if (ov == 2) launch_ls_cfg<M, 2, 10, 2>(d, closed, s, f);
-      else if (ov == 5) launch_ls_cfg<M, 5, 4, 2>(d, closed, s, f);
-      else if (ov == 73) launch_ls_cfg<M, 7, 3, 3>(d, closed, s, f);
-      else if (ov == 74) launch_ls_cfg<M, 7, 3, 4>(d, closed, s, f);
-      else if (ov == 75) launch_ls_cfg<M, 7, 3, 5>(d, closed, s, f);
-      else if (ov == 43) launch_ls_cfg<M, 4, 5, 3>(d, closed, s, f);
-      else if (ov == 54) launch_ls_cfg<M, 5, 4, 4>(d, closed, s, f);
-      else if (ov == 103) launch_ls_cfg<M, 10, 2, 3>(d, closed, s, f);
-      else if (ov == 104) launch_ls_cfg<M, 10, 2, 4>(d, closed, s, f);
-      else if (ov == 42) launch_ls_cfg<M, 4, 5, 2>(d, closed, s, f);
-      else if (ov == 44) launch_ls_cfg<M, 4, 5, 4>(d, closed, s, f);
-      else launch_ls_cfg<M, 5, 4, 3>(d, closed, s, f);      // 5 chains/thread, 4 warps, 3 CTAs/SM (168 regs, no spills)
+      if (ov == 5) launch_ls_cfg<M, 5, 4, 2>(d, closed, s, f);
+      else if (ov == 4) launch_ls_cfg<M, 4, 5, 3>(d, closed, s, f);
+      else launch_ls_cfg<M, 5, 4, 3>(d, closed, s, f);      // 5 chains/thread, 4 warps, 3 CTAs/SM (168 regs)
     } else launch_ls_cfg<M, 4, 13>(d, closed, s, f);
   }
 }
@@ -2252,11 +2291,10 @@ extern "C" int isls_ilqr_admm_solve_f64(const isls_plan *plan, const isls_solve_
       for (int j = 0; j < d.max_outer; j++) {
         LAUNCH(ISLS_KC_KPASS, cs, (k_kpass<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc)));
         for (int a = 0; a < d.max_admm; a++) {
-          int fuse = solve_fuse();
-          if (!(fuse & 2) && !d.proj_x && d.proj_u && !no_fused_update()) fuse |= 4;   // streaming ADMM epilogue
-          if (!(fuse & 1)) LAUNCH(ISLS_KC_FF, cs, launch_ff<M>(dc, cs));
+          const int fuse = (!d.proj_x && d.proj_u && !no_fused_update()) ? 1 : 0;      // streaming ADMM epilogue
+          LAUNCH(ISLS_KC_FF, cs, launch_ff<M>(dc, cs));
           LAUNCH(ISLS_KC_LINESEARCH, cs, launch_linesearch<M>(dc, false, cs, LsFuse{fuse, j, a}));
-          if (!(fuse & 6)) LAUNCH(ISLS_KC_ADMM, cs, (k_admm<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, j, a)));
+          if (!fuse) LAUNCH(ISLS_KC_ADMM, cs, (k_admm<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, j, a)));
         }
         LAUNCH(ISLS_KC_OUTER_END, cs, (k_outer_end<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, j)));
         if (compact && j + 1 < d.max_outer && (j + 1) % solve_compact() == 0) {

@@ -95,6 +95,73 @@ __device__ __forceinline__ void sincos_pio2(double x, double *sp, double *cp) {
   if (bad) sincos_slow(x, sp, cp);
 }
 
+// ---- K independent evaluations written STAGE BY STAGE (loop over the K arguments inside every polynomial stage).
+// ptxas keeps roughly the source order under register pressure: with the chain-by-chain form above the K Horner
+// chains of a line-search thread were emitted one after the other (7 dependent DFMAs, 8 stall cycles each); in this
+// form consecutive instructions belong to different chains, so a dependent DFMA is 2K issue slots away (>= the 8-cycle
+// FP64 latency for K >= 4) and one warp alone can keep the FP64 pipe busy.  Same arithmetic as sincos_core, bit for bit.
+// Sign flips are integer XORs on the high word (the chain form spent a DADD + 2 FSEL each).
+__device__ __forceinline__ double xor_sign(double v, int w) {
+  return __hiloint2double(__double2hiint(v) ^ (w & (int)0x80000000), __double2loint(v));
+}
+// |x| < 200000 on the high word only (no FP64-pipe compare); NaN / inf are out of range
+__device__ __forceinline__ bool sincos_fast_range(double x) {
+  return (__double2hiint(x) & 0x7fffffff) < 0x41086a00;          // 0x41086a00'00000000 = 200000.0
+}
+template <int K, bool CHECK>
+__device__ __forceinline__ void sincos_multi(const double (&x)[K], double (&s)[K], double (&c)[K], bool (&bad)[K]) {
+  double big[K], r[K], z[K], ps[K], pc[K];
+#pragma unroll
+  for (int q = 0; q < K; q++) big[q] = fma(x[q], kSC[0], 6755399441055744.0);
+  if (CHECK) {
+#pragma unroll
+    for (int q = 0; q < K; q++) bad[q] |= !sincos_fast_range(x[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < K; q++) z[q] = big[q] - 6755399441055744.0;             // kd
+#pragma unroll
+  for (int q = 0; q < K; q++) r[q] = fma(-z[q], kSC[1], x[q]);
+#pragma unroll
+  for (int q = 0; q < K; q++) r[q] = fma(-z[q], kSC[2], r[q]);
+#pragma unroll
+  for (int q = 0; q < K; q++) r[q] = fma(-z[q], kSC[3], r[q]);
+#pragma unroll
+  for (int q = 0; q < K; q++) z[q] = r[q] * r[q];
+#pragma unroll
+  for (int q = 0; q < K; q++) { ps[q] = fma(z[q], kSC[4], kSC[5]); pc[q] = fma(z[q], kSC[10], kSC[11]); }
+#pragma unroll
+  for (int q = 0; q < K; q++) { ps[q] = fma(z[q], ps[q], kSC[6]); pc[q] = fma(z[q], pc[q], kSC[12]); }
+#pragma unroll
+  for (int q = 0; q < K; q++) { ps[q] = fma(z[q], ps[q], kSC[7]); pc[q] = fma(z[q], pc[q], kSC[13]); }
+#pragma unroll
+  for (int q = 0; q < K; q++) { ps[q] = fma(z[q], ps[q], kSC[8]); pc[q] = fma(z[q], pc[q], kSC[14]); }
+#pragma unroll
+  for (int q = 0; q < K; q++) { ps[q] = fma(z[q], ps[q], kSC[9]); pc[q] = fma(z[q], pc[q], kSC[15]); }
+#pragma unroll
+  for (int q = 0; q < K; q++) { s[q] = z[q] * r[q]; pc[q] = fma(z[q], pc[q], -0.5); }
+#pragma unroll
+  for (int q = 0; q < K; q++) { ps[q] = fma(s[q], ps[q], r[q]); pc[q] = fma(z[q], pc[q], 1.0); }
+#pragma unroll
+  for (int q = 0; q < K; q++) {
+    const int k = __double2loint(big[q]);
+    const bool odd = k & 1;
+    const double sa = odd ? pc[q] : ps[q], ca = odd ? ps[q] : pc[q];
+    s[q] = xor_sign(sa, k << 30);                 // (k & 2) ? -sa : sa
+    c[q] = xor_sign(ca, (k + 1) << 30);           // ((k + 1) & 2) ? -ca : ca
+  }
+}
+
+// np.mod(a, 2*pi) on [-2pi, 4pi) with ONE add: the addend (-2pi / +2pi / 0) is selected, a + 0.0 = a exactly (and
+// -0.0 + 0.0 = +0.0 = numpy's copysign(0, b)).  The range check is an integer compare on the high word and conservative
+// (a high word equal to the limit's counts as out of range; the slow path is exact, so that only costs time).
+__device__ __forceinline__ double mod_two_pi_fast(double a, bool &bad) {
+  const bool neg = a < 0.0;
+  const double add = (a >= ISLS_TWO_PI) ? -ISLS_TWO_PI : (neg ? ISLS_TWO_PI : 0.0);
+  const int ha = __double2hiint(a) & 0x7fffffff;
+  bad |= ha >= (neg ? 0x401921fb : 0x402921fb);                  // high words of 2pi and 4pi
+  return a + add;
+}
+
 struct CarModel {
   static constexpr int n = 4, m = 2, NJ = 6, NJA = 6;
   __host__ __device__ static constexpr int am(int i, int j) {
@@ -113,6 +180,30 @@ struct CarModel {
     xn[1] = fma(dv, s, x[1]);
     xn[2] = mod_two_pi_core(fma(dv, u[0], x[2]), bad);
     xn[3] = fma(dt, u[1], x[3]);
+  }
+  // K candidate chains advanced together, stage by stage (see sincos_multi).  Precondition: every chain's heading
+  // is inside the fast sincos range - true at entry if fast_state() held for the initial state and afterwards by
+  // construction (the heading leaves mod_two_pi_fast in [0, 2pi) or the chain's flag is raised).
+  __device__ __forceinline__ static bool fast_state(const double (&x)[n]) { return sincos_fast_range(x[2]); }
+  template <int K>
+  __device__ __forceinline__ static void steps_fast(double (&x)[K][n], const double (&u)[K][m], double dt,
+                                                    bool (&bad)[K]) {
+    double th[K], s[K], c[K], dv[K];
+#pragma unroll
+    for (int q = 0; q < K; q++) th[q] = x[q][2];
+    sincos_multi<K, false>(th, s, c, bad);
+#pragma unroll
+    for (int q = 0; q < K; q++) dv[q] = dt * x[q][3];
+#pragma unroll
+    for (int q = 0; q < K; q++) th[q] = fma(dv[q], u[q][0], th[q]);
+#pragma unroll
+    for (int q = 0; q < K; q++) x[q][0] = fma(dv[q], c[q], x[q][0]);
+#pragma unroll
+    for (int q = 0; q < K; q++) x[q][1] = fma(dv[q], s[q], x[q][1]);
+#pragma unroll
+    for (int q = 0; q < K; q++) x[q][3] = fma(dt, u[q][1], x[q][3]);
+#pragma unroll
+    for (int q = 0; q < K; q++) x[q][2] = mod_two_pi_fast(th[q], bad[q]);
   }
   __device__ __forceinline__ static void step(const double (&x)[n], const double (&u)[m], double (&xn)[n],
                                               double dt) {
@@ -171,6 +262,29 @@ struct Arm3Model {
     xn[7] = (s1 + s2) + s3;
     xn[8] = 0.0;
   }
+  __device__ __forceinline__ static bool fast_state(const double (&)[n]) { return true; }
+  template <int K>
+  __device__ __forceinline__ static void steps_fast(double (&x)[K][n], const double (&u)[K][m], double dt,
+                                                    bool (&bad)[K]) {
+    double a[3 * K], s[3 * K], c[3 * K];
+    bool b3[3 * K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      double q[3];
+      qnext(x[k], u[k], q, dt);
+      a[3 * k] = q[0]; a[3 * k + 1] = q[0] + q[1]; a[3 * k + 2] = a[3 * k + 1] + q[2];
+#pragma unroll
+      for (int i = 0; i < 3; i++) { x[k][i] = q[i]; x[k][3 + i] = fma(u[k][i], dt, x[k][3 + i]); b3[3 * k + i] = false; }
+    }
+    sincos_multi<3 * K, true>(a, s, c, b3);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      x[k][6] = (c[3 * k] + c[3 * k + 1]) + c[3 * k + 2];
+      x[k][7] = (s[3 * k] + s[3 * k + 1]) + s[3 * k + 2];
+      x[k][8] = 0.0;
+      bad[k] |= b3[3 * k] | b3[3 * k + 1] | b3[3 * k + 2];
+    }
+  }
   __device__ __forceinline__ static void step(const double (&x)[n], const double (&u)[m], double (&xn)[n],
                                               double dt) {
     double q[3];
@@ -228,6 +342,18 @@ struct DoubleIntModel {
   }
   __device__ __forceinline__ static void step_fast(const double (&x)[n], const double (&u)[m], double (&xn)[n],
                                                    double dt, bool &) { step(x, u, xn, dt); }
+  __device__ __forceinline__ static bool fast_state(const double (&)[n]) { return true; }
+  template <int K>
+  __device__ __forceinline__ static void steps_fast(double (&x)[K][n], const double (&u)[K][m], double dt,
+                                                    bool (&)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      double xn[n];
+      step(x[k], u[k], xn, dt);
+#pragma unroll
+      for (int i = 0; i < n; i++) x[k][i] = xn[i];
+    }
+  }
   __device__ __forceinline__ static void jac(const double (&)[n], const double (&)[m], double (&)[1], double) {}
   __device__ __forceinline__ static void expand(const double (&)[1], double (&A)[n][n], double (&B)[n][m],
                                                 double dt) {

@@ -154,4 +154,56 @@ def make_model(name, **kw):
         return Car(**kw)
     if name == "arm3":
         return Arm3(**kw)
+    if name == "tassa_car":
+        return TassaCar(**kw)
     raise KeyError(name)
+
+
+# ------------------------------------------------------------------------------------------------- Tassa parking car
+class TassaCar:
+    """Car-parking model of Tassa et al. used by the reference's Tutorial (notebooks/Tutorial.ipynb cell 8):
+    state [x, y, car angle, front-wheel velocity], control [front-wheel angle, acceleration], axle distance 2.0.
+    The notebook differentiates it with autograd; get_AB below is the hand-derived Jacobian."""
+    name = "tassa_car"
+    n, m = 4, 2
+    dist = 2.0
+
+    def __init__(self, dt=0.03):
+        self.dt = dt
+
+    def f(self, s, u):
+        dt, d = self.dt, self.dist
+        w, a = u[..., 0], u[..., 1]
+        x, y, o, v = s[..., 0], s[..., 1], s[..., 2], s[..., 3]
+        f_ = dt * v
+        ins = d ** 2 - (np.sin(w) * f_) ** 2
+        b = f_ * np.cos(w) + d - np.sqrt(ins)
+        do = np.arcsin(np.sin(w) * f_ / d)
+        return np.stack([x + b * np.cos(o), y + b * np.sin(o), o + do, v + a * dt], axis=-1)
+
+    def get_AB(self, s, u):
+        dt, d = self.dt, self.dist
+        w = u[..., 0]
+        o, v = s[..., 2], s[..., 3]
+        f_ = dt * v
+        sw, cw = np.sin(w), np.cos(w)
+        S = np.sqrt(d ** 2 - (sw * f_) ** 2)
+        b = f_ * cw + d - S
+        db_dv = dt * (cw + sw * sw * f_ / S)
+        db_dw = -f_ * sw + sw * cw * f_ * f_ / S
+        lead = s.shape[:-1]
+        A = np.zeros(lead + (4, 4))
+        B = np.zeros(lead + (4, 2))
+        for i in range(4):
+            A[..., i, i] = 1.0
+        so, co = np.sin(o), np.cos(o)
+        A[..., 0, 2] = -b * so
+        A[..., 1, 2] = b * co
+        A[..., 0, 3] = db_dv * co
+        A[..., 1, 3] = db_dv * so
+        A[..., 2, 3] = dt * sw / S
+        B[..., 0, 0] = db_dw * co
+        B[..., 1, 0] = db_dw * so
+        B[..., 2, 0] = f_ * cw / S
+        B[..., 3, 1] = dt
+        return A, B
