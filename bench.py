@@ -287,7 +287,7 @@ def run_b200(a):
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=65,536 from the committed
                 # `ncu --set full` capture (profiles/r1_ncu_full_main_kernels.csv), scaled to this batch size
-                "traffic": round(755.0e6 * B / 65536.0), "traffic_source": "profiles/r1_ncu_full_main_kernels.csv",
+                "traffic": round(780.1e6 * B / 65536.0), "traffic_source": "profiles/r1_ncu_linesearch_staged.csv",
                 "two_phase": {"epilogue_bytes_per_launch": epi_bytes, "bound_ms": round(t_bound * 1e3, 4),
                               "measured_ms": round(ls_ms / ls_n, 4),
                               "frac": round(t_bound / (ls_ms / ls_n * 1e-3), 4)}}
@@ -300,6 +300,22 @@ def run_b200(a):
                                  "achieved": round(ff_bytes / (ff_ms / ff_n * 1e-3) / 1e9, 1), "peak": hbm_peak,
                                  "unit": "GB/s", "frac": round(ff_bytes / (ff_ms / ff_n * 1e-3) / 1e9 / hbm_peak, 4),
                                  "algorithmic_bytes_per_launch": ff_bytes, "traffic": round(2171.1e6 * B / 65536.0)}
+    if rank == 0 and roof is not None and "kpass" in prof:
+        # the Riccati K-pass named by BASELINE.json's metric: fused-model variant (Jacobians recomputed in-kernel), per
+        # problem-step x^, u^ in (6 doubles; the car never loads x, y) and K, Qux, packed Quu, Quu^-1 out (22 doubles)
+        # + the ADMM state reset (z_u read; lambda_u, reg_u written: 6 doubles) = 34 doubles; 723 flop.
+        kp_ms, kp_n = prof["kpass"]
+        kp_bytes = float(B) * p["N"] * 34 * 8
+        kp_flops = float(B) * (p["N"] - 1) * 723.0
+        t = kp_ms / kp_n * 1e-3
+        roof["riccati_kernel"] = {"kernel": "k_kpass<CarModel>", "bound": "hbm",
+                                  "achieved": round(kp_bytes / t / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": round(kp_bytes / t / 1e9 / hbm_peak, 4),
+                                  "algorithmic_bytes_per_launch": kp_bytes,
+                                  "fp64": {"algorithmic_flop_per_launch": kp_flops,
+                                           "achieved_tflops": round(kp_flops / t / 1e12, 3),
+                                           "frac_of_dfma_peak": round(kp_flops / t / 1e12 / fp64_peak, 4)},
+                                  "passes_per_s": round(B / t, 1)}
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:

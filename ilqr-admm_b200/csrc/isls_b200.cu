@@ -67,8 +67,11 @@ struct Dev {
   int tile0, tile1;      // tile range of this launch (chunked solves run disjoint ranges on separate streams)
   long long B;
   double dt, u_std;
+  double Rw[3];          // R = u_std * diag(Rw); Rw = 1 unless the plan carries Rdiag (exact for the scalar-R plans)
+  int cost_kind;         // ISLS_COST_*
   // plan constants (device)
-  const double *qd;      // [N][n]  Qdiag[seq[t]]
+  const double *qd;      // [N][n]  Qdiag[seq[t]] (pseudo-Huber: weights of term a)
+  const double *hp, *qd2, *hp2;   // [N][n] pseudo-Huber smoothness of term a, weights / smoothness of term b
   const int *seq;        // [N]
   const int *qnz;        // [N]  1 if Qdiag[seq[t]] has a non-zero
   const double *rho_x, *lo_x, *hi_x;   // [N][n]
@@ -116,18 +119,73 @@ struct TileCtx {
 template <class M>
 __device__ __forceinline__ void retire(const Dev &d, const TileCtx<M> &c, bool finished);
 
-// quadratic via-point state cost of one step: sum_i Qd[t][i] (x_i - z_i)^2   (sls_base.py:25-44)
+// State cost of one step.  Quadratic via-point cost sum_i Qd[t][i] (x_i - z_i)^2 (sls_base.py:25-44) or the
+// pseudo-Huber family of the Tutorial (notebooks/Tutorial.ipynb cell 14): sum_i w (sqrt(e^2 + p^2) - p), e = x_i - z_i,
+// with two (w, p) terms per component (running cost lx and final cost lf both act on x, y at the last step).
+__device__ __forceinline__ double huber_val(double e, double w, double p) { return w * (sqrt(fma(e, e, p * p)) - p); }
 template <class M>
 __device__ __forceinline__ double state_cost(const Dev &d, const double *zs, int t, const double (&x)[M::n]) {
   double c = 0.0;
   if (d.qnz[t]) {
     const int s = d.seq[t];
+    if (d.cost_kind == ISLS_COST_QUADRATIC) {
 #pragma unroll
-    for (int i = 0; i < M::n; i++) {
-      const double dx = x[i] - EL(zs, M::n, s, i);
-      c += (dx * dx) * d.qd[t * M::n + i];
+      for (int i = 0; i < M::n; i++) {
+        const double dx = x[i] - EL(zs, M::n, s, i);
+        c += (dx * dx) * d.qd[t * M::n + i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < M::n; i++) {
+        const double e = x[i] - EL(zs, M::n, s, i);
+        const double wa = d.qd[t * M::n + i], wb = d.qd2[t * M::n + i];
+        if (wa != 0.0) c += huber_val(e, wa, d.hp[t * M::n + i]);
+        if (wb != 0.0) c += huber_val(e, wb, d.hp2[t * M::n + i]);
+      }
     }
   }
+  return c;
+}
+// gradient g and Hessian diagonal h of the state cost at x (the reference's cts[:, :n] and diag(Cts[:, :n, :n]),
+// isls/isls.py:263-279): quadratic 2Q(x - z), 2Q; pseudo-Huber w e / s, w p^2 / s^3 with s = sqrt(e^2 + p^2).
+template <class M>
+__device__ __forceinline__ void state_grad_hess(const Dev &d, const double *zs, int t, const double (&x)[M::n],
+                                                double (&g)[M::n], double (&h)[M::n]) {
+#pragma unroll
+  for (int i = 0; i < M::n; i++) g[i] = h[i] = 0.0;
+  if (!d.qnz[t]) return;
+  const int s = d.seq[t];
+  if (d.cost_kind == ISLS_COST_QUADRATIC) {
+#pragma unroll
+    for (int i = 0; i < M::n; i++) {
+      const double q = d.qd[t * M::n + i];
+      g[i] = 2.0 * q * (x[i] - EL(zs, M::n, s, i));
+      h[i] = 2.0 * q;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < M::n; i++) {
+      const double e = x[i] - EL(zs, M::n, s, i);
+      const double wa = d.qd[t * M::n + i], wb = d.qd2[t * M::n + i];
+      if (wa != 0.0) {
+        const double pp = d.hp[t * M::n + i], sq = sqrt(fma(e, e, pp * pp));
+        g[i] += wa * e / sq;
+        h[i] += wa * (pp * pp) / (sq * sq * sq);
+      }
+      if (wb != 0.0) {
+        const double pp = d.hp2[t * M::n + i], sq = sqrt(fma(e, e, pp * pp));
+        g[i] += wb * e / sq;
+        h[i] += wb * (pp * pp) / (sq * sq * sq);
+      }
+    }
+  }
+}
+// control cost u'Ru / u_std = sum_j Rw_j u_j^2 (Rw = 1: the multiplication is exact)
+template <class M>
+__device__ __forceinline__ double ctrl_sq(const Dev &d, const double (&u)[M::m]) {
+  double c = 0.0;
+#pragma unroll
+  for (int j = 0; j < M::m; j++) c += (d.Rw[j] * u[j]) * u[j];
   return c;
 }
 
@@ -160,8 +218,8 @@ __global__ void k_init(Dev d, const double *x0, const double *u_init, const doub
       EL(uh, M::m, t, j) = u[j];
       EL(zu, M::m, t, j) = 0.0;
       EL(lu, M::m, t, j) = 0.0;
-      cc += u[j] * u[j];
     }
+    cc += ctrl_sq<M>(d, u);
 #pragma unroll
     for (int i = 0; i < M::n; i++) {
       EL(xh, M::n, t, i) = x[i];
@@ -336,6 +394,7 @@ __global__ void k_kpass(Dev d) {
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b]) return;
   const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m);
+  const double *zs = d.zs + (size_t)tile * d.n_via * n * TILE + c.lane;
   double *Kg = c.at(d.Kg, d, m * n), *Qx = c.at(d.Qux, d, m * n);
   double *Qu = c.at(d.Quu, d, nt), *Qi = c.at(d.Qui, d, nt);
   double A[n][n], Bm[n][m], V[n][n];
@@ -344,7 +403,15 @@ __global__ void k_kpass(Dev d) {
   for (int i = 0; i < n; i++)
 #pragma unroll
     for (int j = 0; j < n; j++)
-      V[i][j] = (i == j) ? 2.0 * (d.qd[(d.N - 1) * n + i] + d.rho_x[(d.N - 1) * n + i]) : 0.0;   // isls.py:257
+      V[i][j] = 0.0;
+  {
+    double xl[n], gl[n], hl[n];
+#pragma unroll
+    for (int i = 0; i < n; i++) xl[i] = (d.cost_kind != ISLS_COST_QUADRATIC) ? EL(xh, n, d.N - 1, i) : 0.0;
+    state_grad_hess<M>(d, zs, d.N - 1, xl, gl, hl);
+#pragma unroll
+    for (int i = 0; i < n; i++) V[i][i] = hl[i] + 2.0 * d.rho_x[(d.N - 1) * n + i];              // isls.py:257
+  }
   bool ok = true;
   double xn_[n], un_[m];                   // operands of the next step, loaded while this step's Riccati update runs
 #pragma unroll
@@ -366,10 +433,17 @@ __global__ void k_kpass(Dev d) {
     M::jac(x, u, J, d.dt);
     M::expand(J, A, Bm, d.dt);
     double dxx[n], duu[m], K[m][n], Qux[m][n], Quu[m][m], Qui[m][m];
+    if (d.cost_kind == ISLS_COST_QUADRATIC) {
 #pragma unroll
-    for (int i = 0; i < n; i++) dxx[i] = 2.0 * (d.qd[t * n + i] + d.rho_x[t * n + i]);
+      for (int i = 0; i < n; i++) dxx[i] = 2.0 * (d.qd[t * n + i] + d.rho_x[t * n + i]);
+    } else {
+      double gt[n], ht[n];
+      state_grad_hess<M>(d, zs, t, x, gt, ht);
 #pragma unroll
-    for (int j = 0; j < m; j++) duu[j] = 2.0 * (d.u_std + d.rho_u[t * m + j]);
+      for (int i = 0; i < n; i++) dxx[i] = ht[i] + 2.0 * d.rho_x[t * n + i];
+    }
+#pragma unroll
+    for (int j = 0; j < m; j++) duu[j] = 2.0 * (d.u_std * d.Rw[j] + d.rho_u[t * m + j]);
     ok &= riccati_step<M>(A, Bm, dxx, duu, V, K, Qux, Quu, Qui);
 #pragma unroll
     for (int a = 0; a < m; a++) {
@@ -445,17 +519,21 @@ __device__ __forceinline__ void ff_body(const Dev &d, const TileCtx<M> &c) {
   init_AB<M>(A, Bm);
   double v[n];
   auto costgrad = [&](int t, const double (&x)[n], const double (&u)[m], double (&cx)[n], double (&cu)[m]) {
-    const int s = d.seq[t];
+    if (d.cost_kind == ISLS_COST_QUADRATIC) {
+      const int s = d.seq[t];
+#pragma unroll
+      for (int i = 0; i < n; i++) cx[i] = d.qnz[t] ? 2.0 * d.qd[t * n + i] * (x[i] - EL(zs, n, s, i)) : 0.0;
+    } else {
+      double ht[n];
+      state_grad_hess<M>(d, zs, t, x, cx, ht);
+    }
 #pragma unroll
     for (int i = 0; i < n; i++) {
-      double g = 0.0;
-      if (d.qnz[t]) g = 2.0 * d.qd[t * n + i] * (x[i] - EL(zs, n, s, i));
-      if (d.proj_x) g += 2.0 * d.rho_x[t * n + i] * (x[i] - EL(rgx, n, t, i));
-      cx[i] = g;
+      if (d.proj_x) cx[i] += 2.0 * d.rho_x[t * n + i] * (x[i] - EL(rgx, n, t, i));
     }
 #pragma unroll
     for (int j = 0; j < m; j++) {
-      double g = 2.0 * d.u_std * u[j];
+      double g = 2.0 * (d.u_std * d.Rw[j]) * u[j];
       if (d.proj_u) g += 2.0 * d.rho_u[t * m + j] * (u[j] - EL(rgu, m, t, j));
       cu[j] = g;
     }
@@ -472,7 +550,7 @@ __device__ __forceinline__ void ff_body(const Dev &d, const TileCtx<M> &c) {
 #pragma unroll
     for (int j = 0; j < m; j++) {
       // batch-form last control: du_{N-1} = -Cuu^-1 cu (isls.py:441-465, Su's last block column is zero)
-      const double cuu = 2.0 * (d.u_std + d.rho_u[(d.N - 1) * m + j]);
+      const double cuu = 2.0 * (d.u_std * d.Rw[j] + d.rho_u[(d.N - 1) * m + j]);
       EL(kk, m, d.N - 1, j) = d.last_stage_dp ? 0.0 : -cu[j] / cuu;
     }
   }
@@ -529,9 +607,9 @@ __device__ __forceinline__ void ff_body(const Dev &d, const TileCtx<M> &c) {
       }
       duv[a] = acc + kv[a];
       EL(du, m, t, a) = duv[a];
-      r0 = fma(u[a], u[a], r0);                 // R-only part (scaled by u_std after the loop)
-      r1 = fma(u[a], duv[a], r1);
-      r2 = fma(duv[a], duv[a], r2);
+      r0 = fma(d.Rw[a] * u[a], u[a], r0);       // R-only part (scaled by u_std after the loop)
+      r1 = fma(d.Rw[a] * u[a], duv[a], r1);
+      r2 = fma(d.Rw[a] * duv[a], duv[a], r2);
       if (d.proj_u) {                           // ADMM penalty part
         const double rho = d.rho_u[t * m + a], e = u[a] - ru[a];
         c0 = fma(rho * e, e, c0);
@@ -606,17 +684,21 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
   double v[n];
   auto costgrad = [&](int t, const double (&x)[n], const double (&u)[m], const double (&rx)[n],
                       const double (&ru)[m], double (&cx)[n], double (&cu)[m]) {
-    const int s = d.seq[t];
+    if (d.cost_kind == ISLS_COST_QUADRATIC) {
+      const int s = d.seq[t];
+#pragma unroll
+      for (int i = 0; i < n; i++) cx[i] = d.qnz[t] ? 2.0 * d.qd[t * n + i] * (x[i] - EL(zs, n, s, i)) : 0.0;
+    } else {
+      double ht[n];
+      state_grad_hess<M>(d, zs, t, x, cx, ht);
+    }
 #pragma unroll
     for (int i = 0; i < n; i++) {
-      double g = 0.0;
-      if (d.qnz[t]) g = 2.0 * d.qd[t * n + i] * (x[i] - EL(zs, n, s, i));
-      if (d.proj_x) g += 2.0 * d.rho_x[t * n + i] * (x[i] - rx[i]);
-      cx[i] = g;
+      if (d.proj_x) cx[i] += 2.0 * d.rho_x[t * n + i] * (x[i] - rx[i]);
     }
 #pragma unroll
     for (int j = 0; j < m; j++) {
-      double g = 2.0 * d.u_std * u[j];
+      double g = 2.0 * (d.u_std * d.Rw[j]) * u[j];
       if (d.proj_u) g += 2.0 * d.rho_u[t * m + j] * (u[j] - ru[j]);
       cu[j] = g;
     }
@@ -654,7 +736,7 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
     for (int i = 0; i < n; i++) v[i] = cx[i];
 #pragma unroll
     for (int j = 0; j < m; j++) {
-      const double cuu = 2.0 * (d.u_std + d.rho_u[(N - 1) * m + j]);
+      const double cuu = 2.0 * (d.u_std * d.Rw[j] + d.rho_u[(N - 1) * m + j]);
       EL(kk, m, N - 1, j) = d.last_stage_dp ? 0.0 : -cu[j] / cuu;
     }
   }
@@ -763,9 +845,9 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
       }
       duv[a] = acc + kv[a];
       EL(du, m, t, a) = duv[a];
-      r0 = fma(u[a], u[a], r0);
-      r1 = fma(u[a], duv[a], r1);
-      r2 = fma(duv[a], duv[a], r2);
+      r0 = fma(d.Rw[a] * u[a], u[a], r0);
+      r1 = fma(d.Rw[a] * u[a], duv[a], r1);
+      r2 = fma(d.Rw[a] * duv[a], duv[a], r2);
       if (d.proj_u) {
         const double rho = d.rho_u[t * m + a], e = u[a] - ru[a];
         c0 = fma(rho * e, e, c0);
@@ -840,7 +922,7 @@ __device__ __forceinline__ void admm_finish(const Dev &d, const TileCtx<M> &c, i
 // chunks of its per-step operands (u^, du, reg_x of the tile: contiguous in the tile-blocked layout) in shared memory
 // while the FP64 chains run.  (A register software prefetch did not survive ptxas: it sank the copy of the prefetched
 // registers to right behind the loads, exposing the full memory latency every step - 22 % of all stall samples sat
-// on that one MOV, profiles/r2_linesearch_schedule.md.)
+// on that one MOV, profiles/r1_linesearch_schedule.md.)
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -951,10 +1033,15 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
           const int s = d.seq[t];
 #pragma unroll
           for (int i = 0; i < n; i++) { zv[i] = EL(zs, n, s, i); qd[i] = d.qd[t * n + i]; }
+          if (d.cost_kind == ISLS_COST_QUADRATIC) {
 #pragma unroll
-          for (int q = 0; q < CPT; q++)
+            for (int q = 0; q < CPT; q++)
 #pragma unroll
-            for (int i = 0; i < n; i++) { const double e = x[q][i] - zv[i]; cs[q] += (e * e) * qd[i]; }
+              for (int i = 0; i < n; i++) { const double e = x[q][i] - zv[i]; cs[q] += (e * e) * qd[i]; }
+          } else {
+#pragma unroll
+            for (int q = 0; q < CPT; q++) cs[q] += state_cost<M>(d, zs, t, x[q]);
+          }
         }
         if (PX) {
 #pragma unroll
@@ -1004,6 +1091,7 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
       const int l = w * CPT + q;
       if (l < d.L && !skip) {
         double tot = cs[q] + fma(al[q], fma(al[q], c2, c1), c0);   // cost_function + control penalty (isls.py:470,476)
+        if (d.cost_kind != ISLS_COST_QUADRATIC && tot != tot) tot = 1e6;   // Tutorial cell 14: cost closure, NaN -> 1e6
         if (PX) tot += px[q];                                      // isls.py:473
         sc[l][c.lane] = tot;
         scs[l][c.lane] = cs[q];
@@ -1116,9 +1204,9 @@ __device__ __forceinline__ void admm_body(const Dev &d, const TileCtx<M> &c, int
 #pragma unroll
       for (int i = 0; i < n; i++) { zxv[i] = EL(zx, n, t, i); lxv[i] = EL(lx, n, t, i); lox[i] = d.lo_x[t * n + i]; hix[i] = d.hi_x[t * n + i]; }
     }
+    cc += ctrl_sq<M>(d, u);
 #pragma unroll
     for (int j = 0; j < m; j++) {
-      cc += u[j] * u[j];
       if (d.proj_u) {
         int mk;
         admm_elem(u[j], d.relax, lou[j], hiu[j], zuv[j], luv[j], pru, dru, mk);
@@ -1392,12 +1480,15 @@ __global__ void k_backward_full(Dev d) {
   double A[n][n], Bm[n][m], V[n][n], v[n];
   init_AB<M>(A, Bm);
   {
-    const int t = d.N - 1, s = d.seq[t];
+    const int t = d.N - 1;
+    double xl[n], hl[n];
+#pragma unroll
+    for (int i = 0; i < n; i++) xl[i] = EL(xh, n, t, i);
+    state_grad_hess<M>(d, zs, t, xl, v, hl);                                                       // isls.py:252 / 258
 #pragma unroll
     for (int i = 0; i < n; i++) {
 #pragma unroll
-      for (int j = 0; j < n; j++) V[i][j] = (i == j) ? 2.0 * d.qd[t * n + i] : 0.0;               // isls.py:251
-      v[i] = 2.0 * d.qd[t * n + i] * (EL(xh, n, t, i) - EL(zs, n, s, i));                          // isls.py:252
+      for (int j = 0; j < n; j++) V[i][j] = (i == j) ? hl[i] : 0.0;                                // isls.py:251 / 257
     }
 #pragma unroll
     for (int q = 0; q < m * n; q++) EL(Kg, m * n, t, q) = 0.0;
@@ -1407,18 +1498,14 @@ __global__ void k_backward_full(Dev d) {
   bool ok = true;
   for (int t = d.N - 2; t >= 0; t--) {
     double x[n], u[m], J[M::NJA], dxx[n], duu[m], cx[n], cu[m], K[m][n], Qux[m][n], Quu[m][m], Qui[m][m], kt[m];
-    const int s = d.seq[t];
 #pragma unroll
-    for (int i = 0; i < n; i++) {
-      x[i] = EL(xh, n, t, i);
-      dxx[i] = 2.0 * d.qd[t * n + i];
-      cx[i] = d.qnz[t] ? 2.0 * d.qd[t * n + i] * (x[i] - EL(zs, n, s, i)) : 0.0;
-    }
+    for (int i = 0; i < n; i++) x[i] = EL(xh, n, t, i);
+    state_grad_hess<M>(d, zs, t, x, cx, dxx);
 #pragma unroll
     for (int j = 0; j < m; j++) {
       u[j] = EL(uh, m, t, j);
-      duu[j] = 2.0 * d.u_std;
-      cu[j] = 2.0 * d.u_std * u[j];
+      duu[j] = 2.0 * (d.u_std * d.Rw[j]);
+      cu[j] = 2.0 * (d.u_std * d.Rw[j]) * u[j];
     }
     M::jac(x, u, J, d.dt);
     M::expand(J, A, Bm, d.dt);
@@ -1493,11 +1580,13 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch_closed(Dev d) 
 #pragma unroll
           for (int i = 0; i < n; i++) acc = fma(K[j][i], x[q][i] - xn0[i], acc);
           u[j] = (acc + al[q] * kt[j]) + un[j];                       // isls.py:329
-          cc[q] += u[j] * u[j];
+          cc[q] += (d.Rw[j] * u[j]) * u[j];
         }
         if (qz) {
+          if (d.cost_kind == ISLS_COST_QUADRATIC) {
 #pragma unroll
-          for (int i = 0; i < n; i++) { const double e = x[q][i] - zv[i]; cs[q] += (e * e) * qd[i]; }
+            for (int i = 0; i < n; i++) { const double e = x[q][i] - zv[i]; cs[q] += (e * e) * qd[i]; }
+          } else cs[q] += state_cost<M>(d, zs, t, x[q]);
         }
         M::step(x[q], u, xn, d.dt);
 #pragma unroll
@@ -1509,7 +1598,12 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch_closed(Dev d) 
       const int l = w * CPT + q;
       if (l < d.L) {
         double tot = cs[q] + d.u_std * cc[q];
-        if (tot != tot) { tot = 1e5; d.status[c.b] |= ISLS_ST_NAN_COST; }   // isls.py:362 (benign race: same bit)
+        if (tot != tot) {
+          // isls.py:362 (benign race: same bit).  The Tutorial's cost closure maps NaN to 1e6 itself (cell 14), so
+          // with that cost the solver never sees a NaN and no flag is raised.
+          if (d.cost_kind == ISLS_COST_QUADRATIC) { tot = 1e5; d.status[c.b] |= ISLS_ST_NAN_COST; }
+          else tot = 1e6;
+        }
         sc[l][c.lane] = tot;
       }
     }
@@ -1555,7 +1649,7 @@ __global__ void k_accept_closed(Dev d, int it) {
 #pragma unroll
         for (int i = 0; i < n; i++) acc = fma(EL(Kg, m * n, t, j * n + i), x[i] - EL(xh, n, t, i), acc);
         u[j] = (acc + al * EL(kk, m, t, j)) + EL(uh, m, t, j);
-        cc += u[j] * u[j];
+        cc += (d.Rw[j] * u[j]) * u[j];
       }
 #pragma unroll
       for (int j = 0; j < m; j++) EL(uh, m, t, j) = u[j];
@@ -1613,9 +1707,9 @@ __global__ void k_pack_stage(Dev d, const double *x_nom, const double *u_nom, co
   for (int t = 0; t < d.N; t++)
     for (int j = 0; j < m; j++) {
       const double u = EL(uh, m, t, j), dv = EL(du, m, t, j);
-      r0 = fma(u, u, r0);
-      r1 = fma(u, dv, r1);
-      r2 = fma(dv, dv, r2);
+      r0 = fma(d.Rw[j] * u, u, r0);
+      r1 = fma(d.Rw[j] * u, dv, r1);
+      r2 = fma(d.Rw[j] * dv, dv, r2);
       if (d.proj_u) {
         const double rho = d.rho_u[t * m + j], e = u - EL(rgu, m, t, j);
         c0 = fma(rho * e, e, c0);
@@ -1864,7 +1958,7 @@ __global__ void k_lqt_admm(Dev d, const double *x0_in) {
         for (int i = 0; i < n; i++) acc = fma(Kt[j][i], x[i], acc);
         u[j] = acc + kv[j];
         EL(ua, m, t, j) = u[j];
-        cc += u[j] * u[j];
+        cc += (d.Rw[j] * u[j]) * u[j];
         if (d.proj_u) {
           int mk;
           admm_elem(u[j], d.relax, d.lo_u[t * m + j], d.hi_u[t * m + j], zuv[j], luv[j], pru, dru, mk);
@@ -1960,6 +2054,7 @@ static int model_dims(int model_id, int n, int m, int *NJA) {
   switch (model_id) {
     case ISLS_MODEL_CAR: if (n == 4 && m == 2) { *NJA = 6; return 0; } break;
     case ISLS_MODEL_ARM3: if (n == 9 && m == 3) { *NJA = 6; return 0; } break;
+    case ISLS_MODEL_TASSA_CAR: if (n == 4 && m == 2) { *NJA = 8; return 0; } break;
     case ISLS_MODEL_DOUBLE_INTEGRATOR:
       if ((n == 2 && m == 1) || (n == 4 && m == 2) || (n == 6 && m == 3)) { *NJA = 1; return 0; }
       break;
@@ -1973,6 +2068,7 @@ static int dispatch_model(const isls_plan *p, F &&f) {
     case ISLS_MODEL_CAR: return f(CarModel{});
 #ifndef ISLS_DEV_ONLY_CAR               // development builds (SASS inspection) instantiate one model only
     case ISLS_MODEL_ARM3: return f(Arm3Model{});
+    case ISLS_MODEL_TASSA_CAR: return f(TassaCarModel{});
     case ISLS_MODEL_DOUBLE_INTEGRATOR:
       if (p->m == 1) return f(DoubleIntModel<1>{});
       if (p->m == 2) return f(DoubleIntModel<2>{});
@@ -1990,6 +2086,7 @@ extern "C" int isls_model_id(const char *name) {
   if (!strcmp(name, "double_integrator")) return ISLS_MODEL_DOUBLE_INTEGRATOR;
   if (!strcmp(name, "car")) return ISLS_MODEL_CAR;
   if (!strcmp(name, "arm3")) return ISLS_MODEL_ARM3;
+  if (!strcmp(name, "tassa_car")) return ISLS_MODEL_TASSA_CAR;
   return fail(ISLS_E_UNSUPPORTED, std::string("unknown model: ") + name);
 }
 
@@ -2025,14 +2122,21 @@ extern "C" int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan)
     while (h.size() % 32) h.push_back(0.0);
     return off;
   };
-  std::vector<double> qd((size_t)N * n);
+  const bool huber = desc->cost_kind == ISLS_COST_PSEUDO_HUBER;
+  if (desc->cost_kind != ISLS_COST_QUADRATIC && !huber) { delete p; return fail(ISLS_E_UNSUPPORTED, "unknown cost_kind"); }
+  if (huber && !desc->Hp) { delete p; return fail(ISLS_E_INVALID, "pseudo-Huber cost needs Hp"); }
+  if (desc->Qdiag_b && (!huber || !desc->Hp_b)) { delete p; return fail(ISLS_E_INVALID, "Qdiag_b needs the pseudo-Huber cost and Hp_b"); }
+  std::vector<double> qd((size_t)N * n), hp((size_t)N * n, 1.0), qd2((size_t)N * n, 0.0), hp2((size_t)N * n, 1.0);
   std::vector<int> qnz(N), seq(N);
   for (int t = 0; t < N; t++) {
     seq[t] = desc->seq[t];
     int nz = 0;
     for (int i = 0; i < n; i++) {
-      qd[(size_t)t * n + i] = desc->Qdiag[(size_t)seq[t] * n + i];
-      nz |= qd[(size_t)t * n + i] != 0.0;
+      const size_t q = (size_t)t * n + i, v = (size_t)seq[t] * n + i;
+      qd[q] = desc->Qdiag[v];
+      if (huber) hp[q] = desc->Hp[v];
+      if (desc->Qdiag_b) { qd2[q] = desc->Qdiag_b[v]; hp2[q] = desc->Hp_b[v]; }
+      nz |= qd[q] != 0.0 || qd2[q] != 0.0;
     }
     qnz[t] = nz;
   }
@@ -2041,6 +2145,8 @@ extern "C" int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan)
          o_lx = push(desc->lo_x, (size_t)N * n, -inf), o_hx = push(desc->hi_x, (size_t)N * n, inf),
          o_ru = push(desc->rho_u, (size_t)N * m, 0.0), o_lu = push(desc->lo_u, (size_t)N * m, -inf),
          o_hu = push(desc->hi_u, (size_t)N * m, inf), o_al = push(desc->alphas, desc->L, 0.0);
+  size_t o_hp = 0, o_q2 = 0, o_h2 = 0;
+  if (huber) { o_hp = push(hp.data(), (size_t)N * n, 1.0); o_q2 = push(qd2.data(), (size_t)N * n, 0.0); o_h2 = push(hp2.data(), (size_t)N * n, 1.0); }
   size_t dbytes = h.size() * sizeof(double), ibytes = al256(2 * (size_t)N * sizeof(int));
   cudaError_t e = cudaMalloc(&p->cblock, dbytes + ibytes);
   if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(plan constants)"); }
@@ -2055,6 +2161,14 @@ extern "C" int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan)
   memset(&d, 0, sizeof(d));
   d.N = N; d.n_via = desc->n_via; d.L = desc->L; d.proj_x = p->proj_x; d.proj_u = p->proj_u;
   d.dt = desc->dt; d.u_std = desc->u_std;
+  d.cost_kind = desc->cost_kind;
+  for (int j = 0; j < 3; j++) d.Rw[j] = 1.0;
+  if (desc->Rdiag) {                                 // R = diag(Rdiag) = u_std * diag(Rw) with u_std := Rdiag[0]
+    if (!(desc->Rdiag[0] > 0.0)) { cudaFree(p->cblock); delete p; return fail(ISLS_E_INVALID, "Rdiag[0] must be > 0"); }
+    d.u_std = desc->Rdiag[0];
+    for (int j = 0; j < m; j++) d.Rw[j] = desc->Rdiag[j] / desc->Rdiag[0];
+  }
+  if (huber) { d.hp = cb + o_hp; d.qd2 = cb + o_q2; d.hp2 = cb + o_h2; }
   d.qd = cb + o_qd; d.rho_x = cb + o_rx; d.lo_x = cb + o_lx; d.hi_x = cb + o_hx;
   d.rho_u = cb + o_ru; d.lo_u = cb + o_lu; d.hi_u = cb + o_hu; d.alphas = cb + o_al;
   d.seq = ib; d.qnz = ib + N;
@@ -2366,6 +2480,8 @@ extern "C" int isls_lqt_admm_dp_f64(const isls_plan *plan, const isls_solve_opts
   if (!opts || !out || !x0 || !zs) return fail(ISLS_E_INVALID, "NULL argument");
   if (plan && plan->desc.model_id != ISLS_MODEL_DOUBLE_INTEGRATOR)
     return fail(ISLS_E_UNSUPPORTED, "LQT-ADMM needs a linear model (double_integrator)");
+  if (plan && plan->desc.cost_kind != ISLS_COST_QUADRATIC)
+    return fail(ISLS_E_UNSUPPORTED, "LQT-ADMM needs the quadratic via-point cost");
   if (opts->max_admm < 1) return fail(ISLS_E_INVALID, "max_admm must be >= 1");
   Dev d;
   isls_solve_opts o = *opts;

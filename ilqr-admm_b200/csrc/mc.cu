@@ -111,6 +111,7 @@ extern "C" int isls_mc_rollout_f64(int32_t model_id, int32_t n, int32_t m, int32
                                                           noise_scale, seed, x_out_dev, u_out_dev)
   if (model_id == ISLS_MODEL_CAR) GO(CarModel);
   else if (model_id == ISLS_MODEL_ARM3) GO(Arm3Model);
+  else if (model_id == ISLS_MODEL_TASSA_CAR) GO(TassaCarModel);
   else if (m == 1) GO(DoubleIntModel<1>);
   else if (m == 2) GO(DoubleIntModel<2>);
   else GO(DoubleIntModel<3>);

@@ -16,6 +16,7 @@
 //   arm3  notebooks/3DoF robot/State and control bound constraints.ipynb cells 9-10, closed-form planar 3R
 //         FK / Jacobian for urdfs/3dof_robot.urdf:73-102 (unit links)
 //   double integrator   isls/utils.py:266-276, isls/sls_base.py:49-53
+//   tassa_car   notebooks/Tutorial.ipynb cell 8
 #pragma once
 
 enum { MZ = 0, MO = 1, MV = 2 };
@@ -170,17 +171,6 @@ struct CarModel {
   __host__ __device__ static constexpr int bm(int i, int j) {
     return ((i == 2 && j == 0) || (i == 3 && j == 1)) ? MV : MZ;
   }
-  // branch-free step; `bad` is OR-ed when an argument left the fast range (then xn is invalid: redo with step())
-  __device__ __forceinline__ static void step_fast(const double (&x)[n], const double (&u)[m], double (&xn)[n],
-                                                   double dt, bool &bad) {
-    double s, c;
-    sincos_core(x[2], &s, &c, bad);
-    const double dv = dt * x[3];
-    xn[0] = fma(dv, c, x[0]);
-    xn[1] = fma(dv, s, x[1]);
-    xn[2] = mod_two_pi_core(fma(dv, u[0], x[2]), bad);
-    xn[3] = fma(dt, u[1], x[3]);
-  }
   // K candidate chains advanced together, stage by stage (see sincos_multi).  Precondition: every chain's heading
   // is inside the fast sincos range - true at entry if fast_state() held for the initial state and afterwards by
   // construction (the heading leaves mod_two_pi_fast in [0, 2pi) or the chain's flag is raised).
@@ -234,6 +224,74 @@ struct CarModel {
   }
 };
 
+// Car-parking model of Tassa et al. as written in the reference's Tutorial (notebooks/Tutorial.ipynb cell 8):
+// state [x, y, car angle o, front-wheel velocity v], control [front-wheel angle w, acceleration a], axle distance 2.
+//   f = dt v;  S = sqrt(d^2 - (sin w f)^2);  b = f cos w + d - S;  do = asin(sin w f / d)
+//   x+ = x + b cos o;  y+ = y + b sin o;  o+ = o + do;  v+ = v + a dt
+// The notebook differentiates it with autograd (cell 10); the Jacobian here is the closed form:
+//   db/dv = dt (cos w + sin^2 w f / S),  db/dw = -f sin w + sin w cos w f^2 / S,  d(do)/dv = dt sin w / S,
+//   d(do)/dw = f cos w / S.
+struct TassaCarModel {
+  static constexpr int n = 4, m = 2, NJ = 8, NJA = 8;
+  static constexpr double DIST = 2.0;
+  __host__ __device__ static constexpr int am(int i, int j) {
+    return i == j ? MO : ((i <= 1 && j >= 2) || (i == 2 && j == 3)) ? MV : MZ;
+  }
+  __host__ __device__ static constexpr int bm(int i, int j) {
+    return ((i <= 2 && j == 0) || (i == 3 && j == 1)) ? MV : MZ;
+  }
+  __device__ __forceinline__ static void step(const double (&x)[n], const double (&u)[m], double (&xn)[n],
+                                              double dt) {
+    double sw, cw, so, co;
+    sincos_pio2(u[0], &sw, &cw);
+    sincos_pio2(x[2], &so, &co);
+    const double f = dt * x[3];
+    const double sf = sw * f;
+    const double S = sqrt(DIST * DIST - sf * sf);
+    const double b = (f * cw + DIST) - S;
+    xn[0] = x[0] + b * co;
+    xn[1] = x[1] + b * so;
+    xn[2] = x[2] + asin(sf / DIST);
+    xn[3] = x[3] + u[1] * dt;
+  }
+  __device__ __forceinline__ static bool fast_state(const double (&)[n]) { return true; }
+  template <int K>
+  __device__ __forceinline__ static void steps_fast(double (&x)[K][n], const double (&u)[K][m], double dt,
+                                                    bool (&)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      double xn[n];
+      step(x[k], u[k], xn, dt);
+#pragma unroll
+      for (int i = 0; i < n; i++) x[k][i] = xn[i];
+    }
+  }
+  __device__ __forceinline__ static void jac(const double (&x)[n], const double (&u)[m], double (&J)[NJ],
+                                             double dt) {
+    double sw, cw, so, co;
+    sincos_pio2(u[0], &sw, &cw);
+    sincos_pio2(x[2], &so, &co);
+    const double f = dt * x[3];
+    const double S = sqrt(DIST * DIST - (sw * f) * (sw * f));
+    const double b = (f * cw + DIST) - S;
+    const double db_dv = dt * (cw + sw * sw * f / S);
+    const double db_dw = -f * sw + sw * cw * f * f / S;
+    J[0] = -b * so;          // A[0][2]
+    J[1] = b * co;           // A[1][2]
+    J[2] = db_dv * co;       // A[0][3]
+    J[3] = db_dv * so;       // A[1][3]
+    J[4] = dt * sw / S;      // A[2][3]
+    J[5] = db_dw * co;       // B[0][0]
+    J[6] = db_dw * so;       // B[1][0]
+    J[7] = f * cw / S;       // B[2][0]
+  }
+  __device__ __forceinline__ static void expand(const double (&J)[NJ], double (&A)[n][n], double (&B)[n][m],
+                                                double dt) {
+    A[0][2] = J[0]; A[1][2] = J[1]; A[0][3] = J[2]; A[1][3] = J[3]; A[2][3] = J[4];
+    B[0][0] = J[5]; B[1][0] = J[6]; B[2][0] = J[7]; B[3][1] = dt;
+  }
+};
+
 struct Arm3Model {
   static constexpr int n = 9, m = 3, NJ = 6, NJA = 6;
   __host__ __device__ static constexpr int am(int i, int j) {
@@ -248,19 +306,6 @@ struct Arm3Model {
     const double h = dt * dt;
 #pragma unroll
     for (int i = 0; i < 3; i++) q[i] = fma(0.5 * u[i], h, fma(x[3 + i], dt, x[i]));
-  }
-  __device__ __forceinline__ static void step_fast(const double (&x)[n], const double (&u)[m], double (&xn)[n],
-                                                   double dt, bool &bad) {
-    double q[3];
-    qnext(x, u, q, dt);
-    const double a1 = q[0], a2 = a1 + q[1], a3 = a2 + q[2];
-    double s1, c1, s2, c2, s3, c3;
-    sincos_core(a1, &s1, &c1, bad); sincos_core(a2, &s2, &c2, bad); sincos_core(a3, &s3, &c3, bad);
-#pragma unroll
-    for (int i = 0; i < 3; i++) { xn[i] = q[i]; xn[3 + i] = fma(u[i], dt, x[3 + i]); }
-    xn[6] = (c1 + c2) + c3;
-    xn[7] = (s1 + s2) + s3;
-    xn[8] = 0.0;
   }
   __device__ __forceinline__ static bool fast_state(const double (&)[n]) { return true; }
   template <int K>
@@ -340,8 +385,6 @@ struct DoubleIntModel {
       xn[D + i] = x[D + i] + dt * u[i];
     }
   }
-  __device__ __forceinline__ static void step_fast(const double (&x)[n], const double (&u)[m], double (&xn)[n],
-                                                   double dt, bool &) { step(x, u, xn, dt); }
   __device__ __forceinline__ static bool fast_state(const double (&)[n]) { return true; }
   template <int K>
   __device__ __forceinline__ static void steps_fast(double (&x)[K][n], const double (&u)[K][m], double dt,

@@ -17,7 +17,9 @@ class ProblemDesc(C.Structure):
                 ("n_via", C.c_int32), ("L", C.c_int32), ("dt", C.c_double), ("u_std", C.c_double),
                 ("Qdiag", C.c_void_p), ("seq", C.c_void_p), ("alphas", C.c_void_p),
                 ("rho_x", C.c_void_p), ("lo_x", C.c_void_p), ("hi_x", C.c_void_p),
-                ("rho_u", C.c_void_p), ("lo_u", C.c_void_p), ("hi_u", C.c_void_p)]
+                ("rho_u", C.c_void_p), ("lo_u", C.c_void_p), ("hi_u", C.c_void_p),
+                ("cost_kind", C.c_int32), ("Rdiag", C.c_void_p), ("Hp", C.c_void_p), ("Qdiag_b", C.c_void_p),
+                ("Hp_b", C.c_void_p)]
 
 
 class SolveOpts(C.Structure):

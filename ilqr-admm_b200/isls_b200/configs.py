@@ -104,3 +104,29 @@ def subset(p, idx):
     q = dict(p)
     q["x0"] = p["x0"][idx].copy()
     return q
+
+
+def tassa_batch(B, N=150, dt=0.03, seed=_seed(6), I_o=50, I_a=5, L=40, tol=1e-3):
+    """Tutorial problem (notebooks/Tutorial.ipynb cells 4-27): car parking of Tassa et al. with the pseudo-Huber cost
+    (cell 14: cu = 1e-2*(1, .01), running cx = 1e-3*(1,1) with px = (.1,.1) on (x, y), final cf = (.1,.1,1,.3) with
+    pf = (.01,.01,.01,1)), control limits |w| <= 0.5, |a| <= 2 (cell 25), rho_u = diag(1e-1, 1e-2), 5 ADMM
+    iterations, 40 line-search candidates (cell 27).  The notebook uses N = 500 (15 s); the initial states here are
+    its x0 = (1, 1, 3pi/2, 0) with a seeded perturbation per problem, the initial controls its N(0, 0.1^2) guess."""
+    rng = np.random.default_rng(seed)
+    n, m = 4, 2
+    x0 = np.tile(np.array([1.0, 1.0, 1.5 * np.pi, 0.0]), (B, 1))
+    x0[:, :2] += rng.uniform(-0.3, 0.3, (B, 2))
+    x0[:, 2] += rng.uniform(-0.3, 0.3, B)
+    u0 = rng.normal(0.0, 0.1, (N, m))
+    zs = np.zeros((2, n))
+    cxw = np.array([1e-3, 1e-3, 0.0, 0.0])
+    seq = np.zeros(N, dtype=np.int32)
+    seq[-1] = 1
+    lo_u = np.tile(np.array([-0.5, -2.0]), (N, 1))
+    return dict(name="tassa_car", model="tassa_car", dt=dt, N=N, n=n, m=m, cost="pseudo_huber", zs=zs, seq=seq,
+                Qdiag=np.stack([cxw, cxw]), Hp=np.tile(np.array([0.1, 0.1, 1.0, 1.0]), (2, 1)),
+                Qdiag_b=np.stack([np.zeros(n), np.array([0.1, 0.1, 1.0, 0.3])]),
+                Hp_b=np.stack([np.ones(n), np.array([0.01, 0.01, 0.01, 1.0])]),
+                Rdiag=1e-2 * np.array([1.0, 0.01]), u_std=1e-2, x0=x0, u0=u0,
+                lo_u=lo_u, hi_u=-lo_u, lo_x=None, hi_x=None,
+                rho_u=np.tile(np.array([1e-1, 1e-2]), (N, 1)), rho_x=None, I_o=I_o, I_a=I_a, L=L, tol=tol, alpha=1.0)

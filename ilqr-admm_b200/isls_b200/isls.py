@@ -11,7 +11,31 @@ from ._lib import IslsError
 from .projections import Bound
 from .utils import diag_of
 
-_MODEL_NAMES = ("car", "arm3", "double_integrator")
+_MODEL_NAMES = ("car", "arm3", "double_integrator", "tassa_car")
+
+
+class PseudoHuberCost:
+    """Device descriptor of the Tutorial's cost closure (notebooks/Tutorial.ipynb cell 14):
+        sum_t [ sum_j cu_j u_tj^2 + sum_i cx_i ph(x_ti, px_i) ] + sum_i cf_i ph(x_{N-1,i}, pf_i),
+        ph(x, p) = sqrt(x^2 + p^2) - p.
+    cx / px may be shorter than x_dim (the notebook's running cost acts on (x, y) only); assign it to
+    `iSLS.cost_function`.  Its analytic derivatives (the autograd `get_Cs` of cell 16) are evaluated by the kernels."""
+
+    def __init__(self, cu, cx, px, cf, pf):
+        self.cu, self.cx, self.px, self.cf, self.pf = (np.asarray(a, dtype=np.float64).reshape(-1)
+                                                       for a in (cu, cx, px, cf, pf))
+
+    def arrays(self, n, N):
+        def pad(a, fill):
+            out = np.full(n, fill)
+            out[:a.size] = a
+            return out
+        cx, px = pad(self.cx, 0.0), pad(self.px, 1.0)
+        seq = np.zeros(N, dtype=np.int32)
+        seq[-1] = 1
+        return dict(zs=np.zeros((2, n)), seq=seq, Ws=np.stack([cx, cx]), Ps=np.stack([px, px]),
+                    Ws_b=np.stack([np.zeros(n), pad(self.cf, 0.0)]), Ps_b=np.stack([np.ones(n), pad(self.pf, 1.0)]),
+                    Rdiag=self.cu)
 
 
 class iSLS:
@@ -27,6 +51,7 @@ class iSLS:
         self.A = self.B = None
         self.reset()
         self.zs = self.Qs = self.seq = self.Rt = None
+        self._cost, self._cost_kw = "quadratic", {}
         self._plan_cache = {}
 
     # ------------------------------------------------------------------ plugin slots
@@ -52,12 +77,17 @@ class iSLS:
 
     @property
     def cost_function(self):
-        return "quadratic_viapoint"
+        return "pseudo_huber" if self._cost == "pseudo_huber" else "quadratic_viapoint"
 
     @cost_function.setter
     def cost_function(self, f):
-        if f not in (None, "quadratic_viapoint"):
-            raise TypeError("only the quadratic via-point cost (set_quadratic_cost) is available on the device")
+        """Slot isls/isls_base.py:113-131.  Device costs: the quadratic via-point cost (set_quadratic_cost) and the
+        Tutorial's pseudo-Huber cost (a `PseudoHuberCost` descriptor, or set_pseudo_huber_cost)."""
+        if isinstance(f, PseudoHuberCost):
+            self.set_pseudo_huber_cost(**f.arrays(self.x_dim, self.N))
+        elif f not in (None, "quadratic_viapoint"):
+            raise TypeError("cost_function must be None / 'quadratic_viapoint' (set_quadratic_cost) or a "
+                            "PseudoHuberCost descriptor; Python callables cannot run inside the kernels")
 
     def _check_get_AB(self, get_AB):
         if get_AB is None:
@@ -66,6 +96,13 @@ class iSLS:
         if name != self._model:
             raise TypeError("get_AB must be None or the name of the device model set as forward_model (%r); "
                             "Jacobians are evaluated by the device model" % (self._model,))
+
+    def _check_get_Cs(self, get_Cs):
+        """The cost derivatives (isls.py:263-279, Tutorial cell 16) are evaluated analytically by the kernels for the
+        cost set on this object; a Python get_Cs callable cannot run there."""
+        if get_Cs is not None and get_Cs not in ("analytic", self.cost_function):
+            raise TypeError("get_Cs must be None or 'analytic': the device evaluates the derivatives of the cost "
+                            "set through set_quadratic_cost / cost_function")
 
     # ------------------------------------------------------------------ cost
     def set_quadratic_cost(self, zs, Qs, seq, u_std):
@@ -78,9 +115,27 @@ class iSLS:
         self.seq = np.asarray(seq, dtype=np.int32)
         self.u_std = float(u_std)
         self.Rt = np.eye(self.u_dim) * u_std
+        self._cost, self._cost_kw = "quadratic", {}
         self._plan_cache.clear()
 
     set_cost_variables = set_quadratic_cost          # legacy name (README.md:24-39)
+
+    def set_pseudo_huber_cost(self, zs, Ws, Ps, seq, Rdiag, Ws_b=None, Ps_b=None):
+        """Pseudo-Huber state cost sum_t sum_i W[seq_t, i] (sqrt((x_ti - z[seq_t, i])^2 + P[seq_t, i]^2) - P[seq_t, i])
+        (+ the same with Ws_b, Ps_b) + sum_t u' diag(Rdiag) u: notebooks/Tutorial.ipynb cell 14 in the (zs, seq)
+        via-point form of set_quadratic_cost."""
+        self.zs = np.asarray(zs, dtype=np.float64)
+        self.Qdiag = np.asarray(Ws, dtype=np.float64)
+        self.Qs = self.Qdiag
+        self.seq = np.asarray(seq, dtype=np.int32)
+        Rdiag = np.asarray(Rdiag, dtype=np.float64).reshape(self.u_dim)
+        self.u_std = float(Rdiag[0])
+        self.Rt = np.diag(Rdiag)
+        self._cost = "pseudo_huber"
+        self._cost_kw = dict(Rdiag=Rdiag, Hp=np.asarray(Ps, dtype=np.float64),
+                             Qdiag_b=None if Ws_b is None else np.asarray(Ws_b, dtype=np.float64),
+                             Hp_b=None if Ps_b is None else np.asarray(Ps_b, dtype=np.float64))
+        self._plan_cache.clear()
 
     def compute_Rr_Qr(self, rho_x, rho_u, dp=True):
         """isls/base.py:55-79, returned as per-step DIAGONALS Qr[N,n], Rr[N,m] (None stays None)."""
@@ -145,14 +200,15 @@ class iSLS:
 
     def _solver(self, L, rho_x, bx, rho_u, bu, max_outer, max_admm, want_gains=False, want_masks=False):
         if self._model is None or self.zs is None:
-            raise IslsError("set forward_model and set_quadratic_cost first")
+            raise IslsError("set forward_model and a cost (set_quadratic_cost / cost_function) first")
         key = (L, None if rho_x is None else rho_x.tobytes(), None if bx is None else (bx[0].tobytes(), bx[1].tobytes()),
                None if rho_u is None else rho_u.tobytes(), None if bu is None else (bu[0].tobytes(), bu[1].tobytes()),
                max_outer, max_admm, want_gains, want_masks)
         if key not in self._plan_cache:
             plan = S.Plan(self._model, self.N, self.x_dim, self.u_dim, self._dt(), self.Qdiag, self.seq, self.u_std,
                           L, rho_x=rho_x, lo_x=None if bx is None else bx[0], hi_x=None if bx is None else bx[1],
-                          rho_u=rho_u, lo_u=None if bu is None else bu[0], hi_u=None if bu is None else bu[1])
+                          rho_u=rho_u, lo_u=None if bu is None else bu[0], hi_u=None if bu is None else bu[1],
+                          cost=self._cost, **self._cost_kw)
             self._plan_cache.clear()
             self._plan_cache[key] = S.BatchSolver(plan, self.nb, self.device, max_outer=max_outer, max_admm=max_admm,
                                                   want_gains=want_gains, want_masks=want_masks)
@@ -178,6 +234,7 @@ class iSLS:
         if method != "dp":
             raise NotImplementedError("device path implements method='dp' (the dense batch form is the same minimiser)")
         self._check_get_AB(get_AB)
+        self._check_get_Cs(get_Cs)
         sv = self._solver(max_line_search_iter, None, None, None, None, max_iter, 1, want_gains=True)
         sv.set_inputs(self._x0, self._u_init, self._zs_b())
         out = sv.ilqr(tol_fun=tol_fun, fixed_budget=fixed_budget)
@@ -212,8 +269,7 @@ class iSLS:
         if threshold is not None:
             tol = threshold
         self._check_get_AB(get_AB)
-        if get_Cs is not None:
-            raise NotImplementedError("only the quadratic via-point cost is available on the device")
+        self._check_get_Cs(get_Cs)
         for nm, pr in (("project_x", project_x), ("project_u", project_u)):
             if pr and not isinstance(pr, Bound):
                 raise TypeError("%s must be an isls_b200.projections.Bound (box bounds); Python callables cannot run "

@@ -10,7 +10,8 @@ import torch
 
 from . import _lib
 
-MODEL_DIMS = {"car": (4, 2), "arm3": (9, 3)}
+MODEL_DIMS = {"car": (4, 2), "arm3": (9, 3), "tassa_car": (4, 2)}
+COST_KINDS = {"quadratic": 0, "pseudo_huber": 1}
 
 ST_CONVERGED_COST, ST_LINESEARCH_FAIL, ST_MAX_ITER, ST_OSCILLATING, ST_NON_PD, ST_NAN_COST = 1, 2, 4, 8, 16, 32
 ADMM_CONVERGED, ADMM_STALLED, ADMM_MAXIT = 1, 2, 3
@@ -41,7 +42,9 @@ class Plan:
     diagonal ADMM penalties and box bounds."""
 
     def __init__(self, model, N, n, m, dt, Qdiag, seq, u_std, L, rho_x=None, lo_x=None, hi_x=None, rho_u=None,
-                 lo_u=None, hi_u=None):
+                 lo_u=None, hi_u=None, cost="quadratic", Rdiag=None, Hp=None, Qdiag_b=None, Hp_b=None):
+        """cost="pseudo_huber": Qdiag / Hp are the weights and smoothness scales [n_via, n] of the first term,
+        Qdiag_b / Hp_b of the optional second one (Tutorial cell 14); Rdiag [m] replaces R = u_std I."""
         L_ = _lib.lib()
         mid = L_.isls_model_id(model.encode())
         _lib.check(0 if mid >= 0 else mid, "isls_model_id(%r)" % model)
@@ -60,8 +63,16 @@ class Plan:
             keep.update(rho_u=_f64(rho_u, (N, m)), lo_u=_f64(-np.inf if lo_u is None else lo_u, (N, m)),
                         hi_u=_f64(np.inf if hi_u is None else hi_u, (N, m)))
         assert keep["seq"].shape == (N,)
-        d = _lib.ProblemDesc(model_id=mid, n=n, m=m, N=N, n_via=self.n_via, L=L, dt=dt, u_std=float(u_std))
-        for k in ("Qdiag", "seq", "alphas", "rho_x", "lo_x", "hi_x", "rho_u", "lo_u", "hi_u"):
+        if cost not in COST_KINDS:
+            raise _lib.IslsError("unknown cost %r (device costs: %s)" % (cost, tuple(COST_KINDS)))
+        for nm, arr, shp in (("Rdiag", Rdiag, (m,)), ("Hp", Hp, (self.n_via, n)), ("Qdiag_b", Qdiag_b, (self.n_via, n)),
+                             ("Hp_b", Hp_b, (self.n_via, n))):
+            if arr is not None:
+                keep[nm] = _f64(arr, shp)
+        d = _lib.ProblemDesc(model_id=mid, n=n, m=m, N=N, n_via=self.n_via, L=L, dt=dt, u_std=float(u_std),
+                             cost_kind=COST_KINDS[cost])
+        for k in ("Qdiag", "seq", "alphas", "rho_x", "lo_x", "hi_x", "rho_u", "lo_u", "hi_u", "Rdiag", "Hp", "Qdiag_b",
+                  "Hp_b"):
             setattr(d, k, _ptr(keep.get(k)))
         self._keep = keep
         h = C.c_void_p()

@@ -40,6 +40,12 @@ extern "C" {
 #define ISLS_MODEL_DOUBLE_INTEGRATOR 0   /* isls/utils.py:266-276 + isls/sls_base.py:49-53; n=2d, m=d, d in {1,2,3} */
 #define ISLS_MODEL_CAR 1                 /* notebooks/Car/Iterative LQR with control constraints.ipynb cell 6; n=4,m=2 */
 #define ISLS_MODEL_ARM3 2                /* notebooks/3DoF robot/State and control bound constraints.ipynb cells 9-10; n=9,m=3 */
+#define ISLS_MODEL_TASSA_CAR 3           /* notebooks/Tutorial.ipynb cell 8 (car parking of Tassa et al., axle distance 2); n=4,m=2 */
+
+/* state-cost families (cost_function slot, isls/isls_base.py:113-131) */
+#define ISLS_COST_QUADRATIC 0            /* sum_i Q_ii (x_i - z_i)^2: isls/sls_base.py:25-44 */
+#define ISLS_COST_PSEUDO_HUBER 1         /* sum_i w_i (sqrt((x_i - z_i)^2 + p_i^2) - p_i), two weighted terms per
+                                            component: notebooks/Tutorial.ipynb cell 14 (running + final cost) */
 
 /* per-problem status bits */
 #define ISLS_ST_CONVERGED_COST 1   /* |cost-prev| < tol            isls/isls.py:125, isls/isls.py:493 */
@@ -72,6 +78,12 @@ typedef struct isls_problem_desc {
   const double *lo_x, *hi_x; /* [N, n] box bounds on the state (+-inf = free), required iff rho_x != NULL */
   const double *rho_u;   /* [N, m] or NULL: no control projection */
   const double *lo_u, *hi_u; /* [N, m] */
+  /* ---- optional cost extensions (all 0 / NULL: quadratic via-point cost with R = u_std I) ---- */
+  int32_t cost_kind;     /* ISLS_COST_*: for PSEUDO_HUBER Qdiag holds the weights w of term a */
+  const double *Rdiag;   /* [m] diagonal of R (overrides u_std; Tutorial cell 14: cu) or NULL */
+  const double *Hp;      /* [n_via, n] smoothness scales p of term a (PSEUDO_HUBER) */
+  const double *Qdiag_b; /* [n_via, n] weights of the second term per component or NULL */
+  const double *Hp_b;    /* [n_via, n] smoothness scales of the second term */
 } isls_problem_desc;
 
 typedef struct isls_plan isls_plan;   /* opaque */
@@ -112,7 +124,7 @@ typedef struct isls_solve_out {
 int isls_version(void);
 const char *isls_last_error_string(void);
 
-/* name -> ISLS_MODEL_* (or ISLS_E_UNSUPPORTED).  Names: "double_integrator", "car", "arm3". */
+/* name -> ISLS_MODEL_* (or ISLS_E_UNSUPPORTED).  Names: "double_integrator", "car", "arm3", "tassa_car". */
 int isls_model_id(const char *name);
 /* 0 if the (model, n, m) combination has a compiled kernel */
 int isls_model_supported(int32_t model_id, int32_t n, int32_t m);

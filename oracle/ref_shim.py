@@ -133,3 +133,90 @@ def run_ilqr_dp(s, model, max_iter=100, max_line_search_iter=25, tol_fun=1e-5):
         s.solve(model.get_AB, get_Cs_quadratic(s), method="dp", max_iter=max_iter,
                 max_line_search_iter=max_line_search_iter, tol_fun=tol_fun)
     return dict(x=s.x_nom.copy(), u=s.u_nom.copy(), cost_log=np.array(s.cost_log, dtype=np.float64))
+
+
+# ----------------------------------------------------------------------------- Tutorial problem (pseudo-Huber cost)
+def tutorial_cost(p):
+    """The Tutorial's cost closure (notebooks/Tutorial.ipynb cell 14) in plain numpy: lu + lf + lx per step, summed;
+    NaN -> 1e6 for batched inputs.  p: oracle problem dict (configs.tassa_batch)."""
+    N = p["N"]
+    cu = np.asarray(p["Rdiag"])
+    cf_ = np.asarray(p["Qdiag_b"])[p["seq"]]                       # [N, n]: zero rows except the last
+    pf = np.asarray(p["Hp_b"])[1]
+    cx_ = np.asarray(p["Qdiag"])[p["seq"]][:, :2]
+    px = np.asarray(p["Hp"])[0][:2][None]
+
+    def pseudo_huber(x, pp):
+        return np.sqrt(x ** 2 + pp ** 2) - pp
+
+    def cost_vec(x, u):
+        lu = np.sum(cu * (u ** 2), axis=-1)
+        lf = cf_ @ pseudo_huber(x[-1], pf)
+        lx = np.sum(cx_ * pseudo_huber(x[:, :2], px), axis=-1)
+        return lf + lu + lx
+
+    def cost(x, u):
+        if x.ndim == 3:
+            costs = np.zeros(x.shape[0])
+            for i in range(x.shape[0]):
+                costs[i] = np.sum(cost_vec(x[i], u[i]), -1)
+            costs[np.isnan(costs)] = 1e6
+        else:
+            costs = np.sum(cost_vec(x, u), -1)
+        return costs
+    return cost
+
+
+def tutorial_get_Cs(p):
+    """Analytic replacement of the autograd get_Cs of Tutorial cell 16 (autograd is not installed here): gradient and
+    (diagonal) Hessian of cost_vec; the cost has no x-u coupling (the notebook says so), so Cux = 0."""
+    n, m, N = p["n"], p["m"], p["N"]
+    terms = [(np.asarray(p["Qdiag"])[p["seq"]], np.asarray(p["Hp"])[p["seq"]]),
+             (np.asarray(p["Qdiag_b"])[p["seq"]], np.asarray(p["Hp_b"])[p["seq"]])]
+    cu = np.asarray(p["Rdiag"])
+
+    def get_Cs(x, u):
+        c = np.zeros((N, n + m))
+        C = np.zeros((N, n + m, n + m))
+        g = np.zeros((N, n))
+        h = np.zeros((N, n))
+        for W, P in terms:
+            sq = np.sqrt(x * x + P * P)
+            g += W * x / sq
+            h += W * (P * P) / (sq * sq * sq)
+        c[:, :n] = g
+        c[:, n:] = 2.0 * cu * u
+        i = np.arange(n)
+        C[:, i, i] = h
+        j = n + np.arange(m)
+        C[:, j, j] = 2.0 * cu
+        return c, C
+    return get_Cs
+
+
+def make_isls_tutorial(model, p):
+    """iSLS object set up the way Tutorial cells 17-18 do (forward_model + cost_function callables)."""
+    pkg, _ = load()
+    with quiet():
+        s = pkg.iSLS(model.n, model.m, p["N"])
+        s.C, s.D = s.Sw, s.Su                                        # shim S1
+        s.forward_model = model.f
+        s.cost_function = tutorial_cost(p)
+    return s
+
+
+def run_tutorial_dp(s, model, p, max_iter=100, max_line_search_iter=40):
+    with quiet():
+        s.solve(model.get_AB, tutorial_get_Cs(p), max_iter=max_iter, max_line_search_iter=max_line_search_iter,
+                method="dp", verbose=False)                           # Tutorial cell 20
+    return dict(x=s.x_nom.copy(), u=s.u_nom.copy(), cost_log=np.array(s.cost_log, dtype=np.float64))
+
+
+def run_tutorial_admm(s, model, p):
+    lo, hi = p["lo_u"].flatten(), p["hi_u"].flatten()
+    with quiet():
+        log = s.ilqr_admm(get_AB=model.get_AB, get_Cs=tutorial_get_Cs(p), project_u=lambda z: np.clip(z, lo, hi),
+                          max_iter=p["I_o"], max_admm_iter=p["I_a"], max_line_search_iter=p["L"],
+                          rho_u=np.diag(p["rho_u"][0]), tol=p["tol"], verbose=False, log=True)   # Tutorial cell 27
+    return dict(x=s.x_nom.copy(), u=s.u_nom.copy(), cost_log=np.array(s.cost_log, dtype=np.float64),
+                admm_log=np.array(log, dtype=np.float64))

@@ -76,6 +76,55 @@ def quad_cost(p, zs, x, u):
     return c
 
 
+def _R(p):
+    """Diagonal of R: u_std * I (base.py:86-89) or the per-control weights of the Tutorial (cell 14: cu)."""
+    if p.get("Rdiag") is not None:
+        return np.asarray(p["Rdiag"], dtype=np.float64)
+    return np.full(p["m"], float(p["u_std"]))
+
+
+def _huber_terms(p):
+    """[(W[N,n], P[N,n])]: the weighted pseudo-Huber terms per time step (running term a, final term b)."""
+    seq = p["seq"]
+    terms = [(np.asarray(p["Qdiag"], float)[seq], np.asarray(p["Hp"], float)[seq])]
+    if p.get("Qdiag_b") is not None:
+        terms.append((np.asarray(p["Qdiag_b"], float)[seq], np.asarray(p["Hp_b"], float)[seq]))
+    return terms
+
+
+def total_cost(p, zs, x, u):
+    """cost_function of the problem: the quadratic via-point cost, or the Tutorial's pseudo-Huber cost
+    (notebooks/Tutorial.ipynb cell 14: lu + lf + lx, NaN -> 1e6 for batched inputs)."""
+    if p.get("cost", "quadratic") == "quadratic" and p.get("Rdiag") is None:
+        return quad_cost(p, zs, x, u)
+    e = x - zs[:, p["seq"]][:, None]
+    if p.get("cost", "quadratic") == "quadratic":
+        c = np.sum(e * e * np.asarray(p["Qdiag"], float)[p["seq"]], axis=(-1, -2))
+    else:
+        c = 0.0
+        for W, P in _huber_terms(p):
+            c = c + np.sum(W * (np.sqrt(e * e + P * P) - P), axis=(-1, -2))
+        c = c + np.sum(_R(p) * u * u, axis=(-1, -2))
+        return np.where(np.isnan(c), 1e6, c)
+    return c + np.sum(_R(p) * u * u, axis=(-1, -2))
+
+
+def state_grad_hess(p, zs_seq, x):
+    """cts[:, :n] and diag(Cts[:, :n, :n]) of get_Cs at x[b,N,n] (Tutorial cell 16; isls.py:263-279): quadratic
+    2Q(x-z), 2Q; pseudo-Huber w e / s, w p^2 / s^3, s = sqrt(e^2 + p^2)."""
+    e = x - zs_seq
+    if p.get("cost", "quadratic") == "quadratic":
+        Qd = np.asarray(p["Qdiag"], float)[p["seq"]]
+        return 2.0 * Qd * e, np.broadcast_to(2.0 * Qd, e.shape)
+    g = np.zeros_like(e)
+    h = np.zeros_like(e)
+    for W, P in _huber_terms(p):
+        sq = np.sqrt(e * e + P * P)
+        g = g + W * e / sq
+        h = h + W * (P * P) / (sq * sq * sq)
+    return g, h
+
+
 # ------------------------------------------------------------------------------------------------ rollouts
 def rollout_open(model, x0, u):
     """isls.py:135-154.  x0[B,n], u[B,L,N,m] -> x[B,L,N,n]."""
@@ -223,16 +272,17 @@ def initial_rollout(p):
 
 # -------------------------------------------------------------------------------------------- plain iLQR (DP)
 def ilqr_dp(p, max_iter=100, L=25, tol_fun=1e-5, fixed_budget=False):
-    """iSLS.solve(method='dp') for the quadratic via-point cost (isls.py:54-132 + 336-374)."""
+    """iSLS.solve(method='dp') (isls.py:54-132 + 336-374) for the quadratic via-point cost or the pseudo-Huber cost
+    with analytic get_Cs (Cux = 0)."""
     model = _model_of(p)
     N, n, m = p["N"], p["n"], p["m"]
     x_nom, u_nom = initial_rollout(p)
     B = x_nom.shape[0]
     zs = _zs_b(p, B)
     seq = p["seq"]
-    Qd = p["Qdiag"][seq]
     al = alphas(L)
-    cost = quad_cost(p, zs, x_nom[:, None], u_nom[:, None])[:, 0]
+    Rv = _R(p)
+    cost = total_cost(p, zs, x_nom[:, None], u_nom[:, None])[:, 0]
     cost_log = np.full((B, max_iter + 1), np.nan)
     cost_log[:, 0] = cost
     n_log = np.ones(B, dtype=np.int64)
@@ -240,8 +290,7 @@ def ilqr_dp(p, max_iter=100, L=25, tol_fun=1e-5, fixed_budget=False):
     iters = np.zeros(B, dtype=np.int32)
     alpha_idx = np.full((B, max_iter), -1, dtype=np.int32)
     active = np.ones(B, dtype=bool)
-    Cxx = _diag_embed(2.0 * Qd)[None]
-    Cuu = _diag_embed(np.full((N, m), 2.0 * p["u_std"]))[None]
+    Cuu = _diag_embed(np.broadcast_to(2.0 * Rv, (N, m)))[None]
     K_out = np.zeros((B, N, m, n))
     k_out = np.zeros((B, N, m))
     for it in range(max_iter):
@@ -250,13 +299,14 @@ def ilqr_dp(p, max_iter=100, L=25, tol_fun=1e-5, fixed_budget=False):
             break
         xn, un = x_nom[idx], u_nom[idx]
         A, Bm = model.get_AB(xn, un)
-        cx = 2.0 * Qd * (xn - zs[idx][:, seq])
-        cu = 2.0 * p["u_std"] * un
+        cx, hxx = state_grad_hess(p, zs[idx][:, seq], xn)
+        Cxx = _diag_embed(hxx)
+        cu = 2.0 * Rv * un
         K, k, non_pd = backward_pass(A, Bm, cx, cu, Cxx, Cuu)
         K_out[idx], k_out[idx] = K, k
         k_cand = k[:, None] * al[None, :, None, None]                         # isls.py:357
         xs, us = rollout_closed(model, xn, un, K, k_cand)
-        costs = quad_cost(p, zs[idx], xs, us)
+        costs = total_cost(p, zs[idx], xs, us)
         nan = np.isnan(costs)
         costs = np.where(nan, 1e5, costs)                                     # isls.py:362
         ind = np.argmin(costs, axis=1)
@@ -269,7 +319,7 @@ def ilqr_dp(p, max_iter=100, L=25, tol_fun=1e-5, fixed_budget=False):
         x_nom[acc] = xs[ok, ind[ok]]
         u_nom[acc] = us[ok, ind[ok]]
         # nominal_values setter re-evaluates the cost (isls_base.py:80-85)
-        newc = quad_cost(p, zs[acc], x_nom[acc][:, None], u_nom[acc][:, None])[:, 0]
+        newc = total_cost(p, zs[acc], x_nom[acc][:, None], u_nom[acc][:, None])[:, 0]
         cost[acc] = newc
         cost_log[acc, n_log[acc]] = newc
         n_log[acc] += 1
@@ -304,15 +354,15 @@ def ilqr_admm(p, fixed_budget=False, outer_tol=1e-3, keep_trace=False):
     B = x_nom.shape[0]
     zs = _zs_b(p, B)
     seq = p["seq"]
-    Qd = p["Qdiag"][seq]                                                      # [N,n]
-    R = p["u_std"]
+    R = _R(p)                                                                 # [m] diagonal of R
+    quadratic = p.get("cost", "quadratic") == "quadratic"
     bx, bu = _bounds(p, "x", N, n), _bounds(p, "u", N, m)
     proj_x, proj_u = bx is not None, bu is not None
     rho_x = np.broadcast_to(np.asarray(p["rho_x"], float), (N, n)) if proj_x else np.zeros((N, n))
     rho_u = np.broadcast_to(np.asarray(p["rho_u"], float), (N, m)) if proj_u else np.zeros((N, m))
     al = alphas(L)
 
-    cost = quad_cost(p, zs, x_nom[:, None], u_nom[:, None])[:, 0]
+    cost = total_cost(p, zs, x_nom[:, None], u_nom[:, None])[:, 0]
     cost_log = np.full((B, I_o + 1), np.nan)
     cost_log[:, 0] = cost
     n_log = np.ones(B, dtype=np.int64)
@@ -329,7 +379,8 @@ def ilqr_admm(p, fixed_budget=False, outer_tol=1e-3, keep_trace=False):
     trace = [] if keep_trace else None
     active = np.ones(B, dtype=bool)
 
-    Cxx = _diag_embed(2.0 * (Qd + rho_x))[None]                               # recipe step 1
+    if quadratic:
+        Cxx = _diag_embed(2.0 * (np.asarray(p["Qdiag"], float)[seq] + rho_x))[None]   # recipe step 1
     Cuu = _diag_embed(2.0 * (R + rho_u))[None]
     Cuu_last = 2.0 * (R + rho_u[-1])
 
@@ -342,9 +393,12 @@ def ilqr_admm(p, fixed_budget=False, outer_tol=1e-3, keep_trace=False):
         A, Bm = model.get_AB(xn, un)                                          # isls.py:424
         zero_cx = np.zeros((1, N, n))
         zero_cu = np.zeros((1, N, m))
+        zs_i = zs[idx][:, seq]                                                # [b,N,n]
+        gx, hxx = state_grad_hess(p, zs_i, xn)                                # get_Cs at the nominal (isls.py:427-432)
+        if not quadratic:
+            Cxx = _diag_embed(hxx + 2.0 * rho_x)
         K, _, non_pd, Quu, Quu_inv, Qux = backward_pass(A, Bm, zero_cx, zero_cu, Cxx, Cuu, logs=True)
         status[idx[non_pd]] |= ST_NON_PD
-        zs_i = zs[idx][:, seq]                                                # [b,N,n]
         zx, zu = z_x[idx].copy(), z_u[idx].copy()                             # warm start (isls.py:489-490)
         lx, lu = np.zeros_like(zx), np.zeros_like(zu)                         # lambda reset (isls.py:414-415)
         prim = np.full(idx.size, 1e6)
@@ -358,14 +412,14 @@ def ilqr_admm(p, fixed_budget=False, outer_tol=1e-3, keep_trace=False):
             g = idx[ia]
             reg_x, reg_u = zx[ia] - lx[ia], zu[ia] - lu[ia]                   # admm.py:32-33
             # ---- f_argmin (isls.py:456-478) in Riccati form
-            cx = 2.0 * Qd * (xn[ia] - zs_i[ia]) + 2.0 * rho_x * (xn[ia] - reg_x)
+            cx = gx[ia] + 2.0 * rho_x * (xn[ia] - reg_x)
             cu = 2.0 * R * un[ia] + 2.0 * rho_u * (un[ia] - reg_u)
             k = ff_pass(A[ia], Bm[ia], cx, cu, K[ia], Quu[ia], Quu_inv[ia], Qux[ia])
             k[:, -1] = -cu[:, -1] / Cuu_last                                  # batch-form last control
             _, du = linear_rollout(A[ia], Bm[ia], K[ia], k)
             u_cand = un[ia][:, None] + al[None, :, None, None] * du[:, None]  # isls.py:468
             x_cand = rollout_open(model, xn[ia][:, 0], u_cand)                # isls.py:469
-            costs = quad_cost(p, zs[g], x_cand, u_cand)                       # isls.py:470
+            costs = total_cost(p, zs[g], x_cand, u_cand)                      # isls.py:470
             if proj_x:
                 dxr = x_cand - reg_x[:, None]
                 costs = costs + np.sum(dxr * dxr * rho_x, axis=(-1, -2))      # isls.py:471-473 (diagonal Qr)
@@ -423,7 +477,7 @@ def ilqr_admm(p, fixed_budget=False, outer_tol=1e-3, keep_trace=False):
         admm_exit[idx[a_active], j] = ADMM_MAXIT
         # ---- after ADMM (isls.py:488-499)
         x_nom[idx], u_nom[idx] = x_last, u_last                              # nominal <- last primal iterate
-        newc = quad_cost(p, zs[idx], x_last[:, None], u_last[:, None])[:, 0]
+        newc = total_cost(p, zs[idx], x_last[:, None], u_last[:, None])[:, 0]
         cost[idx] = newc
         cost_log[idx, n_log[idx]] = newc
         n_log[idx] += 1

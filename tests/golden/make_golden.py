@@ -142,22 +142,6 @@ def golden_notebook_pins():
     np.savez_compressed(os.path.join(OUT, "notebook_pins.npz"), **out)
 
 
-if __name__ == "__main__":
-    assert S.available(), "needs the reference tree"
-    golden_ilqr_admm(P.car_batch(6), "car_ilqr_admm", 10.0)
-    golden_ilqr_admm(P.car_batch(3, stress=True), "car_stress_ilqr_admm", 10.0)
-    golden_ilqr_admm(P.arm_batch(3), "arm_ilqr_admm", 1e-3)
-    golden_ilqr_dp(P.car_batch(4), "car_ilqr_dp", 30, 25)
-    golden_ilqr_dp(P.arm_batch(2), "arm_ilqr_dp", 20, 25)
-    golden_backward_pass("car_backward_pass", "car", 100, 11)
-    golden_backward_pass("arm_backward_pass", "arm3", 100, 12)
-    pd = P.di_batch(3)
-    golden_lqt_admm_dp(pd, "di_lqt_admm_dp")
-    golden_notebook_pins()
-    golden_sls()
-    golden_mc()
-
-
 def golden_sls(name="sls_admm"):
     """SLS.solve_sls / ADMM_SLS / controller of the unmodified reference on (a) the notebook problem
     'LQR and SLS with control bounds' (n=2, m=1, N=100; known printout: "can't improve anymore at iteration 25",
@@ -254,3 +238,53 @@ def golden_mc(name="mc_rollouts"):
         out["car_sls_x"], out["car_sls_u"] = np.stack(xs), np.stack(uu)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
     print(name, {k: v.shape for k, v in out.items() if k.endswith("_x")})
+
+
+def golden_tutorial(B=3, N=150):
+    """Tutorial problem (Tassa car parking + pseudo-Huber cost): reference solve(method='dp') (cell 20) and
+    ilqr_admm with control limits (cell 27), analytic get_AB / get_Cs standing in for autograd (not installed)."""
+    p = P.tassa_batch(B, N=N)
+    model = M.make_model("tassa_car", dt=p["dt"])
+    out = {}
+    for tag, run in (("dp", S.run_tutorial_dp), ("admm", S.run_tutorial_admm)):
+        xs, us, logs, admm = [], [], [], []
+        for b in range(B):
+            s = S.make_isls_tutorial(model, p)
+            S.init_nominal(s, p["x0"][b], p["u0"])
+            r = run(s, model, p)
+            xs.append(r["x"]); us.append(r["u"]); logs.append(r["cost_log"])
+            if "admm_log" in r:
+                admm.append(r["admm_log"].reshape(-1, 2))
+            print("tutorial", tag, b, len(r["cost_log"]), r["cost_log"][0], r["cost_log"][-1])
+        out.update({"x_" + tag: np.stack(xs), "u_" + tag: np.stack(us), "cost_log_" + tag: _pad(logs)})
+        if admm:
+            k = max(len(a) for a in admm)
+            la = np.full((B, k, 2), np.nan)
+            for i, a in enumerate(admm):
+                la[i, :len(a)] = a
+            out["last_admm_log"] = la
+    np.savez_compressed(os.path.join(OUT, "tutorial_tassa.npz"), x0=p["x0"], u0=p["u0"], N=N, **out)
+
+
+if __name__ == "__main__":
+    assert S.available(), "needs the reference tree"
+    only = set(sys.argv[1:])                       # e.g. `make_golden.py tutorial` regenerates one fixture family
+
+    def want(tag):
+        return not only or tag in only
+    if want("ilqr"):
+        golden_ilqr_admm(P.car_batch(6), "car_ilqr_admm", 10.0)
+        golden_ilqr_admm(P.car_batch(3, stress=True), "car_stress_ilqr_admm", 10.0)
+        golden_ilqr_admm(P.arm_batch(3), "arm_ilqr_admm", 1e-3)
+        golden_ilqr_dp(P.car_batch(4), "car_ilqr_dp", 30, 25)
+        golden_ilqr_dp(P.arm_batch(2), "arm_ilqr_dp", 20, 25)
+        golden_backward_pass("car_backward_pass", "car", 100, 11)
+        golden_backward_pass("arm_backward_pass", "arm3", 100, 12)
+        golden_lqt_admm_dp(P.di_batch(3), "di_lqt_admm_dp")
+        golden_notebook_pins()
+    if want("sls"):
+        golden_sls()
+    if want("mc"):
+        golden_mc()
+    if want("tutorial"):
+        golden_tutorial()

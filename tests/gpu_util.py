@@ -10,7 +10,10 @@ def make_isls(p, device="cuda:0"):
     s = iSLS(p["n"], p["m"], p["N"], batch=B, device=device)
     kw = {"dt": p["dt"]}
     s.forward_model = (p["model"], kw)
-    s.set_quadratic_cost(p["zs"], p["Qdiag"], p["seq"], p["u_std"])
+    if p.get("cost", "quadratic") == "pseudo_huber":
+        s.set_pseudo_huber_cost(p["zs"], p["Qdiag"], p["Hp"], p["seq"], p["Rdiag"], p.get("Qdiag_b"), p.get("Hp_b"))
+    else:
+        s.set_quadratic_cost(p["zs"], p["Qdiag"], p["seq"], p["u_std"])
     s.set_initial(p["x0"], p["u0"])
     return s
 

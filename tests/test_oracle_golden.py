@@ -161,3 +161,42 @@ def test_mc_rollouts_match_reference(golden):
     assert np.abs(x - g["car_dp_x"]).max() < 1e-12 and np.abs(u - g["car_dp_u"]).max() < 1e-12
     x, u = R.mc_rollout(car, "sls", g["car_x0"], g["car_Ks"], g["car_ks"], 25, g["car_x_nom"], g["car_u_nom"])
     assert np.abs(x - g["car_sls_x"]).max() < 1e-12 and np.abs(u - g["car_sls_u"]).max() < 1e-12
+
+
+def test_tutorial_tassa_pseudo_huber_vs_reference_golden(golden):
+    """Tutorial problem (Tassa car + pseudo-Huber cost) - oracle vs the unmodified reference's
+    solve(method='dp') and ilqr_admm (analytic get_AB / get_Cs callbacks), identical iteration counts."""
+    g = golden("tutorial_tassa")
+    p = P.tassa_batch(3, N=int(g["N"]))
+    o = R.ilqr_dp(p, max_iter=100, L=40)
+    ref = g["cost_log_dp"]
+    assert np.array_equal(o["n_log"], (~np.isnan(ref)).sum(1))
+    m = ~np.isnan(ref)
+    assert np.max(np.abs(o["cost_log"][:, :ref.shape[1]][m] - ref[m]) / np.abs(ref[m])) < 1e-9
+    assert np.abs(o["u"] - g["u_dp"]).max() < 1e-9 and np.abs(o["x"] - g["x_dp"]).max() < 1e-9
+    o = R.ilqr_admm(p)
+    ref = g["cost_log_admm"]
+    assert np.array_equal(o["n_log"], (~np.isnan(ref)).sum(1))
+    m = ~np.isnan(ref)
+    assert np.max(np.abs(o["cost_log"][:, :ref.shape[1]][m] - ref[m]) / np.abs(ref[m])) < 1e-9
+    assert np.abs(o["u"] - g["u_admm"]).max() < 1e-9 and np.abs(o["x"] - g["x_admm"]).max() < 1e-9
+
+
+def test_tassa_jacobian_finite_differences():
+    """The hand-derived Jacobian of the Tassa car (the notebook uses autograd) against central differences."""
+    from oracle import models as M
+    mdl = M.make_model("tassa_car", dt=0.03)
+    rng = np.random.default_rng(0)
+    x = rng.normal(0, 1, (16, 4))
+    x[:, 3] *= 3
+    u = rng.normal(0, 0.4, (16, 2))
+    A, B = mdl.get_AB(x, u)
+    eps = 1e-6
+    for i in range(4):
+        d = np.zeros(4)
+        d[i] = eps
+        assert np.allclose((mdl.f(x + d, u) - mdl.f(x - d, u)) / (2 * eps), A[:, :, i], atol=1e-8)
+    for j in range(2):
+        d = np.zeros(2)
+        d[j] = eps
+        assert np.allclose((mdl.f(x, u + d) - mdl.f(x, u - d)) / (2 * eps), B[:, :, j], atol=1e-8)

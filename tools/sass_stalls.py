@@ -5,7 +5,7 @@ and the sum of the compiler's stall counts (= cycles one warp alone needs per tr
     python tools/sass_stalls.py <cubin-or-so> <mangled-function-substring> [--dump LO HI]
 
 Used for the line-search kernel: FP64 instructions occupy the pipe 2 cycles each, so  2 * (#FP64 ops) / (sum of
-stalls)  is the FP64-pipe share one warp can reach alone; profiles/r2_linesearch_schedule.md records the numbers.
+stalls)  is the FP64-pipe share one warp can reach alone; profiles/r1_linesearch_schedule.md records the numbers.
 """
 import collections
 import re
