@@ -77,6 +77,11 @@ struct Dev {
   const double *rho_x, *lo_x, *hi_x;   // [N][n]
   const double *rho_u, *lo_u, *hi_u;   // [N][m]
   const double *alphas;  // [L]
+  // obstacle sets of the state projection (n_obst = 0: box): centres [K][2], W / W^-1 [K][4], lower [K]
+  int n_obst, obst_max_iter;
+  double obst_upper, obst_rho, obst_threshold;
+  const double *ob_c, *ob_W, *ob_Wi, *ob_lo;
+  double *obw;           // workspace [3 + 2K][T][N][n][32]: winner x, pre-projection point, inner x, z_k, lambda_k
   // workspace, tile-blocked [T][N][dim][32]
   double *xh, *uh, *du, *zx, *lx, *zu, *lu, *rgx, *rgu, *Kg, *Qux, *Quu, *Qui, *kk, *zs;   // Quu, Qui: packed lower
   double *lsc;           // [T][L][32] candidate costs of the last line search
@@ -253,6 +258,9 @@ __global__ void k_init(Dev d, const double *x0, const double *u_init, const doub
     if (d.out.alpha_idx)
       for (int i = 0; i < d.max_outer * d.max_admm; i++)
         d.out.alpha_idx[(size_t)c.ob * d.max_outer * d.max_admm + i] = -1;
+    if (d.out.inner_iters)
+      for (int i = 0; i < d.max_outer * d.max_admm; i++)
+        d.out.inner_iters[(size_t)c.ob * d.max_outer * d.max_admm + i] = 0;
   }
 }
 
@@ -1172,6 +1180,94 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
   }
 }
 
+// ---- state projection onto the outside of obstacle sets: project_set_convex (isls/projections.py:289-374) with
+// As = I, bs = 0 and per-set projections  p -> c + W^-1 Pi_sq(W (p - c))  on the position (project_square_batch,
+// projections.py:246-255; Car/Iterative LQR with state constraints.ipynb cell 18).  One problem per thread; all N rows
+// are projected together (the reference's stop rule is the maximum over sets and rows), so the inner ADMM sweeps the
+// rows once per iteration with z_k, lambda_k kept in the workspace.  Returns the number of inner iterations.
+__device__ __forceinline__ void obst_project_one(const Dev &d, int k, double (&y)[2]) {
+  const double c0 = d.ob_c[2 * k], c1 = d.ob_c[2 * k + 1];
+  const double *W = d.ob_W + 4 * k, *Wi = d.ob_Wi + 4 * k;
+  const double z0 = y[0] - c0, z1 = y[1] - c1;
+  double w0 = z0 * W[0] + z1 * W[1], w1 = z0 * W[2] + z1 * W[3];          // z @ W.T
+  const double lo = d.ob_lo[k], up = d.obst_upper;
+  const double a0 = fabs(w0), a1 = fabs(w1);
+  if (fmax(a0, a1) < lo) {                                                // np.argmax: first maximum
+    if (a0 >= a1) w0 = lo * ((w0 > 0.0) - (w0 < 0.0));
+    else w1 = lo * ((w1 > 0.0) - (w1 < 0.0));
+  }
+  w0 = fmax(fmin(w0, up), -up);
+  w1 = fmax(fmin(w1, up), -up);
+  y[0] = (w0 * Wi[0] + w1 * Wi[1]) + c0;                                  // zp @ W_inv.T + c
+  y[1] = (w0 * Wi[2] + w1 * Wi[3]) + c1;
+}
+
+template <class M>
+__device__ __forceinline__ int obst_project_rows(const Dev &d, const TileCtx<M> &c) {
+  constexpr int n = M::n;
+  const int K = d.n_obst, N = d.N;
+  const size_t arr = (size_t)d.T * N * n * TILE;                          // one [T][N][n][32] array
+  const double *pre = c.at(d.obw + arr, d, n);
+  double *xin = c.at(d.obw + 2 * arr, d, n);
+  const double rho = d.obst_rho;
+  const double inv = 1.0 / (1.0 + rho * K);                               // inv(I + rho sum A_i'A_i), A_i = I
+  double prim_ = 1e5, dual_ = 1e5;
+  int it = 0;
+  for (int j = 0; j < d.obst_max_iter; j++) {
+    it = j + 1;
+    double pmax = 0.0, dmax = 0.0;
+    for (int t = 0; t < N; t++) {
+      double x0[n], zk[ISLS_MAX_OBST][n], lk[ISLS_MAX_OBST][n], x[n];
+#pragma unroll
+      for (int i = 0; i < n; i++) x0[i] = EL(pre, n, t, i);
+      for (int k = 0; k < K; k++) {
+        const double *zp = c.at(d.obw + (3 + 2 * k) * arr, d, n), *lp = c.at(d.obw + (4 + 2 * k) * arr, d, n);
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+          zk[k][i] = j == 0 ? x0[i] : EL(zp, n, t, i);                    // z_i = A_i x0 + b_i, lambda_i = 0
+          lk[k][i] = j == 0 ? 0.0 : EL(lp, n, t, i);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < n; i++) {
+        double r = 0.0;
+        for (int k = 0; k < K; k++) r = r + (zk[k][i] - lk[k][i]);
+        x[i] = inv * (x0[i] + rho * r);
+        EL(xin, n, t, i) = x[i];
+      }
+      for (int k = 0; k < K; k++) {
+        double *zp = c.at(d.obw + (3 + 2 * k) * arr, d, n), *lp = c.at(d.obw + (4 + 2 * k) * arr, d, n);
+        double zn[n], y[2];
+#pragma unroll
+        for (int i = 0; i < n; i++) zn[i] = x[i] + lk[k][i];
+        y[0] = zn[0]; y[1] = zn[1];
+        obst_project_one(d, k, y);
+        zn[0] = y[0]; zn[1] = y[1];
+        double ps = 0.0, ds = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+          const double pr = x[i] - zn[i], du_ = rho * (zn[i] - zk[k][i]);
+          ps += pr * pr;
+          ds += du_ * du_;
+          EL(zp, n, t, i) = zn[i];
+          EL(lp, n, t, i) = lk[k][i] + pr;
+        }
+        pmax = fmax(pmax, sqrt(ps));
+        dmax = fmax(dmax, sqrt(ds));
+      }
+    }
+    const double pprim = prim_, pdual = dual_;
+    prim_ = pmax;
+    dual_ = dmax;
+    if (prim_ < d.obst_threshold && dual_ < d.obst_threshold) break;
+    if (j < d.obst_max_iter - 1) {
+      const double pc = fabs(pprim - prim_) / (pprim + 1e-30), dc = fabs(pdual - dual_) / (pdual + 1e-30);
+      if (pc < 1e-5 && dc < 1e-5) break;
+    }
+  }
+  return it;
+}
+
 // Winner rollout + ADMM update: re-roll the chosen candidate (the primal iterate (x,u) returned by f_argmin,
 // isls/isls.py:478; it is not stored - k_outer_end re-rolls the last one in place), apply the z-projection and scaled dual update element by element (admm.py:43-59), form the
 // residual norms (admm.py:62-69) and run the stop tests (admm.py:72-85).
@@ -1216,7 +1312,16 @@ __device__ __forceinline__ void admm_body(const Dev &d, const TileCtx<M> &c, int
         if (mku) mku[t * m + j] = (int8_t)mk;
       }
     }
-    if (d.proj_x) {
+    if (d.proj_x && d.n_obst > 0) {
+      // obstacle sets: park the winner state and the pre-projection point; the rows are projected together below
+      const size_t arr = (size_t)d.T * d.N * n * TILE;
+      double *xw = c.at(d.obw, d, n), *pre = c.at(d.obw + arr, d, n);
+#pragma unroll
+      for (int i = 0; i < n; i++) {
+        EL(xw, n, t, i) = x[i];
+        EL(pre, n, t, i) = __dadd_rn(__dadd_rn(__dmul_rn(d.relax, x[i]), __dmul_rn(__dsub_rn(1.0, d.relax), zxv[i])), lxv[i]);
+      }
+    } else if (d.proj_x) {
 #pragma unroll
       for (int i = 0; i < n; i++) {
         int mk;
@@ -1231,6 +1336,28 @@ __device__ __forceinline__ void admm_body(const Dev &d, const TileCtx<M> &c, int
     M::step(x, u, xn, d.dt);
 #pragma unroll
     for (int i = 0; i < n; i++) x[i] = xn[i];
+  }
+  if (d.proj_x && d.n_obst > 0) {
+    const int its = obst_project_rows<M>(d, c);
+    if (c.valid && d.out.inner_iters)
+      d.out.inner_iters[((size_t)c.ob * d.max_outer + outer) * d.max_admm + inner] = its;
+    const size_t arr = (size_t)d.T * d.N * n * TILE;
+    const double *xw = c.at(d.obw, d, n), *xin = c.at(d.obw + 2 * arr, d, n);
+    for (int t = 0; t < d.N; t++) {
+      double xv[n], zn[n], zo[n], lv[n];
+#pragma unroll
+      for (int i = 0; i < n; i++) { xv[i] = EL(xw, n, t, i); zn[i] = EL(xin, n, t, i); zo[i] = EL(zx, n, t, i); lv[i] = EL(lx, n, t, i); }
+#pragma unroll
+      for (int i = 0; i < n; i++) {                       // admm.py:49-59 with z = project_x(.)
+        const double r = __dsub_rn(xv[i], zn[i]), dz = __dsub_rn(zn[i], zo[i]);
+        lv[i] = __dadd_rn(lv[i], r);
+        prx = fma(r, r, prx);
+        drx = fma(dz, dz, drx);
+        EL(zx, n, t, i) = zn[i];
+        EL(lx, n, t, i) = lv[i];
+        EL(rgx, n, t, i) = __dsub_rn(zn[i], lv[i]);
+      }
+    }
   }
   d.cost_adm[c.b] = cs + d.u_std * cc;
   admm_finish<M>(d, c, outer, inner, bi, sqrt(prx) + sqrt(pru), sqrt(drx) + sqrt(dru));   // admm.py:62-69
@@ -2103,7 +2230,11 @@ extern "C" int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan)
   if (model_dims(desc->model_id, desc->n, desc->m, &nja)) return fail(ISLS_E_UNSUPPORTED, "unsupported (model, n, m)");
   if (desc->N < 2 || desc->n_via < 1 || desc->L < 1 || desc->L > MAX_L) return fail(ISLS_E_INVALID, "bad N / n_via / L");
   if (!desc->Qdiag || !desc->seq || !desc->alphas) return fail(ISLS_E_INVALID, "Qdiag/seq/alphas is NULL");
-  if (desc->rho_x && (!desc->lo_x || !desc->hi_x)) return fail(ISLS_E_INVALID, "rho_x without lo_x/hi_x");
+  if (desc->n_obst < 0 || desc->n_obst > ISLS_MAX_OBST) return fail(ISLS_E_INVALID, "n_obst out of range");
+  if (desc->n_obst > 0 && (!desc->rho_x || !desc->obst_centers || !desc->obst_W || !desc->obst_W_inv || !desc->obst_lower ||
+                           desc->obst_max_iter < 1 || desc->n < 2))
+    return fail(ISLS_E_INVALID, "obstacle sets need rho_x, centres, W, W_inv, lower and obst_max_iter >= 1");
+  if (desc->rho_x && !desc->n_obst && (!desc->lo_x || !desc->hi_x)) return fail(ISLS_E_INVALID, "rho_x without lo_x/hi_x");
   if (desc->rho_u && (!desc->lo_u || !desc->hi_u)) return fail(ISLS_E_INVALID, "rho_u without lo_u/hi_u");
   const int n = desc->n, m = desc->m, N = desc->N;
   for (int t = 0; t < N; t++)
@@ -2145,6 +2276,11 @@ extern "C" int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan)
          o_lx = push(desc->lo_x, (size_t)N * n, -inf), o_hx = push(desc->hi_x, (size_t)N * n, inf),
          o_ru = push(desc->rho_u, (size_t)N * m, 0.0), o_lu = push(desc->lo_u, (size_t)N * m, -inf),
          o_hu = push(desc->hi_u, (size_t)N * m, inf), o_al = push(desc->alphas, desc->L, 0.0);
+  size_t o_oc = 0, o_ow = 0, o_oi = 0, o_ol = 0;
+  if (desc->n_obst > 0) {
+    o_oc = push(desc->obst_centers, 2 * (size_t)desc->n_obst, 0.0); o_ow = push(desc->obst_W, 4 * (size_t)desc->n_obst, 0.0);
+    o_oi = push(desc->obst_W_inv, 4 * (size_t)desc->n_obst, 0.0); o_ol = push(desc->obst_lower, (size_t)desc->n_obst, 0.0);
+  }
   size_t o_hp = 0, o_q2 = 0, o_h2 = 0;
   if (huber) { o_hp = push(hp.data(), (size_t)N * n, 1.0); o_q2 = push(qd2.data(), (size_t)N * n, 0.0); o_h2 = push(hp2.data(), (size_t)N * n, 1.0); }
   size_t dbytes = h.size() * sizeof(double), ibytes = al256(2 * (size_t)N * sizeof(int));
@@ -2169,6 +2305,9 @@ extern "C" int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan)
     for (int j = 0; j < m; j++) d.Rw[j] = desc->Rdiag[j] / desc->Rdiag[0];
   }
   if (huber) { d.hp = cb + o_hp; d.qd2 = cb + o_q2; d.hp2 = cb + o_h2; }
+  d.n_obst = desc->n_obst; d.obst_max_iter = desc->obst_max_iter;
+  d.obst_upper = desc->obst_upper; d.obst_rho = desc->obst_rho; d.obst_threshold = desc->obst_threshold;
+  if (desc->n_obst > 0) { d.ob_c = cb + o_oc; d.ob_W = cb + o_ow; d.ob_Wi = cb + o_oi; d.ob_lo = cb + o_ol; }
   d.qd = cb + o_qd; d.rho_x = cb + o_rx; d.lo_x = cb + o_lx; d.hi_x = cb + o_hx;
   d.rho_u = cb + o_ru; d.lo_u = cb + o_lu; d.hi_u = cb + o_hu; d.alphas = cb + o_al;
   d.seq = ib; d.qnz = ib + N;
@@ -2214,6 +2353,7 @@ static size_t carve(const isls_plan *p, long long B, char *base, Dev *d, Dev *al
   takeD(d ? &d->kk : nullptr, tm);
   takeD(d ? &d->zs : nullptr, T * p->n_via * n * TILE);
   takeD(d ? &d->lsc : nullptr, T * p->L * TILE);
+  takeD(d ? &d->obw : nullptr, p->desc.n_obst > 0 ? (3 + 2 * (size_t)p->desc.n_obst) * tn : 0);
   const size_t S = T * TILE;
   takeD(d ? &d->cost : nullptr, S); takeD(d ? &d->prev_cost : nullptr, S); takeD(d ? &d->prim : nullptr, S);
   takeD(d ? &d->dual : nullptr, S); takeD(d ? &d->cost_adm : nullptr, S); takeD(d ? &d->best_cost : nullptr, S);
@@ -2449,6 +2589,7 @@ extern "C" int isls_ilqr_solve_f64(const isls_plan *plan, const isls_solve_opts 
   d.out.res_log = nullptr;
   d.out.admm_iters = nullptr;
   d.out.admm_exit = nullptr;
+  d.out.inner_iters = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   return dispatch_model(plan, [&](auto model) -> int {
     using M = decltype(model);
@@ -2482,6 +2623,8 @@ extern "C" int isls_lqt_admm_dp_f64(const isls_plan *plan, const isls_solve_opts
     return fail(ISLS_E_UNSUPPORTED, "LQT-ADMM needs a linear model (double_integrator)");
   if (plan && plan->desc.cost_kind != ISLS_COST_QUADRATIC)
     return fail(ISLS_E_UNSUPPORTED, "LQT-ADMM needs the quadratic via-point cost");
+  if (plan && plan->desc.n_obst > 0)
+    return fail(ISLS_E_UNSUPPORTED, "obstacle-set state projections are implemented for iLQR-ADMM only");
   if (opts->max_admm < 1) return fail(ISLS_E_INVALID, "max_admm must be >= 1");
   Dev d;
   isls_solve_opts o = *opts;

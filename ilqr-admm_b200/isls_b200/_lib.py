@@ -19,7 +19,10 @@ class ProblemDesc(C.Structure):
                 ("rho_x", C.c_void_p), ("lo_x", C.c_void_p), ("hi_x", C.c_void_p),
                 ("rho_u", C.c_void_p), ("lo_u", C.c_void_p), ("hi_u", C.c_void_p),
                 ("cost_kind", C.c_int32), ("Rdiag", C.c_void_p), ("Hp", C.c_void_p), ("Qdiag_b", C.c_void_p),
-                ("Hp_b", C.c_void_p)]
+                ("Hp_b", C.c_void_p), ("n_obst", C.c_int32), ("obst_max_iter", C.c_int32),
+                ("obst_centers", C.c_void_p), ("obst_W", C.c_void_p), ("obst_W_inv", C.c_void_p),
+                ("obst_lower", C.c_void_p), ("obst_upper", C.c_double), ("obst_rho", C.c_double),
+                ("obst_threshold", C.c_double)]
 
 
 class SolveOpts(C.Structure):
@@ -28,7 +31,7 @@ class SolveOpts(C.Structure):
 
 
 OUT_FIELDS = ["x", "u", "cost", "cost_log", "n_log", "status", "outer_iters", "admm_iters", "admm_exit", "res_log",
-              "alpha_idx", "z_x", "z_u", "lam_x", "lam_u", "K", "k", "mask_x", "mask_u"]
+              "alpha_idx", "z_x", "z_u", "lam_x", "lam_u", "K", "k", "mask_x", "mask_u", "inner_iters"]
 
 
 class SlsAdmmOpts(C.Structure):

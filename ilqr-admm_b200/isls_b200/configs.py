@@ -130,3 +130,35 @@ def tassa_batch(B, N=150, dt=0.03, seed=_seed(6), I_o=50, I_a=5, L=40, tol=1e-3)
                 Rdiag=1e-2 * np.array([1.0, 0.01]), u_std=1e-2, x0=x0, u0=u0,
                 lo_u=lo_u, hi_u=-lo_u, lo_x=None, hi_x=None,
                 rho_u=np.tile(np.array([1e-1, 1e-2]), (N, 1)), rho_x=None, I_o=I_o, I_a=I_a, L=L, tol=tol, alpha=1.0)
+
+
+def parking_batch(B, N=500, dt=0.03, seed=_seed(7), I_o=10, I_a=10, L=50, tol=1e-1):
+    """Parking between two parked cars: iLQR-ADMM with a STATE projection onto the outside of two rotated rectangles
+    (notebooks/Car/Iterative LQR with state constraints.ipynb cells 4-20; README animation_state_bounds.gif).
+    Problem 0 is the notebook's x0 = (0, -2, pi/2, 0)."""
+    rng = np.random.default_rng(seed)
+    n, m = 4, 2
+    # start states: the notebook's, then four behind / beside the parked cars (their paths cross the obstacle sets, so
+    # the inner projection ADMM really iterates), then seeded perturbations of those five
+    anchors = np.array([[0.0, -2.0, np.pi / 2, 0.0], [-9.0, -1.0, -np.pi / 2, 0.0], [-1.0, -9.0, np.pi, 0.0],
+                        [-10.0, -4.0, 0.0, 0.0], [-2.0, -10.0, np.pi / 2, 0.0]])
+    x0 = anchors[np.arange(B) % 5].copy()
+    if B > 5:
+        x0[5:, :2] += rng.uniform(-0.4, 0.4, (B - 5, 2))
+        x0[5:, 2] += rng.uniform(-0.3, 0.3, B - 5)
+    zs = np.stack([np.zeros(n), np.array([-5.0, -5.0, np.pi / 4, 0.0])])
+    Qdiag = np.stack([np.zeros(n), np.full(n, 1e2)])
+    seq = np.zeros(N, dtype=np.int32)
+    seq[-1] = 1
+    a_safe = np.array([[2.0, 1.0], [2.0, 1.0]]) + 0.5                   # cell 18
+    Ws = np.stack([np.diag(a_safe[i, 0] / a_safe[i]) for i in range(2)])
+    al = -np.pi / 4
+    Rm = np.array([[np.cos(al), -np.sin(al)], [np.sin(al), np.cos(al)]])
+    Ws = Ws @ Rm.T
+    rho_x = np.zeros((N, n))
+    rho_x[:, :2] = 1e-1
+    obstacles = dict(kind="square", centers=np.array([[-7.0, -3.0], [-3.0, -7.0]]), W=Ws, W_inv=np.linalg.inv(Ws),
+                     lower=a_safe[:, 0] / 2, upper=1e5, rho=1e1, max_iter=15, threshold=1e-3)
+    return dict(name="parking", model="car", dt=dt, N=N, n=n, m=m, zs=zs, Qdiag=Qdiag, seq=seq, u_std=1e-2,
+                x0=x0, u0=np.zeros((N, m)), lo_u=None, hi_u=None, lo_x=None, hi_x=None, rho_u=None, rho_x=rho_x,
+                obstacles=obstacles, I_o=I_o, I_a=I_a, L=L, tol=tol, alpha=1.0)

@@ -8,7 +8,7 @@ import torch
 
 from . import solver as S
 from ._lib import IslsError
-from .projections import Bound
+from .projections import Bound, ObstacleSets
 from .utils import diag_of
 
 _MODEL_NAMES = ("car", "arm3", "double_integrator", "tassa_car")
@@ -198,17 +198,19 @@ class iSLS:
         zs = torch.as_tensor(self.zs)
         return zs.expand(self.nb, zs.shape[-2], self.x_dim)
 
-    def _solver(self, L, rho_x, bx, rho_u, bu, max_outer, max_admm, want_gains=False, want_masks=False):
+    def _solver(self, L, rho_x, bx, rho_u, bu, max_outer, max_admm, want_gains=False, want_masks=False,
+                obstacles=None):
         if self._model is None or self.zs is None:
             raise IslsError("set forward_model and a cost (set_quadratic_cost / cost_function) first")
         key = (L, None if rho_x is None else rho_x.tobytes(), None if bx is None else (bx[0].tobytes(), bx[1].tobytes()),
                None if rho_u is None else rho_u.tobytes(), None if bu is None else (bu[0].tobytes(), bu[1].tobytes()),
-               max_outer, max_admm, want_gains, want_masks)
+               max_outer, max_admm, want_gains, want_masks, None if obstacles is None else obstacles.key())
         if key not in self._plan_cache:
             plan = S.Plan(self._model, self.N, self.x_dim, self.u_dim, self._dt(), self.Qdiag, self.seq, self.u_std,
                           L, rho_x=rho_x, lo_x=None if bx is None else bx[0], hi_x=None if bx is None else bx[1],
                           rho_u=rho_u, lo_u=None if bu is None else bu[0], hi_u=None if bu is None else bu[1],
-                          cost=self._cost, **self._cost_kw)
+                          cost=self._cost, obstacles=None if obstacles is None else obstacles.as_dict(),
+                          **self._cost_kw)
             self._plan_cache.clear()
             self._plan_cache[key] = S.BatchSolver(plan, self.nb, self.device, max_outer=max_outer, max_admm=max_admm,
                                                   want_gains=want_gains, want_masks=want_masks)
@@ -270,16 +272,18 @@ class iSLS:
             tol = threshold
         self._check_get_AB(get_AB)
         self._check_get_Cs(get_Cs)
+        obstacles = project_x if isinstance(project_x, ObstacleSets) else None
         for nm, pr in (("project_x", project_x), ("project_u", project_u)):
-            if pr and not isinstance(pr, Bound):
-                raise TypeError("%s must be an isls_b200.projections.Bound (box bounds); Python callables cannot run "
-                                "inside the kernels" % nm)
+            if pr and not isinstance(pr, Bound) and not (nm == "project_x" and obstacles is not None):
+                raise TypeError("%s must be an isls_b200.projections.Bound (box bounds) or, for project_x, ObstacleSets; "
+                                "Python callables cannot run inside the kernels" % nm)
         Qr, Rr = self.compute_Rr_Qr(rho_x if project_x else None, rho_u if project_u else None)
         if project_x and Qr is None or project_u and Rr is None:
             raise ValueError("rho_x / rho_u is required for a projected variable")
-        bx = project_x.expand(self.N, self.x_dim) if project_x else None
+        bx = project_x.expand(self.N, self.x_dim) if project_x and obstacles is None else None
         bu = project_u.expand(self.N, self.u_dim) if project_u else None
-        sv = self._solver(max_line_search_iter, Qr, bx, Rr, bu, max_iter, max_admm_iter, want_masks=want_masks)
+        sv = self._solver(max_line_search_iter, Qr, bx, Rr, bu, max_iter, max_admm_iter, want_masks=want_masks,
+                          obstacles=obstacles)
         sv.set_inputs(self._x0, self._u_init, self._zs_b())
         out = sv.ilqr_admm(tol=tol, relax=float(alpha), fixed_budget=fixed_budget)
         self._publish(out)

@@ -108,3 +108,26 @@ def project_square_batch(x, l, u, center=None):
 def project_unit_ball_batch(x):
     """isls/projections.py:232-240 row-wise."""
     return _rows(5, x)
+
+
+class ObstacleSets:
+    """Device descriptor of the notebooks' obstacle-avoidance state projection (Car/Iterative LQR with state
+    constraints.ipynb cell 18): `project_set_convex(x, [I]*K, [0]*K, projections, rho, max_iter, threshold)` where
+    projection k maps the position p = x[:2] of every time step to  c_k + W_k^-1 Pi_sq(W_k (p - c_k))  with
+    Pi_sq = project_square_batch(., lower_k, upper) (isls/projections.py:246-255, 289-374).  Pass it as `project_x`."""
+
+    def __init__(self, centers, W, lower, upper=1e5, rho=1e1, max_iter=15, threshold=1e-3):
+        self.centers = np.asarray(centers, dtype=np.float64).reshape(-1, 2)
+        K = self.centers.shape[0]
+        self.W = np.asarray(W, dtype=np.float64).reshape(K, 2, 2)
+        self.W_inv = np.linalg.inv(self.W)
+        self.lower = np.asarray(lower, dtype=np.float64).reshape(K)
+        self.upper, self.rho, self.max_iter, self.threshold = float(upper), float(rho), int(max_iter), float(threshold)
+
+    def as_dict(self):
+        return dict(kind="square", centers=self.centers, W=self.W, W_inv=self.W_inv, lower=self.lower, upper=self.upper,
+                    rho=self.rho, max_iter=self.max_iter, threshold=self.threshold)
+
+    def key(self):
+        return (self.centers.tobytes(), self.W.tobytes(), self.lower.tobytes(), self.upper, self.rho, self.max_iter,
+                self.threshold)

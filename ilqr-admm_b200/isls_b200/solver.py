@@ -42,7 +42,7 @@ class Plan:
     diagonal ADMM penalties and box bounds."""
 
     def __init__(self, model, N, n, m, dt, Qdiag, seq, u_std, L, rho_x=None, lo_x=None, hi_x=None, rho_u=None,
-                 lo_u=None, hi_u=None, cost="quadratic", Rdiag=None, Hp=None, Qdiag_b=None, Hp_b=None):
+                 lo_u=None, hi_u=None, cost="quadratic", Rdiag=None, Hp=None, Qdiag_b=None, Hp_b=None, obstacles=None):
         """cost="pseudo_huber": Qdiag / Hp are the weights and smoothness scales [n_via, n] of the first term,
         Qdiag_b / Hp_b of the optional second one (Tutorial cell 14); Rdiag [m] replaces R = u_std I."""
         L_ = _lib.lib()
@@ -56,7 +56,11 @@ class Plan:
                     alphas=alphas(L))
         self.proj_x = rho_x is not None
         self.proj_u = rho_u is not None
-        if self.proj_x:
+        if obstacles is not None and not self.proj_x:
+            raise _lib.IslsError("obstacle sets are a state projection: rho_x is required")
+        if self.proj_x and obstacles is not None:
+            keep.update(rho_x=_f64(rho_x, (N, n)))
+        elif self.proj_x:
             keep.update(rho_x=_f64(rho_x, (N, n)), lo_x=_f64(-np.inf if lo_x is None else lo_x, (N, n)),
                         hi_x=_f64(np.inf if hi_x is None else hi_x, (N, n)))
         if self.proj_u:
@@ -71,6 +75,15 @@ class Plan:
                 keep[nm] = _f64(arr, shp)
         d = _lib.ProblemDesc(model_id=mid, n=n, m=m, N=N, n_via=self.n_via, L=L, dt=dt, u_std=float(u_std),
                              cost_kind=COST_KINDS[cost])
+        if obstacles is not None:
+            ob = obstacles
+            K = len(ob["centers"])
+            keep.update(obst_centers=_f64(ob["centers"], (K, 2)), obst_W=_f64(ob["W"], (K, 2, 2)),
+                        obst_W_inv=_f64(ob["W_inv"], (K, 2, 2)), obst_lower=_f64(ob["lower"], (K,)))
+            d.n_obst, d.obst_max_iter = K, int(ob["max_iter"])
+            d.obst_upper, d.obst_rho, d.obst_threshold = float(ob["upper"]), float(ob["rho"]), float(ob["threshold"])
+            for k in ("obst_centers", "obst_W", "obst_W_inv", "obst_lower"):
+                setattr(d, k, _ptr(keep[k]))
         for k in ("Qdiag", "seq", "alphas", "rho_x", "lo_x", "hi_x", "rho_u", "lo_u", "hi_u", "Rdiag", "Hp", "Qdiag_b",
                   "Hp_b"):
             setattr(d, k, _ptr(keep.get(k)))
@@ -126,6 +139,7 @@ class BatchSolver:
                      admm_exit=torch.empty(B_, self.max_outer, **i32),
                      res_log=torch.empty(B_, self.max_outer, max(self.max_admm, 1), 2, **f64),
                      alpha_idx=torch.empty(B_, self.max_outer, max(self.max_admm, 1), **i32),
+                     inner_iters=torch.empty(B_, self.max_outer, max(self.max_admm, 1), **i32),
                      z_x=torch.empty(B_, N, n, **f64), z_u=torch.empty(B_, N, m, **f64),
                      lam_x=torch.empty(B_, N, n, **f64), lam_u=torch.empty(B_, N, m, **f64))
         if want_gains:

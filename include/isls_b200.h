@@ -84,7 +84,21 @@ typedef struct isls_problem_desc {
   const double *Hp;      /* [n_via, n] smoothness scales p of term a (PSEUDO_HUBER) */
   const double *Qdiag_b; /* [n_via, n] weights of the second term per component or NULL */
   const double *Hp_b;    /* [n_via, n] smoothness scales of the second term */
+  /* ---- optional state projection onto the outside of obstacle sets instead of the box lo_x / hi_x (rho_x still
+   * required): project_set_convex (isls/projections.py:289-374) with As = I, bs = 0 over n_obst sets, each the
+   * infinity-norm shell lower_k <= ||W_k (p - c_k)||_inf <= upper of the position p = x[:2]
+   * (project_square_batch, isls/projections.py:246-255; notebooks/Car/Iterative LQR with state constraints.ipynb
+   * cell 18).  All rows (time steps) of a problem are projected together: the inner ADMM stops on the maximum of the
+   * residual norms over sets and rows. ---- */
+  int32_t n_obst;              /* 0: box projection; 1..ISLS_MAX_OBST */
+  int32_t obst_max_iter;       /* max_iter of the inner ADMM */
+  const double *obst_centers;  /* [n_obst, 2] */
+  const double *obst_W;        /* [n_obst, 2, 2] row-major */
+  const double *obst_W_inv;    /* [n_obst, 2, 2] */
+  const double *obst_lower;    /* [n_obst] */
+  double obst_upper, obst_rho, obst_threshold;
 } isls_problem_desc;
+#define ISLS_MAX_OBST 4
 
 typedef struct isls_plan isls_plan;   /* opaque */
 
@@ -119,6 +133,8 @@ typedef struct isls_solve_out {
   double *K;            /* [B, N, m, n] optional: feedback gains of the last backward pass */
   double *k;            /* [B, N, m] optional: feed-forward gains of the last backward pass */
   int8_t *mask_x, *mask_u; /* [B, N, dim] optional: clip mask of the last projection (-1 at lo, +1 at hi) */
+  int32_t *inner_iters; /* [B, max_outer, max_admm] optional: iterations of the inner project_set_convex ADMM
+                           (obstacle-set state projection only) */
 } isls_solve_out;
 
 int isls_version(void);

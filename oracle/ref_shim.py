@@ -220,3 +220,47 @@ def run_tutorial_admm(s, model, p):
                           rho_u=np.diag(p["rho_u"][0]), tol=p["tol"], verbose=False, log=True)   # Tutorial cell 27
     return dict(x=s.x_nom.copy(), u=s.u_nom.copy(), cost_log=np.array(s.cost_log, dtype=np.float64),
                 admm_log=np.array(log, dtype=np.float64))
+
+
+# ------------------------------------------------------- parking between two cars (state constraints, obstacle sets)
+def parking_project_state(p):
+    """The notebook's project_state closure (Car/Iterative LQR with state constraints.ipynb cell 18), built from the
+    reference's own project_set_convex / project_square_batch: the position must stay outside two rotated rectangles
+    (infinity-norm shells in the frame W_i around the parked cars)."""
+    load()
+    from isls.projections import project_set_convex, project_square_batch
+    ob = p["obstacles"]
+    N, d = p["N"], p["n"]
+    Ws, Ws_inv, xs_ = ob["W"], ob["W_inv"], ob["centers"]
+    lower_sq, upper_sq = ob["lower"], ob["upper"]
+
+    def make_function(i):
+        def f(y):
+            y_ = y.reshape(N, d).copy()
+            z = y_[:, :2] - xs_[i][None]
+            z_projected = project_square_batch(z @ Ws[i].T, lower_sq[i], upper_sq)
+            z_projected = z_projected @ Ws_inv[i].T
+            y_[:, :2] = z_projected + xs_[i][None]
+            return y_
+        return f
+
+    projections = [make_function(i) for i in range(len(xs_))]
+    As = [np.eye(d)] * len(xs_)
+    bs = [np.zeros(d)] * len(xs_)
+
+    def project_state(x):
+        x_ = x.reshape(N, d).copy()
+        return project_set_convex(x_, As, bs, projections, rho=ob["rho"], max_iter=ob["max_iter"], verbose=0,
+                                  threshold=ob["threshold"]).flatten()
+    return project_state
+
+
+def run_parking(p, b=0):
+    """Shimmed HEAD ilqr_admm on the parking problem (cell 20: state projection only)."""
+    from . import models as M
+    model = M.make_model("car", dt=p["dt"])
+    s = make_isls(model, p["N"], p["zs"], np.stack([np.diag(q) for q in p["Qdiag"]]), p["seq"], p["u_std"])
+    init_nominal(s, p["x0"][b], p["u0"])
+    rho_x = np.stack([np.diag(r) for r in p["rho_x"]])
+    return run_ilqr_admm(s, model, project_x=parking_project_state(p), rho_x=rho_x, max_iter=p["I_o"],
+                         max_admm_iter=p["I_a"], max_line_search_iter=p["L"], tol=p["tol"])

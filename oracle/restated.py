@@ -340,6 +340,73 @@ def ilqr_dp(p, max_iter=100, L=25, tol_fun=1e-5, fixed_budget=False):
                 alpha_idx=alpha_idx, K=K_out, k=k_out)
 
 
+# ------------------------------------------------------------------------- state projection onto obstacle sets
+def project_square_batch(x, l, u):
+    """isls/projections.py:246-255: rows of x onto l <= ||x||_inf <= u (only the largest component is pushed out)."""
+    z = x.copy()
+    j = np.argmax(np.abs(x), axis=-1)
+    inside = np.max(np.abs(x), axis=-1) < l
+    r = np.nonzero(inside)[0]
+    z[r, j[r]] = l * np.sign(x[r, j[r]])
+    return np.maximum(np.minimum(z, u), -u)
+
+
+def obstacle_projections(ob):
+    """The per-set projections of the parking notebook (Car/Iterative LQR with state constraints.ipynb cell 18):
+    rows y[:, :2] -> centre + W^-1 Pi_square(W (y - centre)); other components untouched."""
+    def make(i):
+        W, Wi, c = ob["W"][i], ob["W_inv"][i], ob["centers"][i]
+
+        def f(y):
+            y_ = y.copy()
+            z = y_[:, :2] - c[None]
+            zp = project_square_batch(z @ W.T, ob["lower"][i], ob["upper"])
+            y_[:, :2] = zp @ Wi.T + c[None]
+            return y_
+        return f
+    return [make(i) for i in range(len(ob["centers"]))]
+
+
+def project_set_convex_rows(x0, projections, rho, max_iter, threshold):
+    """isls/projections.py:289-374 for As = I, bs = 0 (what both obstacle notebooks pass): consensus ADMM over the
+    sets, rows of x0 [rows, dim] projected together, stop on the MAX over sets and rows of the residual norms (< threshold),
+    or when both maxima change by < 1e-5 relative, or after max_iter.  Returns (x [rows, dim], iterations)."""
+    K = len(projections)
+    dim = x0.shape[-1]
+    x = x0.T.copy()
+    z = [x.copy() for _ in range(K)]
+    lmb = [np.zeros_like(x) for _ in range(K)]
+    l_side_inv = np.linalg.inv(np.eye(dim) + rho * K * np.eye(dim))
+    prim_ = dual_ = 1e5
+    it = 0
+    for j in range(max_iter):
+        it = j + 1
+        r_side = 0.0
+        for i in range(K):
+            r_side = r_side + (z[i] - lmb[i])
+        x = l_side_inv @ (x0.T + rho * r_side)
+        z_prev = [zi for zi in z]
+        pprim, pdual = prim_, dual_
+        pn = np.zeros((K, x.shape[1]))
+        dn = np.zeros((K, x.shape[1]))
+        for i in range(K):
+            z[i] = projections[i]((x + lmb[i]).T).T
+            prim = x - z[i]
+            dual = rho * (z[i] - z_prev[i])
+            lmb[i] = lmb[i] + prim
+            pn[i] = np.linalg.norm(prim, axis=0)
+            dn[i] = np.linalg.norm(dual, axis=0)
+        prim_, dual_ = np.max(pn), np.max(dn)
+        if prim_ < threshold and dual_ < threshold:
+            break
+        if j < max_iter - 1:
+            pc = np.abs(pprim - prim_) / (pprim + 1e-30)
+            dc = np.abs(pdual - dual_) / (pdual + 1e-30)
+            if pc < 1e-5 and dc < 1e-5:
+                break
+    return x.T, it
+
+
 # ----------------------------------------------------------------------------------------------- iLQR-ADMM
 def ilqr_admm(p, fixed_budget=False, outer_tol=1e-3, keep_trace=False):
     """Riccati-form restatement of iSLS.ilqr_admm (isls.py:379-501) + ADMM (admm.py:6-106) with box projections.
@@ -357,7 +424,10 @@ def ilqr_admm(p, fixed_budget=False, outer_tol=1e-3, keep_trace=False):
     R = _R(p)                                                                 # [m] diagonal of R
     quadratic = p.get("cost", "quadratic") == "quadratic"
     bx, bu = _bounds(p, "x", N, n), _bounds(p, "u", N, m)
-    proj_x, proj_u = bx is not None, bu is not None
+    obst = p.get("obstacles")
+    obst_proj = obstacle_projections(obst) if obst is not None else None
+    inner_log = np.zeros((B, I_o, I_a), dtype=np.int32) if obst is not None else None
+    proj_x, proj_u = bx is not None or obst is not None, bu is not None
     rho_x = np.broadcast_to(np.asarray(p["rho_x"], float), (N, n)) if proj_x else np.zeros((N, n))
     rho_u = np.broadcast_to(np.asarray(p["rho_u"], float), (N, m)) if proj_u else np.zeros((N, m))
     al = alphas(L)
@@ -440,8 +510,14 @@ def ilqr_admm(p, fixed_budget=False, outer_tol=1e-3, keep_trace=False):
             if proj_x:
                 zprev = zx[ia]
                 pre = relax * xx + (1.0 - relax) * zprev + lx[ia]
-                znew = np.clip(pre, bx[0], bx[1])                             # projections.py:7-11
-                mask_x[g] = (pre > bx[1]).astype(np.int8) - (pre < bx[0]).astype(np.int8)
+                if obst is not None:                                          # project_set_convex over the obstacle sets
+                    znew = np.empty_like(pre)
+                    for q in range(ia.size):
+                        znew[q], inner_log[g[q], j, a] = project_set_convex_rows(
+                            pre[q], obst_proj, obst["rho"], obst["max_iter"], obst["threshold"])
+                else:
+                    znew = np.clip(pre, bx[0], bx[1])                         # projections.py:7-11
+                    mask_x[g] = (pre > bx[1]).astype(np.int8) - (pre < bx[0]).astype(np.int8)
                 r = xx - znew
                 lx[ia] = lx[ia] + r
                 zx[ia] = znew
@@ -500,6 +576,8 @@ def ilqr_admm(p, fixed_budget=False, outer_tol=1e-3, keep_trace=False):
     out = dict(x=x_nom, u=u_nom, cost=cost, cost_log=cost_log, n_log=n_log, status=status,
                outer_iters=outer_iters, admm_iters=admm_iters, admm_exit=admm_exit, res_log=res_log,
                alpha_idx=alpha_idx, z_x=z_x, z_u=z_u, lam_x=lam_x, lam_u=lam_u, mask_x=mask_x, mask_u=mask_u)
+    if inner_log is not None:
+        out["inner_iters"] = inner_log
     if keep_trace:
         out["trace"] = trace
     return out

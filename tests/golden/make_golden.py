@@ -266,6 +266,32 @@ def golden_tutorial(B=3, N=150):
     np.savez_compressed(os.path.join(OUT, "tutorial_tassa.npz"), x0=p["x0"], u0=p["u0"], N=N, **out)
 
 
+def golden_parking():
+    """Parking between two cars (state projection onto obstacle sets): (a) the notebook configuration N=500, dt=0.03
+    (known answer: first iterate 2564.0110889491493, Car/Iterative LQR with state constraints.ipynb cell 20 output),
+    (b) five start states at N=200 whose paths cross the obstacles, (c) the reference's project_state closure on
+    random trajectories."""
+    out = {}
+    p = P.parking_batch(1)
+    r = S.run_parking(p, 0)
+    out.update(nb_cost_log=r["cost_log"], nb_x=r["x"], nb_u=r["u"])
+    print("parking notebook", r["cost_log"])
+    p = P.parking_batch(5, N=200, dt=0.075)
+    xs, us, logs = [], [], []
+    for b in range(5):
+        r = S.run_parking(p, b)
+        xs.append(r["x"]); us.append(r["u"]); logs.append(r["cost_log"])
+        print("parking", b, len(r["cost_log"]), r["cost_log"][-1])
+    out.update(x=np.stack(xs), u=np.stack(us), cost_log=_pad(logs), x0=p["x0"])
+    rng = np.random.default_rng(77)
+    proj = S.parking_project_state(p)
+    pts = np.zeros((6, 200, 4))
+    pts[:, :, :2] = rng.uniform(-10.0, 0.0, (6, 200, 2))
+    pts[:, :, 2:] = rng.normal(0, 1, (6, 200, 2))
+    out.update(proj_in=pts, proj_out=np.stack([proj(q.flatten()).reshape(200, 4) for q in pts]))
+    np.savez_compressed(os.path.join(OUT, "parking_obstacles.npz"), **out)
+
+
 if __name__ == "__main__":
     assert S.available(), "needs the reference tree"
     only = set(sys.argv[1:])                       # e.g. `make_golden.py tutorial` regenerates one fixture family
@@ -288,3 +314,5 @@ if __name__ == "__main__":
         golden_mc()
     if want("tutorial"):
         golden_tutorial()
+    if want("parking"):
+        golden_parking()

@@ -21,6 +21,12 @@ def make_isls(p, device="cuda:0"):
 def run_ilqr_admm(p, fixed_budget=False, want_masks=True, device="cuda:0"):
     s = make_isls(p, device)
     kw = {}
+    if p.get("obstacles") is not None:
+        from isls_b200 import ObstacleSets
+        ob = p["obstacles"]
+        kw.update(project_x=ObstacleSets(ob["centers"], ob["W"], ob["lower"], ob["upper"], ob["rho"], ob["max_iter"],
+                                         ob["threshold"]), rho_x=p["rho_x"])
+        want_masks = False
     if p.get("lo_x") is not None:
         kw.update(project_x=Bound(p["lo_x"], p["hi_x"]), rho_x=p["rho_x"])
     if p.get("lo_u") is not None:
