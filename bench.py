@@ -315,7 +315,9 @@ def run_b200(a):
                                   "fp64": {"algorithmic_flop_per_launch": kp_flops,
                                            "achieved_tflops": round(kp_flops / t / 1e12, 3),
                                            "frac_of_dfma_peak": round(kp_flops / t / 1e12 / fp64_peak, 4)},
-                                  "passes_per_s": round(B / t, 1)}
+                                  "passes_per_s": round(B / t, 1),
+                                  # dram bytes read + written of one launch, profiles/r1_ncu_kpass_ff.csv
+                                  "traffic": round(1671.1e6 * B / 65536.0)}
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
