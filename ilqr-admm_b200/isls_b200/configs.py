@@ -162,3 +162,37 @@ def parking_batch(B, N=500, dt=0.03, seed=_seed(7), I_o=10, I_a=10, L=50, tol=1e
     return dict(name="parking", model="car", dt=dt, N=N, n=n, m=m, zs=zs, Qdiag=Qdiag, seq=seq, u_std=1e-2,
                 x0=x0, u0=np.zeros((N, m)), lo_u=None, hi_u=None, lo_x=None, hi_x=None, rho_u=None, rho_x=rho_x,
                 obstacles=obstacles, I_o=I_o, I_a=I_a, L=L, tol=tol, alpha=1.0)
+
+
+def arm_robust_batch(B, N=100, dt=0.01, seed=_seed(8), I_o=50, I_a=10, L=30, tol=1e-4, var_x0=0.1, prob=0.82):
+    """Robust iSLS-ADMM on the planar 3-DoF arm (notebooks/3DoF robot/State bounds and robust control bounds.ipynb
+    cells 12-26): reach final_pos = (1.5, 2, 0) with |u| <= 6 holding with probability `prob` under N(0, var_x0)
+    perturbations of the initial joint positions; columns [d_u | Phi_u(:, :3)].  Problem 0 is the notebook's q0."""
+    from scipy.stats import norm
+    rng = np.random.default_rng(seed)
+    n, m = 9, 3
+    q0 = np.tile(np.array([np.pi / 3, -np.pi / 2, -np.pi / 4]), (B, 1))
+    if B > 1:
+        q0[1:] += rng.normal(0.0, 0.1, (B - 1, 3))
+    a1 = q0[:, 0]
+    a2 = a1 + q0[:, 1]
+    a3 = a2 + q0[:, 2]
+    fk = np.stack([np.cos(a1) + np.cos(a2) + np.cos(a3), np.sin(a1) + np.sin(a2) + np.sin(a3), np.zeros(B)], -1)
+    x0 = np.concatenate([q0, np.zeros_like(q0), fk], axis=-1)
+    zs = np.stack([np.zeros(n), np.array([0, 0, 0, 0, 0, 0, 1.5, 2.0, 0.0])])
+    Qdiag = np.stack([np.zeros(n), np.array([0, 0, 0, 1e3, 1e3, 1e3, 1e3, 1e3, 0.0])])       # cell 12
+    seq = np.zeros(N, dtype=np.int32)
+    seq[-1] = 1
+    dim = 3
+    mu = np.zeros(1 + dim)
+    mu[0] = 1.0
+    sigma = np.zeros(1 + dim)
+    sigma[1:] = var_x0
+    psi_inv = norm.ppf(prob)
+    Au = np.diag(np.sqrt(sigma))
+    As = [np.concatenate([Au, (-mu / psi_inv)[None]], axis=0), np.concatenate([Au, (mu / psi_inv)[None]], axis=0)]
+    bs = [np.append(np.zeros(1 + dim), 6.0 / psi_inv), np.append(np.zeros(1 + dim), 6.0 / psi_inv)]
+    robust = dict(dim=dim, As=As, bs=bs, rho_u=1.0, inner_rho=1e1, inner_max_iter=100, inner_threshold=1e-4)
+    return dict(name="arm3_robust", model="arm3", dt=dt, N=N, n=n, m=m, zs=zs, Qdiag=Qdiag, seq=seq, u_std=1e-4,
+                x0=x0, u0=np.zeros((N, m)), lo_u=None, hi_u=None, lo_x=None, hi_x=None, rho_u=None, rho_x=None,
+                robust=robust, I_o=I_o, I_a=I_a, L=L, tol=tol, alpha=1.0)

@@ -264,3 +264,45 @@ def run_parking(p, b=0):
     rho_x = np.stack([np.diag(r) for r in p["rho_x"]])
     return run_ilqr_admm(s, model, project_x=parking_project_state(p), rho_x=rho_x, max_iter=p["I_o"],
                          max_admm_iter=p["I_a"], max_line_search_iter=p["L"], tol=p["tol"])
+
+
+# ------------------------------------------------------------ robust iSLS-ADMM (3-DoF arm, chance-constrained controls)
+def soc_chance_cones(dim, var_x0, prob, lower_u, upper_u):
+    """The A_, b_ of `3DoF robot/State bounds and robust control bounds.ipynb` cell 24 (b_ as in `Double
+    integrator/LQR and SLS with control bounds.ipynb` cell 15, where the same construction is spelled out):
+    rows z = [d_u + u_nom | Phi_u(:, :dim)] must satisfy  psi^-1 ||sqrt(sigma) z|| <= upper - z mu  and the mirrored
+    lower bound."""
+    from scipy.stats import norm
+    mu = np.zeros(1 + dim)
+    mu[0] = 1.0
+    sigma = np.zeros(1 + dim)
+    sigma[1:] = var_x0
+    psi_inv = norm.ppf(prob)
+    Au = np.diag(np.sqrt(sigma))
+    As = [np.concatenate([Au, (-mu / psi_inv)[None]], axis=0), np.concatenate([Au, (mu / psi_inv)[None]], axis=0)]
+    bs = [np.append(np.zeros(1 + dim), upper_u / psi_inv), np.append(np.zeros(1 + dim), -lower_u / psi_inv)]
+    return As, bs
+
+
+def run_isls_admm(model, p, b=0):
+    """Shimmed HEAD `iSLS.isls_admm` (isls.py:503-712) on problem b of an oracle problem dict with p["robust"]."""
+    load()
+    from isls.projections import project_set_convex, project_soc_unit
+    rb = p["robust"]
+    s = make_isls(model, p["N"], p["zs"], np.stack([np.diag(q) for q in p["Qdiag"]]), p["seq"], p["u_std"])
+    init_nominal(s, p["x0"][b], p["u0"])
+    As, bs = rb["As"], rb["bs"]
+
+    def project_u(u, u_nom):                                        # notebook cell 25
+        u_nom_ = u_nom.flatten()
+        y_ = u.copy()
+        y_[:, 0] += u_nom_
+        y_ = project_set_convex(y_, As, bs, projections=[project_soc_unit] * len(As), rho=rb["inner_rho"],
+                                max_iter=rb["inner_max_iter"], threshold=rb["inner_threshold"], verbose=0)
+        y_[:, 0] -= u_nom_
+        return y_
+    with quiet():
+        du, phi_u = s.isls_admm(rb["dim"], model.get_AB, max_line_search=p["L"], k_max=p["I_o"], project_u=project_u,
+                                rho_u=rb["rho_u"], max_admm_iter=p["I_a"], threshold=p["tol"], verbose=0, log=True)
+    return dict(x=s.x_nom.copy(), u=s.u_nom.copy(), cost_log=np.array(s.cost_log, dtype=np.float64), du=du.copy(),
+                phi_u=phi_u.copy())

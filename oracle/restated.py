@@ -863,3 +863,138 @@ def mc_rollout(model, mode, x0, K, k, N, x_nom=None, u_nom=None):
         xs[:, t], us[:, t] = x, u
         x = model.f(x, u)
     return xs, us
+
+
+# ------------------------------------------------------------------------ robust nonlinear iSLS-ADMM
+def isls_admm(p, fixed_budget=False):
+    """iSLS.isls_admm (isls/isls.py:503-712) with project_u = project_set_convex over SOC chance constraints
+    (3DoF robot/State bounds and robust control bounds.ipynb cells 24-26), in Riccati form.
+
+    The reference solves  [d_u | Phi_u] = l_side^-1 (r_side + Rr reg_u)  with the dense (N m)^2 inverse
+    (isls.py:562-579).  Column by column that is an LQ problem around the nominal trajectory with the gains K_t of one
+    Riccati pass (Cxx = 2Q, Cuu = 2(R + Rr)):
+      column 0 (d_u):        dx_0 = 0,    cx = 2Q(x^ - z_via), cu = 2R u^ - 2Rr reg_0
+      column c >= 1 (Phi_u): dx_0 = e_c   (Sx = C[:, :dim], isls.py:546), cx = 0, cu = -2Rr reg_c
+    each a feed-forward pass (sls.py:168-202) + linear rollout du_t = K_t dx_t + k_t, with the batch-form last control
+    du_{N-1} = -Cuu^-1 cu.  Line search on column 0 only, cost_function without penalty terms (isls.py:586-599);
+    ADMM on the matrix variable with the row-wise projection, residuals weighted by Rr (isls.py:641-654), stall
+    threshold 1e-3 (isls.py:664), outer stop |dcost| < 1e-4 or oscillation (isls.py:700-706).
+    Returns per problem: x, u, cost_log, d_u [N,m], phi_u [N,m,dim], iteration counts."""
+    model = _model_of(p)
+    N, n, m = p["N"], p["n"], p["m"]
+    rb = p["robust"]
+    dim, rho = rb["dim"], float(rb["rho_u"])
+    I_o, I_a, L, tol, relax = p["I_o"], p["I_a"], p["L"], p["tol"], p.get("alpha", 1.0)
+    x_nom, u_nom = initial_rollout(p)
+    B = x_nom.shape[0]
+    zs = _zs_b(p, B)
+    seq = p["seq"]
+    Qd = np.asarray(p["Qdiag"], float)[seq]
+    R = _R(p)
+    al = alphas(L)
+    C = dim + 1
+    cost = total_cost(p, zs, x_nom[:, None], u_nom[:, None])[:, 0]
+    cost_log = np.full((B, I_o + 1), np.nan)
+    cost_log[:, 0] = cost
+    n_log = np.ones(B, dtype=np.int64)
+    status = np.zeros(B, dtype=np.int32)
+    outer_iters = np.zeros(B, dtype=np.int32)
+    admm_iters = np.zeros((B, I_o), dtype=np.int32)
+    inner_iters = np.zeros((B, I_o, I_a), dtype=np.int32)
+    res_log = np.full((B, I_o, I_a, 2), np.nan)
+    alpha_idx = np.full((B, I_o, I_a), -1, dtype=np.int32)
+    d_u = np.zeros((B, N, m))
+    phi_u = np.zeros((B, N, m, dim))
+    Cxx = _diag_embed(2.0 * Qd)[None]
+    Cuu = _diag_embed(np.broadcast_to(2.0 * (R + rho), (N, m)))[None]
+    Cuu_last = 2.0 * (R + rho)
+    for b in range(B):
+        z_u = np.zeros((N, m, C))                                             # z_u_init (isls.py:537)
+        xn, un = x_nom[b:b + 1].copy(), u_nom[b:b + 1].copy()
+        for k in range(I_o):
+            prev_cost = cost[b]
+            A, Bm = model.get_AB(xn, un)
+            Kg, _, non_pd, Quu, Quu_inv, Qux = backward_pass(A, Bm, np.zeros((1, N, n)), np.zeros((1, N, m)), Cxx, Cuu,
+                                                             logs=True)
+            if non_pd[0]:
+                status[b] |= ST_NON_PD
+            lam = np.zeros_like(z_u)                                          # lmb_u = 0 (isls.py:615)
+            prim = dual = 1e6
+            cx0 = 2.0 * Qd * (xn - zs[b:b + 1][:, seq])
+            x_u = np.zeros((N, m, C))
+            x_win = xn.copy()
+            for j in range(I_a):
+                reg = z_u - lam                                               # isls.py:624
+                # ---- f_argmin (isls.py:568-608)
+                du_ = np.zeros((N, m, C))
+                for c in range(C):
+                    if c == 0:
+                        cx, cu = cx0, 2.0 * R * un - 2.0 * rho * reg[None, :, :, 0]
+                        dx0 = None
+                    else:
+                        cx, cu = np.zeros((1, N, n)), -2.0 * rho * reg[None, :, :, c]
+                        dx0 = np.zeros((1, n))
+                        dx0[0, c - 1] = 1.0
+                    kk = ff_pass(A, Bm, cx, cu, Kg, Quu, Quu_inv, Qux)
+                    kk[:, -1] = -cu[:, -1] / Cuu_last
+                    _, duc = linear_rollout(A, Bm, Kg, kk, dx0)
+                    du_[:, :, c] = duc[0]
+                u_cand = un[:, None] + al[None, :, None, None] * du_[None, None, :, :, 0]
+                x_cand = rollout_open(model, xn[:, 0], u_cand)
+                costs = total_cost(p, zs[b:b + 1], x_cand, u_cand)            # isls.py:586 (no penalty terms)
+                ind = int(np.argmin(costs[0]))
+                alpha_idx[b, k, j] = ind
+                x_u = du_.copy()
+                x_u[:, :, 0] = al[ind] * du_[:, :, 0]                         # isls.py:602-603
+                x_win = x_cand[:, ind]
+                # ---- ADMM update (isls.py:628-654)
+                z_prev = z_u
+                y = relax * x_u + (1.0 - relax) * z_u + lam
+                y2 = y.reshape(N * m, C).copy()
+                y2[:, 0] += un[0].reshape(-1)                                 # project_u(z, u_nom): notebook cell 25
+                zp, its = project_set_convex_soc(y2, rb["As"], rb["bs"], rho=rb["inner_rho"],
+                                                 max_iter=rb["inner_max_iter"], threshold=rb["inner_threshold"])
+                zp = zp.copy()
+                zp[:, 0] -= un[0].reshape(-1)
+                z_u = zp.reshape(N, m, C)
+                inner_iters[b, k, j] = its
+                r = x_u - z_u
+                lam = lam + r
+                pprim, pdual = prim, dual
+                dual = np.linalg.norm(rho * (z_u - z_prev).reshape(N * m, C))
+                prim = np.linalg.norm(rho * r.reshape(N * m, C))
+                res_log[b, k, j] = prim, dual
+                admm_iters[b, k] = j + 1
+                if not fixed_budget:
+                    if prim < tol and dual < tol:
+                        break
+                    pc = abs(pprim - prim) / (pprim + 1e-30)
+                    dc = abs(pdual - dual) / (pdual + 1e-30)
+                    if pc < 1e-3 and dc < 1e-3:
+                        break
+            # ---- new nominal (isls.py:690-693)
+            un = un + x_u[None, :, :, 0]
+            xn = xn + (x_win - xn)
+            newc = total_cost(p, zs[b:b + 1], xn[:, None], un[:, None])[0, 0]
+            cost[b] = newc
+            cost_log[b, n_log[b]] = newc
+            n_log[b] += 1
+            outer_iters[b] = k + 1
+            d_u[b] = x_u[:, :, 0]
+            phi_u[b] = x_u[:, :, 1:]
+            if not fixed_budget:
+                if abs(newc - prev_cost) < 1e-4:                              # isls.py:700
+                    status[b] |= ST_CONVERGED_COST
+                    break
+                nl = n_log[b]
+                last4 = cost_log[b, max(0, nl - 4):nl]
+                prev4 = cost_log[b, max(0, nl - 8):max(0, nl - 4)]
+                if prev4.size and abs(np.mean(last4) - np.mean(prev4)) < 1e-3:  # isls.py:704
+                    status[b] |= ST_OSCILLATING
+                    break
+        else:
+            status[b] |= ST_MAX_ITER
+        x_nom[b], u_nom[b] = xn[0], un[0]
+    return dict(x=x_nom, u=u_nom, cost=cost, cost_log=cost_log, n_log=n_log, status=status, outer_iters=outer_iters,
+                admm_iters=admm_iters, inner_iters=inner_iters, res_log=res_log, alpha_idx=alpha_idx, d_u=d_u,
+                phi_u=phi_u)

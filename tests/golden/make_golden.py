@@ -292,6 +292,20 @@ def golden_parking():
     np.savez_compressed(os.path.join(OUT, "parking_obstacles.npz"), **out)
 
 
+def golden_isls_admm(B=3):
+    """Robust iSLS-ADMM of the unmodified reference (isls.py:503-712) on the 3-DoF arm with chance-constrained control
+    bounds (3DoF robot/State bounds and robust control bounds.ipynb cells 12-26): problem 0 is the notebook's q0."""
+    p = P.arm_robust_batch(B)
+    model = M.make_model("arm3", dt=p["dt"])
+    xs, us, logs, dus, phis = [], [], [], [], []
+    for b in range(B):
+        r = S.run_isls_admm(model, p, b)
+        xs.append(r["x"]); us.append(r["u"]); logs.append(r["cost_log"]); dus.append(r["du"]); phis.append(r["phi_u"])
+        print("isls_admm", b, len(r["cost_log"]), r["cost_log"][-1], np.abs(r["u"]).max())
+    np.savez_compressed(os.path.join(OUT, "arm_isls_admm.npz"), x0=p["x0"], x=np.stack(xs), u=np.stack(us),
+                        cost_log=_pad(logs), du=np.stack(dus), phi_u=np.stack(phis))
+
+
 if __name__ == "__main__":
     assert S.available(), "needs the reference tree"
     only = set(sys.argv[1:])                       # e.g. `make_golden.py tutorial` regenerates one fixture family
@@ -316,3 +330,5 @@ if __name__ == "__main__":
         golden_tutorial()
     if want("parking"):
         golden_parking()
+    if want("isls_admm"):
+        golden_isls_admm()

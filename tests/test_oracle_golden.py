@@ -229,3 +229,21 @@ def test_parking_obstacle_sets_vs_reference_golden(golden):
     for q, ref in zip(g["proj_in"], g["proj_out"]):
         z, _ = R.project_set_convex_rows(q, proj, ob["rho"], ob["max_iter"], ob["threshold"])
         assert np.abs(z - ref).max() < 1e-12
+
+
+def test_isls_admm_riccati_form_vs_reference_golden(golden):
+    """robust nonlinear iSLS-ADMM (isls.py:503-712) - the Riccati-form restatement (one K-pass +
+    (dim+1) feed-forward passes / linear rollouts instead of the dense (N m)^2 inverse) against the unmodified
+    reference on the 3-DoF arm with SOC chance constraints: identical iteration counts, cost log 1e-9, d_u / Phi_u 1e-9."""
+    g = golden("arm_isls_admm")
+    B = g["x0"].shape[0]
+    p = P.arm_robust_batch(B)
+    assert np.array_equal(p["x0"], g["x0"])
+    assert abs(g["cost_log"][0, 0] - 6775.068343357641) < 1e-9 * 6775.0      # notebook pin (initial cost)
+    o = R.isls_admm(p)
+    _check_logs(o, g, 1e-9)
+    assert np.abs(o["u"] - g["u"]).max() < 1e-9 and np.abs(o["x"] - g["x"]).max() < 1e-9
+    N, m = p["N"], p["m"]
+    assert np.abs(o["d_u"].reshape(B, N * m) - g["du"]).max() < 1e-9
+    assert np.abs(o["phi_u"].reshape(B, N * m, -1) - g["phi_u"]).max() < 1e-9 * max(1.0, np.abs(g["phi_u"]).max())
+    assert np.abs(o["u"]).max() < 6.0                       # the nominal respects the (tightened) bound
