@@ -29,6 +29,7 @@
 #define MAX_L 50
 
 #include "common.cuh"
+#include "soc.cuh"
 
 static thread_local std::string g_err;
 int isls_fail(int code, const std::string &msg) {
@@ -82,6 +83,11 @@ struct Dev {
   double obst_upper, obst_rho, obst_threshold;
   const double *ob_c, *ob_W, *ob_Wi, *ob_lo;
   double *obw;           // workspace [3 + 2K][T][N][n][32]: winner x, pre-projection point, inner x, z_k, lambda_k
+  // robust iSLS-ADMM: C = dim + 1 columns [d_u | Phi_u(:, :dim)]; Zm, Lm (ADMM z, lambda, delta coordinates) and Xu
+  // (primal iterate) are [T][N][m * C][32] with component index j * C + c
+  int isls_C, ls_cost_only;
+  double *Zm, *Lm, *Xu;
+  double stall_tol, osc_tol;
   // workspace, tile-blocked [T][N][dim][32]
   double *xh, *uh, *du, *zx, *lx, *zu, *lu, *rgx, *rgu, *Kg, *Qux, *Quu, *Qui, *kk, *zs;   // Quu, Qui: packed lower
   double *lsc;           // [T][L][32] candidate costs of the last line search
@@ -235,6 +241,10 @@ __global__ void k_init(Dev d, const double *x0, const double *u_init, const doub
     M::step(x, u, xn, d.dt);
 #pragma unroll
     for (int i = 0; i < M::n; i++) x[i] = xn[i];
+    if (d.isls_C > 0) {                                  // z_u_init = 0 (isls.py:537)
+      double *Zm = c.at(d.Zm, d, M::m * d.isls_C);
+      for (int q = 0; q < M::m * d.isls_C; q++) EL(Zm, M::m * d.isls_C, t, q) = 0.0;
+    }
   }
   const double cost = cs + d.u_std * cc;
   d.cost[c.b] = cost;
@@ -1093,7 +1103,9 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
       }
     }
     const size_t S = (size_t)d.T * TILE;
-    const double c0 = d.cq[c.b], c1 = d.cq[S + c.b], c2 = d.cq[2 * S + c.b];
+    // isls_admm searches on the cost alone (isls.py:586-599): R-only polynomial (rows 3-5)
+    const int pr0 = d.ls_cost_only ? 3 : 0;
+    const double c0 = d.cq[pr0 * S + c.b], c1 = d.cq[(pr0 + 1) * S + c.b], c2 = d.cq[(pr0 + 2) * S + c.b];
 #pragma unroll
     for (int q = 0; q < CPT; q++) {
       const int l = w * CPT + q;
@@ -1386,7 +1398,7 @@ __device__ __forceinline__ void admm_finish(const Dev &d, const TileCtx<M> &c, i
     else {
       const double pch = fabs(pprim - prim) / (pprim + 1e-30);                   // admm.py:78-79
       const double dch = fabs(pdual - dual) / (pdual + 1e-30);
-      if (pch < d.tol && dch < d.tol) ex = ISLS_ADMM_STALLED;                    // admm.py:80
+      if (pch < d.stall_tol && dch < d.stall_tol) ex = ISLS_ADMM_STALLED;        // admm.py:80
     }
   }
   if (!ex && inner == d.max_admm - 1) ex = ISLS_ADMM_MAXIT;
@@ -1403,6 +1415,187 @@ __global__ void k_admm(Dev d, int outer, int inner) {
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b] || d.adone[c.b]) return;
   admm_body<M>(d, c, outer, inner);
+}
+
+// ------------------------------------------------------------------------------ robust iSLS-ADMM (isls.py:503-712)
+// Riccati form of  [d_u | Phi_u] = l_side^-1 (r_side + Rr reg)  (isls.py:562-579), column by column: column 0 is the
+// iLQR-ADMM step (k_ff: cx = 2Q(x^ - z), cu = 2R u^ + 2Rr(u^ - reg_abs) with reg_abs = u^ + reg_0, dx_0 = 0); column
+// c >= 1 has dx_0 = e_c (Sx = C[:, :dim]), cx = 0, cu = -2Rr reg_c.
+
+// start of an outer iteration: lambda = 0 (isls.py:615), z warm start kept in delta coordinates (isls.py:695-696),
+// reg_abs of column 0 for k_ff
+template <class M>
+__global__ void k_isls_reset(Dev d) {
+  constexpr int m = M::m;
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
+  TileCtx<M> c(d, tile, threadIdx.x);
+  if (d.odone[c.b]) return;
+  const int C = d.isls_C;
+  const double *uh = c.at(d.uh, d, m), *Zm = c.at(d.Zm, d, m * C);
+  double *Lm = c.at(d.Lm, d, m * C), *rgu = c.at(d.rgu, d, m);
+  for (int t = 0; t < d.N; t++)
+    for (int j = 0; j < m; j++) {
+      for (int q = 0; q < C; q++) EL(Lm, m * C, t, j * C + q) = 0.0;
+      EL(rgu, m, t, j) = EL(uh, m, t, j) + EL(Zm, m * C, t, j * C);
+    }
+}
+
+// columns c = 1..dim (blockIdx.y + 1): feed-forward sweep (sls.py:168-202) with cx = 0, cu = -2 Rr (z_c - lambda_c),
+// batch-form last control, then the linear rollout from dx_0 = e_c.  k_t is parked in Xu[., c] between the sweeps.
+template <class M>
+__global__ void k_isls_cols(Dev d) {
+  constexpr int n = M::n, m = M::m, nt = NTRI(M::m);
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
+  TileCtx<M> c(d, tile, threadIdx.x);
+  if (d.odone[c.b] || d.adone[c.b]) return;
+  const int C = d.isls_C, col = blockIdx.y + 1, N = d.N;
+  const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m);
+  const double *Kg = c.at(d.Kg, d, m * n), *Qx = c.at(d.Qux, d, m * n);
+  const double *Qu = c.at(d.Quu, d, nt), *Qi = c.at(d.Qui, d, nt);
+  const double *Zm = c.at(d.Zm, d, m * C), *Lm = c.at(d.Lm, d, m * C);
+  double *Xu = c.at(d.Xu, d, m * C);
+  double A[n][n], Bm[n][m], v[n], cx[n];
+  init_AB<M>(A, Bm);
+#pragma unroll
+  for (int i = 0; i < n; i++) { v[i] = 0.0; cx[i] = 0.0; }
+  auto cu_of = [&](int t, double (&cu)[m]) {
+#pragma unroll
+    for (int j = 0; j < m; j++)
+      cu[j] = -2.0 * d.rho_u[t * m + j] * (EL(Zm, m * C, t, j * C + col) - EL(Lm, m * C, t, j * C + col));
+  };
+  {
+    double cu[m];
+    cu_of(N - 1, cu);
+#pragma unroll
+    for (int j = 0; j < m; j++)
+      EL(Xu, m * C, N - 1, j * C + col) = -cu[j] / (2.0 * (d.u_std * d.Rw[j] + d.rho_u[(N - 1) * m + j]));
+  }
+  for (int t = N - 2; t >= 0; t--) {
+    double x[n], u[m], J[M::NJA], cu[m], Qux[m][n], Quu[m][m], Qui[m][m], kt[m];
+#pragma unroll
+    for (int i = 0; i < n; i++) x[i] = EL(xh, n, t, i);
+#pragma unroll
+    for (int j = 0; j < m; j++) u[j] = EL(uh, m, t, j);
+#pragma unroll
+    for (int a = 0; a < m; a++) {
+#pragma unroll
+      for (int j = 0; j < n; j++) Qux[a][j] = EL(Qx, m * n, t, a * n + j);
+#pragma unroll
+      for (int b2 = 0; b2 <= a; b2++) {
+        Qui[a][b2] = EL(Qi, nt, t, tri(a, b2)); Qui[b2][a] = Qui[a][b2];
+        Quu[a][b2] = EL(Qu, nt, t, tri(a, b2)); Quu[b2][a] = Quu[a][b2];
+      }
+    }
+    M::jac(x, u, J, d.dt);
+    M::expand(J, A, Bm, d.dt);
+    cu_of(t, cu);
+    ff_step<M>(A, Bm, cx, cu, Qux, Quu, Qui, v, kt);
+#pragma unroll
+    for (int j = 0; j < m; j++) EL(Xu, m * C, t, j * C + col) = kt[j];
+  }
+  double dx[n];
+#pragma unroll
+  for (int i = 0; i < n; i++) dx[i] = (i == col - 1) ? 1.0 : 0.0;
+  for (int t = 0; t < N; t++) {
+    double x[n], u[m], K[m][n], kv[m], duv[m];
+#pragma unroll
+    for (int a = 0; a < m; a++) {
+#pragma unroll
+      for (int j = 0; j < n; j++) K[a][j] = EL(Kg, m * n, t, a * n + j);
+      kv[a] = EL(Xu, m * C, t, a * C + col);
+      u[a] = EL(uh, m, t, a);
+    }
+#pragma unroll
+    for (int i = 0; i < n; i++) x[i] = EL(xh, n, t, i);
+#pragma unroll
+    for (int a = 0; a < m; a++) {
+      double acc = 0.0;
+      if (t < N - 1) {
+#pragma unroll
+        for (int j = 0; j < n; j++) acc = fma(K[a][j], dx[j], acc);
+      }
+      duv[a] = acc + kv[a];
+      EL(Xu, m * C, t, a * C + col) = duv[a];
+    }
+    if (t < N - 1) {
+      double J[M::NJA], dxn[n];
+      M::jac(x, u, J, d.dt);
+      M::expand(J, A, Bm, d.dt);
+      mat_Ax_Bu<M>(A, Bm, dx, duv, dxn);
+#pragma unroll
+      for (int i = 0; i < n; i++) dx[i] = dxn[i];
+    }
+  }
+}
+
+// ADMM update on the matrix variable (isls.py:628-654): one CTA per problem, thread r = row (t, j) of
+// [d_u | Phi_u(:, :dim)]; z = project_u(alpha x + (1 - alpha) z + lambda, u_nom) with the notebook's closure (column 0
+// shifted by u_nom, project_set_convex over the SOC set, shifted back), lambda += x - z, residuals weighted by Rr.
+template <class M>
+__global__ void k_isls_update(Dev d, SocSet S, int outer, int inner) {
+  constexpr int m = M::m;
+  __shared__ double red[32];
+  const long long b = blockIdx.x;
+  const int tile = (int)(b / TILE), lane = (int)(b % TILE);
+  TileCtx<M> c(d, tile, lane);
+  if (!c.valid || d.odone[c.b] || d.adone[c.b]) return;               // uniform over the CTA
+  const int C = d.isls_C, r = threadIdx.x, rows = d.N * m;
+  const bool act = r < rows;
+  const int t = act ? r / m : 0, j = act ? r % m : 0;
+  const double *uh = c.at(d.uh, d, m), *du = c.at(d.du, d, m);
+  double *Zm = c.at(d.Zm, d, m * C), *Lm = c.at(d.Lm, d, m * C), *Xu = c.at(d.Xu, d, m * C), *rgu = c.at(d.rgu, d, m);
+  const int bi = d.best[c.b];
+  double xu[SOC_MAXC] = {}, z[SOC_MAXC] = {}, lm[SOC_MAXC] = {}, y[SOC_MAXC] = {}, zn[SOC_MAXC] = {};
+  double un = 0.0, rho = 0.0;
+  if (act) {
+    un = EL(uh, m, t, j);
+    rho = d.rho_u[t * m + j];
+    xu[0] = d.alphas[bi] * EL(du, m, t, j);                           // isls.py:602-603
+    for (int q = 1; q < C; q++) xu[q] = EL(Xu, m * C, t, j * C + q);
+    for (int q = 0; q < C; q++) { z[q] = EL(Zm, m * C, t, j * C + q); lm[q] = EL(Lm, m * C, t, j * C + q); }
+    for (int q = 0; q < C; q++) y[q] = (d.relax * xu[q] + (1.0 - d.relax) * z[q]) + lm[q];
+    y[0] += un;                                                       // notebook cell 25
+  }
+  const int its = soc_project_set(S, y, zn, act, red);
+  double ps = 0.0, ds = 0.0;
+  if (act) {
+    zn[0] -= un;
+    for (int q = 0; q < C; q++) {
+      const double pr = xu[q] - zn[q], dz = zn[q] - z[q];
+      lm[q] += pr;
+      ps = fma(rho * pr, rho * pr, ps);
+      ds = fma(rho * dz, rho * dz, ds);
+      EL(Zm, m * C, t, j * C + q) = zn[q];
+      EL(Lm, m * C, t, j * C + q) = lm[q];
+    }
+    EL(Xu, m * C, t, j * C) = xu[0];
+    EL(rgu, m, t, j) = un + (zn[0] - lm[0]);                          // reg_abs of column 0 for the next k_ff
+  }
+  const double prim = sqrt(block_sum(ps, red)), dual = sqrt(block_sum(ds, red));
+  if (r == 0) {
+    if (d.out.inner_iters) d.out.inner_iters[((size_t)c.ob * d.max_outer + outer) * d.max_admm + inner] = its;
+    d.cost_adm[c.b] = d.best_cost[c.b];                               // the search cost is the plain cost
+    admm_finish<M>(d, c, outer, inner, bi, prim, dual);
+  }
+}
+
+// d_u = x_u[:, 0] and Phi_u(:, :dim) = x_u[:, 1:] of the last ADMM iterate, natural layouts (isls.py:710-712)
+template <class M>
+__global__ void k_isls_out(Dev d, double *du_out, double *phi_out) {
+  constexpr int m = M::m;
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
+  TileCtx<M> c(d, tile, threadIdx.x);
+  if (!c.valid) return;
+  const int C = d.isls_C;
+  const double *Xu = c.at(d.Xu, d, m * C);
+  for (int t = 0; t < d.N; t++)
+    for (int j = 0; j < m; j++) {
+      du_out[((size_t)c.ob * d.N + t) * m + j] = EL(Xu, m * C, t, j * C);
+      for (int q = 1; q < C; q++) phi_out[(((size_t)c.ob * d.N + t) * m + j) * (C - 1) + q - 1] = EL(Xu, m * C, t, j * C + q);
+    }
 }
 
 // After ADMM (isls/isls.py:488-499): nominal <- last primal iterate, cost log, outer stop tests.
@@ -1462,7 +1655,7 @@ __global__ void k_outer_end(Dev d, int outer) {
       double s1 = 0.0, s2 = 0.0;
       for (int i = a0; i < len; i++) s1 += (i == nl) ? cost : cl[i];
       for (int i = p0; i < p1; i++) s2 += cl[i];
-      if (fabs(s1 / (len - a0) - s2 / (p1 - p0)) < d.outer_tol) st = ISLS_ST_OSCILLATING;
+      if (fabs(s1 / (len - a0) - s2 / (p1 - p0)) < d.osc_tol) st = ISLS_ST_OSCILLATING;
     }
   }
   if (st) {
@@ -2231,6 +2424,10 @@ extern "C" int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan)
   if (desc->N < 2 || desc->n_via < 1 || desc->L < 1 || desc->L > MAX_L) return fail(ISLS_E_INVALID, "bad N / n_via / L");
   if (!desc->Qdiag || !desc->seq || !desc->alphas) return fail(ISLS_E_INVALID, "Qdiag/seq/alphas is NULL");
   if (desc->n_obst < 0 || desc->n_obst > ISLS_MAX_OBST) return fail(ISLS_E_INVALID, "n_obst out of range");
+  if (desc->isls_dim < 0 || desc->isls_dim + 1 > SOC_MAXC || desc->isls_dim > desc->n)
+    return fail(ISLS_E_UNSUPPORTED, "isls_dim must be in 0..3 and <= x_dim");
+  if (desc->isls_dim > 0 && (!desc->rho_u || (long long)desc->N * desc->m > 1024))
+    return fail(ISLS_E_UNSUPPORTED, "isls_admm needs rho_u and N * u_dim <= 1024");
   if (desc->n_obst > 0 && (!desc->rho_x || !desc->obst_centers || !desc->obst_W || !desc->obst_W_inv || !desc->obst_lower ||
                            desc->obst_max_iter < 1 || desc->n < 2))
     return fail(ISLS_E_INVALID, "obstacle sets need rho_x, centres, W, W_inv, lower and obst_max_iter >= 1");
@@ -2354,6 +2551,8 @@ static size_t carve(const isls_plan *p, long long B, char *base, Dev *d, Dev *al
   takeD(d ? &d->zs : nullptr, T * p->n_via * n * TILE);
   takeD(d ? &d->lsc : nullptr, T * p->L * TILE);
   takeD(d ? &d->obw : nullptr, p->desc.n_obst > 0 ? (3 + 2 * (size_t)p->desc.n_obst) * tn : 0);
+  const size_t tC = p->desc.isls_dim > 0 ? tm * (size_t)(p->desc.isls_dim + 1) : 0;
+  takeD(d ? &d->Zm : nullptr, tC); takeD(d ? &d->Lm : nullptr, tC); takeD(d ? &d->Xu : nullptr, tC);
   const size_t S = T * TILE;
   takeD(d ? &d->cost : nullptr, S); takeD(d ? &d->prev_cost : nullptr, S); takeD(d ? &d->prim : nullptr, S);
   takeD(d ? &d->dual : nullptr, S); takeD(d ? &d->cost_adm : nullptr, S); takeD(d ? &d->best_cost : nullptr, S);
@@ -2393,6 +2592,8 @@ static int setup(const isls_plan *plan, const isls_solve_opts *o, int64_t B, voi
     if (o->max_outer < 1 || o->max_admm < 0) return fail(ISLS_E_INVALID, "bad iteration budgets");
     d->max_outer = o->max_outer; d->max_admm = o->max_admm; d->tol = o->tol; d->outer_tol = o->outer_tol;
     d->relax = o->relax; d->fixed_budget = o->fixed_budget; d->last_stage_dp = o->last_stage_dp;
+    d->stall_tol = o->stall_tol > 0.0 ? o->stall_tol : o->tol;
+    d->osc_tol = o->osc_tol > 0.0 ? o->osc_tol : o->outer_tol;
   }
   if (out) {
     if (!out->cost_log) return fail(ISLS_E_INVALID, "out->cost_log is required");
@@ -2600,6 +2801,51 @@ extern "C" int isls_ilqr_solve_f64(const isls_plan *plan, const isls_solve_opts 
       LAUNCH(ISLS_KC_ACCEPT, s, (k_accept_closed<M><<<tp_grid(d), tp_block(), 0, s>>>(d, j)));
     }
     LAUNCH(ISLS_KC_FINALIZE, s, (k_finalize<M><<<tp_grid(d), tp_block(), 0, s>>>(d)));
+    CK(cudaGetLastError());
+    return ISLS_OK;
+  });
+}
+
+extern "C" int isls_isls_admm_solve_f64(const isls_plan *plan, const isls_solve_opts *opts,
+                                        const isls_sls_admm_opts *soc, int64_t B, const double *x0,
+                                        const double *u_init, const double *zs, void *ws, size_t ws_bytes,
+                                        const isls_solve_out *out, double *du_dev, double *phi_u_dev, void *stream) {
+  if (!opts || !soc || !out || !x0 || !u_init || !zs || !du_dev || !phi_u_dev) return fail(ISLS_E_INVALID, "NULL argument");
+  if (opts->max_admm < 1) return fail(ISLS_E_INVALID, "max_admm must be >= 1");
+  if (!plan || plan->desc.isls_dim < 1) return fail(ISLS_E_INVALID, "the plan was not created with isls_dim > 0");
+  if (plan->proj_x || !plan->proj_u) return fail(ISLS_E_UNSUPPORTED, "isls_admm: control projection only (rho_u, no rho_x)");
+  const int C = plan->desc.isls_dim + 1;
+  if (soc->n_cones < 1 || soc->n_cones > SOC_MAXP || soc->cone_rows != C + 1 || !soc->As || !soc->bs)
+    return fail(ISLS_E_UNSUPPORTED, "unsupported cone set (need A_i of shape [dim + 2, dim + 1])");
+  Dev d;
+  int rc = setup(plan, opts, B, ws, ws_bytes, out, &d);
+  if (rc) return rc;
+  d.lsc = nullptr;
+  d.isls_C = C;
+  d.ls_cost_only = 1;
+  SocSet S;
+  soc_set_build(&S, soc->n_cones, C, soc->cone_rows, soc->As, soc->bs, soc->inner_rho, soc->inner_max_iter,
+                soc->inner_threshold);
+  cudaStream_t s = (cudaStream_t)stream;
+  return dispatch_model(plan, [&](auto model) -> int {
+    using M = decltype(model);
+    const int rows = d.N * M::m, threads = ((rows + 31) / 32) * 32;
+    dim3 gcols = tp_grid(d);
+    gcols.y = C - 1;
+    LAUNCH(ISLS_KC_INIT, s, (k_init<M><<<tp_grid(d), tp_block(), 0, s>>>(d, x0, u_init, zs)));
+    for (int j = 0; j < d.max_outer; j++) {
+      LAUNCH(ISLS_KC_KPASS, s, (k_kpass<M><<<tp_grid(d), tp_block(), 0, s>>>(d)));
+      k_isls_reset<M><<<tp_grid(d), tp_block(), 0, s>>>(d);
+      for (int a = 0; a < d.max_admm; a++) {
+        LAUNCH(ISLS_KC_FF, s, launch_ff<M>(d, s));
+        LAUNCH(ISLS_KC_LINESEARCH, s, launch_linesearch<M>(d, false, s, LsFuse{0, j, a}));
+        LAUNCH(ISLS_KC_ISLS_COLS, s, (k_isls_cols<M><<<gcols, tp_block(), 0, s>>>(d)));
+        LAUNCH(ISLS_KC_ISLS_UPDATE, s, (k_isls_update<M><<<(unsigned)B, threads, 0, s>>>(d, S, j, a)));
+      }
+      LAUNCH(ISLS_KC_OUTER_END, s, (k_outer_end<M><<<tp_grid(d), tp_block(), 0, s>>>(d, j)));
+    }
+    LAUNCH(ISLS_KC_FINALIZE, s, (k_finalize<M><<<tp_grid(d), tp_block(), 0, s>>>(d)));
+    k_isls_out<M><<<tp_grid(d), tp_block(), 0, s>>>(d, du_dev, phi_u_dev);
     CK(cudaGetLastError());
     return ISLS_OK;
   });

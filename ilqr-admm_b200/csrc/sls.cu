@@ -189,17 +189,7 @@ __global__ void k_mask_blt(int n, int m, int N, double *Y) {
 }
 
 // ------------------------------------------------------------------------------------------------ ADMM_SLS
-#define SOC_MAXC 4      // columns of the projected rows: 1 + x_dim/2
-#define SOC_MAXR 5      // rows of each A_i (= c + 1)
-#define SOC_MAXP 4      // cones per row
-struct SocSet {
-  int P, c, ra;                       // number of cones, columns, rows of A_i
-  double A[SOC_MAXP][SOC_MAXR][SOC_MAXC];
-  double b[SOC_MAXP][SOC_MAXR];
-  double linv[SOC_MAXC][SOC_MAXC];    // (I + rho sum A_i'A_i)^-1
-  double rho, threshold;
-  int max_iter;
-};
+#include "soc.cuh"
 
 struct SlsAdmm {
   int Nm, Nn, c, max_iter, fixed_budget;
@@ -214,46 +204,6 @@ struct SlsAdmm {
   int *iters, *exits;     // [B]
   long long *inner_total; // [B] or NULL
 };
-
-__device__ __forceinline__ double block_max(double v, double *sm) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  __syncthreads();
-  if (lane == 0) sm[w] = v;
-  __syncthreads();
-  double r = sm[0];
-  for (int i = 1; i < (int)((blockDim.x + 31) >> 5); i++) r = fmax(r, sm[i]);
-  return r;
-}
-__device__ __forceinline__ double block_sum(double v, double *sm) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if (lane == 0) sm[w] = v;
-  __syncthreads();
-  double r = 0.0;
-  for (int i = 0; i < (int)((blockDim.x + 31) >> 5); i++) r += sm[i];
-  return r;
-}
-
-// project_soc_unit_batch (isls/projections.py:140-162) on one row [z(0..d-1), t], incl. the D9 behaviour (every
-// row with t < 0 is zeroed): later masks win (cond2, then cond1, then cond3), exactly like the numpy code.
-__device__ __forceinline__ void soc_unit_row(int d, const double *y, double *out) {
-  double s = 0.0;
-  for (int i = 0; i < d; i++) s = fma(y[i], y[i], s);
-  const double zn = sqrt(s), t = y[d];
-  const bool c1 = (zn <= -t) || (t < 0.0);
-  const bool c2 = (zn > t) || (zn > -t);
-  const bool c3 = zn <= t;
-  for (int i = 0; i <= d; i++) out[i] = y[i];
-  if (c2) {
-    const double tmp = (zn + t) / 2.0;
-    for (int i = 0; i < d; i++) out[i] = tmp * y[i] / (zn + 1e-30);
-    out[d] = tmp;
-  }
-  if (c1) for (int i = 0; i <= d; i++) out[i] = 0.0;
-  if (c3) for (int i = 0; i <= d; i++) out[i] = y[i];
-}
 
 // One CTA per problem, thread r = row r of [d_u | Phi_u(:, :c-1)]   (sls.py:372-447 + projections.py:289-374)
 __global__ void k_sls_admm(SlsAdmm a, SocSet S) {
@@ -288,65 +238,9 @@ __global__ void k_sls_admm(SlsAdmm a, SocSet S) {
       for (int q = 0; q < c; q++) xu[q] = acc[q];
     }
     // ---- z = project_set_convex(alpha x + (1-alpha) z + lambda)               sls.py:403-405
-    double x0[SOC_MAXC], x[SOC_MAXC], zi[SOC_MAXP][SOC_MAXR], li[SOC_MAXP][SOC_MAXR];
-    for (int q = 0; q < c; q++) { x0[q] = (a.alpha * xu[q] + (1.0 - a.alpha) * z[q]) + lm[q]; x[q] = x0[q]; }
-    for (int i = 0; i < S.P; i++)
-      for (int e = 0; e < S.ra; e++) {
-        double v = S.b[i][e];
-        for (int q = 0; q < c; q++) v = fma(S.A[i][e][q], x[q], v);
-        zi[i][e] = v;                         // z_i = A_i x + b_i   (projections.py:315)
-        li[i][e] = 0.0;
-      }
-    double pm = 1e5, dm = 1e5;
-    for (int j = 0; j < S.max_iter; j++) {
-      inner++;
-      double rsd[SOC_MAXC] = {};
-      for (int i = 0; i < S.P; i++)
-        for (int e = 0; e < S.ra; e++) {
-          const double w = (-S.b[i][e] + zi[i][e]) - li[i][e];
-          for (int q = 0; q < c; q++) rsd[q] = fma(S.A[i][e][q], w, rsd[q]);
-        }
-      double tq[SOC_MAXC];
-      for (int q = 0; q < c; q++) tq[q] = x0[q] + S.rho * rsd[q];
-      for (int q = 0; q < c; q++) {
-        double v = 0.0;
-        for (int p = 0; p < c; p++) v = fma(S.linv[q][p], tq[p], v);
-        x[q] = v;                              // projections.py:330
-      }
-      double pmax = 0.0, dmax = 0.0;
-      for (int i = 0; i < S.P; i++) {
-        double axb[SOC_MAXR], y[SOC_MAXR], zn[SOC_MAXR];
-        for (int e = 0; e < S.ra; e++) {
-          double v = S.b[i][e];
-          for (int q = 0; q < c; q++) v = fma(S.A[i][e][q], x[q], v);
-          axb[e] = v;
-          y[e] = v + li[i][e];
-        }
-        soc_unit_row(S.ra - 1, y, zn);
-        double ps = 0.0, dr[SOC_MAXC] = {};
-        for (int e = 0; e < S.ra; e++) {
-          const double pr = axb[e] - zn[e];
-          ps = fma(pr, pr, ps);
-          const double dz = zn[e] - zi[i][e];
-          for (int q = 0; q < c; q++) dr[q] = fma(S.A[i][e][q], dz, dr[q]);
-          li[i][e] += pr;
-          zi[i][e] = zn[e];
-        }
-        double ds = 0.0;
-        for (int q = 0; q < c; q++) ds = fma(S.rho * dr[q], S.rho * dr[q], ds);
-        pmax = fmax(pmax, sqrt(ps));
-        dmax = fmax(dmax, sqrt(ds));
-      }
-      // stop rule on the max over rows and cones (projections.py:343-348)
-      const double pprev = pm, dprev = dm;
-      pm = block_max(act ? pmax : 0.0, red);
-      dm = block_max(act ? dmax : 0.0, red);
-      if (pm < S.threshold && dm < S.threshold) break;
-      if (j < S.max_iter - 1) {
-        const double pch = fabs(pprev - pm) / (pprev + 1e-30), dch = fabs(dprev - dm) / (dprev + 1e-30);
-        if (pch < 1e-5 && dch < 1e-5) break;
-      }
-    }
+    double x0[SOC_MAXC], x[SOC_MAXC];
+    for (int q = 0; q < c; q++) x0[q] = (a.alpha * xu[q] + (1.0 - a.alpha) * z[q]) + lm[q];
+    inner += soc_project_set(S, x0, x, act, red);
     // ---- dual update and residuals (sls.py:406-418), Rr = rho_u I
     double ps = 0.0, ds = 0.0;
     for (int q = 0; q < c; q++) {
@@ -577,38 +471,7 @@ extern "C" int isls_sls_admm_f64(isls_sls_plan *p, const isls_sls_admm_opts *o, 
     p->have_rho = true;
   }
   SocSet S;
-  memset(&S, 0, sizeof(S));
-  S.P = o->n_cones; S.c = c; S.ra = o->cone_rows; S.rho = o->inner_rho; S.threshold = o->inner_threshold;
-  S.max_iter = o->inner_max_iter;
-  // (I + rho sum A_i'A_i)^-1 on the host (c x c, c <= 4): Gauss-Jordan with partial pivoting
-  double Mx[SOC_MAXC][2 * SOC_MAXC] = {};
-  for (int i = 0; i < S.P; i++)
-    for (int e = 0; e < S.ra; e++) {
-      S.b[i][e] = o->bs[i * S.ra + e];
-      for (int q = 0; q < c; q++) S.A[i][e][q] = o->As[(i * S.ra + e) * c + q];
-    }
-  for (int q = 0; q < c; q++)
-    for (int r2 = 0; r2 < c; r2++) {
-      double v = (q == r2) ? 1.0 : 0.0;
-      for (int i = 0; i < S.P; i++)
-        for (int e = 0; e < S.ra; e++) v += S.rho * S.A[i][e][q] * S.A[i][e][r2];
-      Mx[q][r2] = v;
-      Mx[q][c + r2] = (q == r2) ? 1.0 : 0.0;
-    }
-  for (int col = 0; col < c; col++) {
-    int piv = col;
-    for (int r2 = col + 1; r2 < c; r2++) if (fabs(Mx[r2][col]) > fabs(Mx[piv][col])) piv = r2;
-    for (int k = 0; k < 2 * c; k++) std::swap(Mx[col][k], Mx[piv][k]);
-    const double d = Mx[col][col];
-    for (int k = 0; k < 2 * c; k++) Mx[col][k] /= d;
-    for (int r2 = 0; r2 < c; r2++)
-      if (r2 != col) {
-        const double f = Mx[r2][col];
-        for (int k = 0; k < 2 * c; k++) Mx[r2][k] -= f * Mx[col][k];
-      }
-  }
-  for (int q = 0; q < c; q++)
-    for (int r2 = 0; r2 < c; r2++) S.linv[q][r2] = Mx[q][c + r2];
+  soc_set_build(&S, o->n_cones, c, o->cone_rows, o->As, o->bs, o->inner_rho, o->inner_max_iter, o->inner_threshold);
   SlsAdmm a;
   a.Nm = p->Nm; a.Nn = p->Nn; a.c = c; a.max_iter = o->max_iter; a.fixed_budget = o->fixed_budget;
   a.rho_u = o->rho_u; a.alpha = o->alpha; a.tol = o->tol;

@@ -22,12 +22,13 @@ class ProblemDesc(C.Structure):
                 ("Hp_b", C.c_void_p), ("n_obst", C.c_int32), ("obst_max_iter", C.c_int32),
                 ("obst_centers", C.c_void_p), ("obst_W", C.c_void_p), ("obst_W_inv", C.c_void_p),
                 ("obst_lower", C.c_void_p), ("obst_upper", C.c_double), ("obst_rho", C.c_double),
-                ("obst_threshold", C.c_double)]
+                ("obst_threshold", C.c_double), ("isls_dim", C.c_int32)]
 
 
 class SolveOpts(C.Structure):
     _fields_ = [("max_outer", C.c_int32), ("max_admm", C.c_int32), ("tol", C.c_double), ("outer_tol", C.c_double),
-                ("relax", C.c_double), ("fixed_budget", C.c_int32), ("last_stage_dp", C.c_int32)]
+                ("relax", C.c_double), ("fixed_budget", C.c_int32), ("last_stage_dp", C.c_int32),
+                ("stall_tol", C.c_double), ("osc_tol", C.c_double)]
 
 
 OUT_FIELDS = ["x", "u", "cost", "cost_log", "n_log", "status", "outer_iters", "admm_iters", "admm_exit", "res_log",
@@ -50,10 +51,11 @@ EXPORTS = ["isls_version", "isls_last_error_string", "isls_model_id", "isls_mode
            "isls_lqt_admm_dp_f64", "isls_riccati_f64", "isls_rollout_linesearch_f64", "isls_admm_project_dual_f64",
            "isls_measure_fp64_tflops", "isls_profile_enable", "isls_profile_collect",
            "isls_sls_plan_create", "isls_sls_plan_destroy", "isls_sls_operators", "isls_sls_solve_f64",
-           "isls_sls_admm_f64", "isls_sls_controller_f64", "isls_mc_rollout_f64", "isls_project_rows_f64"]
+           "isls_sls_admm_f64", "isls_sls_controller_f64", "isls_mc_rollout_f64", "isls_project_rows_f64",
+           "isls_isls_admm_solve_f64"]
 
 KERNEL_CLASSES = ["init", "kpass", "ff", "linesearch", "admm", "outer_end", "finalize", "backward_full", "accept",
-                  "lqt", "compact"]
+                  "lqt", "compact", "isls_cols", "isls_update"]
 
 _lib = None
 
@@ -80,6 +82,9 @@ def lib():
     solve_args = [C.c_void_p, C.POINTER(SolveOpts), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                   C.c_size_t, C.POINTER(SolveOut), C.c_void_p]
     L.isls_ilqr_admm_solve_f64.argtypes = solve_args
+    L.isls_isls_admm_solve_f64.argtypes = [C.c_void_p, C.POINTER(SolveOpts), C.POINTER(SlsAdmmOpts), C.c_int64, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(SolveOut),
+                                           C.c_void_p, C.c_void_p, C.c_void_p]
     L.isls_ilqr_solve_f64.argtypes = solve_args
     L.isls_lqt_admm_dp_f64.argtypes = [C.c_void_p, C.POINTER(SolveOpts), C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_size_t, C.POINTER(SolveOut), C.c_void_p]

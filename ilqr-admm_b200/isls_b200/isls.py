@@ -8,7 +8,7 @@ import torch
 
 from . import solver as S
 from ._lib import IslsError
-from .projections import Bound, ObstacleSets
+from .projections import Bound, ObstacleSets, SetConvexSOC
 from .utils import diag_of
 
 _MODEL_NAMES = ("car", "arm3", "double_integrator", "tassa_car")
@@ -199,18 +199,18 @@ class iSLS:
         return zs.expand(self.nb, zs.shape[-2], self.x_dim)
 
     def _solver(self, L, rho_x, bx, rho_u, bu, max_outer, max_admm, want_gains=False, want_masks=False,
-                obstacles=None):
+                obstacles=None, isls_dim=0):
         if self._model is None or self.zs is None:
             raise IslsError("set forward_model and a cost (set_quadratic_cost / cost_function) first")
         key = (L, None if rho_x is None else rho_x.tobytes(), None if bx is None else (bx[0].tobytes(), bx[1].tobytes()),
                None if rho_u is None else rho_u.tobytes(), None if bu is None else (bu[0].tobytes(), bu[1].tobytes()),
-               max_outer, max_admm, want_gains, want_masks, None if obstacles is None else obstacles.key())
+               max_outer, max_admm, want_gains, want_masks, None if obstacles is None else obstacles.key(), isls_dim)
         if key not in self._plan_cache:
             plan = S.Plan(self._model, self.N, self.x_dim, self.u_dim, self._dt(), self.Qdiag, self.seq, self.u_std,
                           L, rho_x=rho_x, lo_x=None if bx is None else bx[0], hi_x=None if bx is None else bx[1],
                           rho_u=rho_u, lo_u=None if bu is None else bu[0], hi_u=None if bu is None else bu[1],
                           cost=self._cost, obstacles=None if obstacles is None else obstacles.as_dict(),
-                          **self._cost_kw)
+                          isls_dim=isls_dim, **self._cost_kw)
             self._plan_cache.clear()
             self._plan_cache[key] = S.BatchSolver(plan, self.nb, self.device, max_outer=max_outer, max_admm=max_admm,
                                                   want_gains=want_gains, want_masks=want_masks)
@@ -290,6 +290,35 @@ class iSLS:
         if verbose:
             self._report(out)
         return out.res_log if log else out
+
+    def isls_admm(self, dim, get_AB=None, get_Cs=None, project_x=False, project_u=False, max_admm_iter=20, k_max=20,
+                  max_line_search=20, rho_x=None, rho_u=None, alpha=1, threshold=1e-3, verbose=False, log=False,
+                  fixed_budget=False):
+        """Robust nonlinear iSLS-ADMM (isls/isls.py:503-712): ADMM on [d_u | Phi_u(:, :dim)] - robustness with respect
+        to the first `dim` components of the initial state - with the row-wise SOC projection of the notebooks
+        (project_u: `SetConvexSOC`, the device form of `project_u(z, u_nom)` in 3DoF robot/State bounds and robust
+        control bounds.ipynb cell 25).  Returns (du [B, N m], phi_u [B, N m, dim]) like the reference."""
+        self._check_get_AB(get_AB)
+        self._check_get_Cs(get_Cs)
+        if project_x:
+            raise NotImplementedError("device isls_admm implements the control-side projection (project_u)")
+        if not isinstance(project_u, SetConvexSOC):
+            raise TypeError("project_u must be an isls_b200.projections.SetConvexSOC; Python callables cannot run "
+                            "inside the kernels")
+        _, Rr = self.compute_Rr_Qr(None, rho_u)
+        if Rr is None:
+            raise ValueError("rho_u is required")
+        inf = np.full((self.N, self.u_dim), np.inf)
+        sv = self._solver(max_line_search, None, None, Rr, (-inf, inf), k_max, max_admm_iter, isls_dim=int(dim))
+        sv.set_inputs(self._x0, self._u_init, self._zs_b())
+        out = sv.isls_admm(project_u, tol=threshold, relax=float(alpha), fixed_budget=fixed_budget)
+        self._publish(out)
+        if verbose:
+            self._report(out)
+        B_ = self.nb
+        du = out.d_u.reshape(B_, self.N * self.u_dim)
+        phi = out.phi_u.reshape(B_, self.N * self.u_dim, int(dim))
+        return (du[0], phi[0]) if self.batch is None else (du, phi)
 
     def _report(self, out):
         st = out.status.cpu().numpy()

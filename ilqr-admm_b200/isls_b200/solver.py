@@ -42,7 +42,7 @@ class Plan:
     diagonal ADMM penalties and box bounds."""
 
     def __init__(self, model, N, n, m, dt, Qdiag, seq, u_std, L, rho_x=None, lo_x=None, hi_x=None, rho_u=None,
-                 lo_u=None, hi_u=None, cost="quadratic", Rdiag=None, Hp=None, Qdiag_b=None, Hp_b=None, obstacles=None):
+                 lo_u=None, hi_u=None, cost="quadratic", Rdiag=None, Hp=None, Qdiag_b=None, Hp_b=None, obstacles=None, isls_dim=0):
         """cost="pseudo_huber": Qdiag / Hp are the weights and smoothness scales [n_via, n] of the first term,
         Qdiag_b / Hp_b of the optional second one (Tutorial cell 14); Rdiag [m] replaces R = u_std I."""
         L_ = _lib.lib()
@@ -74,7 +74,8 @@ class Plan:
             if arr is not None:
                 keep[nm] = _f64(arr, shp)
         d = _lib.ProblemDesc(model_id=mid, n=n, m=m, N=N, n_via=self.n_via, L=L, dt=dt, u_std=float(u_std),
-                             cost_kind=COST_KINDS[cost])
+                             cost_kind=COST_KINDS[cost], isls_dim=int(isls_dim))
+        self.isls_dim = int(isls_dim)
         if obstacles is not None:
             ob = obstacles
             K = len(ob["centers"])
@@ -180,11 +181,12 @@ class BatchSolver:
         self._stage(self.u_init, u_init, "u_init")
         self._stage(self.zs, zs, "zs")
 
-    def _opts(self, tol, outer_tol, relax, fixed_budget, last_stage_dp, max_outer=None, max_admm=None):
+    def _opts(self, tol, outer_tol, relax, fixed_budget, last_stage_dp, max_outer=None, max_admm=None, stall_tol=0.0,
+              osc_tol=0.0):
         return _lib.SolveOpts(max_outer=self.max_outer if max_outer is None else max_outer,
                               max_admm=self.max_admm if max_admm is None else max_admm, tol=tol,
                               outer_tol=outer_tol, relax=relax, fixed_budget=int(fixed_budget),
-                              last_stage_dp=int(last_stage_dp))
+                              last_stage_dp=int(last_stage_dp), stall_tol=stall_tol, osc_tol=osc_tol)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -196,6 +198,30 @@ class BatchSolver:
                                                      _dptr(self.u_init), _dptr(self.zs), C.c_void_p(self._ws_ptr),
                                                      self._ws_bytes, C.byref(self._cout), self._stream())
         _lib.check(rc, "isls_ilqr_admm_solve_f64")
+        return self.out
+
+    def isls_admm(self, soc, tol=1e-3, relax=1.0, fixed_budget=False):
+        """Robust iSLS-ADMM (isls_isls_admm_solve_f64; isls/isls.py:503-712).  soc: projections.SetConvexSOC.
+        Adds d_u [B,N,m] and phi_u [B,N,m,dim] to the results."""
+        p, dev = self.plan, self.device
+        if p.isls_dim < 1:
+            raise _lib.IslsError("the plan was not created with isls_dim > 0")
+        C_ = p.isls_dim + 1
+        if soc.As.shape[1:] != (C_ + 1, C_):
+            raise ValueError("cone matrices must be [%d, %d] (dim + 2 rows, dim + 1 columns)" % (C_ + 1, C_))
+        o = self._opts(tol, 1e-4, relax, fixed_budget, False, stall_tol=1e-3, osc_tol=1e-3)   # isls.py:664, 700, 704
+        so = _lib.SlsAdmmOpts(max_iter=0, rho_u=0.0, alpha=relax, tol=tol, fixed_budget=int(fixed_budget),
+                              n_cones=soc.As.shape[0], cone_rows=C_ + 1, As=soc.As.ctypes.data, bs=soc.bs.ctypes.data,
+                              inner_rho=soc.rho, inner_max_iter=soc.max_iter, inner_threshold=soc.threshold)
+        if "d_u" not in self.out:
+            f64 = dict(dtype=torch.float64, device=dev)
+            self.out.update(d_u=torch.empty(self.B, p.N, p.m, **f64), phi_u=torch.empty(self.B, p.N, p.m, p.isls_dim, **f64))
+        with torch.cuda.device(dev):
+            rc = _lib.lib().isls_isls_admm_solve_f64(p.handle, C.byref(o), C.byref(so), self.B, _dptr(self.x0),
+                                                     _dptr(self.u_init), _dptr(self.zs), C.c_void_p(self._ws_ptr),
+                                                     self._ws_bytes, C.byref(self._cout), _dptr(self.out.d_u),
+                                                     _dptr(self.out.phi_u), self._stream())
+        _lib.check(rc, "isls_isls_admm_solve_f64")
         return self.out
 
     def ilqr(self, tol_fun=1e-5, fixed_budget=False):

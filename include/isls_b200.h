@@ -97,6 +97,8 @@ typedef struct isls_problem_desc {
   const double *obst_W_inv;    /* [n_obst, 2, 2] */
   const double *obst_lower;    /* [n_obst] */
   double obst_upper, obst_rho, obst_threshold;
+  int32_t isls_dim;            /* > 0: the plan is used by isls_isls_admm_solve_f64 with `dim` robustness columns
+                                  (workspace for the [d_u | Phi_u(:, :dim)] matrix variables); <= 3 */
 } isls_problem_desc;
 #define ISLS_MAX_OBST 4
 
@@ -113,6 +115,8 @@ typedef struct isls_solve_opts {
   int32_t fixed_budget;    /* 1: ignore every stop test (deterministic work, used by the benchmark) */
   int32_t last_stage_dp;   /* 0: batch-form last control du_{N-1} = -Cuu^-1 cu (isls/isls.py:441-465);
                               1: DP form K[N-1]=k[N-1]=0 (isls/isls.py:245-246) */
+  double stall_tol;        /* ADMM relative-change stop threshold; 0: = tol (admm.py:80); isls_admm: 1e-3 (isls.py:664) */
+  double osc_tol;          /* oscillation test threshold; 0: = outer_tol; isls_admm: 1e-3 with outer_tol 1e-4 */
 } isls_solve_opts;
 
 /* Results, natural layouts, DEVICE pointers.  Optional outputs may be NULL. */
@@ -157,6 +161,20 @@ int isls_workspace_bytes(const isls_plan *plan, int64_t B, size_t *bytes);
 int isls_ilqr_admm_solve_f64(const isls_plan *plan, const isls_solve_opts *opts, int64_t B,
                              const double *x0_dev, const double *u_init_dev, const double *zs_dev,
                              void *workspace_dev, size_t workspace_bytes, const isls_solve_out *out, void *stream);
+
+/* Method isls_admm of iSLS, isls/isls.py:503-712: robust nonlinear iSLS-ADMM on the matrix variable [d_u | Phi_u(:, :dim)]
+ * (robustness with respect to the first `dim` components of the initial state) with the row-wise projection
+ * project_u(z, u_nom) = project_set_convex over second-order cones (3DoF robot/State bounds and robust control
+ * bounds.ipynb cells 24-26; `soc` describes the cones like isls_sls_admm_opts: n_cones, cone_rows = dim + 2, As, bs,
+ * inner_rho, inner_max_iter, inner_threshold; its other fields are ignored).  Riccati form: one K-pass per outer
+ * iteration, dim + 1 feed-forward passes + linear rollouts per ADMM iteration instead of the dense (N m)^2 inverse of
+ * isls.py:562-579.  The plan needs rho_u (Rr = diag) and isls_dim = dim; N * m <= 1024.
+ *   du_dev [B, N, m] (= x_u[:, 0]), phi_u_dev [B, N, m, dim] (= x_u[:, 1:]) of the last ADMM iterate. */
+struct isls_sls_admm_opts;
+int isls_isls_admm_solve_f64(const isls_plan *plan, const isls_solve_opts *opts, const struct isls_sls_admm_opts *soc,
+                             int64_t B, const double *x0_dev, const double *u_init_dev, const double *zs_dev,
+                             void *workspace_dev, size_t workspace_bytes, const isls_solve_out *out, double *du_dev,
+                             double *phi_u_dev, void *stream);
 
 /* iSLS.solve(method='dp') (isls/isls.py:54-132, 229-374): unconstrained iLQR with closed-loop line search. */
 int isls_ilqr_solve_f64(const isls_plan *plan, const isls_solve_opts *opts, int64_t B,
@@ -279,7 +297,9 @@ int isls_project_rows_f64(int32_t kind, int64_t rows, int32_t dim, const double 
 #define ISLS_KC_ACCEPT 8
 #define ISLS_KC_LQT 9
 #define ISLS_KC_COMPACT 10
-#define ISLS_KC_COUNT 11
+#define ISLS_KC_ISLS_COLS 11
+#define ISLS_KC_ISLS_UPDATE 12
+#define ISLS_KC_COUNT 13
 /* thread-local switch: when on, every kernel launch of a solve is bracketed by a CUDA event pair on the
  * launching stream (adds a few microseconds per launch; use for per-kernel durations, not for throughput) */
 int isls_profile_enable(int on);
