@@ -105,4 +105,35 @@ if __name__ == "__main__":
     res["C4 SLS-ADMM DI B=1024"] = dict(plan_ms=round(t_plan, 1), admm_ms=round(ms_admm, 2), controller_ms=round(ms_ctl, 2),
                                         problems_per_s=round(Bn / (ms_admm + ms_ctl) * 1e3),
                                         mean_iters=float(s.last.iters.double().mean()))
+    # ---- widened rows: same measurement, reference stop rules
+    import gpu_util
+
+    def widened(name, p, runner, **kw):
+        B = p["x0"].shape[0]
+        holder = {}
+
+        def run():
+            holder["o"] = runner(p, **kw)
+        run()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3            # includes the host-side staging and the D2H of the results
+        S.profile_enable(True)
+        run()
+        prof = S.profile_collect()
+        S.profile_enable(False)
+        o = holder["o"]
+        res[name] = dict(ms=round(ms, 2), problems_per_s=round(B / ms * 1e3),
+                         mean_outer=float(np.mean(o["outer_iters"])), mean_cost=float(np.mean(o["cost"])),
+                         kernels_ms={k: round(v[0], 3) for k, v in prof.items()})
+    widened("8f#3 Tutorial Tassa car + pseudo-Huber iLQR-ADMM N=150 B=4096", configs.tassa_batch(4096),
+            gpu_util.run_ilqr_admm, fixed_budget=a.fixed, want_masks=False)
+    widened("8f#3 Tutorial Tassa car + pseudo-Huber iLQR (dp) N=150 B=4096", configs.tassa_batch(4096),
+            lambda p, **kw: gpu_util.run_ilqr_dp(p, 100, 40, **kw), fixed_budget=a.fixed)
+    widened("8f#2 parking between two cars (obstacle-set state projection) N=200 B=1024",
+            configs.parking_batch(1024, N=200, dt=0.075), gpu_util.run_ilqr_admm, fixed_budget=a.fixed)
+    widened("8f#1 robust iSLS-ADMM 3-DoF arm N=100 B=1024", configs.arm_robust_batch(1024), gpu_util.run_isls_admm,
+            fixed_budget=a.fixed)
     print(json.dumps(res, indent=1))
