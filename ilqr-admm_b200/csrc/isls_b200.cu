@@ -82,7 +82,7 @@ struct Dev {
   int n_obst, obst_max_iter;
   double obst_upper, obst_rho, obst_threshold;
   const double *ob_c, *ob_W, *ob_Wi, *ob_lo;
-  double *obw;           // workspace [3 + 2K][T][N][n][32]: winner x, pre-projection point, inner x, z_k, lambda_k
+  double *obw;           // workspace [2][T][N][n][32]: winner x, pre-projection point
   // robust iSLS-ADMM: C = dim + 1 columns [d_u | Phi_u(:, :dim)]; Zm, Lm (ADMM z, lambda, delta coordinates) and Xu
   // (primal iterate) are [T][N][m * C][32] with component index j * C + c
   int isls_C, ls_cost_only;
@@ -1195,8 +1195,9 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
 // ---- state projection onto the outside of obstacle sets: project_set_convex (isls/projections.py:289-374) with
 // As = I, bs = 0 and per-set projections  p -> c + W^-1 Pi_sq(W (p - c))  on the position (project_square_batch,
 // projections.py:246-255; Car/Iterative LQR with state constraints.ipynb cell 18).  One problem per thread; all N rows
-// are projected together (the reference's stop rule is the maximum over sets and rows), so the inner ADMM sweeps the
-// rows once per iteration with z_k, lambda_k kept in the workspace.  Returns the number of inner iterations.
+// are projected together (the reference's stop rule is the maximum over sets and rows): k_admm parks the winner's
+// states and the pre-projection points, k_obst_project (one CTA per problem, one thread per row, z_k / lambda_k in
+// registers, block reductions for the stop rule) projects and finishes the ADMM update.
 __device__ __forceinline__ void obst_project_one(const Dev &d, int k, double (&y)[2]) {
   const double c0 = d.ob_c[2 * k], c1 = d.ob_c[2 * k + 1];
   const double *W = d.ob_W + 4 * k, *Wi = d.ob_Wi + 4 * k;
@@ -1212,72 +1213,6 @@ __device__ __forceinline__ void obst_project_one(const Dev &d, int k, double (&y
   w1 = fmax(fmin(w1, up), -up);
   y[0] = (w0 * Wi[0] + w1 * Wi[1]) + c0;                                  // zp @ W_inv.T + c
   y[1] = (w0 * Wi[2] + w1 * Wi[3]) + c1;
-}
-
-template <class M>
-__device__ __forceinline__ int obst_project_rows(const Dev &d, const TileCtx<M> &c) {
-  constexpr int n = M::n;
-  const int K = d.n_obst, N = d.N;
-  const size_t arr = (size_t)d.T * N * n * TILE;                          // one [T][N][n][32] array
-  const double *pre = c.at(d.obw + arr, d, n);
-  double *xin = c.at(d.obw + 2 * arr, d, n);
-  const double rho = d.obst_rho;
-  const double inv = 1.0 / (1.0 + rho * K);                               // inv(I + rho sum A_i'A_i), A_i = I
-  double prim_ = 1e5, dual_ = 1e5;
-  int it = 0;
-  for (int j = 0; j < d.obst_max_iter; j++) {
-    it = j + 1;
-    double pmax = 0.0, dmax = 0.0;
-    for (int t = 0; t < N; t++) {
-      double x0[n], zk[ISLS_MAX_OBST][n], lk[ISLS_MAX_OBST][n], x[n];
-#pragma unroll
-      for (int i = 0; i < n; i++) x0[i] = EL(pre, n, t, i);
-      for (int k = 0; k < K; k++) {
-        const double *zp = c.at(d.obw + (3 + 2 * k) * arr, d, n), *lp = c.at(d.obw + (4 + 2 * k) * arr, d, n);
-#pragma unroll
-        for (int i = 0; i < n; i++) {
-          zk[k][i] = j == 0 ? x0[i] : EL(zp, n, t, i);                    // z_i = A_i x0 + b_i, lambda_i = 0
-          lk[k][i] = j == 0 ? 0.0 : EL(lp, n, t, i);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < n; i++) {
-        double r = 0.0;
-        for (int k = 0; k < K; k++) r = r + (zk[k][i] - lk[k][i]);
-        x[i] = inv * (x0[i] + rho * r);
-        EL(xin, n, t, i) = x[i];
-      }
-      for (int k = 0; k < K; k++) {
-        double *zp = c.at(d.obw + (3 + 2 * k) * arr, d, n), *lp = c.at(d.obw + (4 + 2 * k) * arr, d, n);
-        double zn[n], y[2];
-#pragma unroll
-        for (int i = 0; i < n; i++) zn[i] = x[i] + lk[k][i];
-        y[0] = zn[0]; y[1] = zn[1];
-        obst_project_one(d, k, y);
-        zn[0] = y[0]; zn[1] = y[1];
-        double ps = 0.0, ds = 0.0;
-#pragma unroll
-        for (int i = 0; i < n; i++) {
-          const double pr = x[i] - zn[i], du_ = rho * (zn[i] - zk[k][i]);
-          ps += pr * pr;
-          ds += du_ * du_;
-          EL(zp, n, t, i) = zn[i];
-          EL(lp, n, t, i) = lk[k][i] + pr;
-        }
-        pmax = fmax(pmax, sqrt(ps));
-        dmax = fmax(dmax, sqrt(ds));
-      }
-    }
-    const double pprim = prim_, pdual = dual_;
-    prim_ = pmax;
-    dual_ = dmax;
-    if (prim_ < d.obst_threshold && dual_ < d.obst_threshold) break;
-    if (j < d.obst_max_iter - 1) {
-      const double pc = fabs(pprim - prim_) / (pprim + 1e-30), dc = fabs(pdual - dual_) / (pdual + 1e-30);
-      if (pc < 1e-5 && dc < 1e-5) break;
-    }
-  }
-  return it;
 }
 
 // Winner rollout + ADMM update: re-roll the chosen candidate (the primal iterate (x,u) returned by f_argmin,
@@ -1349,29 +1284,13 @@ __device__ __forceinline__ void admm_body(const Dev &d, const TileCtx<M> &c, int
 #pragma unroll
     for (int i = 0; i < n; i++) x[i] = xn[i];
   }
-  if (d.proj_x && d.n_obst > 0) {
-    const int its = obst_project_rows<M>(d, c);
-    if (c.valid && d.out.inner_iters)
-      d.out.inner_iters[((size_t)c.ob * d.max_outer + outer) * d.max_admm + inner] = its;
-    const size_t arr = (size_t)d.T * d.N * n * TILE;
-    const double *xw = c.at(d.obw, d, n), *xin = c.at(d.obw + 2 * arr, d, n);
-    for (int t = 0; t < d.N; t++) {
-      double xv[n], zn[n], zo[n], lv[n];
-#pragma unroll
-      for (int i = 0; i < n; i++) { xv[i] = EL(xw, n, t, i); zn[i] = EL(xin, n, t, i); zo[i] = EL(zx, n, t, i); lv[i] = EL(lx, n, t, i); }
-#pragma unroll
-      for (int i = 0; i < n; i++) {                       // admm.py:49-59 with z = project_x(.)
-        const double r = __dsub_rn(xv[i], zn[i]), dz = __dsub_rn(zn[i], zo[i]);
-        lv[i] = __dadd_rn(lv[i], r);
-        prx = fma(r, r, prx);
-        drx = fma(dz, dz, drx);
-        EL(zx, n, t, i) = zn[i];
-        EL(lx, n, t, i) = lv[i];
-        EL(rgx, n, t, i) = __dsub_rn(zn[i], lv[i]);
-      }
-    }
-  }
   d.cost_adm[c.b] = cs + d.u_std * cc;
+  if (d.proj_x && d.n_obst > 0) {                         // k_obst_project finishes: park the control-side residual
+    const size_t S = (size_t)d.T * TILE;                  // sums in two cq rows (free between the line search and k_ff)
+    d.cq[3 * S + c.b] = pru;
+    d.cq[4 * S + c.b] = dru;
+    return;
+  }
   admm_finish<M>(d, c, outer, inner, bi, sqrt(prx) + sqrt(pru), sqrt(drx) + sqrt(dru));   // admm.py:62-69
 }
 
@@ -1596,6 +1515,95 @@ __global__ void k_isls_out(Dev d, double *du_out, double *phi_out) {
       du_out[((size_t)c.ob * d.N + t) * m + j] = EL(Xu, m * C, t, j * C);
       for (int q = 1; q < C; q++) phi_out[(((size_t)c.ob * d.N + t) * m + j) * (C - 1) + q - 1] = EL(Xu, m * C, t, j * C + q);
     }
+}
+
+// Obstacle-set projection of all rows of one problem + the rest of the ADMM update (admm.py:49-97): CTA = problem,
+// thread = row t.  x = (x0 + rho sum_k (z_k - lambda_k)) / (1 + K rho); z_k = Pi_k(x + lambda_k); lambda_k += x - z_k;
+// stop on the maximum over sets and rows of ||x - z_k||, rho ||z_k - z_k_prev|| (< threshold), or both maxima changing
+// by < 1e-5 relative, or max_iter (projections.py:289-374 with As = I, bs = 0).
+template <class M>
+__global__ void k_obst_project(Dev d, int outer, int inner) {
+  constexpr int n = M::n;
+  __shared__ double red[32];
+  const long long b = blockIdx.x;
+  TileCtx<M> c(d, (int)(b / TILE), (int)(b % TILE));
+  if (!c.valid || d.odone[c.b] || d.adone[c.b]) return;               // uniform over the CTA
+  const int K = d.n_obst, N = d.N;
+  const size_t arr = (size_t)d.T * N * n * TILE;
+  const double *xw = c.at(d.obw, d, n), *pre = c.at(d.obw + arr, d, n);
+  double *zx = c.at(d.zx, d, n), *lx = c.at(d.lx, d, n), *rgx = c.at(d.rgx, d, n);
+  const double rho = d.obst_rho, inv = 1.0 / (1.0 + rho * K);         // inv(I + rho sum A_i'A_i), A_i = I
+  double prx = 0.0, drx = 0.0;
+  int its = 0;
+  // rows are handled in slabs of blockDim.x; the stop rule couples all rows, so for N > blockDim.x every thread keeps
+  // the state of its rows of every slab (N <= 1024 in all notebooks: one slab)
+  const int t = threadIdx.x;
+  const bool act = t < N;
+  double x0[n], x[n], zk[ISLS_MAX_OBST][n], lk[ISLS_MAX_OBST][n];
+#pragma unroll
+  for (int i = 0; i < n; i++) {
+    x0[i] = act ? EL(pre, n, t, i) : 0.0;
+    x[i] = x0[i];
+    for (int k = 0; k < K; k++) { zk[k][i] = x0[i]; lk[k][i] = 0.0; }  // z_i = A_i x0 + b_i, lambda_i = 0
+  }
+  double prim_ = 1e5, dual_ = 1e5;
+  for (int j = 0; j < d.obst_max_iter; j++) {
+    its = j + 1;
+    double pmax = 0.0, dmax = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+      double r = 0.0;
+      for (int k = 0; k < K; k++) r = r + (zk[k][i] - lk[k][i]);
+      x[i] = inv * (x0[i] + rho * r);
+    }
+    for (int k = 0; k < K; k++) {
+      double zn[n], y[2];
+#pragma unroll
+      for (int i = 0; i < n; i++) zn[i] = x[i] + lk[k][i];
+      y[0] = zn[0]; y[1] = zn[1];
+      obst_project_one(d, k, y);
+      zn[0] = y[0]; zn[1] = y[1];
+      double ps = 0.0, ds = 0.0;
+#pragma unroll
+      for (int i = 0; i < n; i++) {
+        const double pr = x[i] - zn[i], du_ = rho * (zn[i] - zk[k][i]);
+        ps += pr * pr;
+        ds += du_ * du_;
+        zk[k][i] = zn[i];
+        lk[k][i] += pr;
+      }
+      pmax = fmax(pmax, sqrt(ps));
+      dmax = fmax(dmax, sqrt(ds));
+    }
+    const double pprim = prim_, pdual = dual_;
+    prim_ = block_max(act ? pmax : 0.0, red);
+    dual_ = block_max(act ? dmax : 0.0, red);
+    if (prim_ < d.obst_threshold && dual_ < d.obst_threshold) break;
+    if (j < d.obst_max_iter - 1) {
+      const double pc = fabs(pprim - prim_) / (pprim + 1e-30), dc = fabs(pdual - dual_) / (pdual + 1e-30);
+      if (pc < 1e-5 && dc < 1e-5) break;
+    }
+  }
+  if (act) {
+#pragma unroll
+    for (int i = 0; i < n; i++) {                                      // admm.py:49-59 with z = project_x(.)
+      const double xv = EL(xw, n, t, i), zo = EL(zx, n, t, i);
+      const double r = __dsub_rn(xv, x[i]), dz = __dsub_rn(x[i], zo);
+      const double lv = __dadd_rn(EL(lx, n, t, i), r);
+      prx = fma(r, r, prx);
+      drx = fma(dz, dz, drx);
+      EL(zx, n, t, i) = x[i];
+      EL(lx, n, t, i) = lv;
+      EL(rgx, n, t, i) = __dsub_rn(x[i], lv);
+    }
+  }
+  const double ps = block_sum(prx, red), ds = block_sum(drx, red);
+  if (threadIdx.x == 0) {
+    if (d.out.inner_iters) d.out.inner_iters[((size_t)c.ob * d.max_outer + outer) * d.max_admm + inner] = its;
+    const size_t S = (size_t)d.T * TILE;
+    const double pru = d.cq[3 * S + c.b], dru = d.cq[4 * S + c.b];     // control-side sums parked by k_admm
+    admm_finish<M>(d, c, outer, inner, d.best[c.b], sqrt(ps) + sqrt(pru), sqrt(ds) + sqrt(dru));
+  }
 }
 
 // After ADMM (isls/isls.py:488-499): nominal <- last primal iterate, cost log, outer stop tests.
@@ -2429,8 +2437,8 @@ extern "C" int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan)
   if (desc->isls_dim > 0 && (!desc->rho_u || (long long)desc->N * desc->m > 1024))
     return fail(ISLS_E_UNSUPPORTED, "isls_admm needs rho_u and N * u_dim <= 1024");
   if (desc->n_obst > 0 && (!desc->rho_x || !desc->obst_centers || !desc->obst_W || !desc->obst_W_inv || !desc->obst_lower ||
-                           desc->obst_max_iter < 1 || desc->n < 2))
-    return fail(ISLS_E_INVALID, "obstacle sets need rho_x, centres, W, W_inv, lower and obst_max_iter >= 1");
+                           desc->obst_max_iter < 1 || desc->n < 2 || desc->N > 1024))
+    return fail(ISLS_E_INVALID, "obstacle sets need rho_x, centres, W, W_inv, lower, obst_max_iter >= 1 and N <= 1024");
   if (desc->rho_x && !desc->n_obst && (!desc->lo_x || !desc->hi_x)) return fail(ISLS_E_INVALID, "rho_x without lo_x/hi_x");
   if (desc->rho_u && (!desc->lo_u || !desc->hi_u)) return fail(ISLS_E_INVALID, "rho_u without lo_u/hi_u");
   const int n = desc->n, m = desc->m, N = desc->N;
@@ -2550,7 +2558,7 @@ static size_t carve(const isls_plan *p, long long B, char *base, Dev *d, Dev *al
   takeD(d ? &d->kk : nullptr, tm);
   takeD(d ? &d->zs : nullptr, T * p->n_via * n * TILE);
   takeD(d ? &d->lsc : nullptr, T * p->L * TILE);
-  takeD(d ? &d->obw : nullptr, p->desc.n_obst > 0 ? (3 + 2 * (size_t)p->desc.n_obst) * tn : 0);
+  takeD(d ? &d->obw : nullptr, p->desc.n_obst > 0 ? 2 * tn : 0);
   const size_t tC = p->desc.isls_dim > 0 ? tm * (size_t)(p->desc.isls_dim + 1) : 0;
   takeD(d ? &d->Zm : nullptr, tC); takeD(d ? &d->Lm : nullptr, tC); takeD(d ? &d->Xu : nullptr, tC);
   const size_t S = T * TILE;
@@ -2749,7 +2757,12 @@ extern "C" int isls_ilqr_admm_solve_f64(const isls_plan *plan, const isls_solve_
           const int fuse = (!d.proj_x && d.proj_u && !no_fused_update()) ? 1 : 0;      // streaming ADMM epilogue
           LAUNCH(ISLS_KC_FF, cs, launch_ff<M>(dc, cs));
           LAUNCH(ISLS_KC_LINESEARCH, cs, launch_linesearch<M>(dc, false, cs, LsFuse{fuse, j, a}));
-          if (!fuse) LAUNCH(ISLS_KC_ADMM, cs, (k_admm<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, j, a)));
+          if (!fuse) {
+            ProfScope ps__(ISLS_KC_ADMM, cs);
+            k_admm<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, j, a);
+            if (d.n_obst > 0)        // obstacle sets: all rows of a problem are projected together, CTA = problem
+              k_obst_project<M><<<(unsigned)((dc.tile1 - dc.tile0) * TILE), ((d.N + 31) / 32) * 32, 0, cs>>>(dc, j, a);
+          }
         }
         LAUNCH(ISLS_KC_OUTER_END, cs, (k_outer_end<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, j)));
         if (compact && j + 1 < d.max_outer && (j + 1) % solve_compact() == 0) {
