@@ -2232,7 +2232,12 @@ __global__ void k_lqt_admm(Dev d, const double *x0_in) {
         v[i] = g;
       }
 #pragma unroll
-      for (int j = 0; j < m; j++) EL(kk, m, t, j) = 0.0;
+      for (int j = 0; j < m; j++) {
+        // DP form: k[N-1] = 0 (sls.py:113-114); batch form (ADMM_LQT_Batch, sls.py:283-286): the last control is
+        // solved for, u_{N-1} = (R + Rr)^-1 Rr reg_u
+        const double cuL = d.proj_u ? -2.0 * d.rho_u[t * m + j] * (EL(zu, m, t, j) - EL(lu, m, t, j)) : 0.0;
+        EL(kk, m, t, j) = d.last_stage_dp ? 0.0 : -cuL / (2.0 * (d.u_std * d.Rw[j] + d.rho_u[t * m + j]));
+      }
     }
     for (int t = d.N - 2; t >= 0; t--) {
       double cx[n], cu[m], Qux[m][n], Quu[m][m], Qui[m][m], kt[m];
@@ -2864,6 +2869,19 @@ extern "C" int isls_isls_admm_solve_f64(const isls_plan *plan, const isls_solve_
   });
 }
 
+// ADMM warm start of the LQT path from natural-layout arrays (ADMM_LQT_Batch: the unconstrained solution, sls.py:266-268)
+template <class M>
+__global__ void k_pack_zinit(Dev d, const double *zx_in, const double *zu_in) {
+  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (tile >= d.tile1) return;
+  TileCtx<M> c(d, tile, threadIdx.x);
+  double *zx = c.at(d.zx, d, M::n), *zu = c.at(d.zu, d, M::m);
+  for (int t = 0; t < d.N; t++) {
+    if (zx_in) for (int i = 0; i < M::n; i++) EL(zx, M::n, t, i) = zx_in[(c.ob * d.N + t) * M::n + i];
+    if (zu_in) for (int j = 0; j < M::m; j++) EL(zu, M::m, t, j) = zu_in[(c.ob * d.N + t) * M::m + j];
+  }
+}
+
 template <class M>
 __global__ void k_pack_zs(Dev d, const double *zs_in) {
   const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
@@ -2911,6 +2929,8 @@ extern "C" int isls_lqt_admm_dp_f64(const isls_plan *plan, const isls_solve_opts
     k_kpass<M><<<1, dim3(TILE, 1), 0, s>>>(d1);
     // the K-pass reset (lambda = 0, reg = z) touched tile 0 only with zeros: state stays zero
     k_pack_zs<M><<<tp_grid(d), tp_block(), 0, s>>>(d, zs);
+    if (opts->z_x_init_dev || opts->z_u_init_dev)
+      k_pack_zinit<M><<<tp_grid(d), tp_block(), 0, s>>>(d, opts->z_x_init_dev, opts->z_u_init_dev);
     LAUNCH(ISLS_KC_LQT, s, (k_lqt_admm<M><<<tp_grid(d), tp_block(), 0, s>>>(d, x0)));
     Dev df = d;
     df.out.K = nullptr;          // gains are shared: unpacked by k_lqt_unpack_K

@@ -28,7 +28,8 @@ class ProblemDesc(C.Structure):
 class SolveOpts(C.Structure):
     _fields_ = [("max_outer", C.c_int32), ("max_admm", C.c_int32), ("tol", C.c_double), ("outer_tol", C.c_double),
                 ("relax", C.c_double), ("fixed_budget", C.c_int32), ("last_stage_dp", C.c_int32),
-                ("stall_tol", C.c_double), ("osc_tol", C.c_double)]
+                ("stall_tol", C.c_double), ("osc_tol", C.c_double), ("z_x_init_dev", C.c_void_p),
+                ("z_u_init_dev", C.c_void_p)]
 
 
 OUT_FIELDS = ["x", "u", "cost", "cost_log", "n_log", "status", "outer_iters", "admm_iters", "admm_exit", "res_log",

@@ -357,6 +357,26 @@ class iSLS:
     def AB(self, value):
         self.A, self.B = value[0], value[1]
 
+    def rollout_DP(self, K, k):
+        """Closed-loop rollouts u_t = K_t (x_t - x^_t) + k_t + u^_t around the current nominal trajectory for every
+        feed-forward sequence k[l] (isls/isls.py:310-334; k: [L, N, m] = k_t scaled by the line-search step sizes).
+        Single-problem objects only (like the reference); returns x_log [L, N, n], u_log [L, N, m]."""
+        if self.batch is not None or self.x_nom is None:
+            raise IslsError("rollout_DP needs a single-problem iSLS with nominal values (after solve / iterate_once_dp)")
+        dev = self.device
+        t = lambda a: torch.as_tensor(a, dtype=torch.float64).to(dev)
+        K, k = t(K), t(k)
+        if k.ndim == 2:
+            k = k[None]
+        xn, un = self.x_nom, self.u_nom
+        kabs = k + (un - torch.einsum("tij,tj->ti", K, xn))[None]             # absolute form u = K x + k'
+        xs, us = [], []
+        for l in range(k.shape[0]):
+            x, u = S.mc_rollout(self._model, self.x_dim, self.u_dim, self.N, self._dt(), "dp", xn[:1], K, kabs[l],
+                                device=dev)
+            xs.append(x[0]); us.append(u[0])
+        return torch.stack(xs), torch.stack(us)
+
     def rollout_batch(self, x_nom, u_nom):
         """Open-loop rollout from x_nom[0] for every control sequence in u_nom [nb,N,m] (isls/isls.py:135-154)."""
         x_nom = torch.as_tensor(np.asarray(x_nom)) if not isinstance(x_nom, torch.Tensor) else x_nom

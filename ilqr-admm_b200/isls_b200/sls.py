@@ -65,7 +65,8 @@ class SLS:
             r = diag_of(r, "rho")
         return np.ascontiguousarray(np.broadcast_to(r, (self.N, dim)))
 
-    def _lqt(self, x0, project_x, project_u, max_iter, rho_x, rho_u, alpha, tol, fixed_budget, want_masks):
+    def _lqt(self, x0, project_x, project_u, max_iter, rho_x, rho_u, alpha, tol, fixed_budget, want_masks,
+             last_stage_dp=True, z_init=None):
         bx = project_x.expand(self.N, self.x_dim) if project_x else None
         bu = project_u.expand(self.N, self.u_dim) if project_u else None
         plan = S.Plan("double_integrator", self.N, self.x_dim, self.u_dim, self._dt, self.Qdiag, self.seq, self.u_std,
@@ -80,7 +81,8 @@ class SLS:
         sv.set_inputs(x0.reshape(-1, self.x_dim).expand(self.nb, self.x_dim),
                       torch.zeros(self.N, self.u_dim, dtype=torch.float64),
                       zs.expand(self.nb, zs.shape[-2], self.x_dim))
-        out = sv.lqt_admm_dp(tol=tol, relax=float(alpha), fixed_budget=fixed_budget)
+        out = sv.lqt_admm_dp(tol=tol, relax=float(alpha), fixed_budget=fixed_budget, last_stage_dp=last_stage_dp,
+                             z_x_init=None if z_init is None else z_init[0], z_u_init=None if z_init is None else z_init[1])
         self.last = out
         return out
 
@@ -145,6 +147,35 @@ class SLS:
         if log:
             ret += (sq(out.res_log[:, 0]),)
         return ret
+
+    def ADMM_LQT_Batch(self, x0, project_x=False, project_u=False, max_iter=20, rho_x=None, rho_u=None, alpha=1.0,
+                       tol=1e-3, verbose=False, log=False, fixed_budget=False, want_masks=False):
+        """LQT-ADMM in "batch" form (isls/sls.py:250-294).  The reference's dense least-squares argmin is the same LQ
+        minimiser the Riccati recursion computes, except that its last control is solved for (u_{N-1} = (R + Rr)^-1 Rr
+        reg_u) and ADMM starts from the unconstrained solution (sls.py:266-268); both are reproduced here on top of
+        the LQT kernel.  Returns (x, u[, logs])."""
+        self._check_lqt()
+        for nm, pr in (("project_x", project_x), ("project_u", project_u)):
+            if pr and not isinstance(pr, Bound):
+                raise TypeError("%s must be an isls_b200.projections.Bound" % nm)
+        unc = self._lqt(x0, False, False, 1, None, None, 1.0, 0.0, True, False)          # z_x_init, z_u_init
+        z_init = (unc.x.clone(), unc.u.clone())
+        out = self._lqt(x0, project_x, project_u, max_iter, rho_x, rho_u, alpha, tol, fixed_budget, want_masks,
+                        last_stage_dp=False, z_init=z_init)
+        sq = (lambda t: t[0]) if self.batch is None else (lambda t: t)
+        ret = (sq(out.x).reshape(*out.x.shape[:-2], -1) if self.batch is not None else out.x[0].reshape(-1),
+               sq(out.u).reshape(*out.u.shape[:-2], -1) if self.batch is not None else out.u[0].reshape(-1))
+        if log:
+            ret += (sq(out.res_log[:, 0]),)
+        return ret
+
+    def solve_dp_ff(self, K=None, Quu=None, Qux=None, Quu_inv=None, Qr=None, Rr=None, ur=None, xr=None, x0=None):
+        """Feed-forward gains k of the LQT problem (isls/sls.py:168-202).  On the device the Riccati logs K, Quu, Qux,
+        Quu_inv of solve_dp live in the solver's workspace, so the arguments are accepted for signature compatibility
+        only; the regularised variant (Qr, Rr, xr, ur) is internal to ADMM_LQT_DP / ADMM_LQT_Batch."""
+        if Qr is not None or Rr is not None:
+            raise NotImplementedError("regularised solve_dp_ff is internal to ADMM_LQT_DP on the device path")
+        return self.solve_dp(x0=x0)[1]
 
     # ------------------------------------------------------------------ SLS (system level synthesis) path
     def _plan(self):

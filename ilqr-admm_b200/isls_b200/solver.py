@@ -233,8 +233,12 @@ class BatchSolver:
         _lib.check(rc, "isls_ilqr_solve_f64")
         return self.out
 
-    def lqt_admm_dp(self, tol=1e-3, relax=1.0, fixed_budget=False):
-        o = self._opts(tol, 0.0, relax, fixed_budget, True, max_outer=1)
+    def lqt_admm_dp(self, tol=1e-3, relax=1.0, fixed_budget=False, last_stage_dp=True, z_x_init=None, z_u_init=None):
+        """z_x_init [B,N,n] / z_u_init [B,N,m]: device tensors (ADMM warm start) or None."""
+        o = self._opts(tol, 0.0, relax, fixed_budget, last_stage_dp, max_outer=1)
+        self._zinit = (None if z_x_init is None else z_x_init.contiguous(),
+                       None if z_u_init is None else z_u_init.contiguous())       # keep alive until the launch
+        o.z_x_init_dev, o.z_u_init_dev = (None if t is None else t.data_ptr() for t in self._zinit)
         with torch.cuda.device(self.device):
             rc = _lib.lib().isls_lqt_admm_dp_f64(self.plan.handle, C.byref(o), self.B, _dptr(self.x0),
                                                  _dptr(self.zs), C.c_void_p(self._ws_ptr), self._ws_bytes,

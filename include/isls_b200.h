@@ -117,6 +117,9 @@ typedef struct isls_solve_opts {
                               1: DP form K[N-1]=k[N-1]=0 (isls/isls.py:245-246) */
   double stall_tol;        /* ADMM relative-change stop threshold; 0: = tol (admm.py:80); isls_admm: 1e-3 (isls.py:664) */
   double osc_tol;          /* oscillation test threshold; 0: = outer_tol; isls_admm: 1e-3 with outer_tol 1e-4 */
+  const double *z_x_init_dev; /* isls_lqt_admm_dp_f64 only: ADMM warm start z_x [B, N, n] / z_u [B, N, m] (DEVICE pointers, */
+  const double *z_u_init_dev; /* natural layout) or NULL = zeros.  ADMM_LQT_Batch starts from the unconstrained solution
+                                 (isls/sls.py:266-268) and uses last_stage_dp = 0. */
 } isls_solve_opts;
 
 /* Results, natural layouts, DEVICE pointers.  Optional outputs may be NULL. */

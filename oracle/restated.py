@@ -584,10 +584,14 @@ def ilqr_admm(p, fixed_budget=False, outer_tol=1e-3, keep_trace=False):
 
 
 # ------------------------------------------------------------------------------------- LQT-ADMM with Riccati
-def lqt_admm_dp(p, fixed_budget=False):
+def lqt_admm_dp(p, fixed_budget=False, batch_form=False):
     """SLS.ADMM_LQT_DP (sls.py:298-317): linear dynamics, one Riccati pass (sls.py:85-166), then per ADMM
     iteration the feed-forward recursion (sls.py:168-202) + closed-loop linear rollout
-    (sls_base.py:76-89) + projection / dual update (admm.py).  Budget p['I_a'] iterations, tolerance p['tol']."""
+    (sls_base.py:76-89) + projection / dual update (admm.py).  Budget p['I_a'] iterations, tolerance p['tol'].
+
+    batch_form=True restates SLS.ADMM_LQT_Batch (sls.py:250-294) in the same Riccati form: the dense least-squares
+    argmin is the same LQ minimiser except that its last control is solved for, u_{N-1} = (R + Rr)^-1 Rr reg_u, and
+    ADMM is warm-started at the unconstrained solution (z_x_init, z_u_init, sls.py:266-268)."""
     model = _model_of(p)
     N, n, m = p["N"], p["n"], p["m"]
     I_a, tol, relax = p["I_a"], p["tol"], p.get("alpha", 1.0)
@@ -614,6 +618,13 @@ def lqt_admm_dp(p, fixed_budget=False):
     Quub, Quuib, Quxb = (np.broadcast_to(a, (B,) + a.shape[1:]) for a in (Quu, Quu_inv, Qux))
     zs_i = zs[:, seq]
     zx, zu = np.zeros((B, N, n)), np.zeros((B, N, m))
+    if batch_form:                                                             # sls.py:266-268
+        K0, _, _, Quu0, Quui0, Qux0 = backward_pass(A, Bm, np.zeros((1, N, n)), np.zeros((1, N, m)),
+                                                    _diag_embed(2.0 * Qd)[None],
+                                                    _diag_embed(np.full((N, m), 2.0 * R))[None], logs=True)
+        bc = lambda a: np.broadcast_to(a, (B,) + a.shape[1:])
+        k0 = ff_pass(Ab, Bb, -2.0 * Qd * zs_i, np.zeros((B, N, m)), bc(K0), bc(Quu0), bc(Quui0), bc(Qux0))
+        zx, zu = linear_rollout(Ab, Bb, bc(K0), k0, dx0=x0)
     lx, lu = np.zeros((B, N, n)), np.zeros((B, N, m))
     x_last, u_last = np.zeros((B, N, n)), np.zeros((B, N, m))
     k_last = np.zeros((B, N, m))
@@ -632,6 +643,8 @@ def lqt_admm_dp(p, fixed_budget=False):
         cx = -2.0 * Qd * zs_i[ia] - 2.0 * rho_x * reg_x                        # sls.py:187-193
         cu = -2.0 * rho_u * reg_u
         k = ff_pass(Ab[ia], Bb[ia], cx, cu, Kb[ia], Quub[ia], Quuib[ia], Quxb[ia])
+        if batch_form:
+            k[:, -1] = -cu[:, -1] / (2.0 * (R + rho_u[-1]))
         xs, us = linear_rollout(Ab[ia], Bb[ia], Kb[ia], k, dx0=x0[ia])         # sls_base.py:76-89
         x_last[ia], u_last[ia], k_last[ia] = xs, us, k
         pprim, pdual = prim[ia].copy(), dual[ia].copy()

@@ -111,6 +111,27 @@ def golden_lqt_admm_dp(p, name):
                         K=np.stack(Ks), k=np.stack(ks), iters=np.array(its), last_res=np.stack(res))
 
 
+def golden_lqt_admm_batch(p, name):
+    """SLS.ADMM_LQT_Batch of the unmodified reference (isls/sls.py:250-294) on the C1 problems."""
+    pkg, _ = S.load()
+    N, n, m = p["N"], p["n"], p["m"]
+    model = M.make_model("double_integrator", nb_dim=m, dt=p["dt"])
+    xs, us, its, res = [], [], [], []
+    for b in range(p["x0"].shape[0]):
+        with S.quiet():
+            s = pkg.SLS(n, m, N)
+            s.AB = [model.A, model.B]
+            s.set_quadratic_cost(p["zs"], _Qs(p), p["seq"], p["u_std"])
+            x, u, logs = s.ADMM_LQT_Batch(p["x0"][b], project_x=_clip(p["lo_x"], p["hi_x"]),
+                                          project_u=_clip(p["lo_u"], p["hi_u"]), max_iter=p["I_a"],
+                                          rho_x=np.stack([np.diag(q) for q in p["rho_x"]]),
+                                          rho_u=float(p["rho_u"][0, 0]), tol=p["tol"], log=True)
+        xs.append(x.reshape(N, n)); us.append(u.reshape(N, m)); its.append(len(logs)); res.append(np.array(logs)[-1])
+        print(name, b, len(logs))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), x0=p["x0"], x=np.stack(xs), u=np.stack(us),
+                        iters=np.array(its), last_res=np.stack(res))
+
+
 def golden_notebook_pins():
     """Known answers printed in the reference's notebooks, re-derived here from HEAD."""
     pkg, _ = S.load()
@@ -332,3 +353,5 @@ if __name__ == "__main__":
         golden_parking()
     if want("isls_admm"):
         golden_isls_admm()
+    if want("lqt_batch"):
+        golden_lqt_admm_batch(P.di_batch(3), "di_lqt_admm_batch")

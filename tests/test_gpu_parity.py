@@ -412,3 +412,37 @@ def test_status_flags_nan_and_non_pd():
     p["u_std"] = -5.0
     o3 = g.run_ilqr_dp(p, 2, 10)
     assert np.all(o3["status"] & 16) and np.all(o3["status"] & 2) and np.all(o3["n_log"] == 1)
+
+
+def test_di_lqt_admm_batch_form_and_stage_api(golden):
+    """SLS.ADMM_LQT_Batch (sls.py:250-294), SLS.solve_dp_ff (sls.py:168-202) and iSLS.rollout_DP (isls.py:310-334)
+    of the reference's surface."""
+    import torch
+    from isls_b200 import Bound, SLS, get_double_integrator_AB
+    g = golden("di_lqt_admm_batch")
+    p = P.di_batch(3)
+    s = SLS(p["n"], p["m"], p["N"], batch=3)
+    s.AB = get_double_integrator_AB(p["m"], 2, p["dt"])
+    s.set_quadratic_cost(p["zs"], p["Qdiag"], p["seq"], p["u_std"])
+    x, u, log = s.ADMM_LQT_Batch(p["x0"], project_x=Bound(p["lo_x"], p["hi_x"]), project_u=Bound(p["lo_u"], p["hi_u"]),
+                                 rho_x=p["rho_x"], rho_u=p["rho_u"], max_iter=p["I_a"], tol=p["tol"], log=True)
+    its = s.last.admm_iters[:, 0].cpu().numpy()
+    assert np.array_equal(its, g["iters"]), "ADMM_LQT_Batch iteration counts differ from the reference"
+    assert np.abs(x.cpu().numpy().reshape(3, p["N"], -1) - g["x"]).max() < 1e-9
+    assert np.abs(u.cpu().numpy().reshape(3, p["N"], -1) - g["u"]).max() < 1e-9
+    o = R.lqt_admm_dp(p, batch_form=True)
+    assert np.abs(u.cpu().numpy().reshape(3, p["N"], -1) - o["u"]).max() < 1e-9
+    # solve_dp_ff returns the feed-forward gains of solve_dp
+    K, k = s.solve_dp()
+    assert torch.equal(s.solve_dp_ff(K=K), k)
+    # rollout_DP: closed-loop rollouts of the line-search candidates around the nominal trajectory
+    pc = P.car_batch(1)
+    c = _gpu().make_isls(dict(pc, x0=pc["x0"][:1]))
+    c.batch, c.nb = None, 1
+    c.solve("car", max_iter=3, max_line_search_iter=10, fixed_budget=True)
+    al = torch.as_tensor(c.alphas[:4], device=c.k.device)
+    xl, ul = c.rollout_DP(c.K, al[:, None, None] * c.k[None])
+    model = R._model_of(pc)
+    xs, us = R.rollout_closed(model, c.x_nom.cpu().numpy()[None], c.u_nom.cpu().numpy()[None],
+                              c.K.cpu().numpy()[None], (al[:, None, None] * c.k[None]).cpu().numpy()[None])
+    assert np.abs(xl.cpu().numpy() - xs[0]).max() < 1e-10 and np.abs(ul.cpu().numpy() - us[0]).max() < 1e-10

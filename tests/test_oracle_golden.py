@@ -247,3 +247,16 @@ def test_isls_admm_riccati_form_vs_reference_golden(golden):
     assert np.abs(o["d_u"].reshape(B, N * m) - g["du"]).max() < 1e-9
     assert np.abs(o["phi_u"].reshape(B, N * m, -1) - g["phi_u"]).max() < 1e-9 * max(1.0, np.abs(g["phi_u"]).max())
     assert np.abs(o["u"]).max() < 6.0                       # the nominal respects the (tightened) bound
+
+
+def test_lqt_admm_batch_form_vs_reference_golden(golden):
+    """SLS.ADMM_LQT_Batch (isls/sls.py:250-294; SURVEY 8d C1: "converged at iteration 580"): the Riccati-form
+    restatement with batch-form last control and the unconstrained warm start against the unmodified reference."""
+    g = golden("di_lqt_admm_batch")
+    p = P.di_batch(3)
+    o = R.lqt_admm_dp(p, batch_form=True)
+    assert np.array_equal(o["iters"], g["iters"])
+    assert R.lqt_admm_dp(P.di_batch(1), batch_form=True)["iters"][0] == 581     # HEAD: "converged at iteration 580"
+    assert np.abs(o["x"] - g["x"]).max() < 1e-9 and np.abs(o["u"] - g["u"]).max() < 1e-9
+    last = o["res_log"][np.arange(3), o["iters"] - 1]
+    assert np.abs(last - g["last_res"]).max() < 1e-9
