@@ -435,14 +435,16 @@ def test_di_lqt_admm_batch_form_and_stage_api(golden):
     # solve_dp_ff returns the feed-forward gains of solve_dp
     K, k = s.solve_dp()
     assert torch.equal(s.solve_dp_ff(K=K), k)
-    # rollout_DP: closed-loop rollouts of the line-search candidates around the nominal trajectory
-    pc = P.car_batch(1)
-    c = _gpu().make_isls(dict(pc, x0=pc["x0"][:1]))
+    # rollout_DP: closed-loop rollouts of the line-search candidates around the nominal trajectory (arm: no angle
+    # wrap, so the comparison is not at the mercy of a mod-2pi flip under feedback)
+    pc = P.arm_batch(1)
+    c = _gpu().make_isls(pc)
     c.batch, c.nb = None, 1
-    c.solve("car", max_iter=3, max_line_search_iter=10, fixed_budget=True)
+    c.solve("arm3", max_iter=3, max_line_search_iter=10, fixed_budget=True)
     al = torch.as_tensor(c.alphas[:4], device=c.k.device)
     xl, ul = c.rollout_DP(c.K, al[:, None, None] * c.k[None])
     model = R._model_of(pc)
     xs, us = R.rollout_closed(model, c.x_nom.cpu().numpy()[None], c.u_nom.cpu().numpy()[None],
                               c.K.cpu().numpy()[None], (al[:, None, None] * c.k[None]).cpu().numpy()[None])
-    assert np.abs(xl.cpu().numpy() - xs[0]).max() < 1e-10 and np.abs(ul.cpu().numpy() - us[0]).max() < 1e-10
+    scale = max(1.0, np.abs(us).max())
+    assert np.abs(xl.cpu().numpy() - xs[0]).max() < 1e-9 * scale and np.abs(ul.cpu().numpy() - us[0]).max() < 1e-9 * scale
