@@ -39,14 +39,21 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="problems per GPU")
     ap.add_argument("--early-exit", action="store_true", help="reference stop rules instead of the fixed budget")
+    ap.add_argument("--notebook-budget", action="store_true",
+                    help="I_o=30, I_a=5, L=50 (Car/Iterative LQR with control constraints.ipynb cell 20) instead of the "
+                         "reference defaults I_o=20, L=20 (secondary figure of SURVEY 8d; not the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work per reference step")
     return ap.parse_args()
 
 
-def workload(B):
+BUDGET = dict(I_o=20, I_a=5, L=20)
+
+
+def workload(B, seed=None):
     from isls_b200 import configs
-    return configs.car_batch(B, I_o=20, I_a=5, L=20, tol=1e-3)
+    kw = {} if seed is None else {"seed": seed}
+    return configs.car_batch(B, tol=1e-3, **BUDGET, **kw)
 
 
 def config_dict(p, B, n_gpus, fixed):
@@ -111,7 +118,7 @@ def run_reference(a):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(p, a.batch, a.gpus, fixed),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "single_core_solve_s": t1},
+                             "single_core_solve_s": t1, "riccati_pass_ms_one_core": round(cpu_riccati_pass_ms(), 3)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -183,7 +190,7 @@ def run_b200(a):
     # every rank solves its own B problems (weak scaling): different seeds per rank
     if world > 1:
         from isls_b200 import configs
-        p = configs.car_batch(B, seed=1234 + 2 + 1000 * rank, I_o=20, I_a=5, L=20, tol=1e-3)
+        p = workload(B, seed=1234 + 2 + 1000 * rank)
     plan = S.Plan("car", p["N"], 4, 2, p["dt"], p["Qdiag"], p["seq"], p["u_std"], p["L"], rho_u=p["rho_u"],
                   lo_u=p["lo_u"], hi_u=p["hi_u"])
     sv = S.BatchSolver(plan, B, dev, max_outer=p["I_o"], max_admm=p["I_a"], logs=False)
@@ -275,7 +282,8 @@ def run_b200(a):
         epi_bytes = float(B) * p["N"] * 2 * 5 * 8 if fused_update else 0.0
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         t_bound = flops / (fp64_peak * 1e12) + epi_bytes / (hbm_peak * 1e9)
-        roof = {"kernel": "k_linesearch<CarModel,5,4,3>" + (" + fused ADMM z/lambda epilogue" if fused_update else ""),
+        shape = "5,4,3" if p["L"] <= 20 else "5,10,1"            # csrc/isls_b200.cu: launch_linesearch
+        roof = {"kernel": "k_linesearch<CarModel,%s>" % shape + (" + fused ADMM z/lambda epilogue" if fused_update else ""),
                 "bound": "fp64", "achieved": round(ach, 3),
                 "peak": round(fp64_peak, 3), "unit": "TFLOP/s", "frac": round(ach / fp64_peak, 4),
                 "peak_source": "DFMA throughput measured live by isls_measure_fp64_tflops (MEASURED_PEAKS.json has "
@@ -323,7 +331,8 @@ def run_b200(a):
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
                                 "--warmup", "0", "--cpu-seconds", str(a.cpu_seconds)] +
-                               (["--early-exit"] if a.early_exit else []), capture_output=True, text=True,
+                               (["--early-exit"] if a.early_exit else []) +
+                               (["--notebook-budget"] if a.notebook_budget else []), capture_output=True, text=True,
                                timeout=600)
             cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
         except Exception as e:                                # the baseline is a report, never a blocker
@@ -343,8 +352,29 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+def cpu_riccati_pass_ms(reps=5):
+    """One backward_pass_DP of the reference's algorithm (isls.py:229-308; oracle port) on one car problem, ms."""
+    import numpy as np
+    from oracle import restated as R
+    p = workload(1)
+    model = R._model_of(p)
+    x, u = R.initial_rollout(p)
+    A, Bm = model.get_AB(x, u)
+    N, n, m = p["N"], p["n"], p["m"]
+    Cxx = R._diag_embed(2.0 * (p["Qdiag"][p["seq"]] + 1.0))[None]
+    Cuu = R._diag_embed(np.full((N, m), 2.0 * (p["u_std"] + 10.0)))[None]
+    z = np.zeros((1, N, n)), np.zeros((1, N, m))
+    R.backward_pass(A, Bm, z[0], z[1], Cxx, Cuu)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        R.backward_pass(A, Bm, z[0], z[1], Cxx, Cuu)
+    return (time.perf_counter() - t0) / reps * 1e3
+
+
 if __name__ == "__main__":
     args = parse()
+    if args.notebook_budget:
+        BUDGET.update(I_o=30, I_a=5, L=50)
     if args.impl == "reference":
         run_reference(args)
     else:

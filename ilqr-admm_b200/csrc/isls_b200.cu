@@ -2711,7 +2711,7 @@ static void launch_linesearch(const Dev &d, bool closed, cudaStream_t s, LsFuse 
       if (ov == 5) launch_ls_cfg<M, 5, 4, 2>(d, closed, s, f);
       else if (ov == 4) launch_ls_cfg<M, 4, 5, 3>(d, closed, s, f);
       else launch_ls_cfg<M, 5, 4, 3>(d, closed, s, f);      // 5 chains/thread, 4 warps, 3 CTAs/SM (168 regs)
-    } else launch_ls_cfg<M, 4, 13>(d, closed, s, f);
+    } else launch_ls_cfg<M, 5, 10>(d, closed, s, f);        // 21..50 candidates: 10 warps x 5 chains, one CTA per SM
   }
 }
 

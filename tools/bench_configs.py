@@ -105,6 +105,23 @@ if __name__ == "__main__":
     res["C4 SLS-ADMM DI B=1024"] = dict(plan_ms=round(t_plan, 1), admm_ms=round(ms_admm, 2), controller_ms=round(ms_ctl, 2),
                                         problems_per_s=round(Bn / (ms_admm + ms_ctl) * 1e3),
                                         mean_iters=float(s.last.iters.double().mean()))
+    # ---- stage-level generic-operator Riccati pass (isls_riccati_f64, SURVEY 8a a1 / 8d roofline (i)): dense A, B, c, C
+    # from HBM in the reference's natural layouts, 608 B per problem-step for the car shape
+    for (n_, m_, Bq) in ((4, 2, 65536), (9, 3, 16384)):
+        N_ = 100
+        g = torch.Generator(device="cuda").manual_seed(1)
+        A_ = torch.eye(n_, dtype=torch.float64, device="cuda").expand(Bq, N_, n_, n_).contiguous()
+        A_ += 0.05 * torch.randn(Bq, N_, n_, n_, dtype=torch.float64, device="cuda", generator=g)
+        B_ = 0.1 * torch.randn(Bq, N_, n_, m_, dtype=torch.float64, device="cuda", generator=g)
+        c_ = torch.randn(Bq, N_, n_ + m_, dtype=torch.float64, device="cuda", generator=g)
+        W_ = torch.randn(Bq, N_, n_ + m_, n_ + m_, dtype=torch.float64, device="cuda", generator=g)
+        C_ = W_ @ W_.transpose(-1, -2) + torch.eye(n_ + m_, dtype=torch.float64, device="cuda")
+        ms = timed(lambda: S.riccati(A_, B_, c_, C_))
+        byts = Bq * N_ * 8.0 * (n_ * n_ + n_ * m_ + (n_ + m_) + (n_ + m_) ** 2 + m_ * n_ + m_)
+        res["a1 generic-operator Riccati pass n=%d m=%d N=100 B=%d" % (n_, m_, Bq)] = dict(
+            ms=round(ms, 3), passes_per_s=round(Bq / ms * 1e3), algorithmic_GBps=round(byts / ms / 1e6, 1),
+            frac_of_hbm_peak=round(byts / ms / 1e6 / 6542.7, 3))
+        del A_, B_, c_, W_, C_
     # ---- widened rows: same measurement, reference stop rules
     import gpu_util
 
