@@ -2371,11 +2371,7 @@ __global__ void k_fp64_peak(double *out, int iters) {
 }
 
 // ----------------------------------------------------------------------------------------------------- host side
-#define MAX_CHUNKS 8
 struct isls_plan {
-  cudaStream_t aux[MAX_CHUNKS];      // auxiliary streams for chunked solves (created lazily)
-  cudaEvent_t ev_fork, ev_join[MAX_CHUNKS];
-  bool aux_ready;
   isls_problem_desc desc;   // pointers inside are NOT valid after create (copied to the device block)
   int n, m, N, n_via, L, NJA;
   bool proj_x, proj_u;
@@ -2450,7 +2446,6 @@ extern "C" int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan)
   for (int t = 0; t < N; t++)
     if (desc->seq[t] < 0 || desc->seq[t] >= desc->n_via) return fail(ISLS_E_INVALID, "seq entry out of range");
   isls_plan *p = new isls_plan();
-  p->aux_ready = false;
   p->desc = *desc;
   p->n = n; p->m = m; p->N = N; p->n_via = desc->n_via; p->L = desc->L; p->NJA = nja;
   p->proj_x = desc->rho_x != nullptr;
@@ -2527,10 +2522,6 @@ extern "C" int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan)
 
 extern "C" int isls_plan_destroy(isls_plan *plan) {
   if (!plan) return ISLS_OK;
-  if (plan->aux_ready) {
-    for (int i = 0; i < MAX_CHUNKS; i++) { cudaStreamDestroy(plan->aux[i]); cudaEventDestroy(plan->ev_join[i]); }
-    cudaEventDestroy(plan->ev_fork);
-  }
   cudaFree(plan->cblock);
   delete plan;
   return ISLS_OK;
@@ -2655,32 +2646,9 @@ struct LsFuse { int fuse, outer, inner; };
 template <class M, int CPT, int MAXW, int MINB = 1>
 static void launch_ls_cfg(const Dev &d, bool closed, cudaStream_t s, LsFuse f) {
   const int W = (d.L + CPT - 1) / CPT;
-  // optional dynamic shared-memory padding caps the CTAs per SM (experiments with concurrent HBM-bound kernels)
-  static int pad_kb = -1;
-  if (pad_kb < 0) { const char *e = getenv("ISLS_LS_PAD_KB"); pad_kb = e ? atoi(e) : 0; }
-  const size_t pad = (size_t)pad_kb * 1024;
   if (closed) k_linesearch_closed<M, CPT, MAXW, MINB><<<d.tile1 - d.tile0, dim3(TILE, W), 0, s>>>(d);
-  else {
-    if (pad) {
-      static bool set = false;
-      if (!set) {
-        cudaFuncSetAttribute(k_linesearch<M, CPT, MAXW, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
-        cudaFuncSetAttribute(k_linesearch<M, CPT, MAXW, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
-        set = true;
-      }
-    }
-    if (d.proj_x) k_linesearch<M, CPT, MAXW, MINB, true><<<d.tile1 - d.tile0, dim3(TILE, W), pad, s>>>(d, f.fuse, f.outer, f.inner);
-    else k_linesearch<M, CPT, MAXW, MINB, false><<<d.tile1 - d.tile0, dim3(TILE, W), pad, s>>>(d, f.fuse, f.outer, f.inner);
-  }
-}
-static int solve_chunks() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("ISLS_CHUNKS");      // number of concurrently running batch chunks (streams)
-    v = e ? atoi(e) : 1;
-    if (v < 1) v = 1;
-  }
-  return v;
+  else if (d.proj_x) k_linesearch<M, CPT, MAXW, MINB, true><<<d.tile1 - d.tile0, dim3(TILE, W), 0, s>>>(d, f.fuse, f.outer, f.inner);
+  else k_linesearch<M, CPT, MAXW, MINB, false><<<d.tile1 - d.tile0, dim3(TILE, W), 0, s>>>(d, f.fuse, f.outer, f.inner);
 }
 static int solve_compact() {
   static int v = -1;
@@ -2727,34 +2695,16 @@ extern "C" int isls_ilqr_admm_solve_f64(const isls_plan *plan, const isls_solve_
   cudaStream_t s = (cudaStream_t)stream;
   return dispatch_model(plan, [&](auto model) -> int {
     using M = decltype(model);
-    // Problems are independent, so the batch is cut into `chunks` disjoint tile ranges that run the same kernel
-    // sequence on separate streams (forked from / joined to the caller's stream): the HBM-bound recursions of one
-    // chunk overlap the FP64-bound line search of another.
-    int chunks = solve_chunks();
-    if (g_prof_on) chunks = 1;                       // per-kernel event timing wants serialised launches
-    chunks = std::max(1, std::min(std::min(chunks, MAX_CHUNKS), d.T));
-    isls_plan *pl = const_cast<isls_plan *>(plan);
-    if (chunks > 1 && !pl->aux_ready) {
-      for (int i = 0; i < MAX_CHUNKS; i++) {
-        CK(cudaStreamCreateWithFlags(&pl->aux[i], cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&pl->ev_join[i], cudaEventDisableTiming));
-      }
-      CK(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
-      pl->aux_ready = true;
-    }
-    if (chunks > 1) CK(cudaEventRecord(pl->ev_fork, s));
     // Reference stop rules: finished problems are retired and the active ones re-packed into dense tiles after
-    // every outer iteration (k_compact_*), so a tile never carries idle lanes for long.
-    const bool compact = !d.fixed_budget && d.max_outer > 1 && solve_compact() && chunks == 1;
+    // every outer iteration (k_compact_*), so a tile never carries idle lanes for long.  (Cutting the batch into
+    // chunks on separate streams was measured and dropped: every kernel fills the GPU, profiles/r1_tuning_log.md.)
+    const bool compact = !d.fixed_budget && d.max_outer > 1 && solve_compact();
     Dev dalt = d;
     if (compact) carve(plan, B, (char *)ws, &d, &dalt);
     else d.orig = nullptr;
-    for (int ch = 0; ch < chunks; ch++) {
+    {
       Dev dc = d;
-      dc.tile0 = (int)((long long)d.T * ch / chunks);
-      dc.tile1 = (int)((long long)d.T * (ch + 1) / chunks);
-      cudaStream_t cs = ch == 0 ? s : pl->aux[ch];
-      if (ch > 0) CK(cudaStreamWaitEvent(cs, pl->ev_fork, 0));
+      cudaStream_t cs = s;
       LAUNCH(ISLS_KC_INIT, cs, (k_init<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, x0, u_init, zs)));
       for (int j = 0; j < d.max_outer; j++) {
         LAUNCH(ISLS_KC_KPASS, cs, (k_kpass<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc)));
@@ -2785,10 +2735,6 @@ extern "C" int isls_ilqr_admm_solve_f64(const isls_plan *plan, const isls_solve_
         }
       }
       LAUNCH(ISLS_KC_FINALIZE, cs, (k_finalize<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc)));
-      if (ch > 0) {
-        CK(cudaEventRecord(pl->ev_join[ch], cs));
-        CK(cudaStreamWaitEvent(s, pl->ev_join[ch], 0));
-      }
     }
     CK(cudaGetLastError());
     return ISLS_OK;
