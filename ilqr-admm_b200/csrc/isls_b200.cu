@@ -2622,7 +2622,9 @@ static int launch_ff(const Dev &d, cudaStream_t s) {
   constexpr int SB = n + m + m * n + 2 * nt + m + n, SF = m * n + 3 * m + n, SL = SB > SF ? SB : SF;
   const int tiles = d.tile1 - d.tile0;
   int stages = mode;
-  if (stages < 0) stages = (tiles < 1536 && (size_t)4 * SL * TILE * sizeof(double) <= 32 * 1024) ? 4 : 0;
+  // small batches are latency-bound: stage 4 steps ahead when 3-4 single-warp CTAs with that stage fit an SM
+  // (car 17 KB, arm 64.5 KB per CTA; C3 arm B=16,384: ff 80 -> 66 ms per solve)
+  if (stages < 0) stages = (tiles < 1536 && (size_t)4 * SL * TILE * sizeof(double) <= 66 * 1024) ? 4 : 0;
   if (stages == 4) {
     const size_t smem = (size_t)4 * SL * TILE * sizeof(double);
     static bool set4 = false;
