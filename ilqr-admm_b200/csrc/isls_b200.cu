@@ -2118,6 +2118,58 @@ __global__ void k_admm_flat(long long len, double relax, const double *x, double
 // ----------------------------------------------------------------------------- generic-operator Riccati (stage a1)
 // iSLS.backward_pass_DP(Cts, cts) with dense operators read from HBM (isls/isls.py:229-308, general branch
 // including Cux).  One problem per thread, natural layouts.
+// One step of iSLS.backward_pass_DP with dense operators (isls/isls.py:285-302, general branch including Cux).
+// ST = element stride of the operand arrays: 1 for the natural global layout, RIC_LD for the staged shared-memory tile.
+template <int n, int m, int ST>
+__device__ __forceinline__ bool riccati_generic_step(const double *A, const double *Bm, const double *cc, const double *C,
+                                                     double (&V)[n][n], double (&v)[n], double (&K)[m][n],
+                                                     double (&kt)[m]) {
+  constexpr int nm = n + m;
+  double VA[n][n], VB[n][m], Qxx[n][n], Qux[m][n], Quu[m][m], Qui[m][m], qx[n], qu[m];
+  for (int i = 0; i < n; i++) {
+    for (int j = 0; j < n; j++) { double a = 0.0; for (int k = 0; k < n; k++) a = fma(V[i][k], A[(k * n + j) * ST], a); VA[i][j] = a; }
+    for (int j = 0; j < m; j++) { double a = 0.0; for (int k = 0; k < n; k++) a = fma(V[i][k], Bm[(k * m + j) * ST], a); VB[i][j] = a; }
+  }
+  for (int i = 0; i < n; i++) {
+    double a = cc[(i) * ST];
+    for (int k = 0; k < n; k++) a = fma(A[(k * n + i) * ST], v[k], a);
+    qx[i] = a;
+    for (int j = 0; j < n; j++) { double s = C[(i * nm + j) * ST]; for (int k = 0; k < n; k++) s = fma(A[(k * n + i) * ST], VA[k][j], s); Qxx[i][j] = s; }
+  }
+  for (int i = 0; i < m; i++) {
+    double a = cc[(n + i) * ST];
+    for (int k = 0; k < n; k++) a = fma(Bm[(k * m + i) * ST], v[k], a);
+    qu[i] = a;
+    for (int j = 0; j < n; j++) { double s = C[((n + i) * nm + j) * ST]; for (int k = 0; k < n; k++) s = fma(Bm[(k * m + i) * ST], VA[k][j], s); Qux[i][j] = s; }
+    for (int j = 0; j < m; j++) { double s = C[((n + i) * nm + n + j) * ST]; for (int k = 0; k < n; k++) s = fma(Bm[(k * m + i) * ST], VB[k][j], s); Quu[i][j] = s; }
+  }
+  const bool ok = spd_inverse<m>(Quu, Qui);
+  for (int a = 0; a < m; a++) {
+    for (int j = 0; j < n; j++) { double s = 0.0; for (int b2 = 0; b2 < m; b2++) s = fma(Qui[a][b2], Qux[b2][j], s); K[a][j] = -s; }
+    double s = 0.0;
+    for (int b2 = 0; b2 < m; b2++) s = fma(Qui[a][b2], qu[b2], s);
+    kt[a] = -s;
+  }
+  double QK[m][n], Qk[m];
+  for (int a = 0; a < m; a++) {
+    for (int j = 0; j < n; j++) { double s = 0.0; for (int b2 = 0; b2 < m; b2++) s = fma(Quu[a][b2], K[b2][j], s); QK[a][j] = s; }
+    double s = 0.0;
+    for (int b2 = 0; b2 < m; b2++) s = fma(Quu[a][b2], kt[b2], s);
+    Qk[a] = s;
+  }
+  for (int i = 0; i < n; i++) {
+    for (int j = 0; j < n; j++) {
+      double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+      for (int a = 0; a < m; a++) { t1 = fma(K[a][i], QK[a][j], t1); t2 = fma(Qux[a][i], K[a][j], t2); t3 = fma(K[a][i], Qux[a][j], t3); }
+      V[i][j] = ((Qxx[i][j] + t1) + t2) + t3;                                       // isls.py:300
+    }
+    double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    for (int a = 0; a < m; a++) { t1 = fma(K[a][i], qu[a], t1); t2 = fma(K[a][i], Qk[a], t2); t3 = fma(Qux[a][i], kt[a], t3); }
+    v[i] = ((qx[i] + t1) + t2) + t3;                                                // isls.py:302
+  }
+  return ok;
+}
+
 template <int n, int m>
 __global__ void k_riccati_generic(int N, long long B, const double *Ag, const double *Bg, const double *cg,
                                   const double *Cg, double *Kg, double *kg, int *non_pd) {
@@ -2141,54 +2193,83 @@ __global__ void k_riccati_generic(int N, long long B, const double *Ag, const do
   for (int t = N - 2; t >= 0; t--) {
     const double *A = Ab + (size_t)t * n * n, *Bm = Bb + (size_t)t * n * m;
     const double *C = Cb + (size_t)t * nm * nm, *cc = cb + (size_t)t * nm;
-    double VA[n][n], VB[n][m], Qxx[n][n], Qux[m][n], Quu[m][m], Qui[m][m], qx[n], qu[m], K[m][n], kt[m];
-    for (int i = 0; i < n; i++) {
-      for (int j = 0; j < n; j++) { double a = 0.0; for (int k = 0; k < n; k++) a = fma(V[i][k], A[k * n + j], a); VA[i][j] = a; }
-      for (int j = 0; j < m; j++) { double a = 0.0; for (int k = 0; k < n; k++) a = fma(V[i][k], Bm[k * m + j], a); VB[i][j] = a; }
-    }
-    for (int i = 0; i < n; i++) {
-      double a = cc[i];
-      for (int k = 0; k < n; k++) a = fma(A[k * n + i], v[k], a);
-      qx[i] = a;
-      for (int j = 0; j < n; j++) { double s = C[i * nm + j]; for (int k = 0; k < n; k++) s = fma(A[k * n + i], VA[k][j], s); Qxx[i][j] = s; }
-    }
-    for (int i = 0; i < m; i++) {
-      double a = cc[n + i];
-      for (int k = 0; k < n; k++) a = fma(Bm[k * m + i], v[k], a);
-      qu[i] = a;
-      for (int j = 0; j < n; j++) { double s = C[(n + i) * nm + j]; for (int k = 0; k < n; k++) s = fma(Bm[k * m + i], VA[k][j], s); Qux[i][j] = s; }
-      for (int j = 0; j < m; j++) { double s = C[(n + i) * nm + n + j]; for (int k = 0; k < n; k++) s = fma(Bm[k * m + i], VB[k][j], s); Quu[i][j] = s; }
-    }
-    ok &= spd_inverse<m>(Quu, Qui);
-    for (int a = 0; a < m; a++) {
-      for (int j = 0; j < n; j++) { double s = 0.0; for (int b2 = 0; b2 < m; b2++) s = fma(Qui[a][b2], Qux[b2][j], s); K[a][j] = -s; }
-      double s = 0.0;
-      for (int b2 = 0; b2 < m; b2++) s = fma(Qui[a][b2], qu[b2], s);
-      kt[a] = -s;
-    }
-    double QK[m][n], Qk[m];
-    for (int a = 0; a < m; a++) {
-      for (int j = 0; j < n; j++) { double s = 0.0; for (int b2 = 0; b2 < m; b2++) s = fma(Quu[a][b2], K[b2][j], s); QK[a][j] = s; }
-      double s = 0.0;
-      for (int b2 = 0; b2 < m; b2++) s = fma(Quu[a][b2], kt[b2], s);
-      Qk[a] = s;
-    }
-    for (int i = 0; i < n; i++) {
-      for (int j = 0; j < n; j++) {
-        double t1 = 0.0, t2 = 0.0, t3 = 0.0;
-        for (int a = 0; a < m; a++) { t1 = fma(K[a][i], QK[a][j], t1); t2 = fma(Qux[a][i], K[a][j], t2); t3 = fma(K[a][i], Qux[a][j], t3); }
-        V[i][j] = ((Qxx[i][j] + t1) + t2) + t3;                                       // isls.py:300
-      }
-      double t1 = 0.0, t2 = 0.0, t3 = 0.0;
-      for (int a = 0; a < m; a++) { t1 = fma(K[a][i], qu[a], t1); t2 = fma(K[a][i], Qk[a], t2); t3 = fma(Qux[a][i], kt[a], t3); }
-      v[i] = ((qx[i] + t1) + t2) + t3;                                                // isls.py:302
-    }
+    double K[m][n], kt[m];
+    ok &= riccati_generic_step<n, m, 1>(A, Bm, cc, C, V, v, K, kt);
     for (int a = 0; a < m; a++) {
       for (int j = 0; j < n; j++) Kb[(size_t)t * m * n + a * n + j] = K[a][j];
       kb[(size_t)t * m + a] = kt[a];
     }
   }
   if (non_pd) non_pd[b] = ok ? 0 : 1;
+}
+
+// Staged variant for the small shapes: a warp owns 32 problems; per time step its lanes copy the 32 problems' operand
+// blocks (each contiguous in the natural layout) into a shared-memory tile [element][problem] with cp.async, two steps
+// ahead, so every global access is a run of full lines instead of 32 scattered ones and the recursion reads its
+// operands conflict-free (row pitch RIC_LD = 33).
+#define RIC_LD 33
+template <int n, int m, int STAGES>
+__global__ void __launch_bounds__(TILE) k_riccati_generic_staged(int N, long long B, const double *Ag, const double *Bg,
+                                                                 const double *cg, const double *Cg, double *Kg,
+                                                                 double *kg, int *non_pd) {
+  constexpr int nm = n + m, EA = n * n, EB = n * m, Ec = nm, EC = nm * nm, ET = EA + EB + Ec + EC;
+  extern __shared__ double ric_sm[];
+  const int lane = threadIdx.x;
+  const long long b0 = (long long)blockIdx.x * TILE, b = b0 + lane;
+  const bool valid = b < B;
+  const int np = (int)min((long long)TILE, B - b0);                 // problems of this tile
+  auto issue = [&](int t, int stage) {
+    double *dst = ric_sm + (size_t)stage * ET * RIC_LD;
+    auto copy = [&](const double *src, int E, int off) {
+      for (int idx = lane; idx < np * E; idx += TILE) {
+        const int p = idx / E, e = idx - p * E;
+        cp_async8(dst + (size_t)(off + e) * RIC_LD + p, src + ((size_t)(b0 + p) * N + t) * E + e);
+      }
+    };
+    copy(Ag, EA, 0); copy(Bg, EB, EA); copy(cg, Ec, EA + EB); copy(Cg, EC, EA + EB + Ec);
+  };
+  double *Kb = Kg + (size_t)(valid ? b : 0) * N * m * n, *kb = kg + (size_t)(valid ? b : 0) * N * m;
+  double V[n][n], v[n];
+  int t_issue = N - 1;
+#pragma unroll
+  for (int s = 0; s < STAGES; s++) {
+    if (t_issue >= 0) issue(t_issue, (N - 1 - t_issue) % STAGES);
+    cp_async_commit();
+    t_issue--;
+  }
+  bool ok = true;
+  for (int t = N - 1; t >= 0; t--) {
+    cp_async_wait<STAGES - 1>();
+    __syncwarp();
+    const double *st = ric_sm + (size_t)((N - 1 - t) % STAGES) * ET * RIC_LD + lane;
+    const double *A = st, *Bm = st + (size_t)EA * RIC_LD, *cc = st + (size_t)(EA + EB) * RIC_LD;
+    const double *C = st + (size_t)(EA + EB + Ec) * RIC_LD;
+    if (t == N - 1) {
+      for (int i = 0; i < n; i++) {
+        for (int j = 0; j < n; j++) V[i][j] = C[(i * nm + j) * RIC_LD];
+        v[i] = cc[i * RIC_LD];
+      }
+      if (valid) {
+        for (int q = 0; q < m * n; q++) Kb[(size_t)t * m * n + q] = 0.0;
+        for (int j = 0; j < m; j++) kb[(size_t)t * m + j] = 0.0;
+      }
+    } else {
+      double K[m][n], kt[m];
+      ok &= riccati_generic_step<n, m, RIC_LD>(A, Bm, cc, C, V, v, K, kt);
+      if (valid) {
+        for (int a = 0; a < m; a++) {
+          for (int j = 0; j < n; j++) Kb[(size_t)t * m * n + a * n + j] = K[a][j];
+          kb[(size_t)t * m + a] = kt[a];
+        }
+      }
+    }
+    __syncwarp();                                                   // every lane has read the stage
+    if (t_issue >= 0) issue(t_issue, (N - 1 - t_issue) % STAGES);
+    cp_async_commit();
+    t_issue--;
+  }
+  cp_async_wait<0>();
+  if (non_pd && valid) non_pd[b] = ok ? 0 : 1;
 }
 
 // ------------------------------------------------------------------------------------------- LQT-ADMM (DP) kernel
@@ -2895,9 +2976,15 @@ extern "C" int isls_riccati_f64(int32_t n, int32_t m, int32_t N, int64_t B, cons
   if (!A || !Bm || !c || !C || !K || !k || N < 2 || B <= 0) return fail(ISLS_E_INVALID, "NULL argument or bad size");
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned grid = (unsigned)((B + 63) / 64);
-  if (n == 2 && m == 1) k_riccati_generic<2, 1><<<grid, 64, 0, s>>>(N, B, A, Bm, c, C, K, k, non_pd);
-  else if (n == 4 && m == 2) k_riccati_generic<4, 2><<<grid, 64, 0, s>>>(N, B, A, Bm, c, C, K, k, non_pd);
-  else if (n == 6 && m == 3) k_riccati_generic<6, 3><<<grid, 64, 0, s>>>(N, B, A, Bm, c, C, K, k, non_pd);
+  auto staged = [&](auto kern, int ET) -> int {
+    const size_t smem = (size_t)2 * ET * RIC_LD * sizeof(double);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)((B + TILE - 1) / TILE), TILE, smem, s>>>(N, B, A, Bm, c, C, K, k, non_pd);
+    return 0;
+  };
+  if (n == 2 && m == 1) { if (staged(k_riccati_generic_staged<2, 1, 2>, 4 + 2 + 3 + 9)) return 1; }
+  else if (n == 4 && m == 2) { if (staged(k_riccati_generic_staged<4, 2, 2>, 16 + 8 + 6 + 36)) return 1; }
+  else if (n == 6 && m == 3) { if (staged(k_riccati_generic_staged<6, 3, 2>, 36 + 18 + 9 + 81)) return 1; }
   else if (n == 9 && m == 3) k_riccati_generic<9, 3><<<grid, 64, 0, s>>>(N, B, A, Bm, c, C, K, k, non_pd);
   else return fail(ISLS_E_UNSUPPORTED, "unsupported (n, m) for isls_riccati_f64");
   CK(cudaGetLastError());
