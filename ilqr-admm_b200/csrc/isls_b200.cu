@@ -79,8 +79,8 @@ struct Dev {
   const double *rho_u, *lo_u, *hi_u;   // [N][m]
   const double *alphas;  // [L]
   // obstacle sets of the state projection (n_obst = 0: box): centres [K][2], W / W^-1 [K][4], lower [K]
-  int n_obst, obst_max_iter;
-  double obst_upper, obst_rho, obst_threshold;
+  int n_obst, obst_max_iter, obst_kind, obst_dyk_max_iter;
+  double obst_upper, obst_rho, obst_threshold, obst_dyk_tol;
   const double *ob_c, *ob_W, *ob_Wi, *ob_lo;
   double *obw;           // workspace [2][T][N][n][32]: winner x, pre-projection point
   // robust iSLS-ADMM: C = dim + 1 columns [d_u | Phi_u(:, :dim)]; Zm, Lm (ADMM z, lambda, delta coordinates) and Xu
@@ -1200,6 +1200,17 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
 // registers, block reductions for the stop rule) projects and finishes the ADMM update.
 __device__ __forceinline__ void obst_project_one(const Dev &d, int k, double (&y)[2]) {
   const double c0 = d.ob_c[2 * k], c1 = d.ob_c[2 * k + 1];
+  if (d.obst_kind == 1) {        // project_quadratic_batch(p - c, lower, upper) + c   (projections.py:91-105)
+    const double z0 = y[0] - c0, z1 = y[1] - c1;
+    const double ss = z0 * z0 + z1 * z1, val = 0.5 * ss;
+    double s2 = 0.0;                                                     // x * sqrt(2 l) / ||x||, left to right
+    if (val > d.obst_upper) s2 = sqrt(2.0 * d.obst_upper);
+    if (d.ob_lo[k] > val) s2 = sqrt(2.0 * d.ob_lo[k]);                   // later mask wins, like the numpy code
+    const double nr = sqrt(ss);
+    y[0] = (s2 == 0.0 ? z0 : (z0 * s2) / nr) + c0;
+    y[1] = (s2 == 0.0 ? z1 : (z1 * s2) / nr) + c1;
+    return;
+  }
   const double *W = d.ob_W + 4 * k, *Wi = d.ob_Wi + 4 * k;
   const double z0 = y[0] - c0, z1 = y[1] - c1;
   double w0 = z0 * W[0] + z1 * W[1], w1 = z0 * W[2] + z1 * W[3];          // z @ W.T
@@ -2272,6 +2283,96 @@ __global__ void __launch_bounds__(TILE) k_riccati_generic_staged(int N, long lon
   if (non_pd && valid) non_pd[b] = ok ? 0 : 1;
 }
 
+// State projection of the spherical-obstacle notebook on the LQT path (one problem per thread, rows swept sequentially;
+// Double integrator/LQR and SLS with spherical obstacle avoidance.ipynb cell 12): positions through project_set_convex
+// (As = I_2, bs = 0; projections.py:289-374), then project_set_convex_dykstra (projections.py:465-505); the other state
+// components pass through.  obw arrays [T][N][n][32]: 0 pre-projection point (in), 1 result (out), 2.. scratch
+// (z_k, lambda_k of the consensus ADMM in components 0-1 / 2-3 of array 2 + k; Dykstra increments in array 2 + K + k).
+template <class M>
+__device__ __forceinline__ void lqt_obst_project(const Dev &d, const TileCtx<M> &c, int *its1, int *its2) {
+  constexpr int n = M::n;
+  const int K = d.n_obst, N = d.N;
+  const size_t arr = (size_t)d.T * N * n * TILE;
+  const double *pre = c.at(d.obw, d, n);
+  double *res = c.at(d.obw + arr, d, n);
+  const double rho = d.obst_rho, inv = 1.0 / (1.0 + rho * K);
+  double prim_ = 1e5, dual_ = 1e5;
+  int it = 0;
+  for (int j = 0; j < d.obst_max_iter; j++) {
+    it = j + 1;
+    double pmax = 0.0, dmax = 0.0;
+    for (int t = 0; t < N; t++) {
+      double x0[2], x[2], zk[ISLS_MAX_OBST][2], lk[ISLS_MAX_OBST][2];
+      x0[0] = EL(pre, n, t, 0); x0[1] = EL(pre, n, t, 1);
+      for (int k = 0; k < K; k++) {
+        const double *sk = c.at(d.obw + (2 + k) * arr, d, n);
+        for (int i = 0; i < 2; i++) { zk[k][i] = j == 0 ? x0[i] : EL(sk, n, t, i); lk[k][i] = j == 0 ? 0.0 : EL(sk, n, t, 2 + i); }
+      }
+      for (int i = 0; i < 2; i++) {
+        double r = 0.0;
+        for (int k = 0; k < K; k++) r = r + (zk[k][i] - lk[k][i]);
+        x[i] = inv * (x0[i] + rho * r);
+        EL(res, n, t, i) = x[i];
+      }
+      for (int k = 0; k < K; k++) {
+        double *sk = c.at(d.obw + (2 + k) * arr, d, n);
+        double y[2] = {x[0] + lk[k][0], x[1] + lk[k][1]};
+        obst_project_one(d, k, y);
+        double ps = 0.0, ds = 0.0;
+        for (int i = 0; i < 2; i++) {
+          const double pr = x[i] - y[i], du_ = rho * (y[i] - zk[k][i]);
+          ps += pr * pr;
+          ds += du_ * du_;
+          EL(sk, n, t, i) = y[i];
+          EL(sk, n, t, 2 + i) = lk[k][i] + pr;
+        }
+        pmax = fmax(pmax, sqrt(ps));
+        dmax = fmax(dmax, sqrt(ds));
+      }
+    }
+    const double pprim = prim_, pdual = dual_;
+    prim_ = pmax;
+    dual_ = dmax;
+    if (prim_ < d.obst_threshold && dual_ < d.obst_threshold) break;
+    if (j < d.obst_max_iter - 1) {
+      const double pc = fabs(pprim - prim_) / (pprim + 1e-30), dc = fabs(pdual - dual_) / (pdual + 1e-30);
+      if (pc < 1e-5 && dc < 1e-5) break;
+    }
+  }
+  *its1 = it;
+  // ---- Dykstra: u = x; z_i = 0; sweep the sets while any row's summed squared increment change is >= tol
+  int kd = 0;
+  if (d.obst_dyk_max_iter > 0) {
+    bool any = true;
+    while (kd <= d.obst_dyk_max_iter && any) {
+      any = false;
+      for (int t = 0; t < N; t++) {
+        double u[2] = {EL(res, n, t, 0), EL(res, n, t, 1)};
+        double cI = 0.0;
+        for (int k = 0; k < K; k++) {
+          double *zd = c.at(d.obw + (2 + K + k) * arr, d, n);
+          const double pz0 = kd == 0 ? 0.0 : EL(zd, n, t, 0), pz1 = kd == 0 ? 0.0 : EL(zd, n, t, 1);
+          const double pu0 = u[0], pu1 = u[1];
+          double y[2] = {pu0 - pz0, pu1 - pz1};
+          obst_project_one(d, k, y);
+          u[0] = y[0]; u[1] = y[1];
+          const double nz0 = u[0] - (pu0 - pz0), nz1 = u[1] - (pu1 - pz1);
+          EL(zd, n, t, 0) = nz0; EL(zd, n, t, 1) = nz1;
+          const double e0 = pz0 - nz0, e1 = pz1 - nz1, nr = sqrt(e0 * e0 + e1 * e1);
+          cI += nr * nr;                                        // np.linalg.norm(.)**2
+        }
+        EL(res, n, t, 0) = u[0]; EL(res, n, t, 1) = u[1];
+        any |= cI >= d.obst_dyk_tol;
+      }
+      kd++;
+    }
+  }
+  *its2 = kd;
+  for (int t = 0; t < N; t++)
+#pragma unroll
+    for (int i = 2; i < n; i++) EL(res, n, t, i) = EL(pre, n, t, i);
+}
+
 // ------------------------------------------------------------------------------------------- LQT-ADMM (DP) kernel
 // SLS.ADMM_LQT_DP (isls/sls.py:298-317): the gains K, Quu, Quu^-1, Qux depend only on (A, B, Q, rho), so one
 // thread block computes them once (k_kpass on a single tile with a zero nominal works for linear models because
@@ -2365,6 +2466,12 @@ __global__ void k_lqt_admm(Dev d, const double *x0_in) {
 #pragma unroll
         for (int i = 0; i < n; i++) { zxv[i] = EL(zx, n, t, i); lxv[i] = EL(lx, n, t, i); }
       }
+      if (d.n_obst > 0) {          // park the pre-projection point; the rows are projected together after the rollout
+        double *pre = c.at(d.obw, d, n);
+#pragma unroll
+        for (int i = 0; i < n; i++)
+          EL(pre, n, t, i) = __dadd_rn(__dadd_rn(__dmul_rn(d.relax, x[i]), __dmul_rn(__dsub_rn(1.0, d.relax), zxv[i])), lxv[i]);
+      }
 #pragma unroll
       for (int j = 0; j < m; j++) {
         double acc = 0.0;
@@ -2384,7 +2491,7 @@ __global__ void k_lqt_admm(Dev d, const double *x0_in) {
 #pragma unroll
       for (int i = 0; i < n; i++) {
         EL(xa, n, t, i) = x[i];
-        if (d.proj_x) {
+        if (d.proj_x && d.n_obst == 0) {
           int mk;
           admm_elem(x[i], d.relax, d.lo_x[t * n + i], d.hi_x[t * n + i], zxv[i], lxv[i], prx, drx, mk);
           EL(zx, n, t, i) = zxv[i];
@@ -2398,6 +2505,26 @@ __global__ void k_lqt_admm(Dev d, const double *x0_in) {
       for (int i = 0; i < n; i++) x[i] = xn[i];
     }
     cost = cs + d.u_std * cc;
+    if (d.n_obst > 0) {
+      int i1, i2;
+      lqt_obst_project<M>(d, c, &i1, &i2);
+      if (c.valid && d.out.inner_iters) {
+        d.out.inner_iters[((size_t)c.b * d.max_admm + it)] = i1 * 1000 + i2;      // set-convex iterations, Dykstra sweeps
+      }
+      const size_t arr = (size_t)d.T * d.N * n * TILE;
+      const double *zn_a = c.at(d.obw + arr, d, n);
+      for (int t = 0; t < d.N; t++) {
+#pragma unroll
+        for (int i = 0; i < n; i++) {                      // admm.py:49-59 with z = project_x(.)
+          const double xv = EL(xa, n, t, i), zn = EL(zn_a, n, t, i), zo = EL(zx, n, t, i);
+          const double r = __dsub_rn(xv, zn), dz = __dsub_rn(zn, zo);
+          EL(lx, n, t, i) = __dadd_rn(EL(lx, n, t, i), r);
+          EL(zx, n, t, i) = zn;
+          prx = fma(r, r, prx);
+          drx = fma(dz, dz, drx);
+        }
+      }
+    }
     const double pprim = prim, pdual = dual;
     prim = sqrt(prx) + sqrt(pru);
     dual = sqrt(drx) + sqrt(dru);
@@ -2518,7 +2645,8 @@ extern "C" int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan)
     return fail(ISLS_E_UNSUPPORTED, "isls_dim must be in 0..3 and <= x_dim");
   if (desc->isls_dim > 0 && (!desc->rho_u || (long long)desc->N * desc->m > 1024))
     return fail(ISLS_E_UNSUPPORTED, "isls_admm needs rho_u and N * u_dim <= 1024");
-  if (desc->n_obst > 0 && (!desc->rho_x || !desc->obst_centers || !desc->obst_W || !desc->obst_W_inv || !desc->obst_lower ||
+  if (desc->obst_kind < 0 || desc->obst_kind > 1) return fail(ISLS_E_UNSUPPORTED, "unknown obst_kind");
+  if (desc->n_obst > 0 && (!desc->rho_x || !desc->obst_centers || (desc->obst_kind == 0 && (!desc->obst_W || !desc->obst_W_inv)) || !desc->obst_lower ||
                            desc->obst_max_iter < 1 || desc->n < 2 || desc->N > 1024))
     return fail(ISLS_E_INVALID, "obstacle sets need rho_x, centres, W, W_inv, lower, obst_max_iter >= 1 and N <= 1024");
   if (desc->rho_x && !desc->n_obst && (!desc->lo_x || !desc->hi_x)) return fail(ISLS_E_INVALID, "rho_x without lo_x/hi_x");
@@ -2564,8 +2692,8 @@ extern "C" int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan)
          o_hu = push(desc->hi_u, (size_t)N * m, inf), o_al = push(desc->alphas, desc->L, 0.0);
   size_t o_oc = 0, o_ow = 0, o_oi = 0, o_ol = 0;
   if (desc->n_obst > 0) {
-    o_oc = push(desc->obst_centers, 2 * (size_t)desc->n_obst, 0.0); o_ow = push(desc->obst_W, 4 * (size_t)desc->n_obst, 0.0);
-    o_oi = push(desc->obst_W_inv, 4 * (size_t)desc->n_obst, 0.0); o_ol = push(desc->obst_lower, (size_t)desc->n_obst, 0.0);
+    o_oc = push(desc->obst_centers, 2 * (size_t)desc->n_obst, 0.0); o_ow = push(desc->obst_W, 4 * (size_t)desc->n_obst, 1.0);
+    o_oi = push(desc->obst_W_inv, 4 * (size_t)desc->n_obst, 1.0); o_ol = push(desc->obst_lower, (size_t)desc->n_obst, 0.0);
   }
   size_t o_hp = 0, o_q2 = 0, o_h2 = 0;
   if (huber) { o_hp = push(hp.data(), (size_t)N * n, 1.0); o_q2 = push(qd2.data(), (size_t)N * n, 0.0); o_h2 = push(hp2.data(), (size_t)N * n, 1.0); }
@@ -2593,6 +2721,7 @@ extern "C" int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan)
   if (huber) { d.hp = cb + o_hp; d.qd2 = cb + o_q2; d.hp2 = cb + o_h2; }
   d.n_obst = desc->n_obst; d.obst_max_iter = desc->obst_max_iter;
   d.obst_upper = desc->obst_upper; d.obst_rho = desc->obst_rho; d.obst_threshold = desc->obst_threshold;
+  d.obst_kind = desc->obst_kind; d.obst_dyk_max_iter = desc->obst_dykstra_max_iter; d.obst_dyk_tol = desc->obst_dykstra_tol;
   if (desc->n_obst > 0) { d.ob_c = cb + o_oc; d.ob_W = cb + o_ow; d.ob_Wi = cb + o_oi; d.ob_lo = cb + o_ol; }
   d.qd = cb + o_qd; d.rho_x = cb + o_rx; d.lo_x = cb + o_lx; d.hi_x = cb + o_hx;
   d.rho_u = cb + o_ru; d.lo_u = cb + o_lu; d.hi_u = cb + o_hu; d.alphas = cb + o_al;
@@ -2635,7 +2764,7 @@ static size_t carve(const isls_plan *p, long long B, char *base, Dev *d, Dev *al
   takeD(d ? &d->kk : nullptr, tm);
   takeD(d ? &d->zs : nullptr, T * p->n_via * n * TILE);
   takeD(d ? &d->lsc : nullptr, T * p->L * TILE);
-  takeD(d ? &d->obw : nullptr, p->desc.n_obst > 0 ? 2 * tn : 0);
+  takeD(d ? &d->obw : nullptr, p->desc.n_obst > 0 ? (2 + (p->desc.obst_kind == 1 ? 2 * (size_t)p->desc.n_obst : 0)) * tn : 0);
   const size_t tC = p->desc.isls_dim > 0 ? tm * (size_t)(p->desc.isls_dim + 1) : 0;
   takeD(d ? &d->Zm : nullptr, tC); takeD(d ? &d->Lm : nullptr, tC); takeD(d ? &d->Xu : nullptr, tC);
   const size_t S = T * TILE;
@@ -2771,6 +2900,8 @@ extern "C" int isls_ilqr_admm_solve_f64(const isls_plan *plan, const isls_solve_
                                         size_t ws_bytes, const isls_solve_out *out, void *stream) {
   if (!opts || !out || !x0 || !u_init || !zs) return fail(ISLS_E_INVALID, "NULL argument");
   if (opts->max_admm < 1) return fail(ISLS_E_INVALID, "max_admm must be >= 1");
+  if (plan && plan->desc.n_obst > 0 && plan->desc.obst_kind != 0)
+    return fail(ISLS_E_UNSUPPORTED, "iLQR-ADMM implements the rotated-rectangle (obst_kind = 0) obstacle projection");
   Dev d;
   int rc = setup(plan, opts, B, ws, ws_bytes, out, &d);
   if (rc) return rc;
@@ -2929,8 +3060,8 @@ extern "C" int isls_lqt_admm_dp_f64(const isls_plan *plan, const isls_solve_opts
     return fail(ISLS_E_UNSUPPORTED, "LQT-ADMM needs a linear model (double_integrator)");
   if (plan && plan->desc.cost_kind != ISLS_COST_QUADRATIC)
     return fail(ISLS_E_UNSUPPORTED, "LQT-ADMM needs the quadratic via-point cost");
-  if (plan && plan->desc.n_obst > 0)
-    return fail(ISLS_E_UNSUPPORTED, "obstacle-set state projections are implemented for iLQR-ADMM only");
+  if (plan && plan->desc.n_obst > 0 && (plan->desc.obst_kind != 1 || plan->n < 4))
+    return fail(ISLS_E_UNSUPPORTED, "the LQT path implements the spherical (obst_kind = 1) obstacle projection, x_dim >= 4");
   if (opts->max_admm < 1) return fail(ISLS_E_INVALID, "max_admm must be >= 1");
   Dev d;
   isls_solve_opts o = *opts;
@@ -2950,6 +3081,7 @@ extern "C" int isls_lqt_admm_dp_f64(const isls_plan *plan, const isls_solve_opts
     CK(cudaMemsetAsync(d.odone, 0, T * TILE * sizeof(int), s));
     CK(cudaMemsetAsync(d.status, 0, T * TILE * sizeof(int), s));
     CK(cudaMemsetAsync(d.cost, 0, T * TILE * sizeof(double), s));
+    if (d.out.inner_iters) CK(cudaMemsetAsync(d.out.inner_iters, 0, (size_t)B * d.max_admm * sizeof(int), s));
     // shared gains: K-pass on tile 0 only (linear model: the Jacobian does not depend on the trajectory)
     Dev d1 = d;
     d1.T = 1;

@@ -22,7 +22,8 @@ class ProblemDesc(C.Structure):
                 ("Hp_b", C.c_void_p), ("n_obst", C.c_int32), ("obst_max_iter", C.c_int32),
                 ("obst_centers", C.c_void_p), ("obst_W", C.c_void_p), ("obst_W_inv", C.c_void_p),
                 ("obst_lower", C.c_void_p), ("obst_upper", C.c_double), ("obst_rho", C.c_double),
-                ("obst_threshold", C.c_double), ("isls_dim", C.c_int32)]
+                ("obst_threshold", C.c_double), ("obst_kind", C.c_int32), ("obst_dykstra_max_iter", C.c_int32),
+                ("obst_dykstra_tol", C.c_double), ("isls_dim", C.c_int32)]
 
 
 class SolveOpts(C.Structure):

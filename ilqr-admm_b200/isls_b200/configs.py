@@ -196,3 +196,28 @@ def arm_robust_batch(B, N=100, dt=0.01, seed=_seed(8), I_o=50, I_a=10, L=30, tol
     return dict(name="arm3_robust", model="arm3", dt=dt, N=N, n=n, m=m, zs=zs, Qdiag=Qdiag, seq=seq, u_std=1e-4,
                 x0=x0, u0=np.zeros((N, m)), lo_u=None, hi_u=None, lo_x=None, hi_x=None, rho_u=None, rho_x=None,
                 robust=robust, I_o=I_o, I_a=I_a, L=L, tol=tol, alpha=1.0)
+
+
+def di_obstacle_batch(B=1, N=100, seed=_seed(9), max_iter=200, tol=1e-3):
+    """LQT-ADMM double integrator (n=4, m=2) avoiding two spherical obstacles with a STATE projection
+    (notebooks/Double integrator/LQR and SLS with spherical obstacle avoidance.ipynb cells 4-14, scenario 0):
+    project_set_convex (5 iterations, threshold 1e-2) followed by Dykstra (50 iterations, tol 1e-5) over the quadratic
+    shells 0.5 ||p - c_k||^2 >= 0.5 (1.1 r_k)^2 of the position.  Problem 0 is the notebook's (x0 = 0, target (1,1))."""
+    rng = np.random.default_rng(seed)
+    n, m = 4, 2
+    dt = 1.0 / N
+    zs = np.stack([np.zeros(n), np.array([1.0, 1.0, 0.0, 0.0])])
+    Qdiag = np.stack([np.zeros(n), np.full(n, 1e3)])
+    seq = np.zeros(N, dtype=np.int32)
+    seq[-1] = 1
+    x0 = np.zeros((B, n))
+    if B > 1:
+        x0[1:, :2] = rng.uniform(-0.1, 0.3, (B - 1, 2))
+    rho_x = np.zeros((N, n))
+    rho_x[:, :2] = 1.0
+    radii = np.array([0.1, 0.15]) * 1.1
+    obstacles = dict(kind="quadratic", centers=np.array([[0.5, 0.5], [0.5, 0.2]]), lower=0.5 * radii ** 2, upper=1e2,
+                     rho=1.0, max_iter=5, threshold=1e-2, dykstra_max_iter=50, dykstra_tol=1e-5)
+    return dict(name="di_obstacles", model="double_integrator", dt=dt, N=N, n=n, m=m, zs=zs, Qdiag=Qdiag, seq=seq,
+                u_std=1e-4, x0=x0, u0=np.zeros((N, m)), lo_u=None, hi_u=None, lo_x=None, hi_x=None, rho_u=None,
+                rho_x=rho_x, obstacles=obstacles, I_o=1, I_a=max_iter, L=1, tol=tol, alpha=1.0)

@@ -116,18 +116,29 @@ class ObstacleSets:
     projection k maps the position p = x[:2] of every time step to  c_k + W_k^-1 Pi_sq(W_k (p - c_k))  with
     Pi_sq = project_square_batch(., lower_k, upper) (isls/projections.py:246-255, 289-374).  Pass it as `project_x`."""
 
-    def __init__(self, centers, W, lower, upper=1e5, rho=1e1, max_iter=15, threshold=1e-3):
+    def __init__(self, centers, W=None, lower=None, upper=1e5, rho=1e1, max_iter=15, threshold=1e-3, kind="square",
+                 dykstra_max_iter=0, dykstra_tol=1e-5):
+        """kind="square": rotated infinity-norm shells (W required; all state components go through the consensus
+        ADMM, As = I_n).  kind="quadratic": spherical shells lower <= 0.5 ||p - c||^2 <= upper on the position only
+        (`project_quadratic`, isls/projections.py:91-105), followed by `project_set_convex_dykstra` when
+        dykstra_max_iter > 0 - the project_state of Double integrator/LQR and SLS with spherical obstacle
+        avoidance.ipynb cell 12 (LQT path: SLS.ADMM_LQT_DP / ADMM_LQT_Batch)."""
         self.centers = np.asarray(centers, dtype=np.float64).reshape(-1, 2)
         K = self.centers.shape[0]
-        self.W = np.asarray(W, dtype=np.float64).reshape(K, 2, 2)
+        self.kind = kind
+        if kind not in ("square", "quadratic"):
+            raise ValueError("kind must be 'square' or 'quadratic'")
+        self.W = np.tile(np.eye(2), (K, 1, 1)) if W is None else np.asarray(W, dtype=np.float64).reshape(K, 2, 2)
         self.W_inv = np.linalg.inv(self.W)
         self.lower = np.asarray(lower, dtype=np.float64).reshape(K)
         self.upper, self.rho, self.max_iter, self.threshold = float(upper), float(rho), int(max_iter), float(threshold)
+        self.dykstra_max_iter, self.dykstra_tol = int(dykstra_max_iter), float(dykstra_tol)
 
     def as_dict(self):
-        return dict(kind="square", centers=self.centers, W=self.W, W_inv=self.W_inv, lower=self.lower, upper=self.upper,
-                    rho=self.rho, max_iter=self.max_iter, threshold=self.threshold)
+        return dict(kind=self.kind, centers=self.centers, W=self.W, W_inv=self.W_inv, lower=self.lower,
+                    upper=self.upper, rho=self.rho, max_iter=self.max_iter, threshold=self.threshold,
+                    dykstra_max_iter=self.dykstra_max_iter, dykstra_tol=self.dykstra_tol)
 
     def key(self):
-        return (self.centers.tobytes(), self.W.tobytes(), self.lower.tobytes(), self.upper, self.rho, self.max_iter,
-                self.threshold)
+        return (self.kind, self.centers.tobytes(), self.W.tobytes(), self.lower.tobytes(), self.upper, self.rho,
+                self.max_iter, self.threshold, self.dykstra_max_iter, self.dykstra_tol)

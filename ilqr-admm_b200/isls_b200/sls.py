@@ -7,7 +7,7 @@ from ._lib import IslsError
 import ctypes as C
 
 from . import _lib
-from .projections import Bound, SetConvexSOC
+from .projections import Bound, ObstacleSets, SetConvexSOC
 from .utils import diag_of, get_double_integrator_AB
 
 
@@ -67,13 +67,15 @@ class SLS:
 
     def _lqt(self, x0, project_x, project_u, max_iter, rho_x, rho_u, alpha, tol, fixed_budget, want_masks,
              last_stage_dp=True, z_init=None):
-        bx = project_x.expand(self.N, self.x_dim) if project_x else None
+        obst = project_x if isinstance(project_x, ObstacleSets) else None
+        bx = project_x.expand(self.N, self.x_dim) if project_x and obst is None else None
         bu = project_u.expand(self.N, self.u_dim) if project_u else None
         plan = S.Plan("double_integrator", self.N, self.x_dim, self.u_dim, self._dt, self.Qdiag, self.seq, self.u_std,
                       1, rho_x=self._rho(rho_x, self.x_dim) if project_x else None,
                       lo_x=None if bx is None else bx[0], hi_x=None if bx is None else bx[1],
                       rho_u=self._rho(rho_u, self.u_dim) if project_u else None,
-                      lo_u=None if bu is None else bu[0], hi_u=None if bu is None else bu[1])
+                      lo_u=None if bu is None else bu[0], hi_u=None if bu is None else bu[1],
+                      obstacles=None if obst is None else obst.as_dict())
         sv = S.BatchSolver(plan, self.nb, self.device, max_outer=1, max_admm=max_iter, logs=True, want_gains=True,
                            want_masks=want_masks)
         x0 = torch.as_tensor(np.asarray(x0, dtype=np.float64)) if not isinstance(x0, torch.Tensor) else x0
@@ -137,8 +139,8 @@ class SLS:
         projection/dual update per iteration, all inside one kernel.  Returns (x, u, K, k[, logs])."""
         self._check_lqt()
         for nm, pr in (("project_x", project_x), ("project_u", project_u)):
-            if pr and not isinstance(pr, Bound):
-                raise TypeError("%s must be an isls_b200.projections.Bound" % nm)
+            if pr and not isinstance(pr, Bound) and not (nm == "project_x" and isinstance(pr, ObstacleSets)):
+                raise TypeError("%s must be an isls_b200.projections.Bound (or ObstacleSets for project_x)" % nm)
         out = self._lqt(x0, project_x, project_u, max_iter, rho_x, rho_u, alpha, tol, fixed_budget, want_masks)
         sq = (lambda t: t[0]) if self.batch is None else (lambda t: t)
         ret = (sq(out.x).reshape(*out.x.shape[:-2], -1) if self.batch is not None else out.x[0].reshape(-1),
@@ -156,8 +158,8 @@ class SLS:
         the LQT kernel.  Returns (x, u[, logs])."""
         self._check_lqt()
         for nm, pr in (("project_x", project_x), ("project_u", project_u)):
-            if pr and not isinstance(pr, Bound):
-                raise TypeError("%s must be an isls_b200.projections.Bound" % nm)
+            if pr and not isinstance(pr, Bound) and not (nm == "project_x" and isinstance(pr, ObstacleSets)):
+                raise TypeError("%s must be an isls_b200.projections.Bound (or ObstacleSets for project_x)" % nm)
         unc = self._lqt(x0, False, False, 1, None, None, 1.0, 0.0, True, False)          # z_x_init, z_u_init
         z_init = (unc.x.clone(), unc.u.clone())
         out = self._lqt(x0, project_x, project_u, max_iter, rho_x, rho_u, alpha, tol, fixed_budget, want_masks,

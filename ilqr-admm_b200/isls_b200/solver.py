@@ -82,6 +82,8 @@ class Plan:
             keep.update(obst_centers=_f64(ob["centers"], (K, 2)), obst_W=_f64(ob["W"], (K, 2, 2)),
                         obst_W_inv=_f64(ob["W_inv"], (K, 2, 2)), obst_lower=_f64(ob["lower"], (K,)))
             d.n_obst, d.obst_max_iter = K, int(ob["max_iter"])
+            d.obst_kind = {"square": 0, "quadratic": 1}[ob.get("kind", "square")]
+            d.obst_dykstra_max_iter, d.obst_dykstra_tol = int(ob.get("dykstra_max_iter", 0)), float(ob.get("dykstra_tol", 0.0))
             d.obst_upper, d.obst_rho, d.obst_threshold = float(ob["upper"]), float(ob["rho"]), float(ob["threshold"])
             for k in ("obst_centers", "obst_W", "obst_W_inv", "obst_lower"):
                 setattr(d, k, _ptr(keep[k]))

@@ -97,6 +97,14 @@ typedef struct isls_problem_desc {
   const double *obst_W_inv;    /* [n_obst, 2, 2] */
   const double *obst_lower;    /* [n_obst] */
   double obst_upper, obst_rho, obst_threshold;
+  int32_t obst_kind;           /* 0: rotated infinity-norm shells on all n components (As = I_n, car parking notebook);
+                                  1: quadratic shells obst_lower <= 0.5 ||p - c||^2 <= obst_upper of the position only
+                                  (As = I_2; project_quadratic, isls/projections.py:91-105; obst_W unused), followed by
+                                  project_set_convex_dykstra (isls/projections.py:465-505) when obst_dykstra_max_iter > 0
+                                  (Double integrator/LQR and SLS with spherical obstacle avoidance.ipynb cell 12;
+                                  implemented on the LQT path, isls_lqt_admm_dp_f64) */
+  int32_t obst_dykstra_max_iter;
+  double obst_dykstra_tol;
   int32_t isls_dim;            /* > 0: the plan is used by isls_isls_admm_solve_f64 with `dim` robustness columns
                                   (workspace for the [d_u | Phi_u(:, :dim)] matrix variables); <= 3 */
 } isls_problem_desc;

@@ -306,3 +306,45 @@ def run_isls_admm(model, p, b=0):
                                 rho_u=rb["rho_u"], max_admm_iter=p["I_a"], threshold=p["tol"], verbose=0, log=True)
     return dict(x=s.x_nom.copy(), u=s.u_nom.copy(), cost_log=np.array(s.cost_log, dtype=np.float64), du=du.copy(),
                 phi_u=phi_u.copy())
+
+
+# ------------------------------------------------------ double integrator, spherical obstacles (LQT-ADMM, state proj.)
+def di_obstacle_project_state(p):
+    """project_state of `Double integrator/LQR and SLS with spherical obstacle avoidance.ipynb` cell 12, built from the
+    reference's own project_set_convex, project_quadratic and project_set_convex_dykstra."""
+    load()
+    from isls.projections import project_quadratic, project_set_convex, project_set_convex_dykstra
+    ob = p["obstacles"]
+    d, x_dim = p["n"], 2
+    xs, lowers, upper = ob["centers"], ob["lower"], ob["upper"]
+    K = len(xs)
+    As = [np.eye(x_dim)] * K
+    bs = [-xs[i] * 0 for i in range(K)]
+    projections = [lambda x, lower=lower, i=i: project_quadratic(x - xs[i], lower, upper) + xs[i]
+                   for i, lower in enumerate(lowers)]
+
+    def project_state(x):
+        x_ = x.reshape(-1, d).copy()
+        x_[:, :x_dim] = project_set_convex(x_[:, :x_dim], As, bs, projections, max_iter=ob["max_iter"], verbose=0,
+                                           threshold=ob["threshold"])
+        x_[:, :x_dim] = project_set_convex_dykstra(x_[:, :x_dim], projections, max_iter=ob["dykstra_max_iter"],
+                                                   verbose=0, tol=ob["dykstra_tol"])
+        return x_.flatten()
+    return project_state
+
+
+def run_di_obstacles(p, b=0, form="dp"):
+    from . import models as M
+    pkg, _ = load()
+    N, n, m = p["N"], p["n"], p["m"]
+    model = M.make_model("double_integrator", nb_dim=m, dt=p["dt"])
+    rho_x = np.stack([np.diag(r) for r in p["rho_x"]])
+    with quiet():
+        s = pkg.SLS(n, m, N)
+        s.AB = [model.A, model.B]
+        s.set_quadratic_cost(p["zs"], np.stack([np.diag(q) for q in p["Qdiag"]]), p["seq"], p["u_std"])
+        fn = s.ADMM_LQT_DP if form == "dp" else s.ADMM_LQT_Batch
+        r = fn(p["x0"][b], project_x=di_obstacle_project_state(p), max_iter=p["I_a"], rho_x=rho_x, alpha=1.0,
+               tol=p["tol"], verbose=False, log=True)
+        cost = s.compute_cost(r[0], r[1])
+    return dict(x=r[0].reshape(N, n), u=r[1].reshape(N, m), logs=np.array(r[-1]), cost=float(cost))

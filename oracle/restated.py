@@ -367,6 +367,55 @@ def obstacle_projections(ob):
     return [make(i) for i in range(len(ob["centers"]))]
 
 
+def project_quadratic_batch(x, l, u):
+    """isls/projections.py:91-105: rows of x onto l <= 0.5 ||x||^2 <= u (radial scaling)."""
+    z = x.copy()
+    val = 0.5 * np.sum(x * x, axis=-1)
+    c1 = np.nonzero(val > u)[0]
+    c2 = np.nonzero(l > val)[0]
+    z[c1] = x[c1] * np.sqrt(2 * u) / np.linalg.norm(x[c1], axis=-1)[:, None]
+    z[c2] = x[c2] * np.sqrt(2 * l) / np.linalg.norm(x[c2], axis=-1)[:, None]
+    return z
+
+
+def sphere_projections(ob):
+    """Per-obstacle projections of the spherical-obstacle notebook (Double integrator/LQR and SLS with spherical
+    obstacle avoidance.ipynb cell 12): positions p -> c + Pi_quadratic(p - c, lower, upper)."""
+    return [(lambda x, i=i: project_quadratic_batch(x - ob["centers"][i], ob["lower"][i], ob["upper"]) + ob["centers"][i])
+            for i in range(len(ob["centers"]))]
+
+
+def project_set_convex_dykstra(x0, projections, max_iter, tol):
+    """isls/projections.py:465-505: Dykstra's alternating projections on all rows together; stops when every row's
+    summed squared increment change is below tol, or after max_iter + 1 sweeps.  Returns (u, sweeps)."""
+    d = len(projections)
+    u = x0.copy()
+    z = np.zeros((d,) + x0.shape)
+    k = 0
+    cI = np.full(x0.shape[0], 10.0)
+    while k <= max_iter and np.any(cI >= tol):
+        cI = cI * 0
+        for i in range(d):
+            prev_u = u.copy()
+            u = projections[i](prev_u - z[i])
+            prev_z = z[i].copy()
+            z[i] = u - (prev_u - prev_z)
+            cI = cI + np.linalg.norm(prev_z - z[i], axis=-1) ** 2
+        k += 1
+    return u, k
+
+
+def project_positions_spheres(pre, ob):
+    """project_state of the spherical-obstacle notebook on one problem's rows pre [N, n]: positions through
+    project_set_convex (rho, max_iter, threshold) then Dykstra; the other components pass through."""
+    proj = sphere_projections(ob)
+    z = pre.copy()
+    p1, its = project_set_convex_rows(pre[:, :2], proj, ob["rho"], ob["max_iter"], ob["threshold"])
+    p2, sweeps = project_set_convex_dykstra(p1, proj, ob["dykstra_max_iter"], ob["dykstra_tol"])
+    z[:, :2] = p2
+    return z, its, sweeps
+
+
 def project_set_convex_rows(x0, projections, rho, max_iter, threshold):
     """isls/projections.py:289-374 for As = I, bs = 0 (what both obstacle notebooks pass): consensus ADMM over the
     sets, rows of x0 [rows, dim] projected together, stop on the MAX over sets and rows of the residual norms (< threshold),
@@ -602,7 +651,9 @@ def lqt_admm_dp(p, fixed_budget=False, batch_form=False):
     Qd = p["Qdiag"][seq]
     R = p["u_std"]
     bx, bu = _bounds(p, "x", N, n), _bounds(p, "u", N, m)
-    proj_x, proj_u = bx is not None, bu is not None
+    obst = p.get("obstacles")
+    proj_x, proj_u = bx is not None or obst is not None, bu is not None
+    inner_log = np.zeros((B, I_a, 2), dtype=np.int32) if obst is not None else None
     rho_x = np.broadcast_to(np.asarray(p["rho_x"], float), (N, n)) if proj_x else np.zeros((N, n))
     rho_u = np.broadcast_to(np.asarray(p["rho_u"], float), (N, m)) if proj_u else np.zeros((N, m))
     A1, B1 = model.A, model.B
@@ -652,8 +703,14 @@ def lqt_admm_dp(p, fixed_budget=False, batch_form=False):
         if proj_x:
             zprev = zx[ia]
             pre = relax * xs + (1.0 - relax) * zprev + lx[ia]
-            znew = np.clip(pre, bx[0], bx[1])
-            mask_x[ia] = (pre > bx[1]).astype(np.int8) - (pre < bx[0]).astype(np.int8)
+            if obst is not None:
+                znew = np.empty_like(pre)
+                for q in range(ia.size):
+                    znew[q], i1, i2 = project_positions_spheres(pre[q], obst)
+                    inner_log[ia[q], a] = i1, i2
+            else:
+                znew = np.clip(pre, bx[0], bx[1])
+                mask_x[ia] = (pre > bx[1]).astype(np.int8) - (pre < bx[0]).astype(np.int8)
             r = xs - znew
             lx[ia] = lx[ia] + r
             zx[ia] = znew
@@ -686,7 +743,7 @@ def lqt_admm_dp(p, fixed_budget=False, batch_form=False):
     cost = quad_cost(p, zs, x_last[:, None], u_last[:, None])[:, 0]
     return dict(x=x_last, u=u_last, K=np.broadcast_to(K, (B, N, m, n)).copy(), k=k_last, cost=cost, iters=iters,
                 exit_code=exit_code, res_log=res_log, z_x=zx, z_u=zu, lam_x=lx, lam_u=lu, mask_x=mask_x,
-                mask_u=mask_u, non_pd=np.broadcast_to(non_pd, (B,)).copy())
+                mask_u=mask_u, non_pd=np.broadcast_to(non_pd, (B,)).copy(), inner_iters=inner_log)
 
 
 # ================================================================================ SLS path (item 4, config 4)

@@ -327,6 +327,30 @@ def golden_isls_admm(B=3):
                         cost_log=_pad(logs), du=np.stack(dus), phi_u=np.stack(phis))
 
 
+def golden_di_obstacles():
+    """LQT-ADMM with the spherical-obstacle state projection (set-convex + Dykstra) of the unmodified reference:
+    the notebook problem with ADMM_LQT_DP (500 iterations: printed cost 2.701e-01) and ADMM_LQT_Batch, plus three more
+    start states; residual logs kept in full (the non-convex iteration does not converge and amplifies rounding, so
+    parity is checked on the first iterations)."""
+    out = {}
+    p = P.di_obstacle_batch(4, max_iter=500, tol=1e-4)
+    res = [S.run_di_obstacles(p, b, "dp") for b in range(4)]
+    out.update(x0=p["x0"], dp_x=np.stack([r["x"] for r in res]), dp_u=np.stack([r["u"] for r in res]),
+               dp_logs=np.stack([r["logs"] for r in res]), dp_cost=np.array([r["cost"] for r in res]))
+    print("di obstacles dp costs", out["dp_cost"])
+    p = P.di_obstacle_batch(4, max_iter=200, tol=1e-3)
+    res = [S.run_di_obstacles(p, b, "batch") for b in range(4)]
+    out.update(batch_logs=np.stack([r["logs"] for r in res]), batch_cost=np.array([r["cost"] for r in res]))
+    # the projection closure alone on random position clouds around the obstacles
+    rng = np.random.default_rng(5)
+    proj = S.di_obstacle_project_state(p)
+    pts = np.zeros((5, 100, 4))
+    pts[:, :, :2] = rng.uniform(0.1, 0.9, (5, 100, 2))
+    pts[:, :, 2:] = rng.normal(0, 1, (5, 100, 2))
+    out.update(proj_in=pts, proj_out=np.stack([proj(q.flatten()).reshape(100, 4) for q in pts]))
+    np.savez_compressed(os.path.join(OUT, "di_obstacles.npz"), **out)
+
+
 if __name__ == "__main__":
     assert S.available(), "needs the reference tree"
     only = set(sys.argv[1:])                       # e.g. `make_golden.py tutorial` regenerates one fixture family
@@ -353,5 +377,7 @@ if __name__ == "__main__":
         golden_parking()
     if want("isls_admm"):
         golden_isls_admm()
+    if want("di_obstacles"):
+        golden_di_obstacles()
     if want("lqt_batch"):
         golden_lqt_admm_batch(P.di_batch(3), "di_lqt_admm_batch")

@@ -42,19 +42,26 @@ def run_ilqr_dp(p, max_iter, L, tol_fun=1e-5, fixed_budget=False, device="cuda:0
     return {k: v.cpu().numpy() for k, v in out.items()}
 
 
-def run_lqt_admm_dp(p, fixed_budget=False, device="cuda:0"):
+def run_lqt_admm_dp(p, fixed_budget=False, device="cuda:0", batch_form=False):
     from isls_b200 import get_double_integrator_AB
     B = p["x0"].shape[0]
     s = SLS(p["n"], p["m"], p["N"], batch=B, device=device)
     s.AB = get_double_integrator_AB(p["m"], 2, p["dt"])
     s.set_quadratic_cost(p["zs"], p["Qdiag"], p["seq"], p["u_std"])
     kw = {}
+    if p.get("obstacles") is not None:
+        from isls_b200 import ObstacleSets
+        ob = p["obstacles"]
+        kw.update(project_x=ObstacleSets(ob["centers"], None, ob["lower"], ob["upper"], ob["rho"], ob["max_iter"],
+                                         ob["threshold"], kind=ob["kind"], dykstra_max_iter=ob["dykstra_max_iter"],
+                                         dykstra_tol=ob["dykstra_tol"]), rho_x=p["rho_x"])
     if p.get("lo_x") is not None:
         kw.update(project_x=Bound(p["lo_x"], p["hi_x"]), rho_x=p["rho_x"])
     if p.get("lo_u") is not None:
         kw.update(project_u=Bound(p["lo_u"], p["hi_u"]), rho_u=p["rho_u"])
-    s.ADMM_LQT_DP(p["x0"], max_iter=p["I_a"], tol=p["tol"], alpha=p.get("alpha", 1.0), fixed_budget=fixed_budget,
-                  want_masks=True, **kw)
+    fn = s.ADMM_LQT_Batch if batch_form else s.ADMM_LQT_DP
+    fn(p["x0"], max_iter=p["I_a"], tol=p["tol"], alpha=p.get("alpha", 1.0), fixed_budget=fixed_budget,
+       want_masks=p.get("obstacles") is None, **kw)
     return {k: v.cpu().numpy() for k, v in s.last.items()}
 
 
