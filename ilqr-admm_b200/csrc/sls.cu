@@ -484,6 +484,51 @@ extern "C" int isls_sls_admm_f64(isls_sls_plan *p, const isls_sls_admm_opts *o, 
   return ISLS_OK;
 }
 
+// k_new = k + (I - K Su) Linv0 Su'Q (xd_new - xd_old)   (sls.py:244-248), one CTA per problem
+__global__ void k_sls_replan(int Nm, int Nn, const double *Linv0, const double *DTQ, const double *Su, const double *K,
+                             const double *k, const double *xdn, const double *xdo, double *kn) {
+  extern __shared__ double sv[];            // [Nn] delta / Su t2, [Nm] t1, [Nm] t2
+  double *dl = sv, *t1 = sv + Nn, *t2 = t1 + Nm;
+  const long long b = blockIdx.x;
+  for (int r = threadIdx.x; r < Nn; r += blockDim.x) dl[r] = xdn[(size_t)b * Nn + r] - xdo[(size_t)b * Nn + r];
+  __syncthreads();
+  for (int r = threadIdx.x; r < Nm; r += blockDim.x) {
+    double acc = 0.0;
+    for (int q = 0; q < Nn; q++) acc = fma(DTQ[(size_t)r * Nn + q], dl[q], acc);
+    t1[r] = acc;
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < Nm; r += blockDim.x) {
+    double acc = 0.0;
+    for (int q = 0; q < Nm; q++) acc = fma(Linv0[(size_t)r * Nm + q], t1[q], acc);
+    t2[r] = acc;
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < Nn; r += blockDim.x) {
+    double acc = 0.0;
+    for (int q = 0; q < Nm; q++) acc = fma(Su[(size_t)r * Nm + q], t2[q], acc);
+    dl[r] = acc;
+  }
+  __syncthreads();
+  const double *Kb = K + (size_t)b * Nm * Nn;
+  for (int r = threadIdx.x; r < Nm; r += blockDim.x) {
+    double acc = 0.0;
+    for (int q = 0; q < Nn; q++) acc = fma(Kb[(size_t)r * Nn + q], dl[q], acc);
+    kn[(size_t)b * Nm + r] = k[(size_t)b * Nm + r] + (t2[r] - acc);
+  }
+}
+
+extern "C" int isls_sls_replan_f64(const isls_sls_plan *p, int64_t B, const double *K_dev, const double *k_dev,
+                                   const double *xd_new_dev, const double *xd_old_dev, double *k_new_dev, void *stream) {
+  if (!p || B <= 0 || !K_dev || !k_dev || !xd_new_dev || !xd_old_dev || !k_new_dev)
+    return isls_fail(ISLS_E_INVALID, "NULL argument or B <= 0");
+  const size_t smem = ((size_t)p->Nn + 2 * p->Nm) * sizeof(double);
+  k_sls_replan<<<(unsigned)B, 256, smem, (cudaStream_t)stream>>>(p->Nm, p->Nn, p->Linv0, p->DTQ, p->Su, K_dev, k_dev,
+                                                                xd_new_dev, xd_old_dev, k_new_dev);
+  CK(cudaGetLastError());
+  return ISLS_OK;
+}
+
 extern "C" int isls_sls_controller_f64(const isls_sls_plan *p, int64_t B, int32_t n_first_cols,
                                        const double *phi_cols_dev, const double *du_dev, void *workspace_dev,
                                        size_t workspace_bytes, double *K_dev, double *k_dev, void *stream) {

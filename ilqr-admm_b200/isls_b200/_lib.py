@@ -54,7 +54,7 @@ EXPORTS = ["isls_version", "isls_last_error_string", "isls_model_id", "isls_mode
            "isls_measure_fp64_tflops", "isls_profile_enable", "isls_profile_collect",
            "isls_sls_plan_create", "isls_sls_plan_destroy", "isls_sls_operators", "isls_sls_solve_f64",
            "isls_sls_admm_f64", "isls_sls_controller_f64", "isls_mc_rollout_f64", "isls_project_rows_f64",
-           "isls_isls_admm_solve_f64"]
+           "isls_isls_admm_solve_f64", "isls_sls_replan_f64"]
 
 KERNEL_CLASSES = ["init", "kpass", "ff", "linesearch", "admm", "outer_end", "finalize", "backward_full", "accept",
                   "lqt", "compact", "isls_cols", "isls_update"]
@@ -102,6 +102,7 @@ def lib():
     L.isls_sls_admm_f64.argtypes = [C.c_void_p, C.POINTER(SlsAdmmOpts), C.c_int64] + [C.c_void_p] * 8
     L.isls_sls_controller_f64.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.isls_sls_replan_f64.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
     L.isls_mc_rollout_f64.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int64,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                       C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -296,6 +296,35 @@ class SLS:
         return (K[0], k[0]) if single else (K, k)
 
 
+def _replan_api():
+    def initialize_replanning_procedure(self, K):
+        """isls/sls.py:244-245.  The replan matrix (I - K Su)(Su'Q Su + R)^-1 Su'Q is never formed: the gains are kept
+        and replan_feedforward applies it as four matrix-vector products per problem."""
+        Nm, Nn = self.N * self.u_dim, self.N * self.x_dim
+        self._replan_K = torch.as_tensor(K, dtype=torch.float64).to(self.device).reshape(-1, Nm, Nn).contiguous()
+
+    def replan_feedforward(self, k, xd):
+        """k + replan_matrix @ (xd - self.xd) (isls/sls.py:247-248); k [N m] / [B, N m], xd [N n] / [B, N n]."""
+        pl = self._plan()
+        dev = self.device
+        Nm, Nn = self.N * self.u_dim, self.N * self.x_dim
+        k = torch.as_tensor(k, dtype=torch.float64).to(dev)
+        single = k.ndim == 1
+        k = k.reshape(-1, Nm).contiguous()
+        B_ = k.shape[0]
+        xd = torch.as_tensor(xd, dtype=torch.float64).to(dev).reshape(-1, Nn).expand(B_, Nn).contiguous()
+        xo = self._xd().to(dev).reshape(-1, Nn).expand(B_, Nn).contiguous()
+        K = self._replan_K.expand(B_, Nm, Nn).contiguous()
+        out = torch.empty_like(k)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        with torch.cuda.device(dev):
+            rc = _lib.lib().isls_sls_replan_f64(pl.handle, B_, p(K), p(k), p(xd), p(xo), p(out),
+                                                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(rc, "isls_sls_replan_f64")
+        return out[0] if single else out
+    return initialize_replanning_procedure, replan_feedforward
+
+
 def _mc_api(cls_is_nonlinear):
     """get_trajectory_batch / dp / sls (isls/sls_base.py:62-105, isls/isls_base.py:28-71) on the device."""
     def _args(self):
@@ -354,3 +383,4 @@ class _SlsPlan:
 
 
 SLS.get_trajectory_batch, SLS.get_trajectory_dp, SLS.get_trajectory_sls = _mc_api(False)
+SLS.initialize_replanning_procedure, SLS.replan_feedforward = _replan_api()

@@ -272,6 +272,13 @@ int isls_sls_controller_f64(const isls_sls_plan *plan, int64_t B, int32_t n_firs
                             const double *du_dev, void *workspace_dev, size_t workspace_bytes, double *K_dev,
                             double *k_dev, void *stream);
 
+/* SLS.initialize_replanning_procedure + SLS.replan_feedforward (isls/sls.py:244-248): new feed-forward terms for a new
+ * target vector without re-solving,  k_new = k + (I - K Su) (Su'Q Su + R)^-1 Su'Q (xd_new - xd_old),  evaluated as four
+ * matrix-vector products per problem (the replan matrix is never formed).
+ *   K_dev [B, N m, N n], k_dev [B, N m], xd_new_dev / xd_old_dev [B, N n] -> k_new_dev [B, N m]. */
+int isls_sls_replan_f64(const isls_sls_plan *plan, int64_t B, const double *K_dev, const double *k_dev,
+                        const double *xd_new_dev, const double *xd_old_dev, double *k_new_dev, void *stream);
+
 /* ---- Monte-Carlo closed-loop evaluation of one controller over B sampled initial states ----
  * mode 0: get_trajectory_batch  u_t = us[t]                         (k_dev = us [N, m])
  * mode 1: get_trajectory_dp     u_t = K_t x_t + k_t                 (K_dev [N, m, n], k_dev [N, m])

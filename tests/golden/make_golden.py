@@ -351,6 +351,34 @@ def golden_di_obstacles():
     np.savez_compressed(os.path.join(OUT, "di_obstacles.npz"), **out)
 
 
+def golden_replan():
+    """SLS.initialize_replanning_procedure / replan_feedforward (isls/sls.py:244-248) of the unmodified reference on the
+    C4-style double integrator (n=4, m=2, N=50): controller from solve_sls, then three new targets."""
+    pkg, _ = S.load()
+    from isls.utils import get_double_integrator_AB
+    n, m, N = 4, 2, 50
+    A, B = get_double_integrator_AB(2, nb_deriv=2, dt=1.0 / N)
+    zs = np.stack([np.zeros(n), np.array([0.8, 0.7, 0.0, 0.0])])
+    Qs = np.stack([np.zeros((n, n)), np.eye(n) * 1e6])
+    seq = np.zeros(N, dtype=np.int32); seq[-1] = 1
+    with S.quiet():
+        s = pkg.SLS(n, m, N)
+        s.AB = [A, B]
+        s.set_quadratic_cost(zs, Qs, seq, 1e-2)
+        PHI_U, du = s.solve_sls()
+        K, k = s.controller(PHI_U, du)
+        s.initialize_replanning_procedure(K)
+        rng = np.random.default_rng(3)
+        tg = rng.uniform(0.5, 1.0, (3, 2))
+        xds, ks = [], []
+        for t in tg:
+            xd = s.xd.copy()
+            xd[-n:-n + 2] = t
+            xds.append(xd); ks.append(s.replan_feedforward(k, xd))
+    np.savez_compressed(os.path.join(OUT, "sls_replan.npz"), zs=zs, K=K, k=k, xd_new=np.stack(xds), k_new=np.stack(ks),
+                        xd_old=np.array(s.xd))
+
+
 if __name__ == "__main__":
     assert S.available(), "needs the reference tree"
     only = set(sys.argv[1:])                       # e.g. `make_golden.py tutorial` regenerates one fixture family
@@ -377,6 +405,8 @@ if __name__ == "__main__":
         golden_parking()
     if want("isls_admm"):
         golden_isls_admm()
+    if want("replan"):
+        golden_replan()
     if want("di_obstacles"):
         golden_di_obstacles()
     if want("lqt_batch"):
