@@ -221,3 +221,28 @@ def di_obstacle_batch(B=1, N=100, seed=_seed(9), max_iter=200, tol=1e-3):
     return dict(name="di_obstacles", model="double_integrator", dt=dt, N=N, n=n, m=m, zs=zs, Qdiag=Qdiag, seq=seq,
                 u_std=1e-4, x0=x0, u0=np.zeros((N, m)), lo_u=None, hi_u=None, lo_x=None, hi_x=None, rho_u=None,
                 rho_x=rho_x, obstacles=obstacles, I_o=1, I_a=max_iter, L=1, tol=tol, alpha=1.0)
+
+
+def sls_state_bounds_problem(N=100):
+    """SLS-ADMM with robust control bounds AND a robust terminal state constraint (notebooks/Double integrator/LQR
+    and SLS with state bounds.ipynb cells 3-17): 1-D double integrator (n=2, m=1), no tracking cost (Q = 0: the
+    final state is imposed by the constraints only), |u| <= 3, final position in [0.5, 0.5], final velocity 0, all as
+    chance constraints (p = 0.9, var_x0 = 0.02) on the rows of [d | Phi(:, :1)]."""
+    from scipy.stats import norm
+    n, m = 2, 1
+    zs = np.stack([np.zeros(n), np.array([1.0, 1.0])])
+    seq = np.zeros(N, dtype=np.int32)
+    seq[-1] = 1
+    mu = np.zeros(2)
+    mu[0] = 1.0
+    sigma = np.zeros(2)
+    sigma[1:] = 0.02
+    psi = norm.ppf(0.9)
+    Au = np.diag(np.sqrt(sigma))
+    As = [np.concatenate([Au, (-mu / psi)[None]], 0), np.concatenate([Au, (mu / psi)[None]], 0)]
+    cone = lambda up, lo: [np.append(np.zeros(2), up / psi), np.append(np.zeros(2), -lo / psi)]
+    rho_x = np.zeros(N * n)
+    rho_x[-2:] = 1e3
+    return dict(n=n, m=m, N=N, dt=1.0 / N, zs=zs, Qdiag=np.zeros((2, n)), seq=seq, u_std=1e-4, As=As,
+                bs_u=cone(3.0, -3.0), x_rows=[(N * n - 2, As, cone(0.5, 0.5)), (N * n - 1, As, cone(0.0, 0.0))],
+                rho_x=rho_x, rho_u=1e-3, max_iter=100, tol=1e-5, inner_rho=1e1, inner_max_iter=20, inner_threshold=1e-2)

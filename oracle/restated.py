@@ -850,17 +850,27 @@ def sls_solve(A, Bm, N, Qdiag_t, xd, u_std):
 
 
 def admm_sls(A, Bm, N, Qdiag_t, xd, u_std, As, bs, rho_u, max_iter=5000, alpha=1.0, tol=1e-3, inner_rho=1.0,
-             inner_max_iter=200, inner_threshold=1e-4, fixed_budget=False):
-    """SLS.ADMM_SLS (isls/sls.py:319-454) with project_u = project_set_convex(.., [project_soc_unit]*P) row-wise and
-    no state projection.  One problem per row of xd [B, N n].  Returns du [B, N m], phi_u [B, N m, N n], logs."""
+             inner_max_iter=200, inner_threshold=1e-4, fixed_budget=False, x_rows=None, rho_x=None):
+    """SLS.ADMM_SLS (isls/sls.py:319-454) with project_u = project_set_convex(.., [project_soc_unit]*P) row-wise.
+    One problem per row of xd [B, N n].  Returns du [B, N m], phi_u [B, N m, N n], logs.
+
+    State side (`LQR and SLS with state bounds.ipynb` cells 16-17): rho_x [N n] = diagonal of Qr, x_rows = list of
+    (row index into N n, As_i, bs_i): project_x projects each listed row of [d_x | Phi_x(:, :n/2)] by its own
+    project_set_convex call (same inner parameters) and leaves the other rows alone."""
     n, m = Bm.shape
     c = n // 2 + 1
     base = sls_solve(A, Bm, N, Qdiag_t, xd, u_std)
     Sw, Su, DTQ = base["Sw"], base["Su"], base["DTQ"]
     Sx = Sw[:, :n // 2]
     l_side = base["L"] + rho_u * np.eye(N * m)                     # sls.py:339-349 (Rr = rho_u I)
-    l_inv = trailing_inverses(l_side, m, N)[0]                     # sls.py:352, 367
     r_fb = -DTQ @ Sx
+    proj_x = x_rows is not None
+    if proj_x:
+        qr = np.asarray(rho_x, float).reshape(-1)
+        SuTQr = Su.T * qr[None, :]                                 # sls.py:342-347
+        l_side = l_side + SuTQr @ Su
+        r_fb = r_fb - SuTQr @ Sx
+    l_inv = trailing_inverses(l_side, m, N)[0]                     # sls.py:352, 367
     xd2 = np.atleast_2d(xd)
     B = xd2.shape[0]
     du_out = np.zeros((B, N * m))
@@ -870,13 +880,30 @@ def admm_sls(A, Bm, N, Qdiag_t, xd, u_std, As, bs, rho_u, max_iter=5000, alpha=1
         r_side = np.concatenate([(DTQ @ xd2[b])[:, None], r_fb], axis=-1)
         z_u = np.zeros((N * m, c))
         lmb = np.zeros((N * m, c))
+        z_x = np.zeros((N * n, c))
+        lmb_x = np.zeros((N * n, c))
         prim = dual = 1e6
         lg = []
         ex = ADMM_MAXIT
         for j in range(max_iter):
             reg_u = z_u - lmb
-            x_u = l_inv @ (r_side + rho_u * reg_u)                 # sls.py:372-380
+            rs = r_side + rho_u * reg_u
+            if proj_x:
+                rs = rs + SuTQr @ (z_x - lmb_x)
+            x_u = l_inv @ rs                                       # sls.py:372-380
             pprim, pdual = prim, dual
+            if proj_x:
+                x_x = Su @ x_u
+                x_x[:, 1:] += Sx                                   # sls.py:381-382
+                zx_prev = z_x.copy()
+                y = alpha * x_x + (1 - alpha) * z_x + lmb_x
+                z_x = y.copy()
+                for (row, As_x, bs_x) in x_rows:
+                    z_x[row:row + 1], it_in = project_set_convex_soc(y[row:row + 1], As_x, bs_x, rho=inner_rho,
+                                                                     max_iter=inner_max_iter, threshold=inner_threshold)
+                    inner_total[b] += it_in
+                pr_x = x_x - z_x
+                lmb_x = lmb_x + pr_x
             z_prev = z_u.copy()
             z_u, it_in = project_set_convex_soc(alpha * x_u + (1 - alpha) * z_u + lmb, As, bs, rho=inner_rho,
                                                 max_iter=inner_max_iter, threshold=inner_threshold)
@@ -885,6 +912,9 @@ def admm_sls(A, Bm, N, Qdiag_t, xd, u_std, As, bs, rho_u, max_iter=5000, alpha=1
             lmb = lmb + pr
             dual = np.linalg.norm(rho_u * (z_u - z_prev))          # sls.py:417 (Frobenius, Rr = rho_u I)
             prim = np.linalg.norm(rho_u * pr)
+            if proj_x:                                             # sls.py:414-415
+                dual = np.linalg.norm(qr[:, None] * (z_x - zx_prev)) + dual
+                prim = np.linalg.norm(qr[:, None] * pr_x) + prim
             lg.append((prim, dual))
             iters[b] = j + 1
             if fixed_budget:

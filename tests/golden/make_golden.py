@@ -379,6 +379,35 @@ def golden_replan():
                         xd_old=np.array(s.xd))
 
 
+def golden_sls_state_bounds():
+    """SLS.ADMM_SLS with project_u AND project_x of the unmodified reference on the notebook problem
+    (Double integrator/LQR and SLS with state bounds.ipynb cells 16-17; printed: "primal: 1.37e-04 dual: 1.80e-01")."""
+    pkg, _ = S.load()
+    from isls.utils import get_double_integrator_AB
+    from isls.projections import project_set_convex, project_soc_unit
+    p = P.sls_state_bounds_problem()
+    N, n = p["N"], p["n"]
+    A, B = get_double_integrator_AB(1, nb_deriv=2, dt=p["dt"])
+    kw = dict(rho=p["inner_rho"], max_iter=p["inner_max_iter"], threshold=p["inner_threshold"])
+    project_u = lambda y: project_set_convex(y, p["As"], p["bs_u"], projections=[project_soc_unit] * 2, verbose=False, **kw)
+
+    def project_x(x):
+        x_ = x.copy()
+        for row, As_x, bs_x in p["x_rows"]:
+            x_[row:row + 1] = project_set_convex(x_[row:row + 1], As_x, bs_x, projections=[project_soc_unit] * 2, **kw)
+        return x_
+    rho_x = np.zeros((N, n, n))
+    rho_x[-1, 0, 0] = rho_x[-1, 1, 1] = 1e3
+    with S.quiet():
+        s = pkg.SLS(n, 1, N)
+        s.AB = [A, B]
+        s.set_quadratic_cost(p["zs"], np.zeros((2, n, n)), p["seq"], p["u_std"])
+        du, PHI, log = s.ADMM_SLS(project_u=project_u, project_x=project_x, max_iter=p["max_iter"], rho_x=rho_x,
+                                  rho_u=p["rho_u"], alpha=1.0, tol=p["tol"], verbose=0, log=True)
+    print("sls state bounds", len(log), log[-1])
+    np.savez_compressed(os.path.join(OUT, "sls_state_bounds.npz"), du=du, phi_u=PHI, logs=np.array(log))
+
+
 if __name__ == "__main__":
     assert S.available(), "needs the reference tree"
     only = set(sys.argv[1:])                       # e.g. `make_golden.py tutorial` regenerates one fixture family
@@ -405,6 +434,8 @@ if __name__ == "__main__":
         golden_parking()
     if want("isls_admm"):
         golden_isls_admm()
+    if want("sls_state"):
+        golden_sls_state_bounds()
     if want("replan"):
         golden_replan()
     if want("di_obstacles"):

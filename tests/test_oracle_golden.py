@@ -280,3 +280,21 @@ def test_di_spherical_obstacles_vs_reference_golden(golden):
     for q, ref in zip(g["proj_in"], g["proj_out"]):
         z, i1, i2 = R.project_positions_spheres(q, ob)
         assert np.abs(z - ref).max() < 1e-12 and i1 == 5 and 1 <= i2 <= 51
+
+
+def test_admm_sls_state_projection_vs_reference_golden(golden):
+    """SLS.ADMM_SLS with project_u and project_x (sls.py:319-454; Double integrator/LQR and SLS with state bounds.ipynb
+    cells 16-17): oracle vs the unmodified reference, incl. the notebook's printed residuals 1.37e-04 / 1.80e-01."""
+    from oracle import models as M
+    g = golden("sls_state_bounds")
+    assert abs(g["logs"][-1, 0] - 1.37e-04) < 5e-7 and abs(g["logs"][-1, 1] - 1.80e-01) < 5e-4 and len(g["logs"]) == 100
+    p = P.sls_state_bounds_problem()
+    mdl = M.make_model("double_integrator", nb_dim=1, dt=p["dt"])
+    xd = p["zs"][p["seq"]].reshape(-1)
+    o = R.admm_sls(mdl.A, mdl.B, p["N"], np.zeros((p["N"], p["n"])), xd, p["u_std"], p["As"], p["bs_u"], p["rho_u"],
+                   max_iter=p["max_iter"], alpha=1.0, tol=p["tol"], inner_rho=p["inner_rho"],
+                   inner_max_iter=p["inner_max_iter"], inner_threshold=p["inner_threshold"], x_rows=p["x_rows"],
+                   rho_x=p["rho_x"])
+    assert o["iters"][0] == 100
+    assert np.abs(o["logs"][0] - g["logs"]).max() < 1e-8
+    assert np.abs(o["du"][0] - g["du"]).max() < 1e-9 and np.abs(o["phi_u"][0] - g["phi_u"]).max() < 1e-8
