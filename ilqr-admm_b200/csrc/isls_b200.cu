@@ -1488,7 +1488,7 @@ __global__ void k_isls_update(Dev d, SocSet S, int outer, int inner) {
     for (int q = 0; q < C; q++) y[q] = (d.relax * xu[q] + (1.0 - d.relax) * z[q]) + lm[q];
     y[0] += un;                                                       // notebook cell 25
   }
-  const int its = soc_project_set(S, y, zn, act, red);
+  const int its = soc_project_set(S, S.b, y, zn, act, red);
   double ps = 0.0, ds = 0.0;
   if (act) {
     zn[0] -= un;

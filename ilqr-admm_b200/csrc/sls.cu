@@ -191,6 +191,13 @@ __global__ void k_mask_blt(int n, int m, int N, double *Y) {
 // ------------------------------------------------------------------------------------------------ ADMM_SLS
 #include "soc.cuh"
 
+struct SocRowsX {                       // state-side projection: a few rows of [d_x | Phi_x(:, :c-1)]
+  int nx;
+  int row[ISLS_MAX_XROWS];
+  double qr[ISLS_MAX_XROWS];
+  double b[ISLS_MAX_XROWS][SOC_MAXP][SOC_MAXR];
+};
+
 struct SlsAdmm {
   int Nm, Nn, c, max_iter, fixed_budget;
   double rho_u, alpha, tol;
@@ -203,13 +210,17 @@ struct SlsAdmm {
   double *logs;           // [B x max_iter x 2] or NULL
   int *iters, *exits;     // [B]
   long long *inner_total; // [B] or NULL
+  const double *Su;       // [Nn x Nm] (state side)
+  const double *Sw;       // [Nn x Nn]
 };
 
 // One CTA per problem, thread r = row r of [d_u | Phi_u(:, :c-1)]   (sls.py:372-447 + projections.py:289-374)
-__global__ void k_sls_admm(SlsAdmm a, SocSet S) {
+__global__ void k_sls_admm(SlsAdmm a, SocSet S, SocRowsX X) {
   extern __shared__ double sh[];
-  double *rhs = sh;                         // [Nm][c] right-hand side of the current iteration
+  double *rhs = sh;                         // [Nm][c] right-hand side of the current iteration, then x_u
   double *red = sh + (size_t)a.Nm * a.c;    // reduction scratch [32]
+  double *zxs = red + 32;                   // [nx][c] z_x - lambda_x of the projected state rows (reg_x)
+  double zx[SOC_MAXC] = {}, lx[SOC_MAXC] = {};           // thread i < nx owns state row X.row[i]
   const int b = blockIdx.x, r = threadIdx.x, c = a.c;
   const bool act = r < a.Nm;
   // r_side row: column 0 = (Su'Q xd)[r], columns 1.. = -Su'Q Sx (shared)
@@ -226,7 +237,14 @@ __global__ void k_sls_admm(SlsAdmm a, SocSet S) {
   long long inner = 0;
   for (it = 0; it < a.max_iter && !ex; it++) {
     // x_u = l_inv (r_side + Rr (z - lambda))                                   sls.py:372-380
-    if (act) for (int q = 0; q < c; q++) rhs[r * c + q] = rs[q] + a.rho_u * (z[q] - lm[q]);
+    if (r < X.nx) for (int q = 0; q < c; q++) zxs[r * c + q] = zx[q] - lx[q];
+    __syncthreads();
+    if (act) for (int q = 0; q < c; q++) {
+      double v = rs[q] + a.rho_u * (z[q] - lm[q]);
+      for (int i = 0; i < X.nx; i++)                     // + Su'Qr reg_x (sls.py:371): Qr is zero off the listed rows
+        v = fma(X.qr[i] * a.Su[(size_t)X.row[i] * a.Nm + r], zxs[i * c + q], v);
+      rhs[r * c + q] = v;
+    }
     __syncthreads();
     if (act) {
       double acc[SOC_MAXC] = {};
@@ -237,10 +255,37 @@ __global__ void k_sls_admm(SlsAdmm a, SocSet S) {
       }
       for (int q = 0; q < c; q++) xu[q] = acc[q];
     }
+    double psx = 0.0, dsx = 0.0;
+    if (X.nx > 0) {
+      // ---- state side: x_x = Su x_u (+ Sx on the feedback columns) at the listed rows, own projection each
+      __syncthreads();
+      if (act) for (int q = 0; q < c; q++) rhs[r * c + q] = xu[q];
+      __syncthreads();
+      int xin = 0;
+      if (r < X.nx) {
+        double xx[SOC_MAXC] = {}, y[SOC_MAXC], zn[SOC_MAXC];
+        const double *su = a.Su + (size_t)X.row[r] * a.Nm;
+        for (int k = 0; k < a.Nm; k++) {
+          const double sv_ = su[k];
+          for (int q = 0; q < c; q++) xx[q] = fma(sv_, rhs[k * c + q], xx[q]);
+        }
+        for (int q = 1; q < c; q++) xx[q] += a.Sw[(size_t)X.row[r] * a.Nn + q - 1];              // sls.py:381-382
+        for (int q = 0; q < c; q++) y[q] = (a.alpha * xx[q] + (1.0 - a.alpha) * zx[q]) + lx[q];
+        xin = soc_project_set(S, X.b[r], y, zn, true, nullptr);
+        for (int q = 0; q < c; q++) {
+          const double pr = xx[q] - zn[q], dz = zn[q] - zx[q];
+          lx[q] += pr;
+          zx[q] = zn[q];
+          psx = fma(X.qr[r] * pr, X.qr[r] * pr, psx);
+          dsx = fma(X.qr[r] * dz, X.qr[r] * dz, dsx);
+        }
+      }
+      inner += (long long)(block_sum((double)xin, red) + 0.5);
+    }
     // ---- z = project_set_convex(alpha x + (1-alpha) z + lambda)               sls.py:403-405
     double x0[SOC_MAXC], x[SOC_MAXC];
     for (int q = 0; q < c; q++) x0[q] = (a.alpha * xu[q] + (1.0 - a.alpha) * z[q]) + lm[q];
-    inner += soc_project_set(S, x0, x, act, red);
+    inner += soc_project_set(S, S.b, x0, x, act, red);
     // ---- dual update and residuals (sls.py:406-418), Rr = rho_u I
     double ps = 0.0, ds = 0.0;
     for (int q = 0; q < c; q++) {
@@ -253,6 +298,10 @@ __global__ void k_sls_admm(SlsAdmm a, SocSet S) {
     const double pprim = prim, pdual = dual;
     prim = sqrt(block_sum(act ? ps : 0.0, red));
     dual = sqrt(block_sum(act ? ds : 0.0, red));
+    if (X.nx > 0) {                                                          // sls.py:414-415
+      prim = sqrt(block_sum(psx, red)) + prim;
+      dual = sqrt(block_sum(dsx, red)) + dual;
+    }
     if (a.logs && r == 0) {
       a.logs[((size_t)b * a.max_iter + it) * 2] = prim;
       a.logs[((size_t)b * a.max_iter + it) * 2 + 1] = dual;
@@ -448,6 +497,22 @@ extern "C" int isls_sls_solve_f64(const isls_sls_plan *p, int64_t B, const doubl
   return ISLS_OK;
 }
 
+// state-side terms of the operators (sls.py:342-347): Lrho += sum_i qr_i Su[i,:]' Su[i,:],  rfb -= sum_i qr_i Su[i,:]' Sx[i,:]
+__global__ void k_sls_xrows_update(int Nm, int Nn, int c1, SocRowsX X, const double *Su, const double *Sw, double *Lrho,
+                                   double *rfb) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < (size_t)Nm * Nm; e += (size_t)gridDim.x * blockDim.x) {
+    const int ra = (int)(e / Nm), cb = (int)(e % Nm);
+    double acc = 0.0;
+    for (int i = 0; i < X.nx; i++) acc = fma(X.qr[i] * Su[(size_t)X.row[i] * Nm + ra], Su[(size_t)X.row[i] * Nm + cb], acc);
+    Lrho[e] += acc;
+    if (cb < c1) {
+      double f = 0.0;
+      for (int i = 0; i < X.nx; i++) f = fma(X.qr[i] * Su[(size_t)X.row[i] * Nm + ra], Sw[(size_t)X.row[i] * Nn + cb], f);
+      rfb[(size_t)ra * c1 + cb] -= f;
+    }
+  }
+}
+
 extern "C" int isls_sls_admm_f64(isls_sls_plan *p, const isls_sls_admm_opts *o, int64_t B, const double *xd_dev,
                                  double *du_dev, double *phi_cols_dev, double *logs_dev, int32_t *iters_dev,
                                  int32_t *exit_dev, int64_t *inner_total_dev, void *stream) {
@@ -458,17 +523,39 @@ extern "C" int isls_sls_admm_f64(isls_sls_plan *p, const isls_sls_admm_opts *o, 
     return isls_fail(ISLS_E_UNSUPPORTED, "unsupported cone set (need A_i of shape [c+1, c], c = 1 + x_dim/2 <= 4)");
   if (p->Nm > 1024) return isls_fail(ISLS_E_UNSUPPORTED, "N*u_dim > 1024");
   cudaStream_t s = (cudaStream_t)stream;
-  // (L + rho_u I)^-1 and -Su'Q Sx, cached per (rho_u)                        (sls.py:339-352, 367)
-  if (!p->have_rho || p->rho_cached != o->rho_u) {
+  SocRowsX X;
+  memset(&X, 0, sizeof(X));
+  if (o->n_x_rows < 0 || o->n_x_rows > ISLS_MAX_XROWS) return isls_fail(ISLS_E_INVALID, "n_x_rows out of range");
+  if (o->n_x_rows > 0) {
+    if (!o->x_row_idx || !o->x_bs || !o->rho_x_rows) return isls_fail(ISLS_E_INVALID, "state projection: NULL row data");
+    if (o->n_x_rows > p->Nm) return isls_fail(ISLS_E_UNSUPPORTED, "more projected state rows than control rows");
+    X.nx = o->n_x_rows;
+    for (int i = 0; i < X.nx; i++) {
+      if (o->x_row_idx[i] < 0 || o->x_row_idx[i] >= p->Nn) return isls_fail(ISLS_E_INVALID, "state row index out of range");
+      X.row[i] = o->x_row_idx[i];
+      X.qr[i] = o->rho_x_rows[i];
+      for (int q = 0; q < o->n_cones; q++)
+        for (int e = 0; e < o->cone_rows; e++) X.b[i][q][e] = o->x_bs[((size_t)i * o->n_cones + q) * o->cone_rows + e];
+    }
+  }
+  // (L + rho_u I [+ Su'Qr Su])^-1 and -Su'Q Sx [- Su'Qr Sx], cached per (rho_u) when there is no state side
+  if (!p->have_rho || p->rho_cached != o->rho_u || X.nx > 0) {
     CK(cudaMemcpyAsync(p->Lrho, p->L, (size_t)p->Nm * p->Nm * sizeof(double), cudaMemcpyDeviceToDevice, s));
     k_add_diag<<<(p->Nm + 127) / 128, 128, 0, s>>>(p->Nm, p->Lrho, o->rho_u);
     int rc = spd_inverse_dev(p, p->Lrho, p->Linv_rho, s);
     if (rc) return rc;
     // rfb = -DTQ * Sw[:, :c-1]  (Sx = first x_dim/2 columns of Sw)
     dgemm(s, p->Nm, c - 1, p->Nn, -1.0, p->DTQ, p->Nn, false, p->Sw, p->Nn, 0.0, p->rfb, c - 1);
+    if (X.nx > 0) {
+      CK(cudaMemcpyAsync(p->Lrho, p->L, (size_t)p->Nm * p->Nm * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      k_add_diag<<<(p->Nm + 127) / 128, 128, 0, s>>>(p->Nm, p->Lrho, o->rho_u);
+      k_sls_xrows_update<<<148, 256, 0, s>>>(p->Nm, p->Nn, c - 1, X, p->Su, p->Sw, p->Lrho, p->rfb);
+      int rc2 = spd_inverse_dev(p, p->Lrho, p->Linv_rho, s);
+      if (rc2) return rc2;
+    }
     // restore W = U^-1 of L (the shared PHI_U does not need it any more, but keep the plan consistent)
     p->rho_cached = o->rho_u;
-    p->have_rho = true;
+    p->have_rho = X.nx == 0;
   }
   SocSet S;
   soc_set_build(&S, o->n_cones, c, o->cone_rows, o->As, o->bs, o->inner_rho, o->inner_max_iter, o->inner_threshold);
@@ -477,9 +564,10 @@ extern "C" int isls_sls_admm_f64(isls_sls_plan *p, const isls_sls_admm_opts *o, 
   a.rho_u = o->rho_u; a.alpha = o->alpha; a.tol = o->tol;
   a.linv = p->Linv_rho; a.DTQ = p->DTQ; a.rfb = p->rfb; a.xd = xd_dev; a.du = du_dev; a.phic = phi_cols_dev;
   a.logs = logs_dev; a.iters = iters_dev; a.exits = exit_dev; a.inner_total = (long long *)inner_total_dev;
+  a.Su = p->Su; a.Sw = p->Sw;
   const int threads = ((p->Nm + 31) / 32) * 32;
-  const size_t smem = ((size_t)p->Nm * c + 32) * sizeof(double);
-  k_sls_admm<<<(unsigned)B, threads, smem, s>>>(a, S);
+  const size_t smem = ((size_t)p->Nm * c + 32 + (size_t)ISLS_MAX_XROWS * c) * sizeof(double);
+  k_sls_admm<<<(unsigned)B, threads, smem, s>>>(a, S, X);
   CK(cudaGetLastError());
   return ISLS_OK;
 }

@@ -63,15 +63,18 @@ __device__ __forceinline__ void soc_unit_row(int d, const double *y, double *out
 
 // Inner ADMM of project_set_convex for this thread's row x0[c] -> x[c]; `act` = the thread owns a row; every thread of
 // the CTA must call it (block reductions).  Returns the number of inner iterations.
-__device__ __forceinline__ int soc_project_set(const SocSet &S, const double (&x0)[SOC_MAXC], double (&x)[SOC_MAXC],
-                                               bool act, double *red) {
+// `bb`: the offsets b_i to use (S.b, or a row's own); red == nullptr: a single row projected on its own (its stop rule
+// is its own residual; no block reduction, callable by a subset of the CTA).
+__device__ __forceinline__ int soc_project_set(const SocSet &S, const double (&bb)[SOC_MAXP][SOC_MAXR],
+                                               const double (&x0)[SOC_MAXC], double (&x)[SOC_MAXC], bool act,
+                                               double *red) {
   const int c = S.c;
   double zi[SOC_MAXP][SOC_MAXR], li[SOC_MAXP][SOC_MAXR];
   int inner = 0;
   for (int q = 0; q < c; q++) x[q] = x0[q];
   for (int i = 0; i < S.P; i++)
     for (int e = 0; e < S.ra; e++) {
-      double v = S.b[i][e];
+      double v = bb[i][e];
       for (int q = 0; q < c; q++) v = fma(S.A[i][e][q], x[q], v);
       zi[i][e] = v;                         // z_i = A_i x + b_i   (projections.py:315)
       li[i][e] = 0.0;
@@ -82,7 +85,7 @@ __device__ __forceinline__ int soc_project_set(const SocSet &S, const double (&x
     double rsd[SOC_MAXC] = {};
     for (int i = 0; i < S.P; i++)
       for (int e = 0; e < S.ra; e++) {
-        const double w = (-S.b[i][e] + zi[i][e]) - li[i][e];
+        const double w = (-bb[i][e] + zi[i][e]) - li[i][e];
         for (int q = 0; q < c; q++) rsd[q] = fma(S.A[i][e][q], w, rsd[q]);
       }
     double tq[SOC_MAXC];
@@ -96,7 +99,7 @@ __device__ __forceinline__ int soc_project_set(const SocSet &S, const double (&x
     for (int i = 0; i < S.P; i++) {
       double axb[SOC_MAXR], y[SOC_MAXR], zn[SOC_MAXR];
       for (int e = 0; e < S.ra; e++) {
-        double v = S.b[i][e];
+        double v = bb[i][e];
         for (int q = 0; q < c; q++) v = fma(S.A[i][e][q], x[q], v);
         axb[e] = v;
         y[e] = v + li[i][e];
@@ -118,8 +121,8 @@ __device__ __forceinline__ int soc_project_set(const SocSet &S, const double (&x
     }
     // stop rule on the max over rows and cones (projections.py:343-348)
     const double pprev = pm, dprev = dm;
-    pm = block_max(act ? pmax : 0.0, red);
-    dm = block_max(act ? dmax : 0.0, red);
+    pm = red ? block_max(act ? pmax : 0.0, red) : pmax;
+    dm = red ? block_max(act ? dmax : 0.0, red) : dmax;
     if (pm < S.threshold && dm < S.threshold) break;
     if (j < S.max_iter - 1) {
       const double pch = fabs(pprev - pm) / (pprev + 1e-30), dch = fabs(dprev - dm) / (dprev + 1e-30);

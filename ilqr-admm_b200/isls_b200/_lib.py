@@ -41,7 +41,8 @@ class SlsAdmmOpts(C.Structure):
     _fields_ = [("max_iter", C.c_int32), ("rho_u", C.c_double), ("alpha", C.c_double), ("tol", C.c_double),
                 ("fixed_budget", C.c_int32), ("n_cones", C.c_int32), ("cone_rows", C.c_int32), ("As", C.c_void_p),
                 ("bs", C.c_void_p), ("inner_rho", C.c_double), ("inner_max_iter", C.c_int32),
-                ("inner_threshold", C.c_double)]
+                ("inner_threshold", C.c_double), ("n_x_rows", C.c_int32), ("x_row_idx", C.c_void_p),
+                ("x_bs", C.c_void_p), ("rho_x_rows", C.c_void_p)]
 
 
 class SolveOut(C.Structure):

@@ -54,6 +54,19 @@ class SetConvexSOC:
         self.rho, self.max_iter, self.threshold = float(rho), int(max_iter), float(threshold)
 
 
+class SetConvexSOCRows:
+    """State-side projection of ADMM_SLS (notebooks/Double integrator/LQR and SLS with state bounds.ipynb cell 16): each
+    listed row of [d_x | Phi_x(:, :n/2)] (index into N * x_dim, negative indices allowed) is projected by its own
+    `project_set_convex(x[row:row+1], A_, b_row, [project_soc_unit]*P, rho, max_iter, threshold)`; all other rows pass
+    through.  The cone matrices A_ and the inner parameters are those of the control-side `SetConvexSOC`."""
+
+    def __init__(self, rows, bs):
+        self.rows = [int(r) for r in rows]
+        self.bs = np.ascontiguousarray(np.stack([np.stack([np.asarray(b, dtype=np.float64) for b in row_bs])
+                                                 for row_bs in bs]))
+        assert self.bs.ndim == 3 and self.bs.shape[0] == len(self.rows)
+
+
 # ---------------------------------------------------------------- batched row projections on the device (CUDA tensors)
 def _rows(kind, x, p0=None, p1=None, l=0.0, u=0.0):
     import ctypes as C

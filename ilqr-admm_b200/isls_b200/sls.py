@@ -7,7 +7,7 @@ from ._lib import IslsError
 import ctypes as C
 
 from . import _lib
-from .projections import Bound, ObstacleSets, SetConvexSOC
+from .projections import Bound, ObstacleSets, SetConvexSOC, SetConvexSOCRows
 from .utils import diag_of, get_double_integrator_AB
 
 
@@ -231,8 +231,8 @@ class SLS:
                  verbose=False, log=False, fixed_budget=False):
         """SLS-ADMM with robust (chance-constrained) control bounds w.r.t. the initial position
         (isls/sls.py:319-454).  project_u: `SetConvexSOC`; returns (du, phi_u[, logs])."""
-        if project_x:
-            raise NotImplementedError("device ADMM_SLS implements the control-side projection (project_u)")
+        if project_x and not isinstance(project_x, SetConvexSOCRows):
+            raise TypeError("project_x must be an isls_b200.projections.SetConvexSOCRows")
         if not isinstance(project_u, SetConvexSOC):
             raise TypeError("project_u must be an isls_b200.projections.SetConvexSOC")
         pl = self._plan()
@@ -253,6 +253,22 @@ class SLS:
                              fixed_budget=int(fixed_budget), n_cones=As.shape[0], cone_rows=c + 1,
                              As=As.ctypes.data, bs=bs.ctypes.data, inner_rho=project_u.rho,
                              inner_max_iter=project_u.max_iter, inner_threshold=project_u.threshold)
+        if project_x:
+            rows = np.array([r % Nn for r in project_x.rows], dtype=np.int32)
+            xbs = project_x.bs
+            if xbs.shape[1:] != bs.shape:
+                raise ValueError("state-row cone offsets must be [rows, %d, %d]" % bs.shape)
+            rx = np.asarray(rho_x, dtype=np.float64)
+            if rx.ndim == 3:                                   # [N, n, n] like the reference
+                rx = np.stack([np.diag(q) for q in rx]).reshape(-1)
+            rx = np.ascontiguousarray(np.broadcast_to(rx.reshape(-1), (Nn,)))
+            off = np.ones(Nn, dtype=bool)
+            off[rows] = False
+            if np.any(rx[off] != 0.0):
+                raise ValueError("rho_x must be zero on the rows project_x leaves alone")
+            rxr = np.ascontiguousarray(rx[rows])
+            o.n_x_rows, o.x_row_idx, o.x_bs, o.rho_x_rows = len(rows), rows.ctypes.data, xbs.ctypes.data, rxr.ctypes.data
+            self._keep_x = (rows, xbs, rxr)
         p = lambda t: C.c_void_p(t.data_ptr())
         with torch.cuda.device(dev):
             rc = _lib.lib().isls_sls_admm_f64(pl.handle, C.byref(o), B_, p(xd), p(du), p(phic), p(logs), p(iters),

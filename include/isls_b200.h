@@ -257,7 +257,16 @@ typedef struct isls_sls_admm_opts {
   double inner_rho;        /* project_set_convex rho */
   int32_t inner_max_iter;  /* project_set_convex max_iter */
   double inner_threshold;  /* project_set_convex threshold */
+  /* ---- optional state-side projection project_x (sls.py:342-347, 381-382, 396-401, 414-415; Double integrator/LQR
+   * and SLS with state bounds.ipynb cells 16-17): the listed rows of [d_x | Phi_x(:, :n/2)] are each projected by
+   * their own project_set_convex call onto {A_i x + b_i in SOC} (same A_i as the control side, own b_i); Qr = diag
+   * with rho_x_rows on those rows and 0 elsewhere.  n_x_rows = 0: no state projection. ---- */
+  int32_t n_x_rows;          /* <= ISLS_MAX_XROWS */
+  const int32_t *x_row_idx;  /* host [n_x_rows]: row index into N * n */
+  const double *x_bs;        /* host [n_x_rows, P, cone_rows] */
+  const double *rho_x_rows;  /* host [n_x_rows]: Qr diagonal entries of those rows */
 } isls_sls_admm_opts;
+#define ISLS_MAX_XROWS 8
 /* xd_dev [B, N n] -> du_dev [B, N m] (= x_u[:,0]), phi_cols_dev [B, N m, c-1] (= x_u[:,1:c]; the full PHI_U of a
  * problem is [phi_cols | shared PHI_U[:, c-1:]], sls.py:450), logs_dev [B, max_iter, 2] (optional), iters_dev [B],
  * exit_dev [B] (ISLS_ADMM_*), inner_total_dev [B] int64 (optional: total inner projection iterations). */

@@ -229,3 +229,36 @@ def test_replanning_vs_reference_golden(golden):
     err2 = np.abs(kn2.cpu().numpy() - ref).max() / np.abs(ref).max()
     print("replan_feedforward (reference gains): rel err", err2)
     assert err2 < 1e-6
+
+
+def test_admm_sls_state_projection(golden):
+    """SLS.ADMM_SLS with project_u AND project_x (sls.py:319-454; Double integrator/LQR and SLS with state bounds.ipynb
+    cells 16-17: robust terminal position / velocity constraints, Q = 0): CUDA vs the unmodified reference (whose run
+    reproduces the notebook's printed residuals 1.37e-04 / 1.80e-01) and vs the oracle."""
+    from isls_b200 import SLS, SetConvexSOC, SetConvexSOCRows, get_double_integrator_AB
+    from oracle import problems as P
+    g = golden("sls_state_bounds")
+    p = P.sls_state_bounds_problem()
+    N, n = p["N"], p["n"]
+    s = SLS(n, 1, N)
+    s.AB = get_double_integrator_AB(1, 2, p["dt"])
+    s.set_quadratic_cost(p["zs"], p["Qdiag"], p["seq"], p["u_std"])
+    pu = SetConvexSOC(p["As"], p["bs_u"], rho=p["inner_rho"], max_iter=p["inner_max_iter"], threshold=p["inner_threshold"])
+    px = SetConvexSOCRows([r for r, _, _ in p["x_rows"]], [b for _, _, b in p["x_rows"]])
+    du, phi, logs = s.ADMM_SLS(project_u=pu, project_x=px, max_iter=p["max_iter"], rho_x=p["rho_x"], rho_u=p["rho_u"],
+                               alpha=1.0, tol=p["tol"], log=True)
+    logs = logs.cpu().numpy()
+    it = int(s.last.iters[0])
+    ref = g["logs"]
+    print("ADMM_SLS + project_x: iterations gpu %d reference %d; last residuals gpu" % (it, len(ref)), logs[it - 1],
+          "reference", ref[-1], " max|d(du)|", np.abs(du.cpu().numpy() - g["du"]).max())
+    assert it == len(ref) == 100
+    assert abs(logs[it - 1, 0] - 1.37e-04) < 5e-7 and abs(logs[it - 1, 1] - 1.80e-01) < 5e-4      # notebook printout
+    assert np.abs(logs[:it] - ref).max() < 1e-6
+    assert np.abs(du.cpu().numpy() - g["du"]).max() < 1e-6
+    c = n // 2 + 1
+    assert np.abs(phi.cpu().numpy()[:, :c - 1] - g["phi_u"][:, :c - 1]).max() < 1e-6
+    # terminal state of the nominal response: position 0.5, velocity 0 (the constraints are equalities)
+    Su = s.Su.cpu().numpy()
+    xT = (Su @ du.cpu().numpy())[-2:]
+    assert abs(xT[0] - 0.5) < 2e-2 and abs(xT[1]) < 2e-2
