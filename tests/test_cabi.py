@@ -66,3 +66,30 @@ def test_host_mirror_argument_checks():
     # legacy spellings exist (README.md:24-39)
     assert s.set_cost_variables.__func__ is s.set_quadratic_cost.__func__
     assert hasattr(s, "solve_ilqr")
+
+
+def test_ctypes_struct_layouts_match_the_header():
+    """The ctypes mirrors of the POD structs (isls_b200/_lib.py) must have the size and field offsets gcc gives the
+    declarations of include/isls_b200.h - a silent mismatch would shift every argument."""
+    import ctypes as C
+    import subprocess
+    import tempfile
+    L = _lib()
+    structs = {"isls_problem_desc": L.ProblemDesc, "isls_solve_opts": L.SolveOpts, "isls_solve_out": L.SolveOut,
+               "isls_sls_admm_opts": L.SlsAdmmOpts}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "isls_b200.h"', 'int main(void) {']
+    for cname, ct in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0;', '}']
+    with tempfile.TemporaryDirectory() as td:
+        src, exe = os.path.join(td, "layout.c"), os.path.join(td, "layout")
+        open(src, "w").write("\n".join(lines))
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, src])
+        out = subprocess.check_output([exe], text=True)
+    got = dict(ln.split() for ln in out.strip().splitlines())
+    for cname, ct in structs.items():
+        assert int(got[cname]) == C.sizeof(ct), "sizeof(%s): header %s, ctypes %d" % (cname, got[cname], C.sizeof(ct))
+        for fname, _ in ct._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(ct, fname).offset, (cname, fname)
