@@ -2993,7 +2993,9 @@ extern "C" int isls_isls_admm_solve_f64(const isls_plan *plan, const isls_solve_
   if (!plan || plan->desc.isls_dim < 1) return fail(ISLS_E_INVALID, "the plan was not created with isls_dim > 0");
   if (plan->proj_x || !plan->proj_u) return fail(ISLS_E_UNSUPPORTED, "isls_admm: control projection only (rho_u, no rho_x)");
   const int C = plan->desc.isls_dim + 1;
-  if (soc->n_cones < 1 || soc->n_cones > SOC_MAXP || soc->cone_rows != C + 1 || !soc->As || !soc->bs)
+  // n_cones = 0: no projection (isls_admm called without project_u, notebook cell 23): z = x, zero residuals, one
+  // ADMM iteration per outer iteration - the unconstrained iSLS step
+  if (soc->n_cones < 0 || soc->n_cones > SOC_MAXP || (soc->n_cones > 0 && (soc->cone_rows != C + 1 || !soc->As || !soc->bs)))
     return fail(ISLS_E_UNSUPPORTED, "unsupported cone set (need A_i of shape [dim + 2, dim + 1])");
   Dev d;
   int rc = setup(plan, opts, B, ws, ws_bytes, out, &d);

@@ -302,12 +302,16 @@ class iSLS:
         self._check_get_Cs(get_Cs)
         if project_x:
             raise NotImplementedError("device isls_admm implements the control-side projection (project_u)")
-        if not isinstance(project_u, SetConvexSOC):
+        if project_u and not isinstance(project_u, SetConvexSOC):
             raise TypeError("project_u must be an isls_b200.projections.SetConvexSOC; Python callables cannot run "
                             "inside the kernels")
-        _, Rr = self.compute_Rr_Qr(None, rho_u)
-        if Rr is None:
-            raise ValueError("rho_u is required")
+        if project_u:
+            _, Rr = self.compute_Rr_Qr(None, rho_u)
+            if Rr is None:
+                raise ValueError("rho_u is required")
+        else:                                # isls_admm without constraints (notebook cell 23): Rr = 0, z = x
+            Rr = np.zeros((self.N, self.u_dim))
+            project_u = None
         inf = np.full((self.N, self.u_dim), np.inf)
         sv = self._solver(max_line_search, None, None, Rr, (-inf, inf), k_max, max_admm_iter, isls_dim=int(dim))
         sv.set_inputs(self._x0, self._u_init, self._zs_b())

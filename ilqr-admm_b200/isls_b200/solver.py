@@ -209,12 +209,17 @@ class BatchSolver:
         if p.isls_dim < 1:
             raise _lib.IslsError("the plan was not created with isls_dim > 0")
         C_ = p.isls_dim + 1
-        if soc.As.shape[1:] != (C_ + 1, C_):
-            raise ValueError("cone matrices must be [%d, %d] (dim + 2 rows, dim + 1 columns)" % (C_ + 1, C_))
         o = self._opts(tol, 1e-4, relax, fixed_budget, False, stall_tol=1e-3, osc_tol=1e-3)   # isls.py:664, 700, 704
-        so = _lib.SlsAdmmOpts(max_iter=0, rho_u=0.0, alpha=relax, tol=tol, fixed_budget=int(fixed_budget),
-                              n_cones=soc.As.shape[0], cone_rows=C_ + 1, As=soc.As.ctypes.data, bs=soc.bs.ctypes.data,
-                              inner_rho=soc.rho, inner_max_iter=soc.max_iter, inner_threshold=soc.threshold)
+        if soc is None:                      # no projection: unconstrained iSLS step (z = x)
+            so = _lib.SlsAdmmOpts(max_iter=0, rho_u=0.0, alpha=relax, tol=tol, fixed_budget=int(fixed_budget),
+                                  n_cones=0, cone_rows=C_ + 1, inner_rho=1.0, inner_max_iter=1, inner_threshold=1.0)
+        else:
+            if soc.As.shape[1:] != (C_ + 1, C_):
+                raise ValueError("cone matrices must be [%d, %d] (dim + 2 rows, dim + 1 columns)" % (C_ + 1, C_))
+            so = _lib.SlsAdmmOpts(max_iter=0, rho_u=0.0, alpha=relax, tol=tol, fixed_budget=int(fixed_budget),
+                                  n_cones=soc.As.shape[0], cone_rows=C_ + 1, As=soc.As.ctypes.data,
+                                  bs=soc.bs.ctypes.data, inner_rho=soc.rho, inner_max_iter=soc.max_iter,
+                                  inner_threshold=soc.threshold)
         if "d_u" not in self.out:
             f64 = dict(dtype=torch.float64, device=dev)
             self.out.update(d_u=torch.empty(self.B, p.N, p.m, **f64), phi_u=torch.empty(self.B, p.N, p.m, p.isls_dim, **f64))

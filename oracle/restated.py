@@ -984,6 +984,9 @@ def isls_admm(p, fixed_budget=False):
     N, n, m = p["N"], p["n"], p["m"]
     rb = p["robust"]
     dim, rho = rb["dim"], float(rb["rho_u"])
+    projected = rb.get("As") is not None                   # isls_admm without project_u: Rr = 0, z = x (cell 23)
+    if not projected:
+        rho = 0.0
     I_o, I_a, L, tol, relax = p["I_o"], p["I_a"], p["L"], p["tol"], p.get("alpha", 1.0)
     x_nom, u_nom = initial_rollout(p)
     B = x_nom.shape[0]
@@ -1052,8 +1055,11 @@ def isls_admm(p, fixed_budget=False):
                 y = relax * x_u + (1.0 - relax) * z_u + lam
                 y2 = y.reshape(N * m, C).copy()
                 y2[:, 0] += un[0].reshape(-1)                                 # project_u(z, u_nom): notebook cell 25
-                zp, its = project_set_convex_soc(y2, rb["As"], rb["bs"], rho=rb["inner_rho"],
-                                                 max_iter=rb["inner_max_iter"], threshold=rb["inner_threshold"])
+                if projected:
+                    zp, its = project_set_convex_soc(y2, rb["As"], rb["bs"], rho=rb["inner_rho"],
+                                                     max_iter=rb["inner_max_iter"], threshold=rb["inner_threshold"])
+                else:
+                    zp, its = y2, 1
                 zp = zp.copy()
                 zp[:, 0] -= un[0].reshape(-1)
                 z_u = zp.reshape(N, m, C)

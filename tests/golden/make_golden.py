@@ -323,8 +323,19 @@ def golden_isls_admm(B=3):
         r = S.run_isls_admm(model, p, b)
         xs.append(r["x"]); us.append(r["u"]); logs.append(r["cost_log"]); dus.append(r["du"]); phis.append(r["phi_u"])
         print("isls_admm", b, len(r["cost_log"]), r["cost_log"][-1], np.abs(r["u"]).max())
+    # the same problems without any projection (notebook cell 23: isls_admm(q_dim, get_AB, max_line_search=10, ...))
+    ulogs, uphis = [], []
+    for b in range(B):
+        s = S.make_isls(model, p["N"], p["zs"], _Qs(p), p["seq"], p["u_std"])
+        S.init_nominal(s, p["x0"][b], p["u0"])
+        with S.quiet():
+            _, phi = s.isls_admm(3, model.get_AB, max_line_search=10, k_max=100, max_admm_iter=10, threshold=1e-4,
+                                 verbose=0, log=True)
+        ulogs.append(np.array(s.cost_log)); uphis.append(phi)
+        print("isls_admm unconstrained", b, len(s.cost_log), s.cost_log[-1])
     np.savez_compressed(os.path.join(OUT, "arm_isls_admm.npz"), x0=p["x0"], x=np.stack(xs), u=np.stack(us),
-                        cost_log=_pad(logs), du=np.stack(dus), phi_u=np.stack(phis))
+                        cost_log=_pad(logs), du=np.stack(dus), phi_u=np.stack(phis), unc_cost_log=_pad(ulogs),
+                        unc_phi_u=np.stack(uphis))
 
 
 def golden_di_obstacles():

@@ -75,8 +75,8 @@ def run_isls_admm(p, fixed_budget=False, device="cuda:0"):
     from isls_b200 import SetConvexSOC
     rb = p["robust"]
     s = make_isls(p, device)
-    soc = SetConvexSOC(rb["As"], rb["bs"], rho=rb["inner_rho"], max_iter=rb["inner_max_iter"],
-                       threshold=rb["inner_threshold"])
+    soc = False if rb.get("As") is None else SetConvexSOC(rb["As"], rb["bs"], rho=rb["inner_rho"],
+                                                          max_iter=rb["inner_max_iter"], threshold=rb["inner_threshold"])
     s.isls_admm(rb["dim"], p["model"], project_u=soc, max_admm_iter=p["I_a"], k_max=p["I_o"], max_line_search=p["L"],
                 rho_u=rb["rho_u"], alpha=p.get("alpha", 1.0), threshold=p["tol"], fixed_budget=fixed_budget)
     return {k: v.cpu().numpy() for k, v in s.last.items()}
