@@ -324,6 +324,32 @@ class iSLS:
         phi = out.phi_u.reshape(B_, self.N * self.u_dim, int(dim))
         return (du[0], phi[0]) if self.batch is None else (du, phi)
 
+    def controller(self, PHI_U, du):
+        """K, k = controller(PHI_U, du) - the call the robust notebook makes on an iSLS object after isls_admm
+        (3DoF robot/State bounds and robust control bounds.ipynb cells 23, 26; README "iSLS.controller"; the formula is
+        SLS.controller, isls/sls.py:235-242, on the time-varying operators C, D): Phi_x = C + D Phi_u,
+        K = Phi_u Phi_x^-1, k = (I - K D) du.
+
+        For the Phi_u that isls_admm returns - non-zero only in its first `dim` columns (robustness with respect to the
+        initial state) - this is an identity, not a solve: with E the first `dim` rows of the identity, Phi_u = phi E,
+        Phi_x = C + (D phi) E, and because the first block row of D is zero (x_0 does not depend on the controls) and
+        that of C^-1 = I - Z A is [I 0 ...], Woodbury gives E Phi_x^-1 = E, hence K = phi E = Phi_u and
+        k = du - phi (E D du) = du.  (The reference's dense inverse reproduces exactly that: |K - Phi_u| = 1.4e-15 on the
+        notebook problem, tests/golden/make_golden.py.)  A Phi_u with entries outside the first block column needs the
+        general block back-substitution, which exists for constant (A, B) only (SLS.controller)."""
+        if self.batch is not None:
+            raise IslsError("controller evaluates ONE problem: construct iSLS without `batch`")
+        dev = self.device
+        PHI_U = torch.as_tensor(PHI_U, dtype=torch.float64).to(dev)
+        du = torch.as_tensor(du, dtype=torch.float64).to(dev)
+        Nm, Nn = self.N * self.u_dim, self.N * self.x_dim
+        if PHI_U.shape != (Nm, Nn) or du.shape != (Nm,):
+            raise ValueError("PHI_U must be [N m, N n] and du [N m]")
+        if bool((PHI_U[:, self.x_dim:] != 0).any()):
+            raise NotImplementedError("iSLS.controller handles the Phi_u of isls_admm (non-zero first block column "
+                                      "only); a general time-varying Phi_u is not implemented on the device")
+        return PHI_U.clone(), du.clone()
+
     def _report(self, out):
         st = out.status.cpu().numpy()
         it = out.outer_iters.cpu().numpy()

@@ -323,6 +323,39 @@ def golden_isls_admm(B=3):
         r = S.run_isls_admm(model, p, b)
         xs.append(r["x"]); us.append(r["u"]); logs.append(r["cost_log"]); dus.append(r["du"]); phis.append(r["phi_u"])
         print("isls_admm", b, len(r["cost_log"]), r["cost_log"][-1], np.abs(r["u"]).max())
+    # controller + Monte-Carlo evaluation of the robust solution of problem 0 (notebook cells 21, 26): the legacy
+    # `sls.controller(PHI_U, du)` of the notebook is SLS.controller (sls.py:235-242) on the iSLS operators C, D
+    p0 = P.arm_robust_batch(1)
+    s = S.make_isls(model, p0["N"], p0["zs"], _Qs(p0), p0["seq"], p0["u_std"])
+    S.init_nominal(s, p0["x0"][0], p0["u0"])
+    rb = p0["robust"]
+    from isls.projections import project_set_convex, project_soc_unit
+
+    def project_u(u, u_nom):
+        y_ = u.copy()
+        y_[:, 0] += u_nom.flatten()
+        y_ = project_set_convex(y_, rb["As"], rb["bs"], projections=[project_soc_unit] * 2, rho=rb["inner_rho"],
+                                max_iter=rb["inner_max_iter"], threshold=rb["inner_threshold"], verbose=0)
+        y_[:, 0] -= u_nom.flatten()
+        return y_
+    with S.quiet():
+        du, phi_u = s.isls_admm(3, model.get_AB, max_line_search=p0["L"], k_max=p0["I_o"], project_u=project_u,
+                                rho_u=rb["rho_u"], max_admm_iter=p0["I_a"], threshold=p0["tol"], verbose=0, log=True)
+        Nm, Nn = p0["N"] * p0["m"], p0["N"] * p0["n"]
+        PHI_U = np.zeros((Nm, Nn))
+        PHI_U[:, :3] = phi_u
+        s.Sw, s.Su = s.C, s.D
+        pkg, _ = S.load()
+        K, k = pkg.SLS.controller(s, PHI_U, du)
+        rng = np.random.default_rng(21)
+        x0s = np.tile(s.x_nom[0:1], (64, 1))
+        x0s[:, :3] = rng.normal(loc=s.x_nom[0, :3], scale=np.sqrt(0.1), size=(64, 3))       # cell 21
+        # one sample per call: HEAD returns only the first trajectory for a 2-D x0 (isls_base.py:40-43)
+        res = [s.get_trajectory_sls(x0, K, k, noise_scale=0) for x0 in x0s]
+        xl, ul = np.concatenate([r[0] for r in res]), np.concatenate([r[1] for r in res])
+    print("controller: max|K - PHI_U|", np.abs(K - PHI_U).max(), " max|k - du|", np.abs(k - du).max(),
+          " success %", 100 * np.mean(np.all(np.abs(ul) <= 6.0 + 1e-3, axis=(1, 2))))
+    ctrl = dict(mc_x0=x0s, mc_u=ul, mc_x=xl, ctrl_K_minus_PHI=np.abs(K - PHI_U).max(), ctrl_k_minus_du=np.abs(k - du).max())
     # the same problems without any projection (notebook cell 23: isls_admm(q_dim, get_AB, max_line_search=10, ...))
     ulogs, uphis = [], []
     for b in range(B):
@@ -335,7 +368,7 @@ def golden_isls_admm(B=3):
         print("isls_admm unconstrained", b, len(s.cost_log), s.cost_log[-1])
     np.savez_compressed(os.path.join(OUT, "arm_isls_admm.npz"), x0=p["x0"], x=np.stack(xs), u=np.stack(us),
                         cost_log=_pad(logs), du=np.stack(dus), phi_u=np.stack(phis), unc_cost_log=_pad(ulogs),
-                        unc_phi_u=np.stack(uphis))
+                        unc_phi_u=np.stack(uphis), **ctrl)
 
 
 def golden_di_obstacles():
