@@ -448,3 +448,15 @@ def test_di_lqt_admm_batch_form_and_stage_api(golden):
                               c.K.cpu().numpy()[None], (al[:, None, None] * c.k[None]).cpu().numpy()[None])
     scale = max(1.0, np.abs(us).max())
     assert np.abs(xl.cpu().numpy() - xs[0]).max() < 1e-9 * scale and np.abs(ul.cpu().numpy() - us[0]).max() < 1e-9 * scale
+
+
+def test_ragged_horizon_and_candidate_counts():
+    """Horizons that are not a multiple of the line search's staged chunk (10 steps; ragged last bulk copy) and
+    candidate counts that do not fill the CTA shapes (L = 33 -> 7 of 10 warps, L = 7 -> 2 warps)."""
+    for N, L, B in ((37, 33, 5), (11, 7, 33), (101, 20, 3)):
+        p = P.car_batch(B, N=N, I_o=4, I_a=3, L=L)
+        out = _gpu().run_ilqr_admm(p, fixed_budget=True)
+        o = R.ilqr_admm(p, fixed_budget=True)
+        assert np.array_equal(out["alpha_idx"], o["alpha_idx"]), (N, L)
+        assert _gpu().rel_logs(out["cost_log"], o["cost_log"]) < 1e-9, (N, L)
+        assert np.abs(out["u"] - o["u"]).max() < 1e-9 and np.abs(out["z_u"] - o["z_u"]).max() < 1e-9, (N, L)
