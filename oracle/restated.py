@@ -3,7 +3,7 @@
 This is the checker, never the product: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 `--impl reference` legs may import it.  The CUDA path must not (and does not) route through it.
 
-Parity status: PINNED.  tests/test_oracle_vs_reference.py (container only, needs /root/reference) runs the
+Parity status: PINNED.  tests/test_oracle_vs_reference.py (container only, needs /root/reference; skipped elsewhere) runs the
 unmodified reference (oracle/ref_shim.py) side by side with this file, and tests/golden/*.npz hold
 reference-generated vectors (made by tests/golden/make_golden.py) that this file is checked against
 everywhere (including the GPU box, where the reference does not exist).

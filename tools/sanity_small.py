@@ -36,8 +36,8 @@ S.admm_project_dual(x, z, lam, torch.full((77,), -0.5, dtype=torch.float64), tor
                     want_mask=True)
 # SLS path
 import test_gpu_sls as T
-from oracle import models as M
-A, B = M.double_integrator_AB(2, 2, 0.05)
+from isls_b200 import get_double_integrator_AB
+A, B = get_double_integrator_AB(2, 2, 0.05)
 s = T._make_sls(4, 2, 20, A, B, np.array([[0.8, 0.7], [0.6, 0.9], [1.0, 1.0]]))
 PHI, du = s.solve_sls()
 from scipy.stats import norm
