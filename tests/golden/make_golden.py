@@ -287,6 +287,23 @@ def golden_tutorial(B=3, N=150):
     np.savez_compressed(os.path.join(OUT, "tutorial_tassa.npz"), x0=p["x0"], u0=p["u0"], N=N, **out)
 
 
+def golden_tutorial_fullsize(N=500):
+    """The same problem at the notebooks' own size (Tutorial cell 4 / `Car/Replicate of control-limited ddp car
+    example.ipynb` cells 5, 14-15, 19-21: T = 15 s, N = 500, x0 = (1, 1, 3pi/2, 0), max_iter=100 resp. 50 x 5 ADMM
+    iterations x 40 candidates, rho_u = diag(1e-1, 1e-2)); the notebooks draw u0 unseeded, here it is seeded."""
+    p = P.tassa_batch(1, N=N)
+    p["x0"][0] = np.array([1.0, 1.0, 1.5 * np.pi, 0.0])
+    model = M.make_model("tassa_car", dt=p["dt"])
+    out = {}
+    for tag, run in (("dp", S.run_tutorial_dp), ("admm", S.run_tutorial_admm)):
+        s = S.make_isls_tutorial(model, p)
+        S.init_nominal(s, p["x0"][0], p["u0"])
+        r = run(s, model, p)
+        print("tutorial N=%d" % N, tag, len(r["cost_log"]), r["cost_log"][0], r["cost_log"][-1])
+        out.update({"x_" + tag: r["x"][None], "u_" + tag: r["u"][None], "cost_log_" + tag: r["cost_log"][None]})
+    np.savez_compressed(os.path.join(OUT, "tutorial_tassa_n%d.npz" % N), x0=p["x0"], u0=p["u0"], N=N, **out)
+
+
 def golden_parking():
     """Parking between two cars (state projection onto obstacle sets): (a) the notebook configuration N=500, dt=0.03
     (known answer: first iterate 2564.0110889491493, Car/Iterative LQR with state constraints.ipynb cell 20 output),
@@ -474,6 +491,8 @@ if __name__ == "__main__":
         golden_mc()
     if want("tutorial"):
         golden_tutorial()
+    if want("tutorial_fullsize"):
+        golden_tutorial_fullsize()
     if want("parking"):
         golden_parking()
     if want("isls_admm"):

@@ -182,6 +182,27 @@ def test_tutorial_tassa_pseudo_huber_vs_reference_golden(golden):
     assert np.abs(o["u"] - g["u_admm"]).max() < 1e-9 and np.abs(o["x"] - g["x_admm"]).max() < 1e-9
 
 
+def _tassa_fullsize(g):
+    p = P.tassa_batch(1, N=int(g["N"]))
+    p["x0"] = g["x0"].copy()
+    assert np.array_equal(p["u0"], g["u0"])
+    return p
+
+
+def test_tutorial_fullsize_vs_reference_golden(golden):
+    """The Tutorial / 'Replicate of control-limited ddp car example' problem at the notebooks' own size (N = 500,
+    T = 15 s, x0 = (1, 1, 3pi/2, 0)): oracle vs the unmodified reference, dp (60 iterations) and ADMM (45)."""
+    g = golden("tutorial_tassa_n500")
+    p = _tassa_fullsize(g)
+    for tag, o in (("dp", R.ilqr_dp(p, max_iter=100, L=40)), ("admm", R.ilqr_admm(p))):
+        ref = g["cost_log_" + tag][0]
+        assert o["n_log"][0] == len(ref), tag
+        rel = np.max(np.abs(o["cost_log"][0, :len(ref)] - ref) / np.abs(ref))
+        du = np.abs(o["u"] - g["u_" + tag]).max()
+        print("tutorial N=500", tag, "rel cost_log", rel, "max|du|", du)
+        assert rel < 1e-8 and du < 1e-6, tag
+
+
 def test_tassa_jacobian_finite_differences():
     """The hand-derived Jacobian of the Tassa car (the notebook uses autograd) against central differences."""
     from oracle import models as M
