@@ -2825,21 +2825,43 @@ template <class M>
 static int launch_ff(const Dev &d, cudaStream_t s) {
   static int mode = -2;
   if (mode == -2) {
-    const char *e = getenv("ISLS_FF_STAGES");         // -1 auto (default), 0 plain, 2/4 forced pipeline depth
+    const char *e = getenv("ISLS_FF_STAGES");         // -1 auto (default), 0 plain, 2/3/4 forced pipeline depth
     mode = e ? atoi(e) : -1;
   }
   constexpr int n = M::n, m = M::m, nt = NTRI(M::m);
   constexpr int SB = n + m + m * n + 2 * nt + m + n, SF = m * n + 3 * m + n, SL = SB > SF ? SB : SF;
   const int tiles = d.tile1 - d.tile0;
   int stages = mode;
-  // small batches are latency-bound: stage 4 steps ahead when 3-4 single-warp CTAs with that stage fit an SM
-  // (car 17 KB, arm 64.5 KB per CTA; C3 arm B=16,384: ff 80 -> 66 ms per solve)
-  if (stages < 0) stages = (tiles < 1536 && (size_t)4 * SL * TILE * sizeof(double) <= 66 * 1024) ? 4 : 0;
+  // small batches are latency-bound: stage up to 4 steps ahead through shared memory (car 17 KB, arm 64.5 KB per
+  // single-warp CTA at depth 4).  The depth is the deepest one at which ALL tiles are resident at once: with the arm's
+  // 64.5 KB stage only 3 CTAs fit an SM (444 slots), so C3's 512 tiles ran as two waves (the second 15 % full, the
+  // kernel twice one CTA's latency); depth 3 (48 KB, 4 CTAs per SM, 592 slots) runs them as one.
+  if (stages < 0) {
+    stages = 0;
+    if (tiles < 1536) {
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const size_t per_sm = 227 * 1024, per_stage = (size_t)SL * TILE * sizeof(double);
+      for (int st = 4; st >= 2 && !stages; st--) {
+        const size_t cta = st * per_stage + 1024;                       // + the per-CTA reservation
+        if (st == 4 && st * per_stage > 66 * 1024) continue;
+        const long long slots = (long long)sms * (long long)std::min((size_t)32, per_sm / cta);
+        if (st == 2 || slots >= tiles) stages = st;
+      }
+      if (stages == 2 && (size_t)2 * per_stage > 66 * 1024) stages = 0;
+    }
+  }
   if (stages == 4) {
     const size_t smem = (size_t)4 * SL * TILE * sizeof(double);
     static bool set4 = false;
     if (!set4) { CK(cudaFuncSetAttribute(k_ff_staged<M, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set4 = true; }
     k_ff_staged<M, 4><<<tiles, TILE, smem, s>>>(d);
+  } else if (stages == 3) {
+    const size_t smem = (size_t)3 * SL * TILE * sizeof(double);
+    static bool set3 = false;
+    if (!set3) { CK(cudaFuncSetAttribute(k_ff_staged<M, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set3 = true; }
+    k_ff_staged<M, 3><<<tiles, TILE, smem, s>>>(d);
   } else if (stages == 2) {
     const size_t smem = (size_t)2 * SL * TILE * sizeof(double);
     static bool set2 = false;

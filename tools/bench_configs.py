@@ -53,6 +53,7 @@ def isls_case(p, fixed):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--fixed", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="C2 and C3 only")
     a = ap.parse_args()
     res = {}
     # C2: car, 4,096 problems
@@ -64,6 +65,9 @@ if __name__ == "__main__":
     res["C3 arm iLQR-ADMM B=16384"] = dict(ms=round(ms, 2), problems_per_s=round(16384 / ms * 1e3),
                                            mean_outer=float(out.outer_iters.double().mean()),
                                            mean_cost=float(out.cost.mean()), kernels_ms=prof)
+    if a.quick:
+        print(json.dumps(res))
+        sys.exit(0)
     # C1: LQT-ADMM DP double integrator, B = 1 and 1,024
     for B in (1, 1024):
         p = configs.di_batch(B)
