@@ -700,24 +700,38 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
   double A[n][n], Bm[n][m];
   init_AB<M>(A, Bm);
   double v[n];
-  auto costgrad = [&](int t, const double (&x)[n], const double (&u)[m], const double (&rx)[n],
-                      const double (&ru)[m], double (&cx)[n], double (&cu)[m]) {
-    if (d.cost_kind == ISLS_COST_QUADRATIC) {
-      const int s = d.seq[t];
+  // Plan constants of a step (rho_x, rho_u, seq, qnz) are fetched ONE STEP AHEAD into registers (ldc, read-only
+  // path): as plain loads inside the step they sat behind the previous step's stores and missed L1 (the cp.async.ca
+  // stream flushes it), a third of this kernel's stall samples at C3 (profiles/r1_c3_small_batch_kernels.md).
+  double rw2[m], rw[m];
 #pragma unroll
-      for (int i = 0; i < n; i++) cx[i] = d.qnz[t] ? 2.0 * d.qd[t * n + i] * (x[i] - EL(zs, n, s, i)) : 0.0;
+  for (int j = 0; j < m; j++) { rw[j] = d.Rw[j]; rw2[j] = 2.0 * (d.u_std * rw[j]); }
+  auto ldc = [&](int t, double (&rhx)[n], double (&rhu)[m], int &qz, int &sq) {
+    qz = __ldg(d.qnz + t);
+    sq = __ldg(d.seq + t);
+#pragma unroll
+    for (int i = 0; i < n; i++) rhx[i] = d.proj_x ? __ldg(d.rho_x + t * n + i) : 0.0;
+#pragma unroll
+    for (int j = 0; j < m; j++) rhu[j] = d.proj_u ? __ldg(d.rho_u + t * m + j) : 0.0;
+  };
+  auto costgrad = [&](int t, const double (&x)[n], const double (&u)[m], const double (&rx)[n],
+                      const double (&ru)[m], double (&cx)[n], double (&cu)[m], const double (&rhx)[n],
+                      const double (&rhu)[m], int qz, int sq) {
+    if (d.cost_kind == ISLS_COST_QUADRATIC) {
+#pragma unroll
+      for (int i = 0; i < n; i++) cx[i] = qz ? 2.0 * d.qd[t * n + i] * (x[i] - EL(zs, n, sq, i)) : 0.0;
     } else {
       double ht[n];
       state_grad_hess<M>(d, zs, t, x, cx, ht);
     }
 #pragma unroll
     for (int i = 0; i < n; i++) {
-      if (d.proj_x) cx[i] += 2.0 * d.rho_x[t * n + i] * (x[i] - rx[i]);
+      if (d.proj_x) cx[i] += 2.0 * rhx[i] * (x[i] - rx[i]);
     }
 #pragma unroll
     for (int j = 0; j < m; j++) {
-      double g = 2.0 * (d.u_std * d.Rw[j]) * u[j];
-      if (d.proj_u) g += 2.0 * d.rho_u[t * m + j] * (u[j] - ru[j]);
+      double g = rw2[j] * u[j];
+      if (d.proj_u) g += 2.0 * rhu[j] * (u[j] - ru[j]);
       cu[j] = g;
     }
   };
@@ -749,12 +763,15 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
     for (int i = 0; i < n; i++) { x[i] = EL(xh, n, N - 1, i); rx[i] = d.proj_x ? EL(rgx, n, N - 1, i) : 0.0; }
 #pragma unroll
     for (int j = 0; j < m; j++) { u[j] = EL(uh, m, N - 1, j); ru[j] = d.proj_u ? EL(rgu, m, N - 1, j) : 0.0; }
-    costgrad(N - 1, x, u, rx, ru, cx, cu);
+    double rhx[n], rhu[m];
+    int qz, sq;
+    ldc(N - 1, rhx, rhu, qz, sq);
+    costgrad(N - 1, x, u, rx, ru, cx, cu, rhx, rhu, qz, sq);
 #pragma unroll
     for (int i = 0; i < n; i++) v[i] = cx[i];
 #pragma unroll
     for (int j = 0; j < m; j++) {
-      const double cuu = 2.0 * (d.u_std * d.Rw[j] + d.rho_u[(N - 1) * m + j]);
+      const double cuu = 2.0 * (d.u_std * rw[j] + d.rho_u[(N - 1) * m + j]);
       EL(kk, m, N - 1, j) = d.last_stage_dp ? 0.0 : -cu[j] / cuu;
     }
   }
@@ -766,7 +783,13 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
     cp_async_commit();
     t_issue--;
   }
+  double rhx_c[n], rhu_c[m];
+  int qz_c = 0, sq_c = 0;
+  if (N >= 2) ldc(N - 2, rhx_c, rhu_c, qz_c, sq_c);
   for (int t = N - 2; t >= 0; t--) {
+    double rhx_n[n], rhu_n[m];
+    int qz_n = 0, sq_n = 0;
+    if (t > 0) ldc(t - 1, rhx_n, rhu_n, qz_n, sq_n);
     if (t_issue >= 0) issue_b(t_issue, (N - 2 - t_issue) % STAGES);
     cp_async_commit();
     t_issue--;
@@ -799,10 +822,18 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
     for (int i = 0; i < n; i++) rx[i] = d.proj_x ? *slot(st, k + i) : 0.0;
     M::jac(x, u, J, d.dt);
     M::expand(J, A, Bm, d.dt);
-    costgrad(t, x, u, rx, ru, cx, cu);
+    costgrad(t, x, u, rx, ru, cx, cu, rhx_c, rhu_c, qz_c, sq_c);
     ff_step<M>(A, Bm, cx, cu, Qux, Quu, Qui, v, kt);
 #pragma unroll
     for (int j = 0; j < m; j++) EL(kk, m, t, j) = kt[j];
+    if (t > 0) {
+#pragma unroll
+      for (int i = 0; i < n; i++) rhx_c[i] = rhx_n[i];
+#pragma unroll
+      for (int j = 0; j < m; j++) rhu_c[j] = rhu_n[j];
+      qz_c = qz_n;
+      sq_c = sq_n;
+    }
   }
   cp_async_wait<0>();
   // ---- forward sweep (linear rollout + control-cost polynomials), STAGES deep
@@ -833,7 +864,13 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
     cp_async_commit();
     t_issue++;
   }
+  double rho_c[m];
+#pragma unroll
+  for (int j = 0; j < m; j++) rho_c[j] = d.proj_u ? __ldg(d.rho_u + j) : 0.0;
   for (int t = 0; t < N; t++) {
+    double rho_n[m];
+#pragma unroll
+    for (int j = 0; j < m; j++) rho_n[j] = (d.proj_u && t + 1 < N) ? __ldg(d.rho_u + (t + 1) * m + j) : 0.0;
     if (t_issue < N) issue_f(t_issue, t_issue % STAGES);
     cp_async_commit();
     t_issue++;
@@ -863,11 +900,11 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
       }
       duv[a] = acc + kv[a];
       EL(du, m, t, a) = duv[a];
-      r0 = fma(d.Rw[a] * u[a], u[a], r0);
-      r1 = fma(d.Rw[a] * u[a], duv[a], r1);
-      r2 = fma(d.Rw[a] * duv[a], duv[a], r2);
+      r0 = fma(rw[a] * u[a], u[a], r0);
+      r1 = fma(rw[a] * u[a], duv[a], r1);
+      r2 = fma(rw[a] * duv[a], duv[a], r2);
       if (d.proj_u) {
-        const double rho = d.rho_u[t * m + a], e = u[a] - ru[a];
+        const double rho = rho_c[a], e = u[a] - ru[a];
         c0 = fma(rho * e, e, c0);
         c1 = fma(2.0 * rho * e, duv[a], c1);
         c2 = fma(rho * duv[a], duv[a], c2);
@@ -881,6 +918,8 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
 #pragma unroll
       for (int i = 0; i < n; i++) dx[i] = dxn[i];
     }
+#pragma unroll
+    for (int j = 0; j < m; j++) rho_c[j] = rho_n[j];
   }
   cp_async_wait<0>();
   const size_t S = (size_t)d.T * TILE;
@@ -1229,11 +1268,96 @@ __device__ __forceinline__ void obst_project_one(const Dev &d, int k, double (&y
 // Winner rollout + ADMM update: re-roll the chosen candidate (the primal iterate (x,u) returned by f_argmin,
 // isls/isls.py:478; it is not stored - k_outer_end re-rolls the last one in place), apply the z-projection and scaled dual update element by element (admm.py:43-59), form the
 // residual norms (admm.py:62-69) and run the stop tests (admm.py:72-85).
+// Operand fetch policies of admm_body.  AdmmFetchGlobal: plain global loads, all of a step issued together (one memory
+// round trip per step).  AdmmFetchStaged (k_admm_staged, small batches): each thread streams its own operands of the
+// next STAGES-1 steps into a private slice of shared memory with cp.async, like k_ff_staged.
 template <class M>
-__device__ __forceinline__ void admm_body(const Dev &d, const TileCtx<M> &c, int outer, int inner) {
+struct AdmmFetchGlobal {
+  static constexpr int n = M::n, m = M::m;
+  const Dev &d;
+  const double *uh, *du, *zx, *lx, *zu, *lu;
+  __device__ __forceinline__ AdmmFetchGlobal(const Dev &d_, const TileCtx<M> &c)
+      : d(d_), uh(c.at(d_.uh, d_, m)), du(c.at(d_.du, d_, m)), zx(c.at(d_.zx, d_, n)), lx(c.at(d_.lx, d_, n)),
+        zu(c.at(d_.zu, d_, m)), lu(c.at(d_.lu, d_, m)) {}
+  __device__ __forceinline__ void operator()(int t, double (&duv)[m], double (&uhv)[m], double (&zuv)[m],
+                                             double (&luv)[m], double (&zxv)[n], double (&lxv)[n]) {
+#pragma unroll
+    for (int j = 0; j < m; j++) {
+      duv[j] = EL(du, m, t, j);
+      uhv[j] = EL(uh, m, t, j);
+      if (d.proj_u) { zuv[j] = EL(zu, m, t, j); luv[j] = EL(lu, m, t, j); }
+    }
+    if (d.proj_x) {
+#pragma unroll
+      for (int i = 0; i < n; i++) { zxv[i] = EL(zx, n, t, i); lxv[i] = EL(lx, n, t, i); }
+    }
+  }
+};
+
+template <class M, int STAGES>
+struct AdmmFetchStaged {
+  static constexpr int n = M::n, m = M::m, SL = 4 * m + 2 * n;   // du, u^, z_u, lambda_u, z_x, lambda_x
+  const Dev &d;
+  const double *uh, *du, *zx, *lx, *zu, *lu;
+  double *sm;
+  int t_issue;
+  __device__ __forceinline__ double *slot(int stage, int k) const { return sm + ((size_t)stage * SL + k) * TILE; }
+  __device__ __forceinline__ void issue(int t) {
+    const int st = t % STAGES;
+    int k = 0;
+#pragma unroll
+    for (int j = 0; j < m; j++) cp_async8(slot(st, k++), &EL(du, m, t, j));
+#pragma unroll
+    for (int j = 0; j < m; j++) cp_async8(slot(st, k++), &EL(uh, m, t, j));
+    if (d.proj_u) {
+#pragma unroll
+      for (int j = 0; j < m; j++) { cp_async8(slot(st, k + j), &EL(zu, m, t, j)); cp_async8(slot(st, k + m + j), &EL(lu, m, t, j)); }
+    }
+    k += 2 * m;
+    if (d.proj_x) {
+#pragma unroll
+      for (int i = 0; i < n; i++) { cp_async8(slot(st, k + i), &EL(zx, n, t, i)); cp_async8(slot(st, k + n + i), &EL(lx, n, t, i)); }
+    }
+  }
+  __device__ __forceinline__ AdmmFetchStaged(const Dev &d_, const TileCtx<M> &c, double *smem)
+      : d(d_), uh(c.at(d_.uh, d_, m)), du(c.at(d_.du, d_, m)), zx(c.at(d_.zx, d_, n)), lx(c.at(d_.lx, d_, n)),
+        zu(c.at(d_.zu, d_, m)), lu(c.at(d_.lu, d_, m)), sm(smem + c.lane), t_issue(0) {
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+      if (t_issue < d.N) issue(t_issue);
+      cp_async_commit();
+      t_issue++;
+    }
+  }
+  __device__ __forceinline__ void operator()(int t, double (&duv)[m], double (&uhv)[m], double (&zuv)[m],
+                                             double (&luv)[m], double (&zxv)[n], double (&lxv)[n]) {
+    if (t_issue < d.N) issue(t_issue);
+    cp_async_commit();
+    t_issue++;
+    cp_async_wait<STAGES - 1>();
+    const int st = t % STAGES;
+    int k = 0;
+#pragma unroll
+    for (int j = 0; j < m; j++) duv[j] = *slot(st, k++);
+#pragma unroll
+    for (int j = 0; j < m; j++) uhv[j] = *slot(st, k++);
+    if (d.proj_u) {
+#pragma unroll
+      for (int j = 0; j < m; j++) { zuv[j] = *slot(st, k + j); luv[j] = *slot(st, k + m + j); }
+    }
+    k += 2 * m;
+    if (d.proj_x) {
+#pragma unroll
+      for (int i = 0; i < n; i++) { zxv[i] = *slot(st, k + i); lxv[i] = *slot(st, k + n + i); }
+    }
+  }
+};
+
+template <class M, class Fetch>
+__device__ __forceinline__ void admm_body(const Dev &d, const TileCtx<M> &c, int outer, int inner, Fetch &fetch) {
   constexpr int n = M::n, m = M::m;
   const int tile = c.tile;
-  const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m), *du = c.at(d.du, d, m);
+  const double *xh = c.at(d.xh, d, n);
   double *zx = c.at(d.zx, d, n), *lx = c.at(d.lx, d, n), *rgx = c.at(d.rgx, d, n);
   double *zu = c.at(d.zu, d, m), *lu = c.at(d.lu, d, m), *rgu = c.at(d.rgu, d, m);
   const double *zs = d.zs + (size_t)tile * d.n_via * n * TILE + c.lane;
@@ -1248,16 +1372,21 @@ __device__ __forceinline__ void admm_body(const Dev &d, const TileCtx<M> &c, int
   for (int t = 0; t < d.N; t++) {
     // all loads of the step are issued before the first store (the stores may alias as far as the compiler knows,
     // which would otherwise serialise one memory round trip per element)
-    double zuv[m], luv[m], lou[m], hiu[m], zxv[n], lxv[n], lox[n], hix[n];
+    // (control-side AND state-side: with the control u formed between them the state-side loads were only issued
+    // after the control-side ones had arrived - two serialised round trips per step, 54 % of k_admm<Arm3Model> in the
+    // ncu source view, profiles/r1_c3_small_batch_kernels.md)
+    double duv[m], uhv[m], zuv[m], luv[m], lou[m], hiu[m], zxv[n], lxv[n], lox[n], hix[n];
+    if (d.proj_u) {
 #pragma unroll
-    for (int j = 0; j < m; j++) {
-      u[j] = fma(al, EL(du, m, t, j), EL(uh, m, t, j));
-      if (d.proj_u) { zuv[j] = EL(zu, m, t, j); luv[j] = EL(lu, m, t, j); lou[j] = d.lo_u[t * m + j]; hiu[j] = d.hi_u[t * m + j]; }
+      for (int j = 0; j < m; j++) { lou[j] = __ldg(d.lo_u + t * m + j); hiu[j] = __ldg(d.hi_u + t * m + j); }
     }
     if (d.proj_x) {
 #pragma unroll
-      for (int i = 0; i < n; i++) { zxv[i] = EL(zx, n, t, i); lxv[i] = EL(lx, n, t, i); lox[i] = d.lo_x[t * n + i]; hix[i] = d.hi_x[t * n + i]; }
+      for (int i = 0; i < n; i++) { lox[i] = __ldg(d.lo_x + t * n + i); hix[i] = __ldg(d.hi_x + t * n + i); }
     }
+    fetch(t, duv, uhv, zuv, luv, zxv, lxv);
+#pragma unroll
+    for (int j = 0; j < m; j++) u[j] = fma(al, duv[j], uhv[j]);
     cc += ctrl_sq<M>(d, u);
 #pragma unroll
     for (int j = 0; j < m; j++) {
@@ -1344,7 +1473,39 @@ __global__ void k_admm(Dev d, int outer, int inner) {
   if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b] || d.adone[c.b]) return;
-  admm_body<M>(d, c, outer, inner);
+  AdmmFetchGlobal<M> fetch(d, c);
+  admm_body<M>(d, c, outer, inner, fetch);
+}
+
+// small batches (latency-bound, < 1,536 tiles): one tile per CTA, per-step operands cp.async-staged STAGES deep
+template <class M, int STAGES>
+__global__ void __launch_bounds__(TILE) k_admm_staged(Dev d, int outer, int inner) {
+  extern __shared__ double smem_admm[];
+  const int tile = d.tile0 + blockIdx.x;
+  if (tile >= d.tile1) return;
+  TileCtx<M> c(d, tile, threadIdx.x);
+  if (d.odone[c.b] || d.adone[c.b]) return;
+  AdmmFetchStaged<M, STAGES> fetch(d, c, smem_admm);
+  admm_body<M>(d, c, outer, inner, fetch);
+}
+
+template <class M>
+static int launch_admm(const Dev &d, int outer, int inner, cudaStream_t s) {
+  static int mode = -2;
+  if (mode == -2) {
+    const char *e = getenv("ISLS_ADMM_STAGES");       // -1 auto (default), 0 plain, 4 forced
+    mode = e ? atoi(e) : -1;
+  }
+  const int tiles = d.tile1 - d.tile0;
+  constexpr int ST = 4;
+  const size_t smem = (size_t)ST * AdmmFetchStaged<M, ST>::SL * TILE * sizeof(double);
+  const bool staged = mode == ST || (mode < 0 && tiles < 1536 && smem <= 48 * 1024);
+  if (staged) {
+    k_admm_staged<M, ST><<<tiles, TILE, smem, s>>>(d, outer, inner);
+  } else {
+    k_admm<M><<<dim3((tiles + 1) / 2), dim3(TILE, 2), 0, s>>>(d, outer, inner);
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------ robust iSLS-ADMM (isls.py:503-712)
@@ -2950,7 +3111,7 @@ extern "C" int isls_ilqr_admm_solve_f64(const isls_plan *plan, const isls_solve_
           LAUNCH(ISLS_KC_LINESEARCH, cs, launch_linesearch<M>(dc, false, cs, LsFuse{fuse, j, a}));
           if (!fuse) {
             ProfScope ps__(ISLS_KC_ADMM, cs);
-            k_admm<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, j, a);
+            launch_admm<M>(dc, j, a, cs);
             if (d.n_obst > 0)        // obstacle sets: all rows of a problem are projected together, CTA = problem
               k_obst_project<M><<<(unsigned)((dc.tile1 - dc.tile0) * TILE), ((d.N + 31) / 32) * 32, 0, cs>>>(dc, j, a);
           }
