@@ -701,8 +701,9 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
   init_AB<M>(A, Bm);
   double v[n];
   // Plan constants of a step (rho_x, rho_u, seq, qnz) are fetched ONE STEP AHEAD into registers (ldc, read-only
-  // path): as plain loads inside the step they sat behind the previous step's stores and missed L1 (the cp.async.ca
-  // stream flushes it), a third of this kernel's stall samples at C3 (profiles/r1_c3_small_batch_kernels.md).
+  // path; re-loaded in place right after their last use in costgrad, so there is no second register set): as plain
+  // loads inside the step they sat behind the previous step's stores and missed L1 (the cp.async.ca stream flushes
+  // it), a third of this kernel's stall samples at C3 (profiles/r1_c3_small_batch_kernels.md).
   double rw2[m], rw[m];
 #pragma unroll
   for (int j = 0; j < m; j++) { rw[j] = d.Rw[j]; rw2[j] = 2.0 * (d.u_std * rw[j]); }
@@ -787,9 +788,6 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
   int qz_c = 0, sq_c = 0;
   if (N >= 2) ldc(N - 2, rhx_c, rhu_c, qz_c, sq_c);
   for (int t = N - 2; t >= 0; t--) {
-    double rhx_n[n], rhu_n[m];
-    int qz_n = 0, sq_n = 0;
-    if (t > 0) ldc(t - 1, rhx_n, rhu_n, qz_n, sq_n);
     if (t_issue >= 0) issue_b(t_issue, (N - 2 - t_issue) % STAGES);
     cp_async_commit();
     t_issue--;
@@ -823,35 +821,33 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
     M::jac(x, u, J, d.dt);
     M::expand(J, A, Bm, d.dt);
     costgrad(t, x, u, rx, ru, cx, cu, rhx_c, rhu_c, qz_c, sq_c);
+    if (t > 0) ldc(t - 1, rhx_c, rhu_c, qz_c, sq_c);
     ff_step<M>(A, Bm, cx, cu, Qux, Quu, Qui, v, kt);
 #pragma unroll
     for (int j = 0; j < m; j++) EL(kk, m, t, j) = kt[j];
-    if (t > 0) {
-#pragma unroll
-      for (int i = 0; i < n; i++) rhx_c[i] = rhx_n[i];
-#pragma unroll
-      for (int j = 0; j < m; j++) rhu_c[j] = rhu_n[j];
-      qz_c = qz_n;
-      sq_c = sq_n;
-    }
   }
   cp_async_wait<0>();
   // ---- forward sweep (linear rollout + control-cost polynomials), STAGES deep
+  // (the forward step needs fewer slots and is shorter than the backward one: the same shared memory holds SFW >=
+  // STAGES forward stages - with only STAGES the operands were not there yet when the step started, 10 % of the
+  // kernel's stall samples on the cp.async wait)
+  constexpr int SFW = (STAGES * SL) / SF < 8 ? (STAGES * SL) / SF : 8;
+  auto slotf = [&](int stage, int k) -> double * { return smem_ff + ((size_t)stage * SF + k) * TILE + tid; };
   auto issue_f = [&](int t, int stage) {
     int k = 0;
 #pragma unroll
-    for (int q = 0; q < m * n; q++) cp_async8(slot(stage, k++), &EL(Kg, m * n, t, q));
+    for (int q = 0; q < m * n; q++) cp_async8(slotf(stage, k++), &EL(Kg, m * n, t, q));
 #pragma unroll
-    for (int j = 0; j < m; j++) cp_async8(slot(stage, k++), &EL(kk, m, t, j));
+    for (int j = 0; j < m; j++) cp_async8(slotf(stage, k++), &EL(kk, m, t, j));
 #pragma unroll
-    for (int j = 0; j < m; j++) cp_async8(slot(stage, k++), &EL(uh, m, t, j));
+    for (int j = 0; j < m; j++) cp_async8(slotf(stage, k++), &EL(uh, m, t, j));
     if (d.proj_u) {
 #pragma unroll
-      for (int j = 0; j < m; j++) cp_async8(slot(stage, k + j), &EL(rgu, m, t, j));
+      for (int j = 0; j < m; j++) cp_async8(slotf(stage, k + j), &EL(rgu, m, t, j));
     }
     k += m;
 #pragma unroll
-    for (int i = 0; i < n; i++) cp_async8(slot(stage, k++), &EL(xh, n, t, i));
+    for (int i = 0; i < n; i++) cp_async8(slotf(stage, k++), &EL(xh, n, t, i));
   };
   double dx[n];
 #pragma unroll
@@ -859,8 +855,8 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
   double c0 = 0.0, c1 = 0.0, c2 = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0;
   t_issue = 0;
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; s++) {
-    if (t_issue < N) issue_f(t_issue, t_issue % STAGES);
+  for (int s = 0; s < SFW - 1; s++) {
+    if (t_issue < N) issue_f(t_issue, t_issue % SFW);
     cp_async_commit();
     t_issue++;
   }
@@ -868,29 +864,26 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
 #pragma unroll
   for (int j = 0; j < m; j++) rho_c[j] = d.proj_u ? __ldg(d.rho_u + j) : 0.0;
   for (int t = 0; t < N; t++) {
-    double rho_n[m];
-#pragma unroll
-    for (int j = 0; j < m; j++) rho_n[j] = (d.proj_u && t + 1 < N) ? __ldg(d.rho_u + (t + 1) * m + j) : 0.0;
-    if (t_issue < N) issue_f(t_issue, t_issue % STAGES);
+    if (t_issue < N) issue_f(t_issue, t_issue % SFW);
     cp_async_commit();
     t_issue++;
-    cp_async_wait<STAGES - 1>();
-    const int st = t % STAGES;
+    cp_async_wait<SFW - 1>();
+    const int st = t % SFW;
     double duv[m], u[m], K[m][n], kv[m], ru[m], x[n];
     int k = 0;
 #pragma unroll
     for (int a = 0; a < m; a++)
 #pragma unroll
-      for (int j = 0; j < n; j++) K[a][j] = *slot(st, k++);
+      for (int j = 0; j < n; j++) K[a][j] = *slotf(st, k++);
 #pragma unroll
-    for (int j = 0; j < m; j++) kv[j] = *slot(st, k++);
+    for (int j = 0; j < m; j++) kv[j] = *slotf(st, k++);
 #pragma unroll
-    for (int j = 0; j < m; j++) u[j] = *slot(st, k++);
+    for (int j = 0; j < m; j++) u[j] = *slotf(st, k++);
 #pragma unroll
-    for (int j = 0; j < m; j++) ru[j] = d.proj_u ? *slot(st, k + j) : 0.0;
+    for (int j = 0; j < m; j++) ru[j] = d.proj_u ? *slotf(st, k + j) : 0.0;
     k += m;
 #pragma unroll
-    for (int i = 0; i < n; i++) x[i] = *slot(st, k++);
+    for (int i = 0; i < n; i++) x[i] = *slotf(st, k++);
 #pragma unroll
     for (int a = 0; a < m; a++) {
       double acc = 0.0;
@@ -910,6 +903,8 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
         c2 = fma(rho * duv[a], duv[a], c2);
       }
     }
+#pragma unroll
+    for (int j = 0; j < m; j++) rho_c[j] = (d.proj_u && t + 1 < N) ? __ldg(d.rho_u + (t + 1) * m + j) : 0.0;
     if (t < N - 1) {
       double J[M::NJA], dxn[n];
       M::jac(x, u, J, d.dt);
@@ -918,8 +913,6 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
 #pragma unroll
       for (int i = 0; i < n; i++) dx[i] = dxn[i];
     }
-#pragma unroll
-    for (int j = 0; j < m; j++) rho_c[j] = rho_n[j];
   }
   cp_async_wait<0>();
   const size_t S = (size_t)d.T * TILE;
@@ -1369,21 +1362,26 @@ __device__ __forceinline__ void admm_body(const Dev &d, const TileCtx<M> &c, int
   double cs = 0.0, cc = 0.0, prx = 0.0, pru = 0.0, drx = 0.0, dru = 0.0;
   int8_t *mkx = (d.out.mask_x && c.valid) ? d.out.mask_x + c.ob * d.N * n : nullptr;
   int8_t *mku = (d.out.mask_u && c.valid) ? d.out.mask_u + c.ob * d.N * m : nullptr;
+  // bounds of a step: read-only plan constants, fetched one step ahead (re-loaded in place after their last use)
+  double lou[m], hiu[m], lox[n], hix[n];
+  auto ld_bounds = [&](int t) {
+    if (d.proj_u) {
+#pragma unroll
+      for (int j = 0; j < m; j++) { lou[j] = __ldg(d.lo_u + t * m + j); hiu[j] = __ldg(d.hi_u + t * m + j); }
+    }
+    if (d.proj_x && d.n_obst == 0) {
+#pragma unroll
+      for (int i = 0; i < n; i++) { lox[i] = __ldg(d.lo_x + t * n + i); hix[i] = __ldg(d.hi_x + t * n + i); }
+    }
+  };
+  ld_bounds(0);
   for (int t = 0; t < d.N; t++) {
     // all loads of the step are issued before the first store (the stores may alias as far as the compiler knows,
     // which would otherwise serialise one memory round trip per element)
     // (control-side AND state-side: with the control u formed between them the state-side loads were only issued
     // after the control-side ones had arrived - two serialised round trips per step, 54 % of k_admm<Arm3Model> in the
     // ncu source view, profiles/r1_c3_small_batch_kernels.md)
-    double duv[m], uhv[m], zuv[m], luv[m], lou[m], hiu[m], zxv[n], lxv[n], lox[n], hix[n];
-    if (d.proj_u) {
-#pragma unroll
-      for (int j = 0; j < m; j++) { lou[j] = __ldg(d.lo_u + t * m + j); hiu[j] = __ldg(d.hi_u + t * m + j); }
-    }
-    if (d.proj_x) {
-#pragma unroll
-      for (int i = 0; i < n; i++) { lox[i] = __ldg(d.lo_x + t * n + i); hix[i] = __ldg(d.hi_x + t * n + i); }
-    }
+    double duv[m], uhv[m], zuv[m], luv[m], zxv[n], lxv[n];
     fetch(t, duv, uhv, zuv, luv, zxv, lxv);
 #pragma unroll
     for (int j = 0; j < m; j++) u[j] = fma(al, duv[j], uhv[j]);
@@ -1419,6 +1417,7 @@ __device__ __forceinline__ void admm_body(const Dev &d, const TileCtx<M> &c, int
         if (mkx) mkx[t * n + i] = (int8_t)mk;
       }
     }
+    if (t + 1 < d.N) ld_bounds(t + 1);
     cs += state_cost<M>(d, zs, t, x);
     M::step(x, u, xn, d.dt);
 #pragma unroll

@@ -90,10 +90,25 @@ __device__ __forceinline__ void sincos_core(double x, double *sp, double *cp, bo
   *cp = ((k + 1) & 2) ? -ca : ca;
 }
 
+// The slow path returns by value: handing the caller's s / c to a non-inlined function by address gave them a home in
+// local memory (STL in the fast path, LDL after the reconvergence point - an L1-missing round trip per model
+// evaluation in the cp.async-staged kernels, whose streams flush L1; profiles/r1_c3_small_batch_kernels.md).
+static __device__ __noinline__ double2 sincos_slow2(double x) {
+  double s, c;
+  sincos(x, &s, &c);
+  return make_double2(s, c);
+}
 __device__ __forceinline__ void sincos_pio2(double x, double *sp, double *cp) {
   bool bad = false;
-  sincos_core(x, sp, cp, bad);
-  if (bad) sincos_slow(x, sp, cp);
+  double s, c;
+  sincos_core(x, &s, &c, bad);
+  if (bad) {
+    const double2 r = sincos_slow2(x);
+    s = r.x;
+    c = r.y;
+  }
+  *sp = s;
+  *cp = c;
 }
 
 // ---- K independent evaluations written STAGE BY STAGE (loop over the K arguments inside every polynomial stage).
