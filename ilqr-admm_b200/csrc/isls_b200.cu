@@ -135,9 +135,10 @@ __device__ __forceinline__ void retire(const Dev &d, const TileCtx<M> &c, bool f
 // with two (w, p) terms per component (running cost lx and final cost lf both act on x, y at the last step).
 __device__ __forceinline__ double huber_val(double e, double w, double p) { return w * (sqrt(fma(e, e, p * p)) - p); }
 template <class M>
-__device__ __forceinline__ double state_cost(const Dev &d, const double *zs, int t, const double (&x)[M::n]) {
+__device__ __forceinline__ double state_cost(const Dev &d, const double *zs, int t, const double (&x)[M::n],
+                                             int qnz_t = -1) {     // qnz_t >= 0: d.qnz[t] already fetched by the caller
   double c = 0.0;
-  if (d.qnz[t]) {
+  if (qnz_t >= 0 ? qnz_t : d.qnz[t]) {
     const int s = d.seq[t];
     if (d.cost_kind == ISLS_COST_QUADRATIC) {
 #pragma unroll
@@ -1364,7 +1365,9 @@ __device__ __forceinline__ void admm_body(const Dev &d, const TileCtx<M> &c, int
   int8_t *mku = (d.out.mask_u && c.valid) ? d.out.mask_u + c.ob * d.N * m : nullptr;
   // bounds of a step: read-only plan constants, fetched one step ahead (re-loaded in place after their last use)
   double lou[m], hiu[m], lox[n], hix[n];
+  int qnz_t = 0;
   auto ld_bounds = [&](int t) {
+    qnz_t = __ldg(d.qnz + t);
     if (d.proj_u) {
 #pragma unroll
       for (int j = 0; j < m; j++) { lou[j] = __ldg(d.lo_u + t * m + j); hiu[j] = __ldg(d.hi_u + t * m + j); }
@@ -1417,8 +1420,8 @@ __device__ __forceinline__ void admm_body(const Dev &d, const TileCtx<M> &c, int
         if (mkx) mkx[t * n + i] = (int8_t)mk;
       }
     }
+    cs += state_cost<M>(d, zs, t, x, qnz_t);
     if (t + 1 < d.N) ld_bounds(t + 1);
-    cs += state_cost<M>(d, zs, t, x);
     M::step(x, u, xn, d.dt);
 #pragma unroll
     for (int i = 0; i < n; i++) x[i] = xn[i];
@@ -1492,11 +1495,11 @@ template <class M>
 static int launch_admm(const Dev &d, int outer, int inner, cudaStream_t s) {
   static int mode = -2;
   if (mode == -2) {
-    const char *e = getenv("ISLS_ADMM_STAGES");       // -1 auto (default), 0 plain, 4 forced
+    const char *e = getenv("ISLS_ADMM_STAGES");       // -1 auto (default), 0 plain, 6 forced
     mode = e ? atoi(e) : -1;
   }
   const int tiles = d.tile1 - d.tile0;
-  constexpr int ST = 4;
+  constexpr int ST = 6;     // the step is short: at 4 stages 7 % of the samples still sat on the cp.async wait
   const size_t smem = (size_t)ST * AdmmFetchStaged<M, ST>::SL * TILE * sizeof(double);
   const bool staged = mode == ST || (mode < 0 && tiles < 1536 && smem <= 48 * 1024);
   if (staged) {
