@@ -1556,7 +1556,7 @@ __global__ void k_isls_cols(Dev d) {
   auto cu_of = [&](int t, double (&cu)[m]) {
 #pragma unroll
     for (int j = 0; j < m; j++)
-      cu[j] = -2.0 * d.rho_u[t * m + j] * (EL(Zm, m * C, t, j * C + col) - EL(Lm, m * C, t, j * C + col));
+      cu[j] = -2.0 * __ldg(d.rho_u + t * m + j) * (EL(Zm, m * C, t, j * C + col) - EL(Lm, m * C, t, j * C + col));
   };
   {
     double cu[m];
@@ -1581,9 +1581,9 @@ __global__ void k_isls_cols(Dev d) {
         Quu[a][b2] = EL(Qu, nt, t, tri(a, b2)); Quu[b2][a] = Quu[a][b2];
       }
     }
+    cu_of(t, cu);                  // its loads go out with the step's other loads, not after the Jacobian has waited
     M::jac(x, u, J, d.dt);
     M::expand(J, A, Bm, d.dt);
-    cu_of(t, cu);
     ff_step<M>(A, Bm, cx, cu, Qux, Quu, Qui, v, kt);
 #pragma unroll
     for (int j = 0; j < m; j++) EL(Xu, m * C, t, j * C + col) = kt[j];
@@ -1620,6 +1620,182 @@ __global__ void k_isls_cols(Dev d) {
 #pragma unroll
       for (int i = 0; i < n; i++) dx[i] = dxn[i];
     }
+  }
+}
+
+// cp.async-staged form of k_isls_cols for small batches (one warp per CTA, each thread streams its own operands of the
+// next STAGES-1 steps into a private slice of shared memory, as in k_ff_staged); identical arithmetic.
+template <class M, int STAGES>
+__global__ void __launch_bounds__(TILE) k_isls_cols_staged(Dev d) {
+  constexpr int n = M::n, m = M::m, nt = NTRI(M::m);
+  constexpr int SB = n + m + m * n + 2 * nt + 2 * m;     // backward slots: x^, u^, Qux, Quu, Quu^-1, Z_c, Lambda_c
+  constexpr int SF = m * n + 2 * m + n;                  // forward slots:  K, k_c, u^, x^
+  constexpr int SFW = (STAGES * SB) / SF < 8 ? (STAGES * SB) / SF : 8;
+  extern __shared__ double smem_cols[];
+  const int tile = d.tile0 + blockIdx.x;
+  if (tile >= d.tile1) return;
+  TileCtx<M> c(d, tile, threadIdx.x);
+  if (d.odone[c.b] || d.adone[c.b]) return;
+  const int tid = threadIdx.x;
+  const int C = d.isls_C, col = blockIdx.y + 1, N = d.N;
+  const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m);
+  const double *Kg = c.at(d.Kg, d, m * n), *Qx = c.at(d.Qux, d, m * n);
+  const double *Qu = c.at(d.Quu, d, nt), *Qi = c.at(d.Qui, d, nt);
+  const double *Zm = c.at(d.Zm, d, m * C), *Lm = c.at(d.Lm, d, m * C);
+  double *Xu = c.at(d.Xu, d, m * C);
+  auto slot = [&](int stage, int k) -> double * { return smem_cols + ((size_t)stage * SB + k) * TILE + tid; };
+  auto slotf = [&](int stage, int k) -> double * { return smem_cols + ((size_t)stage * SF + k) * TILE + tid; };
+  double A[n][n], Bm[n][m], v[n], cx[n];
+  init_AB<M>(A, Bm);
+#pragma unroll
+  for (int i = 0; i < n; i++) { v[i] = 0.0; cx[i] = 0.0; }
+  {
+#pragma unroll
+    for (int j = 0; j < m; j++) {
+      const double rho = d.rho_u[(N - 1) * m + j];
+      const double cu = -2.0 * rho * (EL(Zm, m * C, N - 1, j * C + col) - EL(Lm, m * C, N - 1, j * C + col));
+      EL(Xu, m * C, N - 1, j * C + col) = -cu / (2.0 * (d.u_std * d.Rw[j] + rho));
+    }
+  }
+  auto issue_b = [&](int t, int stage) {
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < n; i++) cp_async8(slot(stage, k++), &EL(xh, n, t, i));
+#pragma unroll
+    for (int j = 0; j < m; j++) cp_async8(slot(stage, k++), &EL(uh, m, t, j));
+#pragma unroll
+    for (int q = 0; q < m * n; q++) cp_async8(slot(stage, k++), &EL(Qx, m * n, t, q));
+#pragma unroll
+    for (int q = 0; q < nt; q++) cp_async8(slot(stage, k++), &EL(Qu, nt, t, q));
+#pragma unroll
+    for (int q = 0; q < nt; q++) cp_async8(slot(stage, k++), &EL(Qi, nt, t, q));
+#pragma unroll
+    for (int j = 0; j < m; j++) cp_async8(slot(stage, k++), &EL(Zm, m * C, t, j * C + col));
+#pragma unroll
+    for (int j = 0; j < m; j++) cp_async8(slot(stage, k++), &EL(Lm, m * C, t, j * C + col));
+  };
+  int t_issue = N - 2;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (t_issue >= 0) issue_b(t_issue, (N - 2 - t_issue) % STAGES);
+    cp_async_commit();
+    t_issue--;
+  }
+  double rho_c[m];
+#pragma unroll
+  for (int j = 0; j < m; j++) rho_c[j] = N >= 2 ? __ldg(d.rho_u + (N - 2) * m + j) : 0.0;
+  for (int t = N - 2; t >= 0; t--) {
+    if (t_issue >= 0) issue_b(t_issue, (N - 2 - t_issue) % STAGES);
+    cp_async_commit();
+    t_issue--;
+    cp_async_wait<STAGES - 1>();
+    const int st = (N - 2 - t) % STAGES;
+    double x[n], u[m], J[M::NJA], cu[m], Qux[m][n], Quu[m][m], Qui[m][m], kt[m];
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < n; i++) x[i] = *slot(st, k++);
+#pragma unroll
+    for (int j = 0; j < m; j++) u[j] = *slot(st, k++);
+#pragma unroll
+    for (int a = 0; a < m; a++)
+#pragma unroll
+      for (int j = 0; j < n; j++) Qux[a][j] = *slot(st, k++);
+#pragma unroll
+    for (int a = 0; a < m; a++)
+#pragma unroll
+      for (int b2 = 0; b2 <= a; b2++) { Quu[a][b2] = *slot(st, k + tri(a, b2)); Quu[b2][a] = Quu[a][b2]; }
+    k += nt;
+#pragma unroll
+    for (int a = 0; a < m; a++)
+#pragma unroll
+      for (int b2 = 0; b2 <= a; b2++) { Qui[a][b2] = *slot(st, k + tri(a, b2)); Qui[b2][a] = Qui[a][b2]; }
+    k += nt;
+#pragma unroll
+    for (int j = 0; j < m; j++) cu[j] = -2.0 * rho_c[j] * (*slot(st, k + j) - *slot(st, k + m + j));
+#pragma unroll
+    for (int j = 0; j < m; j++) rho_c[j] = t > 0 ? __ldg(d.rho_u + (t - 1) * m + j) : 0.0;
+    M::jac(x, u, J, d.dt);
+    M::expand(J, A, Bm, d.dt);
+    ff_step<M>(A, Bm, cx, cu, Qux, Quu, Qui, v, kt);
+#pragma unroll
+    for (int j = 0; j < m; j++) EL(Xu, m * C, t, j * C + col) = kt[j];
+  }
+  cp_async_wait<0>();
+  auto issue_f = [&](int t, int stage) {
+    int k = 0;
+#pragma unroll
+    for (int q = 0; q < m * n; q++) cp_async8(slotf(stage, k++), &EL(Kg, m * n, t, q));
+#pragma unroll
+    for (int j = 0; j < m; j++) cp_async8(slotf(stage, k++), &EL(Xu, m * C, t, j * C + col));
+#pragma unroll
+    for (int j = 0; j < m; j++) cp_async8(slotf(stage, k++), &EL(uh, m, t, j));
+#pragma unroll
+    for (int i = 0; i < n; i++) cp_async8(slotf(stage, k++), &EL(xh, n, t, i));
+  };
+  double dx[n];
+#pragma unroll
+  for (int i = 0; i < n; i++) dx[i] = (i == col - 1) ? 1.0 : 0.0;
+  t_issue = 0;
+#pragma unroll
+  for (int s = 0; s < SFW - 1; s++) {
+    if (t_issue < N) issue_f(t_issue, t_issue % SFW);
+    cp_async_commit();
+    t_issue++;
+  }
+  for (int t = 0; t < N; t++) {
+    if (t_issue < N) issue_f(t_issue, t_issue % SFW);
+    cp_async_commit();
+    t_issue++;
+    cp_async_wait<SFW - 1>();
+    const int st = t % SFW;
+    double x[n], u[m], K[m][n], kv[m], duv[m];
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < m; a++)
+#pragma unroll
+      for (int j = 0; j < n; j++) K[a][j] = *slotf(st, k++);
+#pragma unroll
+    for (int j = 0; j < m; j++) kv[j] = *slotf(st, k++);
+#pragma unroll
+    for (int j = 0; j < m; j++) u[j] = *slotf(st, k++);
+#pragma unroll
+    for (int i = 0; i < n; i++) x[i] = *slotf(st, k++);
+#pragma unroll
+    for (int a = 0; a < m; a++) {
+      double acc = 0.0;
+      if (t < N - 1) {
+#pragma unroll
+        for (int j = 0; j < n; j++) acc = fma(K[a][j], dx[j], acc);
+      }
+      duv[a] = acc + kv[a];
+      EL(Xu, m * C, t, a * C + col) = duv[a];
+    }
+    if (t < N - 1) {
+      double J[M::NJA], dxn[n];
+      M::jac(x, u, J, d.dt);
+      M::expand(J, A, Bm, d.dt);
+      mat_Ax_Bu<M>(A, Bm, dx, duv, dxn);
+#pragma unroll
+      for (int i = 0; i < n; i++) dx[i] = dxn[i];
+    }
+  }
+  cp_async_wait<0>();
+}
+
+template <class M>
+static void launch_isls_cols(const Dev &d, cudaStream_t s) {
+  constexpr int n = M::n, m = M::m, nt = NTRI(M::m), SB = n + m + m * n + 2 * nt + 2 * m, ST = 3;
+  const int tiles = d.tile1 - d.tile0, cols = d.isls_C - 1;
+  const size_t smem = (size_t)ST * SB * TILE * sizeof(double);
+  static int mode = -2;
+  if (mode == -2) {
+    const char *e = getenv("ISLS_COLS_STAGES");       // -1 auto (default), 0 plain, 3 forced
+    mode = e ? atoi(e) : -1;
+  }
+  if (mode == ST || (mode < 0 && (long long)tiles * cols < 1536 && smem <= 48 * 1024)) {
+    k_isls_cols_staged<M, ST><<<dim3(tiles, cols), TILE, smem, s>>>(d);
+  } else {
+    k_isls_cols<M><<<dim3((tiles + 1) / 2, cols), dim3(TILE, 2), 0, s>>>(d);
   }
 }
 
@@ -3195,8 +3371,6 @@ extern "C" int isls_isls_admm_solve_f64(const isls_plan *plan, const isls_solve_
   return dispatch_model(plan, [&](auto model) -> int {
     using M = decltype(model);
     const int rows = d.N * M::m, threads = ((rows + 31) / 32) * 32;
-    dim3 gcols = tp_grid(d);
-    gcols.y = C - 1;
     LAUNCH(ISLS_KC_INIT, s, (k_init<M><<<tp_grid(d), tp_block(), 0, s>>>(d, x0, u_init, zs)));
     for (int j = 0; j < d.max_outer; j++) {
       LAUNCH(ISLS_KC_KPASS, s, (k_kpass<M><<<tp_grid(d), tp_block(), 0, s>>>(d)));
@@ -3204,7 +3378,7 @@ extern "C" int isls_isls_admm_solve_f64(const isls_plan *plan, const isls_solve_
       for (int a = 0; a < d.max_admm; a++) {
         LAUNCH(ISLS_KC_FF, s, launch_ff<M>(d, s));
         LAUNCH(ISLS_KC_LINESEARCH, s, launch_linesearch<M>(d, false, s, LsFuse{0, j, a}));
-        LAUNCH(ISLS_KC_ISLS_COLS, s, (k_isls_cols<M><<<gcols, tp_block(), 0, s>>>(d)));
+        LAUNCH(ISLS_KC_ISLS_COLS, s, launch_isls_cols<M>(d, s));
         LAUNCH(ISLS_KC_ISLS_UPDATE, s, (k_isls_update<M><<<(unsigned)B, threads, 0, s>>>(d, S, j, a)));
       }
       LAUNCH(ISLS_KC_OUTER_END, s, (k_outer_end<M><<<tp_grid(d), tp_block(), 0, s>>>(d, j)));
