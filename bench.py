@@ -120,7 +120,7 @@ def run_reference(a):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "single_core_solve_s": t1, "riccati_pass_ms_one_core": round(cpu_riccati_pass_ms(), 3)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
@@ -167,6 +167,9 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+_OUT = sys.stdout
 
 
 def run_b200(a):
@@ -347,7 +350,7 @@ def run_b200(a):
                         "h2d_bytes_per_step": sv.h2d_bytes, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches_per_step * a.steps, "roofline": roof, "kernels": kernels,
                 "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -371,8 +374,19 @@ def cpu_riccati_pass_ms(reps=5):
     return (time.perf_counter() - t0) / reps * 1e3
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout
+    when NCCL_DEBUG is set, as it is on the GPU boxes), so file descriptor 1 is pointed at stderr for the whole run and
+    the JSON line goes to a private duplicate of the original stdout."""
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 if __name__ == "__main__":
     args = parse()
+    _claim_stdout()
     if args.notebook_budget:
         BUDGET.update(I_o=30, I_a=5, L=50)
     if args.impl == "reference":
