@@ -2717,15 +2717,60 @@ __device__ __forceinline__ void lqt_obst_project(const Dev &d, const TileCtx<M> 
 // thread block computes them once (k_kpass on a single tile with a zero nominal works for linear models because
 // the Jacobian does not depend on the trajectory); every problem then iterates ff-pass (sls.py:168-202) +
 // closed-loop rollout from its x0 (sls_base.py:76-89) + projection / dual update (admm.py) inside ONE kernel.
-template <class M>
-__global__ void k_lqt_admm(Dev d, const double *x0_in) {
+// Everything that is the same for all problems and all iterations - the shared gains K, Qux, Quu, Quu^-1 and the plan
+// constants (Q, rho, bounds, seq) - is staged ONCE into shared memory when it fits (SM = true: 18 KB at N = 50, n = 4,
+// m = 2), and each thread's own operands (z, lambda, k) are fetched one step ahead into registers: a problem's ADMM
+// loop is a chain of max_iter x 2N dependent steps run by a lone warp, and with plain loads every step paid an L2 round
+// trip (C1: 90 us per iteration; profiles/r1_c3_small_batch_kernels.md).
+template <class M, bool SM>
+__global__ void k_lqt_admm(Dev d_in, const double *x0_in) {
   constexpr int n = M::n, m = M::m;
+  constexpr int nt = NTRI(M::m);
+  extern __shared__ double smem_lqt[];
+  Dev d = d_in;
+  const int N_ = d.N;
+  const double *sK = nullptr, *sQx = nullptr, *sQu = nullptr, *sQi = nullptr;
+  if (SM) {
+    double *w = smem_lqt;
+    const int nthr = blockDim.x * blockDim.y, tid0 = threadIdx.y * blockDim.x + threadIdx.x;
+    auto stage_gain = [&](const double *g, int dim) -> const double * {     // tile 0 / lane 0 of a tile-blocked array
+      double *dst = w;
+      for (int q = tid0; q < N_ * dim; q += nthr) dst[q] = g[(size_t)q * TILE];
+      w += N_ * dim;
+      return dst;
+    };
+    auto stage_plan = [&](const double *g, int dim) -> const double * {
+      double *dst = w;
+      for (int q = tid0; q < N_ * dim; q += nthr) dst[q] = g ? g[q] : 0.0;
+      w += N_ * dim;
+      return g ? dst : nullptr;
+    };
+    sK = stage_gain(d.Kg, m * n);
+    sQx = stage_gain(d.Qux, m * n);
+    sQu = stage_gain(d.Quu, nt);
+    sQi = stage_gain(d.Qui, nt);
+    d.qd = stage_plan(d_in.qd, n);
+    d.rho_x = stage_plan(d_in.rho_x, n);
+    d.lo_x = stage_plan(d_in.lo_x, n);
+    d.hi_x = stage_plan(d_in.hi_x, n);
+    d.rho_u = stage_plan(d_in.rho_u, m);
+    d.lo_u = stage_plan(d_in.lo_u, m);
+    d.hi_u = stage_plan(d_in.hi_u, m);
+    int *wi = reinterpret_cast<int *>(w);
+    for (int q = tid0; q < N_; q += nthr) { wi[q] = d_in.seq[q]; wi[N_ + q] = d_in.qnz[q]; }
+    d.seq = wi;
+    d.qnz = wi + N_;
+    __syncthreads();
+  }
   const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
   if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   // gains are shared: tile 0 / lane 0 of the gain arrays
-  constexpr int nt = NTRI(M::m);
   const double *Kg = d.Kg, *Qx = d.Qux, *Qu = d.Quu, *Qi = d.Qui;
+  auto gK = [&](int t, int q) -> double { return SM ? sK[t * (m * n) + q] : EL(Kg, m * n, t, q); };
+  auto gQx = [&](int t, int q) -> double { return SM ? sQx[t * (m * n) + q] : EL(Qx, m * n, t, q); };
+  auto gQu = [&](int t, int q) -> double { return SM ? sQu[t * nt + q] : EL(Qu, nt, t, q); };
+  auto gQi = [&](int t, int q) -> double { return SM ? sQi[t * nt + q] : EL(Qi, nt, t, q); };
   double *xa = c.at(d.xh, d, n), *ua = c.at(d.uh, d, m), *kk = c.at(d.kk, d, m);   // primal iterate -> result
   double *zx = c.at(d.zx, d, n), *lx = c.at(d.lx, d, n);
   double *zu = c.at(d.zu, d, m), *lu = c.at(d.lu, d, m);
@@ -2760,26 +2805,46 @@ __global__ void k_lqt_admm(Dev d, const double *x0_in) {
         EL(kk, m, t, j) = d.last_stage_dp ? 0.0 : -cuL / (2.0 * (d.u_std * d.Rw[j] + d.rho_u[t * m + j]));
       }
     }
+    // this thread's operands of the next step to process, fetched one step ahead
+    double pzx[n], plx[n], pzu[m], plu[m], pkk[m];
+    auto fetch_own = [&](int t, bool with_k) {
+      if (d.proj_x) {
+#pragma unroll
+        for (int i = 0; i < n; i++) { pzx[i] = EL(zx, n, t, i); plx[i] = EL(lx, n, t, i); }
+      }
+#pragma unroll
+      for (int j = 0; j < m; j++) {
+        if (d.proj_u) { pzu[j] = EL(zu, m, t, j); plu[j] = EL(lu, m, t, j); }
+        if (with_k) pkk[j] = EL(kk, m, t, j);
+      }
+    };
+    if (d.N >= 2) fetch_own(d.N - 2, false);
     for (int t = d.N - 2; t >= 0; t--) {
       double cx[n], cu[m], Qux[m][n], Quu[m][m], Qui[m][m], kt[m];
+      double czx[n], clx[n], czu[m], clu[m];
+#pragma unroll
+      for (int i = 0; i < n; i++) { czx[i] = pzx[i]; clx[i] = plx[i]; }
+#pragma unroll
+      for (int j = 0; j < m; j++) { czu[j] = pzu[j]; clu[j] = plu[j]; }
+      if (t > 0) fetch_own(t - 1, false);
       const int s = d.seq[t];
 #pragma unroll
       for (int i = 0; i < n; i++) {
         double g = d.qnz[t] ? -2.0 * d.qd[t * n + i] * EL(zs, n, s, i) : 0.0;
-        if (d.proj_x) g += -2.0 * d.rho_x[t * n + i] * (EL(zx, n, t, i) - EL(lx, n, t, i));
+        if (d.proj_x) g += -2.0 * d.rho_x[t * n + i] * (czx[i] - clx[i]);
         cx[i] = g;
       }
 #pragma unroll
       for (int j = 0; j < m; j++)
-        cu[j] = d.proj_u ? -2.0 * d.rho_u[t * m + j] * (EL(zu, m, t, j) - EL(lu, m, t, j)) : 0.0;
+        cu[j] = d.proj_u ? -2.0 * d.rho_u[t * m + j] * (czu[j] - clu[j]) : 0.0;
 #pragma unroll
       for (int a = 0; a < m; a++) {
 #pragma unroll
-        for (int j = 0; j < n; j++) Qux[a][j] = EL(Qx, m * n, t, a * n + j);
+        for (int j = 0; j < n; j++) Qux[a][j] = gQx(t, a * n + j);
 #pragma unroll
         for (int b2 = 0; b2 <= a; b2++) {
-          Qui[a][b2] = EL(Qi, nt, t, tri(a, b2)); Qui[b2][a] = Qui[a][b2];
-          Quu[a][b2] = EL(Qu, nt, t, tri(a, b2)); Quu[b2][a] = Quu[a][b2];
+          Qui[a][b2] = gQi(t, tri(a, b2)); Qui[b2][a] = Qui[a][b2];
+          Quu[a][b2] = gQu(t, tri(a, b2)); Quu[b2][a] = Quu[a][b2];
         }
       }
       ff_step<M>(A, Bm, cx, cu, Qux, Quu, Qui, v, kt);
@@ -2791,20 +2856,21 @@ __global__ void k_lqt_admm(Dev d, const double *x0_in) {
 #pragma unroll
     for (int i = 0; i < n; i++) x[i] = x0[i];
     double cs = 0.0, cc = 0.0, prx = 0.0, pru = 0.0, drx = 0.0, dru = 0.0;
+    fetch_own(0, true);
     for (int t = 0; t < d.N; t++) {
-      // loads of the step first, then stores (see admm_body)
+      // the step's own operands were fetched during the previous step; the next step's go out before this step's stores
       double zuv[m], luv[m], kv[m], zxv[n], lxv[n], Kt[m][n];
 #pragma unroll
       for (int j = 0; j < m; j++) {
 #pragma unroll
-        for (int i = 0; i < n; i++) Kt[j][i] = EL(Kg, m * n, t, j * n + i);
-        kv[j] = EL(kk, m, t, j);
-        if (d.proj_u) { zuv[j] = EL(zu, m, t, j); luv[j] = EL(lu, m, t, j); }
+        for (int i = 0; i < n; i++) Kt[j][i] = gK(t, j * n + i);
+        kv[j] = pkk[j];
+        zuv[j] = pzu[j];
+        luv[j] = plu[j];
       }
-      if (d.proj_x) {
 #pragma unroll
-        for (int i = 0; i < n; i++) { zxv[i] = EL(zx, n, t, i); lxv[i] = EL(lx, n, t, i); }
-      }
+      for (int i = 0; i < n; i++) { zxv[i] = pzx[i]; lxv[i] = plx[i]; }
+      if (t + 1 < d.N) fetch_own(t + 1, true);
       if (d.n_obst > 0) {          // park the pre-projection point; the rows are projected together after the rollout
         double *pre = c.at(d.obw, d, n);
 #pragma unroll
@@ -3453,7 +3519,23 @@ extern "C" int isls_lqt_admm_dp_f64(const isls_plan *plan, const isls_solve_opts
     k_pack_zs<M><<<tp_grid(d), tp_block(), 0, s>>>(d, zs);
     if (opts->z_x_init_dev || opts->z_u_init_dev)
       k_pack_zinit<M><<<tp_grid(d), tp_block(), 0, s>>>(d, opts->z_x_init_dev, opts->z_u_init_dev);
-    LAUNCH(ISLS_KC_LQT, s, (k_lqt_admm<M><<<tp_grid(d), tp_block(), 0, s>>>(d, x0)));
+    {
+      constexpr int nt_ = NTRI(M::m);
+      const size_t lqt_smem = N * (size_t)(2 * M::m * M::n + 2 * nt_ + 4 * M::n + 3 * M::m) * sizeof(double) +
+                              2 * N * sizeof(int);
+      static int lqt_mode = -2;
+      if (lqt_mode == -2) {
+        const char *e = getenv("ISLS_LQT_SMEM");          // -1 auto (default), 0 global-memory constants
+        lqt_mode = e ? atoi(e) : -1;
+      }
+      if (lqt_mode != 0 && lqt_smem <= 200 * 1024) {
+        static bool set_sm = false;
+        if (!set_sm) { CK(cudaFuncSetAttribute(k_lqt_admm<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set_sm = true; }
+        LAUNCH(ISLS_KC_LQT, s, (k_lqt_admm<M, true><<<tp_grid(d), tp_block(), lqt_smem, s>>>(d, x0)));
+      } else {
+        LAUNCH(ISLS_KC_LQT, s, (k_lqt_admm<M, false><<<tp_grid(d), tp_block(), 0, s>>>(d, x0)));
+      }
+    }
     Dev df = d;
     df.out.K = nullptr;          // gains are shared: unpacked by k_lqt_unpack_K
     k_finalize<M><<<tp_grid(d), tp_block(), 0, s>>>(df);

@@ -22,5 +22,11 @@ for tag, p in (("arm", configs.arm_batch(40, I_o=4, I_a=4)),                    
 o = G.run_isls_admm(configs.arm_robust_batch(3, I_o=3, I_a=3))      # robust iSLS-ADMM: k_isls_cols
 for k, v in o.items():
     out["robust_" + k] = v
+o = G.run_lqt_admm_dp(configs.di_batch(5, max_iter=60))                 # LQT-ADMM: k_lqt_admm<., SM>
+for k, v in o.items():
+    out["lqt_" + k] = v
+o = G.run_lqt_admm_dp(configs.di_obstacle_batch(2, max_iter=12))        # ... with the spherical-obstacle projection
+for k, v in o.items():
+    out["lqtobs_" + k] = v
 np.savez(sys.argv[1], **out)
 print("variant ok", sorted(k for k in os.environ if k.startswith("ISLS_")))

@@ -25,7 +25,8 @@ def _run(tmp_path, name, env_extra):
 
 def test_staged_and_plain_kernels_agree_bitwise(tmp_path):
     auto = _run(tmp_path, "auto", {})
-    plain = _run(tmp_path, "plain", {"ISLS_FF_STAGES": "0", "ISLS_ADMM_STAGES": "0", "ISLS_COLS_STAGES": "0"})
+    plain = _run(tmp_path, "plain", {"ISLS_FF_STAGES": "0", "ISLS_ADMM_STAGES": "0", "ISLS_COLS_STAGES": "0",
+                                   "ISLS_LQT_SMEM": "0"})
     deep2 = _run(tmp_path, "ff2", {"ISLS_FF_STAGES": "2"})
     assert set(auto.files) == set(plain.files)
     for k in auto.files:
