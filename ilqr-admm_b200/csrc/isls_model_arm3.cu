@@ -1,0 +1,3 @@
+// Arm3Model instantiation of the model-templated kernels (isls_kernels.cuh)
+#include "isls_kernels.cuh"
+const isls_model_ops *isls_ops_arm3() { return ModelImpl<Arm3Model>::ops(); }

@@ -1,0 +1,3 @@
+// CarModel instantiation of the model-templated kernels (isls_kernels.cuh)
+#include "isls_kernels.cuh"
+const isls_model_ops *isls_ops_car() { return ModelImpl<CarModel>::ops(); }
