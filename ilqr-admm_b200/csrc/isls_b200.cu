@@ -27,6 +27,14 @@ int isls_cuda_fail(cudaError_t e, const char *what) {
 }
 static int cuda_fail(cudaError_t e, const char *what) { return isls_cuda_fail(e, what); }
 
+// ABI guard: the caller states the size of the struct it was built against (first field of every POD struct)
+#define ABI_CHECK(ptr, type)                                                                                        \
+  do {                                                                                                              \
+    if ((ptr) && (ptr)->struct_size != (uint32_t)sizeof(type))                                                      \
+      return fail(ISLS_E_INVALID, #type ".struct_size = " + std::to_string((ptr)->struct_size) + ", this library "  \
+                  "expects " + std::to_string(sizeof(type)) + " (binding built against another isls_b200.h?)");     \
+  } while (0)
+
 thread_local bool g_prof_on = false;
 thread_local std::vector<ProfRec> g_prof;
 
@@ -305,6 +313,7 @@ static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan) {
   if (!desc || !plan) return fail(ISLS_E_INVALID, "desc/plan is NULL");
+  ABI_CHECK(desc, isls_problem_desc);
   int nja;
   if (model_dims(desc->model_id, desc->n, desc->m, &nja)) return fail(ISLS_E_UNSUPPORTED, "unsupported (model, n, m)");
   if (desc->N < 2 || desc->n_via < 1 || desc->L < 1 || desc->L > MAX_L) return fail(ISLS_E_INVALID, "bad N / n_via / L");
@@ -433,6 +442,9 @@ size_t isls_carve(const isls_plan *p, long long B, char *base, Dev *d, Dev *alt)
   takeD(d ? &d->kk : nullptr, tm);
   takeD(d ? &d->zs : nullptr, T * p->n_via * n * TILE);
   takeD(d ? &d->lsc : nullptr, T * p->L * TILE);
+  // Jacobian cache of the small-batch feed-forward kernels (k_ff_tma); large batches recompute (HBM-bound there)
+  takeD(d ? &d->Jc : nullptr, T < 1536 ? T * N * (size_t)p->NJA * TILE : 0);
+  if (d && T >= 1536) d->Jc = nullptr;
   takeD(d ? &d->obw : nullptr, p->desc.n_obst > 0 ? (2 + (p->desc.obst_kind == 1 ? 2 * (size_t)p->desc.n_obst : 0)) * tn : 0);
   const size_t tC = p->desc.isls_dim > 0 ? tm * (size_t)(p->desc.isls_dim + 1) : 0;
   takeD(d ? &d->Zm : nullptr, tC); takeD(d ? &d->Lm : nullptr, tC); takeD(d ? &d->Xu : nullptr, tC);
@@ -489,6 +501,8 @@ extern "C" int isls_ilqr_admm_solve_f64(const isls_plan *plan, const isls_solve_
                                         const double *x0, const double *u_init, const double *zs, void *ws,
                                         size_t ws_bytes, const isls_solve_out *out, void *stream) {
   if (!opts || !out || !x0 || !u_init || !zs) return fail(ISLS_E_INVALID, "NULL argument");
+  ABI_CHECK(opts, isls_solve_opts);
+  ABI_CHECK(out, isls_solve_out);
   if (opts->max_admm < 1) return fail(ISLS_E_INVALID, "max_admm must be >= 1");
   if (plan && plan->desc.n_obst > 0 && plan->desc.obst_kind != 0)
     return fail(ISLS_E_UNSUPPORTED, "iLQR-ADMM implements the rotated-rectangle (obst_kind = 0) obstacle projection");
@@ -506,6 +520,8 @@ extern "C" int isls_ilqr_solve_f64(const isls_plan *plan, const isls_solve_opts 
                                    const double *u_init, const double *zs, void *ws, size_t ws_bytes,
                                    const isls_solve_out *out, void *stream) {
   if (!opts || !out || !x0 || !u_init || !zs) return fail(ISLS_E_INVALID, "NULL argument");
+  ABI_CHECK(opts, isls_solve_opts);
+  ABI_CHECK(out, isls_solve_out);
   Dev d;
   isls_solve_opts o = *opts;
   o.max_admm = 1;     // log strides: alpha_idx is [B, max_outer]
@@ -527,6 +543,9 @@ extern "C" int isls_isls_admm_solve_f64(const isls_plan *plan, const isls_solve_
                                         const double *u_init, const double *zs, void *ws, size_t ws_bytes,
                                         const isls_solve_out *out, double *du_dev, double *phi_u_dev, void *stream) {
   if (!opts || !soc || !out || !x0 || !u_init || !zs || !du_dev || !phi_u_dev) return fail(ISLS_E_INVALID, "NULL argument");
+  ABI_CHECK(opts, isls_solve_opts);
+  ABI_CHECK(out, isls_solve_out);
+  ABI_CHECK(soc, isls_sls_admm_opts);
   if (opts->max_admm < 1) return fail(ISLS_E_INVALID, "max_admm must be >= 1");
   if (!plan || plan->desc.isls_dim < 1) return fail(ISLS_E_INVALID, "the plan was not created with isls_dim > 0");
   if (plan->proj_x || !plan->proj_u) return fail(ISLS_E_UNSUPPORTED, "isls_admm: control projection only (rho_u, no rho_x)");
@@ -554,6 +573,8 @@ extern "C" int isls_lqt_admm_dp_f64(const isls_plan *plan, const isls_solve_opts
                                     const double *zs, void *ws, size_t ws_bytes, const isls_solve_out *out,
                                     void *stream) {
   if (!opts || !out || !x0 || !zs) return fail(ISLS_E_INVALID, "NULL argument");
+  ABI_CHECK(opts, isls_solve_opts);
+  ABI_CHECK(out, isls_solve_out);
   if (plan && plan->desc.model_id != ISLS_MODEL_DOUBLE_INTEGRATOR)
     return fail(ISLS_E_UNSUPPORTED, "LQT-ADMM needs a linear model (double_integrator)");
   if (plan && plan->desc.cost_kind != ISLS_COST_QUADRATIC)

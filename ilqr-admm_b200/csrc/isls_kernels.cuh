@@ -22,6 +22,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -83,6 +84,7 @@ struct Dev {
   double stall_tol, osc_tol;
   // workspace, tile-blocked [T][N][dim][32]
   double *xh, *uh, *du, *zx, *lx, *zu, *lu, *rgx, *rgu, *Kg, *Qux, *Quu, *Qui, *kk, *zs;   // Quu, Qui: packed lower
+  double *Jc;            // [T][N][NJA][32] Jacobian scalars of the current linearisation (small batches only; else NULL)
   double *lsc;           // [T][L][32] candidate costs of the last line search
   // per-problem scalars [T*32]
   double *cost, *prev_cost, *prim, *dual, *cost_adm, *best_cost;
@@ -425,37 +427,47 @@ __global__ void k_kpass(Dev d) {
     for (int i = 0; i < n; i++) V[i][i] = hl[i] + 2.0 * d.rho_x[(d.N - 1) * n + i];              // isls.py:257
   }
   bool ok = true;
-  double xn_[n], un_[m];                   // operands of the next step, loaded while this step's Riccati update runs
+  double *Jc = d.Jc ? c.at(d.Jc, d, M::NJA) : nullptr;
+  // operands of the next step, loaded while this step's Riccati update runs - including the plan constants (q_t, rho_t:
+  // as plain loads inside the step they were an exposed L2 round trip per step, a quarter of this kernel's stall
+  // samples at 8,192 problems; profiles/r2_small_batch.md)
+  double xn_[n], un_[m], qdn_[n], rxn_[n], run_[m];
+  auto prefetch = [&](int t) {
 #pragma unroll
-  for (int i = 0; i < n; i++) xn_[i] = EL(xh, n, d.N - 2, i);
-#pragma unroll
-  for (int j = 0; j < m; j++) un_[j] = EL(uh, m, d.N - 2, j);
-  for (int t = d.N - 2; t >= 0; t--) {
-    double x[n], u[m], J[M::NJA];
-#pragma unroll
-    for (int i = 0; i < n; i++) x[i] = xn_[i];
-#pragma unroll
-    for (int j = 0; j < m; j++) u[j] = un_[j];
-    if (t > 0) {
-#pragma unroll
-      for (int i = 0; i < n; i++) xn_[i] = EL(xh, n, t - 1, i);
-#pragma unroll
-      for (int j = 0; j < m; j++) un_[j] = EL(uh, m, t - 1, j);
+    for (int i = 0; i < n; i++) {
+      xn_[i] = EL(xh, n, t, i);
+      qdn_[i] = __ldg(d.qd + t * n + i);
+      rxn_[i] = __ldg(d.rho_x + t * n + i);
     }
+#pragma unroll
+    for (int j = 0; j < m; j++) { un_[j] = EL(uh, m, t, j); run_[j] = __ldg(d.rho_u + t * m + j); }
+  };
+  prefetch(d.N - 2);
+  for (int t = d.N - 2; t >= 0; t--) {
+    double x[n], u[m], J[M::NJA], qd_t[n], rx_t[n], ru_t[m];
+#pragma unroll
+    for (int i = 0; i < n; i++) { x[i] = xn_[i]; qd_t[i] = qdn_[i]; rx_t[i] = rxn_[i]; }
+#pragma unroll
+    for (int j = 0; j < m; j++) { u[j] = un_[j]; ru_t[j] = run_[j]; }
+    if (t > 0) prefetch(t - 1);
     M::jac(x, u, J, d.dt);
     M::expand(J, A, Bm, d.dt);
+    if (Jc) {
+#pragma unroll
+      for (int q = 0; q < M::NJA; q++) EL(Jc, M::NJA, t, q) = J[q];
+    }
     double dxx[n], duu[m], K[m][n], Qux[m][n], Quu[m][m], Qui[m][m];
     if (d.cost_kind == ISLS_COST_QUADRATIC) {
 #pragma unroll
-      for (int i = 0; i < n; i++) dxx[i] = 2.0 * (d.qd[t * n + i] + d.rho_x[t * n + i]);
+      for (int i = 0; i < n; i++) dxx[i] = 2.0 * (qd_t[i] + rx_t[i]);
     } else {
       double gt[n], ht[n];
       state_grad_hess<M>(d, zs, t, x, gt, ht);
 #pragma unroll
-      for (int i = 0; i < n; i++) dxx[i] = ht[i] + 2.0 * d.rho_x[t * n + i];
+      for (int i = 0; i < n; i++) dxx[i] = ht[i] + 2.0 * rx_t[i];
     }
 #pragma unroll
-    for (int j = 0; j < m; j++) duu[j] = 2.0 * (d.u_std * d.Rw[j] + d.rho_u[t * m + j]);
+    for (int j = 0; j < m; j++) duu[j] = 2.0 * (d.u_std * d.Rw[j] + ru_t[j]);
     ok &= riccati_step<M>(A, Bm, dxx, duu, V, K, Qux, Quu, Qui);
 #pragma unroll
     for (int a = 0; a < m; a++) {
@@ -989,6 +1001,273 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
                  : "r"(smem_u32(bar)), "r"(parity)
                  : "memory");
   } while (!ok);
+}
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ---- ff-pass + linear rollout (same arithmetic as ff_body / k_ff_staged, bit for bit) with the per-step operands
+// staged by 1-D TMA bulk copies: one warp per tile, lane 0 issues ONE cp.async.bulk per operand array and chunk of TC
+// time steps (a tile's array is contiguous over time in the tile-blocked layout), NST chunks in flight, mbarrier
+// completion.  Small batches run less than one warp per SM scheduler, so a launch lasts as long as ONE warp's
+// instruction stream: against k_ff_staged (one 8-byte cp.async + address arithmetic per operand and thread, 250
+// instructions per time step) this form issues a handful of copies per chunk from one lane, keeps up to NST * TC steps
+// of operands in flight, reads plan constants from shared memory, and - with JC - takes the Jacobian scalars of the
+// linearisation from the cache k_kpass wrote (d.Jc) instead of re-evaluating sincos in both sweeps.
+// Finished lanes stay in the loop (the warp shares the copies) and are masked at the stores.
+template <class M, bool PX, bool JC, int TC, int NST>
+__global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
+  constexpr int n = M::n, m = M::m, nt = NTRI(M::m), NJ = M::NJA;
+  constexpr bool XB = !JC || PX;                          // the backward sweep stages x^ (Jacobian and / or cx)
+  // backward slab: doubles per lane and step
+  constexpr int oJ = 0, oX = oJ + (JC ? NJ : 0), oU = oX + (XB ? n : 0), oQx = oU + m, oQu = oQx + m * n,
+                oQi = oQu + nt, oRu = oQi + nt, oRx = oRu + m, SB = oRx + (PX ? n : 0);
+  // forward slab
+  constexpr int fK = 0, fk = fK + m * n, fU = fk + m, fRu = fU + m, fJ = fRu + m, SF = fJ + (JC ? NJ : n);
+  constexpr int NSTF_ = (NST * SB) / SF, NSTF = NSTF_ > 8 ? 8 : NSTF_;   // forward stages in the same memory
+  static_assert(SF <= SB, "forward slab must fit the backward slab");
+  extern __shared__ __align__(128) double smem_fft[];
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_fft);     // [NST] backward, [8] forward
+  double *ring = smem_fft + 16;
+  double *s_rhu = ring + (size_t)NST * TC * SB * TILE;    // plan constants of all steps
+  const int N = d.N;
+  double *s_rhx = s_rhu + (size_t)N * m;
+  int *s_qnz = reinterpret_cast<int *>(s_rhx + (PX ? (size_t)N * n : 0));
+  int *s_seq = s_qnz + N;
+  const int tile = d.tile0 + blockIdx.x;
+  if (tile >= d.tile1) return;
+  const int lane = threadIdx.x;
+  TileCtx<M> c(d, tile, lane);
+  const bool live = !(d.odone[c.b] || d.adone[c.b]);
+  if (!__any_sync(0xffffffffu, live)) return;
+  const double *xh = c.at(d.xh, d, n);
+  const double *zs = d.zs + (size_t)tile * d.n_via * n * TILE + c.lane;
+  double *kk = c.at(d.kk, d, m), *du = c.at(d.du, d, m);
+  // tile base pointers of the staged arrays
+  const size_t tb = (size_t)tile * N * TILE;
+  const double *t_xh = d.xh + tb * n, *t_uh = d.uh + tb * m, *t_Qx = d.Qux + tb * (m * n), *t_Qu = d.Quu + tb * nt,
+               *t_Qi = d.Qui + tb * nt, *t_ru = d.rgu + tb * m, *t_rx = PX ? d.rgx + tb * n : nullptr,
+               *t_K = d.Kg + tb * (m * n), *t_kk = d.kk + tb * m, *t_J = JC ? d.Jc + tb * NJ : nullptr;
+  for (int q = lane; q < N * m; q += TILE) s_rhu[q] = d.proj_u ? d.rho_u[q] : 0.0;
+  if (PX)
+    for (int q = lane; q < N * n; q += TILE) s_rhx[q] = d.rho_x[q];
+  for (int q = lane; q < N; q += TILE) { s_qnz[q] = d.qnz[q]; s_seq[q] = d.seq[q]; }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NST + 8; i++) mbar_init(&bar[i], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  const bool pu = d.proj_u != 0;
+  constexpr unsigned ROWB = TILE * sizeof(double);        // bytes of one component row of a step
+  auto copy = [&](double *stage, int off, const double *src, int D, int t_lo, int cnt, unsigned long long *b) {
+    bulk_g2s(stage + (size_t)off * TC * TILE, src + (size_t)t_lo * D * TILE, (unsigned)(cnt * D) * ROWB, b);
+  };
+  // ---- backward sweep: chunk ch covers t_hi = N-2 - ch*TC down to t_lo
+  const int nchb = (N - 1 + TC - 1) / TC;
+  auto issue_b = [&](int ch) {                            // lane 0 only
+    const int st = ch % NST, t_hi = N - 2 - ch * TC, t_lo = max(0, t_hi - TC + 1), cnt = t_hi - t_lo + 1;
+    double *sb = ring + (size_t)st * TC * SB * TILE;
+    const int rows = (JC ? NJ : 0) + (XB ? n : 0) + m + m * n + 2 * nt + (pu ? m : 0) + (PX ? n : 0);
+    mbar_expect_tx(&bar[st], (unsigned)(cnt * rows) * ROWB);
+    if (JC) copy(sb, oJ, t_J, NJ, t_lo, cnt, &bar[st]);
+    if (XB) copy(sb, oX, t_xh, n, t_lo, cnt, &bar[st]);
+    copy(sb, oU, t_uh, m, t_lo, cnt, &bar[st]);
+    copy(sb, oQx, t_Qx, m * n, t_lo, cnt, &bar[st]);
+    copy(sb, oQu, t_Qu, nt, t_lo, cnt, &bar[st]);
+    copy(sb, oQi, t_Qi, nt, t_lo, cnt, &bar[st]);
+    if (pu) copy(sb, oRu, t_ru, m, t_lo, cnt, &bar[st]);
+    if (PX) copy(sb, oRx, t_rx, n, t_lo, cnt, &bar[st]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NST; i++)
+      if (i < nchb) issue_b(i);
+  }
+  double A[n][n], Bm[n][m];
+  init_AB<M>(A, Bm);
+  double v[n], rw2[m], rw[m];
+#pragma unroll
+  for (int j = 0; j < m; j++) { rw[j] = d.Rw[j]; rw2[j] = 2.0 * (d.u_std * rw[j]); }
+  auto costgrad = [&](int t, const double (&x)[n], const double (&u)[m], const double (&rx)[n],
+                      const double (&ru)[m], double (&cx)[n], double (&cu)[m], int qz, int sq) {
+    if (d.cost_kind == ISLS_COST_QUADRATIC) {
+#pragma unroll
+      for (int i = 0; i < n; i++) cx[i] = qz ? 2.0 * d.qd[t * n + i] * (x[i] - EL(zs, n, sq, i)) : 0.0;
+    } else {
+      double ht[n];
+      state_grad_hess<M>(d, zs, t, x, cx, ht);
+    }
+    if (PX) {
+#pragma unroll
+      for (int i = 0; i < n; i++) cx[i] += 2.0 * s_rhx[t * n + i] * (x[i] - rx[i]);
+    }
+#pragma unroll
+    for (int j = 0; j < m; j++) {
+      double g = rw2[j] * u[j];
+      if (pu) g += 2.0 * s_rhu[t * m + j] * (u[j] - ru[j]);
+      cu[j] = g;
+    }
+  };
+  {   // terminal step N-1 (plain loads)
+    double x[n], u[m], rx[n], ru[m], cx[n], cu[m];
+#pragma unroll
+    for (int i = 0; i < n; i++) { x[i] = EL(xh, n, N - 1, i); rx[i] = PX ? d.rgx[tb * n + ((size_t)(N - 1) * n + i) * TILE + lane] : 0.0; }
+#pragma unroll
+    for (int j = 0; j < m; j++) {
+      u[j] = t_uh[((size_t)(N - 1) * m + j) * TILE + lane];
+      ru[j] = pu ? t_ru[((size_t)(N - 1) * m + j) * TILE + lane] : 0.0;
+    }
+    costgrad(N - 1, x, u, rx, ru, cx, cu, s_qnz[N - 1], s_seq[N - 1]);
+#pragma unroll
+    for (int i = 0; i < n; i++) v[i] = cx[i];
+#pragma unroll
+    for (int j = 0; j < m; j++) {
+      const double cuu = 2.0 * (d.u_std * rw[j] + d.rho_u[(N - 1) * m + j]);
+      if (live) EL(kk, m, N - 1, j) = d.last_stage_dp ? 0.0 : -cu[j] / cuu;
+    }
+  }
+  const bool need_x_glob = !XB;                           // x^ only where the state cost needs it (via-point steps)
+  for (int ch = 0; ch < nchb; ch++) {
+    const int st = ch % NST, t_hi = N - 2 - ch * TC, t_lo = max(0, t_hi - TC + 1);
+    const double *sb = ring + (size_t)st * TC * SB * TILE + lane;
+    mbar_wait(&bar[st], (unsigned)((ch / NST) & 1));
+#pragma unroll 1
+    for (int t = t_hi; t >= t_lo; t--) {
+      const int tt = t - t_lo;
+      double x[n], u[m], rx[n], ru[m], J[NJ], cx[n], cu[m], Qux[m][n], Quu[m][m], Qui[m][m], kt[m];
+      const int qz = s_qnz[t], sq = s_seq[t];
+#pragma unroll
+      for (int i = 0; i < n; i++) {
+        if (XB) x[i] = sb[(size_t)(oX * TC + tt * n + i) * TILE];
+        else x[i] = (need_x_glob && qz) ? EL(xh, n, t, i) : 0.0;
+        rx[i] = PX ? sb[(size_t)(oRx * TC + tt * n + i) * TILE] : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < m; j++) {
+        u[j] = sb[(size_t)(oU * TC + tt * m + j) * TILE];
+        ru[j] = pu ? sb[(size_t)(oRu * TC + tt * m + j) * TILE] : 0.0;
+      }
+#pragma unroll
+      for (int a = 0; a < m; a++) {
+#pragma unroll
+        for (int j = 0; j < n; j++) Qux[a][j] = sb[(size_t)(oQx * TC + tt * (m * n) + a * n + j) * TILE];
+#pragma unroll
+        for (int b2 = 0; b2 <= a; b2++) {
+          Quu[a][b2] = sb[(size_t)(oQu * TC + tt * nt + tri(a, b2)) * TILE]; Quu[b2][a] = Quu[a][b2];
+          Qui[a][b2] = sb[(size_t)(oQi * TC + tt * nt + tri(a, b2)) * TILE]; Qui[b2][a] = Qui[a][b2];
+        }
+      }
+      if (JC) {
+#pragma unroll
+        for (int q = 0; q < NJ; q++) J[q] = sb[(size_t)(oJ * TC + tt * NJ + q) * TILE];
+      } else {
+        M::jac(x, u, J, d.dt);
+      }
+      M::expand(J, A, Bm, d.dt);
+      costgrad(t, x, u, rx, ru, cx, cu, qz, sq);
+      ff_step<M>(A, Bm, cx, cu, Qux, Quu, Qui, v, kt);
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < m; j++) EL(kk, m, t, j) = kt[j];
+      }
+    }
+    __syncwarp();                                         // every lane is done with stage `st`
+    if (lane == 0 && ch + NST < nchb) issue_b(ch + NST);
+  }
+  // the forward sweep reads k through the async proxy: order this warp's generic-proxy stores of k before it
+  fence_proxy_async();
+  __syncwarp();
+  // ---- forward sweep (linear rollout + control-cost polynomials): chunk ch covers t_lo = ch*TC upwards
+  const int nchf = (N + TC - 1) / TC;
+  unsigned long long *barf = bar + NST;
+  auto issue_f = [&](int ch) {                            // lane 0 only
+    const int st = ch % NSTF, t_lo = ch * TC, cnt = min(TC, N - t_lo);
+    double *sf = ring + (size_t)st * TC * SF * TILE;
+    const int rows = m * n + m + m + (pu ? m : 0) + (JC ? NJ : n);
+    mbar_expect_tx(&barf[st], (unsigned)(cnt * rows) * ROWB);
+    copy(sf, fK, t_K, m * n, t_lo, cnt, &barf[st]);
+    copy(sf, fk, t_kk, m, t_lo, cnt, &barf[st]);
+    copy(sf, fU, t_uh, m, t_lo, cnt, &barf[st]);
+    if (pu) copy(sf, fRu, t_ru, m, t_lo, cnt, &barf[st]);
+    if (JC) copy(sf, fJ, t_J, NJ, t_lo, cnt, &barf[st]);
+    else copy(sf, fJ, t_xh, n, t_lo, cnt, &barf[st]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NSTF; i++)
+      if (i < nchf) issue_f(i);
+  }
+  double dx[n];
+#pragma unroll
+  for (int i = 0; i < n; i++) dx[i] = 0.0;
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0;
+  for (int ch = 0; ch < nchf; ch++) {
+    const int st = ch % NSTF, t_lo = ch * TC, cnt = min(TC, N - t_lo);
+    const double *sf = ring + (size_t)st * TC * SF * TILE + lane;
+    mbar_wait(&barf[st], (unsigned)((ch / NSTF) & 1));
+#pragma unroll 1
+    for (int tt = 0; tt < cnt; tt++) {
+      const int t = t_lo + tt;
+      double duv[m], u[m], K[m][n], kv[m], ru[m];
+#pragma unroll
+      for (int a = 0; a < m; a++) {
+#pragma unroll
+        for (int j = 0; j < n; j++) K[a][j] = sf[(size_t)(fK * TC + tt * (m * n) + a * n + j) * TILE];
+        kv[a] = sf[(size_t)(fk * TC + tt * m + a) * TILE];
+        u[a] = sf[(size_t)(fU * TC + tt * m + a) * TILE];
+        ru[a] = pu ? sf[(size_t)(fRu * TC + tt * m + a) * TILE] : 0.0;
+      }
+#pragma unroll
+      for (int a = 0; a < m; a++) {
+        double acc = 0.0;
+        if (t < N - 1) {
+#pragma unroll
+          for (int j = 0; j < n; j++) acc = fma(K[a][j], dx[j], acc);
+        }
+        duv[a] = acc + kv[a];
+        if (live) EL(du, m, t, a) = duv[a];
+        r0 = fma(rw[a] * u[a], u[a], r0);
+        r1 = fma(rw[a] * u[a], duv[a], r1);
+        r2 = fma(rw[a] * duv[a], duv[a], r2);
+        if (pu) {
+          const double rho = s_rhu[t * m + a], e = u[a] - ru[a];
+          c0 = fma(rho * e, e, c0);
+          c1 = fma(2.0 * rho * e, duv[a], c1);
+          c2 = fma(rho * duv[a], duv[a], c2);
+        }
+      }
+      if (t < N - 1) {
+        double J[NJ], dxn[n];
+        if (JC) {
+#pragma unroll
+          for (int q = 0; q < NJ; q++) J[q] = sf[(size_t)(fJ * TC + tt * NJ + q) * TILE];
+        } else {
+          double x[n];
+#pragma unroll
+          for (int i = 0; i < n; i++) x[i] = sf[(size_t)(fJ * TC + tt * n + i) * TILE];
+          M::jac(x, u, J, d.dt);
+        }
+        M::expand(J, A, Bm, d.dt);
+        mat_Ax_Bu<M>(A, Bm, dx, duv, dxn);
+#pragma unroll
+        for (int i = 0; i < n; i++) dx[i] = dxn[i];
+      }
+    }
+    __syncwarp();
+    if (lane == 0 && ch + NSTF < nchf) issue_f(ch + NSTF);
+  }
+  if (live) {
+    const size_t S = (size_t)d.T * TILE;
+    r0 *= d.u_std;
+    r1 *= 2.0 * d.u_std;
+    r2 *= d.u_std;
+    d.cq[c.b] = c0 + r0;
+    d.cq[S + c.b] = c1 + r1;
+    d.cq[2 * S + c.b] = c2 + r2;
+    d.cq[3 * S + c.b] = r0;
+    d.cq[4 * S + c.b] = r1;
+    d.cq[5 * S + c.b] = r2;
+  }
 }
 
 // `fuse` != 0: the CTA finishes with the streaming ADMM z / lambda / reg update of the winner (control-only
@@ -2044,6 +2323,21 @@ __device__ __forceinline__ void retire(const Dev &d, const TileCtx<M> &c, bool f
   unpack(d.lu, o.lam_u, m);
   unpack(d.Kg, o.K, m * n);
   unpack(d.kk, o.k, m);
+  if (o.Qux || o.Quu || o.Quu_inv) {            // Riccati logs of the last K-pass (sls.py:159-162); row N-1 is zero
+    constexpr int nt = NTRI(M::m);
+    const double *qx = c.at(d.Qux, d, m * n), *qu = c.at(d.Quu, d, nt), *qi = c.at(d.Qui, d, nt);
+    for (int t = 0; t < d.N; t++) {
+      const bool last = t == d.N - 1;
+      if (o.Qux)
+        for (int q = 0; q < m * n; q++) o.Qux[((size_t)c.ob * d.N + t) * m * n + q] = last ? 0.0 : EL(qx, m * n, t, q);
+      for (int a = 0; a < m; a++)
+        for (int b2 = 0; b2 < m; b2++) {
+          const int q = a >= b2 ? tri(a, b2) : tri(b2, a);
+          if (o.Quu) o.Quu[(((size_t)c.ob * d.N + t) * m + a) * m + b2] = last ? 0.0 : EL(qu, nt, t, q);
+          if (o.Quu_inv) o.Quu_inv[(((size_t)c.ob * d.N + t) * m + a) * m + b2] = last ? 0.0 : EL(qi, nt, t, q);
+        }
+    }
+  }
   int st = d.status[c.b];
   if (!finished) st |= ISLS_ST_MAX_ITER;
   if (o.cost) o.cost[c.ob] = d.cost[c.b];
@@ -2744,11 +3038,23 @@ __global__ void k_lqt_admm(Dev d_in, const double *x0_in) {
 template <class M>
 __global__ void k_lqt_unpack_K(Dev d) {
   constexpr int n = M::n, m = M::m;
+  constexpr int nt = NTRI(M::m);
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= d.B || !d.out.K) return;
-  double *q = d.out.K + (size_t)b * d.N * m * n;
-  for (int t = 0; t < d.N; t++)
-    for (int i = 0; i < m * n; i++) q[t * m * n + i] = EL(d.Kg, m * n, t, i);
+  if (b >= d.B) return;
+  const isls_solve_out &o = d.out;
+  for (int t = 0; t < d.N; t++) {
+    const bool last = t == d.N - 1;
+    for (int i = 0; i < m * n; i++) {
+      if (o.K) o.K[((size_t)b * d.N + t) * m * n + i] = EL(d.Kg, m * n, t, i);
+      if (o.Qux) o.Qux[((size_t)b * d.N + t) * m * n + i] = last ? 0.0 : EL(d.Qux, m * n, t, i);
+    }
+    for (int a = 0; a < m; a++)
+      for (int b2 = 0; b2 < m; b2++) {
+        const int q = a >= b2 ? tri(a, b2) : tri(b2, a);
+        if (o.Quu) o.Quu[(((size_t)b * d.N + t) * m + a) * m + b2] = last ? 0.0 : EL(d.Quu, nt, t, q);
+        if (o.Quu_inv) o.Quu_inv[(((size_t)b * d.N + t) * m + a) * m + b2] = last ? 0.0 : EL(d.Qui, nt, t, q);
+      }
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------- host side
@@ -2790,6 +3096,25 @@ static __global__ void k_fill_logs(double *res_log, int *alpha_idx, long long cn
 static dim3 tp_block() { return dim3(TILE, TPB_TILES); }
 static dim3 tp_grid(const Dev &d) { return dim3((d.tile1 - d.tile0 + TPB_TILES - 1) / TPB_TILES); }
 
+// k_ff_tma launcher for one ring shape: launches iff the ring fits an SM and (unless forced) all tiles are resident in
+// one wave.  Returns non-zero on a CUDA error; `launched` reports whether the kernel went out.
+template <class M, bool PX, bool JC, int TC, int NST>
+static int try_ff_tma(const Dev &d, cudaStream_t s, int tiles, int sms, bool force, bool &launched) {
+  constexpr int n = M::n, m = M::m, nt = NTRI(M::m), NJ = M::NJA;
+  constexpr int SB = (JC ? NJ : 0) + ((!JC || PX) ? n : 0) + m + m * n + 2 * nt + m + (PX ? n : 0);
+  constexpr size_t ring = (size_t)NST * TC * SB * TILE * sizeof(double);
+  if constexpr (ring <= 200 * 1024) {
+    const size_t smem = 128 + ring + (size_t)d.N * (m + (PX ? n : 0)) * sizeof(double) + 2 * (size_t)d.N * sizeof(int);
+    if (smem > 226 * 1024) return 0;
+    const long long per_sm = std::min<long long>(32, (227 * 1024) / (long long)(smem + 1024));
+    if (!force && per_sm * sms < tiles) return 0;
+    if (ensure_dyn_smem<k_ff_tma<M, PX, JC, TC, NST>>((int)smem)) return 1;
+    k_ff_tma<M, PX, JC, TC, NST><<<tiles, TILE, smem, s>>>(d);
+    launched = true;
+  }
+  return 0;
+}
+
 // ff-pass launcher: plain kernel for large batches (bandwidth-bound), cp.async-staged kernel for small ones
 template <class M>
 static int launch_ff(const Dev &d, cudaStream_t s) {
@@ -2801,6 +3126,32 @@ static int launch_ff(const Dev &d, cudaStream_t s) {
   constexpr int n = M::n, m = M::m, nt = NTRI(M::m);
   constexpr int SB = n + m + m * n + 2 * nt + m + n, SF = m * n + 3 * m + n, SL = SB > SF ? SB : SF;
   const int tiles = d.tile1 - d.tile0;
+  // small batches (less than one warp per SM scheduler): TMA-staged single-warp CTAs, the deepest operand ring at
+  // which all tiles are resident in one wave; Jacobian scalars from the cache of k_kpass when the workspace has one
+  static int ff_mode = -2, ff_jc = -1;
+  if (ff_mode == -2) {
+    const char *e = getenv("ISLS_FF_MODE");           // -1 auto (default), 0: cp.async / plain rules below, 2: TMA
+    ff_mode = e ? atoi(e) : -1;
+    const char *j = getenv("ISLS_FF_JC");             // 0: recompute the Jacobian in the TMA kernels
+    ff_jc = j ? atoi(j) : 1;
+  }
+  if (mode < 0 && (ff_mode == 2 || (ff_mode < 0 && tiles < 1536))) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const bool jc = d.Jc != nullptr && ff_jc != 0, force = ff_mode == 2;
+    bool done = false;
+    auto go = [&](auto px, auto jcc) -> int {
+      constexpr bool PX_ = decltype(px)::value, JC_ = decltype(jcc)::value;
+      if (try_ff_tma<M, PX_, JC_, 4, 4>(d, s, tiles, sms, false, done) || done) return 0;
+      if (try_ff_tma<M, PX_, JC_, 3, 3>(d, s, tiles, sms, false, done) || done) return 0;
+      if (try_ff_tma<M, PX_, JC_, 2, 2>(d, s, tiles, sms, force, done) || done) return 0;
+      return 0;
+    };
+    if (d.proj_x) { if (jc) go(std::true_type{}, std::true_type{}); else go(std::true_type{}, std::false_type{}); }
+    else { if (jc) go(std::false_type{}, std::true_type{}); else go(std::false_type{}, std::false_type{}); }
+    if (done) return 0;
+  }
   int stages = mode;
   // small batches are latency-bound: stage up to 4 steps ahead through shared memory (car 17 KB, arm 64.5 KB per
   // single-warp CTA at depth 4).  The depth is the deepest one at which ALL tiles are resident at once: with the arm's
@@ -3059,9 +3410,11 @@ struct ModelImpl {
       }
     }
     Dev df = d;
-    df.out.K = nullptr;          // gains are shared: unpacked by k_lqt_unpack_K
+    df.out.K = nullptr;          // gains and Riccati logs are shared: unpacked by k_lqt_unpack_K
+    df.out.Qux = df.out.Quu = df.out.Quu_inv = nullptr;
     k_finalize<M><<<tp_grid(d), tp_block(), 0, s>>>(df);
-    if (d.out.K) k_lqt_unpack_K<M><<<(unsigned)((B + 127) / 128), 128, 0, s>>>(d);
+    if (d.out.K || d.out.Qux || d.out.Quu || d.out.Quu_inv)
+      k_lqt_unpack_K<M><<<(unsigned)((B + 127) / 128), 128, 0, s>>>(d);
     CK(cudaGetLastError());
     return ISLS_OK;
   }

@@ -518,6 +518,8 @@ extern "C" int isls_sls_admm_f64(isls_sls_plan *p, const isls_sls_admm_opts *o, 
                                  int32_t *exit_dev, int64_t *inner_total_dev, void *stream) {
   if (!p || !o || B <= 0 || !xd_dev || !du_dev || !phi_cols_dev || !iters_dev || !exit_dev)
     return isls_fail(ISLS_E_INVALID, "NULL argument or B <= 0");
+  if (o->struct_size != (uint32_t)sizeof(isls_sls_admm_opts))
+    return isls_fail(ISLS_E_INVALID, "isls_sls_admm_opts.struct_size mismatch (binding built against another isls_b200.h?)");
   const int c = p->n / 2 + 1;
   if (o->n_cones < 1 || o->n_cones > SOC_MAXP || c > SOC_MAXC || o->cone_rows != c + 1 || !o->As || !o->bs)
     return isls_fail(ISLS_E_UNSUPPORTED, "unsupported cone set (need A_i of shape [c+1, c], c = 1 + x_dim/2 <= 4)");

@@ -12,8 +12,18 @@ c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
 
 
-class ProblemDesc(C.Structure):
-    _fields_ = [("model_id", C.c_int32), ("n", C.c_int32), ("m", C.c_int32), ("N", C.c_int32),
+class _Guarded(C.Structure):
+    """POD struct of the C-ABI: the first field is the ABI guard `struct_size`, filled in automatically."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(**kw)
+        if a:
+            raise TypeError("keyword arguments only")
+        self.struct_size = C.sizeof(self)
+
+
+class ProblemDesc(_Guarded):
+    _fields_ = [("struct_size", C.c_uint32), ("model_id", C.c_int32), ("n", C.c_int32), ("m", C.c_int32), ("N", C.c_int32),
                 ("n_via", C.c_int32), ("L", C.c_int32), ("dt", C.c_double), ("u_std", C.c_double),
                 ("Qdiag", C.c_void_p), ("seq", C.c_void_p), ("alphas", C.c_void_p),
                 ("rho_x", C.c_void_p), ("lo_x", C.c_void_p), ("hi_x", C.c_void_p),
@@ -26,27 +36,27 @@ class ProblemDesc(C.Structure):
                 ("obst_dykstra_tol", C.c_double), ("isls_dim", C.c_int32)]
 
 
-class SolveOpts(C.Structure):
-    _fields_ = [("max_outer", C.c_int32), ("max_admm", C.c_int32), ("tol", C.c_double), ("outer_tol", C.c_double),
+class SolveOpts(_Guarded):
+    _fields_ = [("struct_size", C.c_uint32), ("max_outer", C.c_int32), ("max_admm", C.c_int32), ("tol", C.c_double), ("outer_tol", C.c_double),
                 ("relax", C.c_double), ("fixed_budget", C.c_int32), ("last_stage_dp", C.c_int32),
                 ("stall_tol", C.c_double), ("osc_tol", C.c_double), ("z_x_init_dev", C.c_void_p),
                 ("z_u_init_dev", C.c_void_p)]
 
 
 OUT_FIELDS = ["x", "u", "cost", "cost_log", "n_log", "status", "outer_iters", "admm_iters", "admm_exit", "res_log",
-              "alpha_idx", "z_x", "z_u", "lam_x", "lam_u", "K", "k", "mask_x", "mask_u", "inner_iters"]
+              "alpha_idx", "z_x", "z_u", "lam_x", "lam_u", "K", "k", "mask_x", "mask_u", "inner_iters", "Quu", "Quu_inv", "Qux"]
 
 
-class SlsAdmmOpts(C.Structure):
-    _fields_ = [("max_iter", C.c_int32), ("rho_u", C.c_double), ("alpha", C.c_double), ("tol", C.c_double),
+class SlsAdmmOpts(_Guarded):
+    _fields_ = [("struct_size", C.c_uint32), ("max_iter", C.c_int32), ("rho_u", C.c_double), ("alpha", C.c_double), ("tol", C.c_double),
                 ("fixed_budget", C.c_int32), ("n_cones", C.c_int32), ("cone_rows", C.c_int32), ("As", C.c_void_p),
                 ("bs", C.c_void_p), ("inner_rho", C.c_double), ("inner_max_iter", C.c_int32),
                 ("inner_threshold", C.c_double), ("n_x_rows", C.c_int32), ("x_row_idx", C.c_void_p),
                 ("x_bs", C.c_void_p), ("rho_x_rows", C.c_void_p)]
 
 
-class SolveOut(C.Structure):
-    _fields_ = [(f, C.c_void_p) for f in OUT_FIELDS]
+class SolveOut(_Guarded):
+    _fields_ = [("struct_size", C.c_uint32)] + [(f, C.c_void_p) for f in OUT_FIELDS]
 
 
 EXPORTS = ["isls_version", "isls_last_error_string", "isls_model_id", "isls_model_supported", "isls_plan_create",

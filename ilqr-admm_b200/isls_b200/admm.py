@@ -36,13 +36,15 @@ def ADMM(shape_x, shape_u, f_argmin, project_x=False, project_u=False, z_x_init=
         ret = f_argmin(reg_x, reg_u)
         x_x, x_u = ret[0], ret[1]
         pprim, pdual = prim, dual
-        prim = dual = 0.0
+        sq = []                                                               # squared residual sums, still on the device
         if project_x:
-            p, d, _ = S.admm_project_dual(x_x.reshape(1, -1).contiguous(), z_x, l_x, bx[0], bx[1], alpha)
-            prim += float(p.sqrt()[0]); dual += float(d.sqrt()[0])
+            sq += list(S.admm_project_dual(x_x.reshape(1, -1).contiguous(), z_x, l_x, bx[0], bx[1], alpha)[:2])
         if project_u:
-            p, d, _ = S.admm_project_dual(x_u.reshape(1, -1).contiguous(), z_u, l_u, bu[0], bu[1], alpha)
-            prim += float(p.sqrt()[0]); dual += float(d.sqrt()[0])
+            sq += list(S.admm_project_dual(x_u.reshape(1, -1).contiguous(), z_u, l_u, bu[0], bu[1], alpha)[:2])
+        prim = dual = 0.0
+        if sq:                                                                # ONE device -> host read per iteration
+            r = torch.cat(sq).sqrt().tolist()
+            prim, dual = sum(r[0::2]), sum(r[1::2])                           # admm.py:62-69
         logs.append((prim, dual))
         if prim < tol and dual < tol:                                         # admm.py:72
             if verbose:

@@ -210,7 +210,7 @@ class iSLS:
                           L, rho_x=rho_x, lo_x=None if bx is None else bx[0], hi_x=None if bx is None else bx[1],
                           rho_u=rho_u, lo_u=None if bu is None else bu[0], hi_u=None if bu is None else bu[1],
                           cost=self._cost, obstacles=None if obstacles is None else obstacles.as_dict(),
-                          isls_dim=isls_dim, **self._cost_kw)
+                          isls_dim=isls_dim, device=self.device, **self._cost_kw)
             self._plan_cache.clear()
             self._plan_cache[key] = S.BatchSolver(plan, self.nb, self.device, max_outer=max_outer, max_admm=max_admm,
                                                   want_gains=want_gains, want_masks=want_masks)
@@ -415,7 +415,7 @@ class iSLS:
         plan = S.Plan(self._model, self.N, self.x_dim, self.u_dim, self._dt(),
                       np.zeros((1, self.x_dim)) if self.zs is None else self.Qdiag,
                       np.zeros(self.N, dtype=np.int32) if self.zs is None else self.seq,
-                      0.0 if self.zs is None else self.u_std, 1)
+                      0.0 if self.zs is None else self.u_std, 1, device=self.device)
         sv = S.BatchSolver(plan, nb, self.device, logs=False)
         zs = torch.zeros(nb, plan.n_via, self.x_dim, dtype=torch.float64)
         xn = x_nom.reshape(-1, self.N, self.x_dim)[:1].expand(nb, self.N, self.x_dim)

@@ -66,7 +66,7 @@ class SLS:
         return np.ascontiguousarray(np.broadcast_to(r, (self.N, dim)))
 
     def _lqt(self, x0, project_x, project_u, max_iter, rho_x, rho_u, alpha, tol, fixed_budget, want_masks,
-             last_stage_dp=True, z_init=None):
+             last_stage_dp=True, z_init=None, want_Qs=False):
         obst = project_x if isinstance(project_x, ObstacleSets) else None
         bx = project_x.expand(self.N, self.x_dim) if project_x and obst is None else None
         bu = project_u.expand(self.N, self.u_dim) if project_u else None
@@ -75,9 +75,9 @@ class SLS:
                       lo_x=None if bx is None else bx[0], hi_x=None if bx is None else bx[1],
                       rho_u=self._rho(rho_u, self.u_dim) if project_u else None,
                       lo_u=None if bu is None else bu[0], hi_u=None if bu is None else bu[1],
-                      obstacles=None if obst is None else obst.as_dict())
+                      obstacles=None if obst is None else obst.as_dict(), device=self.device)
         sv = S.BatchSolver(plan, self.nb, self.device, max_outer=1, max_admm=max_iter, logs=True, want_gains=True,
-                           want_masks=want_masks)
+                           want_masks=want_masks, want_Qs=want_Qs)
         x0 = torch.as_tensor(np.asarray(x0, dtype=np.float64)) if not isinstance(x0, torch.Tensor) else x0
         zs = torch.as_tensor(self.zs)
         sv.set_inputs(x0.reshape(-1, self.x_dim).expand(self.nb, self.x_dim),
@@ -95,14 +95,38 @@ class SLS:
             raise NotImplementedError("the LQT (DP) kernels need A, B = get_double_integrator_AB(u_dim, 2, dt) "
                                       "(the registered linear model)")
 
-    def solve_dp(self, Qr=None, Rr=None, ur=None, xr=None, return_Qs=False, x0=None):
-        """K, k of the unconstrained LQT problem by the Riccati recursion (isls/sls.py:85-166).  The regularised
-        variant (Qr, Rr, xr, ur) is internal to ADMM_LQT_DP on the device."""
-        if Qr is not None or Rr is not None or return_Qs:
-            raise NotImplementedError("regularised solve_dp is internal to ADMM_LQT_DP on the device path")
+    def _regularised(self, Qr, Rr, ur, xr, x0, return_Qs):
+        """One K-pass + one feed-forward pass of the regularised LQT problem (isls/sls.py:85-202 with Qr, Rr, xr, ur):
+        on the device this is the first ADMM iteration of the LQT kernel started from z = (xr, ur), lambda = 0 with
+        penalties diag(Qr), diag(Rr) and identity projections.  Qr [N,n,n] / Rr N x [m,m] must be diagonal."""
         self._check_lqt()
-        out = self._lqt(np.zeros(self.x_dim) if x0 is None else x0, False, False, 1, None, None, 1.0, 0.0, True, False)
-        sq = (lambda t: t[0]) if self.batch is None else (lambda t: t)
+        N, n, m = self.N, self.x_dim, self.u_dim
+        inf = Bound(-np.inf, np.inf)
+        rho_x = rho_u = None
+        zx = zu = None
+        f64 = dict(dtype=torch.float64, device=self.device)
+        if Qr is not None:
+            if xr is None:
+                raise ValueError("Qr needs xr (isls/sls.py:108)")
+            rho_x = diag_of(np.asarray(Qr, dtype=np.float64), "Qr")
+            zx = torch.as_tensor(np.asarray(xr, dtype=np.float64).reshape(-1, N, n), **f64).expand(self.nb, N, n)
+        if Rr is not None:
+            if ur is None:
+                raise ValueError("Rr needs ur (isls/sls.py:114)")
+            rho_u = diag_of(np.stack([np.asarray(r, dtype=np.float64) for r in Rr]), "Rr")
+            zu = torch.as_tensor(np.asarray(ur, dtype=np.float64).reshape(-1, N, m), **f64).expand(self.nb, N, m)
+        return self._lqt(np.zeros(n) if x0 is None else x0, inf if Qr is not None else False,
+                         inf if Rr is not None else False, 1, rho_x, rho_u, 1.0, 0.0, True, False,
+                         z_init=(zx, zu) if (zx is not None or zu is not None) else None, want_Qs=return_Qs)
+
+    def solve_dp(self, Qr=None, Rr=None, ur=None, xr=None, return_Qs=False, x0=None):
+        """K, k of the LQT problem by the Riccati recursion (isls/sls.py:85-166), optionally regularised for ADMM
+        (Cxx += 2Qr, cx -= 2Qr xr, Cuu += 2Rr, cu -= 2Rr ur; diagonal Qr / Rr) and with the logs Quu, Quu_inv, Qux
+        (return_Qs) that solve_dp_ff takes."""
+        out = self._regularised(Qr, Rr, ur, xr, x0, return_Qs)
+        sq = (lambda t: t[0].clone()) if self.batch is None else (lambda t: t.clone())
+        if return_Qs:
+            return sq(out.K), sq(out.k), sq(out.Quu), sq(out.Quu_inv), sq(out.Qux)
         return sq(out.K), sq(out.k)
 
     def solve(self, x0=None, method="dp", verbose=False):
@@ -172,12 +196,12 @@ class SLS:
         return ret
 
     def solve_dp_ff(self, K=None, Quu=None, Qux=None, Quu_inv=None, Qr=None, Rr=None, ur=None, xr=None, x0=None):
-        """Feed-forward gains k of the LQT problem (isls/sls.py:168-202).  On the device the Riccati logs K, Quu, Qux,
-        Quu_inv of solve_dp live in the solver's workspace, so the arguments are accepted for signature compatibility
-        only; the regularised variant (Qr, Rr, xr, ur) is internal to ADMM_LQT_DP / ADMM_LQT_Batch."""
-        if Qr is not None or Rr is not None:
-            raise NotImplementedError("regularised solve_dp_ff is internal to ADMM_LQT_DP on the device path")
-        return self.solve_dp(x0=x0)[1]
+        """Feed-forward gains k of the (regularised) LQT problem for new xr, ur (isls/sls.py:168-202).  The reference
+        re-uses the logs K, Quu, Qux, Quu_inv of a previous solve_dp with the same Qr, Rr; on the device that K-pass
+        is part of the same launch sequence (it depends on A, B, Q, Qr, Rr only), so the log arguments are accepted for
+        signature compatibility and not read."""
+        out = self._regularised(Qr, Rr, ur, xr, x0, False)
+        return out.k[0].clone() if self.batch is None else out.k.clone()
 
     # ------------------------------------------------------------------ SLS (system level synthesis) path
     def _plan(self):

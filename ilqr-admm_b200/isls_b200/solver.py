@@ -42,10 +42,17 @@ class Plan:
     diagonal ADMM penalties and box bounds."""
 
     def __init__(self, model, N, n, m, dt, Qdiag, seq, u_std, L, rho_x=None, lo_x=None, hi_x=None, rho_u=None,
-                 lo_u=None, hi_u=None, cost="quadratic", Rdiag=None, Hp=None, Qdiag_b=None, Hp_b=None, obstacles=None, isls_dim=0):
+                 lo_u=None, hi_u=None, cost="quadratic", Rdiag=None, Hp=None, Qdiag_b=None, Hp_b=None, obstacles=None, isls_dim=0,
+                 device="cuda:0"):
         """cost="pseudo_huber": Qdiag / Hp are the weights and smoothness scales [n_via, n] of the first term,
-        Qdiag_b / Hp_b of the optional second one (Tutorial cell 14); Rdiag [m] replaces R = u_std I."""
+        Qdiag_b / Hp_b of the optional second one (Tutorial cell 14); Rdiag [m] replaces R = u_std I.
+        device: the GPU that holds the plan's constant block - a BatchSolver must use the same one."""
         L_ = _lib.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.IslsError("isls_b200 needs a CUDA device (there is no CPU path)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         mid = L_.isls_model_id(model.encode())
         _lib.check(0 if mid >= 0 else mid, "isls_model_id(%r)" % model)
         _lib.check(L_.isls_model_supported(mid, n, m), "isls_model_supported(%s, n=%d, m=%d)" % (model, n, m))
@@ -92,7 +99,8 @@ class Plan:
             setattr(d, k, _ptr(keep.get(k)))
         self._keep = keep
         h = C.c_void_p()
-        _lib.check(L_.isls_plan_create(C.byref(d), C.byref(h)), "isls_plan_create")
+        with torch.cuda.device(self.device):          # the constant block is allocated on the current device
+            _lib.check(L_.isls_plan_create(C.byref(d), C.byref(h)), "isls_plan_create")
         self.handle = h
 
     def workspace_bytes(self, B):
@@ -102,7 +110,8 @@ class Plan:
 
     def close(self):
         if getattr(self, "handle", None):
-            _lib.lib().isls_plan_destroy(self.handle)
+            with torch.cuda.device(self.device):
+                _lib.lib().isls_plan_destroy(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -121,10 +130,14 @@ class BatchSolver:
     torch stream.  Inputs may be host (numpy / pinned torch) or device tensors."""
 
     def __init__(self, plan, B, device="cuda:0", max_outer=20, max_admm=20, logs=True, want_gains=False,
-                 want_masks=False):
+                 want_masks=False, want_Qs=False):
         if not torch.cuda.is_available():
             raise _lib.IslsError("isls_b200 needs a CUDA device (there is no CPU path)")
         self.plan, self.B, self.device = plan, int(B), torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if self.device != plan.device:
+            raise _lib.IslsError("plan constants live on %s but the solver was asked for %s" % (plan.device, self.device))
         self.max_outer, self.max_admm = int(max_outer), int(max_admm)
         p, dev = plan, self.device
         with torch.cuda.device(dev):
@@ -147,6 +160,9 @@ class BatchSolver:
                      lam_x=torch.empty(B_, N, n, **f64), lam_u=torch.empty(B_, N, m, **f64))
         if want_gains:
             o.update(K=torch.empty(B_, N, m, n, **f64), k=torch.empty(B_, N, m, **f64))
+        if want_Qs:               # Riccati logs of SLS.solve_dp(return_Qs=True) (isls/sls.py:117-120)
+            o.update(Quu=torch.empty(B_, N, m, m, **f64), Quu_inv=torch.empty(B_, N, m, m, **f64),
+                     Qux=torch.empty(B_, N, m, n, **f64))
         if want_masks:
             o.update(mask_x=torch.zeros(B_, N, n, dtype=torch.int8, device=dev),
                      mask_u=torch.zeros(B_, N, m, dtype=torch.int8, device=dev))

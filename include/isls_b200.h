@@ -16,24 +16,31 @@
  *   - return value: 0 ok; <0 invalid argument / unsupported (see ISLS_E_*); >0 a cudaError_t.
  *     isls_last_error_string() describes the last failure on the calling thread.
  *   - per-problem conditions are reported in `status[B]` bit-fields (ISLS_ST_*), never as return codes.
+ *   - ABI guard: every POD struct starts with `uint32_t struct_size`, which the caller sets to sizeof(the struct) as
+ *     declared in the header it was built against.  A mismatch (stale binding) is rejected with ISLS_E_INVALID
+ *     instead of reading past the caller's struct.  Use ISLS_INIT(type, var) in C.
  */
 #ifndef ISLS_B200_H
 #define ISLS_B200_H
 
 #include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define ISLS_VERSION 100
+#define ISLS_VERSION 200
 
 /* return codes */
 #define ISLS_OK 0
 #define ISLS_E_INVALID (-1)      /* bad argument (NULL pointer, non-positive size, ...) */
 #define ISLS_E_UNSUPPORTED (-2)  /* unknown model / unsupported (n, m) */
 #define ISLS_E_WORKSPACE (-3)    /* workspace too small or misaligned */
+
+/* zero-initialised struct with its ABI guard set:  ISLS_INIT(isls_solve_opts, o); o.max_outer = 20; ... */
+#define ISLS_INIT(type, var) type var; memset(&(var), 0, sizeof(var)); (var).struct_size = (uint32_t)sizeof(var)
 
 /* device-side dynamics models, registered by name behind the reference's forward_model / get_AB plugin slots
  * (isls/isls_base.py:106-111 forward_model; get_AB argument of isls/isls.py:54, isls/isls.py:379) */
@@ -65,6 +72,7 @@ extern "C" {
  * rho only - see SURVEY D10) and box bounds (isls/projections.py:7-11 project_bound).  All pointers are HOST
  * pointers, copied by isls_plan_create. */
 typedef struct isls_problem_desc {
+  uint32_t struct_size;  /* = sizeof(isls_problem_desc) (ABI guard) */
   int32_t model_id;      /* ISLS_MODEL_* */
   int32_t n, m, N;       /* x_dim, u_dim, horizon (N states x_0..x_{N-1}, N controls) */
   int32_t n_via;         /* number of via-points k (rows of zs / Qdiag) */
@@ -115,6 +123,7 @@ typedef struct isls_plan isls_plan;   /* opaque */
 /* iteration budgets and tolerances: keyword arguments of iSLS.ilqr_admm (isls/isls.py:379-381) and
  * iSLS.solve (isls/isls.py:54-55) */
 typedef struct isls_solve_opts {
+  uint32_t struct_size;    /* = sizeof(isls_solve_opts) (ABI guard) */
   int32_t max_outer;       /* max_iter */
   int32_t max_admm;        /* max_admm_iter (ignored by isls_ilqr_solve_f64) */
   double tol;              /* ADMM residual tolerance `tol` (admm.py:72-85) / tol_fun for plain iLQR */
@@ -132,6 +141,7 @@ typedef struct isls_solve_opts {
 
 /* Results, natural layouts, DEVICE pointers.  Optional outputs may be NULL. */
 typedef struct isls_solve_out {
+  uint32_t struct_size; /* = sizeof(isls_solve_out) (ABI guard) */
   double *x;            /* [B, N, n] final nominal states            (iSLS.x_nom) */
   double *u;            /* [B, N, m] final nominal controls          (iSLS.u_nom) */
   double *cost;         /* [B] final cost                            (iSLS.cost) */
@@ -150,6 +160,8 @@ typedef struct isls_solve_out {
   int8_t *mask_x, *mask_u; /* [B, N, dim] optional: clip mask of the last projection (-1 at lo, +1 at hi) */
   int32_t *inner_iters; /* [B, max_outer, max_admm] optional: iterations of the inner project_set_convex ADMM
                            (obstacle-set state projection only) */
+  double *Quu, *Quu_inv;/* [B, N, m, m] optional: Quu_t and its inverse of the last backward pass (the `return_Qs` logs of */
+  double *Qux;          /* SLS.solve_dp, isls/sls.py:117-120, 159-162); Qux [B, N, m, n].  Row N-1 is zero. */
 } isls_solve_out;
 
 int isls_version(void);
@@ -247,6 +259,7 @@ int isls_sls_solve_f64(const isls_sls_plan *plan, int64_t B, const double *xd_de
 /* SLS.ADMM_SLS (isls/sls.py:319-454) with project_u = row-wise project_set_convex(.., [project_soc_unit]*P)
  * (isls/projections.py:289-374, 140-162) and no state projection: robust control bounds w.r.t. the initial position. */
 typedef struct isls_sls_admm_opts {
+  uint32_t struct_size;    /* = sizeof(isls_sls_admm_opts) (ABI guard) */
   int32_t max_iter;        /* ADMM_SLS max_iter */
   double rho_u, alpha, tol;
   int32_t fixed_budget;    /* 1: ignore the stop tests */

@@ -469,6 +469,79 @@ def golden_sls_state_bounds():
     np.savez_compressed(os.path.join(OUT, "sls_state_bounds.npz"), du=du, phi_u=PHI, logs=np.array(log))
 
 
+def golden_arm_lq_step(nb=3):
+    """One outer x one ADMM x one candidate (alpha = 1) iteration of the unmodified reference on arm problems:
+    u_head = u^ + du* with du* from HEAD's explicit dense inverse (isls.py:462-465), plus the condition number of the
+    dense normal matrix.  Arbitrated against a 40-digit solve in tests/test_gpu_baseline_sizes.py."""
+    from oracle import restated as R
+    p = P.arm_batch(nb, I_o=1, I_a=1, L=1)
+    model = M.make_model(p["model"], dt=p["dt"])
+    us, conds = [], []
+    for b in range(nb):
+        s = S.make_isls(model, p["N"], p["zs"], _Qs(p), p["seq"], p["u_std"])
+        S.init_nominal(s, p["x0"][b], p["u0"])
+        rho_x = np.stack([np.diag(r) for r in p["rho_x"]])
+        r = S.run_ilqr_admm(s, model, project_x=_clip(p["lo_x"], p["hi_x"]), project_u=_clip(p["lo_u"], p["hi_u"]),
+                            rho_x=rho_x, rho_u=float(p["rho_u"][0, 0]), max_iter=1, max_admm_iter=1,
+                            max_line_search_iter=1, tol=0.0)
+        us.append(r["u"])
+        # dense normal matrix Su'(Q + Qr)Su + R + Rr of this linearisation (what HEAD inverts)
+        Qd = np.diag((p["Qdiag"][p["seq"]] + p["rho_x"]).reshape(-1))
+        Rd = np.diag((p["u_std"] + p["rho_u"]).reshape(-1))
+        conds.append(np.linalg.cond(s.Su.T @ Qd @ s.Su + Rd))
+        print("arm_lq_step", b, "cond %.2e" % conds[-1])
+    np.savez_compressed(os.path.join(OUT, "arm_lq_step.npz"), x0=p["x0"], u_head=np.stack(us), cond=np.array(conds))
+
+
+def golden_solve_dp_ff():
+    """SLS.solve_dp(return_Qs=True) and SLS.solve_dp_ff of the unmodified reference (isls/sls.py:85-202) on the C1 double
+    integrator: unregularised, and the regularised (ADMM) form with diagonal Qr, Rr and random xr, ur."""
+    pkg, _ = S.load()
+    p = P.di_batch(1)
+    N, n, m = p["N"], p["n"], p["m"]
+    model = M.make_model("double_integrator", nb_dim=m, dt=p["dt"])
+    rng = np.random.default_rng(77)
+    with S.quiet():
+        s = pkg.SLS(n, m, N)
+        s.AB = [model.A, model.B]
+        s.set_quadratic_cost(p["zs"], _Qs(p), p["seq"], p["u_std"])
+        K, k, Quu, Qui, Qux = s.solve_dp(return_Qs=True)
+        k_ff = s.solve_dp_ff(K, Quu, Qux, Qui)
+        qr, rr = rng.uniform(0.1, 2.0, (N, n)), rng.uniform(0.01, 1.0, (N, m))
+        xr, ur = rng.normal(0, 0.5, N * n), rng.normal(0, 1.0, N * m)
+        Qr = np.stack([np.diag(q) for q in qr])
+        Rr = [np.diag(r) for r in rr]
+        Kr, kr, Quur, Quir, Quxr = s.solve_dp(Qr=Qr, Rr=Rr, ur=ur, xr=xr, return_Qs=True)
+        xr2, ur2 = rng.normal(0, 0.5, N * n), rng.normal(0, 1.0, N * m)
+        kr_ff = s.solve_dp_ff(Kr, Quur, Quxr, Quir, Qr=Qr, Rr=Rr, ur=ur2, xr=xr2)
+    np.savez_compressed(os.path.join(OUT, "di_solve_dp_ff.npz"), K=K, k=k, Quu=Quu, Quu_inv=Qui, Qux=Qux, k_ff=k_ff,
+                        qr=qr, rr=rr, xr=xr, ur=ur, Kr=Kr, kr=kr, Quur=Quur, Quu_invr=Quir, Quxr=Quxr, xr2=xr2, ur2=ur2,
+                        kr_ff=kr_ff)
+    print("di_solve_dp_ff: |k_ff - k| %.2e" % np.abs(k_ff - k).max())
+
+
+def golden_admm_toy():
+    """The reference's generic ADMM driver (isls/admm.py:6-106) on a toy separable problem with a closed-form argmin:
+    min |x - a|^2 + |u - b|^2  s.t. box bounds, f_argmin(reg) = (a + rho reg) / (1 + rho); alpha = 1 and 1.5."""
+    pkg, _ = S.load()
+    from isls.admm import ADMM
+    rng = np.random.default_rng(5)
+    a, b = rng.normal(0, 1.0, 12), rng.normal(0, 2.0, 8)
+    rho = 0.7
+    out = dict(a=a, b=b, rho=rho)
+    for tag, alpha in (("a10", 1.0), ("a15", 1.5)):
+        def f_argmin(reg_x, reg_u):
+            return (a + rho * reg_x) / (1 + rho), (b + rho * reg_u) / (1 + rho)
+        with S.quiet():
+            r = ADMM(12, 8, f_argmin, project_x=lambda z: np.clip(z, -0.5, 0.5), project_u=lambda z: np.clip(z, -1.0, 1.5),
+                     max_iter=200, alpha=alpha, tol=1e-6, return_lmb=True, log=True)
+        x, u, lx, lu, zx, zu, logs = r
+        out.update({tag + "_x": x, tag + "_u": u, tag + "_lx": lx, tag + "_lu": lu, tag + "_zx": zx, tag + "_zu": zu,
+                    tag + "_logs": np.array(logs)})
+        print("admm_toy", tag, len(logs))
+    np.savez_compressed(os.path.join(OUT, "admm_toy.npz"), **out)
+
+
 if __name__ == "__main__":
     assert S.available(), "needs the reference tree"
     only = set(sys.argv[1:])                       # e.g. `make_golden.py tutorial` regenerates one fixture family
@@ -503,5 +576,11 @@ if __name__ == "__main__":
         golden_replan()
     if want("di_obstacles"):
         golden_di_obstacles()
+    if want("admm_toy"):
+        golden_admm_toy()
+    if want("arm_lq_step"):
+        golden_arm_lq_step()
+    if want("solve_dp_ff"):
+        golden_solve_dp_ff()
     if want("lqt_batch"):
         golden_lqt_admm_batch(P.di_batch(3), "di_lqt_admm_batch")

@@ -25,7 +25,7 @@ def test_header_symbols_exported():
     for nm in sorted(names):
         assert hasattr(lib, nm), "header declares %s but the library does not export it" % nm
     assert names == set(L.EXPORTS), (names ^ set(L.EXPORTS))
-    assert lib.isls_version() == 100
+    assert lib.isls_version() == 200
 
 
 def test_model_registry_and_errors():

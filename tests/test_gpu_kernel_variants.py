@@ -1,5 +1,6 @@
-"""GPU: the cp.async-staged small-batch kernels (k_ff_staged, k_admm_staged, k_isls_cols_staged - selected automatically below 1,536
-tiles) against the plain kernels the large batches use (k_ff, k_admm, k_isls_cols).  The variants differ in how operands reach the
+"""GPU: the small-batch kernels (TMA-staged k_ff_tma with the Jacobian cache, cp.async-staged k_ff_staged, k_admm_staged,
+k_isls_cols_staged - selected automatically below 1,536 tiles) against the plain kernels the large batches use (k_ff, k_admm,
+k_isls_cols).  The variants differ in how operands reach the
 registers, not in arithmetic: every output must agree BIT FOR BIT.  The library reads its variant switches once per
 process, so each variant runs in its own subprocess (tests/run_variant.py)."""
 import os
@@ -28,8 +29,11 @@ def test_staged_and_plain_kernels_agree_bitwise(tmp_path):
     plain = _run(tmp_path, "plain", {"ISLS_FF_STAGES": "0", "ISLS_ADMM_STAGES": "0", "ISLS_COLS_STAGES": "0",
                                    "ISLS_LQT_SMEM": "0"})
     deep2 = _run(tmp_path, "ff2", {"ISLS_FF_STAGES": "2"})
+    tma_nojc = _run(tmp_path, "tma_nojc", {"ISLS_FF_MODE": "2", "ISLS_FF_JC": "0"})    # k_ff_tma recomputing the Jacobian
+    staged = _run(tmp_path, "staged", {"ISLS_FF_MODE": "0"})                           # round-1 rule: cp.async staging
     assert set(auto.files) == set(plain.files)
     for k in auto.files:
-        for other, nm in ((plain, "plain"), (deep2, "ff depth 2")):
+        for other, nm in ((plain, "plain"), (deep2, "ff depth 2"), (tma_nojc, "TMA ff without the Jacobian cache"),
+                          (staged, "cp.async-staged ff")):
             assert np.array_equal(auto[k], other[k], equal_nan=True), "%s differs between auto and %s" % (k, nm)
     assert auto["arm_n_log"].min() >= 1 and np.isfinite(auto["park_cost"]).all()

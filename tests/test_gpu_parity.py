@@ -432,9 +432,25 @@ def test_di_lqt_admm_batch_form_and_stage_api(golden):
     assert np.abs(u.cpu().numpy().reshape(3, p["N"], -1) - g["u"]).max() < 1e-9
     o = R.lqt_admm_dp(p, batch_form=True)
     assert np.abs(u.cpu().numpy().reshape(3, p["N"], -1) - o["u"]).max() < 1e-9
-    # solve_dp_ff returns the feed-forward gains of solve_dp
-    K, k = s.solve_dp()
-    assert torch.equal(s.solve_dp_ff(K=K), k)
+    # solve_dp / solve_dp_ff (isls/sls.py:85-202) against the unmodified reference: unregularised and the regularised
+    # (ADMM) form with diagonal Qr, Rr, incl. the return_Qs logs
+    gd = golden("di_solve_dp_ff")
+    s1 = SLS(p["n"], p["m"], p["N"])
+    s1.AB = get_double_integrator_AB(p["m"], 2, p["dt"])
+    s1.set_quadratic_cost(p["zs"], p["Qdiag"], p["seq"], p["u_std"])
+    rel = lambda a, b: float(np.abs(a.cpu().numpy() - b).max() / max(np.abs(b).max(), 1e-300))
+    K, k, Quu, Qui, Qux = s1.solve_dp(return_Qs=True)
+    for a, nm in ((K, "K"), (k, "k"), (Quu, "Quu"), (Qui, "Quu_inv"), (Qux, "Qux")):
+        assert rel(a, gd[nm]) < 1e-9, nm
+    assert rel(s1.solve_dp_ff(K, Quu, Qux, Qui), gd["k_ff"]) < 1e-9
+    Qr = np.stack([np.diag(q) for q in gd["qr"]])
+    Rr = [np.diag(r) for r in gd["rr"]]
+    Kr, kr, Quur, Quir, Quxr = s1.solve_dp(Qr=Qr, Rr=Rr, ur=gd["ur"], xr=gd["xr"], return_Qs=True)
+    for a, nm in ((Kr, "Kr"), (kr, "kr"), (Quur, "Quur"), (Quir, "Quu_invr"), (Quxr, "Quxr")):
+        assert rel(a, gd[nm]) < 1e-9, nm
+    assert rel(s1.solve_dp_ff(Kr, Quur, Quxr, Quir, Qr=Qr, Rr=Rr, ur=gd["ur2"], xr=gd["xr2"]), gd["kr_ff"]) < 1e-9
+    with pytest.raises(NotImplementedError):
+        s1.solve_dp(Qr=Qr + 0.1, xr=gd["xr"])                          # dense Qr: SURVEY D10
     # rollout_DP: closed-loop rollouts of the line-search candidates around the nominal trajectory (arm: no angle
     # wrap, so the comparison is not at the mercy of a mod-2pi flip under feedback)
     pc = P.arm_batch(1)
@@ -460,3 +476,23 @@ def test_ragged_horizon_and_candidate_counts():
         assert np.array_equal(out["alpha_idx"], o["alpha_idx"]), (N, L)
         assert _gpu().rel_logs(out["cost_log"], o["cost_log"]) < 1e-9, (N, L)
         assert np.abs(out["u"] - o["u"]).max() < 1e-9 and np.abs(out["z_u"] - o["z_u"]).max() < 1e-9, (N, L)
+
+
+def test_host_admm_driver_vs_reference_golden(golden):
+    """isls_b200.ADMM (the reference's generic driver, isls/admm.py:6-106, with the projection / dual update in the
+    isls_admm_project_dual_f64 kernel) on the toy problem the reference's own ADMM() solved for the fixture: identical
+    iteration counts and residual logs, z / lambda / primal iterates to 1e-12, for alpha = 1 and the over-relaxed 1.5."""
+    import torch
+    from isls_b200 import ADMM, Bound
+    g = golden("admm_toy")
+    a, b = torch.as_tensor(g["a"], device="cuda:0"), torch.as_tensor(g["b"], device="cuda:0")
+    rho = float(g["rho"])
+    for tag, alpha in (("a10", 1.0), ("a15", 1.5)):
+        x, u, lx, lu, zx, zu, logs = ADMM(12, 8, lambda rx, ru: ((a + rho * rx) / (1 + rho), (b + rho * ru) / (1 + rho)),
+                                          project_x=Bound(-0.5, 0.5), project_u=Bound(-1.0, 1.5), max_iter=200,
+                                          alpha=alpha, tol=1e-6, return_lmb=True, log=True)
+        ref = g[tag + "_logs"]
+        assert len(logs) == len(ref), "iteration counts differ"
+        assert np.allclose(np.array(logs), ref, rtol=1e-9, atol=1e-15)
+        for t, nm in ((x, "x"), (u, "u"), (lx, "lx"), (lu, "lu"), (zx, "zx"), (zu, "zu")):
+            assert np.abs(t.cpu().numpy() - g[tag + "_" + nm]).max() < 1e-12, nm
