@@ -481,6 +481,7 @@ static int setup(const isls_plan *plan, const isls_solve_opts *o, int64_t B, voi
   d->T = (int)((B + TILE - 1) / TILE);
   d->tile0 = 0;
   d->tile1 = d->T;
+  d->tstep = 1;
   isls_carve(plan, B, (char *)ws, d);
   d->orig = nullptr;                  // identity slot mapping unless the solve compacts (isls_ilqr_admm_solve_f64)
   if (o) {
@@ -639,6 +640,23 @@ extern "C" int isls_admm_project_dual_f64(int64_t B, int64_t len, double relax, 
   k_admm_flat<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(len, relax, x, z, lam, lo, hi, prim_sq, dual_sq, mask);
   CK(cudaGetLastError());
   return ISLS_OK;
+}
+
+extern "C" int isls_probe_overlap_f64(const isls_plan *plan, const isls_solve_opts *opts, int64_t B, const double *x0,
+                                      const double *u_init, const double *zs, void *ws, size_t ws_bytes,
+                                      const isls_solve_out *out, int32_t ls_ctas, int32_t ff_depth, double *ms_host,
+                                      void *stream) {
+  if (!opts || !out || !x0 || !u_init || !zs || !ms_host) return fail(ISLS_E_INVALID, "NULL argument");
+  ABI_CHECK(opts, isls_solve_opts);
+  ABI_CHECK(out, isls_solve_out);
+  Dev d;
+  int rc = setup(plan, opts, B, ws, ws_bytes, out, &d);
+  if (rc) return rc;
+  if (d.proj_x || !d.proj_u || d.L > 20 || d.T < 2) return fail(ISLS_E_UNSUPPORTED, "overlap probe: control-only projection, L <= 20");
+  d.lsc = nullptr;
+  const isls_model_ops *ops = ops_of(plan);
+  if (!ops) return fail(ISLS_E_UNSUPPORTED, "unsupported model");
+  return ops->overlap_probe(d, x0, u_init, zs, (cudaStream_t)stream, ls_ctas, ff_depth, ms_host);
 }
 
 extern "C" int isls_profile_enable(int on) {

@@ -59,7 +59,9 @@ struct ProfScope {
 // ------------------------------------------------------------------------------------------------ device context
 struct Dev {
   int N, n_via, L, proj_x, proj_u, T;
-  int tile0, tile1;      // tile range of this launch (chunked solves run disjoint ranges on separate streams)
+  int tile0, tile1;      // tile range of this launch
+  int tstep;             // tile stride of this launch (k_ff, k_ff_tma, k_linesearch: 2 = every other tile, the half
+                         // batches of the overlapped schedule; all other kernels use stride 1)
   long long B;
   double dt, u_std;
   double Rw[3];          // R = u_std * diag(Rw); Rw = 1 unless the plan carries Rdiag (exact for the scalar-R plans)
@@ -201,7 +203,7 @@ __device__ __forceinline__ double ctrl_sq(const Dev &d, const double (&u)[M::m])
 // nominal_values, isls/isls.py:135-154, isls/isls_base.py:80-85) + workspace initialisation.
 template <class M>
 __global__ void k_init(Dev d, const double *x0, const double *u_init, const double *zs_in) {
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  const int tile = d.tile0 + (blockIdx.x * blockDim.y + threadIdx.y) * d.tstep;
   if (tile >= d.tile1) return;
   int *orig = d.orig;
   d.orig = nullptr;                       // slots == problems at initialisation
@@ -400,10 +402,10 @@ __device__ __forceinline__ void init_AB(double (&A)[M::n][M::n], double (&Bm)[M:
 // Cxx = 2(Q_t + Qr_t), Cuu = 2(R + Rr_t) (regularised form of sls.py:132-137).  Stores K_t, Qux_t and the packed
 // Quu_t, Quu_t^-1 (the logs of sls.py:159-162 that the feed-forward passes need); resets the ADMM state of the new outer
 // iteration (lambda = 0, isls/isls.py:414-415; z warm start isls/isls.py:489-490).
-template <class M>
+template <class M, bool SMALL = false>
 __global__ void k_kpass(Dev d) {
   constexpr int n = M::n, m = M::m, nt = NTRI(M::m);
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  const int tile = d.tile0 + (blockIdx.x * blockDim.y + threadIdx.y) * d.tstep;
   if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b]) return;
@@ -431,28 +433,35 @@ __global__ void k_kpass(Dev d) {
   // operands of the next step, loaded while this step's Riccati update runs - including the plan constants (q_t, rho_t:
   // as plain loads inside the step they were an exposed L2 round trip per step, a quarter of this kernel's stall
   // samples at 8,192 problems; profiles/r2_small_batch.md)
-  double xn_[n], un_[m], qdn_[n], rxn_[n], run_[m];
+  // (SMALL only: at 65,536 problems the kernel is HBM-bound and the 34 extra registers cost residency - 0.31 -> 0.41 ms)
+  double xn_[n], un_[m], qdn_[SMALL ? n : 1], rxn_[SMALL ? n : 1], run_[SMALL ? m : 1];
   auto prefetch = [&](int t) {
 #pragma unroll
     for (int i = 0; i < n; i++) {
       xn_[i] = EL(xh, n, t, i);
-      qdn_[i] = __ldg(d.qd + t * n + i);
-      rxn_[i] = __ldg(d.rho_x + t * n + i);
+      if (SMALL) { qdn_[i] = __ldg(d.qd + t * n + i); rxn_[i] = __ldg(d.rho_x + t * n + i); }
     }
 #pragma unroll
-    for (int j = 0; j < m; j++) { un_[j] = EL(uh, m, t, j); run_[j] = __ldg(d.rho_u + t * m + j); }
+    for (int j = 0; j < m; j++) {
+      un_[j] = EL(uh, m, t, j);
+      if (SMALL) run_[j] = __ldg(d.rho_u + t * m + j);
+    }
   };
   prefetch(d.N - 2);
   for (int t = d.N - 2; t >= 0; t--) {
     double x[n], u[m], J[M::NJA], qd_t[n], rx_t[n], ru_t[m];
 #pragma unroll
-    for (int i = 0; i < n; i++) { x[i] = xn_[i]; qd_t[i] = qdn_[i]; rx_t[i] = rxn_[i]; }
+    for (int i = 0; i < n; i++) {
+      x[i] = xn_[i];
+      qd_t[i] = SMALL ? qdn_[i] : d.qd[t * n + i];
+      rx_t[i] = SMALL ? rxn_[i] : d.rho_x[t * n + i];
+    }
 #pragma unroll
-    for (int j = 0; j < m; j++) { u[j] = un_[j]; ru_t[j] = run_[j]; }
+    for (int j = 0; j < m; j++) { u[j] = un_[j]; ru_t[j] = SMALL ? run_[j] : d.rho_u[t * m + j]; }
     if (t > 0) prefetch(t - 1);
     M::jac(x, u, J, d.dt);
     M::expand(J, A, Bm, d.dt);
-    if (Jc) {
+    if (SMALL && Jc) {
 #pragma unroll
       for (int q = 0; q < M::NJA; q++) EL(Jc, M::NJA, t, q) = J[q];
     }
@@ -523,6 +532,16 @@ __global__ void k_kpass(Dev d) {
   d.dual[c.b] = 1e6;
 }
 
+// Cost-gradient terms of the ff-pass with the rounding order spelled out (no compiler-chosen FMA contraction): the
+// plain, cp.async-staged and TMA-staged variants must produce the same bits (tests/test_gpu_kernel_variants.py; the
+// a*b + c*d form left the choice of the fused product to the compiler and the arm differed by one ulp between variants).
+__device__ __forceinline__ double ff_cx_quad(double qd, double x, double z) {            // 2 Q (x^ - z_via)
+  return __dmul_rn(__dmul_rn(2.0, qd), __dsub_rn(x, z));
+}
+__device__ __forceinline__ double ff_pen(double c, double rho, double v, double reg) {   // c + 2 rho (v - reg)
+  return __fma_rn(__dmul_rn(2.0, rho), __dsub_rn(v, reg), c);
+}
+
 // ff-pass + linear rollout = the argmin of the regularised LQ problem, delta_u* (isls/isls.py:457-465 in
 // Riccati form, SURVEY 8c' step 2): backward feed-forward recursion (sls.py:168-202) with
 //   cx = 2Q(x^ - z_via) + 2Qr(x^ - reg_x), cu = 2R u^ + 2Rr(u^ - reg_u),
@@ -546,19 +565,19 @@ __device__ __forceinline__ void ff_body(const Dev &d, const TileCtx<M> &c) {
     if (d.cost_kind == ISLS_COST_QUADRATIC) {
       const int s = d.seq[t];
 #pragma unroll
-      for (int i = 0; i < n; i++) cx[i] = d.qnz[t] ? 2.0 * d.qd[t * n + i] * (x[i] - EL(zs, n, s, i)) : 0.0;
+      for (int i = 0; i < n; i++) cx[i] = d.qnz[t] ? ff_cx_quad(d.qd[t * n + i], x[i], EL(zs, n, s, i)) : 0.0;
     } else {
       double ht[n];
       state_grad_hess<M>(d, zs, t, x, cx, ht);
     }
 #pragma unroll
     for (int i = 0; i < n; i++) {
-      if (d.proj_x) cx[i] += 2.0 * d.rho_x[t * n + i] * (x[i] - EL(rgx, n, t, i));
+      if (d.proj_x) cx[i] = ff_pen(cx[i], d.rho_x[t * n + i], x[i], EL(rgx, n, t, i));
     }
 #pragma unroll
     for (int j = 0; j < m; j++) {
-      double g = 2.0 * (d.u_std * d.Rw[j]) * u[j];
-      if (d.proj_u) g += 2.0 * d.rho_u[t * m + j] * (u[j] - EL(rgu, m, t, j));
+      double g = __dmul_rn(2.0 * (d.u_std * d.Rw[j]), u[j]);
+      if (d.proj_u) g = ff_pen(g, d.rho_u[t * m + j], u[j], EL(rgu, m, t, j));
       cu[j] = g;
     }
   };
@@ -574,7 +593,7 @@ __device__ __forceinline__ void ff_body(const Dev &d, const TileCtx<M> &c) {
 #pragma unroll
     for (int j = 0; j < m; j++) {
       // batch-form last control: du_{N-1} = -Cuu^-1 cu (isls.py:441-465, Su's last block column is zero)
-      const double cuu = 2.0 * (d.u_std * d.Rw[j] + d.rho_u[(d.N - 1) * m + j]);
+      const double cuu = __dmul_rn(2.0, __fma_rn(d.u_std, d.Rw[j], d.rho_u[(d.N - 1) * m + j]));
       EL(kk, m, d.N - 1, j) = d.last_stage_dp ? 0.0 : -cu[j] / cuu;
     }
   }
@@ -664,7 +683,7 @@ __device__ __forceinline__ void ff_body(const Dev &d, const TileCtx<M> &c) {
 
 template <class M>
 __global__ void k_ff(Dev d) {
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  const int tile = d.tile0 + (blockIdx.x * blockDim.y + threadIdx.y) * d.tstep;
   if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b] || d.adone[c.b]) return;
@@ -726,19 +745,19 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
                       const double (&rhu)[m], int qz, int sq) {
     if (d.cost_kind == ISLS_COST_QUADRATIC) {
 #pragma unroll
-      for (int i = 0; i < n; i++) cx[i] = qz ? 2.0 * d.qd[t * n + i] * (x[i] - EL(zs, n, sq, i)) : 0.0;
+      for (int i = 0; i < n; i++) cx[i] = qz ? ff_cx_quad(d.qd[t * n + i], x[i], EL(zs, n, sq, i)) : 0.0;
     } else {
       double ht[n];
       state_grad_hess<M>(d, zs, t, x, cx, ht);
     }
 #pragma unroll
     for (int i = 0; i < n; i++) {
-      if (d.proj_x) cx[i] += 2.0 * rhx[i] * (x[i] - rx[i]);
+      if (d.proj_x) cx[i] = ff_pen(cx[i], rhx[i], x[i], rx[i]);
     }
 #pragma unroll
     for (int j = 0; j < m; j++) {
-      double g = rw2[j] * u[j];
-      if (d.proj_u) g += 2.0 * rhu[j] * (u[j] - ru[j]);
+      double g = __dmul_rn(rw2[j], u[j]);
+      if (d.proj_u) g = ff_pen(g, rhu[j], u[j], ru[j]);
       cu[j] = g;
     }
   };
@@ -778,7 +797,7 @@ __global__ void __launch_bounds__(TILE) k_ff_staged(Dev d) {
     for (int i = 0; i < n; i++) v[i] = cx[i];
 #pragma unroll
     for (int j = 0; j < m; j++) {
-      const double cuu = 2.0 * (d.u_std * rw[j] + d.rho_u[(N - 1) * m + j]);
+      const double cuu = __dmul_rn(2.0, __fma_rn(d.u_std, rw[j], d.rho_u[(N - 1) * m + j]));
       EL(kk, m, N - 1, j) = d.last_stage_dp ? 0.0 : -cu[j] / cuu;
     }
   }
@@ -1033,20 +1052,9 @@ __global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
   double *s_rhx = s_rhu + (size_t)N * m;
   int *s_qnz = reinterpret_cast<int *>(s_rhx + (PX ? (size_t)N * n : 0));
   int *s_seq = s_qnz + N;
-  const int tile = d.tile0 + blockIdx.x;
-  if (tile >= d.tile1) return;
   const int lane = threadIdx.x;
-  TileCtx<M> c(d, tile, lane);
-  const bool live = !(d.odone[c.b] || d.adone[c.b]);
-  if (!__any_sync(0xffffffffu, live)) return;
-  const double *xh = c.at(d.xh, d, n);
-  const double *zs = d.zs + (size_t)tile * d.n_via * n * TILE + c.lane;
-  double *kk = c.at(d.kk, d, m), *du = c.at(d.du, d, m);
-  // tile base pointers of the staged arrays
-  const size_t tb = (size_t)tile * N * TILE;
-  const double *t_xh = d.xh + tb * n, *t_uh = d.uh + tb * m, *t_Qx = d.Qux + tb * (m * n), *t_Qu = d.Quu + tb * nt,
-               *t_Qi = d.Qui + tb * nt, *t_ru = d.rgu + tb * m, *t_rx = PX ? d.rgx + tb * n : nullptr,
-               *t_K = d.Kg + tb * (m * n), *t_kk = d.kk + tb * m, *t_J = JC ? d.Jc + tb * NJ : nullptr;
+  const int ntiles = (d.tile1 - d.tile0 + d.tstep - 1) / d.tstep;
+  if ((int)blockIdx.x >= ntiles) return;
   for (int q = lane; q < N * m; q += TILE) s_rhu[q] = d.proj_u ? d.rho_u[q] : 0.0;
   if (PX)
     for (int q = lane; q < N * n; q += TILE) s_rhx[q] = d.rho_x[q];
@@ -1057,6 +1065,21 @@ __global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
     mbar_fence_init();
   }
   __syncwarp();
+  unsigned gb = 0, gf = 0;      // chunks consumed so far by this warp (backward / forward rings keep running across tiles)
+  // persistent over tiles (grid = tiles for the small-batch launches, fewer CTAs in the overlapped schedule)
+  for (int it = blockIdx.x; it < ntiles; it += gridDim.x) {
+  const int tile = d.tile0 + it * d.tstep;
+  TileCtx<M> c(d, tile, lane);
+  const bool live = !(d.odone[c.b] || d.adone[c.b]);
+  if (!__any_sync(0xffffffffu, live)) continue;
+  const double *xh = c.at(d.xh, d, n);
+  const double *zs = d.zs + (size_t)tile * d.n_via * n * TILE + c.lane;
+  double *kk = c.at(d.kk, d, m), *du = c.at(d.du, d, m);
+  // tile base pointers of the staged arrays
+  const size_t tb = (size_t)tile * N * TILE;
+  const double *t_xh = d.xh + tb * n, *t_uh = d.uh + tb * m, *t_Qx = d.Qux + tb * (m * n), *t_Qu = d.Quu + tb * nt,
+               *t_Qi = d.Qui + tb * nt, *t_ru = d.rgu + tb * m, *t_rx = PX ? d.rgx + tb * n : nullptr,
+               *t_K = d.Kg + tb * (m * n), *t_kk = d.kk + tb * m, *t_J = JC ? d.Jc + tb * NJ : nullptr;
   const bool pu = d.proj_u != 0;
   constexpr unsigned ROWB = TILE * sizeof(double);        // bytes of one component row of a step
   auto copy = [&](double *stage, int off, const double *src, int D, int t_lo, int cnt, unsigned long long *b) {
@@ -1065,7 +1088,7 @@ __global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
   // ---- backward sweep: chunk ch covers t_hi = N-2 - ch*TC down to t_lo
   const int nchb = (N - 1 + TC - 1) / TC;
   auto issue_b = [&](int ch) {                            // lane 0 only
-    const int st = ch % NST, t_hi = N - 2 - ch * TC, t_lo = max(0, t_hi - TC + 1), cnt = t_hi - t_lo + 1;
+    const int st = (int)((gb + ch) % NST), t_hi = N - 2 - ch * TC, t_lo = max(0, t_hi - TC + 1), cnt = t_hi - t_lo + 1;
     double *sb = ring + (size_t)st * TC * SB * TILE;
     const int rows = (JC ? NJ : 0) + (XB ? n : 0) + m + m * n + 2 * nt + (pu ? m : 0) + (PX ? n : 0);
     mbar_expect_tx(&bar[st], (unsigned)(cnt * rows) * ROWB);
@@ -1092,19 +1115,19 @@ __global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
                       const double (&ru)[m], double (&cx)[n], double (&cu)[m], int qz, int sq) {
     if (d.cost_kind == ISLS_COST_QUADRATIC) {
 #pragma unroll
-      for (int i = 0; i < n; i++) cx[i] = qz ? 2.0 * d.qd[t * n + i] * (x[i] - EL(zs, n, sq, i)) : 0.0;
+      for (int i = 0; i < n; i++) cx[i] = qz ? ff_cx_quad(d.qd[t * n + i], x[i], EL(zs, n, sq, i)) : 0.0;
     } else {
       double ht[n];
       state_grad_hess<M>(d, zs, t, x, cx, ht);
     }
     if (PX) {
 #pragma unroll
-      for (int i = 0; i < n; i++) cx[i] += 2.0 * s_rhx[t * n + i] * (x[i] - rx[i]);
+      for (int i = 0; i < n; i++) cx[i] = ff_pen(cx[i], s_rhx[t * n + i], x[i], rx[i]);
     }
 #pragma unroll
     for (int j = 0; j < m; j++) {
-      double g = rw2[j] * u[j];
-      if (pu) g += 2.0 * s_rhu[t * m + j] * (u[j] - ru[j]);
+      double g = __dmul_rn(rw2[j], u[j]);
+      if (pu) g = ff_pen(g, s_rhu[t * m + j], u[j], ru[j]);
       cu[j] = g;
     }
   };
@@ -1122,15 +1145,15 @@ __global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
     for (int i = 0; i < n; i++) v[i] = cx[i];
 #pragma unroll
     for (int j = 0; j < m; j++) {
-      const double cuu = 2.0 * (d.u_std * rw[j] + d.rho_u[(N - 1) * m + j]);
+      const double cuu = __dmul_rn(2.0, __fma_rn(d.u_std, rw[j], d.rho_u[(N - 1) * m + j]));
       if (live) EL(kk, m, N - 1, j) = d.last_stage_dp ? 0.0 : -cu[j] / cuu;
     }
   }
   const bool need_x_glob = !XB;                           // x^ only where the state cost needs it (via-point steps)
   for (int ch = 0; ch < nchb; ch++) {
-    const int st = ch % NST, t_hi = N - 2 - ch * TC, t_lo = max(0, t_hi - TC + 1);
+    const int st = (int)((gb + ch) % NST), t_hi = N - 2 - ch * TC, t_lo = max(0, t_hi - TC + 1);
     const double *sb = ring + (size_t)st * TC * SB * TILE + lane;
-    mbar_wait(&bar[st], (unsigned)((ch / NST) & 1));
+    mbar_wait(&bar[st], (unsigned)(((gb + ch) / NST) & 1));
 #pragma unroll 1
     for (int t = t_hi; t >= t_lo; t--) {
       const int tt = t - t_lo;
@@ -1174,6 +1197,7 @@ __global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
     __syncwarp();                                         // every lane is done with stage `st`
     if (lane == 0 && ch + NST < nchb) issue_b(ch + NST);
   }
+  gb += (unsigned)nchb;
   // the forward sweep reads k through the async proxy: order this warp's generic-proxy stores of k before it
   fence_proxy_async();
   __syncwarp();
@@ -1181,7 +1205,7 @@ __global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
   const int nchf = (N + TC - 1) / TC;
   unsigned long long *barf = bar + NST;
   auto issue_f = [&](int ch) {                            // lane 0 only
-    const int st = ch % NSTF, t_lo = ch * TC, cnt = min(TC, N - t_lo);
+    const int st = (int)((gf + ch) % NSTF), t_lo = ch * TC, cnt = min(TC, N - t_lo);
     double *sf = ring + (size_t)st * TC * SF * TILE;
     const int rows = m * n + m + m + (pu ? m : 0) + (JC ? NJ : n);
     mbar_expect_tx(&barf[st], (unsigned)(cnt * rows) * ROWB);
@@ -1202,9 +1226,9 @@ __global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
   for (int i = 0; i < n; i++) dx[i] = 0.0;
   double c0 = 0.0, c1 = 0.0, c2 = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0;
   for (int ch = 0; ch < nchf; ch++) {
-    const int st = ch % NSTF, t_lo = ch * TC, cnt = min(TC, N - t_lo);
+    const int st = (int)((gf + ch) % NSTF), t_lo = ch * TC, cnt = min(TC, N - t_lo);
     const double *sf = ring + (size_t)st * TC * SF * TILE + lane;
-    mbar_wait(&barf[st], (unsigned)((ch / NSTF) & 1));
+    mbar_wait(&barf[st], (unsigned)(((gf + ch) / NSTF) & 1));
 #pragma unroll 1
     for (int tt = 0; tt < cnt; tt++) {
       const int t = t_lo + tt;
@@ -1268,14 +1292,20 @@ __global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
     d.cq[4 * S + c.b] = r1;
     d.cq[5 * S + c.b] = r2;
   }
+  gf += (unsigned)nchf;
+  __syncwarp();                 // the ring is re-used by the next tile's backward sweep
+  }
 }
 
 // `fuse` != 0: the CTA finishes with the streaming ADMM z / lambda / reg update of the winner (control-only
 // projections).  PX = the plan has a state projection (compile-time, so the control-only kernel carries no penalty
 // accumulators or reg_x operands).  Every thread of the CTA runs the rollout loop (it contains CTA barriers); lanes
 // whose problem is finished compute on stale data and are masked at the writes.
-template <class M, int CPT, int MAXW, int MINB, bool PX>
-__global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fuse, int outer, int inner) {
+// One tile's line search; returns the number of staged chunks it consumed (the mbarrier ring keeps running across the
+// tiles of a persistent CTA: `gch` = chunks consumed so far by this CTA, `init_bars` = first tile of the CTA).
+template <class M, int CPT, int MAXW, bool PX>
+__device__ __forceinline__ int ls_tile(const Dev &d, const int tile, int fuse, int outer, int inner, const unsigned gch,
+                                       const bool init_bars) {
   constexpr int n = M::n, m = M::m;
   constexpr int LMAX = CPT * MAXW;                            // candidates this CTA shape can hold (>= d.L)
   constexpr int ROWS = 2 * m + (PX ? n : 0);                  // staged doubles per lane and step
@@ -1291,25 +1321,24 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
   __shared__ double scs[LMAX][TILE];         // state-cost part of every candidate (cost of the winner w/o penalty)
   __shared__ double sred[2][MAXW][TILE];     // residual partial sums of the fused ADMM update
   __shared__ int sbest[TILE];
-  const int tile = d.tile0 + blockIdx.x;
   TileCtx<M> c(d, tile, threadIdx.x);
   const int w = threadIdx.y;
   const bool skip = d.odone[c.b] || d.adone[c.b];
-  if (__syncthreads_and(skip)) return;
+  if (__syncthreads_and(skip)) return 0;
+  const int nchunks = (d.N + TC - 1) / TC;
   {
     const bool leader = threadIdx.x == 0 && w == 0;
-    const int nchunks = (d.N + TC - 1) / TC;
     const double *uh_t = d.uh + (size_t)tile * d.N * m * TILE, *du_t = d.du + (size_t)tile * d.N * m * TILE;
     const double *rg_t = PX ? d.rgx + (size_t)tile * d.N * n * TILE : nullptr;
     auto issue = [&](int ch) {                                // leader only
-      const int st = ch % NST, t0 = ch * TC, cnt = min(TC, d.N - t0);
+      const int st = (int)((gch + ch) % NST), t0 = ch * TC, cnt = min(TC, d.N - t0);
       const unsigned bu = (unsigned)(cnt * m * TILE * sizeof(double)), bx = (unsigned)(cnt * n * TILE * sizeof(double));
       mbar_expect_tx(&fullbar[st], 2 * bu + (PX ? bx : 0u));
       bulk_g2s(&su[st][0][0][0], uh_t + (size_t)t0 * m * TILE, bu, &fullbar[st]);
       bulk_g2s(&sd[st][0][0][0], du_t + (size_t)t0 * m * TILE, bu, &fullbar[st]);
       if (PX) bulk_g2s(&sr[st][0][0][0], rg_t + (size_t)t0 * n * TILE, bx, &fullbar[st]);
     };
-    if (leader) {
+    if (leader && init_bars) {
 #pragma unroll
       for (int i = 0; i < NST; i++) mbar_init(&fullbar[i], 1);
       mbar_fence_init();
@@ -1335,12 +1364,12 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
       bad[q] = !M::fast_state(x[q]);
     }
     for (int ch = 0; ch < nchunks; ch++) {
-      const int st = ch % NST, t0 = ch * TC, cnt = min(TC, d.N - t0);
+      const int st = (int)((gch + ch) % NST), t0 = ch * TC, cnt = min(TC, d.N - t0);
       unsigned qmask = 0;                                     // steps of this chunk that carry a state cost
 #pragma unroll
       for (int tt = 0; tt < TC; tt++)
         if (tt < cnt && d.qnz[t0 + tt]) qmask |= 1u << tt;
-      mbar_wait(&fullbar[st], (unsigned)((ch / NST) & 1));
+      mbar_wait(&fullbar[st], (unsigned)(((gch + ch) / NST) & 1));
 #pragma unroll 2
       for (int tt = 0; tt < cnt; tt++) {
         const int t = t0 + tt;
@@ -1436,7 +1465,7 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
       for (int l = 0; l < d.L; l++) o[(size_t)l * TILE] = sc[l][c.lane];
     }
   }
-  if (!fuse) return;
+  if (!fuse) return nchunks;
   // ---- fused ADMM update for control-only projections (admm.py:43-97): z_u, lambda_u and reg_u depend on the winner
   // only through u = u^ + alpha* du, so the whole CTA streams the tile's N x m elements (warp w takes t = w, w+W, ..)
   // instead of a separate trajectory-per-thread kernel re-rolling the model.  Residual sums: fixed-order reduction.
@@ -1495,6 +1524,32 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fus
     d.cost_adm[c.b] = scs[bi][c.lane] + fma(al, fma(al, d.cq[5 * S + c.b], d.cq[4 * S + c.b]), d.cq[3 * S + c.b]);
     admm_finish<M>(d, c, outer, inner, bi, sqrt(ps), sqrt(ds));
   }
+  return nchunks;
+}
+
+template <class M, int CPT, int MAXW, int MINB, bool PX>
+__global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch(Dev d, int fuse, int outer, int inner) {
+  ls_tile<M, CPT, MAXW, PX>(d, d.tile0 + blockIdx.x * d.tstep, fuse, outer, inner, 0u, true);
+}
+
+// Persistent form for the overlapped schedule (see ModelImpl::ilqr_admm): exactly as many CTAs as stay resident next
+// to the HBM-bound feed-forward kernel of the other half batch; tiles are fetched from a counter (ctr[0]; the last CTA
+// to leave resets it and the exit count ctr[1], so the pair is ready for the next launch).
+template <class M, int CPT, int MAXW, int MINB, bool PX>
+__global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch_pers(Dev d, int fuse, int outer, int inner, int *ctr) {
+  __shared__ int s_tile;
+  const bool t0 = threadIdx.x == 0 && threadIdx.y == 0;
+  const int ntiles = (d.tile1 - d.tile0 + d.tstep - 1) / d.tstep;
+  unsigned gch = 0;                                           // 0 until a tile got past its skip test = barriers not initialised
+  for (;;) {
+    __syncthreads();                                          // the previous tile's shared state is dead
+    if (t0) s_tile = atomicAdd(&ctr[0], 1);
+    __syncthreads();
+    const int i = s_tile;
+    if (i >= ntiles) break;
+    gch += (unsigned)ls_tile<M, CPT, MAXW, PX>(d, d.tile0 + i * d.tstep, fuse, outer, inner, gch, gch == 0);
+  }
+  if (t0 && atomicAdd(&ctr[1], 1) == (int)gridDim.x - 1) { ctr[0] = 0; ctr[1] = 0; }
 }
 
 // ---- state projection onto the outside of obstacle sets: project_set_convex (isls/projections.py:289-374) with
@@ -1743,7 +1798,7 @@ __device__ __forceinline__ void admm_finish(const Dev &d, const TileCtx<M> &c, i
 
 template <class M>
 __global__ void k_admm(Dev d, int outer, int inner) {
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  const int tile = d.tile0 + (blockIdx.x * blockDim.y + threadIdx.y) * d.tstep;
   if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b] || d.adone[c.b]) return;
@@ -1792,7 +1847,7 @@ static int launch_admm(const Dev &d, int outer, int inner, cudaStream_t s) {
 template <class M>
 __global__ void k_isls_reset(Dev d) {
   constexpr int m = M::m;
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  const int tile = d.tile0 + (blockIdx.x * blockDim.y + threadIdx.y) * d.tstep;
   if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b]) return;
@@ -1811,7 +1866,7 @@ __global__ void k_isls_reset(Dev d) {
 template <class M>
 __global__ void k_isls_cols(Dev d) {
   constexpr int n = M::n, m = M::m, nt = NTRI(M::m);
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  const int tile = d.tile0 + (blockIdx.x * blockDim.y + threadIdx.y) * d.tstep;
   if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b] || d.adone[c.b]) return;
@@ -2126,7 +2181,7 @@ __global__ void k_isls_update(Dev d, SocSet S, int outer, int inner) {
 template <class M>
 __global__ void k_isls_out(Dev d, double *du_out, double *phi_out) {
   constexpr int m = M::m;
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  const int tile = d.tile0 + (blockIdx.x * blockDim.y + threadIdx.y) * d.tstep;
   if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (!c.valid) return;
@@ -2232,7 +2287,7 @@ __global__ void k_obst_project(Dev d, int outer, int inner) {
 template <class M>
 __global__ void k_outer_end(Dev d, int outer) {
   constexpr int n = M::n, m = M::m;
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  const int tile = d.tile0 + (blockIdx.x * blockDim.y + threadIdx.y) * d.tstep;
   if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b]) return;
@@ -2349,7 +2404,7 @@ __device__ __forceinline__ void retire(const Dev &d, const TileCtx<M> &c, bool f
 // Unpack results to the natural (reference) layouts.
 template <class M>
 __global__ void k_finalize(Dev d) {
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  const int tile = d.tile0 + (blockIdx.x * blockDim.y + threadIdx.y) * d.tstep;
   if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (!c.valid) return;
@@ -2406,7 +2461,7 @@ __global__ void k_compact_move(Dev a, Dev b) {           // a: current buffers, 
 template <class M>
 __global__ void k_backward_full(Dev d) {
   constexpr int n = M::n, m = M::m;
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  const int tile = d.tile0 + (blockIdx.x * blockDim.y + threadIdx.y) * d.tstep;
   if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b]) return;
@@ -2557,7 +2612,7 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch_closed(Dev d) 
 template <class M>
 __global__ void k_accept_closed(Dev d, int it) {
   constexpr int n = M::n, m = M::m;
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  const int tile = d.tile0 + (blockIdx.x * blockDim.y + threadIdx.y) * d.tstep;
   if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (d.odone[c.b]) return;
@@ -2620,7 +2675,7 @@ template <class M>
 __global__ void k_pack_stage(Dev d, const double *x_nom, const double *u_nom, const double *du_in,
                              const double *zs_in, const double *regx, const double *regu) {
   constexpr int n = M::n, m = M::m;
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  const int tile = d.tile0 + (blockIdx.x * blockDim.y + threadIdx.y) * d.tstep;
   if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m), *du = c.at(d.du, d, m);
@@ -2671,7 +2726,7 @@ __global__ void k_pack_stage(Dev d, const double *x_nom, const double *u_nom, co
 template <class M>
 __global__ void k_unpack_stage(Dev d, double *costs, int *best, double *x_best, double *u_best) {
   constexpr int n = M::n, m = M::m;
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  const int tile = d.tile0 + (blockIdx.x * blockDim.y + threadIdx.y) * d.tstep;
   if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   if (!c.valid) return;
@@ -2835,7 +2890,7 @@ __global__ void k_lqt_admm(Dev d_in, const double *x0_in) {
     d.qnz = wi + N_;
     __syncthreads();
   }
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  const int tile = d.tile0 + (blockIdx.x * blockDim.y + threadIdx.y) * d.tstep;
   if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   // gains are shared: tile 0 / lane 0 of the gain arrays
@@ -3093,8 +3148,9 @@ static __global__ void k_fill_logs(double *res_log, int *alpha_idx, long long cn
 }
 
 #define TPB_TILES 2   // tiles (warps) per CTA for the one-thread-per-problem kernels
+static inline int n_tiles(const Dev &d) { return (d.tile1 - d.tile0 + d.tstep - 1) / d.tstep; }   // tiles of this launch
 static dim3 tp_block() { return dim3(TILE, TPB_TILES); }
-static dim3 tp_grid(const Dev &d) { return dim3((d.tile1 - d.tile0 + TPB_TILES - 1) / TPB_TILES); }
+static dim3 tp_grid(const Dev &d) { return dim3((n_tiles(d) + TPB_TILES - 1) / TPB_TILES); }
 
 // k_ff_tma launcher for one ring shape: launches iff the ring fits an SM and (unless forced) all tiles are resident in
 // one wave.  Returns non-zero on a CUDA error; `launched` reports whether the kernel went out.
@@ -3115,6 +3171,13 @@ static int try_ff_tma(const Dev &d, cudaStream_t s, int tiles, int sms, bool for
   return 0;
 }
 
+// K-pass launcher: below 1,536 tiles the latency-oriented form (plan constants one step ahead, Jacobian cache)
+template <class M>
+static void launch_kpass(const Dev &d, cudaStream_t s) {
+  if (d.Jc) k_kpass<M, true><<<tp_grid(d), tp_block(), 0, s>>>(d);
+  else k_kpass<M, false><<<tp_grid(d), tp_block(), 0, s>>>(d);
+}
+
 // ff-pass launcher: plain kernel for large batches (bandwidth-bound), cp.async-staged kernel for small ones
 template <class M>
 static int launch_ff(const Dev &d, cudaStream_t s) {
@@ -3125,7 +3188,7 @@ static int launch_ff(const Dev &d, cudaStream_t s) {
   }
   constexpr int n = M::n, m = M::m, nt = NTRI(M::m);
   constexpr int SB = n + m + m * n + 2 * nt + m + n, SF = m * n + 3 * m + n, SL = SB > SF ? SB : SF;
-  const int tiles = d.tile1 - d.tile0;
+  const int tiles = n_tiles(d);
   // small batches (less than one warp per SM scheduler): TMA-staged single-warp CTAs, the deepest operand ring at
   // which all tiles are resident in one wave; Jacobian scalars from the cache of k_kpass when the workspace has one
   static int ff_mode = -2, ff_jc = -1;
@@ -3198,9 +3261,9 @@ struct LsFuse { int fuse, outer, inner; };
 template <class M, int CPT, int MAXW, int MINB = 1>
 static void launch_ls_cfg(const Dev &d, bool closed, cudaStream_t s, LsFuse f) {
   const int W = (d.L + CPT - 1) / CPT;
-  if (closed) k_linesearch_closed<M, CPT, MAXW, MINB><<<d.tile1 - d.tile0, dim3(TILE, W), 0, s>>>(d);
-  else if (d.proj_x) k_linesearch<M, CPT, MAXW, MINB, true><<<d.tile1 - d.tile0, dim3(TILE, W), 0, s>>>(d, f.fuse, f.outer, f.inner);
-  else k_linesearch<M, CPT, MAXW, MINB, false><<<d.tile1 - d.tile0, dim3(TILE, W), 0, s>>>(d, f.fuse, f.outer, f.inner);
+  if (closed) k_linesearch_closed<M, CPT, MAXW, MINB><<<n_tiles(d), dim3(TILE, W), 0, s>>>(d);
+  else if (d.proj_x) k_linesearch<M, CPT, MAXW, MINB, true><<<n_tiles(d), dim3(TILE, W), 0, s>>>(d, f.fuse, f.outer, f.inner);
+  else k_linesearch<M, CPT, MAXW, MINB, false><<<n_tiles(d), dim3(TILE, W), 0, s>>>(d, f.fuse, f.outer, f.inner);
 }
 static int solve_compact() {
   static int v = -1;
@@ -3240,7 +3303,7 @@ static void launch_linesearch(const Dev &d, bool closed, cudaStream_t s, LsFuse 
 // ADMM warm start of the LQT path from natural-layout arrays (ADMM_LQT_Batch: the unconstrained solution, sls.py:266-268)
 template <class M>
 __global__ void k_pack_zinit(Dev d, const double *zx_in, const double *zu_in) {
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  const int tile = d.tile0 + (blockIdx.x * blockDim.y + threadIdx.y) * d.tstep;
   if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   double *zx = c.at(d.zx, d, M::n), *zu = c.at(d.zu, d, M::m);
@@ -3252,7 +3315,7 @@ __global__ void k_pack_zinit(Dev d, const double *zx_in, const double *zu_in) {
 
 template <class M>
 __global__ void k_pack_zs(Dev d, const double *zs_in) {
-  const int tile = d.tile0 + blockIdx.x * blockDim.y + threadIdx.y;
+  const int tile = d.tile0 + (blockIdx.x * blockDim.y + threadIdx.y) * d.tstep;
   if (tile >= d.tile1) return;
   TileCtx<M> c(d, tile, threadIdx.x);
   double *zs = d.zs + (size_t)tile * d.n_via * M::n * TILE + c.lane;
@@ -3273,11 +3336,40 @@ struct isls_model_ops {
   int (*rollout_linesearch)(Dev d, const double *x_nom, const double *u_nom, const double *du, const double *zs,
                             const double *reg_x, const double *reg_u, double *costs, int32_t *best, double *x_best,
                             double *u_best, cudaStream_t s);
+  int (*overlap_probe)(Dev d, const double *x0, const double *u_init, const double *zs, cudaStream_t s, int ls_ctas,
+                       int ff_depth, double *ms);
 };
 const isls_model_ops *isls_ops_car();
 const isls_model_ops *isls_ops_arm3();
 const isls_model_ops *isls_ops_tassa_car();
 const isls_model_ops *isls_ops_double_integrator(int m);
+
+// ---- overlapped schedule (large batches, control-only projections): the FP64-bound line search of one half of the
+// tiles runs concurrently with the HBM-bound kernels (feed-forward pass; outer end + K-pass at outer boundaries) of the
+// other half, on two streams.  The line search runs as a persistent kernel with a capped number of CTAs per SM so the
+// TMA-staged feed-forward CTAs of the other half find registers and shared memory on every SM.
+struct OvlAux {
+  cudaStream_t s;
+  cudaEvent_t ev[8];
+};
+static inline OvlAux *ovl_aux() {                        // per host thread and device: side stream + event ring
+  static thread_local OvlAux aux[64];
+  static thread_local bool have[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  dev &= 63;
+  if (!have[dev]) {
+    if (cudaStreamCreateWithFlags(&aux[dev].s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (auto &e : aux[dev].ev)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    have[dev] = true;
+  }
+  return &aux[dev];
+}
+static inline int ovl_env(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
 template <class M>
 struct ModelImpl {
@@ -3292,12 +3384,18 @@ struct ModelImpl {
     Dev dalt = d;
     if (compact) isls_carve(plan, B, (char *)ws, &d, &dalt);
     else d.orig = nullptr;
+    if constexpr (M::n < 9) {
+      static const int ovl = ovl_env("ISLS_OVERLAP", -1);      // -1 auto (>= 1,536 tiles), 0 off, 1 forced
+      const bool fuse_ok = !d.proj_x && d.proj_u && !no_fused_update();
+      if (ovl != 0 && !compact && !g_prof_on && fuse_ok && d.L <= 20 && (ovl == 1 || d.T >= 1536) && d.T >= 2)
+        return ilqr_admm_overlapped(d, x0, u_init, zs, s);
+    }
     {
       Dev dc = d;
       cudaStream_t cs = s;
       LAUNCH(ISLS_KC_INIT, cs, (k_init<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, x0, u_init, zs)));
       for (int j = 0; j < d.max_outer; j++) {
-        LAUNCH(ISLS_KC_KPASS, cs, (k_kpass<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc)));
+        LAUNCH(ISLS_KC_KPASS, cs, launch_kpass<M>(dc, cs));
         for (int a = 0; a < d.max_admm; a++) {
           const int fuse = (!d.proj_x && d.proj_u && !no_fused_update()) ? 1 : 0;      // streaming ADMM epilogue
           LAUNCH(ISLS_KC_FF, cs, launch_ff<M>(dc, cs));
@@ -3330,6 +3428,78 @@ struct ModelImpl {
     return ISLS_OK;
   }
 
+  // Overlapped form of the same launch sequence.  The tiles are split into two interleaved halves H0 (even tiles), H1
+  // (odd tiles) - two independent chains  K-pass, [ff, line search] x I_a, outer end, K-pass, ...  - and H1 runs one slot
+  // behind H0, so in every slot one half is in its FP64-bound step (line search, stream A) while the other is in its
+  // HBM-bound step (ff-pass; at outer boundaries outer end + K-pass + ff-pass; stream B).  A slot ends with an event
+  // barrier between the two streams.  Same kernels and arithmetic as the sequential schedule: results are bit-identical.
+  static int ilqr_admm_overlapped(Dev d, const double *x0, const double *u_init, const double *zs, cudaStream_t sA) {
+    OvlAux *aux = ovl_aux();
+    if (!aux) return fail(ISLS_E_INVALID, "could not create the side stream of the overlapped schedule");
+    cudaStream_t sB = aux->s;
+    static const int ls_ctas = ovl_env("ISLS_OVL_LS_CTAS", 2);       // resident line-search CTAs per SM
+    static const int ff_depth = ovl_env("ISLS_OVL_FF_DEPTH", 4);     // feed-forward ring depth (steps in flight + 1)
+    int dev = 0, sms = 148;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int evi = 0;
+    auto barrier = [&]() -> int {                              // both streams wait for each other
+      cudaEvent_t ea = aux->ev[evi & 7], eb = aux->ev[(evi + 1) & 7];
+      evi += 2;
+      CK(cudaEventRecord(ea, sA));
+      CK(cudaEventRecord(eb, sB));
+      CK(cudaStreamWaitEvent(sA, eb, 0));
+      CK(cudaStreamWaitEvent(sB, ea, 0));
+      return 0;
+    };
+    Dev h[2] = {d, d};
+    for (int q = 0; q < 2; q++) { h[q].tile0 = d.tile0 + q; h[q].tstep = 2; }
+    int *ctr = d.nact + 8;                                     // tile counter + exit count of the persistent line search
+    CK(cudaMemsetAsync(d.nact, 0, 64 * sizeof(int), sA));
+    k_init<M><<<tp_grid(d), tp_block(), 0, sA>>>(d, x0, u_init, zs);
+    if (barrier()) return 1;
+    const int I_a = d.max_admm, steps = 2 * d.max_outer * I_a + 1;   // per half: (HBM, LS) x I_o I_a, final outer end
+    auto hbm_step = [&](const Dev &dh, int i) -> int {         // stream B: [outer end j-1,] [K-pass j,] ff-pass (j, a)
+      const int j = i / I_a, a = i % I_a;
+      if (a == 0) {
+        if (j > 0) k_outer_end<M><<<tp_grid(dh), tp_block(), 0, sB>>>(dh, j - 1);
+        launch_kpass<M>(dh, sB);
+      }
+      bool done = false;
+      const int nt_ = n_tiles(dh);
+      int rc = 0;
+      if (ff_depth >= 6) rc = try_ff_tma<M, false, false, 1, 6>(dh, sB, nt_, sms, true, done);
+      else if (ff_depth == 5) rc = try_ff_tma<M, false, false, 1, 5>(dh, sB, nt_, sms, true, done);
+      else if (ff_depth == 4) rc = try_ff_tma<M, false, false, 1, 4>(dh, sB, nt_, sms, true, done);
+      else if (ff_depth == 3) rc = try_ff_tma<M, false, false, 1, 3>(dh, sB, nt_, sms, true, done);
+      else if (ff_depth > 0) rc = try_ff_tma<M, false, false, 2, 2>(dh, sB, nt_, sms, true, done);
+      if (rc) return rc;
+      if (!done) k_ff<M><<<tp_grid(dh), tp_block(), 0, sB>>>(dh);
+      return 0;
+    };
+    auto ls_step = [&](const Dev &dh, int i) {                 // stream A: line search + fused ADMM update (j, a)
+      const int j = i / I_a, a = i % I_a;
+      const int grid = std::min(n_tiles(dh), ls_ctas * sms);
+      if (ls_ctas > 0)
+        k_linesearch_pers<M, 5, 4, 3, false><<<grid, dim3(TILE, (dh.L + 4) / 5), 0, sA>>>(dh, 1, j, a, ctr);
+      else
+        k_linesearch<M, 5, 4, 3, false><<<n_tiles(dh), dim3(TILE, (dh.L + 4) / 5), 0, sA>>>(dh, 1, j, a);
+    };
+    for (int t = 0; t <= steps; t++) {                         // slot t: H0 does its step t, H1 its step t - 1
+      for (int q = 0; q < 2; q++) {
+        const int k = t - q;
+        if (k < 0 || k >= steps) continue;
+        if (k == steps - 1) k_outer_end<M><<<tp_grid(h[q]), tp_block(), 0, sB>>>(h[q], d.max_outer - 1);
+        else if (k & 1) ls_step(h[q], k / 2);
+        else if (hbm_step(h[q], k / 2)) return 1;
+      }
+      if (barrier()) return 1;
+    }
+    k_finalize<M><<<tp_grid(d), tp_block(), 0, sA>>>(d);
+    CK(cudaGetLastError());
+    return ISLS_OK;
+  }
+
   // iSLS.solve(method='dp') (isls/isls.py:54-132)
   static int ilqr(Dev d, const double *x0, const double *u_init, const double *zs, cudaStream_t s) {
     LAUNCH(ISLS_KC_INIT, s, (k_init<M><<<tp_grid(d), tp_block(), 0, s>>>(d, x0, u_init, zs)));
@@ -3349,7 +3519,7 @@ struct ModelImpl {
     const int rows = d.N * M::m, threads = ((rows + 31) / 32) * 32;
     LAUNCH(ISLS_KC_INIT, s, (k_init<M><<<tp_grid(d), tp_block(), 0, s>>>(d, x0, u_init, zs)));
     for (int j = 0; j < d.max_outer; j++) {
-      LAUNCH(ISLS_KC_KPASS, s, (k_kpass<M><<<tp_grid(d), tp_block(), 0, s>>>(d)));
+      LAUNCH(ISLS_KC_KPASS, s, launch_kpass<M>(d, s));
       k_isls_reset<M><<<tp_grid(d), tp_block(), 0, s>>>(d);
       for (int a = 0; a < d.max_admm; a++) {
         LAUNCH(ISLS_KC_FF, s, launch_ff<M>(d, s));
@@ -3430,8 +3600,84 @@ struct ModelImpl {
     return ISLS_OK;
   }
 
+  // Measurement helper (isls_probe_overlap_f64): durations of the two kernels of one slot of the overlapped schedule, each
+  // alone on its half of the tiles and both together on two streams.  ms[0] line search (one CTA per tile), ms[1]
+  // persistent line search with ls_ctas CTAs per SM, ms[2] TMA-staged ff-pass (ring depth ff_depth), ms[3] plain ff-pass,
+  // ms[4] persistent line search || TMA ff-pass, ms[5] plain line search || TMA ff-pass.  Best of 3, synchronous.
+  static int overlap_probe(Dev d, const double *x0, const double *u_init, const double *zs, cudaStream_t sA, int ls_ctas,
+                           int ff_depth, double *ms) {
+    if constexpr (M::n >= 9) {
+      return fail(ISLS_E_UNSUPPORTED, "overlap probe: car-sized models only");
+    } else {
+      OvlAux *aux = ovl_aux();
+      if (!aux) return fail(ISLS_E_INVALID, "could not create the side stream");
+      cudaStream_t sB = aux->s;
+      int dev = 0, sms = 148;
+      CK(cudaGetDevice(&dev));
+      CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      d.orig = nullptr;
+      Dev h[2] = {d, d};
+      for (int q = 0; q < 2; q++) { h[q].tile0 = d.tile0 + q; h[q].tstep = 2; }
+      int *ctr = d.nact + 8;
+      CK(cudaMemsetAsync(d.nact, 0, 64 * sizeof(int), sA));
+      k_init<M><<<tp_grid(d), tp_block(), 0, sA>>>(d, x0, u_init, zs);
+      launch_kpass<M>(d, sA);
+      k_ff<M><<<tp_grid(d), tp_block(), 0, sA>>>(d);
+      const dim3 lsb(TILE, (d.L + 4) / 5);
+      auto ls_plain = [&](cudaStream_t s) { k_linesearch<M, 5, 4, 3, false><<<n_tiles(h[0]), lsb, 0, s>>>(h[0], 1, 0, 0); };
+      auto ls_pers = [&](cudaStream_t s) {
+        k_linesearch_pers<M, 5, 4, 3, false><<<std::min(n_tiles(h[0]), std::max(1, ls_ctas) * sms), lsb, 0, s>>>(h[0], 1, 0, 0, ctr);
+      };
+      auto ff_tma = [&](cudaStream_t s) -> int {
+        bool done = false;
+        const int nt_ = n_tiles(h[1]);
+        if (ff_depth >= 6) return try_ff_tma<M, false, false, 1, 6>(h[1], s, nt_, sms, true, done);
+        if (ff_depth == 5) return try_ff_tma<M, false, false, 1, 5>(h[1], s, nt_, sms, true, done);
+        if (ff_depth == 4) return try_ff_tma<M, false, false, 1, 4>(h[1], s, nt_, sms, true, done);
+        if (ff_depth == 3) return try_ff_tma<M, false, false, 1, 3>(h[1], s, nt_, sms, true, done);
+        return try_ff_tma<M, false, false, 2, 2>(h[1], s, nt_, sms, true, done);
+      };
+      auto ff_plain = [&](cudaStream_t s) { k_ff<M><<<tp_grid(h[1]), tp_block(), 0, s>>>(h[1]); };
+      cudaEvent_t e0, e1;
+      CK(cudaEventCreate(&e0));
+      CK(cudaEventCreate(&e1));
+      auto timed = [&](int idx, auto &&fa, auto &&fb) -> int {      // fa on stream A, fb (may be empty) on stream B
+        double best = 1e30;
+        for (int rep = 0; rep < 4; rep++) {
+          CK(cudaStreamSynchronize(sA));
+          CK(cudaStreamSynchronize(sB));
+          CK(cudaEventRecord(e0, sA));
+          CK(cudaStreamWaitEvent(sB, e0, 0));
+          fa(sA);
+          fb(sB);
+          CK(cudaEventRecord(aux->ev[0], sB));
+          CK(cudaStreamWaitEvent(sA, aux->ev[0], 0));
+          CK(cudaEventRecord(e1, sA));
+          CK(cudaEventSynchronize(e1));
+          float t = 0.f;
+          CK(cudaEventElapsedTime(&t, e0, e1));
+          if (rep > 0 && t < best) best = t;
+        }
+        ms[idx] = best;
+        return 0;
+      };
+      auto none = [&](cudaStream_t) {};
+      auto fft = [&](cudaStream_t s) { ff_tma(s); };
+      if (timed(0, ls_plain, none)) return 1;
+      if (timed(1, ls_pers, none)) return 1;
+      if (timed(2, none, fft)) return 1;
+      if (timed(3, none, ff_plain)) return 1;
+      if (timed(4, ls_pers, fft)) return 1;
+      if (timed(5, ls_plain, fft)) return 1;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      CK(cudaGetLastError());
+      return ISLS_OK;
+    }
+  }
+
   static const isls_model_ops *ops() {
-    static const isls_model_ops o = {&ilqr_admm, &ilqr, &isls_admm, &lqt_admm, &rollout_linesearch};
+    static const isls_model_ops o = {&ilqr_admm, &ilqr, &isls_admm, &lqt_admm, &rollout_linesearch, &overlap_probe};
     return &o;
   }
 };

@@ -166,15 +166,30 @@ class BatchSolver:
         if want_masks:
             o.update(mask_x=torch.zeros(B_, N, n, dtype=torch.int8, device=dev),
                      mask_u=torch.zeros(B_, N, m, dtype=torch.int8, device=dev))
-        self.out = o
-        self._cout = _lib.SolveOut()
-        for f in _lib.OUT_FIELDS:
-            setattr(self._cout, f, _dptr(o.get(f)))
+        self._sets = [(o, self._make_cout(o))]
+        self.out, self._cout = self._sets[0]
         self.h2d_bytes = 0
         # device staging buffers for the inputs
         self.x0 = torch.empty(B_, n, **f64)
         self.u_init = torch.empty(B_, N, m, **f64)
         self.zs = torch.empty(B_, p.n_via, n, **f64)
+
+    @staticmethod
+    def _make_cout(o):
+        c = _lib.SolveOut()
+        for f in _lib.OUT_FIELDS:
+            setattr(c, f, _dptr(o.get(f)))
+        return c
+
+    def add_output_set(self):
+        """Second (third, ...) set of result buffers: a caller that copies results to the host on a side stream while the
+        next solve runs alternates between sets with use_output_set() (bench.py's end-to-end arm)."""
+        o = Result({k: torch.empty_like(v) for k, v in self._sets[0][0].items()})
+        self._sets.append((o, self._make_cout(o)))
+        return len(self._sets) - 1
+
+    def use_output_set(self, i):
+        self.out, self._cout = self._sets[i]
 
     # ---- input staging (host -> device copies happen here when host arrays are given)
     def _stage(self, dst, src, name):
@@ -217,6 +232,18 @@ class BatchSolver:
                                                      self._ws_bytes, C.byref(self._cout), self._stream())
         _lib.check(rc, "isls_ilqr_admm_solve_f64")
         return self.out
+
+    def probe_overlap(self, ls_ctas=2, ff_depth=4):
+        """Measurement helper (isls_probe_overlap_f64): ms of the line search / ff-pass of the two half batches alone and
+        together.  -> dict"""
+        o = self._opts(1e-3, 1e-3, 1.0, True, False)
+        ms = (C.c_double * 6)()
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().isls_probe_overlap_f64(self.plan.handle, C.byref(o), self.B, _dptr(self.x0), _dptr(self.u_init),
+                                                   _dptr(self.zs), C.c_void_p(self._ws_ptr), self._ws_bytes,
+                                                   C.byref(self._cout), int(ls_ctas), int(ff_depth), ms, self._stream())
+        _lib.check(rc, "isls_probe_overlap_f64")
+        return dict(zip(("ls_plain", "ls_pers", "ff_tma", "ff_plain", "ls_pers||ff_tma", "ls_plain||ff_tma"), list(ms)))
 
     def isls_admm(self, soc, tol=1e-3, relax=1.0, fixed_budget=False):
         """Robust iSLS-ADMM (isls_isls_admm_solve_f64; isls/isls.py:503-712).  soc: projections.SetConvexSOC.

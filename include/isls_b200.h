@@ -345,6 +345,13 @@ int isls_project_rows_f64(int32_t kind, int64_t rows, int32_t dim, const double 
 int isls_profile_enable(int on);
 /* synchronises, sums elapsed milliseconds and launch counts per kernel class ([ISLS_KC_COUNT] each), resets */
 int isls_profile_collect(double *ms_sum, int64_t *launches);
+/* durations (ms, best of 3; synchronous) of the two kernels of one slot of the overlapped large-batch schedule, each alone
+ * on its half of the tiles and both together: ms_host[6] = line search (CTA per tile), persistent line search with
+ * ls_ctas CTAs per SM, TMA-staged ff-pass with ring depth ff_depth, plain ff-pass, persistent line search || TMA
+ * ff-pass, plain line search || TMA ff-pass.  Arguments as isls_ilqr_admm_solve_f64. */
+int isls_probe_overlap_f64(const isls_plan *plan, const isls_solve_opts *opts, int64_t B, const double *x0_dev,
+                           const double *u_init_dev, const double *zs_dev, void *workspace_dev, size_t workspace_bytes,
+                           const isls_solve_out *out, int32_t ls_ctas, int32_t ff_depth, double *ms_host, void *stream);
 /* dependent-free DFMA throughput of the whole GPU in TFLOP/s (FMA = 2 flop), measured with CUDA events */
 int isls_measure_fp64_tflops(double *tflops, void *stream);
 

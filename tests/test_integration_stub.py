@@ -69,9 +69,9 @@ def test_stub_solves_car_problems_like_the_oracle():
     from oracle import problems as P, restated as R
     from isls_b200.solver import alphas
     p = P.car_batch(8, I_o=6, I_a=4)
+    assert p["zs"].ndim == 2, "the stub broadcasts one via-point set [k, n] over the batch"
     ref_like = types.SimpleNamespace(x_dim=4, u_dim=2, N=p["N"], Qs=[np.diag(q) for q in p["Qdiag"]], seq=p["seq"],
-                                     alphas=alphas(50), Rt=np.eye(2) * p["u_std"], zs=p["zs"][0])
-    assert np.all(p["zs"] == p["zs"][0]), "the stub broadcasts one via-point set over the batch"
+                                     alphas=alphas(50), Rt=np.eye(2) * p["u_std"], zs=p["zs"])
     x, u, cl = ns["ilqr_admm_b200"](ref_like, "car", p["dt"], p["x0"], p["u0"] if p["u0"].ndim == 3 else
                                     np.broadcast_to(p["u0"], (8,) + p["u0"].shape[-2:]), p["lo_u"], p["hi_u"], p["rho_u"],
                                     p["I_o"], p["I_a"], p["L"], p["tol"])
