@@ -3132,8 +3132,9 @@ static inline int ensure_dyn_smem(int bytes) {
   int dev = 0;
   CK(cudaGetDevice(&dev));
   const unsigned long long bit = 1ull << (dev & 63);
-  if (!(done & bit)) {
-    CK(cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  (void)bytes;                                 // opt in to the architectural maximum once: later launches of the same
+  if (!(done & bit)) {                         // kernel may ask for more (the plan-constant block grows with N)
+    CK(cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     done |= bit;
   }
   return 0;
@@ -3151,6 +3152,11 @@ static __global__ void k_fill_logs(double *res_log, int *alpha_idx, long long cn
 static inline int n_tiles(const Dev &d) { return (d.tile1 - d.tile0 + d.tstep - 1) / d.tstep; }   // tiles of this launch
 static dim3 tp_block() { return dim3(TILE, TPB_TILES); }
 static dim3 tp_grid(const Dev &d) { return dim3((n_tiles(d) + TPB_TILES - 1) / TPB_TILES); }
+
+static inline int ovl_env(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
 // k_ff_tma launcher for one ring shape: launches iff the ring fits an SM and (unless forced) all tiles are resident in
 // one wave.  Returns non-zero on a CUDA error; `launched` reports whether the kernel went out.
@@ -3197,6 +3203,23 @@ static int launch_ff(const Dev &d, cudaStream_t s) {
     ff_mode = e ? atoi(e) : -1;
     const char *j = getenv("ISLS_FF_JC");             // 0: recompute the Jacobian in the TMA kernels
     ff_jc = j ? atoi(j) : 1;
+  }
+  static const int ff_big = ovl_env("ISLS_FF_BIG", 22);   // >= 1,536 tiles: 0 plain k_ff, 22 / 13 / 12: k_ff_tma<TC, NST>
+  if (mode < 0 && ff_mode < 0 && tiles >= 1536 && ff_big > 0) {
+    // large batches: the TMA-staged kernel also beats the plain one when HBM-bound (65,536 car problems: 0.356 vs
+    // 0.389 ms; shallow rings = more resident single-warp CTAs per SM; profiles/r2_tuning_log.md), Jacobian recomputed
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    bool done = false;
+    auto big = [&](auto px) -> int {
+      constexpr bool PX_ = decltype(px)::value;
+      if (ff_big == 13) return try_ff_tma<M, PX_, false, 1, 3>(d, s, tiles, sms, true, done);
+      if (ff_big == 12) return try_ff_tma<M, PX_, false, 1, 2>(d, s, tiles, sms, true, done);
+      return try_ff_tma<M, PX_, false, 2, 2>(d, s, tiles, sms, true, done);
+    };
+    if (d.proj_x ? big(std::true_type{}) : big(std::false_type{})) return 1;
+    if (done) return 0;
   }
   if (mode < 0 && (ff_mode == 2 || (ff_mode < 0 && tiles < 1536))) {
     int dev = 0, sms = 148;
@@ -3366,10 +3389,6 @@ static inline OvlAux *ovl_aux() {                        // per host thread and 
   }
   return &aux[dev];
 }
-static inline int ovl_env(const char *name, int dflt) {
-  const char *e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
 
 template <class M>
 struct ModelImpl {
@@ -3385,9 +3404,11 @@ struct ModelImpl {
     if (compact) isls_carve(plan, B, (char *)ws, &d, &dalt);
     else d.orig = nullptr;
     if constexpr (M::n < 9) {
-      static const int ovl = ovl_env("ISLS_OVERLAP", -1);      // -1 auto (>= 1,536 tiles), 0 off, 1 forced
+      // experimental, off by default: measured slower than the sequential schedule (the line search needs the whole
+      // register file for its throughput, so the two kernels of a slot do not co-run; profiles/r2_tuning_log.md)
+      static const int ovl = ovl_env("ISLS_OVERLAP", 0);       // 0 off, 1 forced
       const bool fuse_ok = !d.proj_x && d.proj_u && !no_fused_update();
-      if (ovl != 0 && !compact && !g_prof_on && fuse_ok && d.L <= 20 && (ovl == 1 || d.T >= 1536) && d.T >= 2)
+      if (ovl == 1 && !compact && !g_prof_on && fuse_ok && d.L <= 20 && d.T >= 2)
         return ilqr_admm_overlapped(d, x0, u_init, zs, s);
     }
     {

@@ -220,7 +220,9 @@ class iSLS:
         # the solver state persists like the reference's (x_nom, u_nom): a following call continues from here
         self._x0 = out.x[:, 0].clone()
         self._u_init = out.u.clone()
-        sq = (lambda t: t[0]) if self.batch is None else (lambda t: t)
+        # published attributes are COPIES: the solver's result buffers (`out`, also returned by the solve methods and kept
+        # as self.last) are reused by the next solve on this object, the attributes a caller kept are not touched by it
+        sq = (lambda t: t[0].clone()) if self.batch is None else (lambda t: t.clone())
         self.x_nom, self.u_nom = sq(out.x), sq(out.u)
         self.cost = sq(out.cost)
         self.cost_log = sq(out.cost_log)
@@ -254,9 +256,11 @@ class iSLS:
         return (bool(ok[0]) if self.batch is None else ok), self._K, self._k
 
     def solve_ilqr(self, get_AB=None, max_ilqr_iter=100, max_line_search_iter=25, dp=True, verbose=False, **kw):
-        """Legacy spelling used by the notebooks (Car/Iterative LQR with state constraints.ipynb cell 13)."""
-        return self.solve(get_AB, method="dp", max_iter=max_ilqr_iter, max_line_search_iter=max_line_search_iter,
-                          verbose=verbose, **kw)
+        """Legacy spelling used by the notebooks (Car/Iterative LQR with state constraints.ipynb cell 13).  dp=False
+        asked the reference for its dense batch least-squares form (isls/isls.py:157-227): not built on the device -
+        raises like solve(method='batch') instead of silently running the DP form."""
+        return self.solve(get_AB, method="dp" if dp else "batch", max_iter=max_ilqr_iter,
+                          max_line_search_iter=max_line_search_iter, verbose=verbose, **kw)
 
     def ilqr_admm(self, get_AB=None, get_Cs=None, project_x=False, project_u=False, max_iter=20,
                   max_line_search_iter=20, max_admm_iter=20, rho_x=None, rho_u=None, alpha=1, tol=1e-3, verbose=False,

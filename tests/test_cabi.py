@@ -66,6 +66,8 @@ def test_host_mirror_argument_checks():
     # legacy spellings exist (README.md:24-39)
     assert s.set_cost_variables.__func__ is s.set_quadratic_cost.__func__
     assert hasattr(s, "solve_ilqr")
+    with pytest.raises(NotImplementedError):                # the dense batch form is not built: loud, not a silent DP run
+        s.solve_ilqr("car", dp=False)
 
 
 def test_ctypes_struct_layouts_match_the_header():
