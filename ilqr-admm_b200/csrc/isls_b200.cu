@@ -276,6 +276,7 @@ static int model_dims(int model_id, int n, int m, int *NJA) {
     case ISLS_MODEL_ARM3: if (n == 9 && m == 3) { *NJA = 6; return 0; } break;
     case ISLS_MODEL_TASSA_CAR: if (n == 4 && m == 2) { *NJA = 8; return 0; } break;
     case ISLS_MODEL_DOUBLE_INTEGRATOR:
+    case ISLS_MODEL_LTI:
       if ((n == 2 && m == 1) || (n == 4 && m == 2) || (n == 6 && m == 3)) { *NJA = 1; return 0; }
       break;
   }
@@ -288,9 +289,14 @@ static const isls_model_ops *ops_of(const isls_plan *p) {
     case ISLS_MODEL_ARM3: return isls_ops_arm3();
     case ISLS_MODEL_TASSA_CAR: return isls_ops_tassa_car();
     case ISLS_MODEL_DOUBLE_INTEGRATOR: return isls_ops_double_integrator(p->m);
+    case ISLS_MODEL_LTI: return isls_ops_lti(p->n, p->m);
   }
   return nullptr;
 }
+#define OPS_OR_FAIL(ops, plan, stream)                                              \
+  const isls_model_ops *ops = ops_of(plan);                                         \
+  if (!ops) return fail(ISLS_E_UNSUPPORTED, "unsupported model");                   \
+  if (ops->prepare && ops->prepare(plan, (cudaStream_t)(stream))) return 1
 
 extern "C" int isls_version(void) { return ISLS_VERSION; }
 extern "C" const char *isls_last_error_string(void) { return g_err.c_str(); }
@@ -301,6 +307,7 @@ extern "C" int isls_model_id(const char *name) {
   if (!strcmp(name, "car")) return ISLS_MODEL_CAR;
   if (!strcmp(name, "arm3")) return ISLS_MODEL_ARM3;
   if (!strcmp(name, "tassa_car")) return ISLS_MODEL_TASSA_CAR;
+  if (!strcmp(name, "lti")) return ISLS_MODEL_LTI;
   return fail(ISLS_E_UNSUPPORTED, std::string("unknown model: ") + name);
 }
 
@@ -332,8 +339,14 @@ extern "C" int isls_plan_create(const isls_problem_desc *desc, isls_plan **plan)
   const int n = desc->n, m = desc->m, N = desc->N;
   for (int t = 0; t < N; t++)
     if (desc->seq[t] < 0 || desc->seq[t] >= desc->n_via) return fail(ISLS_E_INVALID, "seq entry out of range");
+  if (desc->model_id == ISLS_MODEL_LTI && (!desc->lti_A || !desc->lti_B)) return fail(ISLS_E_INVALID, "the lti model needs lti_A and lti_B");
   isls_plan *p = new isls_plan();
   p->desc = *desc;
+  memset(p->lti, 0, sizeof(p->lti));
+  if (desc->model_id == ISLS_MODEL_LTI) {
+    memcpy(p->lti, desc->lti_A, sizeof(double) * desc->n * desc->n);
+    memcpy(p->lti + 36, desc->lti_B, sizeof(double) * desc->n * desc->m);
+  }
   p->n = n; p->m = m; p->N = N; p->n_via = desc->n_via; p->L = desc->L; p->NJA = nja;
   p->proj_x = desc->rho_x != nullptr;
   p->proj_u = desc->rho_u != nullptr;
@@ -512,8 +525,7 @@ extern "C" int isls_ilqr_admm_solve_f64(const isls_plan *plan, const isls_solve_
   if (rc) return rc;
   d.lsc = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
-  const isls_model_ops *ops = ops_of(plan);
-  if (!ops) return fail(ISLS_E_UNSUPPORTED, "unsupported model");
+  OPS_OR_FAIL(ops, plan, stream);
   return ops->ilqr_admm(plan, d, B, x0, u_init, zs, ws, s);
 }
 
@@ -534,8 +546,7 @@ extern "C" int isls_ilqr_solve_f64(const isls_plan *plan, const isls_solve_opts 
   d.out.admm_exit = nullptr;
   d.out.inner_iters = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
-  const isls_model_ops *ops = ops_of(plan);
-  if (!ops) return fail(ISLS_E_UNSUPPORTED, "unsupported model");
+  OPS_OR_FAIL(ops, plan, stream);
   return ops->ilqr(d, x0, u_init, zs, s);
 }
 
@@ -565,8 +576,7 @@ extern "C" int isls_isls_admm_solve_f64(const isls_plan *plan, const isls_solve_
   soc_set_build(&S, soc->n_cones, C, soc->cone_rows, soc->As, soc->bs, soc->inner_rho, soc->inner_max_iter,
                 soc->inner_threshold);
   cudaStream_t s = (cudaStream_t)stream;
-  const isls_model_ops *ops = ops_of(plan);
-  if (!ops) return fail(ISLS_E_UNSUPPORTED, "unsupported model");
+  OPS_OR_FAIL(ops, plan, stream);
   return ops->isls_admm(d, S, B, x0, u_init, zs, du_dev, phi_u_dev, s);
 }
 
@@ -576,8 +586,8 @@ extern "C" int isls_lqt_admm_dp_f64(const isls_plan *plan, const isls_solve_opts
   if (!opts || !out || !x0 || !zs) return fail(ISLS_E_INVALID, "NULL argument");
   ABI_CHECK(opts, isls_solve_opts);
   ABI_CHECK(out, isls_solve_out);
-  if (plan && plan->desc.model_id != ISLS_MODEL_DOUBLE_INTEGRATOR)
-    return fail(ISLS_E_UNSUPPORTED, "LQT-ADMM needs a linear model (double_integrator)");
+  if (plan && plan->desc.model_id != ISLS_MODEL_DOUBLE_INTEGRATOR && plan->desc.model_id != ISLS_MODEL_LTI)
+    return fail(ISLS_E_UNSUPPORTED, "LQT-ADMM needs a linear model (double_integrator or lti)");
   if (plan && plan->desc.cost_kind != ISLS_COST_QUADRATIC)
     return fail(ISLS_E_UNSUPPORTED, "LQT-ADMM needs the quadratic via-point cost");
   if (plan && plan->desc.n_obst > 0 && (plan->desc.obst_kind != 1 || plan->n < 4))
@@ -589,8 +599,7 @@ extern "C" int isls_lqt_admm_dp_f64(const isls_plan *plan, const isls_solve_opts
   int rc = setup(plan, &o, B, ws, ws_bytes, out, &d);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  const isls_model_ops *ops = ops_of(plan);
-  if (!ops) return fail(ISLS_E_UNSUPPORTED, "unsupported model");
+  OPS_OR_FAIL(ops, plan, stream);
   return ops->lqt_admm(d, opts, B, x0, zs, s);
 }
 
@@ -628,8 +637,7 @@ extern "C" int isls_rollout_linesearch_f64(const isls_plan *plan, int64_t B, con
   if (d.proj_x && !reg_x) return fail(ISLS_E_INVALID, "plan has a state projection: reg_x required");
   if (d.proj_u && !reg_u) return fail(ISLS_E_INVALID, "plan has a control projection: reg_u required");
   cudaStream_t s = (cudaStream_t)stream;
-  const isls_model_ops *ops = ops_of(plan);
-  if (!ops) return fail(ISLS_E_UNSUPPORTED, "unsupported model");
+  OPS_OR_FAIL(ops, plan, stream);
   return ops->rollout_linesearch(d, x_nom, u_nom, du, zs, reg_x, reg_u, costs, best, x_best, u_best, s);
 }
 
@@ -654,8 +662,7 @@ extern "C" int isls_probe_overlap_f64(const isls_plan *plan, const isls_solve_op
   if (rc) return rc;
   if (d.proj_x || !d.proj_u || d.L > 20 || d.T < 2) return fail(ISLS_E_UNSUPPORTED, "overlap probe: control-only projection, L <= 20");
   d.lsc = nullptr;
-  const isls_model_ops *ops = ops_of(plan);
-  if (!ops) return fail(ISLS_E_UNSUPPORTED, "unsupported model");
+  OPS_OR_FAIL(ops, plan, stream);
   return ops->overlap_probe(d, x0, u_init, zs, (cudaStream_t)stream, ls_ctas, ff_depth, ms_host);
 }
 

@@ -2129,7 +2129,7 @@ static void launch_isls_cols(const Dev &d, cudaStream_t s) {
 // ADMM update on the matrix variable (isls.py:628-654): one CTA per problem, thread r = row (t, j) of
 // [d_u | Phi_u(:, :dim)]; z = project_u(alpha x + (1 - alpha) z + lambda, u_nom) with the notebook's closure (column 0
 // shifted by u_nom, project_set_convex over the SOC set, shifted back), lambda += x - z, residuals weighted by Rr.
-template <class M>
+template <class M, int CP = 0, int CC = 0, int CR = 0>
 __global__ void k_isls_update(Dev d, SocSet S, int outer, int inner) {
   constexpr int m = M::m;
   __shared__ double red[32];
@@ -2137,7 +2137,7 @@ __global__ void k_isls_update(Dev d, SocSet S, int outer, int inner) {
   const int tile = (int)(b / TILE), lane = (int)(b % TILE);
   TileCtx<M> c(d, tile, lane);
   if (!c.valid || d.odone[c.b] || d.adone[c.b]) return;               // uniform over the CTA
-  const int C = d.isls_C, r = threadIdx.x, rows = d.N * m;
+  const int C = CC ? CC : d.isls_C, r = threadIdx.x, rows = d.N * m;
   const bool act = r < rows;
   const int t = act ? r / m : 0, j = act ? r % m : 0;
   const double *uh = c.at(d.uh, d, m), *du = c.at(d.du, d, m);
@@ -2149,16 +2149,16 @@ __global__ void k_isls_update(Dev d, SocSet S, int outer, int inner) {
     un = EL(uh, m, t, j);
     rho = d.rho_u[t * m + j];
     xu[0] = d.alphas[bi] * EL(du, m, t, j);                           // isls.py:602-603
-    for (int q = 1; q < C; q++) xu[q] = EL(Xu, m * C, t, j * C + q);
-    for (int q = 0; q < C; q++) { z[q] = EL(Zm, m * C, t, j * C + q); lm[q] = EL(Lm, m * C, t, j * C + q); }
-    for (int q = 0; q < C; q++) y[q] = (d.relax * xu[q] + (1.0 - d.relax) * z[q]) + lm[q];
+    _Pragma("unroll") for (int q = 1; q < C; q++) xu[q] = EL(Xu, m * C, t, j * C + q);
+    _Pragma("unroll") for (int q = 0; q < C; q++) { z[q] = EL(Zm, m * C, t, j * C + q); lm[q] = EL(Lm, m * C, t, j * C + q); }
+    _Pragma("unroll") for (int q = 0; q < C; q++) y[q] = (d.relax * xu[q] + (1.0 - d.relax) * z[q]) + lm[q];
     y[0] += un;                                                       // notebook cell 25
   }
-  const int its = soc_project_set(S, S.b, y, zn, act, red);
+  const int its = soc_project_set<CP, CC, CR>(S, S.b, y, zn, act, red);
   double ps = 0.0, ds = 0.0;
   if (act) {
     zn[0] -= un;
-    for (int q = 0; q < C; q++) {
+    _Pragma("unroll") for (int q = 0; q < C; q++) {
       const double pr = xu[q] - zn[q], dz = zn[q] - z[q];
       lm[q] += pr;
       ps = fma(rho * pr, rho * pr, ps);
@@ -3118,6 +3118,7 @@ struct isls_plan {
   int n, m, N, n_via, L, NJA;
   bool proj_x, proj_u;
   void *cblock;             // device constant block
+  double lti[54];           // ISLS_MODEL_LTI: A [n, n] then B [n, m] at offset 36 (host copy, uploaded per launch sequence)
   Dev base;                 // constants filled in
 };
 
@@ -3361,11 +3362,13 @@ struct isls_model_ops {
                             double *u_best, cudaStream_t s);
   int (*overlap_probe)(Dev d, const double *x0, const double *u_init, const double *zs, cudaStream_t s, int ls_ctas,
                        int ff_depth, double *ms);
+  int (*prepare)(const isls_plan *plan, cudaStream_t s);   // NULL, or stream-ordered set-up before a launch sequence (LTI)
 };
 const isls_model_ops *isls_ops_car();
 const isls_model_ops *isls_ops_arm3();
 const isls_model_ops *isls_ops_tassa_car();
 const isls_model_ops *isls_ops_double_integrator(int m);
+const isls_model_ops *isls_ops_lti(int n, int m);
 
 // ---- overlapped schedule (large batches, control-only projections): the FP64-bound line search of one half of the
 // tiles runs concurrently with the HBM-bound kernels (feed-forward pass; outer end + K-pass at outer boundaries) of the
@@ -3546,7 +3549,12 @@ struct ModelImpl {
         LAUNCH(ISLS_KC_FF, s, launch_ff<M>(d, s));
         LAUNCH(ISLS_KC_LINESEARCH, s, launch_linesearch<M>(d, false, s, LsFuse{0, j, a}));
         LAUNCH(ISLS_KC_ISLS_COLS, s, launch_isls_cols<M>(d, s));
-        LAUNCH(ISLS_KC_ISLS_UPDATE, s, (k_isls_update<M><<<(unsigned)B, threads, 0, s>>>(d, S, j, a)));
+        {
+          ProfScope ps__(ISLS_KC_ISLS_UPDATE, s);
+          if (S.P == 2 && S.c == 4 && S.ra == 5) k_isls_update<M, 2, 4, 5><<<(unsigned)B, threads, 0, s>>>(d, S, j, a);   // dim = 3
+          else if (S.P == 2 && S.c == 3 && S.ra == 4) k_isls_update<M, 2, 3, 4><<<(unsigned)B, threads, 0, s>>>(d, S, j, a);
+          else k_isls_update<M><<<(unsigned)B, threads, 0, s>>>(d, S, j, a);
+        }
       }
       LAUNCH(ISLS_KC_OUTER_END, s, (k_outer_end<M><<<tp_grid(d), tp_block(), 0, s>>>(d, j)));
     }
@@ -3698,7 +3706,7 @@ struct ModelImpl {
   }
 
   static const isls_model_ops *ops() {
-    static const isls_model_ops o = {&ilqr_admm, &ilqr, &isls_admm, &lqt_admm, &rollout_linesearch, &overlap_probe};
+    static const isls_model_ops o = {&ilqr_admm, &ilqr, &isls_admm, &lqt_admm, &rollout_linesearch, &overlap_probe, nullptr};
     return &o;
   }
 };

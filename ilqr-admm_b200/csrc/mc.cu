@@ -13,6 +13,7 @@
 #include "../../include/isls_b200.h"
 #include "common.cuh"
 #include "models.cuh"
+#include "soc.cuh"
 
 __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                                            uint32_t (&out)[4]) {
@@ -187,6 +188,179 @@ extern "C" int isls_project_rows_f64(int32_t kind, int64_t rows, int32_t dim, co
   if (kind == 3 && dim < 2) return isls_fail(ISLS_E_INVALID, "soc_unit needs dim >= 2");
   k_project_rows<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(kind, rows, dim, x_dev, p0_dev, p1_dev, l, u,
                                                                                    out_dev);
+  CK(cudaGetLastError());
+  return ISLS_OK;
+}
+
+// ------------------------------------------------------------------ batched row projections, parameterised (8f #2)
+// project_multilinear (isls/projections.py:46-62), project_soc (163-232: general cone A z + b in SOC by an inner ADMM whose
+// stop rule is a maximum over ALL rows - one CTA, one row per thread), project_block_lower_triangular (277-286).
+#define PROJ_MAXK 8
+struct ProjEx {
+  int k, dim, max_iter;
+  double A[PROJ_MAXK][PROJ_MAXD];
+  double b[PROJ_MAXK], l[PROJ_MAXK], u[PROJ_MAXK];
+  double inv[PROJ_MAXD][PROJ_MAXD];      // multilinear: (A A')^-1 [k, k]; soc: (I + rho A'A)^-1 [dim, dim]
+  double rho, tol;
+};
+
+__global__ void k_project_multilinear(ProjEx P, long long rows, const double *x, double *out) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  double v[PROJ_MAXD], d[PROJ_MAXK], mu[PROJ_MAXK];
+  for (int i = 0; i < P.dim; i++) v[i] = x[r * P.dim + i];
+  for (int a = 0; a < P.k; a++) {
+    double ax = 0.0;
+    for (int i = 0; i < P.dim; i++) ax += P.A[a][i] * v[i];
+    double t = ax;
+    if (ax > P.u[a]) t = P.u[a];
+    if (ax < P.l[a]) t = P.l[a];                       // the later mask wins, like the numpy code
+    d[a] = ax - t;
+  }
+  for (int a = 0; a < P.k; a++) {
+    double m = 0.0;
+    for (int c = 0; c < P.k; c++) m += P.inv[a][c] * d[c];
+    mu[a] = m;
+  }
+  for (int i = 0; i < P.dim; i++) {
+    double c = 0.0;
+    for (int a = 0; a < P.k; a++) c += P.A[a][i] * mu[a];
+    out[r * P.dim + i] = v[i] - c;
+  }
+}
+
+__global__ void k_project_soc(ProjEx P, int rows, const double *x, double *out, int *iters) {
+  __shared__ double red[32];
+  const int r = threadIdx.x;
+  const bool act = r < rows;
+  const int n = P.dim, k = P.k;
+  double z0[PROJ_MAXD], z[PROJ_MAXD], xs[PROJ_MAXK], lm[PROJ_MAXK], y[PROJ_MAXK], azb[PROJ_MAXK];
+  for (int i = 0; i < n; i++) { z0[i] = act ? x[(size_t)r * n + i] : 0.0; z[i] = z0[i]; }
+  for (int a = 0; a < k; a++) lm[a] = 0.0;
+  double pm = 1e5, dm = 1e5;
+  int it = 0;
+  for (int j = 0; j < P.max_iter; j++) {
+    it = j + 1;
+    for (int a = 0; a < k; a++) {
+      double s = P.b[a];
+      for (int i = 0; i < n; i++) s += P.A[a][i] * z[i];
+      y[a] = s + lm[a];
+    }
+    soc_unit_row(k - 1, y, xs);                           // x = project_soc_unit(A z + b + lambda)
+    double zp[PROJ_MAXD], rs[PROJ_MAXD];
+    for (int i = 0; i < n; i++) {
+      zp[i] = z[i];
+      double s = 0.0;
+      for (int a = 0; a < k; a++) s += P.A[a][i] * ((-P.b[a] + xs[a]) - lm[a]);
+      rs[i] = z0[i] + P.rho * s;
+    }
+    for (int i = 0; i < n; i++) {
+      double s = 0.0;
+      for (int c = 0; c < n; c++) s += P.inv[i][c] * rs[c];
+      z[i] = s;
+    }
+    double ps = 0.0, ds = 0.0;
+    for (int a = 0; a < k; a++) {
+      double s = P.b[a];
+      for (int i = 0; i < n; i++) s += P.A[a][i] * z[i];
+      azb[a] = s;
+      const double pr = s - xs[a];
+      ps += pr * pr;
+      lm[a] += pr;
+    }
+    for (int i = 0; i < n; i++) { const double dv = P.rho * (z[i] - zp[i]); ds += dv * dv; }
+    const double pprev = pm, dprev = dm;
+    pm = block_max(act ? sqrt(ps) : 0.0, red);
+    dm = block_max(act ? sqrt(ds) : 0.0, red);
+    if (pm < P.tol && dm < P.tol) break;
+    if (j < P.max_iter - 1) {
+      const double pc = fabs(pprev - pm) / (pprev + 1e-30), dc = fabs(dprev - dm) / (dprev + 1e-30);
+      if (pc < 1e-5 && dc < 1e-5) break;
+    }
+  }
+  if (act)
+    for (int i = 0; i < n; i++) out[(size_t)r * n + i] = z[i];
+  if (iters && r == 0) iters[0] = it;
+}
+
+__global__ void k_project_blt(double *z, int x_dim, int u_dim, int N) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= N * x_dim) return;
+  const int i = q / x_dim, c = q % x_dim;
+  z[(size_t)(i * u_dim) * ((size_t)N * x_dim) + (size_t)i * x_dim + c] = 0.0;
+}
+
+static bool gauss_jordan_inv(int n, const double *Min, double (*out)[PROJ_MAXD]) {
+  double Mx[PROJ_MAXD][2 * PROJ_MAXD] = {};
+  for (int a = 0; a < n; a++)
+    for (int c = 0; c < n; c++) { Mx[a][c] = Min[a * n + c]; Mx[a][n + c] = a == c ? 1.0 : 0.0; }
+  for (int col = 0; col < n; col++) {
+    int piv = col;
+    for (int r2 = col + 1; r2 < n; r2++) if (fabs(Mx[r2][col]) > fabs(Mx[piv][col])) piv = r2;
+    if (Mx[piv][col] == 0.0) return false;
+    for (int q = 0; q < 2 * n; q++) std::swap(Mx[col][q], Mx[piv][q]);
+    const double d = Mx[col][col];
+    for (int q = 0; q < 2 * n; q++) Mx[col][q] /= d;
+    for (int r2 = 0; r2 < n; r2++)
+      if (r2 != col) {
+        const double f = Mx[r2][col];
+        for (int q = 0; q < 2 * n; q++) Mx[r2][q] -= f * Mx[col][q];
+      }
+  }
+  for (int a = 0; a < n; a++)
+    for (int c = 0; c < n; c++) out[a][c] = Mx[a][n + c];
+  return true;
+}
+
+extern "C" int isls_project_rows_ex_f64(const isls_proj_params *pp, int64_t rows, int32_t dim, const double *x_dev,
+                                        double *out_dev, int32_t *iters_dev, void *stream) {
+  if (!pp) return isls_fail(ISLS_E_INVALID, "params is NULL");
+  if (pp->struct_size != (uint32_t)sizeof(isls_proj_params))
+    return isls_fail(ISLS_E_INVALID, "isls_proj_params.struct_size mismatch (binding built against another isls_b200.h?)");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (pp->kind == ISLS_PROJ_BLOCK_LOWER_TRIANGULAR) {
+    if (!out_dev || pp->x_dim < 1 || pp->u_dim < 1 || pp->N < 1) return isls_fail(ISLS_E_INVALID, "bad size or NULL argument");
+    const int tot = pp->N * pp->x_dim;
+    k_project_blt<<<(tot + 127) / 128, 128, 0, s>>>(out_dev, pp->x_dim, pp->u_dim, pp->N);
+    CK(cudaGetLastError());
+    return ISLS_OK;
+  }
+  if (rows <= 0 || dim < 1 || dim > PROJ_MAXD || !x_dev || !out_dev) return isls_fail(ISLS_E_INVALID, "bad size or NULL argument");
+  if (pp->k < 1 || pp->k > PROJ_MAXK || !pp->A) return isls_fail(ISLS_E_INVALID, "A missing or k out of range (1..8)");
+  ProjEx P;
+  memset(&P, 0, sizeof(P));
+  P.k = pp->k; P.dim = dim; P.max_iter = pp->max_iter; P.rho = pp->rho; P.tol = pp->tol;
+  for (int a = 0; a < P.k; a++) {
+    for (int i = 0; i < dim; i++) P.A[a][i] = pp->A[a * dim + i];
+    P.b[a] = pp->b ? pp->b[a] : 0.0;
+    P.l[a] = pp->l ? pp->l[a] : -INFINITY;
+    P.u[a] = pp->u ? pp->u[a] : INFINITY;
+  }
+  if (pp->kind == ISLS_PROJ_MULTILINEAR) {
+    double AAT[PROJ_MAXK * PROJ_MAXK];
+    for (int a = 0; a < P.k; a++)
+      for (int c = 0; c < P.k; c++) {
+        double v = 0.0;
+        for (int i = 0; i < dim; i++) v += P.A[a][i] * P.A[c][i];
+        AAT[a * P.k + c] = v;
+      }
+    if (!gauss_jordan_inv(P.k, AAT, P.inv)) return isls_fail(ISLS_E_INVALID, "A A' is singular");
+    k_project_multilinear<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(P, rows, x_dev, out_dev);
+  } else if (pp->kind == ISLS_PROJ_SOC) {
+    if (rows > 1024) return isls_fail(ISLS_E_UNSUPPORTED, "project_soc: the stop rule couples all rows; rows <= 1024");
+    if (P.k < 2 || P.max_iter < 1) return isls_fail(ISLS_E_INVALID, "project_soc needs k >= 2 and max_iter >= 1");
+    double Lm[PROJ_MAXD * PROJ_MAXD];
+    for (int i = 0; i < dim; i++)
+      for (int c = 0; c < dim; c++) {
+        double v = i == c ? 1.0 : 0.0;
+        for (int a = 0; a < P.k; a++) v += P.rho * P.A[a][i] * P.A[a][c];
+        Lm[i * dim + c] = v;
+      }
+    if (!gauss_jordan_inv(dim, Lm, P.inv)) return isls_fail(ISLS_E_INVALID, "I + rho A'A is singular");
+    k_project_soc<<<1, (unsigned)(((rows + 31) / 32) * 32), 0, s>>>(P, (int)rows, x_dev, out_dev, iters_dev);
+  } else {
+    return isls_fail(ISLS_E_UNSUPPORTED, "unknown projection kind");
+  }
   CK(cudaGetLastError());
   return ISLS_OK;
 }

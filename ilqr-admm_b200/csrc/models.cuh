@@ -420,3 +420,48 @@ struct DoubleIntModel {
     for (int i = 0; i < D; i++) { A[i][i + D] = dt; B[i][i] = h; B[D + i][i] = dt; }
   }
 };
+
+// Generic linear time-invariant model x+ = A x + B u with arbitrary constant A [n, n], B [n, m] (Base.AB of the reference
+// takes any pair, isls/base.py:98-119; SLS.ADMM_LQT_DP, isls/sls.py:298-317).  The matrices live in constant memory of
+// the translation unit that instantiates the model's kernels (isls_model_lti.cu) and are uploaded, stream-ordered,
+// before every launch sequence - one LTI plan per device in flight at a time.
+struct LtiConst { double A[36]; double B[18]; };
+static __constant__ LtiConst c_lti;
+template <int N_, int M_>
+struct LtiModel {
+  static constexpr int n = N_, m = M_, NJ = 0, NJA = 1;
+  __host__ __device__ static constexpr int am(int, int) { return MV; }
+  __host__ __device__ static constexpr int bm(int, int) { return MV; }
+  __device__ __forceinline__ static void step(const double (&x)[n], const double (&u)[m], double (&xn)[n], double) {
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int j = 0; j < n; j++) a = fma(c_lti.A[i * n + j], x[j], a);
+#pragma unroll
+      for (int j = 0; j < m; j++) b = fma(c_lti.B[i * m + j], u[j], b);
+      xn[i] = a + b;                                   // x.dot(A.T) + u.dot(B.T), isls/sls_base.py:49-53
+    }
+  }
+  __device__ __forceinline__ static bool fast_state(const double (&)[n]) { return true; }
+  template <int K>
+  __device__ __forceinline__ static void steps_fast(double (&x)[K][n], const double (&u)[K][m], double dt, bool (&)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      double xn[n];
+      step(x[k], u[k], xn, dt);
+#pragma unroll
+      for (int i = 0; i < n; i++) x[k][i] = xn[i];
+    }
+  }
+  __device__ __forceinline__ static void jac(const double (&)[n], const double (&)[m], double (&)[1], double) {}
+  __device__ __forceinline__ static void expand(const double (&)[1], double (&A)[n][n], double (&B)[n][m], double) {
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+#pragma unroll
+      for (int j = 0; j < n; j++) A[i][j] = c_lti.A[i * n + j];
+#pragma unroll
+      for (int j = 0; j < m; j++) B[i][j] = c_lti.B[i * m + j];
+    }
+  }
+};

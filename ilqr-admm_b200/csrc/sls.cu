@@ -15,6 +15,7 @@
 //   * controller: PHI_X = Sw + Su PHI_U is unit block lower triangular, so K = PHI_U PHI_X^-1 is a block
 //     back-substitution per problem (the reference forms a dense LU inverse of (N n)^2).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -215,13 +216,15 @@ struct SlsAdmm {
 };
 
 // One CTA per problem, thread r = row r of [d_u | Phi_u(:, :c-1)]   (sls.py:372-447 + projections.py:289-374)
+// CP, CC, CR: compile-time cone-set shape (0: run time), see soc_project_set
+template <int CP, int CC, int CR>
 __global__ void k_sls_admm(SlsAdmm a, SocSet S, SocRowsX X) {
   extern __shared__ double sh[];
   double *rhs = sh;                         // [Nm][c] right-hand side of the current iteration, then x_u
   double *red = sh + (size_t)a.Nm * a.c;    // reduction scratch [32]
   double *zxs = red + 32;                   // [nx][c] z_x - lambda_x of the projected state rows (reg_x)
   double zx[SOC_MAXC] = {}, lx[SOC_MAXC] = {};           // thread i < nx owns state row X.row[i]
-  const int b = blockIdx.x, r = threadIdx.x, c = a.c;
+  const int b = blockIdx.x, r = threadIdx.x, c = CC ? CC : a.c;
   const bool act = r < a.Nm;
   // r_side row: column 0 = (Su'Q xd)[r], columns 1.. = -Su'Q Sx (shared)
   double rs[SOC_MAXC] = {}, z[SOC_MAXC] = {}, lm[SOC_MAXC] = {}, xu[SOC_MAXC] = {};
@@ -230,16 +233,16 @@ __global__ void k_sls_admm(SlsAdmm a, SocSet S, SocRowsX X) {
     const double *xd = a.xd + (size_t)b * a.Nn;
     for (int k = 0; k < a.Nn; k++) acc = fma(a.DTQ[(size_t)r * a.Nn + k], xd[k], acc);
     rs[0] = acc;
-    for (int q = 1; q < c; q++) rs[q] = a.rfb[(size_t)r * (c - 1) + q - 1];
+    _Pragma("unroll") for (int q = 1; q < c; q++) rs[q] = a.rfb[(size_t)r * (c - 1) + q - 1];
   }
   double prim = 1e6, dual = 1e6;
   int ex = 0, it = 0;
   long long inner = 0;
   for (it = 0; it < a.max_iter && !ex; it++) {
     // x_u = l_inv (r_side + Rr (z - lambda))                                   sls.py:372-380
-    if (r < X.nx) for (int q = 0; q < c; q++) zxs[r * c + q] = zx[q] - lx[q];
+    if (r < X.nx) _Pragma("unroll") for (int q = 0; q < c; q++) zxs[r * c + q] = zx[q] - lx[q];
     __syncthreads();
-    if (act) for (int q = 0; q < c; q++) {
+    if (act) _Pragma("unroll") for (int q = 0; q < c; q++) {
       double v = rs[q] + a.rho_u * (z[q] - lm[q]);
       for (int i = 0; i < X.nx; i++)                     // + Su'Qr reg_x (sls.py:371): Qr is zero off the listed rows
         v = fma(X.qr[i] * a.Su[(size_t)X.row[i] * a.Nm + r], zxs[i * c + q], v);
@@ -251,15 +254,15 @@ __global__ void k_sls_admm(SlsAdmm a, SocSet S, SocRowsX X) {
       const double *row = a.linv + (size_t)r * a.Nm;
       for (int k = 0; k < a.Nm; k++) {
         const double l = row[k];
-        for (int q = 0; q < c; q++) acc[q] = fma(l, rhs[k * c + q], acc[q]);
+        _Pragma("unroll") for (int q = 0; q < c; q++) acc[q] = fma(l, rhs[k * c + q], acc[q]);
       }
-      for (int q = 0; q < c; q++) xu[q] = acc[q];
+      _Pragma("unroll") for (int q = 0; q < c; q++) xu[q] = acc[q];
     }
     double psx = 0.0, dsx = 0.0;
     if (X.nx > 0) {
       // ---- state side: x_x = Su x_u (+ Sx on the feedback columns) at the listed rows, own projection each
       __syncthreads();
-      if (act) for (int q = 0; q < c; q++) rhs[r * c + q] = xu[q];
+      if (act) _Pragma("unroll") for (int q = 0; q < c; q++) rhs[r * c + q] = xu[q];
       __syncthreads();
       int xin = 0;
       if (r < X.nx) {
@@ -267,12 +270,12 @@ __global__ void k_sls_admm(SlsAdmm a, SocSet S, SocRowsX X) {
         const double *su = a.Su + (size_t)X.row[r] * a.Nm;
         for (int k = 0; k < a.Nm; k++) {
           const double sv_ = su[k];
-          for (int q = 0; q < c; q++) xx[q] = fma(sv_, rhs[k * c + q], xx[q]);
+          _Pragma("unroll") for (int q = 0; q < c; q++) xx[q] = fma(sv_, rhs[k * c + q], xx[q]);
         }
-        for (int q = 1; q < c; q++) xx[q] += a.Sw[(size_t)X.row[r] * a.Nn + q - 1];              // sls.py:381-382
-        for (int q = 0; q < c; q++) y[q] = (a.alpha * xx[q] + (1.0 - a.alpha) * zx[q]) + lx[q];
-        xin = soc_project_set(S, X.b[r], y, zn, true, nullptr);
-        for (int q = 0; q < c; q++) {
+        _Pragma("unroll") for (int q = 1; q < c; q++) xx[q] += a.Sw[(size_t)X.row[r] * a.Nn + q - 1];              // sls.py:381-382
+        _Pragma("unroll") for (int q = 0; q < c; q++) y[q] = (a.alpha * xx[q] + (1.0 - a.alpha) * zx[q]) + lx[q];
+        xin = soc_project_set<CP, CC, CR>(S, X.b[r], y, zn, true, nullptr);
+        _Pragma("unroll") for (int q = 0; q < c; q++) {
           const double pr = xx[q] - zn[q], dz = zn[q] - zx[q];
           lx[q] += pr;
           zx[q] = zn[q];
@@ -284,11 +287,11 @@ __global__ void k_sls_admm(SlsAdmm a, SocSet S, SocRowsX X) {
     }
     // ---- z = project_set_convex(alpha x + (1-alpha) z + lambda)               sls.py:403-405
     double x0[SOC_MAXC], x[SOC_MAXC];
-    for (int q = 0; q < c; q++) x0[q] = (a.alpha * xu[q] + (1.0 - a.alpha) * z[q]) + lm[q];
-    inner += soc_project_set(S, S.b, x0, x, act, red);
+    _Pragma("unroll") for (int q = 0; q < c; q++) x0[q] = (a.alpha * xu[q] + (1.0 - a.alpha) * z[q]) + lm[q];
+    inner += soc_project_set<CP, CC, CR>(S, S.b, x0, x, act, red);
     // ---- dual update and residuals (sls.py:406-418), Rr = rho_u I
     double ps = 0.0, ds = 0.0;
-    for (int q = 0; q < c; q++) {
+    _Pragma("unroll") for (int q = 0; q < c; q++) {
       const double zn = x[q], pr = xu[q] - zn, dz = zn - z[q];
       lm[q] += pr;
       z[q] = zn;
@@ -317,7 +320,7 @@ __global__ void k_sls_admm(SlsAdmm a, SocSet S, SocRowsX X) {
   if (!ex) ex = ISLS_ADMM_MAXIT;
   if (act) {
     a.du[(size_t)b * a.Nm + r] = xu[0];                                      // sls.py:449
-    for (int q = 1; q < c; q++) a.phic[((size_t)b * a.Nm + r) * (c - 1) + q - 1] = xu[q];
+    _Pragma("unroll") for (int q = 1; q < c; q++) a.phic[((size_t)b * a.Nm + r) * (c - 1) + q - 1] = xu[q];
   }
   if (r == 0) {
     a.iters[b] = it;
@@ -398,11 +401,90 @@ __global__ void k_sls_controller(int n, int m, int N, int cfirst, const double *
   }
 }
 
+// Batched controller.  PHI_U of problem b differs from the shared PHI_U in its first `cfirst` columns only, so the
+// columns j >= cfirst of PHI_X = Sw + Su PHI_U and - because the back-substitution runs from the right - of
+// K = PHI_U PHI_X^-1 are THE SAME for every problem: k_sls_ctrl_shared computes them once per (plan, cfirst) with the
+// arithmetic of k_sls_controller (same summation order, bit-identical), k_sls_ctrl_batch adds the cfirst per-problem
+// columns (two (N n) x (N m) mat-vecs each instead of a dense (N n)^2 (N m) product and a 200-step substitution per
+// problem: 4 MFLOP -> 0.1 MFLOP per problem at N = 50), assembles K[b] and k[b] = d_u - K (Su d_u).
+__global__ void k_sls_ctrl_shared(int n, int m, int N, int cfirst, const double *Sw, const double *Su,
+                                  const double *PHI_shared, double *PX, double *Ksh) {
+  const int Nn = N * n, Nm = N * m;
+  for (int e = threadIdx.x; e < Nn * Nn; e += blockDim.x) {
+    const int r = e / Nn, col = e % Nn;
+    double acc = Sw[(size_t)r * Nn + col];
+    const int k0 = (col / n) * m, k1 = (r / n) * m;
+    if (col >= cfirst)
+      for (int k = k0; k < k1; k++) acc = fma(Su[(size_t)r * Nm + k], PHI_shared[(size_t)k * Nn + col], acc);
+    PX[e] = acc;
+  }
+  __syncthreads();
+  for (int col = Nn - 1; col >= cfirst; col--) {
+    for (int r = threadIdx.x; r < Nm; r += blockDim.x) {
+      double acc = PHI_shared[(size_t)r * Nn + col];
+      const int i1 = min(Nn, (r / m + 1) * n);
+      for (int i = col + 1; i < i1; i++) acc = fma(-Ksh[(size_t)r * Nn + i], PX[(size_t)i * Nn + col], acc);
+      Ksh[(size_t)r * Nn + col] = (col < i1) ? acc : 0.0;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void k_sls_ctrl_batch(int n, int m, int N, int cfirst, const double *Sw, const double *Su, const double *Ksh,
+                                 const double *phic, const double *du, double *K, double *kff) {
+  const int Nn = N * n, Nm = N * m;
+  const long long b = blockIdx.x;
+  extern __shared__ double sh[];
+  double *pxc = sh;                 // [Nn] current per-problem column of PHI_X; later Su d_u
+  double *kown = sh + Nn;           // [cfirst][Nm] per-problem columns of K
+  double *Kb = K + (size_t)b * Nm * Nn;
+  for (int col = cfirst - 1; col >= 0; col--) {
+    for (int i = threadIdx.x; i < Nn; i += blockDim.x) {
+      double acc = Sw[(size_t)i * Nn + col];
+      const int k0 = (col / n) * m, k1 = (i / n) * m;
+      for (int k = k0; k < k1; k++) acc = fma(Su[(size_t)i * Nm + k], phic[((size_t)b * Nm + k) * cfirst + col], acc);
+      pxc[i] = acc;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < Nm; r += blockDim.x) {
+      double acc = phic[((size_t)b * Nm + r) * cfirst + col];
+      const int i1 = min(Nn, (r / m + 1) * n);
+      for (int i = col + 1; i < i1; i++) {
+        const double kri = i < cfirst ? kown[i * Nm + r] : Ksh[(size_t)r * Nn + i];
+        acc = fma(-kri, pxc[i], acc);
+      }
+      kown[col * Nm + r] = (col < i1) ? acc : 0.0;
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < Nm * Nn; e += blockDim.x) {
+    const int r = e / Nn, col = e % Nn;
+    Kb[e] = col < cfirst ? kown[col * Nm + r] : Ksh[e];
+  }
+  const double *d = du + (size_t)b * Nm;
+  for (int r = threadIdx.x; r < Nn; r += blockDim.x) {
+    double acc = 0.0;
+    for (int k = 0; k < Nm; k++) acc = fma(Su[(size_t)r * Nm + k], d[k], acc);
+    pxc[r] = acc;
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < Nm; r += blockDim.x) {
+    double acc = d[r];
+    for (int k = 0; k < Nn; k++) {
+      const double krk = k < cfirst ? kown[k * Nm + r] : Ksh[(size_t)r * Nn + k];
+      acc = fma(-krk, pxc[k], acc);
+    }
+    kff[(size_t)b * Nm + r] = acc;
+  }
+}
+
 // ----------------------------------------------------------------------------------------------------- host
 struct isls_sls_plan {
   int n, m, N, Nn, Nm;
   double u_std;
   double *Apow, *Sw, *Su, *DTQ, *L, *Linv0, *W, *R, *Y, *PHI, *fac, *Lrho, *Linv_rho, *rfb, *q;
+  double *PXsh, *Ksh;       // shared columns of PHI_X and K of the batched controller (valid for cfirst = ctrl_cfirst)
+  int ctrl_cfirst;          // -1: not built yet
   int *flag;
   double rho_cached;
   int c_cached;
@@ -437,7 +519,8 @@ extern "C" int isls_sls_plan_create(int32_t n, int32_t m, int32_t N, const doubl
       {&p->Apow, (size_t)N * n * n}, {&p->Sw, Nn * Nn}, {&p->Su, Nn * Nm}, {&p->DTQ, Nm * Nn}, {&p->L, Nm * Nm},
       {&p->Linv0, Nm * Nm}, {&p->W, Nm * Nm}, {&p->R, Nm * Nn}, {&p->Y, Nm * Nn}, {&p->PHI, Nm * Nn},
       {&p->fac, Nm * Nm}, {&p->Lrho, Nm * Nm}, {&p->Linv_rho, Nm * Nm}, {&p->rfb, Nm * (size_t)n}, {&p->q, Nn},
-      {&dA, (size_t)n * n}, {&dB, (size_t)n * m}};
+      {&p->PXsh, Nn * Nn}, {&p->Ksh, Nm * Nn}, {&dA, (size_t)n * n}, {&dB, (size_t)n * m}};
+  p->ctrl_cfirst = -1;
   for (auto &a : arrs) CK(cudaMalloc(a.ptr, al(a.cnt * sizeof(double))));
   CK(cudaMalloc(&p->flag, 256));
   CK(cudaMemcpyAsync(dA, A_host, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -471,7 +554,7 @@ extern "C" int isls_sls_plan_create(int32_t n, int32_t m, int32_t N, const doubl
 extern "C" int isls_sls_plan_destroy(isls_sls_plan *p) {
   if (!p) return ISLS_OK;
   double *ptrs[] = {p->Apow, p->Sw, p->Su, p->DTQ, p->L, p->Linv0, p->W, p->R, p->Y, p->PHI, p->fac, p->Lrho,
-                    p->Linv_rho, p->rfb, p->q};
+                    p->Linv_rho, p->rfb, p->q, p->PXsh, p->Ksh};
   for (double *q : ptrs) cudaFree(q);
   cudaFree(p->flag);
   delete p;
@@ -569,7 +652,10 @@ extern "C" int isls_sls_admm_f64(isls_sls_plan *p, const isls_sls_admm_opts *o, 
   a.Su = p->Su; a.Sw = p->Sw;
   const int threads = ((p->Nm + 31) / 32) * 32;
   const size_t smem = ((size_t)p->Nm * c + 32 + (size_t)ISLS_MAX_XROWS * c) * sizeof(double);
-  k_sls_admm<<<(unsigned)B, threads, smem, s>>>(a, S, X);
+  if (S.P == 2 && S.c == 3 && S.ra == 4) k_sls_admm<2, 3, 4><<<(unsigned)B, threads, smem, s>>>(a, S, X);        // n = 4 (C4)
+  else if (S.P == 2 && S.c == 2 && S.ra == 3) k_sls_admm<2, 2, 3><<<(unsigned)B, threads, smem, s>>>(a, S, X);   // n = 2
+  else if (S.P == 2 && S.c == 4 && S.ra == 5) k_sls_admm<2, 4, 5><<<(unsigned)B, threads, smem, s>>>(a, S, X);   // n = 6
+  else k_sls_admm<0, 0, 0><<<(unsigned)B, threads, smem, s>>>(a, S, X);
   CK(cudaGetLastError());
   return ISLS_OK;
 }
@@ -625,11 +711,24 @@ extern "C" int isls_sls_controller_f64(const isls_sls_plan *p, int64_t B, int32_
   if (!p || B <= 0 || !du_dev || !K_dev || !k_dev || !workspace_dev || n_first_cols < 0 || n_first_cols > p->Nn)
     return isls_fail(ISLS_E_INVALID, "NULL argument or bad size");
   if (n_first_cols > 0 && !phi_cols_dev) return isls_fail(ISLS_E_INVALID, "phi_cols_dev is NULL");
-  const size_t need = (size_t)B * p->Nn * p->Nn * sizeof(double);
-  if (workspace_bytes < need) return isls_fail(ISLS_E_WORKSPACE, "controller workspace too small (B*(N n)^2 doubles)");
-  k_sls_controller<<<(unsigned)B, 256, p->Nn * sizeof(double), (cudaStream_t)stream>>>(
-      p->n, p->m, p->N, n_first_cols, p->Sw, p->Su, p->PHI, phi_cols_dev, du_dev, (double *)workspace_dev, K_dev,
-      k_dev);
+  cudaStream_t s = (cudaStream_t)stream;
+  static const bool dense = getenv("ISLS_SLS_CTRL_DENSE") != nullptr;       // test switch: per-problem dense form
+  const size_t smem = ((size_t)p->Nn + (size_t)n_first_cols * p->Nm) * sizeof(double);
+  if (dense || smem > 48 * 1024) {
+    const size_t need = (size_t)B * p->Nn * p->Nn * sizeof(double);
+    if (workspace_bytes < need) return isls_fail(ISLS_E_WORKSPACE, "controller workspace too small (B*(N n)^2 doubles)");
+    k_sls_controller<<<(unsigned)B, 256, p->Nn * sizeof(double), s>>>(p->n, p->m, p->N, n_first_cols, p->Sw, p->Su, p->PHI,
+                                                                     phi_cols_dev, du_dev, (double *)workspace_dev, K_dev,
+                                                                     k_dev);
+  } else {
+    isls_sls_plan *pm = const_cast<isls_sls_plan *>(p);     // cache of the shared columns (one host thread per plan)
+    if (pm->ctrl_cfirst != n_first_cols) {
+      k_sls_ctrl_shared<<<1, 1024, 0, s>>>(p->n, p->m, p->N, n_first_cols, p->Sw, p->Su, p->PHI, pm->PXsh, pm->Ksh);
+      pm->ctrl_cfirst = n_first_cols;
+    }
+    k_sls_ctrl_batch<<<(unsigned)B, 256, smem, s>>>(p->n, p->m, p->N, n_first_cols, p->Sw, p->Su, pm->Ksh, phi_cols_dev,
+                                                    du_dev, K_dev, k_dev);
+  }
   CK(cudaGetLastError());
   return ISLS_OK;
 }

@@ -45,7 +45,8 @@ __device__ __forceinline__ double block_sum(double v, double *sm) {
 // row with t < 0 is zeroed): later masks win (cond2, then cond1, then cond3), exactly like the numpy code.
 __device__ __forceinline__ void soc_unit_row(int d, const double *y, double *out) {
   double s = 0.0;
-  for (int i = 0; i < d; i++) s = fma(y[i], y[i], s);
+#pragma unroll
+  for (int i = 0; i < SOC_MAXR; i++) if (i < d) s = fma(y[i], y[i], s);
   const double zn = sqrt(s), t = y[d];
   const bool c1 = (zn <= -t) || (t < 0.0);
   const bool c2 = (zn > t) || (zn > -t);
@@ -65,17 +66,21 @@ __device__ __forceinline__ void soc_unit_row(int d, const double *y, double *out
 // the CTA must call it (block reductions).  Returns the number of inner iterations.
 // `bb`: the offsets b_i to use (S.b, or a row's own); red == nullptr: a single row projected on its own (its stop rule
 // is its own residual; no block reduction, callable by a subset of the CTA).
+// CP, CC, CR: compile-time number of cones, columns and rows of A_i (0 = take them from S at run time).  With the
+// compile-time form every loop unrolls and z_i, lambda_i, x live in registers; the run-time form indexes them
+// dynamically, i.e. in local memory - 0.9 GB of DRAM writes per ADMM_SLS call at C4 (profiles/r2_ncu_sls_kernels.csv).
+template <int CP = 0, int CC = 0, int CR = 0>
 __device__ __forceinline__ int soc_project_set(const SocSet &S, const double (&bb)[SOC_MAXP][SOC_MAXR],
                                                const double (&x0)[SOC_MAXC], double (&x)[SOC_MAXC], bool act,
                                                double *red) {
-  const int c = S.c;
+  const int c = CC ? CC : S.c, SP = CP ? CP : S.P, Sra = CR ? CR : S.ra;
   double zi[SOC_MAXP][SOC_MAXR], li[SOC_MAXP][SOC_MAXR];
   int inner = 0;
-  for (int q = 0; q < c; q++) x[q] = x0[q];
-  for (int i = 0; i < S.P; i++)
-    for (int e = 0; e < S.ra; e++) {
+  _Pragma("unroll") for (int q = 0; q < c; q++) x[q] = x0[q];
+  _Pragma("unroll") for (int i = 0; i < SP; i++)
+    _Pragma("unroll") for (int e = 0; e < Sra; e++) {
       double v = bb[i][e];
-      for (int q = 0; q < c; q++) v = fma(S.A[i][e][q], x[q], v);
+      _Pragma("unroll") for (int q = 0; q < c; q++) v = fma(S.A[i][e][q], x[q], v);
       zi[i][e] = v;                         // z_i = A_i x + b_i   (projections.py:315)
       li[i][e] = 0.0;
     }
@@ -83,39 +88,39 @@ __device__ __forceinline__ int soc_project_set(const SocSet &S, const double (&b
   for (int j = 0; j < S.max_iter; j++) {
     inner++;
     double rsd[SOC_MAXC] = {};
-    for (int i = 0; i < S.P; i++)
-      for (int e = 0; e < S.ra; e++) {
+    _Pragma("unroll") for (int i = 0; i < SP; i++)
+      _Pragma("unroll") for (int e = 0; e < Sra; e++) {
         const double w = (-bb[i][e] + zi[i][e]) - li[i][e];
-        for (int q = 0; q < c; q++) rsd[q] = fma(S.A[i][e][q], w, rsd[q]);
+        _Pragma("unroll") for (int q = 0; q < c; q++) rsd[q] = fma(S.A[i][e][q], w, rsd[q]);
       }
     double tq[SOC_MAXC];
-    for (int q = 0; q < c; q++) tq[q] = x0[q] + S.rho * rsd[q];
-    for (int q = 0; q < c; q++) {
+    _Pragma("unroll") for (int q = 0; q < c; q++) tq[q] = x0[q] + S.rho * rsd[q];
+    _Pragma("unroll") for (int q = 0; q < c; q++) {
       double v = 0.0;
-      for (int p = 0; p < c; p++) v = fma(S.linv[q][p], tq[p], v);
+      _Pragma("unroll") for (int p = 0; p < c; p++) v = fma(S.linv[q][p], tq[p], v);
       x[q] = v;                              // projections.py:330
     }
     double pmax = 0.0, dmax = 0.0;
-    for (int i = 0; i < S.P; i++) {
+    _Pragma("unroll") for (int i = 0; i < SP; i++) {
       double axb[SOC_MAXR], y[SOC_MAXR], zn[SOC_MAXR];
-      for (int e = 0; e < S.ra; e++) {
+      _Pragma("unroll") for (int e = 0; e < Sra; e++) {
         double v = bb[i][e];
-        for (int q = 0; q < c; q++) v = fma(S.A[i][e][q], x[q], v);
+        _Pragma("unroll") for (int q = 0; q < c; q++) v = fma(S.A[i][e][q], x[q], v);
         axb[e] = v;
         y[e] = v + li[i][e];
       }
-      soc_unit_row(S.ra - 1, y, zn);
+      soc_unit_row(Sra - 1, y, zn);
       double ps = 0.0, dr[SOC_MAXC] = {};
-      for (int e = 0; e < S.ra; e++) {
+      _Pragma("unroll") for (int e = 0; e < Sra; e++) {
         const double pr = axb[e] - zn[e];
         ps = fma(pr, pr, ps);
         const double dz = zn[e] - zi[i][e];
-        for (int q = 0; q < c; q++) dr[q] = fma(S.A[i][e][q], dz, dr[q]);
+        _Pragma("unroll") for (int q = 0; q < c; q++) dr[q] = fma(S.A[i][e][q], dz, dr[q]);
         li[i][e] += pr;
         zi[i][e] = zn[e];
       }
       double ds = 0.0;
-      for (int q = 0; q < c; q++) ds = fma(S.rho * dr[q], S.rho * dr[q], ds);
+      _Pragma("unroll") for (int q = 0; q < c; q++) ds = fma(S.rho * dr[q], S.rho * dr[q], ds);
       pmax = fmax(pmax, sqrt(ps));
       dmax = fmax(dmax, sqrt(ds));
     }

@@ -33,7 +33,7 @@ class ProblemDesc(_Guarded):
                 ("obst_centers", C.c_void_p), ("obst_W", C.c_void_p), ("obst_W_inv", C.c_void_p),
                 ("obst_lower", C.c_void_p), ("obst_upper", C.c_double), ("obst_rho", C.c_double),
                 ("obst_threshold", C.c_double), ("obst_kind", C.c_int32), ("obst_dykstra_max_iter", C.c_int32),
-                ("obst_dykstra_tol", C.c_double), ("isls_dim", C.c_int32)]
+                ("obst_dykstra_tol", C.c_double), ("isls_dim", C.c_int32), ("lti_A", C.c_void_p), ("lti_B", C.c_void_p)]
 
 
 class SolveOpts(_Guarded):
@@ -55,6 +55,12 @@ class SlsAdmmOpts(_Guarded):
                 ("x_bs", C.c_void_p), ("rho_x_rows", C.c_void_p)]
 
 
+class ProjParams(_Guarded):
+    _fields_ = [("struct_size", C.c_uint32), ("kind", C.c_int32), ("k", C.c_int32), ("A", C.c_void_p), ("b", C.c_void_p),
+                ("l", C.c_void_p), ("u", C.c_void_p), ("rho", C.c_double), ("tol", C.c_double), ("max_iter", C.c_int32),
+                ("x_dim", C.c_int32), ("u_dim", C.c_int32), ("N", C.c_int32)]
+
+
 class SolveOut(_Guarded):
     _fields_ = [("struct_size", C.c_uint32)] + [(f, C.c_void_p) for f in OUT_FIELDS]
 
@@ -65,7 +71,7 @@ EXPORTS = ["isls_version", "isls_last_error_string", "isls_model_id", "isls_mode
            "isls_measure_fp64_tflops", "isls_profile_enable", "isls_profile_collect",
            "isls_sls_plan_create", "isls_sls_plan_destroy", "isls_sls_operators", "isls_sls_solve_f64",
            "isls_sls_admm_f64", "isls_sls_controller_f64", "isls_mc_rollout_f64", "isls_project_rows_f64",
-           "isls_isls_admm_solve_f64", "isls_sls_replan_f64", "isls_probe_overlap_f64"]
+           "isls_isls_admm_solve_f64", "isls_sls_replan_f64", "isls_probe_overlap_f64", "isls_project_rows_ex_f64"]
 
 KERNEL_CLASSES = ["init", "kpass", "ff", "linesearch", "admm", "outer_end", "finalize", "backward_full", "accept",
                   "lqt", "compact", "isls_cols", "isls_update"]
@@ -120,6 +126,8 @@ def lib():
                                       C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.isls_project_rows_f64.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                         C.c_double, C.c_void_p, C.c_void_p]
+    L.isls_project_rows_ex_f64.argtypes = [C.POINTER(ProjParams), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]
     L.isls_profile_enable.argtypes = [C.c_int]
     L.isls_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     _lib = L

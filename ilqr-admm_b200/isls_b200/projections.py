@@ -123,6 +123,64 @@ def project_unit_ball_batch(x):
     return _rows(5, x)
 
 
+def project_affine_batch(x, a, b, l, u):
+    """isls/projections.py:64-68: l <= a'x + b <= u, i.e. project_linear with the bounds shifted by b."""
+    return _rows(1, x, a, None, l - b, u - b)
+
+
+def _rows_ex(kind, x, A=None, b=None, l=None, u=None, rho=1.0, tol=1e-5, max_iter=100, blt=None, want_iters=False):
+    import ctypes as C
+    from . import _lib
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float64 and x.ndim == 2):
+        raise TypeError("device projections take a CUDA float64 tensor [rows, dim]")
+    keep = {}
+
+    def hp(a, shape):
+        if a is None:
+            return None
+        keep[len(keep)] = np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), shape))
+        return keep[len(keep) - 1].ctypes.data
+    p = _lib.ProjParams(kind=kind, rho=float(rho), tol=float(tol), max_iter=int(max_iter))
+    it = torch.zeros(1, dtype=torch.int32, device=x.device) if want_iters else None
+    if blt is not None:
+        p.x_dim, p.u_dim, p.N = blt
+        out = x.contiguous().clone()
+        rows, dim = 1, 1
+    else:
+        A = np.atleast_2d(np.asarray(A, dtype=np.float64))
+        p.k = A.shape[0]
+        p.A, p.b, p.l, p.u = hp(A, A.shape), hp(b, (p.k,)), hp(l, (p.k,)), hp(u, (p.k,))
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        rows, dim = x.shape
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().isls_project_rows_ex_f64(C.byref(p), rows, dim, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                 None if it is None else C.c_void_p(it.data_ptr()),
+                                                 C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    _lib.check(rc, "isls_project_rows_ex_f64")
+    return (out, int(it[0])) if want_iters else out
+
+
+def project_multilinear_batch(x, A, l, u):
+    """isls/projections.py:46-62 on every row: x - A'(A A')^-1 (A x - clip(A x, l, u)) (a boundary projection, not the
+    minimum-norm one - as the reference notes)."""
+    return _rows_ex(6, x, A, None, l, u)
+
+
+def project_soc_batch(z0, A, b, rho=1.0, max_iter=100, tol=1e-5, want_iters=False):
+    """isls/projections.py:163-232: rows z0 onto {z : A z + b in SOC} by the reference's inner ADMM (stop rule: maximum of
+    the residual norms over all rows, so at most 1,024 rows per call)."""
+    return _rows_ex(7, z0, A, b, None, None, rho=rho, tol=tol, max_iter=max_iter, want_iters=want_iters)
+
+
+def project_block_lower_triangular(z, x_dim, u_dim, N):
+    """isls/projections.py:277-286 on a CUDA matrix [N u_dim, N x_dim]: zeroes z[i u_dim, i x_dim:(i+1) x_dim] (exactly
+    the rows the reference touches).  Returns a new tensor."""
+    if z.shape != (N * u_dim, N * x_dim):
+        raise ValueError("z must be [N u_dim, N x_dim]")
+    return _rows_ex(8, z, blt=(x_dim, u_dim, N))
+
+
 class ObstacleSets:
     """Device descriptor of the notebooks' obstacle-avoidance state projection (Car/Iterative LQR with state
     constraints.ipynb cell 18): `project_set_convex(x, [I]*K, [0]*K, projections, rho, max_iter, threshold)` where

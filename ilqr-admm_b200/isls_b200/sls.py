@@ -30,8 +30,9 @@ class SLS:
 
     @AB.setter
     def AB(self, value):
-        """Linear dynamics (isls/base.py:98-119).  The device path registers the double integrator
-        (isls/utils.py:266-276): A, B must be get_double_integrator_AB(u_dim, 2, dt) for some dt."""
+        """Linear dynamics (isls/base.py:98-119): any constant pair A [x_dim, x_dim], B [x_dim, u_dim].  A double
+        integrator (isls/utils.py:266-276) runs on the registered sparse model, anything else on the dense "lti" model
+        ((x_dim, u_dim) in (2,1), (4,2), (6,3))."""
         A, Bm = np.asarray(value[0], dtype=np.float64), np.asarray(value[1], dtype=np.float64)
         d = self.u_dim
         if A.shape != (self.x_dim, self.x_dim) or Bm.shape != (self.x_dim, d):
@@ -70,8 +71,10 @@ class SLS:
         obst = project_x if isinstance(project_x, ObstacleSets) else None
         bx = project_x.expand(self.N, self.x_dim) if project_x and obst is None else None
         bu = project_u.expand(self.N, self.u_dim) if project_u else None
-        plan = S.Plan("double_integrator", self.N, self.x_dim, self.u_dim, self._dt, self.Qdiag, self.seq, self.u_std,
-                      1, rho_x=self._rho(rho_x, self.x_dim) if project_x else None,
+        lti = self._dt is None
+        plan = S.Plan("lti" if lti else "double_integrator", self.N, self.x_dim, self.u_dim, 0.0 if lti else self._dt,
+                      self.Qdiag, self.seq, self.u_std, 1, lti_AB=(self.A, self.B) if lti else None,
+                      rho_x=self._rho(rho_x, self.x_dim) if project_x else None,
                       lo_x=None if bx is None else bx[0], hi_x=None if bx is None else bx[1],
                       rho_u=self._rho(rho_u, self.u_dim) if project_u else None,
                       lo_u=None if bu is None else bu[0], hi_u=None if bu is None else bu[1],
@@ -91,9 +94,9 @@ class SLS:
     def _check_lqt(self):
         if self.A is None or self.zs is None:
             raise IslsError("set AB and set_quadratic_cost first")
-        if self._dt is None:
-            raise NotImplementedError("the LQT (DP) kernels need A, B = get_double_integrator_AB(u_dim, 2, dt) "
-                                      "(the registered linear model)")
+        if self._dt is None and (self.x_dim, self.u_dim) not in ((2, 1), (4, 2), (6, 3)):
+            raise NotImplementedError("the dense LTI model of the LQT (DP) kernels is compiled for (x_dim, u_dim) in "
+                                      "(2,1), (4,2), (6,3)")
 
     def _regularised(self, Qr, Rr, ur, xr, x0, return_Qs):
         """One K-pass + one feed-forward pass of the regularised LQT problem (isls/sls.py:85-202 with Qr, Rr, xr, ur):
@@ -301,6 +304,7 @@ class SLS:
         _lib.check(rc, "isls_sls_admm_f64")
         self.last = S.Result(du=du, phi_cols=phic, logs=logs, iters=iters, exit_code=exits, inner_total=inner)
         phi_u = torch.cat([phic, pl.PHI_U[None, :, c - 1:].expand(B_, Nm, Nn - (c - 1))], dim=-1)   # sls.py:450
+        phi_u._isls_first_cols = c - 1      # hint for controller(): only these columns differ from the shared PHI_U
         if verbose:
             it, ex = iters.cpu().numpy(), exits.cpu().numpy()
             for b in range(min(B_, 8)):
@@ -323,14 +327,24 @@ class SLS:
         single = PHI_U.ndim == 2 and du.ndim == 1
         du = du.reshape(-1, Nm).contiguous()
         B_ = du.shape[0]
-        PHI = PHI_U.reshape(-1, Nm, Nn).expand(B_, Nm, Nn).contiguous()
+        PHI = PHI_U.reshape(-1, Nm, Nn).expand(B_, Nm, Nn)
         f64 = dict(dtype=torch.float64, device=dev)
         K = torch.empty(B_, Nm, Nn, **f64)
         k = torch.empty(B_, Nm, **f64)
-        ws = torch.empty(B_ * Nn * Nn, **f64)
+        # A PHI_U that ADMM_SLS returned differs from the plan's shared PHI_U in its first c - 1 columns only; then the
+        # other columns of PHI_X and K are shared too and the library computes them once (k_sls_ctrl_shared).  The hint is
+        # verified on the device, so a tensor the caller modified takes the general per-problem path.
+        nf = getattr(PHI_U, "_isls_first_cols", None)
+        if nf is not None and PHI.shape[-1] == Nn and torch.equal(PHI[:, :, nf:], pl.PHI_U[None, :, nf:].expand(B_, Nm, Nn - nf)):
+            cols, ncols = PHI[:, :, :nf].contiguous(), nf
+            import os
+            ws = torch.empty(B_ * Nn * Nn if os.environ.get("ISLS_SLS_CTRL_DENSE") else 1, **f64)   # test switch
+        else:
+            cols, ncols = PHI.contiguous(), Nn
+            ws = torch.empty(B_ * Nn * Nn, **f64)
         p = lambda t: C.c_void_p(t.data_ptr())
         with torch.cuda.device(dev):
-            rc = _lib.lib().isls_sls_controller_f64(pl.handle, B_, Nn, p(PHI), p(du), p(ws), ws.numel() * 8, p(K),
+            rc = _lib.lib().isls_sls_controller_f64(pl.handle, B_, ncols, p(cols), p(du), p(ws), ws.numel() * 8, p(K),
                                                     p(k), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         _lib.check(rc, "isls_sls_controller_f64")
         return (K[0], k[0]) if single else (K, k)

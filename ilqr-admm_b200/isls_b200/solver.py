@@ -43,7 +43,7 @@ class Plan:
 
     def __init__(self, model, N, n, m, dt, Qdiag, seq, u_std, L, rho_x=None, lo_x=None, hi_x=None, rho_u=None,
                  lo_u=None, hi_u=None, cost="quadratic", Rdiag=None, Hp=None, Qdiag_b=None, Hp_b=None, obstacles=None, isls_dim=0,
-                 device="cuda:0"):
+                 device="cuda:0", lti_AB=None):
         """cost="pseudo_huber": Qdiag / Hp are the weights and smoothness scales [n_via, n] of the first term,
         Qdiag_b / Hp_b of the optional second one (Tutorial cell 14); Rdiag [m] replaces R = u_std I.
         device: the GPU that holds the plan's constant block - a BatchSolver must use the same one."""
@@ -94,8 +94,10 @@ class Plan:
             d.obst_upper, d.obst_rho, d.obst_threshold = float(ob["upper"]), float(ob["rho"]), float(ob["threshold"])
             for k in ("obst_centers", "obst_W", "obst_W_inv", "obst_lower"):
                 setattr(d, k, _ptr(keep[k]))
+        if lti_AB is not None:            # model "lti": x+ = A x + B u with the given constant matrices
+            keep.update(lti_A=_f64(lti_AB[0], (n, n)), lti_B=_f64(lti_AB[1], (n, m)))
         for k in ("Qdiag", "seq", "alphas", "rho_x", "lo_x", "hi_x", "rho_u", "lo_u", "hi_u", "Rdiag", "Hp", "Qdiag_b",
-                  "Hp_b"):
+                  "Hp_b", "lti_A", "lti_B"):
             setattr(d, k, _ptr(keep.get(k)))
         self._keep = keep
         h = C.c_void_p()

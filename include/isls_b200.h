@@ -48,6 +48,8 @@ extern "C" {
 #define ISLS_MODEL_CAR 1                 /* notebooks/Car/Iterative LQR with control constraints.ipynb cell 6; n=4,m=2 */
 #define ISLS_MODEL_ARM3 2                /* notebooks/3DoF robot/State and control bound constraints.ipynb cells 9-10; n=9,m=3 */
 #define ISLS_MODEL_TASSA_CAR 3           /* notebooks/Tutorial.ipynb cell 8 (car parking of Tassa et al., axle distance 2); n=4,m=2 */
+#define ISLS_MODEL_LTI 4                 /* x+ = A x + B u with any constant A, B (Base.AB, isls/base.py:98-119; name "lti");
+                                            (n,m) in {(2,1),(4,2),(6,3)}; matrices in isls_problem_desc.lti_A / lti_B */
 
 /* state-cost families (cost_function slot, isls/isls_base.py:113-131) */
 #define ISLS_COST_QUADRATIC 0            /* sum_i Q_ii (x_i - z_i)^2: isls/sls_base.py:25-44 */
@@ -115,6 +117,7 @@ typedef struct isls_problem_desc {
   double obst_dykstra_tol;
   int32_t isls_dim;            /* > 0: the plan is used by isls_isls_admm_solve_f64 with `dim` robustness columns
                                   (workspace for the [d_u | Phi_u(:, :dim)] matrix variables); <= 3 */
+  const double *lti_A, *lti_B; /* ISLS_MODEL_LTI: A [n, n], B [n, m] row-major (host; copied) */
 } isls_problem_desc;
 #define ISLS_MAX_OBST 4
 
@@ -167,7 +170,7 @@ typedef struct isls_solve_out {
 int isls_version(void);
 const char *isls_last_error_string(void);
 
-/* name -> ISLS_MODEL_* (or ISLS_E_UNSUPPORTED).  Names: "double_integrator", "car", "arm3", "tassa_car". */
+/* name -> ISLS_MODEL_* (or ISLS_E_UNSUPPORTED).  Names: "double_integrator", "car", "arm3", "tassa_car", "lti". */
 int isls_model_id(const char *name);
 /* 0 if the (model, n, m) combination has a compiled kernel */
 int isls_model_supported(int32_t model_id, int32_t n, int32_t m);
@@ -323,6 +326,28 @@ int isls_mc_rollout_f64(int32_t model_id, int32_t n, int32_t m, int32_t N, doubl
  *   kind 5 unit_ball  |x| <= 1                                                    isls/projections.py:232-240 */
 int isls_project_rows_f64(int32_t kind, int64_t rows, int32_t dim, const double *x_dev, const double *p0_dev,
                           const double *p1_dev, double l, double u, double *out_dev, void *stream);
+
+/* Parameterised row projections (8f #2, continued).  All pointers are HOST arrays (small parameters, copied). */
+#define ISLS_PROJ_MULTILINEAR 6              /* l <= A x <= u, boundary projection x - A'(AA')^-1 (Ax - clip)   isls/projections.py:46-62 */
+#define ISLS_PROJ_SOC 7                      /* A x + b in SOC by the inner ADMM of project_soc (rows <= 1024: its stop
+                                                rule is a maximum over all rows)                                isls/projections.py:163-232 */
+#define ISLS_PROJ_BLOCK_LOWER_TRIANGULAR 8   /* z[i*u_dim, i*x_dim:(i+1)*x_dim] = 0 in place on out_dev [N u_dim, N x_dim]
+                                                                                                                isls/projections.py:277-286 */
+typedef struct isls_proj_params {
+  uint32_t struct_size;  /* = sizeof(isls_proj_params) (ABI guard) */
+  int32_t kind;          /* ISLS_PROJ_* */
+  int32_t k;             /* rows of A (<= 8) */
+  const double *A;       /* [k, dim] */
+  const double *b;       /* [k] (soc) or NULL */
+  const double *l, *u;   /* [k] (multilinear) or NULL = unbounded */
+  double rho, tol;       /* soc: inner ADMM penalty and tolerance */
+  int32_t max_iter;      /* soc */
+  int32_t x_dim, u_dim, N;   /* block_lower_triangular */
+} isls_proj_params;
+/* x_dev [rows, dim] -> out_dev [rows, dim] (dim <= 16); iters_dev [1] optional (soc: inner iterations).
+ * project_affine (isls/projections.py:64-68) is kind 1 of isls_project_rows_f64 with shifted bounds l - b, u - b. */
+int isls_project_rows_ex_f64(const isls_proj_params *params, int64_t rows, int32_t dim, const double *x_dev,
+                             double *out_dev, int32_t *iters_dev, void *stream);
 
 /* ---- measurement helpers (bench.py roofline denominators; not part of the reference surface) ---- */
 /* kernel classes for per-kernel CUDA-event timing */

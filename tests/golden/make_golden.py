@@ -542,6 +542,70 @@ def golden_admm_toy():
     np.savez_compressed(os.path.join(OUT, "admm_toy.npz"), **out)
 
 
+def golden_projections_ex():
+    """project_multilinear, project_affine, project_soc, project_block_lower_triangular of the unmodified reference
+    (isls/projections.py:46-68, 163-232, 277-286) on seeded rows."""
+    S.load()
+    from isls.projections import (project_affine, project_block_lower_triangular, project_multilinear, project_soc)
+    rng = np.random.default_rng(21)
+    x = rng.normal(0, 2.0, (64, 5))
+    A = rng.normal(0, 1.0, (3, 5))
+    l, u = np.array([-0.5, -1.0, 0.2]), np.array([0.5, 0.3, 0.9])
+    ml = np.stack([project_multilinear(x[i], A, l, u) for i in range(64)])
+    a = rng.normal(0, 1.0, 5)
+    aff = np.stack([project_affine(x[i].copy(), a, 0.7, -0.4, 0.6) for i in range(64)])
+    z0 = rng.normal(0, 1.5, (40, 3))
+    As = rng.normal(0, 1.0, (4, 3))
+    bs = np.array([0.1, -0.2, 0.0, 0.8])
+    with S.quiet():
+        soc = project_soc(z0.copy(), As, bs, rho=2.0, max_iter=100, tol=1e-6)
+        soc1 = project_soc(z0[3].copy(), As, bs, rho=2.0, max_iter=100, tol=1e-6)
+    N, xd, ud = 6, 4, 2
+    Z = rng.normal(0, 1.0, (N * ud, N * xd))
+    blt = project_block_lower_triangular(Z.copy(), xd, ud, N)
+    np.savez_compressed(os.path.join(OUT, "projections_ex.npz"), x=x, A=A, l=l, u=u, ml=ml, a=a, aff=aff, z0=z0, As=As,
+                        bs=bs, soc=soc, soc1=soc1, Z=Z, blt=blt)
+    print("projections_ex: soc moved rows by up to %.3f" % np.abs(soc - z0).max())
+
+
+def golden_lqt_lti():
+    """SLS.ADMM_LQT_DP / ADMM_LQT_Batch / solve(method='dp') of the unmodified reference (isls/sls.py:40-60, 250-317) with a
+    GENERAL constant pair (A, B) - a damped, coupled 2-D oscillator, not a double integrator - state and control bounds."""
+    pkg, _ = S.load()
+    N, n, m, dt = 40, 4, 2, 0.05
+    rng = np.random.default_rng(31)
+    A = np.eye(n) + dt * np.array([[0, 0, 1, 0], [0, 0, 0, 1], [-1.5, 0.4, -0.3, 0.1], [0.3, -2.0, 0.05, -0.2]])
+    Bm = dt * np.array([[0.0, 0.0], [0.0, 0.0], [1.0, 0.2], [-0.1, 0.8]]) + 0.5 * dt * dt * rng.normal(0, 1, (n, m))
+    zs = np.array([np.zeros(n), [0.6, -0.4, 0.0, 0.0]])
+    Qs = np.stack([np.zeros((n, n)), np.diag([1e3, 1e3, 1e1, 1e1])])
+    seq = np.zeros(N, dtype=np.int32); seq[-1] = 1
+    x0s = np.array([[0.05, 0.0, 0.0, 0.1], [0.2, -0.1, 0.2, 0.0], [-0.3, 0.2, 0.0, -0.2]])
+    lo_u, hi_u = np.full(N * m, -1.0), np.full(N * m, 1.0)
+    lo_x, hi_x = np.full((N, n), -np.inf), np.full((N, n), np.inf)
+    lo_x[:, 2:], hi_x[:, 2:] = -0.3, 0.3
+    rho_x = np.stack([np.diag([0.0, 0.0, 1.0, 1.0])] * N)
+    out = dict(A=A, B=Bm, zs=zs, Qdiag=np.stack([np.diag(q) for q in Qs]), seq=seq, x0=x0s, lo_x=lo_x, hi_x=hi_x)
+    xs, us, Ks, its, xb, ub, itb, xu, uu = [], [], [], [], [], [], [], [], []
+    for b in range(len(x0s)):
+        with S.quiet():
+            s = pkg.SLS(n, m, N)
+            s.AB = [A, Bm]
+            s.set_quadratic_cost(zs, Qs, seq, 1e-2)
+            Kq, kq = s.solve(method="dp")
+            xq, uq = s.get_trajectory_dp(x0s[b], Kq, kq)
+            r = s.ADMM_LQT_DP(x0s[b], project_x=_clip(lo_x, hi_x), project_u=lambda z: np.clip(z, lo_u, hi_u), max_iter=600,
+                              rho_x=rho_x, rho_u=1e-1, tol=1e-4, log=True)
+            rb = s.ADMM_LQT_Batch(x0s[b], project_x=_clip(lo_x, hi_x), project_u=lambda z: np.clip(z, lo_u, hi_u),
+                                  max_iter=600, rho_x=rho_x, rho_u=1e-1, tol=1e-4, log=True)
+        xs.append(r[0].reshape(N, n)); us.append(r[1].reshape(N, m)); Ks.append(r[2]); its.append(len(r[-1]))
+        xb.append(rb[0].reshape(N, n)); ub.append(rb[1].reshape(N, m)); itb.append(len(rb[-1]))
+        xu.append(np.asarray(xq).reshape(N, n)); uu.append(np.asarray(uq).reshape(N, m))
+        print("lqt_lti", b, its[-1], itb[-1], "max|u| %.3f max|v| %.3f" % (np.abs(us[-1]).max(), np.abs(xs[-1][:, 2:]).max()))
+    out.update(x=np.stack(xs), u=np.stack(us), K=np.stack(Ks), iters=np.array(its), x_batch=np.stack(xb),
+               u_batch=np.stack(ub), iters_batch=np.array(itb), x_unc=np.stack(xu), u_unc=np.stack(uu))
+    np.savez_compressed(os.path.join(OUT, "lqt_lti.npz"), **out)
+
+
 if __name__ == "__main__":
     assert S.available(), "needs the reference tree"
     only = set(sys.argv[1:])                       # e.g. `make_golden.py tutorial` regenerates one fixture family
@@ -576,6 +640,10 @@ if __name__ == "__main__":
         golden_replan()
     if want("di_obstacles"):
         golden_di_obstacles()
+    if want("lqt_lti"):
+        golden_lqt_lti()
+    if want("projections_ex"):
+        golden_projections_ex()
     if want("admm_toy"):
         golden_admm_toy()
     if want("arm_lq_step"):

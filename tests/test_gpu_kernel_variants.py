@@ -27,7 +27,7 @@ def _run(tmp_path, name, env_extra):
 def test_staged_and_plain_kernels_agree_bitwise(tmp_path):
     auto = _run(tmp_path, "auto", {})
     plain = _run(tmp_path, "plain", {"ISLS_FF_STAGES": "0", "ISLS_ADMM_STAGES": "0", "ISLS_COLS_STAGES": "0",
-                                   "ISLS_LQT_SMEM": "0", "ISLS_OVERLAP": "0"})
+                                   "ISLS_LQT_SMEM": "0", "ISLS_OVERLAP": "0", "ISLS_SLS_CTRL_DENSE": "1"})
     deep2 = _run(tmp_path, "ff2", {"ISLS_FF_STAGES": "2"})
     tma_nojc = _run(tmp_path, "tma_nojc", {"ISLS_FF_MODE": "2", "ISLS_FF_JC": "0"})    # k_ff_tma recomputing the Jacobian
     staged = _run(tmp_path, "staged", {"ISLS_FF_MODE": "0"})                           # round-1 rule: cp.async staging

@@ -496,3 +496,30 @@ def test_host_admm_driver_vs_reference_golden(golden):
         assert np.allclose(np.array(logs), ref, rtol=1e-9, atol=1e-15)
         for t, nm in ((x, "x"), (u, "u"), (lx, "lx"), (lu, "lu"), (zx, "zx"), (zu, "zu")):
             assert np.abs(t.cpu().numpy() - g[tag + "_" + nm]).max() < 1e-12, nm
+
+
+def test_lqt_general_lti_pair_vs_reference_golden(golden):
+    """Base.AB takes any constant (A, B) (isls/base.py:98-119): LQT / LQT-ADMM (DP and batch form) with a coupled damped
+    oscillator - not a double integrator - on the dense "lti" device model against the unmodified reference
+    (tests/golden/lqt_lti.npz): identical ADMM iteration counts, trajectories and gains to 1e-9."""
+    from isls_b200 import SLS, Bound
+    g = golden("lqt_lti")
+    N, n, m = 40, 4, 2
+    s = SLS(n, m, N, batch=3)
+    s.AB = [g["A"], g["B"]]
+    assert s._dt is None                                                   # not the registered double integrator
+    s.set_quadratic_cost(g["zs"], g["Qdiag"], g["seq"], 1e-2)
+    x, u = s.solve(g["x0"], method="dp")
+    assert np.abs(x.cpu().numpy().reshape(3, N, n) - g["x_unc"]).max() < 1e-9
+    assert np.abs(u.cpu().numpy().reshape(3, N, m) - g["u_unc"]).max() < 1e-8
+    kw = dict(project_x=Bound(g["lo_x"], g["hi_x"]), project_u=Bound(-1.0, 1.0), rho_x=np.diag([0.0, 0.0, 1.0, 1.0]),
+              rho_u=1e-1, max_iter=600, tol=1e-4)
+    x, u, K, k = s.ADMM_LQT_DP(g["x0"], **kw)
+    assert np.array_equal(s.last.admm_iters[:, 0].cpu().numpy(), g["iters"]), "ADMM_LQT_DP iteration counts differ"
+    assert np.abs(x.cpu().numpy().reshape(3, N, n) - g["x"]).max() < 1e-9
+    assert np.abs(u.cpu().numpy().reshape(3, N, m) - g["u"]).max() < 1e-8
+    assert np.abs(K.cpu().numpy() - g["K"]).max() / np.abs(g["K"]).max() < 1e-9
+    x, u = s.ADMM_LQT_Batch(g["x0"], **kw)
+    assert np.array_equal(s.last.admm_iters[:, 0].cpu().numpy(), g["iters_batch"]), "ADMM_LQT_Batch iteration counts differ"
+    assert np.abs(x.cpu().numpy().reshape(3, N, n) - g["x_batch"]).max() < 1e-9
+    assert np.abs(u.cpu().numpy().reshape(3, N, m) - g["u_batch"]).max() < 1e-8

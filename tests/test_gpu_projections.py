@@ -63,3 +63,25 @@ def test_row_projections_vs_numpy():
     out = Pj.project_soc_unit_batch(torch.tensor([[3.0, 0.0, -1.0], [0.5, 0.0, 1.0], [3.0, 0.0, 1.0]], device="cuda:0",
                                                  dtype=torch.float64)).cpu().numpy()
     assert np.array_equal(out[0], [0, 0, 0]) and np.array_equal(out[1], [0.5, 0, 1.0]) and np.allclose(out[2], [2, 0, 2])
+
+
+def test_parameterised_projections_vs_reference_golden(golden):
+    """project_multilinear, project_affine, project_soc (inner ADMM, identical iterates up to rounding) and
+    project_block_lower_triangular (isls/projections.py:46-68, 163-232, 277-286) against outputs of the unmodified
+    reference on the same seeded rows (tests/golden/projections_ex.npz)."""
+    import torch
+    from isls_b200 import projections as Pj
+    g = golden("projections_ex")
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda:0")
+    ml = Pj.project_multilinear_batch(t(g["x"]), g["A"], g["l"], g["u"]).cpu().numpy()
+    assert np.abs(ml - g["ml"]).max() < 1e-12
+    Ax = ml @ g["A"].T                                         # rows that were outside now sit on the violated bound
+    assert np.all(Ax < g["u"] + 1e-9) and np.all(Ax > g["l"] - 1e-9)
+    aff = Pj.project_affine_batch(t(g["x"]), g["a"], 0.7, -0.4, 0.6).cpu().numpy()
+    assert np.abs(aff - g["aff"]).max() < 1e-13
+    soc, its = Pj.project_soc_batch(t(g["z0"]), g["As"], g["bs"], rho=2.0, max_iter=100, tol=1e-6, want_iters=True)
+    assert np.abs(soc.cpu().numpy() - g["soc"]).max() < 1e-10 and 1 <= its <= 100
+    soc1 = Pj.project_soc_batch(t(g["z0"][3:4]), g["As"], g["bs"], rho=2.0, max_iter=100, tol=1e-6).cpu().numpy()
+    assert np.abs(soc1[0] - g["soc1"]).max() < 1e-10          # a single row stops on its own residual (differs from row 3 of the batch call)
+    blt = Pj.project_block_lower_triangular(t(g["Z"]), 4, 2, 6).cpu().numpy()
+    assert np.array_equal(blt, g["blt"])

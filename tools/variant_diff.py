@@ -10,7 +10,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
-    "plain": {"ISLS_FF_STAGES": "0", "ISLS_ADMM_STAGES": "0", "ISLS_COLS_STAGES": "0", "ISLS_LQT_SMEM": "0", "ISLS_OVERLAP": "0"},
+    "plain": {"ISLS_FF_STAGES": "0", "ISLS_ADMM_STAGES": "0", "ISLS_COLS_STAGES": "0", "ISLS_LQT_SMEM": "0", "ISLS_OVERLAP": "0", "ISLS_SLS_CTRL_DENSE": "1"},
     "auto": {},
     "tma_nojc": {"ISLS_FF_MODE": "2", "ISLS_FF_JC": "0"},
     "staged": {"ISLS_FF_MODE": "0"},
