@@ -3232,7 +3232,8 @@ static int launch_ff(const Dev &d, cudaStream_t s) {
       constexpr bool PX_ = decltype(px)::value, JC_ = decltype(jcc)::value;
       if (try_ff_tma<M, PX_, JC_, 4, 4>(d, s, tiles, sms, false, done) || done) return 0;
       if (try_ff_tma<M, PX_, JC_, 3, 3>(d, s, tiles, sms, false, done) || done) return 0;
-      if (try_ff_tma<M, PX_, JC_, 2, 2>(d, s, tiles, sms, force, done) || done) return 0;
+      if (try_ff_tma<M, PX_, JC_, 2, 2>(d, s, tiles, sms, false, done) || done) return 0;
+      if (try_ff_tma<M, PX_, JC_, 1, 2>(d, s, tiles, sms, force, done) || done) return 0;   // large slabs (arm: 17.7 KB per step)
       return 0;
     };
     if (d.proj_x) { if (jc) go(std::true_type{}, std::true_type{}); else go(std::true_type{}, std::false_type{}); }
