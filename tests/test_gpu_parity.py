@@ -523,3 +523,28 @@ def test_lqt_general_lti_pair_vs_reference_golden(golden):
     assert np.array_equal(s.last.admm_iters[:, 0].cpu().numpy(), g["iters_batch"]), "ADMM_LQT_Batch iteration counts differ"
     assert np.abs(x.cpu().numpy().reshape(3, N, n) - g["x_batch"]).max() < 1e-9
     assert np.abs(u.cpu().numpy().reshape(3, N, m) - g["u_batch"]).max() < 1e-8
+
+
+def test_non_default_device_matches_device_0():
+    """A solver on cuda:1 while cuda:0 is the current device: the plan's constant block, the workspace and the per-device
+    shared-memory opt-ins must all follow the solver's device.  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    torch.cuda.set_device(0)
+    p = P.car_batch(40, I_o=4, I_a=3)
+    a = _gpu().run_ilqr_admm(p, device="cuda:0")
+    b = _gpu().run_ilqr_admm(p, device="cuda:1")
+    for k in ("x", "u", "cost_log", "z_u", "alpha_idx"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    q = P.arm_batch(40, I_o=3, I_a=3)                    # > 48 KB of dynamic shared memory (TMA ring of the arm)
+    a = _gpu().run_ilqr_admm(q, device="cuda:0")
+    b = _gpu().run_ilqr_admm(q, device="cuda:1")
+    assert np.array_equal(a["u"], b["u"]) and np.array_equal(a["cost_log"], b["cost_log"], equal_nan=True)
+    d = _gpu().run_lqt_admm_dp(P.di_batch(5, max_iter=60), device="cuda:1")
+    d0 = _gpu().run_lqt_admm_dp(P.di_batch(5, max_iter=60), device="cuda:0")
+    assert np.array_equal(d["u"], d0["u"])
+    from isls_b200 import _lib, solver as S
+    plan = S.Plan("car", p["N"], 4, 2, p["dt"], p["Qdiag"], p["seq"], p["u_std"], p["L"], device="cuda:1")
+    with pytest.raises(_lib.IslsError):
+        S.BatchSolver(plan, 8, "cuda:0")
