@@ -1297,6 +1297,337 @@ __global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
   }
 }
 
+// ---- Warp-split form of k_ff_tma for models with larger state (arm: n = 9, m = 3) at small batches: G warps share one
+// tile.  Lane = problem as everywhere else (same tile-blocked layout, same TMA-staged operand ring), but the rows of the
+// n-sized algebra are split over the warps - warp w owns the components i with i mod G = w of v, qx, cx, dx - and the
+// recursion state (v in the backward sweep, dx in the forward one) is exchanged through shared memory with one CTA
+// barrier per time step.  The m-sized algebra (qu, k, the refinement step) is computed by every warp (it is cheaper than
+// a second exchange).  Every output element is accumulated in the same order as in ff_step / mat_Ax_Bu, so the results
+// are bit-identical to the one-thread-per-trajectory kernels; what changes is that a lone warp's 500-instruction step
+// becomes four ~120-instruction streams on four SM sub-partitions.  (north_star: "one warp or thread-block per
+// trajectory ... the small dense algebra split across it"; here a thread block per TILE of trajectories, so the loads
+// stay full 256-byte lines.)
+template <class M, bool PX, bool JC, int G, int TC, int NST>
+__global__ void __launch_bounds__(TILE * G, 4) k_ff_ws(Dev d) {
+  constexpr int n = M::n, m = M::m, nt = NTRI(M::m), NJ = M::NJA;
+  constexpr bool XB = !JC || PX;
+  constexpr int oJ = 0, oX = oJ + (JC ? NJ : 0), oU = oX + (XB ? n : 0), oQx = oU + m, oQu = oQx + m * n,
+                oQi = oQu + nt, oRu = oQi + nt, oRx = oRu + m, SB = oRx + (PX ? n : 0);
+  constexpr int fK = 0, fk = fK + m * n, fU = fk + m, fRu = fU + m, fJ = fRu + m, SF = fJ + (JC ? NJ : n);
+  constexpr int NSTF_ = (NST * SB) / SF, NSTF = NSTF_ > 8 ? 8 : NSTF_;
+  static_assert(SF <= SB, "forward slab must fit the backward slab");
+  extern __shared__ __align__(128) double smem_ffw[];
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_ffw);     // [NST] backward, [8] forward
+  double *ring = smem_ffw + 16;
+  double *xch = ring + (size_t)NST * TC * SB * TILE;      // [2][n][TILE] exchange buffer of the recursion state
+  double *s_rhu = xch + 2 * n * TILE;
+  const int N = d.N;
+  double *s_rhx = s_rhu + (size_t)N * m;
+  int *s_qnz = reinterpret_cast<int *>(s_rhx + (PX ? (size_t)N * n : 0));
+  int *s_seq = s_qnz + N;
+  const int lane = threadIdx.x, w = threadIdx.y, tid = w * TILE + lane;
+  const bool leader = tid == 0;
+  const int ntiles = (d.tile1 - d.tile0 + d.tstep - 1) / d.tstep;
+  if ((int)blockIdx.x >= ntiles) return;
+  for (int q = tid; q < N * m; q += TILE * G) s_rhu[q] = d.proj_u ? d.rho_u[q] : 0.0;
+  if (PX)
+    for (int q = tid; q < N * n; q += TILE * G) s_rhx[q] = d.rho_x[q];
+  for (int q = tid; q < N; q += TILE * G) { s_qnz[q] = d.qnz[q]; s_seq[q] = d.seq[q]; }
+  if (leader) {
+#pragma unroll
+    for (int i = 0; i < NST + 8; i++) mbar_init(&bar[i], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  unsigned gb = 0, gf = 0;
+  auto own = [&](int i) -> bool { return (i % G) == w; };
+  for (int it = blockIdx.x; it < ntiles; it += gridDim.x) {
+    const int tile = d.tile0 + it * d.tstep;
+    TileCtx<M> c(d, tile, lane);
+    const bool live = !(d.odone[c.b] || d.adone[c.b]);
+    if (!__syncthreads_or(live)) continue;
+    const double *xh = c.at(d.xh, d, n);
+    const double *zs = d.zs + (size_t)tile * d.n_via * n * TILE + c.lane;
+    double *kk = c.at(d.kk, d, m), *du = c.at(d.du, d, m);
+    const size_t tb = (size_t)tile * N * TILE;
+    const double *t_xh = d.xh + tb * n, *t_uh = d.uh + tb * m, *t_Qx = d.Qux + tb * (m * n), *t_Qu = d.Quu + tb * nt,
+                 *t_Qi = d.Qui + tb * nt, *t_ru = d.rgu + tb * m, *t_rx = PX ? d.rgx + tb * n : nullptr,
+                 *t_K = d.Kg + tb * (m * n), *t_kk = d.kk + tb * m, *t_J = JC ? d.Jc + tb * NJ : nullptr;
+    const bool pu = d.proj_u != 0;
+    constexpr unsigned ROWB = TILE * sizeof(double);
+    auto copy = [&](double *stage, int off, const double *src, int D, int t_lo, int cnt, unsigned long long *b) {
+      bulk_g2s(stage + (size_t)off * TC * TILE, src + (size_t)t_lo * D * TILE, (unsigned)(cnt * D) * ROWB, b);
+    };
+    const int nchb = (N - 1 + TC - 1) / TC;
+    auto issue_b = [&](int ch) {                            // leader only
+      const int st = (int)((gb + ch) % NST), t_hi = N - 2 - ch * TC, t_lo = max(0, t_hi - TC + 1), cnt = t_hi - t_lo + 1;
+      double *sb = ring + (size_t)st * TC * SB * TILE;
+      const int rows = (JC ? NJ : 0) + (XB ? n : 0) + m + m * n + 2 * nt + (pu ? m : 0) + (PX ? n : 0);
+      mbar_expect_tx(&bar[st], (unsigned)(cnt * rows) * ROWB);
+      if (JC) copy(sb, oJ, t_J, NJ, t_lo, cnt, &bar[st]);
+      if (XB) copy(sb, oX, t_xh, n, t_lo, cnt, &bar[st]);
+      copy(sb, oU, t_uh, m, t_lo, cnt, &bar[st]);
+      copy(sb, oQx, t_Qx, m * n, t_lo, cnt, &bar[st]);
+      copy(sb, oQu, t_Qu, nt, t_lo, cnt, &bar[st]);
+      copy(sb, oQi, t_Qi, nt, t_lo, cnt, &bar[st]);
+      if (pu) copy(sb, oRu, t_ru, m, t_lo, cnt, &bar[st]);
+      if (PX) copy(sb, oRx, t_rx, n, t_lo, cnt, &bar[st]);
+    };
+    if (leader) {
+#pragma unroll
+      for (int i = 0; i < NST; i++)
+        if (i < nchb) issue_b(i);
+    }
+    double A[n][n], Bm[n][m];
+    init_AB<M>(A, Bm);
+    double v[n], rw2[m], rw[m];
+#pragma unroll
+    for (int j = 0; j < m; j++) { rw[j] = d.Rw[j]; rw2[j] = 2.0 * (d.u_std * rw[j]); }
+    // cx_i (one component) and cu (all m) with the arithmetic of the other ff variants
+    auto cx_of = [&](int t, int i, double xi, double rxi, int qz, int sq) -> double {
+      double cxi = qz ? ff_cx_quad(d.qd[t * n + i], xi, EL(zs, n, sq, i)) : 0.0;
+      if (PX) cxi = ff_pen(cxi, s_rhx[t * n + i], xi, rxi);
+      return cxi;
+    };
+    auto cu_of = [&](int t, const double (&u)[m], const double (&ru)[m], double (&cu)[m]) {
+#pragma unroll
+      for (int j = 0; j < m; j++) {
+        double g = __dmul_rn(rw2[j], u[j]);
+        if (pu) g = ff_pen(g, s_rhu[t * m + j], u[j], ru[j]);
+        cu[j] = g;
+      }
+    };
+    {   // terminal step N-1: every warp computes the whole v (plain loads; once per launch)
+      double u[m], ru[m], cu[m];
+      const int qz = s_qnz[N - 1], sq = s_seq[N - 1];
+#pragma unroll
+      for (int i = 0; i < n; i++) {
+        const double xi = EL(xh, n, N - 1, i), rxi = PX ? d.rgx[tb * n + ((size_t)(N - 1) * n + i) * TILE + lane] : 0.0;
+        v[i] = cx_of(N - 1, i, xi, rxi, qz, sq);
+      }
+#pragma unroll
+      for (int j = 0; j < m; j++) {
+        u[j] = t_uh[((size_t)(N - 1) * m + j) * TILE + lane];
+        ru[j] = pu ? t_ru[((size_t)(N - 1) * m + j) * TILE + lane] : 0.0;
+      }
+      cu_of(N - 1, u, ru, cu);
+#pragma unroll
+      for (int j = 0; j < m; j++) {
+        const double cuu = __dmul_rn(2.0, __fma_rn(d.u_std, rw[j], d.rho_u[(N - 1) * m + j]));
+        if (live && w == 0) EL(kk, m, N - 1, j) = d.last_stage_dp ? 0.0 : -cu[j] / cuu;
+      }
+    }
+    int xb = 0;                                             // exchange buffer of this step
+    for (int ch = 0; ch < nchb; ch++) {
+      const int st = (int)((gb + ch) % NST), t_hi = N - 2 - ch * TC, t_lo = max(0, t_hi - TC + 1);
+      const double *sb = ring + (size_t)st * TC * SB * TILE + lane;
+      mbar_wait(&bar[st], (unsigned)(((gb + ch) / NST) & 1));
+#pragma unroll 1
+      for (int t = t_hi; t >= t_lo; t--) {
+        const int tt = t - t_lo;
+        double u[m], ru[m], J[NJ], cu[m], Quu[m][m], Qui[m][m], qu[m], k0[m], wv[m], kt[m];
+        const int qz = s_qnz[t], sq = s_seq[t];
+#pragma unroll
+        for (int j = 0; j < m; j++) {
+          u[j] = sb[(size_t)(oU * TC + tt * m + j) * TILE];
+          ru[j] = pu ? sb[(size_t)(oRu * TC + tt * m + j) * TILE] : 0.0;
+        }
+#pragma unroll
+        for (int a = 0; a < m; a++)
+#pragma unroll
+          for (int b2 = 0; b2 <= a; b2++) {
+            Quu[a][b2] = sb[(size_t)(oQu * TC + tt * nt + tri(a, b2)) * TILE]; Quu[b2][a] = Quu[a][b2];
+            Qui[a][b2] = sb[(size_t)(oQi * TC + tt * nt + tri(a, b2)) * TILE]; Qui[b2][a] = Qui[a][b2];
+          }
+        if (JC) {
+#pragma unroll
+          for (int q = 0; q < NJ; q++) J[q] = sb[(size_t)(oJ * TC + tt * NJ + q) * TILE];
+        } else {
+          double x[n];
+#pragma unroll
+          for (int i = 0; i < n; i++) x[i] = sb[(size_t)(oX * TC + tt * n + i) * TILE];
+          M::jac(x, u, J, d.dt);
+        }
+        M::expand(J, A, Bm, d.dt);
+        cu_of(t, u, ru, cu);
+        // ff_step, m-sized part on every warp: qu = cu + B'v, k0 = -Quu^-1 qu, w = qu + Quu k0, k = k0 - Quu^-1 w
+        mat_Bt_v<M>(Bm, v, qu);
+#pragma unroll
+        for (int j = 0; j < m; j++) qu[j] += cu[j];
+#pragma unroll
+        for (int a = 0; a < m; a++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int b2 = 0; b2 < m; b2++) acc = fma(Qui[a][b2], qu[b2], acc);
+          k0[a] = -acc;
+        }
+#pragma unroll
+        for (int a = 0; a < m; a++) {
+          double acc = qu[a];
+#pragma unroll
+          for (int b2 = 0; b2 < m; b2++) acc = fma(Quu[a][b2], k0[b2], acc);
+          wv[a] = acc;
+        }
+#pragma unroll
+        for (int a = 0; a < m; a++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int b2 = 0; b2 < m; b2++) acc = fma(Qui[a][b2], wv[b2], acc);
+          kt[a] = k0[a] - acc;
+        }
+        if (live && w == 0) {
+#pragma unroll
+          for (int j = 0; j < m; j++) EL(kk, m, t, j) = kt[j];
+        }
+        // n-sized part, own rows: qx_i = cx_i + (A'v)_i, v_i <- qx_i + sum_a Qux[a][i] k[a]
+        double *xo = xch + (size_t)xb * n * TILE + lane;
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+          if (own(i)) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < n; k++) {
+              if (M::am(k, i) == MO) acc += v[k];
+              else if (M::am(k, i) == MV) acc = fma(A[k][i], v[k], acc);
+            }
+            double xi = 0.0, rxi = 0.0;
+            if (XB) xi = sb[(size_t)(oX * TC + tt * n + i) * TILE];
+            else if (qz) xi = EL(xh, n, t, i);
+            if (PX) rxi = sb[(size_t)(oRx * TC + tt * n + i) * TILE];
+            double vi = acc + cx_of(t, i, xi, rxi, qz, sq);
+#pragma unroll
+            for (int a = 0; a < m; a++) vi = fma(sb[(size_t)(oQx * TC + tt * (m * n) + a * n + i) * TILE], kt[a], vi);
+            xo[(size_t)i * TILE] = vi;
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < n; i++) v[i] = xo[(size_t)i * TILE];
+        xb ^= 1;
+      }
+      // the per-step barrier above also means every warp is done with stage `st`
+      if (leader && ch + NST < nchb) issue_b(ch + NST);
+    }
+    gb += (unsigned)nchb;
+    fence_proxy_async();                                    // k (written above by warp 0) is read through the async proxy below
+    __syncthreads();
+    // ---- forward sweep
+    const int nchf = (N + TC - 1) / TC;
+    unsigned long long *barf = bar + NST;
+    auto issue_f = [&](int ch) {                            // leader only
+      const int st = (int)((gf + ch) % NSTF), t_lo = ch * TC, cnt = min(TC, N - t_lo);
+      double *sf = ring + (size_t)st * TC * SF * TILE;
+      const int rows = m * n + m + m + (pu ? m : 0) + (JC ? NJ : n);
+      mbar_expect_tx(&barf[st], (unsigned)(cnt * rows) * ROWB);
+      copy(sf, fK, t_K, m * n, t_lo, cnt, &barf[st]);
+      copy(sf, fk, t_kk, m, t_lo, cnt, &barf[st]);
+      copy(sf, fU, t_uh, m, t_lo, cnt, &barf[st]);
+      if (pu) copy(sf, fRu, t_ru, m, t_lo, cnt, &barf[st]);
+      if (JC) copy(sf, fJ, t_J, NJ, t_lo, cnt, &barf[st]);
+      else copy(sf, fJ, t_xh, n, t_lo, cnt, &barf[st]);
+    };
+    if (leader) {
+#pragma unroll
+      for (int i = 0; i < NSTF; i++)
+        if (i < nchf) issue_f(i);
+    }
+    double dx[n];
+#pragma unroll
+    for (int i = 0; i < n; i++) dx[i] = 0.0;
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0;
+    const bool polys = w == G - 1;                          // the warp with the fewest rows accumulates the cost polynomials
+    for (int ch = 0; ch < nchf; ch++) {
+      const int st = (int)((gf + ch) % NSTF), t_lo = ch * TC, cnt = min(TC, N - t_lo);
+      const double *sf = ring + (size_t)st * TC * SF * TILE + lane;
+      mbar_wait(&barf[st], (unsigned)(((gf + ch) / NSTF) & 1));
+#pragma unroll 1
+      for (int tt = 0; tt < cnt; tt++) {
+        const int t = t_lo + tt;
+        double duv[m], u[m];
+#pragma unroll
+        for (int a = 0; a < m; a++) {
+          u[a] = sf[(size_t)(fU * TC + tt * m + a) * TILE];
+          double acc = 0.0;
+          if (t < N - 1) {
+#pragma unroll
+            for (int j = 0; j < n; j++) acc = fma(sf[(size_t)(fK * TC + tt * (m * n) + a * n + j) * TILE], dx[j], acc);
+          }
+          duv[a] = acc + sf[(size_t)(fk * TC + tt * m + a) * TILE];
+        }
+        if (live && w == 0) {
+#pragma unroll
+          for (int a = 0; a < m; a++) EL(du, m, t, a) = duv[a];
+        }
+        if (polys) {
+#pragma unroll
+          for (int a = 0; a < m; a++) {
+            r0 = fma(rw[a] * u[a], u[a], r0);
+            r1 = fma(rw[a] * u[a], duv[a], r1);
+            r2 = fma(rw[a] * duv[a], duv[a], r2);
+            if (pu) {
+              const double rho = s_rhu[t * m + a], e = u[a] - sf[(size_t)(fRu * TC + tt * m + a) * TILE];
+              c0 = fma(rho * e, e, c0);
+              c1 = fma(2.0 * rho * e, duv[a], c1);
+              c2 = fma(rho * duv[a], duv[a], c2);
+            }
+          }
+        }
+        if (t < N - 1) {
+          double J[NJ];
+          if (JC) {
+#pragma unroll
+            for (int q = 0; q < NJ; q++) J[q] = sf[(size_t)(fJ * TC + tt * NJ + q) * TILE];
+          } else {
+            double x[n];
+#pragma unroll
+            for (int i = 0; i < n; i++) x[i] = sf[(size_t)(fJ * TC + tt * n + i) * TILE];
+            M::jac(x, u, J, d.dt);
+          }
+          M::expand(J, A, Bm, d.dt);
+          double *xo = xch + (size_t)xb * n * TILE + lane;
+#pragma unroll
+          for (int i = 0; i < n; i++) {
+            if (own(i)) {                                  // row i of mat_Ax_Bu
+              double acc = 0.0;
+#pragma unroll
+              for (int k = 0; k < n; k++) {
+                if (M::am(i, k) == MO) acc += dx[k];
+                else if (M::am(i, k) == MV) acc = fma(A[i][k], dx[k], acc);
+              }
+#pragma unroll
+              for (int k = 0; k < m; k++) {
+                if (M::bm(i, k) == MO) acc += duv[k];
+                else if (M::bm(i, k) == MV) acc = fma(Bm[i][k], duv[k], acc);
+              }
+              xo[(size_t)i * TILE] = acc;
+            }
+          }
+          __syncthreads();
+#pragma unroll
+          for (int i = 0; i < n; i++) dx[i] = xo[(size_t)i * TILE];
+          xb ^= 1;
+        }
+      }
+      __syncthreads();                                      // (the last step of the sweep has no exchange barrier)
+      if (leader && ch + NSTF < nchf) issue_f(ch + NSTF);
+    }
+    if (live && polys) {
+      const size_t S = (size_t)d.T * TILE;
+      r0 *= d.u_std;
+      r1 *= 2.0 * d.u_std;
+      r2 *= d.u_std;
+      d.cq[c.b] = c0 + r0;
+      d.cq[S + c.b] = c1 + r1;
+      d.cq[2 * S + c.b] = c2 + r2;
+      d.cq[3 * S + c.b] = r0;
+      d.cq[4 * S + c.b] = r1;
+      d.cq[5 * S + c.b] = r2;
+    }
+    gf += (unsigned)nchf;
+    __syncthreads();
+  }
+}
+
 // `fuse` != 0: the CTA finishes with the streaming ADMM z / lambda / reg update of the winner (control-only
 // projections).  PX = the plan has a state projection (compile-time, so the control-only kernel carries no penalty
 // accumulators or reg_x operands).  Every thread of the CTA runs the rollout loop (it contains CTA barriers); lanes
@@ -3185,6 +3516,25 @@ static void launch_kpass(const Dev &d, cudaStream_t s) {
   else k_kpass<M, false><<<tp_grid(d), tp_block(), 0, s>>>(d);
 }
 
+// k_ff_ws launcher for one ring shape (see try_ff_tma)
+template <class M, bool PX, bool JC, int G, int TC, int NST>
+static int try_ff_ws(const Dev &d, cudaStream_t s, int tiles, int sms, bool force, bool &launched) {
+  constexpr int n = M::n, m = M::m, nt = NTRI(M::m), NJ = M::NJA;
+  constexpr int SB = (JC ? NJ : 0) + ((!JC || PX) ? n : 0) + m + m * n + 2 * nt + m + (PX ? n : 0);
+  constexpr size_t ring = (size_t)NST * TC * SB * TILE * sizeof(double);
+  if constexpr (ring <= 200 * 1024) {
+    const size_t smem = 128 + ring + 2 * n * TILE * sizeof(double) + (size_t)d.N * (m + (PX ? n : 0)) * sizeof(double) +
+                        2 * (size_t)d.N * sizeof(int);
+    if (smem > 226 * 1024) return 0;
+    const long long per_sm = std::min<long long>(4, (227 * 1024) / (long long)(smem + 1024));
+    if (!force && per_sm * sms < tiles) return 0;
+    if (ensure_dyn_smem<k_ff_ws<M, PX, JC, G, TC, NST>>((int)smem)) return 1;
+    k_ff_ws<M, PX, JC, G, TC, NST><<<tiles, dim3(TILE, G), smem, s>>>(d);
+    launched = true;
+  }
+  return 0;
+}
+
 // ff-pass launcher: plain kernel for large batches (bandwidth-bound), cp.async-staged kernel for small ones
 template <class M>
 static int launch_ff(const Dev &d, cudaStream_t s) {
@@ -3228,6 +3578,20 @@ static int launch_ff(const Dev &d, cudaStream_t s) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const bool jc = d.Jc != nullptr && ff_jc != 0, force = ff_mode == 2;
     bool done = false;
+    if constexpr (M::n >= 6) {
+      // larger models (arm): the rows of the n-sized algebra split over 4 warps per tile (k_ff_ws)
+      static const int ff_ws = ovl_env("ISLS_FF_WS", 1);
+      if (ff_ws && jc && d.cost_kind == ISLS_COST_QUADRATIC) {
+        auto gw = [&](auto px) -> int {
+          constexpr bool PX_ = decltype(px)::value;
+          if (try_ff_ws<M, PX_, true, 4, 2, 2>(d, s, tiles, sms, false, done) || done) return 0;
+          if (try_ff_ws<M, PX_, true, 4, 1, 2>(d, s, tiles, sms, false, done) || done) return 0;
+          return 0;
+        };
+        if (d.proj_x) gw(std::true_type{}); else gw(std::false_type{});
+        if (done) return 0;
+      }
+    }
     auto go = [&](auto px, auto jcc) -> int {
       constexpr bool PX_ = decltype(px)::value, JC_ = decltype(jcc)::value;
       if (try_ff_tma<M, PX_, JC_, 4, 4>(d, s, tiles, sms, false, done) || done) return 0;
