@@ -3579,8 +3579,11 @@ static int launch_ff(const Dev &d, cudaStream_t s) {
     const bool jc = d.Jc != nullptr && ff_jc != 0, force = ff_mode == 2;
     bool done = false;
     if constexpr (M::n >= 6) {
-      // larger models (arm): the rows of the n-sized algebra split over 4 warps per tile (k_ff_ws)
-      static const int ff_ws = ovl_env("ISLS_FF_WS", 1);
+      // larger models (arm): the rows of the n-sized algebra split over 4 warps per tile (k_ff_ws).  Off by default:
+      // bit-identical but not faster - at C3's size the arm's ff-pass is HBM-bound (1.45 GB per launch at 5.9 TB/s),
+      // at smaller ones its step time is the TMA round trip of the shallow ring its 17.7 KB per step leave room for
+      // (profiles/r2_tuning_log.md, section 2)
+      static const int ff_ws = ovl_env("ISLS_FF_WS", 0);
       if (ff_ws && jc && d.cost_kind == ISLS_COST_QUADRATIC) {
         auto gw = [&](auto px) -> int {
           constexpr bool PX_ = decltype(px)::value;
