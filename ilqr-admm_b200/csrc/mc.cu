@@ -364,3 +364,153 @@ extern "C" int isls_project_rows_ex_f64(const isls_proj_params *pp, int64_t rows
   CK(cudaGetLastError());
   return ISLS_OK;
 }
+
+// ---- generic project_set_convex (isls/projections.py:289-374) over up to 4 sets {A_i x + b_i in C_i}, each C_i one of the
+// primitive row projections (bound / quadratic shell / SOC / infinity-norm shell / unit ball, batch semantics), all rows
+// projected together by one CTA (the stop rule is a maximum over sets and rows).
+#define PSC_MAXS 4
+struct ProjSet {
+  int K, dim, max_iter;
+  int ra[PSC_MAXS], kind[PSC_MAXS];
+  double A[PSC_MAXS][PROJ_MAXK][PROJ_MAXD], b[PSC_MAXS][PROJ_MAXK];
+  double p0[PSC_MAXS][PROJ_MAXK], p1[PSC_MAXS][PROJ_MAXK], l[PSC_MAXS], u[PSC_MAXS];
+  int has_p0[PSC_MAXS];
+  double inv[PROJ_MAXD][PROJ_MAXD];
+  double rho, thr;
+};
+__device__ static void proj_primitive(int kind, int d, const double *v_in, const double *p0, const double *p1, int has_p0,
+                                      double l, double u, double *z) {
+  double v[PROJ_MAXK];
+  for (int i = 0; i < d; i++) v[i] = v_in[i];
+  if (kind == 0) {
+    for (int i = 0; i < d; i++) z[i] = fmin(fmax(v[i], p0[i]), p1[i]);
+  } else if (kind == 2) {
+    double ss = 0.0;
+    for (int i = 0; i < d; i++) { if (has_p0) v[i] -= p0[i]; ss += v[i] * v[i]; }
+    const double val = 0.5 * ss, nrm = sqrt(ss);
+    for (int i = 0; i < d; i++) z[i] = v[i];
+    if (val > u) for (int i = 0; i < d; i++) z[i] = v[i] * sqrt(2.0 * u) / nrm;
+    if (l > val) for (int i = 0; i < d; i++) z[i] = v[i] * sqrt(2.0 * l) / nrm;
+    if (has_p0) for (int i = 0; i < d; i++) z[i] += p0[i];
+  } else if (kind == 3) {
+    soc_unit_row(d - 1, v, z);
+  } else if (kind == 4) {
+    int j = 0;
+    double mx = -1.0;
+    for (int i = 0; i < d; i++) { if (has_p0) v[i] -= p0[i]; const double a = fabs(v[i]); if (a > mx) { mx = a; j = i; } }
+    for (int i = 0; i < d; i++) z[i] = v[i];
+    if (mx < l) z[j] = l * ((v[j] > 0.0) - (v[j] < 0.0));
+    for (int i = 0; i < d; i++) { z[i] = fmax(fmin(z[i], u), -u); if (has_p0) z[i] += p0[i]; }
+  } else {
+    double ss = 0.0;
+    for (int i = 0; i < d; i++) ss += v[i] * v[i];
+    const double nrm = sqrt(ss);
+    for (int i = 0; i < d; i++) z[i] = (nrm <= 1.0) ? v[i] : v[i] / nrm;
+  }
+}
+
+__global__ void k_project_set_convex(ProjSet P, int rows, const double *x, double *out, int *iters) {
+  __shared__ double red[32];
+  const int r = threadIdx.x, n = P.dim;
+  const bool act = r < rows;
+  double x0[PROJ_MAXD], xv[PROJ_MAXD], zi[PSC_MAXS][PROJ_MAXK], li[PSC_MAXS][PROJ_MAXK];
+  for (int i = 0; i < n; i++) { x0[i] = act ? x[(size_t)r * n + i] : 0.0; xv[i] = x0[i]; }
+  for (int s = 0; s < P.K; s++)
+    for (int e = 0; e < P.ra[s]; e++) {
+      double v = P.b[s][e];
+      for (int i = 0; i < n; i++) v += P.A[s][e][i] * xv[i];
+      zi[s][e] = v;
+      li[s][e] = 0.0;
+    }
+  double pm = 1e5, dm = 1e5;
+  int it = 0;
+  for (int j = 0; j < P.max_iter; j++) {
+    it = j + 1;
+    double rs[PROJ_MAXD];
+    for (int i = 0; i < n; i++) rs[i] = 0.0;
+    for (int s = 0; s < P.K; s++)
+      for (int e = 0; e < P.ra[s]; e++) {
+        const double w = (-P.b[s][e] + zi[s][e]) - li[s][e];
+        for (int i = 0; i < n; i++) rs[i] += P.A[s][e][i] * w;
+      }
+    for (int i = 0; i < n; i++) rs[i] = x0[i] + P.rho * rs[i];
+    for (int i = 0; i < n; i++) {
+      double v = 0.0;
+      for (int c = 0; c < n; c++) v += P.inv[i][c] * rs[c];
+      xv[i] = v;
+    }
+    double pmax = 0.0, dmax = 0.0;
+    for (int s = 0; s < P.K; s++) {
+      double axb[PROJ_MAXK], y[PROJ_MAXK], zn[PROJ_MAXK];
+      for (int e = 0; e < P.ra[s]; e++) {
+        double v = P.b[s][e];
+        for (int i = 0; i < n; i++) v += P.A[s][e][i] * xv[i];
+        axb[e] = v;
+        y[e] = v + li[s][e];
+      }
+      proj_primitive(P.kind[s], P.ra[s], y, P.p0[s], P.p1[s], P.has_p0[s], P.l[s], P.u[s], zn);
+      double ps = 0.0, dr[PROJ_MAXD];
+      for (int i = 0; i < n; i++) dr[i] = 0.0;
+      for (int e = 0; e < P.ra[s]; e++) {
+        const double pr = axb[e] - zn[e], dz = zn[e] - zi[s][e];
+        ps += pr * pr;
+        for (int i = 0; i < n; i++) dr[i] += P.A[s][e][i] * dz;
+        li[s][e] += pr;
+        zi[s][e] = zn[e];
+      }
+      double ds = 0.0;
+      for (int i = 0; i < n; i++) ds += (P.rho * dr[i]) * (P.rho * dr[i]);
+      pmax = fmax(pmax, sqrt(ps));
+      dmax = fmax(dmax, sqrt(ds));
+    }
+    const double pprev = pm, dprev = dm;
+    pm = block_max(act ? pmax : 0.0, red);
+    dm = block_max(act ? dmax : 0.0, red);
+    if (pm < P.thr && dm < P.thr) break;
+    if (j < P.max_iter - 1) {
+      const double pc = fabs(pprev - pm) / (pprev + 1e-30), dc = fabs(dprev - dm) / (dprev + 1e-30);
+      if (pc < 1e-5 && dc < 1e-5) break;
+    }
+  }
+  if (act)
+    for (int i = 0; i < n; i++) out[(size_t)r * n + i] = xv[i];
+  if (iters && r == 0) iters[0] = it;
+}
+
+extern "C" int isls_project_set_convex_f64(const isls_proj_set_params *pp, int64_t rows, int32_t dim, const double *x_dev,
+                                           double *out_dev, int32_t *iters_dev, void *stream) {
+  if (!pp || rows <= 0 || rows > 1024 || dim < 1 || dim > PROJ_MAXD || !x_dev || !out_dev)
+    return isls_fail(ISLS_E_INVALID, "bad size (rows <= 1024, dim <= 16) or NULL argument");
+  if (pp->struct_size != (uint32_t)sizeof(isls_proj_set_params))
+    return isls_fail(ISLS_E_INVALID, "isls_proj_set_params.struct_size mismatch (binding built against another isls_b200.h?)");
+  if (pp->n_sets < 1 || pp->n_sets > PSC_MAXS || pp->max_iter < 1) return isls_fail(ISLS_E_INVALID, "n_sets in 1..4, max_iter >= 1");
+  static ProjSet P;                 // ~6 KB: too large for the stack of every caller; filled and passed by value
+  memset(&P, 0, sizeof(P));
+  P.K = pp->n_sets; P.dim = dim; P.max_iter = pp->max_iter; P.rho = pp->rho; P.thr = pp->threshold;
+  for (int s = 0; s < P.K; s++) {
+    const isls_proj_set_entry &e = pp->sets[s];
+    if (e.rows < 1 || e.rows > PROJ_MAXK || !e.A) return isls_fail(ISLS_E_INVALID, "set: A missing or rows out of range (1..8)");
+    if (!(e.kind == 0 || e.kind == 2 || e.kind == 3 || e.kind == 4 || e.kind == 5))
+      return isls_fail(ISLS_E_UNSUPPORTED, "set kind must be bound (0), quadratic (2), soc_unit (3), square (4) or unit_ball (5)");
+    if (e.kind == 0 && (!e.p0 || !e.p1)) return isls_fail(ISLS_E_INVALID, "bound set needs p0 = lo, p1 = hi");
+    P.ra[s] = e.rows; P.kind[s] = e.kind; P.l[s] = e.l; P.u[s] = e.u; P.has_p0[s] = e.p0 != nullptr;
+    for (int a = 0; a < e.rows; a++) {
+      for (int i = 0; i < dim; i++) P.A[s][a][i] = e.A[a * dim + i];
+      P.b[s][a] = e.b ? e.b[a] : 0.0;
+      P.p0[s][a] = e.p0 ? e.p0[a] : 0.0;
+      P.p1[s][a] = e.p1 ? e.p1[a] : 0.0;
+    }
+  }
+  double Lm[PROJ_MAXD * PROJ_MAXD];
+  for (int i = 0; i < dim; i++)
+    for (int c = 0; c < dim; c++) {
+      double v = i == c ? 1.0 : 0.0;
+      for (int s = 0; s < P.K; s++)
+        for (int a = 0; a < P.ra[s]; a++) v += P.rho * P.A[s][a][i] * P.A[s][a][c];
+      Lm[i * dim + c] = v;
+    }
+  if (!gauss_jordan_inv(dim, Lm, P.inv)) return isls_fail(ISLS_E_INVALID, "I + rho sum A'A is singular");
+  k_project_set_convex<<<1, (unsigned)(((rows + 31) / 32) * 32), 0, (cudaStream_t)stream>>>(P, (int)rows, x_dev, out_dev, iters_dev);
+  CK(cudaGetLastError());
+  return ISLS_OK;
+}

@@ -61,6 +61,16 @@ class ProjParams(_Guarded):
                 ("x_dim", C.c_int32), ("u_dim", C.c_int32), ("N", C.c_int32)]
 
 
+class ProjSetEntry(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("rows", C.c_int32), ("A", C.c_void_p), ("b", C.c_void_p), ("p0", C.c_void_p),
+                ("p1", C.c_void_p), ("l", C.c_double), ("u", C.c_double)]
+
+
+class ProjSetParams(_Guarded):
+    _fields_ = [("struct_size", C.c_uint32), ("n_sets", C.c_int32), ("sets", ProjSetEntry * 4), ("rho", C.c_double),
+                ("threshold", C.c_double), ("max_iter", C.c_int32)]
+
+
 class SolveOut(_Guarded):
     _fields_ = [("struct_size", C.c_uint32)] + [(f, C.c_void_p) for f in OUT_FIELDS]
 
@@ -71,7 +81,7 @@ EXPORTS = ["isls_version", "isls_last_error_string", "isls_model_id", "isls_mode
            "isls_measure_fp64_tflops", "isls_profile_enable", "isls_profile_collect",
            "isls_sls_plan_create", "isls_sls_plan_destroy", "isls_sls_operators", "isls_sls_solve_f64",
            "isls_sls_admm_f64", "isls_sls_controller_f64", "isls_mc_rollout_f64", "isls_project_rows_f64",
-           "isls_isls_admm_solve_f64", "isls_sls_replan_f64", "isls_probe_overlap_f64", "isls_project_rows_ex_f64"]
+           "isls_isls_admm_solve_f64", "isls_sls_replan_f64", "isls_probe_overlap_f64", "isls_project_rows_ex_f64", "isls_project_set_convex_f64"]
 
 KERNEL_CLASSES = ["init", "kpass", "ff", "linesearch", "admm", "outer_end", "finalize", "backward_full", "accept",
                   "lqt", "compact", "isls_cols", "isls_update"]
@@ -128,6 +138,8 @@ def lib():
                                         C.c_double, C.c_void_p, C.c_void_p]
     L.isls_project_rows_ex_f64.argtypes = [C.POINTER(ProjParams), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p]
+    L.isls_project_set_convex_f64.argtypes = [C.POINTER(ProjSetParams), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]
     L.isls_profile_enable.argtypes = [C.c_int]
     L.isls_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     _lib = L

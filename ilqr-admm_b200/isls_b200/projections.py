@@ -181,6 +181,50 @@ def project_block_lower_triangular(z, x_dim, u_dim, N):
     return _rows_ex(8, z, blt=(x_dim, u_dim, N))
 
 
+_SET_KINDS = {"bound": 0, "quadratic": 2, "soc_unit": 3, "square": 4, "unit_ball": 5}
+
+
+def project_set_convex_batch(x0, As, bs, projections, rho=1.0, max_iter=200, threshold=1e-4, want_iters=False):
+    """isls/projections.py:289-374 on the device: rows x0 [rows <= 1024, dim] onto the intersection of the sets
+    {x : A_i x + b_i in C_i}.  `projections[i]` describes C_i by one of the primitive batch projections instead of a Python
+    callable: ("bound", lo, hi), ("quadratic", l, u[, center]), ("soc_unit",), ("square", l, u[, center]), ("unit_ball",)."""
+    import ctypes as C
+    from . import _lib
+    if not (isinstance(x0, torch.Tensor) and x0.is_cuda and x0.dtype == torch.float64 and x0.ndim == 2):
+        raise TypeError("device projections take a CUDA float64 tensor [rows, dim]")
+    if not (len(As) == len(bs) == len(projections)) or not 1 <= len(As) <= 4:
+        raise ValueError("1..4 sets, one (A, b, projection) each")
+    x0 = x0.contiguous()
+    dim = x0.shape[1]
+    keep = []
+
+    def hp(a, n):
+        keep.append(np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (n,))))
+        return keep[-1].ctypes.data
+    p = _lib.ProjSetParams(n_sets=len(As), rho=float(rho), threshold=float(threshold), max_iter=int(max_iter))
+    for i, (A, b, pr) in enumerate(zip(As, bs, projections)):
+        A = np.ascontiguousarray(np.atleast_2d(np.asarray(A, dtype=np.float64)))
+        if A.shape[1] != dim:
+            raise ValueError("A_%d must have %d columns" % (i, dim))
+        keep.append(A)
+        e = p.sets[i]
+        e.kind, e.rows, e.A, e.b = _SET_KINDS[pr[0]], A.shape[0], A.ctypes.data, hp(b, A.shape[0])
+        if pr[0] == "bound":
+            e.p0, e.p1 = hp(pr[1], A.shape[0]), hp(pr[2], A.shape[0])
+        elif pr[0] in ("quadratic", "square"):
+            e.l, e.u = float(pr[1]), float(pr[2])
+            if len(pr) > 3 and pr[3] is not None:
+                e.p0 = hp(pr[3], A.shape[0])
+    out = torch.empty_like(x0)
+    it = torch.zeros(1, dtype=torch.int32, device=x0.device)
+    with torch.cuda.device(x0.device):
+        rc = _lib.lib().isls_project_set_convex_f64(C.byref(p), x0.shape[0], dim, C.c_void_p(x0.data_ptr()),
+                                                    C.c_void_p(out.data_ptr()), C.c_void_p(it.data_ptr()),
+                                                    C.c_void_p(torch.cuda.current_stream(x0.device).cuda_stream))
+    _lib.check(rc, "isls_project_set_convex_f64")
+    return (out, int(it[0])) if want_iters else out
+
+
 class ObstacleSets:
     """Device descriptor of the notebooks' obstacle-avoidance state projection (Car/Iterative LQR with state
     constraints.ipynb cell 18): `project_set_convex(x, [I]*K, [0]*K, projections, rho, max_iter, threshold)` where

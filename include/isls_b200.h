@@ -349,6 +349,29 @@ typedef struct isls_proj_params {
 int isls_project_rows_ex_f64(const isls_proj_params *params, int64_t rows, int32_t dim, const double *x_dev,
                              double *out_dev, int32_t *iters_dev, void *stream);
 
+/* Generic project_set_convex (isls/projections.py:289-374): rows x0 onto the intersection of up to 4 sets
+ * {x : A_i x + b_i in C_i} by the reference's consensus ADMM, every C_i one of the primitive row projections of
+ * isls_project_rows_f64 (kind 0 bound with p0 = lo, p1 = hi [rows_i]; 2 quadratic shell l <= 0.5|y - p0|^2 <= u; 3 soc_unit;
+ * 4 infinity-norm shell l <= |y - p0|_inf <= u; 5 unit ball), batch semantics.  The stop rule is a maximum over sets and
+ * rows, so all rows (<= 1024) are projected together.  All pointers are HOST arrays. */
+typedef struct isls_proj_set_entry {
+  int32_t kind;          /* primitive projection of this set (see above) */
+  int32_t rows;          /* rows of A_i (<= 8) */
+  const double *A;       /* [rows, dim] */
+  const double *b;       /* [rows] or NULL = 0 */
+  const double *p0, *p1; /* [rows] parameters of the primitive, or NULL */
+  double l, u;
+} isls_proj_set_entry;
+typedef struct isls_proj_set_params {
+  uint32_t struct_size;  /* = sizeof(isls_proj_set_params) (ABI guard) */
+  int32_t n_sets;        /* 1..4 */
+  isls_proj_set_entry sets[4];
+  double rho, threshold;
+  int32_t max_iter;
+} isls_proj_set_params;
+int isls_project_set_convex_f64(const isls_proj_set_params *params, int64_t rows, int32_t dim, const double *x_dev,
+                                double *out_dev, int32_t *iters_dev, void *stream);
+
 /* ---- measurement helpers (bench.py roofline denominators; not part of the reference surface) ---- */
 /* kernel classes for per-kernel CUDA-event timing */
 #define ISLS_KC_INIT 0

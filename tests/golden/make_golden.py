@@ -606,6 +606,26 @@ def golden_lqt_lti():
     np.savez_compressed(os.path.join(OUT, "lqt_lti.npz"), **out)
 
 
+def golden_set_convex():
+    """project_set_convex of the unmodified reference (isls/projections.py:289-374) over three sets of different kinds: a
+    box on x itself, a quadratic shell of a 2-D linear image, a second-order cone of a 4-D affine image."""
+    S.load()
+    from isls.projections import project_quadratic_batch, project_set_convex, project_soc_unit
+    rng = np.random.default_rng(41)
+    x0 = rng.normal(0, 1.5, (50, 3))
+    A0, b0 = np.eye(3), np.zeros(3)
+    lo, hi = np.array([-0.8, -1.0, -0.5]), np.array([0.9, 0.7, 1.2])
+    A1, b1 = rng.normal(0, 1.0, (2, 3)), np.array([0.1, -0.2])
+    c1 = np.array([0.3, -0.1])
+    A2, b2 = rng.normal(0, 0.7, (4, 3)), np.array([0.0, 0.1, -0.1, 1.5])
+    projs = [lambda y: np.clip(y, lo, hi), lambda y: project_quadratic_batch(y - c1, 0.05, 0.8) + c1, project_soc_unit]
+    with S.quiet():
+        out = project_set_convex(x0.copy(), [A0, A1, A2], [b0, b1, b2], projs, rho=2.0, max_iter=150, threshold=1e-6)
+    np.savez_compressed(os.path.join(OUT, "set_convex.npz"), x0=x0, A0=A0, b0=b0, lo=lo, hi=hi, A1=A1, b1=b1, c1=c1, A2=A2,
+                        b2=b2, out=out)
+    print("set_convex: moved rows by up to %.3f" % np.abs(out - x0).max())
+
+
 if __name__ == "__main__":
     assert S.available(), "needs the reference tree"
     only = set(sys.argv[1:])                       # e.g. `make_golden.py tutorial` regenerates one fixture family
@@ -640,6 +660,8 @@ if __name__ == "__main__":
         golden_replan()
     if want("di_obstacles"):
         golden_di_obstacles()
+    if want("set_convex"):
+        golden_set_convex()
     if want("lqt_lti"):
         golden_lqt_lti()
     if want("projections_ex"):

@@ -78,7 +78,8 @@ def test_ctypes_struct_layouts_match_the_header():
     import tempfile
     L = _lib()
     structs = {"isls_problem_desc": L.ProblemDesc, "isls_solve_opts": L.SolveOpts, "isls_solve_out": L.SolveOut,
-               "isls_sls_admm_opts": L.SlsAdmmOpts}
+               "isls_sls_admm_opts": L.SlsAdmmOpts, "isls_proj_params": L.ProjParams,
+               "isls_proj_set_entry": L.ProjSetEntry, "isls_proj_set_params": L.ProjSetParams}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "isls_b200.h"', 'int main(void) {']
     for cname, ct in structs.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))

@@ -85,3 +85,17 @@ def test_parameterised_projections_vs_reference_golden(golden):
     assert np.abs(soc1[0] - g["soc1"]).max() < 1e-10          # a single row stops on its own residual (differs from row 3 of the batch call)
     blt = Pj.project_block_lower_triangular(t(g["Z"]), 4, 2, 6).cpu().numpy()
     assert np.array_equal(blt, g["blt"])
+
+
+def test_generic_project_set_convex_vs_reference_golden(golden):
+    """project_set_convex (isls/projections.py:289-374) over three sets of different kinds (box, quadratic shell with a
+    centre, second-order cone) against the unmodified reference on the same 50 rows."""
+    import torch
+    from isls_b200 import projections as Pj
+    g = golden("set_convex")
+    x0 = torch.as_tensor(g["x0"], device="cuda:0")
+    out, its = Pj.project_set_convex_batch(
+        x0, [g["A0"], g["A1"], g["A2"]], [g["b0"], g["b1"], g["b2"]],
+        [("bound", g["lo"], g["hi"]), ("quadratic", 0.05, 0.8, g["c1"]), ("soc_unit",)], rho=2.0, max_iter=150,
+        threshold=1e-6, want_iters=True)
+    assert np.abs(out.cpu().numpy() - g["out"]).max() < 1e-9 and 1 <= its <= 150
