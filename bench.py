@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-weak", action="store_true", help="skip the secondary weak-scaling measurement (N > 1)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work per reference step")
+    ap.add_argument("--cpu-total-seconds", type=float, default=150.0,
+                    help="bound on the timed CPU work of the whole reference run (per-step work shrinks with --steps)")
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "reference", "port"],
                     help="CPU arm: the unmodified reference in baseline/_ref (default when present) or the numpy port")
     return ap.parse_args()
@@ -177,7 +179,8 @@ def run_reference(a):
         kind = "reference" if ref_available() else "port"
     if kind == "reference" and not ref_available():
         raise SystemExit("baseline/_ref/isls is missing: run __graft_entry__.build() where /root/reference exists")
-    value, ms, desc = cpu_arm(kind, a.cpu_seconds, a.steps, a.warmup, fixed)
+    per_step = min(a.cpu_seconds, a.cpu_total_seconds / max(a.steps, 1))     # the whole run ends within a few minutes
+    value, ms, desc = cpu_arm(kind, per_step, a.steps, a.warmup, fixed)
     desc["riccati_pass_ms_one_core"] = round(cpu_riccati_pass_ms(), 3)
     if kind == "reference":                                 # the port beside it, one short step
         try:
