@@ -8,6 +8,7 @@
 // Box-Muller), so a run is reproducible from (seed, sample, step) - the reference uses the unseeded global numpy
 // generator, i.e. only its statistics are defined.
 #include <math.h>
+#include <vector>
 #include <stdint.h>
 
 #include "../../include/isls_b200.h"
@@ -484,7 +485,8 @@ extern "C" int isls_project_set_convex_f64(const isls_proj_set_params *pp, int64
   if (pp->struct_size != (uint32_t)sizeof(isls_proj_set_params))
     return isls_fail(ISLS_E_INVALID, "isls_proj_set_params.struct_size mismatch (binding built against another isls_b200.h?)");
   if (pp->n_sets < 1 || pp->n_sets > PSC_MAXS || pp->max_iter < 1) return isls_fail(ISLS_E_INVALID, "n_sets in 1..4, max_iter >= 1");
-  static ProjSet P;                 // ~6 KB: too large for the stack of every caller; filled and passed by value
+  std::vector<ProjSet> holder(1);   // ~7 KB: kept off the caller's stack, no static state (the library is re-entrant)
+  ProjSet &P = holder[0];
   memset(&P, 0, sizeof(P));
   P.K = pp->n_sets; P.dim = dim; P.max_iter = pp->max_iter; P.rho = pp->rho; P.thr = pp->threshold;
   for (int s = 0; s < P.K; s++) {
