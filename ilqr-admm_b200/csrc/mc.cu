@@ -122,6 +122,60 @@ extern "C" int isls_mc_rollout_f64(int32_t model_id, int32_t n, int32_t m, int32
   return ISLS_OK;
 }
 
+// ------------------------------------------------------------------------------------ get_AB of the notebooks
+// A_t = df/dx, B_t = df/du of the registered model at (x_t, u_t) for every row of x [rows, n], u [rows, m]: the device
+// form of the `get_AB(x_nom, u_nom)` callables the reference's callers pass (e.g. 3DoF robot notebooks cell 9,
+// iLQR_ADMM.ipynb cell 5), in the natural layouts A [rows, n, n], B [rows, n, m] that iSLSBase.AB takes
+// (isls/isls_base.py:133-158).  The solver kernels never need it (they linearise in registers); it feeds the
+// stage-level API (iSLS.AB, iSLS.controller).
+template <class M>
+__global__ void k_linearize(long long rows, double dt, const double *x, const double *u, double *A, double *Bm) {
+  constexpr int n = M::n, m = M::m;
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  double xv[n], uv[m], J[M::NJA], Am[n][n], Bv[n][m];
+#pragma unroll
+  for (int i = 0; i < n; i++) xv[i] = x[r * n + i];
+#pragma unroll
+  for (int j = 0; j < m; j++) uv[j] = u[r * m + j];
+#pragma unroll
+  for (int i = 0; i < n; i++) {
+#pragma unroll
+    for (int j = 0; j < n; j++) Am[i][j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int j = 0; j < m; j++) Bv[i][j] = 0.0;
+  }
+  M::jac(xv, uv, J, dt);
+  M::expand(J, Am, Bv, dt);
+#pragma unroll
+  for (int i = 0; i < n; i++) {
+#pragma unroll
+    for (int j = 0; j < n; j++)      // entries the model declares structurally zero / one are not written by expand
+      A[(r * n + i) * n + j] = M::am(i, j) == MZ ? 0.0 : M::am(i, j) == MO ? 1.0 : Am[i][j];
+#pragma unroll
+    for (int j = 0; j < m; j++) Bm[(r * n + i) * m + j] = M::bm(i, j) == MZ ? 0.0 : Bv[i][j];
+  }
+}
+
+extern "C" int isls_linearize_f64(int32_t model_id, int32_t n, int32_t m, double dt, int64_t rows, const double *x_dev,
+                                  const double *u_dev, double *A_dev, double *B_dev, void *stream) {
+  if (rows <= 0 || !x_dev || !u_dev || !A_dev || !B_dev) return isls_fail(ISLS_E_INVALID, "NULL argument or rows <= 0");
+  if (model_id == ISLS_MODEL_LTI) return isls_fail(ISLS_E_UNSUPPORTED, "an LTI model's A, B are its own constants");
+  if (isls_model_supported(model_id, n, m)) return isls_fail(ISLS_E_UNSUPPORTED, "unsupported (model, n, m)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((rows + 127) / 128);
+#define GO(MODEL) k_linearize<MODEL><<<grid, 128, 0, s>>>(rows, dt, x_dev, u_dev, A_dev, B_dev)
+  if (model_id == ISLS_MODEL_CAR) GO(CarModel);
+  else if (model_id == ISLS_MODEL_ARM3) GO(Arm3Model);
+  else if (model_id == ISLS_MODEL_TASSA_CAR) GO(TassaCarModel);
+  else if (m == 1) GO(DoubleIntModel<1>);
+  else if (m == 2) GO(DoubleIntModel<2>);
+  else GO(DoubleIntModel<3>);
+#undef GO
+  CK(cudaGetLastError());
+  return ISLS_OK;
+}
+
 // --------------------------------------------------------------------------- batched row projections
 // Device counterparts of the `_batch` projections of isls/projections.py, one row per thread (dim <= 16):
 //   kind 0 bound      np.clip(x, lo[dim], hi[dim])                                          projections.py:7-11

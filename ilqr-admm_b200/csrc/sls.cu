@@ -355,9 +355,11 @@ __global__ void k_sls_du(int Nm, int Nn, long long B, const double *Linv0, const
 // PHI_X columns are formed on the fly: PHI_X[:, j] = Sw[:, j] + Su PHI_U[:, j].
 __global__ void k_sls_controller(int n, int m, int N, int cfirst, const double *Sw, const double *Su,
                                  const double *PHI_shared, const double *phic, const double *du, double *PHIX_ws,
-                                 double *K, double *kff) {
+                                 double *K, double *kff, size_t sw_stride = 0, size_t su_stride = 0) {
   const int Nn = N * n, Nm = N * m;
   const long long b = blockIdx.x;
+  Sw += (size_t)b * sw_stride;          // per-problem operators (time-varying C, D of iSLS.controller); 0 = shared
+  Su += (size_t)b * su_stride;
   double *PX = PHIX_ws + (size_t)b * Nn * Nn;
   double *Kb = K + (size_t)b * Nm * Nn;
   auto phi = [&](int r, int col) -> double {
@@ -398,6 +400,42 @@ __global__ void k_sls_controller(int n, int m, int N, int cfirst, const double *
     double acc = d[r];
     for (int k = 0; k < Nn; k++) acc = fma(-Kb[(size_t)r * Nn + k], sv[k], acc);
     kff[(size_t)b * Nm + r] = acc;
+  }
+}
+
+// C = (I - Z A_d)^-1 and D = C Z B_d of iSLSBase.AB (isls/isls_base.py:138-158) for time-varying A_t, B_t: block (r, j)
+// of C is A_{r-1} A_{r-2} ... A_j (identity for r = j), block (r, j) of D is C(r, j+1) B_j (r > j), accumulated from
+// the diagonal to the left exactly like the reference's loop (C[., j] = C[., j+1] @ A_j).  CTA = problem, thread = one
+// row (r, i) of C and D, which it walks from its diagonal block leftwards with a row vector v = e_i' A_{r-1} ... A_j.
+#define TV_MAXN 16
+__global__ void k_tv_build_CD(int n, int m, int N, const double *A, const double *Bm, size_t a_stride, size_t b_stride,
+                              double *C, double *D) {
+  const int Nn = N * n, Nm = N * m;
+  const long long b = blockIdx.x;
+  A += (size_t)b * a_stride;
+  Bm += (size_t)b * b_stride;
+  double *Cb = C + (size_t)b * Nn * Nn, *Db = D + (size_t)b * Nn * Nm;
+  for (int row = threadIdx.x; row < Nn; row += blockDim.x) {
+    const int r = row / n, i = row % n;
+    double v[TV_MAXN], w[TV_MAXN];
+    for (int q = 0; q < n; q++) v[q] = (q == i) ? 1.0 : 0.0;
+    for (int q = 0; q < Nn; q++) Cb[(size_t)row * Nn + q] = 0.0;
+    for (int q = 0; q < Nm; q++) Db[(size_t)row * Nm + q] = 0.0;
+    Cb[(size_t)row * Nn + row] = 1.0;
+    for (int j = r - 1; j >= 0; j--) {
+      const double *Aj = A + (size_t)j * n * n, *Bj = Bm + (size_t)j * n * m;
+      for (int q = 0; q < m; q++) {
+        double acc = 0.0;
+        for (int k = 0; k < n; k++) acc = fma(v[k], Bj[k * m + q], acc);
+        Db[(size_t)row * Nm + j * m + q] = acc;
+      }
+      for (int q = 0; q < n; q++) {
+        double acc = 0.0;
+        for (int k = 0; k < n; k++) acc = fma(v[k], Aj[k * n + q], acc);
+        w[q] = acc;
+      }
+      for (int q = 0; q < n; q++) { v[q] = w[q]; Cb[(size_t)row * Nn + j * n + q] = w[q]; }
+    }
   }
 }
 
@@ -701,6 +739,34 @@ extern "C" int isls_sls_replan_f64(const isls_sls_plan *p, int64_t B, const doub
   const size_t smem = ((size_t)p->Nn + 2 * p->Nm) * sizeof(double);
   k_sls_replan<<<(unsigned)B, 256, smem, (cudaStream_t)stream>>>(p->Nm, p->Nn, p->Linv0, p->DTQ, p->Su, K_dev, k_dev,
                                                                 xd_new_dev, xd_old_dev, k_new_dev);
+  CK(cudaGetLastError());
+  return ISLS_OK;
+}
+
+extern "C" size_t isls_controller_tv_workspace_bytes(int32_t n, int32_t m, int32_t N, int64_t B) {
+  const size_t Nn = (size_t)N * n, Nm = (size_t)N * m;
+  return (size_t)B * (2 * Nn * Nn + Nn * Nm) * sizeof(double);
+}
+
+// iSLS.controller for a general causal PHI_U on the time-varying operators (isls/sls.py:235-242 applied to the C, D of
+// isls/isls_base.py:138-158): builds C, D of every problem from its A_t, B_t and runs the block back-substitution.
+extern "C" int isls_controller_tv_f64(int32_t n, int32_t m, int32_t N, int64_t B, const double *A_dev,
+                                      const double *B_dev, int32_t shared_AB, const double *PHI_U_dev,
+                                      const double *du_dev, void *workspace_dev, size_t workspace_bytes,
+                                      double *K_dev, double *k_dev, void *stream) {
+  if (B <= 0 || N < 1 || n < 1 || m < 1 || !A_dev || !B_dev || !PHI_U_dev || !du_dev || !workspace_dev || !K_dev || !k_dev)
+    return isls_fail(ISLS_E_INVALID, "NULL argument or bad size");
+  if (n > TV_MAXN) return isls_fail(ISLS_E_UNSUPPORTED, "x_dim > 16");
+  if (workspace_bytes < isls_controller_tv_workspace_bytes(n, m, N, B))
+    return isls_fail(ISLS_E_WORKSPACE, "controller workspace too small (isls_controller_tv_workspace_bytes)");
+  const size_t Nn = (size_t)N * n, Nm = (size_t)N * m;
+  if (Nn * sizeof(double) > 48 * 1024) return isls_fail(ISLS_E_UNSUPPORTED, "N * x_dim > 6144");
+  cudaStream_t s = (cudaStream_t)stream;
+  double *C = (double *)workspace_dev, *D = C + (size_t)B * Nn * Nn, *PX = D + (size_t)B * Nn * Nm;
+  const size_t as = shared_AB ? 0 : (size_t)N * n * n, bs = shared_AB ? 0 : (size_t)N * n * m;
+  k_tv_build_CD<<<(unsigned)B, 256, 0, s>>>(n, m, N, A_dev, B_dev, as, bs, C, D);
+  k_sls_controller<<<(unsigned)B, 256, Nn * sizeof(double), s>>>(n, m, N, (int)Nn, C, D, nullptr, PHI_U_dev, du_dev, PX, K_dev,
+                                                                 k_dev, Nn * Nn, Nn * Nm);
   CK(cudaGetLastError());
   return ISLS_OK;
 }

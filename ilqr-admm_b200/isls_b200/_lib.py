@@ -81,7 +81,8 @@ EXPORTS = ["isls_version", "isls_last_error_string", "isls_model_id", "isls_mode
            "isls_measure_fp64_tflops", "isls_profile_enable", "isls_profile_collect",
            "isls_sls_plan_create", "isls_sls_plan_destroy", "isls_sls_operators", "isls_sls_solve_f64",
            "isls_sls_admm_f64", "isls_sls_controller_f64", "isls_mc_rollout_f64", "isls_project_rows_f64",
-           "isls_isls_admm_solve_f64", "isls_sls_replan_f64", "isls_probe_overlap_f64", "isls_project_rows_ex_f64", "isls_project_set_convex_f64"]
+           "isls_isls_admm_solve_f64", "isls_sls_replan_f64", "isls_probe_overlap_f64", "isls_project_rows_ex_f64", "isls_project_set_convex_f64",
+           "isls_controller_tv_workspace_bytes", "isls_controller_tv_f64", "isls_linearize_f64"]
 
 KERNEL_CLASSES = ["init", "kpass", "ff", "linesearch", "admm", "outer_end", "finalize", "backward_full", "accept",
                   "lqt", "compact", "isls_cols", "isls_update"]
@@ -131,6 +132,13 @@ def lib():
     L.isls_sls_controller_f64.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
     L.isls_sls_replan_f64.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+    L.isls_controller_tv_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64]
+    L.isls_controller_tv_workspace_bytes.restype = C.c_size_t
+    L.isls_controller_tv_f64.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]
+    L.isls_linearize_f64.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int64, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
     L.isls_mc_rollout_f64.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int64,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                       C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -328,6 +328,18 @@ class iSLS:
         phi = out.phi_u.reshape(B_, self.N * self.u_dim, int(dim))
         return (du[0], phi[0]) if self.batch is None else (du, phi)
 
+    def get_AB(self, x_nom=None, u_nom=None):
+        """A, B = get_AB(x_nom, u_nom): the Jacobians of the device model along a trajectory (default: the current
+        nominal values), A [N, n, n], B [N, n, m] - what the reference's callers compute with their own `get_AB`
+        callable and hand to `iSLS.AB` (isls/isls_base.py:133-158)."""
+        if self._model is None:
+            raise IslsError("set forward_model first")
+        if x_nom is None:
+            if self.x_nom is None:
+                raise IslsError("no nominal values yet: pass x_nom, u_nom or solve first")
+            x_nom, u_nom = self.x_nom, self.u_nom
+        return S.linearize(self._model, self.x_dim, self.u_dim, self._dt(), x_nom, u_nom, device=self.device)
+
     def controller(self, PHI_U, du):
         """K, k = controller(PHI_U, du) - the call the robust notebook makes on an iSLS object after isls_admm
         (3DoF robot/State bounds and robust control bounds.ipynb cells 23, 26; README "iSLS.controller"; the formula is
@@ -339,8 +351,12 @@ class iSLS:
         Phi_x = C + (D phi) E, and because the first block row of D is zero (x_0 does not depend on the controls) and
         that of C^-1 = I - Z A is [I 0 ...], Woodbury gives E Phi_x^-1 = E, hence K = phi E = Phi_u and
         k = du - phi (E D du) = du.  (The reference's dense inverse reproduces exactly that: |K - Phi_u| = 1.4e-15 on the
-        notebook problem, tests/golden/make_golden.py.)  A Phi_u with entries outside the first block column needs the
-        general block back-substitution, which exists for constant (A, B) only (SLS.controller)."""
+        notebook problem, tests/golden/make_golden.py.)
+
+        Any other causal (block lower triangular) Phi_u goes through the block back-substitution on the device
+        (isls_controller_tv_f64) with C, D built from A_t, B_t: the pair set through `iSLS.AB` if there is one (the
+        reference uses the C, D of its last `self.AB = ...`, isls/isls_base.py:138-158), otherwise the Jacobians of the
+        device model at the current nominal values (`get_AB()`)."""
         if self.batch is not None:
             raise IslsError("controller evaluates ONE problem: construct iSLS without `batch`")
         dev = self.device
@@ -349,10 +365,13 @@ class iSLS:
         Nm, Nn = self.N * self.u_dim, self.N * self.x_dim
         if PHI_U.shape != (Nm, Nn) or du.shape != (Nm,):
             raise ValueError("PHI_U must be [N m, N n] and du [N m]")
-        if bool((PHI_U[:, self.x_dim:] != 0).any()):
-            raise NotImplementedError("iSLS.controller handles the Phi_u of isls_admm (non-zero first block column "
-                                      "only); a general time-varying Phi_u is not implemented on the device")
-        return PHI_U.clone(), du.clone()
+        if not bool((PHI_U[:, self.x_dim:] != 0).any()):
+            return PHI_U.clone(), du.clone()
+        if getattr(self, "A", None) is not None and getattr(self, "B", None) is not None:
+            A_, B_ = self.A, self.B
+        else:
+            A_, B_ = self.get_AB()
+        return S.controller_tv(A_, B_, PHI_U, du, device=dev)
 
     def _report(self, out):
         st = out.status.cpu().numpy()

@@ -405,3 +405,62 @@ def mc_rollout(model, n, m, N, dt, mode, x0, K, k, x_nom=None, u_nom=None, noise
                                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
     _lib.check(rc, "isls_mc_rollout_f64")
     return xs, us
+
+
+def _dev_f64(a, dev):
+    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64)))
+    return t.to(dev, dtype=torch.float64).contiguous()
+
+
+def linearize(model, n, m, dt, x, u, device="cuda:0"):
+    """A, B = linearize(...): the notebooks' `get_AB(x_nom, u_nom)` on the device (isls_linearize_f64) for x [..., n],
+    u [..., m] -> A [..., n, n], B [..., n, m]."""
+    L_ = _lib.lib()
+    mid = L_.isls_model_id(model.encode())
+    _lib.check(0 if mid >= 0 else mid, "isls_model_id(%r)" % model)
+    dev = torch.device(device)
+    x, u = _dev_f64(x, dev), _dev_f64(u, dev)
+    lead = tuple(x.shape[:-1])
+    if x.shape[-1] != n or u.shape[-1] != m or tuple(u.shape[:-1]) != lead:
+        raise ValueError("x must be [..., %d] and u [..., %d] with the same leading shape" % (n, m))
+    rows = int(np.prod(lead)) if lead else 1
+    A = torch.empty(lead + (n, n), dtype=torch.float64, device=dev)
+    Bm = torch.empty(lead + (n, m), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = L_.isls_linearize_f64(mid, n, m, float(dt), rows, _dptr(x), _dptr(u), _dptr(A), _dptr(Bm),
+                                   C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "isls_linearize_f64")
+    return A, Bm
+
+
+def controller_tv(A, Bm, PHI_U, du, device="cuda:0"):
+    """K, k = PHI_U PHI_X^-1, (I - K D) du with PHI_X = C + D PHI_U and the time-varying operators C, D of A_t, B_t
+    (isls_controller_tv_f64; isls/sls.py:235-242 on isls/isls_base.py:138-158).  A [N, n, n] / B [N, n, m] shared by the
+    batch or [B, N, n, n] / [B, N, n, m]; PHI_U [B, N m, N n] (or one [N m, N n]), du [B, N m]."""
+    L_ = _lib.lib()
+    dev = torch.device(device)
+    A, Bm, PHI_U, du = _dev_f64(A, dev), _dev_f64(Bm, dev), _dev_f64(PHI_U, dev), _dev_f64(du, dev)
+    single = PHI_U.ndim == 2
+    if single:
+        PHI_U, du = PHI_U[None], du[None]
+    shared = A.ndim == 3
+    N, n, m = int(A.shape[-3]), int(A.shape[-1]), int(Bm.shape[-1])
+    B_ = int(PHI_U.shape[0])
+    if PHI_U.shape != (B_, N * m, N * n) or du.shape != (B_, N * m) or Bm.shape[-3:] != (N, n, m) or (
+            not shared and (A.shape[0] != B_ or Bm.shape[0] != B_)):
+        raise ValueError("shapes: A [(B,) N, n, n], B [(B,) N, n, m], PHI_U [B, N m, N n], du [B, N m]")
+    # causal PHI_U only (u_t reacts to w_s, s <= t): the back-substitution relies on PHI_X being unit block lower
+    # triangular; the reference's dense inverse would accept anything
+    blk = torch.arange(N, device=dev)
+    upper = (blk.repeat_interleave(m)[:, None] < blk.repeat_interleave(n)[None, :])
+    if bool((PHI_U[:, upper] != 0).any()):
+        raise ValueError("PHI_U must be block lower triangular (causal)")
+    nbytes = L_.isls_controller_tv_workspace_bytes(n, m, N, B_)
+    ws = torch.empty(nbytes // 8, dtype=torch.float64, device=dev)
+    K = torch.empty(B_, N * m, N * n, dtype=torch.float64, device=dev)
+    k = torch.empty(B_, N * m, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = L_.isls_controller_tv_f64(n, m, N, B_, _dptr(A), _dptr(Bm), int(shared), _dptr(PHI_U), _dptr(du), _dptr(ws),
+                                       nbytes, _dptr(K), _dptr(k), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "isls_controller_tv_f64")
+    return (K[0], k[0]) if single else (K, k)

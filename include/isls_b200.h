@@ -297,6 +297,22 @@ int isls_sls_controller_f64(const isls_sls_plan *plan, int64_t B, int32_t n_firs
                             const double *du_dev, void *workspace_dev, size_t workspace_bytes, double *K_dev,
                             double *k_dev, void *stream);
 
+/* iSLS.controller for a general causal PHI_U on time-varying dynamics: the same formula (isls/sls.py:235-242) with the
+ * operators C = (I - Z A_d)^-1, D = C Z B_d that iSLSBase.AB builds from A_t, B_t (isls/isls_base.py:138-158).
+ *   A_dev [B, N, n, n], B_dev [B, N, n, m] (or [N, n, n], [N, n, m] shared by the batch when shared_AB != 0; entry N-1
+ *   is not read), PHI_U_dev [B, N m, N n] (block lower triangular: u_t reacts to w_s for s <= t), du_dev [B, N m]
+ *   -> K_dev [B, N m, N n], k_dev [B, N m].  workspace: isls_controller_tv_workspace_bytes(). */
+size_t isls_controller_tv_workspace_bytes(int32_t n, int32_t m, int32_t N, int64_t B);
+int isls_controller_tv_f64(int32_t n, int32_t m, int32_t N, int64_t B, const double *A_dev, const double *B_dev,
+                           int32_t shared_AB, const double *PHI_U_dev, const double *du_dev, void *workspace_dev,
+                           size_t workspace_bytes, double *K_dev, double *k_dev, void *stream);
+
+/* get_AB of the reference's callers on the device: A_t = df/dx, B_t = df/du of a registered model at every row of
+ * x_dev [rows, n], u_dev [rows, m] -> A_dev [rows, n, n], B_dev [rows, n, m] (the layouts iSLSBase.AB takes,
+ * isls/isls_base.py:133-158). */
+int isls_linearize_f64(int32_t model_id, int32_t n, int32_t m, double dt, int64_t rows, const double *x_dev,
+                       const double *u_dev, double *A_dev, double *B_dev, void *stream);
+
 /* SLS.initialize_replanning_procedure + SLS.replan_feedforward (isls/sls.py:244-248): new feed-forward terms for a new
  * target vector without re-solving,  k_new = k + (I - K Su) (Su'Q Su + R)^-1 Su'Q (xd_new - xd_old),  evaluated as four
  * matrix-vector products per problem (the replan matrix is never formed).

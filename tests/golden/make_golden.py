@@ -493,6 +493,38 @@ def golden_arm_lq_step(nb=3):
     np.savez_compressed(os.path.join(OUT, "arm_lq_step.npz"), x0=p["x0"], u_head=np.stack(us), cond=np.array(conds))
 
 
+def golden_controller_tv():
+    """iSLS.controller of the unmodified reference (SLS.controller, sls.py:235-242, on the C, D that iSLSBase.AB builds,
+    isls_base.py:138-158) for a GENERAL causal Phi_u - every block column populated, not only the first one that
+    isls_admm returns - on the car (N = 20) and the arm (N = 12) around a rolled-out nominal trajectory."""
+    out = {}
+    pkg, _ = S.load()
+    for name, p, N in (("car", P.car_batch(1), 20), ("arm", P.arm_batch(1), 12)):
+        model = M.make_model(p["model"], dt=p["dt"])
+        n, m = model.n, model.m
+        rng = np.random.default_rng(77 + N)
+        zs = p["zs"] if p["zs"].ndim == 2 else p["zs"][0]
+        seq = np.zeros(N, dtype=np.int64)
+        seq[-1] = p["seq"][-1]
+        s = S.make_isls(model, N, zs, _Qs(p), seq, p["u_std"])
+        u0 = rng.normal(scale=0.3, size=(N, m))
+        S.init_nominal(s, p["x0"][0], u0)
+        with S.quiet():
+            A, Bm = model.get_AB(s.x_nom, s.u_nom)
+            s.AB = A, Bm
+            PHI_U = np.zeros((N * m, N * n))
+            for t in range(N):
+                PHI_U[t * m:(t + 1) * m, :(t + 1) * n] = rng.normal(scale=0.2, size=(m, (t + 1) * n))
+            du = rng.normal(size=N * m)
+            s.Sw, s.Su = s.C, s.D
+            K, k = pkg.SLS.controller(s, PHI_U, du)
+        print("controller_tv", name, "max|K|", np.abs(K).max(), "cond(PHI_X)", np.linalg.cond(s.C + s.D @ PHI_U))
+        out.update({name + "_x": s.x_nom.copy(), name + "_u": s.u_nom.copy(), name + "_A": np.asarray(A),
+                    name + "_B": np.asarray(Bm), name + "_PHI_U": PHI_U, name + "_du": du, name + "_K": K, name + "_k": k,
+                    name + "_dt": np.array(p["dt"])})
+    np.savez_compressed(os.path.join(OUT, "controller_tv.npz"), **out)
+
+
 def golden_solve_dp_ff():
     """SLS.solve_dp(return_Qs=True) and SLS.solve_dp_ff of the unmodified reference (isls/sls.py:85-202) on the C1 double
     integrator: unregularised, and the regularised (ADMM) form with diagonal Qr, Rr and random xr, ur."""
@@ -672,5 +704,7 @@ if __name__ == "__main__":
         golden_arm_lq_step()
     if want("solve_dp_ff"):
         golden_solve_dp_ff()
+    if want("controller_tv"):
+        golden_controller_tv()
     if want("lqt_batch"):
         golden_lqt_admm_batch(P.di_batch(3), "di_lqt_admm_batch")
