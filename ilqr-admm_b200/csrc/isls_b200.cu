@@ -461,6 +461,9 @@ size_t isls_carve(const isls_plan *p, long long B, char *base, Dev *d, Dev *alt)
   takeD(d ? &d->obw : nullptr, p->desc.n_obst > 0 ? (2 + (p->desc.obst_kind == 1 ? 2 * (size_t)p->desc.n_obst : 0)) * tn : 0);
   const size_t tC = p->desc.isls_dim > 0 ? tm * (size_t)(p->desc.isls_dim + 1) : 0;
   takeD(d ? &d->Zm : nullptr, tC); takeD(d ? &d->Lm : nullptr, tC); takeD(d ? &d->Xu : nullptr, tC);
+  const size_t tCx = (p->desc.isls_dim > 0 && p->proj_x) ? tn * (size_t)(p->desc.isls_dim + 1) : 0;   // state side
+  takeD(d ? &d->Zx : nullptr, tCx); takeD(d ? &d->Lx : nullptr, tCx); takeD(d ? &d->Xx : nullptr, tCx);
+  if (d && !tCx) d->Zx = d->Lx = d->Xx = nullptr;
   const size_t S = T * TILE;
   takeD(d ? &d->cost : nullptr, S); takeD(d ? &d->prev_cost : nullptr, S); takeD(d ? &d->prim : nullptr, S);
   takeD(d ? &d->dual : nullptr, S); takeD(d ? &d->cost_adm : nullptr, S); takeD(d ? &d->best_cost : nullptr, S);
@@ -560,12 +563,34 @@ extern "C" int isls_isls_admm_solve_f64(const isls_plan *plan, const isls_solve_
   ABI_CHECK(soc, isls_sls_admm_opts);
   if (opts->max_admm < 1) return fail(ISLS_E_INVALID, "max_admm must be >= 1");
   if (!plan || plan->desc.isls_dim < 1) return fail(ISLS_E_INVALID, "the plan was not created with isls_dim > 0");
-  if (plan->proj_x || !plan->proj_u) return fail(ISLS_E_UNSUPPORTED, "isls_admm: control projection only (rho_u, no rho_x)");
+  if (!plan->proj_u) return fail(ISLS_E_UNSUPPORTED, "isls_admm: the plan needs rho_u (zeros = no control projection)");
+  if ((plan->proj_x != 0) != (soc->n_x_rows > 0))
+    return fail(ISLS_E_INVALID, "isls_admm: a state projection needs both rho_x in the plan and n_x_rows > 0 components");
+  if (plan->desc.n_obst > 0) return fail(ISLS_E_UNSUPPORTED, "isls_admm: no obstacle sets");
   const int C = plan->desc.isls_dim + 1;
   // n_cones = 0: no projection (isls_admm called without project_u, notebook cell 23): z = x, zero residuals, one
   // ADMM iteration per outer iteration - the unconstrained iSLS step
-  if (soc->n_cones < 0 || soc->n_cones > SOC_MAXP || (soc->n_cones > 0 && (soc->cone_rows != C + 1 || !soc->As || !soc->bs)))
+  // bs == NULL with cones: the control side is not projected (the cones serve the state side only)
+  if (soc->n_cones < 0 || soc->n_cones > SOC_MAXP || (soc->n_cones > 0 && (soc->cone_rows != C + 1 || !soc->As)) ||
+      (soc->n_cones > 0 && !soc->bs && soc->n_x_rows <= 0))
     return fail(ISLS_E_UNSUPPORTED, "unsupported cone set (need A_i of shape [dim + 2, dim + 1])");
+  SocX X;
+  memset(&X, 0, sizeof(X));
+  X.u_identity = (soc->n_cones > 0 && !soc->bs) ? 1 : 0;
+  if (soc->n_x_rows > 0) {
+    // state side (isls.py:631-638): x_row_idx = the projected state COMPONENTS, x_bs [n_x_rows, P, cone_rows] their
+    // cone offsets (the A_i are shared with the control side); Qr comes from the plan's rho_x, rho_x_rows is not read
+    if (soc->n_x_rows > SOC_MAXCOMP || soc->n_cones < 1 || !soc->x_row_idx || !soc->x_bs)
+      return fail(ISLS_E_INVALID, "state projection: 1..8 components with cone offsets");
+    X.ncomp = soc->n_x_rows;
+    for (int g = 0; g < X.ncomp; g++) {
+      if (soc->x_row_idx[g] < 0 || soc->x_row_idx[g] >= plan->n) return fail(ISLS_E_INVALID, "state component out of range");
+      X.comp[g] = soc->x_row_idx[g];
+      for (int q = 0; q < soc->n_cones; q++)
+        for (int e = 0; e < soc->cone_rows; e++)
+          X.b[g][q][e] = soc->x_bs[((size_t)g * soc->n_cones + q) * soc->cone_rows + e];
+    }
+  }
   Dev d;
   int rc = setup(plan, opts, B, ws, ws_bytes, out, &d);
   if (rc) return rc;
@@ -573,11 +598,12 @@ extern "C" int isls_isls_admm_solve_f64(const isls_plan *plan, const isls_solve_
   d.isls_C = C;
   d.ls_cost_only = 1;
   SocSet S;
-  soc_set_build(&S, soc->n_cones, C, soc->cone_rows, soc->As, soc->bs, soc->inner_rho, soc->inner_max_iter,
-                soc->inner_threshold);
+  std::vector<double> zero_b((size_t)SOC_MAXP * SOC_MAXR, 0.0);
+  soc_set_build(&S, soc->n_cones, C, soc->cone_rows, soc->As, soc->bs ? soc->bs : zero_b.data(), soc->inner_rho,
+                soc->inner_max_iter, soc->inner_threshold);
   cudaStream_t s = (cudaStream_t)stream;
   OPS_OR_FAIL(ops, plan, stream);
-  return ops->isls_admm(d, S, B, x0, u_init, zs, du_dev, phi_u_dev, s);
+  return ops->isls_admm(d, S, X, B, x0, u_init, zs, du_dev, phi_u_dev, s);
 }
 
 extern "C" int isls_lqt_admm_dp_f64(const isls_plan *plan, const isls_solve_opts *opts, int64_t B, const double *x0,

@@ -83,6 +83,9 @@ struct Dev {
   // (primal iterate) are [T][N][m * C][32] with component index j * C + c
   int isls_C, ls_cost_only;
   double *Zm, *Lm, *Xu;
+  // state side of isls_admm (project_x, isls.py:631-638): the same three arrays for [d_x | Phi_x(:, :dim)],
+  // [T][N][n * C][32] with component index i * C + c; NULL without a state projection
+  double *Zx, *Lx, *Xx;
   double stall_tol, osc_tol;
   // workspace, tile-blocked [T][N][dim][32]
   double *xh, *uh, *du, *zx, *lx, *zu, *lu, *rgx, *rgu, *Kg, *Qux, *Quu, *Qui, *kk, *zs;   // Quu, Qui: packed lower
@@ -242,6 +245,10 @@ __global__ void k_init(Dev d, const double *x0, const double *u_init, const doub
     if (d.isls_C > 0) {                                  // z_u_init = 0 (isls.py:537)
       double *Zm = c.at(d.Zm, d, M::m * d.isls_C);
       for (int q = 0; q < M::m * d.isls_C; q++) EL(Zm, M::m * d.isls_C, t, q) = 0.0;
+      if (d.Zx) {                                        // z_x_init = 0 (isls.py:536)
+        double *Zx = c.at(d.Zx, d, M::n * d.isls_C);
+        for (int q = 0; q < M::n * d.isls_C; q++) EL(Zx, M::n * d.isls_C, t, q) = 0.0;
+      }
     }
   }
   const double cost = cs + d.u_std * cc;
@@ -276,7 +283,14 @@ __global__ void k_init(Dev d, const double *x0, const double *u_init, const doub
 //   Qxx = Cxx + A'VA, Qux = B'VA, Quu = Cuu + B'VB           isls/isls.py:288-290 (Cux = 0, diagonal Cxx/Cuu)
 //   K = -Quu^-1 Qux                                           isls/isls.py:296-297 (sls.py:149-150 form)
 //   V = Qxx + K'QuuK + Qux'K + K'Qux                          isls/isls.py:300
-template <class M>
+// JOSEPH: the same V in the closed-loop ("Joseph") form  V = Cxx + K'Cuu K + (A + BK)'V(A + BK)  - a sum of
+// positive semi-definite terms instead of the four-term expression above, whose cancellation is unstable in FP64 when
+// the control is cheap next to the accumulated state weights (Cuu << B'VB: with R = 1e-4 and a state penalty Qr = 10
+// on the joint velocities of the arm the four-term recursion loses all but 1-2 digits of the first controls against
+// the exact minimiser, the Joseph form keeps 1e-11; oracle/restated.py::backward_pass).  Used where the reference
+// solves the dense normal equations with such weights (isls_admm); the four-term form mirrors the reference's own DP
+// recursion and stays on every other path.
+template <class M, bool JOSEPH = false>
 __device__ __forceinline__ bool riccati_step(const double (&A)[M::n][M::n], const double (&Bm)[M::n][M::m],
                                              const double (&dxx)[M::n], const double (&duu)[M::m],
                                              double (&V)[M::n][M::n], double (&K)[M::m][M::n],
@@ -289,11 +303,9 @@ __device__ __forceinline__ bool riccati_step(const double (&A)[M::n][M::n], cons
 #pragma unroll
   for (int i = 0; i < n; i++) Qxx[i][i] += dxx[i];
   mat_Bt_X<M, n>(Bm, VA, Qux);
-  {
-    double VB[n][m];
-    mat_V_B<M>(V, Bm, VB);
-    mat_Bt_X<M, m>(Bm, VB, Quu);
-  }
+  double VB[n][m];
+  mat_V_B<M>(V, Bm, VB);
+  mat_Bt_X<M, m>(Bm, VB, Quu);
 #pragma unroll
   for (int i = 0; i < m; i++) Quu[i][i] += duu[i];
   const bool ok = spd_inverse<m>(Quu, Qui);
@@ -306,6 +318,35 @@ __device__ __forceinline__ bool riccati_step(const double (&A)[M::n][M::n], cons
       for (int b2 = 0; b2 < m; b2++) acc = fma(Qui[a][b2], Qux[b2][j], acc);
       K[a][j] = -acc;
     }
+  if (JOSEPH) {
+    // W = V (A + BK) = VA + VB K;  V' = diag(dxx) + K' diag(duu) K + A'W + K'(B'W), symmetrised
+    double W[n][n], AtW[n][n], BtW[m][n];
+#pragma unroll
+    for (int i = 0; i < n; i++)
+#pragma unroll
+      for (int j = 0; j < n; j++) {
+        double acc = VA[i][j];
+#pragma unroll
+        for (int a = 0; a < m; a++) acc = fma(VB[i][a], K[a][j], acc);
+        W[i][j] = acc;
+      }
+    mat_At_X<M, n>(A, W, AtW);
+    mat_Bt_X<M, n>(Bm, W, BtW);
+#pragma unroll
+    for (int i = 0; i < n; i++)
+#pragma unroll
+      for (int j = 0; j < n; j++) {
+        double acc = AtW[i][j];
+#pragma unroll
+        for (int a = 0; a < m; a++) acc = fma(K[a][i], fma(duu[a], K[a][j], BtW[a][j]), acc);
+        Qxx[i][j] = acc;
+      }
+#pragma unroll
+    for (int i = 0; i < n; i++)
+#pragma unroll
+      for (int j = 0; j < n; j++) V[i][j] = 0.5 * (Qxx[i][j] + Qxx[j][i]) + (i == j ? dxx[i] : 0.0);
+    return ok;
+  }
   double QK[m][n];
 #pragma unroll
   for (int a = 0; a < m; a++)
@@ -402,7 +443,7 @@ __device__ __forceinline__ void init_AB(double (&A)[M::n][M::n], double (&Bm)[M:
 // Cxx = 2(Q_t + Qr_t), Cuu = 2(R + Rr_t) (regularised form of sls.py:132-137).  Stores K_t, Qux_t and the packed
 // Quu_t, Quu_t^-1 (the logs of sls.py:159-162 that the feed-forward passes need); resets the ADMM state of the new outer
 // iteration (lambda = 0, isls/isls.py:414-415; z warm start isls/isls.py:489-490).
-template <class M, bool SMALL = false>
+template <class M, bool SMALL = false, bool JOSEPH = false>
 __global__ void k_kpass(Dev d) {
   constexpr int n = M::n, m = M::m, nt = NTRI(M::m);
   const int tile = d.tile0 + (blockIdx.x * blockDim.y + threadIdx.y) * d.tstep;
@@ -477,7 +518,7 @@ __global__ void k_kpass(Dev d) {
     }
 #pragma unroll
     for (int j = 0; j < m; j++) duu[j] = 2.0 * (d.u_std * d.Rw[j] + ru_t[j]);
-    ok &= riccati_step<M>(A, Bm, dxx, duu, V, K, Qux, Quu, Qui);
+    ok &= riccati_step<M, JOSEPH>(A, Bm, dxx, duu, V, K, Qux, Quu, Qui);
 #pragma unroll
     for (int a = 0; a < m; a++) {
 #pragma unroll
@@ -1777,7 +1818,7 @@ __device__ __forceinline__ int ls_tile(const Dev &d, const int tile, int fuse, i
       if (l < d.L && !skip) {
         double tot = cs[q] + fma(al[q], fma(al[q], c2, c1), c0);   // cost_function + control penalty (isls.py:470,476)
         if (d.cost_kind != ISLS_COST_QUADRATIC && tot != tot) tot = 1e6;   // Tutorial cell 14: cost closure, NaN -> 1e6
-        if (PX) tot += px[q];                                      // isls.py:473
+        if (PX && !d.ls_cost_only) tot += px[q];                   // isls.py:473 (isls_admm: no penalty, isls.py:588-590)
         sc[l][c.lane] = tot;
         scs[l][c.lane] = cs[q];
       }
@@ -2190,6 +2231,16 @@ __global__ void k_isls_reset(Dev d) {
       for (int q = 0; q < C; q++) EL(Lm, m * C, t, j * C + q) = 0.0;
       EL(rgu, m, t, j) = EL(uh, m, t, j) + EL(Zm, m * C, t, j * C);
     }
+  if (d.Zx) {                                            // lmb_x = 0 (isls.py:614), reg_abs of column 0
+    constexpr int n = M::n;
+    const double *xh = c.at(d.xh, d, n), *Zx = c.at(d.Zx, d, n * C);
+    double *Lx = c.at(d.Lx, d, n * C), *rgx = c.at(d.rgx, d, n);
+    for (int t = 0; t < d.N; t++)
+      for (int i = 0; i < n; i++) {
+        for (int q = 0; q < C; q++) EL(Lx, n * C, t, i * C + q) = 0.0;
+        EL(rgx, n, t, i) = EL(xh, n, t, i) + EL(Zx, n * C, t, i * C);
+      }
+  }
 }
 
 // columns c = 1..dim (blockIdx.y + 1): feed-forward sweep (sls.py:168-202) with cx = 0, cu = -2 Rr (z_c - lambda_c),
@@ -2203,14 +2254,44 @@ __global__ void k_isls_cols(Dev d) {
   if (d.odone[c.b] || d.adone[c.b]) return;
   const int C = d.isls_C, col = blockIdx.y + 1, N = d.N;
   const double *xh = c.at(d.xh, d, n), *uh = c.at(d.uh, d, m);
+  if (col == C) {
+    // extra job of the state-side variant: x_x[:, 0] = x_noms[ind] - x_nom (isls.py:605-606), the winner's open-loop
+    // rollout (same arithmetic as k_outer_end, which makes it the next nominal trajectory)
+    const double *du = c.at(d.du, d, m);
+    double *Xx = c.at(d.Xx, d, n * C);
+    const double al = d.alphas[d.best[c.b]];
+    double x[n], u[m], xn[n];
+#pragma unroll
+    for (int i = 0; i < n; i++) x[i] = EL(xh, n, 0, i);
+    for (int t = 0; t < N; t++) {
+#pragma unroll
+      for (int j = 0; j < m; j++) u[j] = fma(al, EL(du, m, t, j), EL(uh, m, t, j));
+#pragma unroll
+      for (int i = 0; i < n; i++) EL(Xx, n * C, t, i * C) = x[i] - EL(xh, n, t, i);
+      M::step(x, u, xn, d.dt);
+#pragma unroll
+      for (int i = 0; i < n; i++) x[i] = xn[i];
+    }
+    return;
+  }
   const double *Kg = c.at(d.Kg, d, m * n), *Qx = c.at(d.Qux, d, m * n);
   const double *Qu = c.at(d.Quu, d, nt), *Qi = c.at(d.Qui, d, nt);
   const double *Zm = c.at(d.Zm, d, m * C), *Lm = c.at(d.Lm, d, m * C);
   double *Xu = c.at(d.Xu, d, m * C);
+  const double *Zx = d.Zx ? c.at(d.Zx, d, n * C) : nullptr, *Lx = d.Zx ? c.at(d.Lx, d, n * C) : nullptr;
+  double *Xx = d.Zx ? c.at(d.Xx, d, n * C) : nullptr;
   double A[n][n], Bm[n][m], v[n], cx[n];
   init_AB<M>(A, Bm);
+  // state side (isls.py:571-572 in Riccati form): the column's linear state term cx = -2 Qr (z_x,c - lambda_x,c)
+  auto cx_of = [&](int t, double (&cxv)[n]) {
 #pragma unroll
-  for (int i = 0; i < n; i++) { v[i] = 0.0; cx[i] = 0.0; }
+    for (int i = 0; i < n; i++)
+      cxv[i] = Zx ? -2.0 * __ldg(d.rho_x + t * n + i) * (EL(Zx, n * C, t, i * C + col) - EL(Lx, n * C, t, i * C + col))
+                  : 0.0;
+  };
+  cx_of(N - 1, cx);
+#pragma unroll
+  for (int i = 0; i < n; i++) v[i] = cx[i];
   auto cu_of = [&](int t, double (&cu)[m]) {
 #pragma unroll
     for (int j = 0; j < m; j++)
@@ -2240,6 +2321,7 @@ __global__ void k_isls_cols(Dev d) {
       }
     }
     cu_of(t, cu);                  // its loads go out with the step's other loads, not after the Jacobian has waited
+    cx_of(t, cx);
     M::jac(x, u, J, d.dt);
     M::expand(J, A, Bm, d.dt);
     ff_step<M>(A, Bm, cx, cu, Qux, Quu, Qui, v, kt);
@@ -2251,6 +2333,10 @@ __global__ void k_isls_cols(Dev d) {
   for (int i = 0; i < n; i++) dx[i] = (i == col - 1) ? 1.0 : 0.0;
   for (int t = 0; t < N; t++) {
     double x[n], u[m], K[m][n], kv[m], duv[m];
+    if (Xx) {                      // x_x[:, c] = Sx[:, c] + Su du_c (isls.py:580-582)
+#pragma unroll
+      for (int i = 0; i < n; i++) EL(Xx, n * C, t, i * C + col) = dx[i];
+    }
 #pragma unroll
     for (int a = 0; a < m; a++) {
 #pragma unroll
@@ -2450,18 +2536,20 @@ static void launch_isls_cols(const Dev &d, cudaStream_t s) {
     const char *e = getenv("ISLS_COLS_STAGES");       // -1 auto (default), 0 plain, 3 forced
     mode = e ? atoi(e) : -1;
   }
-  if (mode == ST || (mode < 0 && (long long)tiles * cols < 1536 && smem <= 48 * 1024)) {
+  if (!d.Zx && (mode == ST || (mode < 0 && (long long)tiles * cols < 1536 && smem <= 48 * 1024))) {
     k_isls_cols_staged<M, ST><<<dim3(tiles, cols), TILE, smem, s>>>(d);
-  } else {
-    k_isls_cols<M><<<dim3((tiles + 1) / 2, cols), dim3(TILE, 2), 0, s>>>(d);
+  } else {                          // with a state side: one more job per tile (the winner's rollout, column 0 of x_x)
+    k_isls_cols<M><<<dim3((tiles + 1) / 2, cols + (d.Zx ? 1 : 0)), dim3(TILE, 2), 0, s>>>(d);
   }
 }
 
 // ADMM update on the matrix variable (isls.py:628-654): one CTA per problem, thread r = row (t, j) of
 // [d_u | Phi_u(:, :dim)]; z = project_u(alpha x + (1 - alpha) z + lambda, u_nom) with the notebook's closure (column 0
 // shifted by u_nom, project_set_convex over the SOC set, shifted back), lambda += x - z, residuals weighted by Rr.
+// Launch bounds: the cone-shape-specialised forms keep z_i, lambda_i in registers (<= 384 threads = N m <= 384 rows);
+// the run-time form serves any shape and up to 1,024 rows.
 template <class M, int CP = 0, int CC = 0, int CR = 0>
-__global__ void k_isls_update(Dev d, SocSet S, int outer, int inner) {
+__global__ void __launch_bounds__(CP ? 384 : 1024) k_isls_update(Dev d, SocSet S, SocX X, int outer, int inner) {
   constexpr int m = M::m;
   __shared__ double red[32];
   const long long b = blockIdx.x;
@@ -2485,7 +2573,12 @@ __global__ void k_isls_update(Dev d, SocSet S, int outer, int inner) {
     _Pragma("unroll") for (int q = 0; q < C; q++) y[q] = (d.relax * xu[q] + (1.0 - d.relax) * z[q]) + lm[q];
     y[0] += un;                                                       // notebook cell 25
   }
-  const int its = soc_project_set<CP, CC, CR>(S, S.b, y, zn, act, red);
+  int its = 1;
+  if (X.u_identity) {                                                 // isls_admm without project_u: z_u = y_u
+    _Pragma("unroll") for (int q = 0; q < C; q++) zn[q] = y[q];
+  } else {
+    its = soc_project_set<CP, CC, CR>(S, S.b, y, zn, act, red);
+  }
   double ps = 0.0, ds = 0.0;
   if (act) {
     zn[0] -= un;
@@ -2500,7 +2593,56 @@ __global__ void k_isls_update(Dev d, SocSet S, int outer, int inner) {
     EL(Xu, m * C, t, j * C) = xu[0];
     EL(rgu, m, t, j) = un + (zn[0] - lm[0]);                          // reg_abs of column 0 for the next k_ff
   }
-  const double prim = sqrt(block_sum(ps, red)), dual = sqrt(block_sum(ds, red));
+  double prim = sqrt(block_sum(ps, red)), dual = sqrt(block_sum(ds, red));
+  if (d.Zx) {
+    // ---- state side (isls.py:631-638, 648-650): thread r = time step t, looping over the n rows (t, i) of
+    // [d_x | Phi_x(:, :dim)];  z_x = project_x(alpha x_x + (1 - alpha) z_x + lambda_x, x_nom): column 0 shifted by
+    // x_nom, the rows of every listed component projected by one project_set_convex call over that component's N rows
+    // (its stop rule is the maximum over those rows), all other rows passed through; residuals weighted by Qr and
+    // ADDED to the control side's
+    constexpr int n = M::n;
+    const bool actx = r < d.N;
+    const int tx = actx ? r : 0;
+    const double *xh = c.at(d.xh, d, n);
+    double *Zx = c.at(d.Zx, d, n * C), *Lx = c.at(d.Lx, d, n * C), *Xx = c.at(d.Xx, d, n * C), *rgx = c.at(d.rgx, d, n);
+    double psx = 0.0, dsx = 0.0;
+    for (int ix = 0; ix < n; ix++) {
+      int g = -1;
+      for (int q = 0; q < X.ncomp; q++) if (X.comp[q] == ix) g = q;     // uniform over the CTA
+      double xx[SOC_MAXC] = {}, zxv[SOC_MAXC] = {}, lxv[SOC_MAXC] = {}, yx[SOC_MAXC] = {}, znx[SOC_MAXC] = {};
+      double xn0 = 0.0, rhx = 0.0;
+      if (actx) {
+        xn0 = EL(xh, n, tx, ix);
+        rhx = d.rho_x[tx * n + ix];
+        _Pragma("unroll") for (int q = 0; q < C; q++) {
+          xx[q] = EL(Xx, n * C, tx, ix * C + q);
+          zxv[q] = EL(Zx, n * C, tx, ix * C + q);
+          lxv[q] = EL(Lx, n * C, tx, ix * C + q);
+          yx[q] = (d.relax * xx[q] + (1.0 - d.relax) * zxv[q]) + lxv[q];
+        }
+        yx[0] += xn0;
+      }
+      if (g >= 0) {
+        soc_project_set<CP, CC, CR>(S, X.b[g], yx, znx, actx, red);
+      } else {
+        _Pragma("unroll") for (int q = 0; q < C; q++) znx[q] = yx[q];
+      }
+      if (actx) {
+        znx[0] -= xn0;
+        _Pragma("unroll") for (int q = 0; q < C; q++) {
+          const double pr = xx[q] - znx[q], dz = znx[q] - zxv[q];
+          lxv[q] += pr;
+          psx = fma(rhx * pr, rhx * pr, psx);
+          dsx = fma(rhx * dz, rhx * dz, dsx);
+          EL(Zx, n * C, tx, ix * C + q) = znx[q];
+          EL(Lx, n * C, tx, ix * C + q) = lxv[q];
+        }
+        EL(rgx, n, tx, ix) = xn0 + (znx[0] - lxv[0]);                   // reg_abs of column 0 for the next k_ff
+      }
+    }
+    prim = sqrt(block_sum(psx, red)) + prim;
+    dual = sqrt(block_sum(dsx, red)) + dual;
+  }
   if (r == 0) {
     if (d.out.inner_iters) d.out.inner_iters[((size_t)c.ob * d.max_outer + outer) * d.max_admm + inner] = its;
     d.cost_adm[c.b] = d.best_cost[c.b];                               // the search cost is the plain cost
@@ -3512,7 +3654,10 @@ static int try_ff_tma(const Dev &d, cudaStream_t s, int tiles, int sms, bool for
 // K-pass launcher: below 1,536 tiles the latency-oriented form (plan constants one step ahead, Jacobian cache)
 template <class M>
 static void launch_kpass(const Dev &d, cudaStream_t s) {
-  if (d.Jc) k_kpass<M, true><<<tp_grid(d), tp_block(), 0, s>>>(d);
+  if (d.isls_C > 0) {           // isls_admm: closed-loop (Joseph) form of the value recursion, see riccati_step
+    if (d.Jc) k_kpass<M, true, true><<<tp_grid(d), tp_block(), 0, s>>>(d);
+    else k_kpass<M, false, true><<<tp_grid(d), tp_block(), 0, s>>>(d);
+  } else if (d.Jc) k_kpass<M, true><<<tp_grid(d), tp_block(), 0, s>>>(d);
   else k_kpass<M, false><<<tp_grid(d), tp_block(), 0, s>>>(d);
 }
 
@@ -3722,7 +3867,7 @@ struct isls_model_ops {
   int (*ilqr_admm)(const isls_plan *plan, Dev d, int64_t B, const double *x0, const double *u_init, const double *zs,
                    void *ws, cudaStream_t s);
   int (*ilqr)(Dev d, const double *x0, const double *u_init, const double *zs, cudaStream_t s);
-  int (*isls_admm)(Dev d, SocSet S, int64_t B, const double *x0, const double *u_init, const double *zs,
+  int (*isls_admm)(Dev d, SocSet S, SocX X, int64_t B, const double *x0, const double *u_init, const double *zs,
                    double *du_dev, double *phi_u_dev, cudaStream_t s);
   int (*lqt_admm)(Dev d, const isls_solve_opts *opts, int64_t B, const double *x0, const double *zs, cudaStream_t s);
   int (*rollout_linesearch)(Dev d, const double *x_nom, const double *u_nom, const double *du, const double *zs,
@@ -3906,7 +4051,7 @@ struct ModelImpl {
   }
 
   // iSLS.isls_admm (isls/isls.py:503-712)
-  static int isls_admm(Dev d, SocSet S, int64_t B, const double *x0, const double *u_init, const double *zs,
+  static int isls_admm(Dev d, SocSet S, SocX X, int64_t B, const double *x0, const double *u_init, const double *zs,
                        double *du_dev, double *phi_u_dev, cudaStream_t s) {
     const int rows = d.N * M::m, threads = ((rows + 31) / 32) * 32;
     LAUNCH(ISLS_KC_INIT, s, (k_init<M><<<tp_grid(d), tp_block(), 0, s>>>(d, x0, u_init, zs)));
@@ -3919,9 +4064,9 @@ struct ModelImpl {
         LAUNCH(ISLS_KC_ISLS_COLS, s, launch_isls_cols<M>(d, s));
         {
           ProfScope ps__(ISLS_KC_ISLS_UPDATE, s);
-          if (S.P == 2 && S.c == 4 && S.ra == 5) k_isls_update<M, 2, 4, 5><<<(unsigned)B, threads, 0, s>>>(d, S, j, a);   // dim = 3
-          else if (S.P == 2 && S.c == 3 && S.ra == 4) k_isls_update<M, 2, 3, 4><<<(unsigned)B, threads, 0, s>>>(d, S, j, a);
-          else k_isls_update<M><<<(unsigned)B, threads, 0, s>>>(d, S, j, a);
+          if (threads <= 384 && S.P == 2 && S.c == 4 && S.ra == 5) k_isls_update<M, 2, 4, 5><<<(unsigned)B, threads, 0, s>>>(d, S, X, j, a);   // dim = 3
+          else if (threads <= 384 && S.P == 2 && S.c == 3 && S.ra == 4) k_isls_update<M, 2, 3, 4><<<(unsigned)B, threads, 0, s>>>(d, S, X, j, a);
+          else k_isls_update<M><<<(unsigned)B, threads, 0, s>>>(d, S, X, j, a);
         }
       }
       LAUNCH(ISLS_KC_OUTER_END, s, (k_outer_end<M><<<tp_grid(d), tp_block(), 0, s>>>(d, j)));

@@ -20,6 +20,16 @@ struct SocSet {
 };
 
 
+// State side of the robust iSLS-ADMM (isls.py:631-638): the rows of the listed state components are projected, one
+// project_set_convex call per component over its N rows, onto the cones of S with the component's own offsets.
+#define SOC_MAXCOMP 8
+struct SocX {
+  int ncomp;                 // 0: no state projection
+  int u_identity;            // 1: the control side is not projected (isls_admm without project_u): z_u = y_u
+  int comp[SOC_MAXCOMP];
+  double b[SOC_MAXCOMP][SOC_MAXP][SOC_MAXR];
+};
+
 __device__ __forceinline__ double block_max(double v, double *sm) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));

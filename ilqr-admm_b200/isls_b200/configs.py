@@ -198,6 +198,25 @@ def arm_robust_batch(B, N=100, dt=0.01, seed=_seed(8), I_o=50, I_a=10, L=30, tol
                 robust=robust, I_o=I_o, I_a=I_a, L=L, tol=tol, alpha=1.0)
 
 
+def arm_robust_x_batch(B, comps=(3, 4), v_max=(0.9, 0.8), rho_x=10.0, project_u=True, **kw):
+    """arm_robust_batch plus robust STATE bounds through isls_admm's project_x (isls/isls.py:631-638): the joint
+    velocities listed in `comps` must stay within +-v_max at the same chance level, i.e. the rows
+    [x_nom + d_x | Phi_x(:, :3)] of those components are projected onto the same two cones as the controls with their
+    own offsets; Qr = diag(rho_x) on those components, 0 elsewhere."""
+    from scipy.stats import norm
+    p = arm_robust_batch(B, **kw)
+    rb = p["robust"]
+    psi_inv = norm.ppf(0.82 if "prob" not in kw else kw["prob"])
+    dim = rb["dim"]
+    bs = [[np.append(np.zeros(1 + dim), v / psi_inv), np.append(np.zeros(1 + dim), v / psi_inv)] for v in v_max]
+    rx = np.zeros((p["N"], p["n"]))
+    rx[:, list(comps)] = rho_x
+    rb["x"] = dict(comps=list(comps), bs=np.array(bs), rho_x=rx)
+    rb["u_unprojected"] = not project_u
+    p["name"] = "arm3_robust_x"
+    return p
+
+
 def di_obstacle_batch(B=1, N=100, seed=_seed(9), max_iter=200, tol=1e-3):
     """LQT-ADMM double integrator (n=4, m=2) avoiding two spherical obstacles with a STATE projection
     (notebooks/Double integrator/LQR and SLS with spherical obstacle avoidance.ipynb cells 4-14, scenario 0):

@@ -8,7 +8,7 @@ import torch
 
 from . import solver as S
 from ._lib import IslsError
-from .projections import Bound, ObstacleSets, SetConvexSOC
+from .projections import Bound, ObstacleSets, SetConvexSOC, SetConvexSOCComponents
 from .utils import diag_of
 
 _MODEL_NAMES = ("car", "arm3", "double_integrator", "tassa_car")
@@ -304,8 +304,9 @@ class iSLS:
         control bounds.ipynb cell 25).  Returns (du [B, N m], phi_u [B, N m, dim]) like the reference."""
         self._check_get_AB(get_AB)
         self._check_get_Cs(get_Cs)
-        if project_x:
-            raise NotImplementedError("device isls_admm implements the control-side projection (project_u)")
+        if project_x and not isinstance(project_x, SetConvexSOCComponents):
+            raise TypeError("project_x must be an isls_b200.projections.SetConvexSOCComponents; Python callables cannot "
+                            "run inside the kernels")
         if project_u and not isinstance(project_u, SetConvexSOC):
             raise TypeError("project_u must be an isls_b200.projections.SetConvexSOC; Python callables cannot run "
                             "inside the kernels")
@@ -317,9 +318,18 @@ class iSLS:
             Rr = np.zeros((self.N, self.u_dim))
             project_u = None
         inf = np.full((self.N, self.u_dim), np.inf)
-        sv = self._solver(max_line_search, None, None, Rr, (-inf, inf), k_max, max_admm_iter, isls_dim=int(dim))
+        Qr, bx = None, None
+        if project_x:
+            Qr, _ = self.compute_Rr_Qr(rho_x, None)
+            if Qr is None:
+                raise ValueError("rho_x is required")
+            infx = np.full((self.N, self.x_dim), np.inf)
+            bx = (-infx, infx)
+        else:
+            project_x = None
+        sv = self._solver(max_line_search, Qr, bx, Rr, (-inf, inf), k_max, max_admm_iter, isls_dim=int(dim))
         sv.set_inputs(self._x0, self._u_init, self._zs_b())
-        out = sv.isls_admm(project_u, tol=threshold, relax=float(alpha), fixed_budget=fixed_budget)
+        out = sv.isls_admm(project_u, tol=threshold, relax=float(alpha), fixed_budget=fixed_budget, soc_x=project_x)
         self._publish(out)
         if verbose:
             self._report(out)

@@ -67,6 +67,28 @@ class SetConvexSOCRows:
         assert self.bs.ndim == 3 and self.bs.shape[0] == len(self.rows)
 
 
+class SetConvexSOCComponents:
+    """State-side projection of the robust iSLS-ADMM (`iSLS.isls_admm(project_x=...)`, isls/isls.py:631-638): the device
+    form of the closure
+
+        def project_x(x, x_nom):              # x: [N * x_dim, dim + 1] = [d_x | Phi_x(:, :dim)]
+            y = x.copy(); y[:, 0] += x_nom.flatten()
+            for g, comp in enumerate(components):
+                rows = np.arange(N) * x_dim + comp
+                y[rows] = project_set_convex(y[rows], As, bs[g], [project_soc_unit] * P, rho, max_iter, threshold)
+            y[:, 0] -= x_nom.flatten(); return y
+
+    i.e. chance-constrained bounds on the listed state components (each with its own cone offsets bs[g], shared cone
+    matrices As), all other rows passed through.  As: list of P [dim + 2, dim + 1]; bs: [G][P][dim + 2]."""
+
+    def __init__(self, components, As, bs, rho=1.0, max_iter=200, threshold=1e-4):
+        self.components = [int(c) for c in components]
+        self.As = np.ascontiguousarray(np.stack([np.asarray(a, dtype=np.float64) for a in As]))
+        self.bs = np.ascontiguousarray(np.asarray(bs, dtype=np.float64))
+        assert self.As.ndim == 3 and self.bs.shape == (len(self.components),) + self.As.shape[:2]
+        self.rho, self.max_iter, self.threshold = float(rho), int(max_iter), float(threshold)
+
+
 # ---------------------------------------------------------------- batched row projections on the device (CUDA tensors)
 def _rows(kind, x, p0=None, p1=None, l=0.0, u=0.0):
     import ctypes as C

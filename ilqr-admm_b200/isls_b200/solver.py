@@ -247,15 +247,28 @@ class BatchSolver:
         _lib.check(rc, "isls_probe_overlap_f64")
         return dict(zip(("ls_plain", "ls_pers", "ff_tma", "ff_plain", "ls_pers||ff_tma", "ls_plain||ff_tma"), list(ms)))
 
-    def isls_admm(self, soc, tol=1e-3, relax=1.0, fixed_budget=False):
-        """Robust iSLS-ADMM (isls_isls_admm_solve_f64; isls/isls.py:503-712).  soc: projections.SetConvexSOC.
+    def isls_admm(self, soc, tol=1e-3, relax=1.0, fixed_budget=False, soc_x=None):
+        """Robust iSLS-ADMM (isls_isls_admm_solve_f64; isls/isls.py:503-712).  soc: projections.SetConvexSOC (control
+        side) or None; soc_x: projections.SetConvexSOCComponents (state side; the plan then needs rho_x) or None.
         Adds d_u [B,N,m] and phi_u [B,N,m,dim] to the results."""
         p, dev = self.plan, self.device
         if p.isls_dim < 1:
             raise _lib.IslsError("the plan was not created with isls_dim > 0")
         C_ = p.isls_dim + 1
         o = self._opts(tol, 1e-4, relax, fixed_budget, False, stall_tol=1e-3, osc_tol=1e-3)   # isls.py:664, 700, 704
-        if soc is None:                      # no projection: unconstrained iSLS step (z = x)
+        if soc_x is not None:
+            if soc_x.As.shape[1:] != (C_ + 1, C_):
+                raise ValueError("cone matrices must be [%d, %d] (dim + 2 rows, dim + 1 columns)" % (C_ + 1, C_))
+            if soc is not None and not (np.array_equal(soc.As, soc_x.As) and (soc.rho, soc.max_iter, soc.threshold) ==
+                                        (soc_x.rho, soc_x.max_iter, soc_x.threshold)):
+                raise ValueError("the state and control sides share the cone matrices and the inner ADMM parameters")
+            comps = np.ascontiguousarray(np.asarray(soc_x.components, dtype=np.int32))
+            so = _lib.SlsAdmmOpts(max_iter=0, rho_u=0.0, alpha=relax, tol=tol, fixed_budget=int(fixed_budget),
+                                  n_cones=soc_x.As.shape[0], cone_rows=C_ + 1, As=soc_x.As.ctypes.data,
+                                  bs=soc.bs.ctypes.data if soc is not None else None, inner_rho=soc_x.rho,
+                                  inner_max_iter=soc_x.max_iter, inner_threshold=soc_x.threshold,
+                                  n_x_rows=len(comps), x_row_idx=comps.ctypes.data, x_bs=soc_x.bs.ctypes.data)
+        elif soc is None:                    # no projection: unconstrained iSLS step (z = x)
             so = _lib.SlsAdmmOpts(max_iter=0, rho_u=0.0, alpha=relax, tol=tol, fixed_budget=int(fixed_budget),
                                   n_cones=0, cone_rows=C_ + 1, inner_rho=1.0, inner_max_iter=1, inner_threshold=1.0)
         else:

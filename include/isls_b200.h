@@ -195,6 +195,12 @@ int isls_ilqr_admm_solve_f64(const isls_plan *plan, const isls_solve_opts *opts,
  * inner_rho, inner_max_iter, inner_threshold; its other fields are ignored).  Riccati form: one K-pass per outer
  * iteration, dim + 1 feed-forward passes + linear rollouts per ADMM iteration instead of the dense (N m)^2 inverse of
  * isls.py:562-579.  The plan needs rho_u (Rr = diag) and isls_dim = dim; N * m <= 1024.
+ * State side (project_x, isls.py:556-559, 571-572, 631-638, 648-650): plan with rho_x (Qr = diag, zero on the rows that
+ * are not penalised) and soc->n_x_rows > 0, read here as: x_row_idx[g] = a projected state COMPONENT (<= 8 of them),
+ * x_bs [n_x_rows, P, cone_rows] = the cone offsets of that component (the A_i are shared with the control side),
+ * rho_x_rows not read.  project_x(z, x_nom) shifts column 0 by x_nom, projects the N rows of every listed component of
+ * [d_x | Phi_x(:, :dim)] with one project_set_convex call per component and passes all other rows through.
+ * soc->bs == NULL with n_cones > 0: the control side is not projected (the isls_admm method called with project_x alone).
  *   du_dev [B, N, m] (= x_u[:, 0]), phi_u_dev [B, N, m, dim] (= x_u[:, 1:]) of the last ADMM iterate. */
 struct isls_sls_admm_opts;
 int isls_isls_admm_solve_f64(const isls_plan *plan, const isls_solve_opts *opts, const struct isls_sls_admm_opts *soc,

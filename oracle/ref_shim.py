@@ -301,9 +301,28 @@ def run_isls_admm(model, p, b=0):
                                 max_iter=rb["inner_max_iter"], threshold=rb["inner_threshold"], verbose=0)
         y_[:, 0] -= u_nom_
         return y_
+    kw = dict(project_u=project_u, rho_u=rb["rho_u"])
+    if rb.get("u_unprojected"):
+        kw = {}
+    rx = rb.get("x")
+    if rx:
+        N, n = p["N"], p["n"]
+
+        def project_x(x, x_nom):                                    # the state-side twin of cell 25
+            x_nom_ = x_nom.flatten()
+            y_ = x.copy()
+            y_[:, 0] += x_nom_
+            for g, comp in enumerate(rx["comps"]):
+                rows = np.arange(N) * n + comp
+                y_[rows] = project_set_convex(y_[rows], As, list(rx["bs"][g]), projections=[project_soc_unit] * len(As),
+                                              rho=rb["inner_rho"], max_iter=rb["inner_max_iter"],
+                                              threshold=rb["inner_threshold"], verbose=0)
+            y_[:, 0] -= x_nom_
+            return y_
+        kw.update(project_x=project_x, rho_x=np.diag(rx["rho_x"][0]))
     with quiet():
-        du, phi_u = s.isls_admm(rb["dim"], model.get_AB, max_line_search=p["L"], k_max=p["I_o"], project_u=project_u,
-                                rho_u=rb["rho_u"], max_admm_iter=p["I_a"], threshold=p["tol"], verbose=0, log=True)
+        du, phi_u = s.isls_admm(rb["dim"], model.get_AB, max_line_search=p["L"], k_max=p["I_o"],
+                                max_admm_iter=p["I_a"], threshold=p["tol"], verbose=0, log=True, **kw)
     return dict(x=s.x_nom.copy(), u=s.u_nom.copy(), cost_log=np.array(s.cost_log, dtype=np.float64), du=du.copy(),
                 phi_u=phi_u.copy())
 

@@ -158,12 +158,19 @@ def _T(a):
     return np.swapaxes(a, -1, -2)
 
 
-def backward_pass(A, Bm, cx, cu, Cxx, Cuu, Cux=None, logs=False):
+def backward_pass(A, Bm, cx, cu, Cxx, Cuu, Cux=None, logs=False, joseph=False):
     """Riccati recursion of isls.py:229-308 (general `Cts` branch), batched.
 
     A[B,N,n,n], Bm[B,N,n,m], cx[B,N,n], cu[B,N,m], Cxx[B,N,n,n], Cuu[B,N,m,m] (leading B may be 1 for the
     cost terms), Cux[B,N,m,n] or None.  Returns K[B,N,m,n], k[B,N,m], non_pd[B] (+ Quu, Quu_inv, Qux logs as in
     sls.py:117-120,159-162).  K[N-1] = k[N-1] = 0 (isls.py:245-246, 261).
+
+    joseph=True evaluates the same V in the closed-loop form V = Cxx + K'Cuu K + (A + BK)'V(A + BK) (needs Cux = 0).
+    The reference's four-term expression (isls.py:300) cancels catastrophically in FP64 when the control is cheap
+    next to the accumulated state weights: on the arm with R = 1e-4 and Qr = 10 on the joint velocities (isls_admm with
+    project_x alone) it reproduces the first controls of the exact minimiser - the reference's dense solve, a 60-digit
+    Riccati recursion - to 1 digit only, the closed-loop form to 1e-11.  isls_admm, whose reference IS the dense solve
+    (isls.py:562-579), uses it.
     """
     Bsz, N, n, m = Bm.shape
     K = np.zeros((Bsz, N, m, n))
@@ -193,7 +200,12 @@ def backward_pass(A, Bm, cx, cu, Cxx, Cuu, Cux=None, logs=False):
         rhs = np.concatenate([Qux, qu[:, :, None]], axis=-1)
         sol = -np.linalg.solve(Quu_s, rhs)
         Kt, kt = sol[:, :, :-1], sol[:, :, -1]
-        V = Qxx + _T(Kt) @ Quu @ Kt + _T(Qux) @ Kt + _T(Kt) @ Qux                       # isls.py:300
+        if joseph:
+            Acl = At + Bt @ Kt
+            Vn = _T(Acl) @ (V @ Acl) + _T(Kt) @ np.broadcast_to(Cuu[:, t], (Bsz, m, m)) @ Kt
+            V = 0.5 * (Vn + _T(Vn)) + Cxx[:, t]
+        else:
+            V = Qxx + _T(Kt) @ Quu @ Kt + _T(Qux) @ Kt + _T(Kt) @ Qux                   # isls.py:300
         v = (qx + np.einsum("bji,bj->bi", Kt, qu) + np.einsum("bji,bj->bi", Kt, np.einsum("bij,bj->bi", Quu, kt))
              + np.einsum("bji,bj->bi", Qux, kt))                                         # isls.py:302
         K[:, t], k[:, t] = Kt, kt
@@ -979,14 +991,21 @@ def isls_admm(p, fixed_budget=False):
     du_{N-1} = -Cuu^-1 cu.  Line search on column 0 only, cost_function without penalty terms (isls.py:586-599);
     ADMM on the matrix variable with the row-wise projection, residuals weighted by Rr (isls.py:641-654), stall
     threshold 1e-3 (isls.py:664), outer stop |dcost| < 1e-4 or oscillation (isls.py:700-706).
+    State side (project_x, isls.py:556-559, 571-572, 631-638, 648-650), when p["robust"]["x"] is given: Qr = diag(rho_x)
+    joins Cxx, the columns get the linear state terms cx -= 2 Qr reg_x (column 0) / cx = -2 Qr reg_x (columns >= 1),
+    x_x = [x_win - x^ | dx of the linear rollouts], z_x = project_x(alpha x_x + (1 - alpha) z_x + lambda_x, x_nom) with
+    the closure of ref_shim.run_isls_admm (column 0 shifted by x_nom; one project_set_convex call per listed state
+    component over its N rows; all other rows pass through), residuals ||Qr .||_F added to the control side's.
     Returns per problem: x, u, cost_log, d_u [N,m], phi_u [N,m,dim], iteration counts."""
     model = _model_of(p)
     N, n, m = p["N"], p["n"], p["m"]
     rb = p["robust"]
     dim, rho = rb["dim"], float(rb["rho_u"])
-    projected = rb.get("As") is not None                   # isls_admm without project_u: Rr = 0, z = x (cell 23)
+    projected = rb.get("As") is not None and not rb.get("u_unprojected", False)   # no project_u: Rr = 0, z = x (cell 23)
     if not projected:
         rho = 0.0
+    rx = rb.get("x")                                       # state side: dict(comps, bs [G][P][ra], rho_x [N, n])
+    rhx = np.asarray(rx["rho_x"], float) if rx else np.zeros((p["N"], p["n"]))
     I_o, I_a, L, tol, relax = p["I_o"], p["I_a"], p["L"], p["tol"], p.get("alpha", 1.0)
     x_nom, u_nom = initial_rollout(p)
     B = x_nom.shape[0]
@@ -1004,44 +1023,53 @@ def isls_admm(p, fixed_budget=False):
     outer_iters = np.zeros(B, dtype=np.int32)
     admm_iters = np.zeros((B, I_o), dtype=np.int32)
     inner_iters = np.zeros((B, I_o, I_a), dtype=np.int32)
+    inner_iters_x = np.zeros((B, I_o, I_a, len(rx["comps"]) if rx else 0), dtype=np.int32)
+    d_x = np.zeros((B, N, n))
+    phi_x = np.zeros((B, N, n, dim))
     res_log = np.full((B, I_o, I_a, 2), np.nan)
     alpha_idx = np.full((B, I_o, I_a), -1, dtype=np.int32)
     d_u = np.zeros((B, N, m))
     phi_u = np.zeros((B, N, m, dim))
-    Cxx = _diag_embed(2.0 * Qd)[None]
+    Cxx = _diag_embed(2.0 * (Qd + rhx))[None]
     Cuu = _diag_embed(np.broadcast_to(2.0 * (R + rho), (N, m)))[None]
     Cuu_last = 2.0 * (R + rho)
     for b in range(B):
         z_u = np.zeros((N, m, C))                                             # z_u_init (isls.py:537)
+        z_x = np.zeros((N, n, C))                                             # z_x_init (isls.py:536)
         xn, un = x_nom[b:b + 1].copy(), u_nom[b:b + 1].copy()
         for k in range(I_o):
             prev_cost = cost[b]
             A, Bm = model.get_AB(xn, un)
             Kg, _, non_pd, Quu, Quu_inv, Qux = backward_pass(A, Bm, np.zeros((1, N, n)), np.zeros((1, N, m)), Cxx, Cuu,
-                                                             logs=True)
+                                                             logs=True, joseph=True)
             if non_pd[0]:
                 status[b] |= ST_NON_PD
             lam = np.zeros_like(z_u)                                          # lmb_u = 0 (isls.py:615)
+            lam_x = np.zeros_like(z_x)                                        # lmb_x = 0 (isls.py:614)
+            x_x = np.zeros((N, n, C))
             prim = dual = 1e6
             cx0 = 2.0 * Qd * (xn - zs[b:b + 1][:, seq])
             x_u = np.zeros((N, m, C))
             x_win = xn.copy()
             for j in range(I_a):
                 reg = z_u - lam                                               # isls.py:624
+                reg_x = z_x - lam_x                                           # isls.py:623
                 # ---- f_argmin (isls.py:568-608)
                 du_ = np.zeros((N, m, C))
+                dx_ = np.zeros((N, n, C))
                 for c in range(C):
                     if c == 0:
-                        cx, cu = cx0, 2.0 * R * un - 2.0 * rho * reg[None, :, :, 0]
+                        cx, cu = cx0 - 2.0 * rhx * reg_x[None, :, :, 0], 2.0 * R * un - 2.0 * rho * reg[None, :, :, 0]
                         dx0 = None
                     else:
-                        cx, cu = np.zeros((1, N, n)), -2.0 * rho * reg[None, :, :, c]
+                        cx, cu = -2.0 * rhx * reg_x[None, :, :, c], -2.0 * rho * reg[None, :, :, c]
                         dx0 = np.zeros((1, n))
                         dx0[0, c - 1] = 1.0
                     kk = ff_pass(A, Bm, cx, cu, Kg, Quu, Quu_inv, Qux)
                     kk[:, -1] = -cu[:, -1] / Cuu_last
-                    _, duc = linear_rollout(A, Bm, Kg, kk, dx0)
+                    dxc, duc = linear_rollout(A, Bm, Kg, kk, dx0)
                     du_[:, :, c] = duc[0]
+                    dx_[:, :, c] = dxc[0]
                 u_cand = un[:, None] + al[None, :, None, None] * du_[None, None, :, :, 0]
                 x_cand = rollout_open(model, xn[:, 0], u_cand)
                 costs = total_cost(p, zs[b:b + 1], x_cand, u_cand)            # isls.py:586 (no penalty terms)
@@ -1050,6 +1078,8 @@ def isls_admm(p, fixed_budget=False):
                 x_u = du_.copy()
                 x_u[:, :, 0] = al[ind] * du_[:, :, 0]                         # isls.py:602-603
                 x_win = x_cand[:, ind]
+                x_x = dx_.copy()
+                x_x[:, :, 0] = (x_win - xn)[0]                                # isls.py:605-606
                 # ---- ADMM update (isls.py:628-654)
                 z_prev = z_u
                 y = relax * x_u + (1.0 - relax) * z_u + lam
@@ -1069,6 +1099,22 @@ def isls_admm(p, fixed_budget=False):
                 pprim, pdual = prim, dual
                 dual = np.linalg.norm(rho * (z_u - z_prev).reshape(N * m, C))
                 prim = np.linalg.norm(rho * r.reshape(N * m, C))
+                if rx:                                                        # isls.py:631-638, 648-650
+                    zx_prev = z_x
+                    yx = (relax * x_x + (1.0 - relax) * z_x + lam_x).reshape(N * n, C).copy()
+                    yx[:, 0] += xn[0].reshape(-1)
+                    for g, comp in enumerate(rx["comps"]):
+                        rows = np.arange(N) * n + comp
+                        yx[rows], itx = project_set_convex_soc(yx[rows], rb["As"], rx["bs"][g], rho=rb["inner_rho"],
+                                                               max_iter=rb["inner_max_iter"],
+                                                               threshold=rb["inner_threshold"])
+                        inner_iters_x[b, k, j, g] = itx
+                    yx[:, 0] -= xn[0].reshape(-1)
+                    z_x = yx.reshape(N, n, C)
+                    r_x = x_x - z_x
+                    lam_x = lam_x + r_x
+                    dual = np.linalg.norm((rhx[:, :, None] * (z_x - zx_prev)).reshape(N * n, C)) + dual
+                    prim = np.linalg.norm((rhx[:, :, None] * r_x).reshape(N * n, C)) + prim
                 res_log[b, k, j] = prim, dual
                 admm_iters[b, k] = j + 1
                 if not fixed_budget:
@@ -1088,6 +1134,8 @@ def isls_admm(p, fixed_budget=False):
             outer_iters[b] = k + 1
             d_u[b] = x_u[:, :, 0]
             phi_u[b] = x_u[:, :, 1:]
+            d_x[b] = x_x[:, :, 0]
+            phi_x[b] = x_x[:, :, 1:]
             if not fixed_budget:
                 if abs(newc - prev_cost) < 1e-4:                              # isls.py:700
                     status[b] |= ST_CONVERGED_COST
@@ -1103,4 +1151,4 @@ def isls_admm(p, fixed_budget=False):
         x_nom[b], u_nom[b] = xn[0], un[0]
     return dict(x=x_nom, u=u_nom, cost=cost, cost_log=cost_log, n_log=n_log, status=status, outer_iters=outer_iters,
                 admm_iters=admm_iters, inner_iters=inner_iters, res_log=res_log, alpha_idx=alpha_idx, d_u=d_u,
-                phi_u=phi_u)
+                phi_u=phi_u, d_x=d_x, phi_x=phi_x, inner_iters_x=inner_iters_x)

@@ -388,6 +388,26 @@ def golden_isls_admm(B=3):
                         unc_phi_u=np.stack(uphis), **ctrl)
 
 
+def golden_isls_admm_x(B=3):
+    """Robust iSLS-ADMM of the unmodified reference with a STATE-side projection (isls.py:631-638: project_x on
+    [d_x | Phi_x(:, :3)]): chance-constrained bounds on two joint velocities of the arm beside the control bounds
+    (problems of configs.arm_robust_x_batch, closure in ref_shim.run_isls_admm), and once with project_x alone."""
+    p = P.arm_robust_x_batch(B)
+    model = M.make_model("arm3", dt=p["dt"])
+    xs, us, logs, dus, phis = [], [], [], [], []
+    for b in range(B):
+        r = S.run_isls_admm(model, p, b)
+        xs.append(r["x"]); us.append(r["u"]); logs.append(r["cost_log"]); dus.append(r["du"]); phis.append(r["phi_u"])
+        print("isls_admm_x", b, len(r["cost_log"]), r["cost_log"][-1], "max|qd|", np.abs(r["x"][:, 3:6]).max(0))
+    p1 = P.arm_robust_x_batch(1, project_u=False)
+    r1 = S.run_isls_admm(model, p1, 0)
+    print("isls_admm_x (state side only)", len(r1["cost_log"]), r1["cost_log"][-1], "max|qd|", np.abs(r1["x"][:, 3:6]).max(0),
+          "max|u|", np.abs(r1["u"]).max())
+    np.savez_compressed(os.path.join(OUT, "arm_isls_admm_x.npz"), x0=p["x0"], x=np.stack(xs), u=np.stack(us),
+                        cost_log=_pad(logs), du=np.stack(dus), phi_u=np.stack(phis), xonly_x=r1["x"], xonly_u=r1["u"],
+                        xonly_cost_log=r1["cost_log"], xonly_du=r1["du"], xonly_phi_u=r1["phi_u"])
+
+
 def golden_di_obstacles():
     """LQT-ADMM with the spherical-obstacle state projection (set-convex + Dykstra) of the unmodified reference:
     the notebook problem with ADMM_LQT_DP (500 iterations: printed cost 2.701e-01) and ADMM_LQT_Batch, plus three more
@@ -686,6 +706,8 @@ if __name__ == "__main__":
         golden_parking()
     if want("isls_admm"):
         golden_isls_admm()
+    if want("isls_admm_x"):
+        golden_isls_admm_x()
     if want("sls_state"):
         golden_sls_state_bounds()
     if want("replan"):

@@ -77,6 +77,15 @@ def run_isls_admm(p, fixed_budget=False, device="cuda:0"):
     s = make_isls(p, device)
     soc = False if rb.get("As") is None else SetConvexSOC(rb["As"], rb["bs"], rho=rb["inner_rho"],
                                                           max_iter=rb["inner_max_iter"], threshold=rb["inner_threshold"])
+    kw = {}
+    if rb.get("u_unprojected"):
+        soc = False
+    if rb.get("x"):
+        from isls_b200 import SetConvexSOCComponents
+        rx = rb["x"]
+        kw.update(project_x=SetConvexSOCComponents(rx["comps"], rb["As"], rx["bs"], rho=rb["inner_rho"],
+                                                   max_iter=rb["inner_max_iter"], threshold=rb["inner_threshold"]),
+                  rho_x=rx["rho_x"])
     s.isls_admm(rb["dim"], p["model"], project_u=soc, max_admm_iter=p["I_a"], k_max=p["I_o"], max_line_search=p["L"],
-                rho_u=rb["rho_u"], alpha=p.get("alpha", 1.0), threshold=p["tol"], fixed_budget=fixed_budget)
+                rho_u=rb["rho_u"], alpha=p.get("alpha", 1.0), threshold=p["tol"], fixed_budget=fixed_budget, **kw)
     return {k: v.cpu().numpy() for k, v in s.last.items()}

@@ -270,6 +270,40 @@ def test_isls_admm_riccati_form_vs_reference_golden(golden):
     assert np.abs(o["u"]).max() < 6.0                       # the nominal respects the (tightened) bound
 
 
+def test_isls_admm_state_projection_vs_reference_golden(golden):
+    """isls_admm with project_x (isls.py:556-559, 571-572, 631-638, 648-650): robust bounds on two joint velocities of
+    the arm, with and without the control-side projection, against the unmodified reference (closure in
+    oracle/ref_shim.run_isls_admm).  The state-side-only case is the cheap-control regime (R = 1e-4, no Rr) where the
+    four-term value recursion fails and the closed-loop form is needed (backward_pass(joseph=True))."""
+    g = golden("arm_isls_admm_x")
+    p = P.arm_robust_x_batch(1)
+    o = R.isls_admm(p)
+    ref = g["cost_log"][0]
+    n_ref = int((~np.isnan(ref)).sum())
+    assert o["n_log"][0] == n_ref
+    assert np.abs(o["cost_log"][0, :n_ref] - ref[:n_ref]).max() < 1e-9 * np.abs(ref[:n_ref]).max()
+    N, m = p["N"], p["m"]
+    assert np.abs(o["x"][0] - g["x"][0]).max() < 1e-9 and np.abs(o["u"][0] - g["u"][0]).max() < 1e-9
+    assert np.abs(o["phi_u"][0].reshape(N * m, -1) - g["phi_u"][0]).max() < 1e-9 * max(1.0, np.abs(g["phi_u"][0]).max())
+    p1 = P.arm_robust_x_batch(1, project_u=False)
+    o1 = R.isls_admm(p1)
+    r1 = g["xonly_cost_log"]
+    assert o1["n_log"][0] == len(r1)
+    assert np.abs(o1["cost_log"][0, :len(r1)] - r1).max() < 1e-8 * np.abs(r1).max()
+    assert np.abs(o1["x"][0] - g["xonly_x"]).max() < 1e-7 and np.abs(o1["u"][0] - g["xonly_u"]).max() < 1e-5
+    # the four-term recursion on the first linearisation of this problem: 10 % off in the first controls
+    model = R._model_of(p1)
+    xn, un = R.initial_rollout(p1)
+    A, Bm = model.get_AB(xn, un)
+    Qd = np.asarray(p1["Qdiag"], float)[p1["seq"]]
+    Cxx = R._diag_embed(2.0 * (Qd + p1["robust"]["x"]["rho_x"]))[None]
+    Cuu = R._diag_embed(np.full((N, m), 2.0 * p1["u_std"]))[None]
+    z = np.zeros((1, N, p1["n"])), np.zeros((1, N, m))
+    K4 = R.backward_pass(A, Bm, z[0], z[1], Cxx, Cuu)[0]
+    Kj = R.backward_pass(A, Bm, z[0], z[1], Cxx, Cuu, joseph=True)[0]
+    assert np.abs(K4[0, 0] - Kj[0, 0]).max() > 1e-3 * np.abs(Kj[0, 0]).max()
+
+
 def test_lqt_admm_batch_form_vs_reference_golden(golden):
     """SLS.ADMM_LQT_Batch (isls/sls.py:250-294; SURVEY 8d C1: "converged at iteration 580"): the Riccati-form
     restatement with batch-form last control and the unconstrained warm start against the unmodified reference."""
