@@ -258,6 +258,277 @@ __global__ void __launch_bounds__(TILE) k_riccati_generic_staged(int N, long lon
   if (non_pd && valid) non_pd[b] = ok ? 0 : 1;
 }
 
+// Warp-split variant for the large shape (n = 9, m = 3: 2.1 KB of operands per problem and step, 68 KB per 32-problem
+// stage - too much shared memory to hide a lone warp's latency with several resident CTAs, and V, VA, Qxx = 3 x 81
+// doubles do not fit a thread's registers).  CTA = 32 problems x G warps, lane = problem:
+//   * the operand blocks of a step are fetched by the TMA engine, one 1-D bulk copy per (problem, array) into a
+//     [problem][A | B | c | C] stage, completion on an mbarrier.  (8-byte cp.async copies of the same bytes are bound by
+//     the number of L1 misses an SM keeps in flight: 1.79 ms per 16,384 passes against ... with bulk copies.)  The A
+//     and B blocks are 648 / 216 bytes - 8 modulo 16 - so a block whose source is not 16-byte aligned is fetched from
+//     8 bytes earlier (656 / 224 bytes) and read at an offset of one double; the step N-1 blocks (the last one must not
+//     be over-read) come in through cp.async;
+//   * one stage per CTA, two CTAs per SM: a CTA refills its stage as soon as its warps are done with the operands and
+//     the other CTA computes meanwhile;
+//   * warp w owns the columns j = w, w + G, ... of every n-column product (VA, Qxx, Qux, K, V') and the column(s) a = w,
+//     ... of VB / Quu; its columns live in registers with compile-time indices (no local memory), V is shared
+//     through shared memory, Quu, K and Qux are exchanged through it (3 CTA barriers per step); the 3 x 3 inverse, q_x,
+//     q_u, k and v are computed redundantly by every warp (splitting q_x and v by entry behind warp-uniform branches
+//     was 9 % slower: the branches cut the unrolled schedule);
+//   * K_t leaves through the exchange buffer as 216-byte runs per problem.
+// Every sum runs in the order of riccati_generic_step: results are bit-identical to k_riccati_generic.
+template <int n, int m, int G>
+__global__ void __launch_bounds__(TILE * G) k_riccati_generic_ws(int N, long long B, const double *Ag, const double *Bg,
+                                                                 const double *cg, const double *Cg, double *Kg,
+                                                                 double *kg, int *non_pd) {
+  constexpr int nm = n + m, EA = n * n, EB = n * m, Ec = nm, EC = nm * nm;
+  constexpr int PA = (EA + 1 + 1) / 2 * 2, PBm = (EB + 1 + 1) / 2 * 2;          // padded A, B slots (doubles, even)
+  constexpr int oA = 0, oB = PA, oc = PA + PBm, oC = oc + Ec, PB = oC + EC;     // per-problem block (doubles)
+  static_assert(Ec % 2 == 0 && EC % 2 == 0 && PB % 2 == 0, "16-byte granularity of the bulk copies");
+  static_assert(EA % 2 == 1 && EB % 2 == 1, "the shifted-source scheme assumes odd A and B blocks");
+  constexpr int NJ = (n + G - 1) / G, MJ = (m + G - 1) / G;
+  extern __shared__ __align__(16) double ric_sm[];
+  double *stage = ric_sm;                                     // [TILE][PB]
+  double *sV = stage + (size_t)TILE * PB;                     // [n * n][TILE]
+  double *sK = sV + n * n * TILE;                             // [m * n][TILE]
+  double *sQx = sK + m * n * TILE;                            // [m * n][TILE]
+  double *sQu = sQx + m * n * TILE;                           // [m * m][TILE]
+  unsigned long long *bar = (unsigned long long *)(sQu + m * m * TILE);
+  const int lane = threadIdx.x, w = threadIdx.y, tid = w * TILE + lane;
+  const long long b0 = (long long)blockIdx.x * TILE, b = b0 + lane;
+  const bool valid = b < B;
+  const int np = (int)min((long long)TILE, B - b0);
+  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  // step N-1 by cp.async (8-byte copies, no over-read): warp w copies problems w, w + G, ...
+  for (int p = w; p < np; p += G) {
+    const size_t r = (size_t)(b0 + p) * N + (N - 1);
+    double *dst = stage + (size_t)p * PB;
+    const int sh = (int)(r & 1);
+    for (int e = lane; e < EA; e += TILE) cp_async8(dst + oA + sh + e, Ag + r * EA + e);
+    for (int e = lane; e < EB; e += TILE) cp_async8(dst + oB + sh + e, Bg + r * EB + e);
+    for (int e = lane; e < Ec; e += TILE) cp_async8(dst + oc + e, cg + r * Ec + e);
+    for (int e = lane; e < EC; e += TILE) cp_async8(dst + oC + e, Cg + r * EC + e);
+  }
+  cp_async_commit();
+  // bulk fill of step t < N-1: lane l of warp w issues the copy of array l & 3 of problem w + G (l >> 2 + 8 pass)
+  auto issue = [&](int t) {
+    // (the stage was only READ through the generic proxy; the CTA barrier before this call orders those reads before
+    // the bulk writes - no proxy fence needed for this write-after-read)
+    if (tid == 0) mbar_expect_tx(bar, (unsigned)(np * PB * sizeof(double)));
+#pragma unroll
+    for (int pass = 0; pass < (TILE / G + 8) / 8; pass++) {
+      const int p = w + G * (pass * 8 + (lane >> 2));
+      if (p < np) {
+        const size_t r = (size_t)(b0 + p) * N + t;
+        double *dst = stage + (size_t)p * PB;
+        const int q = lane & 3, sh = (int)(r & 1);
+        if (q == 0) bulk_g2s(dst + oA, Ag + r * EA - sh, PA * sizeof(double), bar);
+        else if (q == 1) bulk_g2s(dst + oB, Bg + r * EB - sh, PBm * sizeof(double), bar);
+        else if (q == 2) bulk_g2s(dst + oc, cg + r * Ec, Ec * sizeof(double), bar);
+        else bulk_g2s(dst + oC, Cg + r * EC, EC * sizeof(double), bar);
+      }
+    }
+  };
+  double *kb = kg + (size_t)(valid ? b : 0) * N * m;
+  double v[n];
+  bool ok = true;
+  unsigned parity = 0;
+  for (int t = N - 1; t >= 0; t--) {
+    if (t == N - 1) cp_async_wait<0>();
+    __syncthreads();                                          // V of step t+1 is visible (and the cp.async stage)
+    if (t < N - 1) { mbar_wait(bar, parity); parity ^= 1; }   // the bulk copies of step t have landed
+    const size_t rl = (size_t)(valid ? b : b0) * N + t;
+    const int shl = (int)(rl & 1);
+    const double *pl = stage + (size_t)lane * PB;
+    const double *A = pl + oA + shl, *Bm = pl + oB + shl, *cc = pl + oc, *C = pl + oC;
+    if (t == N - 1) {                                         // V_N-1 = Cxx, v_N-1 = cx (isls.py:257-258); K = k = 0
+#pragma unroll
+      for (int jj = 0; jj < NJ; jj++) {
+        const int j = w + G * jj;
+        if (j < n) {
+#pragma unroll
+          for (int i = 0; i < n; i++) sV[(i * n + j) * TILE + lane] = C[i * nm + j];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < n; i++) v[i] = cc[i];
+      static_assert(m * n <= TILE, "K_t of one problem is stored by one warp pass");
+      if (lane < m * n)
+        for (int p = w; p < np; p += G) Kg[((size_t)(b0 + p) * N + t) * (m * n) + lane] = 0.0;
+      if (valid && w == 0) {
+#pragma unroll
+        for (int j = 0; j < m; j++) kb[(size_t)t * m + j] = 0.0;
+      }
+      __syncthreads();                                        // every warp is done with the stage
+      if (t > 0) issue(t - 1);
+      continue;
+    }
+    // ---- own columns of A and B in registers
+    double Ao[NJ][n], Bo[MJ][n], VAo[NJ][n], VBo[MJ][n];
+#pragma unroll
+    for (int jj = 0; jj < NJ; jj++) {
+      const int j = min(w + G * jj, n - 1);
+#pragma unroll
+      for (int k = 0; k < n; k++) Ao[jj][k] = A[k * n + j];
+    }
+#pragma unroll
+    for (int aa = 0; aa < MJ; aa++) {
+      const int a = min(w + G * aa, m - 1);
+#pragma unroll
+      for (int k = 0; k < n; k++) Bo[aa][k] = Bm[k * m + a];
+    }
+    // ---- VA, VB (own columns): one pass over the rows of V
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+      double Vr[n];
+#pragma unroll
+      for (int k = 0; k < n; k++) Vr[k] = sV[(i * n + k) * TILE + lane];
+#pragma unroll
+      for (int jj = 0; jj < NJ; jj++) {
+        double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < n; k++) a = fma(Vr[k], Ao[jj][k], a);
+        VAo[jj][i] = a;
+      }
+#pragma unroll
+      for (int aa = 0; aa < MJ; aa++) {
+        double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < n; k++) a = fma(Vr[k], Bo[aa][k], a);
+        VBo[aa][i] = a;
+      }
+    }
+    // ---- Qxx (own columns) and q_x: one pass over the columns of A
+    double Qxxo[NJ][n], qx[n];
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+      double Ac[n];
+#pragma unroll
+      for (int k = 0; k < n; k++) Ac[k] = A[k * n + i];
+      double a = cc[i];
+#pragma unroll
+      for (int k = 0; k < n; k++) a = fma(Ac[k], v[k], a);
+      qx[i] = a;
+#pragma unroll
+      for (int jj = 0; jj < NJ; jj++) {
+        const int j = min(w + G * jj, n - 1);
+        double s2 = C[i * nm + j];
+#pragma unroll
+        for (int k = 0; k < n; k++) s2 = fma(Ac[k], VAo[jj][k], s2);
+        Qxxo[jj][i] = s2;
+      }
+    }
+    // ---- Qux (own columns), q_u, Quu (own columns): one pass over the columns of B
+    double Quxo[NJ][m], qu[m];
+#pragma unroll
+    for (int i = 0; i < m; i++) {
+      double Bc[n];
+#pragma unroll
+      for (int k = 0; k < n; k++) Bc[k] = Bm[k * m + i];
+      double a = cc[n + i];
+#pragma unroll
+      for (int k = 0; k < n; k++) a = fma(Bc[k], v[k], a);
+      qu[i] = a;
+#pragma unroll
+      for (int jj = 0; jj < NJ; jj++) {
+        const int j = min(w + G * jj, n - 1);
+        double s2 = C[(n + i) * nm + j];
+#pragma unroll
+        for (int k = 0; k < n; k++) s2 = fma(Bc[k], VAo[jj][k], s2);
+        Quxo[jj][i] = s2;
+      }
+#pragma unroll
+      for (int aa = 0; aa < MJ; aa++) {
+        const int a2 = w + G * aa;
+        if (a2 < m) {
+          double s2 = C[(n + i) * nm + n + a2];
+#pragma unroll
+          for (int k = 0; k < n; k++) s2 = fma(Bc[k], VBo[aa][k], s2);
+          sQu[(i * m + a2) * TILE + lane] = s2;
+        }
+      }
+    }
+    __syncthreads();                                          // Quu complete; every warp is done with V and the stage
+    if (t > 0) issue(t - 1);                                  // refill the stage with the next step's operands
+    double Quu[m][m], Qui[m][m], kt[m];
+#pragma unroll
+    for (int i = 0; i < m; i++)
+#pragma unroll
+      for (int j = 0; j < m; j++) Quu[i][j] = sQu[(i * m + j) * TILE + lane];
+    ok &= spd_inverse<m>(Quu, Qui);
+    double Ko[NJ][m];
+#pragma unroll
+    for (int jj = 0; jj < NJ; jj++) {
+      const int j = w + G * jj;
+#pragma unroll
+      for (int a = 0; a < m; a++) {
+        double s2 = 0.0;
+#pragma unroll
+        for (int b2 = 0; b2 < m; b2++) s2 = fma(Qui[a][b2], Quxo[jj][b2], s2);
+        Ko[jj][a] = -s2;
+        if (j < n) {
+          sK[(a * n + j) * TILE + lane] = -s2;
+          sQx[(a * n + j) * TILE + lane] = Quxo[jj][a];
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < m; a++) {
+      double s2 = 0.0;
+#pragma unroll
+      for (int b2 = 0; b2 < m; b2++) s2 = fma(Qui[a][b2], qu[b2], s2);
+      kt[a] = -s2;
+    }
+    __syncthreads();                                          // K, Qux complete
+    double QKo[NJ][m], Qk[m];
+#pragma unroll
+    for (int jj = 0; jj < NJ; jj++)
+#pragma unroll
+      for (int a = 0; a < m; a++) {
+        double s2 = 0.0;
+#pragma unroll
+        for (int b2 = 0; b2 < m; b2++) s2 = fma(Quu[a][b2], Ko[jj][b2], s2);
+        QKo[jj][a] = s2;
+      }
+#pragma unroll
+    for (int a = 0; a < m; a++) {
+      double s2 = 0.0;
+#pragma unroll
+      for (int b2 = 0; b2 < m; b2++) s2 = fma(Quu[a][b2], kt[b2], s2);
+      Qk[a] = s2;
+    }
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+      double Kf[m], Qf[m];                                    // column i of K and Qux (all rows) from the exchange
+#pragma unroll
+      for (int a = 0; a < m; a++) { Kf[a] = sK[(a * n + i) * TILE + lane]; Qf[a] = sQx[(a * n + i) * TILE + lane]; }
+#pragma unroll
+      for (int jj = 0; jj < NJ; jj++) {
+        const int j = w + G * jj;
+        double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+        for (int a = 0; a < m; a++) {
+          t1 = fma(Kf[a], QKo[jj][a], t1);
+          t2 = fma(Qf[a], Ko[jj][a], t2);
+          t3 = fma(Kf[a], Quxo[jj][a], t3);
+        }
+        if (j < n) sV[(i * n + j) * TILE + lane] = ((Qxxo[jj][i] + t1) + t2) + t3;            // isls.py:300
+      }
+      double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+      for (int a = 0; a < m; a++) { t1 = fma(Kf[a], qu[a], t1); t2 = fma(Kf[a], Qk[a], t2); t3 = fma(Qf[a], kt[a], t3); }
+      v[i] = ((qx[i] + t1) + t2) + t3;                                                         // isls.py:302
+    }
+    // ---- results: K_t as one 216-byte run per problem out of the exchange buffer, k_t by warp 0
+    if (lane < m * n)
+      for (int p = w; p < np; p += G) Kg[((size_t)(b0 + p) * N + t) * (m * n) + lane] = sK[lane * TILE + p];
+    if (valid && w == 0) {
+#pragma unroll
+      for (int a = 0; a < m; a++) kb[(size_t)t * m + a] = kt[a];
+    }
+  }
+  if (non_pd && valid && w == 0) non_pd[b] = ok ? 0 : 1;
+}
+
 // FP64 peak probe: 8 independent DFMA chains per thread
 __global__ void k_fp64_peak(double *out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -644,7 +915,20 @@ extern "C" int isls_riccati_f64(int32_t n, int32_t m, int32_t N, int64_t B, cons
   if (n == 2 && m == 1) { if (staged(k_riccati_generic_staged<2, 1, 2>, 4 + 2 + 3 + 9)) return 1; }
   else if (n == 4 && m == 2) { if (staged(k_riccati_generic_staged<4, 2, 2>, 16 + 8 + 6 + 36)) return 1; }
   else if (n == 6 && m == 3) { if (staged(k_riccati_generic_staged<6, 3, 2>, 36 + 18 + 9 + 81)) return 1; }
-  else if (n == 9 && m == 3) k_riccati_generic<9, 3><<<grid, 64, 0, s>>>(N, B, A, Bm, c, C, K, k, non_pd);
+  else if (n == 9 && m == 3) {
+    static const bool plain = getenv("ISLS_RICCATI_PLAIN") != nullptr;     // test switch: the one-thread-per-problem form
+    constexpr int G = 3, PB = 82 + 28 + 12 + 144;       // per-problem stage block (doubles), see the kernel
+    const size_t smem = ((size_t)TILE * PB + (size_t)(81 + 27 + 27 + 9) * TILE) * sizeof(double) + 16;
+    // the shifted-source bulk copies need 16-byte aligned array bases (any torch / cudaMalloc allocation is)
+    const bool aligned = ((((uintptr_t)A) | ((uintptr_t)Bm) | ((uintptr_t)c) | ((uintptr_t)C)) & 15) == 0;
+    if (plain || !aligned) {
+      k_riccati_generic<9, 3><<<grid, 64, 0, s>>>(N, B, A, Bm, c, C, K, k, non_pd);
+    } else {
+      CK(cudaFuncSetAttribute(k_riccati_generic_ws<9, 3, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_riccati_generic_ws<9, 3, G><<<(unsigned)((B + TILE - 1) / TILE), dim3(TILE, G), smem, s>>>(N, B, A, Bm, c, C, K, k,
+                                                                                              non_pd);
+    }
+  }
   else return fail(ISLS_E_UNSUPPORTED, "unsupported (n, m) for isls_riccati_f64");
   CK(cudaGetLastError());
   return ISLS_OK;

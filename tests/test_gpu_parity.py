@@ -220,6 +220,30 @@ def test_riccati_teacher_forced(golden):
             assert np.abs(k[b] - g["k"]).max() / np.abs(g["k"]).max() < 1e-10
 
 
+@pytest.mark.parametrize("n,m", [(9, 3), (4, 2), (6, 3)])
+def test_riccati_generic_ragged_batches_vs_oracle(n, m):
+    """isls_riccati_f64 on random dense operators (incl. Cux) against the oracle's backward_pass: batches that do not
+    fill the last 32-problem tile and horizons of both parities - the (9, 3) kernel fetches its A / B blocks with
+    16-byte bulk copies from a source shifted by the parity of (problem * N + t)."""
+    import torch
+    from isls_b200 import solver as S
+    rng = np.random.default_rng(100 * n + m)
+    for B, N in ((37, 7), (64, 12), (5, 100), (33, 31)):
+        A = np.eye(n) + 0.05 * rng.normal(size=(B, N, n, n))
+        Bm = 0.1 * rng.normal(size=(B, N, n, m))
+        c = rng.normal(size=(B, N, n + m))
+        W = rng.normal(size=(B, N, n + m, n + m))
+        C = W @ np.swapaxes(W, -1, -2) + np.eye(n + m)
+        t = lambda a: torch.as_tensor(a, device="cuda:0")
+        K, k, bad = S.riccati(t(A), t(Bm), t(c), t(C))
+        assert int(bad.sum()) == 0
+        Ko, ko, bo = R.backward_pass(A, Bm, c[..., :n], c[..., n:], C[..., :n, :n], C[..., n:, n:], Cux=C[..., n:, :n])
+        assert not bo.any()
+        eK = np.abs(K.cpu().numpy() - Ko).max() / np.abs(Ko).max()
+        ek = np.abs(k.cpu().numpy() - ko).max() / np.abs(ko).max()
+        assert eK < 1e-10 and ek < 1e-10, (n, m, B, N, eK, ek)
+
+
 def test_linesearch_stage_teacher_forced():
     """isls_rollout_linesearch_f64: same x_nom, u_nom, du, reg -> per-candidate costs, argmin and winner rollout
     of the oracle (isls.py:468-477)."""
