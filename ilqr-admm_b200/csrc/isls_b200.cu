@@ -742,7 +742,7 @@ size_t isls_carve(const isls_plan *p, long long B, char *base, Dev *d, Dev *alt)
   takeI(d ? &d->best : nullptr, S); takeI(d ? &d->odone : nullptr, S); takeI(d ? &d->adone : nullptr, S);
   takeI(d ? &d->nlog : nullptr, S); takeI(d ? &d->status : nullptr, S); takeI(d ? &d->oit : nullptr, S);
   takeI(d ? &d->ait : nullptr, S);
-  takeI(d ? &d->orig : nullptr, S); takeI(d ? &d->newpos : nullptr, S); takeI(d ? &d->nact : nullptr, 64);
+  takeI(d ? &d->orig : nullptr, S); takeI(d ? &d->newpos : nullptr, S); takeI(d ? &d->nact : nullptr, 320);   // [0] compaction count, [8..9] persistent line search, [64..319] per-SM arrival slots
   // alternate buffers of the compacting solve (ping-pong partner of xh, uh, zx, zu, zs and the per-problem scalars)
   takeD(alt ? &alt->xh : nullptr, tn); takeD(alt ? &alt->uh : nullptr, tm);
   takeD(alt ? &alt->zx : nullptr, tn); takeD(alt ? &alt->zu : nullptr, tm);

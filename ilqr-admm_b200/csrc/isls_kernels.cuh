@@ -1074,45 +1074,73 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // of operands in flight, reads plan constants from shared memory, and - with JC - takes the Jacobian scalars of the
 // linearisation from the cache k_kpass wrote (d.Jc) instead of re-evaluating sincos in both sweeps.
 // Finished lanes stay in the loop (the warp shares the copies) and are masked at the stores.
+// Shared-memory carve-up of the TMA-staged ff-pass (one warp): [NST + 8 mbarriers][ring][rho_u][rho_x][qnz][seq]
 template <class M, bool PX, bool JC, int TC, int NST>
-__global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
-  constexpr int n = M::n, m = M::m, nt = NTRI(M::m), NJ = M::NJA;
-  constexpr bool XB = !JC || PX;                          // the backward sweep stages x^ (Jacobian and / or cx)
+struct FfTmaShape {
+  static constexpr int n = M::n, m = M::m, nt = NTRI(M::m), NJ = M::NJA;
+  static constexpr bool XB = !JC || PX;                   // the backward sweep stages x^ (Jacobian and / or cx)
   // backward slab: doubles per lane and step
-  constexpr int oJ = 0, oX = oJ + (JC ? NJ : 0), oU = oX + (XB ? n : 0), oQx = oU + m, oQu = oQx + m * n,
-                oQi = oQu + nt, oRu = oQi + nt, oRx = oRu + m, SB = oRx + (PX ? n : 0);
+  static constexpr int oJ = 0, oX = oJ + (JC ? NJ : 0), oU = oX + (XB ? n : 0), oQx = oU + m, oQu = oQx + m * n,
+                       oQi = oQu + nt, oRu = oQi + nt, oRx = oRu + m, SB = oRx + (PX ? n : 0);
   // forward slab
-  constexpr int fK = 0, fk = fK + m * n, fU = fk + m, fRu = fU + m, fJ = fRu + m, SF = fJ + (JC ? NJ : n);
-  constexpr int NSTF_ = (NST * SB) / SF, NSTF = NSTF_ > 8 ? 8 : NSTF_;   // forward stages in the same memory
+  static constexpr int fK = 0, fk = fK + m * n, fU = fk + m, fRu = fU + m, fJ = fRu + m, SF = fJ + (JC ? NJ : n);
+  static constexpr int NSTF_ = (NST * SB) / SF, NSTF = NSTF_ > 8 ? 8 : NSTF_;   // forward stages in the same memory
   static_assert(SF <= SB, "forward slab must fit the backward slab");
-  extern __shared__ __align__(128) double smem_fft[];
+  static constexpr size_t RING_BYTES = (size_t)NST * TC * SB * TILE * sizeof(double);
+  static size_t smem_bytes(int N) {
+    return 128 + RING_BYTES + (size_t)N * (m + (PX ? n : 0)) * sizeof(double) + 2 * (size_t)N * sizeof(int);
+  }
+};
+
+// One warp: plan constants into shared memory, mbarrier initialisation
+template <class M, bool PX, bool JC, int TC, int NST>
+__device__ __forceinline__ void ff_tma_setup(const Dev &d, double *smem_fft, const int lane, double *cst = nullptr,
+                                             const bool fill_cst = true) {
+  using S = FfTmaShape<M, PX, JC, TC, NST>;
+  constexpr int n = S::n, m = S::m;
   unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_fft);     // [NST] backward, [8] forward
   double *ring = smem_fft + 16;
-  double *s_rhu = ring + (size_t)NST * TC * SB * TILE;    // plan constants of all steps
+  double *s_rhu = cst ? cst : ring + (size_t)NST * TC * S::SB * TILE;    // plan constants of all steps
   const int N = d.N;
   double *s_rhx = s_rhu + (size_t)N * m;
   int *s_qnz = reinterpret_cast<int *>(s_rhx + (PX ? (size_t)N * n : 0));
   int *s_seq = s_qnz + N;
-  const int lane = threadIdx.x;
-  const int ntiles = (d.tile1 - d.tile0 + d.tstep - 1) / d.tstep;
-  if ((int)blockIdx.x >= ntiles) return;
-  for (int q = lane; q < N * m; q += TILE) s_rhu[q] = d.proj_u ? d.rho_u[q] : 0.0;
-  if (PX)
-    for (int q = lane; q < N * n; q += TILE) s_rhx[q] = d.rho_x[q];
-  for (int q = lane; q < N; q += TILE) { s_qnz[q] = d.qnz[q]; s_seq[q] = d.seq[q]; }
+  if (fill_cst) {
+    for (int q = lane; q < N * m; q += TILE) s_rhu[q] = d.proj_u ? d.rho_u[q] : 0.0;
+    if (PX)
+      for (int q = lane; q < N * n; q += TILE) s_rhx[q] = d.rho_x[q];
+    for (int q = lane; q < N; q += TILE) { s_qnz[q] = d.qnz[q]; s_seq[q] = d.seq[q]; }
+  }
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < NST + 8; i++) mbar_init(&bar[i], 1);
     mbar_fence_init();
   }
   __syncwarp();
-  unsigned gb = 0, gf = 0;      // chunks consumed so far by this warp (backward / forward rings keep running across tiles)
-  // persistent over tiles (grid = tiles for the small-batch launches, fewer CTAs in the overlapped schedule)
-  for (int it = blockIdx.x; it < ntiles; it += gridDim.x) {
-  const int tile = d.tile0 + it * d.tstep;
+}
+
+// One warp, one tile: ff-pass + linear rollout.  gb / gf = chunks consumed so far by this warp (the backward / forward
+// rings keep running across tiles and calls).
+template <class M, bool PX, bool JC, int TC, int NST>
+__device__ __forceinline__ void ff_tma_tile(const Dev &d, double *smem_fft, const int tile, const int lane, unsigned &gb,
+                                            unsigned &gf, double *cst = nullptr) {
+  using S = FfTmaShape<M, PX, JC, TC, NST>;
+  constexpr int n = S::n, m = S::m, nt = S::nt, NJ = S::NJ;
+  constexpr bool XB = S::XB;
+  constexpr int oJ = S::oJ, oX = S::oX, oU = S::oU, oQx = S::oQx, oQu = S::oQu, oQi = S::oQi, oRu = S::oRu, oRx = S::oRx,
+                SB = S::SB;
+  constexpr int fK = S::fK, fk = S::fk, fU = S::fU, fRu = S::fRu, fJ = S::fJ, SF = S::SF, NSTF = S::NSTF;
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_fft);     // [NST] backward, [8] forward
+  double *ring = smem_fft + 16;
+  double *s_rhu = cst ? cst : ring + (size_t)NST * TC * SB * TILE;    // plan constants of all steps
+  const int N = d.N;
+  double *s_rhx = s_rhu + (size_t)N * m;
+  int *s_qnz = reinterpret_cast<int *>(s_rhx + (PX ? (size_t)N * n : 0));
+  int *s_seq = s_qnz + N;
+  {
   TileCtx<M> c(d, tile, lane);
   const bool live = !(d.odone[c.b] || d.adone[c.b]);
-  if (!__any_sync(0xffffffffu, live)) continue;
+  if (!__any_sync(0xffffffffu, live)) return;
   const double *xh = c.at(d.xh, d, n);
   const double *zs = d.zs + (size_t)tile * d.n_via * n * TILE + c.lane;
   double *kk = c.at(d.kk, d, m), *du = c.at(d.du, d, m);
@@ -1122,6 +1150,11 @@ __global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
                *t_Qi = d.Qui + tb * nt, *t_ru = d.rgu + tb * m, *t_rx = PX ? d.rgx + tb * n : nullptr,
                *t_K = d.Kg + tb * (m * n), *t_kk = d.kk + tb * m, *t_J = JC ? d.Jc + tb * NJ : nullptr;
   const bool pu = d.proj_u != 0;
+  // Rows of x^ the sweeps really need: the Jacobian reads the components >= M::JX0 only (car: theta, v), the quadratic
+  // state cost reads all of them but only at via-point steps (plain loads there).  Without a state projection the rows
+  // below JX0 are not staged at all: 44 -> 40 doubles per problem-step for the car.
+  constexpr int JX0 = (!PX && !JC) ? M::JX0 : 0;
+  const int xb0 = (JX0 > 0 && d.cost_kind == ISLS_COST_QUADRATIC) ? JX0 : 0;   // first staged row, backward sweep
   constexpr unsigned ROWB = TILE * sizeof(double);        // bytes of one component row of a step
   auto copy = [&](double *stage, int off, const double *src, int D, int t_lo, int cnt, unsigned long long *b) {
     bulk_g2s(stage + (size_t)off * TC * TILE, src + (size_t)t_lo * D * TILE, (unsigned)(cnt * D) * ROWB, b);
@@ -1131,10 +1164,16 @@ __global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
   auto issue_b = [&](int ch) {                            // lane 0 only
     const int st = (int)((gb + ch) % NST), t_hi = N - 2 - ch * TC, t_lo = max(0, t_hi - TC + 1), cnt = t_hi - t_lo + 1;
     double *sb = ring + (size_t)st * TC * SB * TILE;
-    const int rows = (JC ? NJ : 0) + (XB ? n : 0) + m + m * n + 2 * nt + (pu ? m : 0) + (PX ? n : 0);
+    const int rows = (JC ? NJ : 0) + (XB ? n - xb0 : 0) + m + m * n + 2 * nt + (pu ? m : 0) + (PX ? n : 0);
     mbar_expect_tx(&bar[st], (unsigned)(cnt * rows) * ROWB);
     if (JC) copy(sb, oJ, t_J, NJ, t_lo, cnt, &bar[st]);
-    if (XB) copy(sb, oX, t_xh, n, t_lo, cnt, &bar[st]);
+    if (XB) {
+      if (xb0 == 0) copy(sb, oX, t_xh, n, t_lo, cnt, &bar[st]);
+      else
+        for (int tt = 0; tt < cnt; tt++)                    // rows xb0 .. n-1 of every step
+          bulk_g2s(sb + ((size_t)oX * TC + tt * n + xb0) * TILE, t_xh + ((size_t)(t_lo + tt) * n + xb0) * TILE,
+                   (unsigned)(n - xb0) * ROWB, &bar[st]);
+    }
     copy(sb, oU, t_uh, m, t_lo, cnt, &bar[st]);
     copy(sb, oQx, t_Qx, m * n, t_lo, cnt, &bar[st]);
     copy(sb, oQu, t_Qu, nt, t_lo, cnt, &bar[st]);
@@ -1202,7 +1241,7 @@ __global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
       const int qz = s_qnz[t], sq = s_seq[t];
 #pragma unroll
       for (int i = 0; i < n; i++) {
-        if (XB) x[i] = sb[(size_t)(oX * TC + tt * n + i) * TILE];
+        if (XB) x[i] = i >= xb0 ? sb[(size_t)(oX * TC + tt * n + i) * TILE] : (qz ? EL(xh, n, t, i) : 0.0);
         else x[i] = (need_x_glob && qz) ? EL(xh, n, t, i) : 0.0;
         rx[i] = PX ? sb[(size_t)(oRx * TC + tt * n + i) * TILE] : 0.0;
       }
@@ -1248,14 +1287,18 @@ __global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
   auto issue_f = [&](int ch) {                            // lane 0 only
     const int st = (int)((gf + ch) % NSTF), t_lo = ch * TC, cnt = min(TC, N - t_lo);
     double *sf = ring + (size_t)st * TC * SF * TILE;
-    const int rows = m * n + m + m + (pu ? m : 0) + (JC ? NJ : n);
+    const int rows = m * n + m + m + (pu ? m : 0) + (JC ? NJ : n - JX0);
     mbar_expect_tx(&barf[st], (unsigned)(cnt * rows) * ROWB);
     copy(sf, fK, t_K, m * n, t_lo, cnt, &barf[st]);
     copy(sf, fk, t_kk, m, t_lo, cnt, &barf[st]);
     copy(sf, fU, t_uh, m, t_lo, cnt, &barf[st]);
     if (pu) copy(sf, fRu, t_ru, m, t_lo, cnt, &barf[st]);
     if (JC) copy(sf, fJ, t_J, NJ, t_lo, cnt, &barf[st]);
-    else copy(sf, fJ, t_xh, n, t_lo, cnt, &barf[st]);
+    else if (JX0 == 0) copy(sf, fJ, t_xh, n, t_lo, cnt, &barf[st]);
+    else
+      for (int tt = 0; tt < cnt; tt++)
+        bulk_g2s(sf + ((size_t)fJ * TC + tt * n + JX0) * TILE, t_xh + ((size_t)(t_lo + tt) * n + JX0) * TILE,
+                 (unsigned)(n - JX0) * ROWB, &barf[st]);
   };
   if (lane == 0) {
 #pragma unroll
@@ -1309,7 +1352,7 @@ __global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
         } else {
           double x[n];
 #pragma unroll
-          for (int i = 0; i < n; i++) x[i] = sf[(size_t)(fJ * TC + tt * n + i) * TILE];
+          for (int i = 0; i < n; i++) x[i] = i >= JX0 ? sf[(size_t)(fJ * TC + tt * n + i) * TILE] : 0.0;   // jac reads rows >= JX0
           M::jac(x, u, J, d.dt);
         }
         M::expand(J, A, Bm, d.dt);
@@ -1336,6 +1379,19 @@ __global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
   gf += (unsigned)nchf;
   __syncwarp();                 // the ring is re-used by the next tile's backward sweep
   }
+}
+
+template <class M, bool PX, bool JC, int TC, int NST>
+__global__ void __launch_bounds__(TILE) k_ff_tma(Dev d) {
+  extern __shared__ __align__(128) double smem_fft[];
+  const int lane = threadIdx.x;
+  const int ntiles = (d.tile1 - d.tile0 + d.tstep - 1) / d.tstep;
+  if ((int)blockIdx.x >= ntiles) return;
+  ff_tma_setup<M, PX, JC, TC, NST>(d, smem_fft, lane);
+  unsigned gb = 0, gf = 0;
+  // persistent over tiles (grid = tiles for the small-batch launches, fewer CTAs in the overlapped schedule)
+  for (int it = blockIdx.x; it < ntiles; it += gridDim.x)
+    ff_tma_tile<M, PX, JC, TC, NST>(d, smem_fft, d.tile0 + it * d.tstep, lane, gb, gf);
 }
 
 // ---- Warp-split form of k_ff_tma for models with larger state (arm: n = 9, m = 3) at small batches: G warps share one
@@ -1675,7 +1731,7 @@ __global__ void __launch_bounds__(TILE * G, 4) k_ff_ws(Dev d) {
 // whose problem is finished compute on stale data and are masked at the writes.
 // One tile's line search; returns the number of staged chunks it consumed (the mbarrier ring keeps running across the
 // tiles of a persistent CTA: `gch` = chunks consumed so far by this CTA, `init_bars` = first tile of the CTA).
-template <class M, int CPT, int MAXW, bool PX>
+template <class M, int CPT, int MAXW, bool PX, int TCMAX = 10>
 __device__ __forceinline__ int ls_tile(const Dev &d, const int tile, int fuse, int outer, int inner, const unsigned gch,
                                        const bool init_bars) {
   constexpr int n = M::n, m = M::m;
@@ -1683,7 +1739,7 @@ __device__ __forceinline__ int ls_tile(const Dev &d, const int tile, int fuse, i
   constexpr int ROWS = 2 * m + (PX ? n : 0);                  // staged doubles per lane and step
   constexpr int STAGE_BYTES = LMAX > 32 ? 4096 : 12288;       // keeps the static shared memory under 48 KB
   constexpr int TC_ = STAGE_BYTES / (ROWS * TILE * 8);        // steps per chunk
-  constexpr int TC = TC_ > 10 ? 10 : (TC_ < 1 ? 1 : TC_);
+  constexpr int TC = TC_ > TCMAX ? TCMAX : (TC_ < 1 ? 1 : TC_);
   constexpr int NST = 2;                                      // chunks in flight
   __shared__ __align__(128) double su[NST][TC][m][TILE];      // u^
   __shared__ __align__(128) double sd[NST][TC][m][TILE];      // du
@@ -1922,6 +1978,71 @@ __global__ void __launch_bounds__(TILE * MAXW, MINB) k_linesearch_pers(Dev d, in
     gch += (unsigned)ls_tile<M, CPT, MAXW, PX>(d, d.tile0 + i * d.tstep, fuse, outer, inner, gch, gch == 0);
   }
   if (t0 && atomicAdd(&ctr[1], 1) == (int)gridDim.x - 1) { ctr[0] = 0; ctr[1] = 0; }
+}
+
+// ---- The whole inner ADMM loop in ONE launch (control-only projections, large batches).  A persistent CTA owns the
+// tiles blockIdx.x, blockIdx.x + gridDim.x, ... for all ADMM iterations of an outer iteration (nothing couples tiles
+// inside one: admm.py:31-97 runs per problem).  Per ADMM iteration and round of up to W tiles: every warp runs the
+// TMA-staged ff-pass + linear rollout of ONE tile (ff_tma_tile, private operand ring: HBM-bound, W x 3 streaming warps
+// per SM like the stand-alone k_ff_tma), then the whole CTA runs the line search + streaming ADMM update of these tiles
+// one after the other (ls_tile: FP64-bound).  The CTAs of an SM drift apart in phase, so the HBM-bound half of one
+// overlaps the FP64-bound half of its neighbours - which two separate kernels never did: the line search needs the
+// whole register file for its residency (profiles/r2_tuning_log.md).  Same device functions, same arithmetic, same order
+// per problem as the k_ff_tma / k_linesearch launch pair: results are bit-identical.  `stagger`: the s-th CTA to arrive on
+// an SM (per-SM counter) sleeps s x stagger ns once, so the first wave does not start in lock-step.
+template <class M, int CPT, int MAXW, int MINB, bool JC, int TC, int NST>
+__global__ void __launch_bounds__(TILE * MAXW, MINB) k_admm_loop(Dev d, int outer, int a0, int a1, unsigned stagger,
+                                                                  int *sm_ctr) {
+  using FS = FfTmaShape<M, false, JC, TC, NST>;
+  extern __shared__ __align__(128) double smem_fft[];
+  const int w = threadIdx.y, lane = threadIdx.x, W = blockDim.y;
+  constexpr size_t RSTRIDE = (128 + FS::RING_BYTES) / sizeof(double);     // per-warp mbarriers + ring
+  double *my = smem_fft + (size_t)w * RSTRIDE;
+  double *cst = smem_fft + (size_t)W * RSTRIDE;                            // one copy of the plan constants
+  ff_tma_setup<M, false, JC, TC, NST>(d, my, lane, cst, w == 0);
+  if (stagger && w == 0) {
+    unsigned slot = 0;
+    if (lane == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      slot = (unsigned)atomicAdd(&sm_ctr[smid & 255], 1);
+    }
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot < 3 && slot > 0) {                       // first wave only
+      for (unsigned left = stagger * slot; left > 0;) {
+        const unsigned q = left > 100000u ? 100000u : left;
+        __nanosleep(q);
+        left -= q;
+      }
+    }
+  }
+  __syncthreads();
+  const int ntiles = (d.tile1 - d.tile0 + d.tstep - 1) / d.tstep, G = gridDim.x;
+  const int mine = (ntiles - (int)blockIdx.x + G - 1) / G;              // tiles of this CTA
+  const int rounds = (mine + W - 1) / W;
+  auto tile_of = [&](int k) { return d.tile0 + ((int)blockIdx.x + k * G) * d.tstep; };
+  unsigned gb = 0, gf = 0, gch = 0;
+  for (int a = a0; a < a1; a++) {
+    bool any = false;
+    int k0 = 0;
+    for (int r = 0; r < rounds; r++) {
+      const int cnt = mine / rounds + (r < mine % rounds ? 1 : 0);      // rounds of (nearly) equal size
+      if (w < cnt) {
+        ff_tma_tile<M, false, JC, TC, NST>(d, my, tile_of(k0 + w), lane, gb, gf, cst);
+        fence_proxy_async();      // du: generic-proxy stores of this warp, read by the line search's bulk copies
+      }
+      __syncthreads();
+      for (int q = 0; q < cnt; q++) {
+        const int used = ls_tile<M, CPT, MAXW, false, 5>(d, tile_of(k0 + q), 1, outer, a, gch, gch == 0);
+        gch += (unsigned)used;
+        any |= used != 0;
+        fence_proxy_async();      // reg_u: generic-proxy stores of the epilogue, read by the next ff-pass's bulk copies
+        __syncthreads();          // (also: the tile's shared state is dead)
+      }
+      k0 += cnt;
+    }
+    if (!any) break;              // every problem of this CTA has left the ADMM loop (uniform over the CTA)
+  }
 }
 
 // ---- state projection onto the outside of obstacle sets: project_set_convex (isls/projections.py:289-374) with
@@ -3608,7 +3729,9 @@ static inline int ensure_dyn_smem(int bytes) {
   const unsigned long long bit = 1ull << (dev & 63);
   (void)bytes;                                 // opt in to the architectural maximum once: later launches of the same
   if (!(done & bit)) {                         // kernel may ask for more (the plan-constant block grows with N)
-    CK(cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cudaFuncAttributes fa;                     // static + dynamic shared memory share the 227 KB of a CTA
+    CK(cudaFuncGetAttributes(&fa, Kern));
+    CK(cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));
     done |= bit;
   }
   return 0;
@@ -3933,7 +4056,51 @@ struct ModelImpl {
       LAUNCH(ISLS_KC_INIT, cs, (k_init<M><<<tp_grid(dc), tp_block(), 0, cs>>>(dc, x0, u_init, zs)));
       for (int j = 0; j < d.max_outer; j++) {
         LAUNCH(ISLS_KC_KPASS, cs, launch_kpass<M>(dc, cs));
-        for (int a = 0; a < d.max_admm; a++) {
+        bool looped = false;
+        if constexpr (M::n < 9) {
+          // experimental, off by default (measured slower, profiles/r2_tuning_log.md section 5): the whole inner loop of
+          // an outer iteration in one launch of persistent CTAs (k_admm_loop)
+          static const int loop_mode = ovl_env("ISLS_ADMM_LOOP", 0);        // 0 off, 1 batches >= 1,536 tiles, 2 any size
+          static const int loop_split = ovl_env("ISLS_ADMM_LOOP_SPLIT", 0); // 1: one launch per ADMM iteration
+          static const int loop_stag = ovl_env("ISLS_ADMM_LOOP_STAGGER", 0);   // ns per arrival slot (first wave)
+          static const int loop_grid = ovl_env("ISLS_ADMM_LOOP_GRID", 0);   // 0 auto (resident CTAs), else CTAs
+          const bool ok = !d.proj_x && d.proj_u && !no_fused_update() && d.L <= 20 && d.cost_kind == ISLS_COST_QUADRATIC &&
+                          (loop_mode == 2 || (loop_mode == 1 && n_tiles(dc) >= 1536));
+          if (ok) {
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const int tiles = n_tiles(dc);
+            auto go = [&](auto jc, auto tc, auto nst) -> int {
+              constexpr bool JC_ = decltype(jc)::value;
+              constexpr int TC_ = decltype(tc)::value, NST_ = decltype(nst)::value;
+              using FS = FfTmaShape<M, false, JC_, TC_, NST_>;
+              constexpr auto kern = k_admm_loop<M, 5, 4, 3, JC_, TC_, NST_>;
+              const int W = (d.L + 4) / 5;
+              // W private operand rings + one copy of the plan constants (+ 23 KB of static line-search staging)
+              const size_t smem = (size_t)W * (128 + FS::RING_BYTES) + (FS::smem_bytes(d.N) - 128 - FS::RING_BYTES);
+              const long long per_sm = std::min<long long>(3, (227 * 1024) / (long long)(smem + 24 * 1024));
+              if (per_sm < 1) return 0;
+              const int grid = (int)std::min<long long>(tiles, loop_grid > 0 ? loop_grid : per_sm * sms);   // persistent
+              if (ensure_dyn_smem<kern>((int)smem)) return 1;
+              int *sm_ctr = dc.nact + 64;
+              if (loop_stag) CK(cudaMemsetAsync(sm_ctr, 0, 256 * sizeof(int), cs));
+              const dim3 blk(TILE, W);
+              if (loop_split) {
+                for (int a = 0; a < d.max_admm; a++)
+                  LAUNCH(ISLS_KC_ADMM_LOOP, cs, (kern<<<grid, blk, smem, cs>>>(dc, j, a, a + 1, (unsigned)loop_stag, sm_ctr)));
+              } else {
+                LAUNCH(ISLS_KC_ADMM_LOOP, cs, (kern<<<grid, blk, smem, cs>>>(dc, j, 0, d.max_admm, (unsigned)loop_stag, sm_ctr)));
+              }
+              looped = true;
+              return 0;
+            };
+            using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
+            // small batches carry the Jacobian cache of k_kpass<., SMALL>
+            if (dc.Jc ? go(std::true_type{}, I2{}, I2{}) : go(std::false_type{}, I1{}, I2{})) return 1;
+          }
+        }
+        for (int a = 0; a < d.max_admm && !looped; a++) {
           const int fuse = (!d.proj_x && d.proj_u && !no_fused_update()) ? 1 : 0;      // streaming ADMM epilogue
           LAUNCH(ISLS_KC_FF, cs, launch_ff<M>(dc, cs));
           LAUNCH(ISLS_KC_LINESEARCH, cs, launch_linesearch<M>(dc, false, cs, LsFuse{fuse, j, a}));

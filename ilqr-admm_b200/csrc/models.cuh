@@ -180,6 +180,7 @@ __device__ __forceinline__ double mod_two_pi_fast(double a, bool &bad) {
 
 struct CarModel {
   static constexpr int n = 4, m = 2, NJ = 6, NJA = 6;
+  static constexpr int JX0 = 2;   // jac() reads the state components >= JX0 only
   __host__ __device__ static constexpr int am(int i, int j) {
     return i == j ? MO : ((i <= 1 && j >= 2) || (i == 2 && j == 3)) ? MV : MZ;
   }
@@ -248,6 +249,7 @@ struct CarModel {
 //   d(do)/dw = f cos w / S.
 struct TassaCarModel {
   static constexpr int n = 4, m = 2, NJ = 8, NJA = 8;
+  static constexpr int JX0 = 2;   // jac() reads the state components >= JX0 only
   static constexpr double DIST = 2.0;
   __host__ __device__ static constexpr int am(int i, int j) {
     return i == j ? MO : ((i <= 1 && j >= 2) || (i == 2 && j == 3)) ? MV : MZ;
@@ -309,6 +311,7 @@ struct TassaCarModel {
 
 struct Arm3Model {
   static constexpr int n = 9, m = 3, NJ = 6, NJA = 6;
+  static constexpr int JX0 = 0;   // jac() reads the state components >= JX0 only
   __host__ __device__ static constexpr int am(int i, int j) {
     return i < 6 ? (i == j ? MO : (i < 3 && j == i + 3) ? MV : MZ)
                  : (i < 8 && j < 6) ? MV : MZ;           // rows 6,7 = [J, J dt, 0]; row 8 (p_z) is zero
@@ -387,6 +390,7 @@ struct Arm3Model {
 template <int D>
 struct DoubleIntModel {
   static constexpr int n = 2 * D, m = D, NJ = 0, NJA = 1;
+  static constexpr int JX0 = 0;   // jac() reads the state components >= JX0 only
   __host__ __device__ static constexpr int am(int i, int j) { return i == j ? MO : (i < D && j == i + D) ? MV : MZ; }
   __host__ __device__ static constexpr int bm(int i, int j) {
     return (i < D && j == i) ? MV : (i >= D && j == i - D) ? MV : MZ;
@@ -430,6 +434,7 @@ static __constant__ LtiConst c_lti;
 template <int N_, int M_>
 struct LtiModel {
   static constexpr int n = N_, m = M_, NJ = 0, NJA = 1;
+  static constexpr int JX0 = 0;   // jac() reads the state components >= JX0 only
   __host__ __device__ static constexpr int am(int, int) { return MV; }
   __host__ __device__ static constexpr int bm(int, int) { return MV; }
   __device__ __forceinline__ static void step(const double (&x)[n], const double (&u)[m], double (&xn)[n], double) {

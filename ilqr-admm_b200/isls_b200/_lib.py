@@ -85,7 +85,7 @@ EXPORTS = ["isls_version", "isls_last_error_string", "isls_model_id", "isls_mode
            "isls_controller_tv_workspace_bytes", "isls_controller_tv_f64", "isls_linearize_f64"]
 
 KERNEL_CLASSES = ["init", "kpass", "ff", "linesearch", "admm", "outer_end", "finalize", "backward_full", "accept",
-                  "lqt", "compact", "isls_cols", "isls_update"]
+                  "lqt", "compact", "isls_cols", "isls_update", "admm_loop"]
 
 _lib = None
 

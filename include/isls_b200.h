@@ -409,7 +409,8 @@ int isls_project_set_convex_f64(const isls_proj_set_params *params, int64_t rows
 #define ISLS_KC_COMPACT 10
 #define ISLS_KC_ISLS_COLS 11
 #define ISLS_KC_ISLS_UPDATE 12
-#define ISLS_KC_COUNT 13
+#define ISLS_KC_ADMM_LOOP 13
+#define ISLS_KC_COUNT 14
 /* thread-local switch: when on, every kernel launch of a solve is bracketed by a CUDA event pair on the
  * launching stream (adds a few microseconds per launch; use for per-kernel durations, not for throughput) */
 int isls_profile_enable(int on);

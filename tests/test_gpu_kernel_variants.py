@@ -32,9 +32,11 @@ def test_staged_and_plain_kernels_agree_bitwise(tmp_path):
     tma_nojc = _run(tmp_path, "tma_nojc", {"ISLS_FF_MODE": "2", "ISLS_FF_JC": "0"})    # k_ff_tma recomputing the Jacobian
     staged = _run(tmp_path, "staged", {"ISLS_FF_MODE": "0"})                           # round-1 rule: cp.async staging
     ovl = _run(tmp_path, "overlap", {"ISLS_OVERLAP": "1"})        # two-stream overlapped schedule forced at this size
+    loop = _run(tmp_path, "loop", {"ISLS_ADMM_LOOP": "2"})        # whole inner ADMM loop in one persistent launch (k_admm_loop)
     assert set(auto.files) == set(plain.files)
     for k in auto.files:
         for other, nm in ((plain, "plain"), (deep2, "ff depth 2"), (tma_nojc, "TMA ff without the Jacobian cache"),
-                          (staged, "cp.async-staged ff"), (ovl, "overlapped schedule")):
+                          (staged, "cp.async-staged ff"), (ovl, "overlapped schedule"),
+                          (loop, "inner loop in one launch")):
             assert np.array_equal(auto[k], other[k], equal_nan=True), "%s differs between auto and %s" % (k, nm)
     assert auto["arm_n_log"].min() >= 1 and np.isfinite(auto["park_cost"]).all()

@@ -36,7 +36,7 @@ def run(B, model="car", reps=3):
     S.profile_enable(False)
     return dict(model=model, B=B, ms=round(ms, 3), solves_per_s=round(B / ms * 1e3),
                 us_per_launch={k: round(1e3 * v[0] / v[1], 1) for k, v in prof.items()},
-                cost_mean=float(sv.out.cost.mean()))
+                cost_mean=float(sv.out.cost.mean()), u_sum=float(sv.out.u.double().sum()))
 
 
 if __name__ == "__main__":

@@ -10,11 +10,13 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
-    "plain": {"ISLS_FF_STAGES": "0", "ISLS_ADMM_STAGES": "0", "ISLS_COLS_STAGES": "0", "ISLS_LQT_SMEM": "0", "ISLS_OVERLAP": "0", "ISLS_SLS_CTRL_DENSE": "1"},
+    "plain": {"ISLS_FF_STAGES": "0", "ISLS_ADMM_STAGES": "0", "ISLS_COLS_STAGES": "0", "ISLS_LQT_SMEM": "0", "ISLS_OVERLAP": "0", "ISLS_SLS_CTRL_DENSE": "1", "ISLS_ADMM_LOOP": "0"},
     "auto": {},
     "tma_nojc": {"ISLS_FF_MODE": "2", "ISLS_FF_JC": "0"},
     "staged": {"ISLS_FF_MODE": "0"},
     "overlap": {"ISLS_OVERLAP": "1"},
+    "loop": {"ISLS_ADMM_LOOP": "2"},
+    "loop_split": {"ISLS_ADMM_LOOP": "2", "ISLS_ADMM_LOOP_SPLIT": "1"},
 }
 td = tempfile.mkdtemp()
 res = {}
