@@ -727,8 +727,8 @@ size_t isls_carve(const isls_plan *p, long long B, char *base, Dev *d, Dev *alt)
   takeD(d ? &d->zs : nullptr, T * p->n_via * n * TILE);
   takeD(d ? &d->lsc : nullptr, T * p->L * TILE);
   // Jacobian cache of the small-batch feed-forward kernels (k_ff_tma); large batches recompute (HBM-bound there)
-  takeD(d ? &d->Jc : nullptr, T < 1536 ? T * N * (size_t)p->NJA * TILE : 0);
-  if (d && T >= 1536) d->Jc = nullptr;
+  takeD(d ? &d->Jc : nullptr, T < (size_t)isls_small_tiles() ? T * N * (size_t)p->NJA * TILE : 0);
+  if (d && T >= (size_t)isls_small_tiles()) d->Jc = nullptr;
   takeD(d ? &d->obw : nullptr, p->desc.n_obst > 0 ? (2 + (p->desc.obst_kind == 1 ? 2 * (size_t)p->desc.n_obst : 0)) * tn : 0);
   const size_t tC = p->desc.isls_dim > 0 ? tm * (size_t)(p->desc.isls_dim + 1) : 0;
   takeD(d ? &d->Zm : nullptr, tC); takeD(d ? &d->Lm : nullptr, tC); takeD(d ? &d->Xu : nullptr, tC);

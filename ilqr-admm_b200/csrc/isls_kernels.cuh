@@ -56,6 +56,14 @@ struct ProfScope {
 };
 #define LAUNCH(kc, stream, ...) do { ProfScope ps__(kc, stream); __VA_ARGS__; } while (0)
 
+// Batches below this many tiles (less than one warp per SM scheduler and wave) take the latency-oriented kernel forms:
+// Jacobian cache, deep operand rings, plan constants one step ahead.  ISLS_SMALL_TILES overrides (tuning).
+static inline int isls_small_tiles() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("ISLS_SMALL_TILES"); v = e ? atoi(e) : 1536; }
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------------ device context
 struct Dev {
   int N, n_via, L, proj_x, proj_u, T;
@@ -3824,12 +3832,18 @@ static int launch_ff(const Dev &d, cudaStream_t s) {
     ff_jc = j ? atoi(j) : 1;
   }
   static const int ff_big = ovl_env("ISLS_FF_BIG", 22);   // >= 1,536 tiles: 0 plain k_ff, 22 / 13 / 12: k_ff_tma<TC, NST>
-  if (mode < 0 && ff_mode < 0 && tiles >= 1536 && ff_big > 0) {
+  int dev_ = 0, sms_ = 148;
+  cudaGetDevice(&dev_);
+  cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev_);
+  // Mid-size batches (512 < tiles <= one wave of the shallow-ring form, 8 single-warp CTAs per SM) are bandwidth-bound
+  // already: the shallow-ring form without the Jacobian cache moves fewer bytes than the deep-ring form with it (car,
+  // 32,768 problems: 178 vs 209 us per launch; at 1,280 tiles - two waves - it loses, 291 vs 253 us; at 512 tiles they tie)
+  static const int ff_mid = ovl_env("ISLS_FF_MID", 1);
+  const bool mid = ff_mid && M::n < 6 && tiles > 512 && tiles <= 8 * sms_;
+  if (mode < 0 && ff_mode < 0 && (tiles >= isls_small_tiles() || mid) && ff_big > 0) {
     // large batches: the TMA-staged kernel also beats the plain one when HBM-bound (65,536 car problems: 0.356 vs
     // 0.389 ms; shallow rings = more resident single-warp CTAs per SM; profiles/r2_tuning_log.md), Jacobian recomputed
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sms_;
     bool done = false;
     auto big = [&](auto px) -> int {
       constexpr bool PX_ = decltype(px)::value;
@@ -3840,7 +3854,7 @@ static int launch_ff(const Dev &d, cudaStream_t s) {
     if (d.proj_x ? big(std::true_type{}) : big(std::false_type{})) return 1;
     if (done) return 0;
   }
-  if (mode < 0 && (ff_mode == 2 || (ff_mode < 0 && tiles < 1536))) {
+  if (mode < 0 && (ff_mode == 2 || (ff_mode < 0 && tiles < isls_small_tiles()))) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
 {
-python tools/bench_small.py 65536 || exit 1
-python tools/bench_small.py 8192 32768
-} > gpurun_out/xpart_bench.txt 2>&1
-python tools/variant_diff.py > gpurun_out/xpart_variants.txt 2>&1
+echo "== default"; python tools/bench_small.py 14336 16384 18944 24576 32768 || exit 1
+echo "== ISLS_LS_CPT=54"; ISLS_LS_CPT=54 python tools/bench_small.py 8192 14336 16384 18944 24576
+} > gpurun_out/ls54.txt 2>&1
