@@ -2,7 +2,7 @@ import sys, time
 sys.path[:0]=["/root/repo","/root/repo/ilqr-admm_b200","/root/repo/tests"]
 import torch, numpy as np
 from isls_b200 import Bound, SLS, configs, get_double_integrator_AB, solver as S
-for B in (1024, 32, 1024):
+for B in (1, 32, 1024):
     p = configs.di_batch(B)
     s = SLS(4, 2, p["N"], batch=B)
     s.AB = get_double_integrator_AB(2, 2, p["dt"])
