@@ -316,6 +316,25 @@ def test_batch_composition_invariance_and_ragged():
             assert np.array_equal(sub[k], full[k][idx], equal_nan=True), k
 
 
+def test_kernel_selection_regimes_agree_bitwise():
+    """The launch rules pick other kernel forms by batch size (csrc/isls_kernels.cuh, launch_ff / launch_kpass): below
+    513 tiles the deep-ring ff-pass with the Jacobian cache, from 513 to 1,184 tiles the shallow-ring form next to the
+    small-batch K-pass, from 1,536 tiles the large-batch forms.  The same 96 problems embedded in a 96-, a 20,000- and a
+    50,000-problem batch must come out bit for bit the same (the strong-scaling shards of one job take all three)."""
+    I_o, I_a = 2, 3
+    big = P.car_batch(50000, I_o=I_o, I_a=I_a, L=20)
+    idx = np.random.default_rng(5).choice(20000, 96, replace=False)
+    outs = []
+    for B in (50000, 20000):
+        o = _gpu().run_ilqr_admm(P.subset(big, np.arange(B)), fixed_budget=True, want_masks=False)
+        outs.append({k: o[k][idx] for k in ("x", "u", "cost_log", "z_u")})
+    o = _gpu().run_ilqr_admm(P.subset(big, idx), fixed_budget=True, want_masks=False)
+    outs.append({k: o[k] for k in ("x", "u", "cost_log", "z_u")})
+    for other in outs[1:]:
+        for k in outs[0]:
+            assert np.array_equal(outs[0][k], other[k], equal_nan=True), k
+
+
 def test_full_size_properties():
     """BASELINE size (car, N=100, B=65,536), fixed budget: size-independent properties - determinism across
     runs, agreement of a random subsample with the oracle, feasibility of z, cost_log consistent with cost."""
