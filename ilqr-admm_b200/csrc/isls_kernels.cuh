@@ -3835,11 +3835,14 @@ static int launch_ff(const Dev &d, cudaStream_t s) {
   int dev_ = 0, sms_ = 148;
   cudaGetDevice(&dev_);
   cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev_);
-  // Mid-size batches (512 < tiles <= one wave of the shallow-ring form, 8 single-warp CTAs per SM) are bandwidth-bound
+  // Mid-size batches (512 < tiles <= one wave of the shallow-ring form: 8 single-warp CTAs per SM at N = 100) are bandwidth-bound
   // already: the shallow-ring form without the Jacobian cache moves fewer bytes than the deep-ring form with it (car,
   // 32,768 problems: 178 vs 209 us per launch; at 1,280 tiles - two waves - it loses, 291 vs 253 us; at 512 tiles they tie)
   static const int ff_mid = ovl_env("ISLS_FF_MID", 1);
-  const bool mid = ff_mid && M::n < 6 && tiles > 512 && tiles <= 8 * sms_;
+  const size_t smem22 = d.proj_x ? FfTmaShape<M, true, false, 2, 2>::smem_bytes(d.N)
+                                 : FfTmaShape<M, false, false, 2, 2>::smem_bytes(d.N);
+  const long long wave22 = (long long)sms_ * std::min<long long>(32, (227 * 1024) / (long long)(smem22 + 1024));
+  const bool mid = ff_mid && M::n < 6 && tiles > 512 && tiles <= wave22;
   if (mode < 0 && ff_mode < 0 && (tiles >= isls_small_tiles() || mid) && ff_big > 0) {
     // large batches: the TMA-staged kernel also beats the plain one when HBM-bound (65,536 car problems: 0.356 vs
     // 0.389 ms; shallow rings = more resident single-warp CTAs per SM; profiles/r2_tuning_log.md), Jacobian recomputed
