@@ -1913,21 +1913,24 @@ __device__ __forceinline__ int ls_tile(const Dev &d, const int tile, int fuse, i
     double *zu = c.at(d.zu, d, m), *lu = c.at(d.lu, d, m), *rgu = c.at(d.rgu, d, m);
     const double al = d.alphas[sbest[c.lane]];
     int8_t *mku = (d.out.mask_u && c.valid) ? d.out.mask_u + c.ob * d.N * m : nullptr;
-    constexpr int UB = 7;                       // time steps in flight per thread (all loads issued before use)
+    // UB time steps in flight per thread.  The load phase is branch-free (t clamped to N-1, only the stores are
+    // predicated) and holds the raw operands: with the guards and u = u^ + alpha du inside it, ptxas emitted UB separate
+    // load-then-use blocks, i.e. UB serialised memory round trips per batch (28 per tile at N = 100: a fifth of all stall
+    // samples at 8,192 problems, profiles/r2_tuning_log.md section 8).
+    constexpr int UB = 4;
     for (int t0 = w; t0 < d.N; t0 += W * UB) {
-      double uv[UB][m], zv[UB][m], lv[UB][m], lo[UB][m], hi[UB][m];
+      double dv[UB][m], hv[UB][m], zv[UB][m], lv[UB][m], lo[UB][m], hi[UB][m];
 #pragma unroll
       for (int q = 0; q < UB; q++) {
-        const int t = t0 + q * W;
-        if (t < d.N) {
+        const int t = min(t0 + q * W, d.N - 1);
 #pragma unroll
-          for (int j = 0; j < m; j++) {
-            uv[q][j] = fma(al, EL(du, m, t, j), EL(uh, m, t, j));        // identical to the candidate's u
-            zv[q][j] = EL(zu, m, t, j);
-            lv[q][j] = EL(lu, m, t, j);
-            lo[q][j] = d.lo_u[t * m + j];
-            hi[q][j] = d.hi_u[t * m + j];
-          }
+        for (int j = 0; j < m; j++) {
+          dv[q][j] = EL(du, m, t, j);
+          hv[q][j] = EL(uh, m, t, j);
+          zv[q][j] = EL(zu, m, t, j);
+          lv[q][j] = EL(lu, m, t, j);
+          lo[q][j] = d.lo_u[t * m + j];
+          hi[q][j] = d.hi_u[t * m + j];
         }
       }
 #pragma unroll
@@ -1937,7 +1940,8 @@ __device__ __forceinline__ int ls_tile(const Dev &d, const int tile, int fuse, i
 #pragma unroll
           for (int j = 0; j < m; j++) {
             int mk;
-            admm_elem(uv[q][j], d.relax, lo[q][j], hi[q][j], zv[q][j], lv[q][j], pru, dru, mk);
+            const double uv = fma(al, dv[q][j], hv[q][j]);                // identical to the candidate's u
+            admm_elem(uv, d.relax, lo[q][j], hi[q][j], zv[q][j], lv[q][j], pru, dru, mk);
             EL(zu, m, t, j) = zv[q][j];
             EL(lu, m, t, j) = lv[q][j];
             EL(rgu, m, t, j) = __dsub_rn(zv[q][j], lv[q][j]);
