@@ -2906,19 +2906,23 @@ __global__ void k_outer_end(Dev d, int outer) {
     double x[n], u[m], xn[n];
 #pragma unroll
     for (int i = 0; i < n; i++) x[i] = EL(xh, n, 0, i);
-    for (int t0 = 0; t0 < d.N; t0 += 4) {          // 4 steps of loads in flight before the first store
-      double uv[4][m];
+    constexpr int UB = 8;                          // steps of loads in flight before the first store
+    for (int t0 = 0; t0 < d.N; t0 += UB) {
+      // branch-free load phase (t clamped, raw operands): the guarded form with the FMA inside compiled to one
+      // load-then-use block per step, i.e. one memory round trip per step (see the line-search epilogue)
+      double dv[UB][m], hv[UB][m];
 #pragma unroll
-      for (int q = 0; q < 4; q++)
+      for (int q = 0; q < UB; q++) {
+        const int t = min(t0 + q, d.N - 1);
 #pragma unroll
-        for (int j = 0; j < m; j++)
-          uv[q][j] = (t0 + q < d.N) ? fma(al, EL(du, m, t0 + q, j), EL(uh, m, t0 + q, j)) : 0.0;
+        for (int j = 0; j < m; j++) { dv[q][j] = EL(du, m, t, j); hv[q][j] = EL(uh, m, t, j); }
+      }
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
+      for (int q = 0; q < UB; q++) {
         const int t = t0 + q;
         if (t < d.N) {
 #pragma unroll
-          for (int j = 0; j < m; j++) { u[j] = uv[q][j]; EL(uh, m, t, j) = u[j]; }
+          for (int j = 0; j < m; j++) { u[j] = fma(al, dv[q][j], hv[q][j]); EL(uh, m, t, j) = u[j]; }
 #pragma unroll
           for (int i = 0; i < n; i++) EL(xh, n, t, i) = x[i];
           M::step(x, u, xn, d.dt);
