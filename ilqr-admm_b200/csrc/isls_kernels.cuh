@@ -1200,7 +1200,8 @@ __device__ __forceinline__ void ff_tma_tile(const Dev &d, double *smem_fft, cons
 #pragma unroll
   for (int j = 0; j < m; j++) { rw[j] = d.Rw[j]; rw2[j] = 2.0 * (d.u_std * rw[j]); }
   auto costgrad = [&](int t, const double (&x)[n], const double (&u)[m], const double (&rx)[n],
-                      const double (&ru)[m], double (&cx)[n], double (&cu)[m], int qz, int sq) {
+                      const double (&ru)[m], double (&cx)[n], double (&cu)[m], int qz, int sq,
+                      const double (&rhx)[PX ? n : 1], const double (&rhu)[m]) {
     if (d.cost_kind == ISLS_COST_QUADRATIC) {
 #pragma unroll
       for (int i = 0; i < n; i++) cx[i] = qz ? ff_cx_quad(d.qd[t * n + i], x[i], EL(zs, n, sq, i)) : 0.0;
@@ -1210,12 +1211,12 @@ __device__ __forceinline__ void ff_tma_tile(const Dev &d, double *smem_fft, cons
     }
     if (PX) {
 #pragma unroll
-      for (int i = 0; i < n; i++) cx[i] = ff_pen(cx[i], s_rhx[t * n + i], x[i], rx[i]);
+      for (int i = 0; i < n; i++) cx[i] = ff_pen(cx[i], rhx[PX ? i : 0], x[i], rx[i]);
     }
 #pragma unroll
     for (int j = 0; j < m; j++) {
       double g = __dmul_rn(rw2[j], u[j]);
-      if (pu) g = ff_pen(g, s_rhu[t * m + j], u[j], ru[j]);
+      if (pu) g = ff_pen(g, rhu[j], u[j], ru[j]);
       cu[j] = g;
     }
   };
@@ -1228,7 +1229,12 @@ __device__ __forceinline__ void ff_tma_tile(const Dev &d, double *smem_fft, cons
       u[j] = t_uh[((size_t)(N - 1) * m + j) * TILE + lane];
       ru[j] = pu ? t_ru[((size_t)(N - 1) * m + j) * TILE + lane] : 0.0;
     }
-    costgrad(N - 1, x, u, rx, ru, cx, cu, s_qnz[N - 1], s_seq[N - 1]);
+    double rhxT[PX ? n : 1], rhuT[m];
+#pragma unroll
+    for (int i = 0; i < (PX ? n : 1); i++) rhxT[i] = PX ? s_rhx[(N - 1) * n + i] : 0.0;
+#pragma unroll
+    for (int j = 0; j < m; j++) rhuT[j] = s_rhu[(N - 1) * m + j];
+    costgrad(N - 1, x, u, rx, ru, cx, cu, s_qnz[N - 1], s_seq[N - 1], rhxT, rhuT);
 #pragma unroll
     for (int i = 0; i < n; i++) v[i] = cx[i];
 #pragma unroll
@@ -1238,6 +1244,20 @@ __device__ __forceinline__ void ff_tma_tile(const Dev &d, double *smem_fft, cons
     }
   }
   const bool need_x_glob = !XB;                           // x^ only where the state cost needs it (via-point steps)
+  // The step's plan constants (rho, qnz, seq: warp-uniform shared-memory loads) are fetched ONE STEP AHEAD into
+  // registers: read at their use inside costgrad each of them cost a uniform-address set-up (S2UR + ULEA) plus the
+  // shared-memory latency right on the c_u -> q_u -> k chain of a lone warp (profiles/r2_tuning_log.md section 9).
+  double rhx_n[PX ? n : 1], rhu_n[m];
+  int qz_n, sq_n;
+  auto fetch_consts = [&](int t) {
+#pragma unroll
+    for (int i = 0; i < (PX ? n : 1); i++) rhx_n[i] = PX ? s_rhx[t * n + i] : 0.0;
+#pragma unroll
+    for (int j = 0; j < m; j++) rhu_n[j] = s_rhu[t * m + j];
+    qz_n = s_qnz[t];
+    sq_n = s_seq[t];
+  };
+  fetch_consts(N >= 2 ? N - 2 : 0);
   for (int ch = 0; ch < nchb; ch++) {
     const int st = (int)((gb + ch) % NST), t_hi = N - 2 - ch * TC, t_lo = max(0, t_hi - TC + 1);
     const double *sb = ring + (size_t)st * TC * SB * TILE + lane;
@@ -1246,7 +1266,13 @@ __device__ __forceinline__ void ff_tma_tile(const Dev &d, double *smem_fft, cons
     for (int t = t_hi; t >= t_lo; t--) {
       const int tt = t - t_lo;
       double x[n], u[m], rx[n], ru[m], J[NJ], cx[n], cu[m], Qux[m][n], Quu[m][m], Qui[m][m], kt[m];
-      const int qz = s_qnz[t], sq = s_seq[t];
+      const int qz = qz_n, sq = sq_n;
+      double rhx_c[PX ? n : 1], rhu_c[m];
+#pragma unroll
+      for (int i = 0; i < (PX ? n : 1); i++) rhx_c[i] = rhx_n[i];
+#pragma unroll
+      for (int j = 0; j < m; j++) rhu_c[j] = rhu_n[j];
+      if (t > 0) fetch_consts(t - 1);
 #pragma unroll
       for (int i = 0; i < n; i++) {
         if (XB) x[i] = i >= xb0 ? sb[(size_t)(oX * TC + tt * n + i) * TILE] : (qz ? EL(xh, n, t, i) : 0.0);
@@ -1275,7 +1301,7 @@ __device__ __forceinline__ void ff_tma_tile(const Dev &d, double *smem_fft, cons
         M::jac(x, u, J, d.dt);
       }
       M::expand(J, A, Bm, d.dt);
-      costgrad(t, x, u, rx, ru, cx, cu, qz, sq);
+      costgrad(t, x, u, rx, ru, cx, cu, qz, sq, rhx_c, rhu_c);
       ff_step<M>(A, Bm, cx, cu, Qux, Quu, Qui, v, kt);
       if (live) {
 #pragma unroll
@@ -1317,6 +1343,8 @@ __device__ __forceinline__ void ff_tma_tile(const Dev &d, double *smem_fft, cons
 #pragma unroll
   for (int i = 0; i < n; i++) dx[i] = 0.0;
   double c0 = 0.0, c1 = 0.0, c2 = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0;
+#pragma unroll
+  for (int j = 0; j < m; j++) rhu_n[j] = s_rhu[j];         // step 0; every step fetches its successor's
   for (int ch = 0; ch < nchf; ch++) {
     const int st = (int)((gf + ch) % NSTF), t_lo = ch * TC, cnt = min(TC, N - t_lo);
     const double *sf = ring + (size_t)st * TC * SF * TILE + lane;
@@ -1324,7 +1352,13 @@ __device__ __forceinline__ void ff_tma_tile(const Dev &d, double *smem_fft, cons
 #pragma unroll 1
     for (int tt = 0; tt < cnt; tt++) {
       const int t = t_lo + tt;
-      double duv[m], u[m], K[m][n], kv[m], ru[m];
+      double duv[m], u[m], K[m][n], kv[m], ru[m], rhu_c[m];
+#pragma unroll
+      for (int j = 0; j < m; j++) rhu_c[j] = rhu_n[j];
+      if (t + 1 < N) {
+#pragma unroll
+        for (int j = 0; j < m; j++) rhu_n[j] = s_rhu[(t + 1) * m + j];
+      }
 #pragma unroll
       for (int a = 0; a < m; a++) {
 #pragma unroll
@@ -1346,7 +1380,7 @@ __device__ __forceinline__ void ff_tma_tile(const Dev &d, double *smem_fft, cons
         r1 = fma(rw[a] * u[a], duv[a], r1);
         r2 = fma(rw[a] * duv[a], duv[a], r2);
         if (pu) {
-          const double rho = s_rhu[t * m + a], e = u[a] - ru[a];
+          const double rho = rhu_c[a], e = u[a] - ru[a];
           c0 = fma(rho * e, e, c0);
           c1 = fma(2.0 * rho * e, duv[a], c1);
           c2 = fma(rho * duv[a], duv[a], c2);
