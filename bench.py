@@ -475,8 +475,8 @@ def rooflines(prof, B, p, fp64_peak):
                     "peak_gbs": hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=65,536 from the committed
-            # `ncu --set full` capture (profiles/r2b_ncu_c5_kernels.csv), scaled to this batch size
-            "traffic": round(794.6e6 * B / 65536.0), "traffic_source": "profiles/r2b_ncu_c5_kernels.csv",
+            # `ncu --set full` capture (profiles/r2c_ncu_c5_kernels.csv), scaled to this batch size
+            "traffic": round(763.6e6 * B / 65536.0), "traffic_source": "profiles/r2c_ncu_c5_kernels.csv",
             "two_phase": {"epilogue_bytes_per_launch": epi_bytes, "bound_ms": round(t_bound * 1e3, 4),
                           "measured_ms": round(t_ls * 1e3, 4), "frac": round(t_bound / t_ls, 4)}}
     if "ff" in prof:
@@ -491,9 +491,9 @@ def rooflines(prof, B, p, fp64_peak):
                                  "unit": "GB/s", "frac": round(ff_bytes / (ff_ms / ff_n * 1e-3) / 1e9 / hbm_peak, 4),
                                  "algorithmic_bytes_per_launch": ff_bytes, "doubles_per_problem_step": 40,
                                  # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 65,536 problems
-                                 # (profiles/r2b_ncu_c5_kernels.csv: 1.840 + 0.205 GB; k is written and read back
+                                 # (profiles/r2c_ncu_c5_kernels.csv: 1.841 + 0.205 GB; k is written and read back
                                  # through L2), scaled to this batch size
-                                 "traffic": round(2045.4e6 * B / 65536.0)}
+                                 "traffic": round(2045.9e6 * B / 65536.0)}
     if "kpass" in prof:
         # the Riccati K-pass named by BASELINE.json's metric: fused-model variant (Jacobians recomputed in-kernel), per
         # problem-step x^, u^ in (6 doubles; the car never loads x, y) and K, Qux, packed Quu, Quu^-1 out (22 doubles)
@@ -510,8 +510,8 @@ def rooflines(prof, B, p, fp64_peak):
                                            "achieved_tflops": round(kp_flops / t / 1e12, 3),
                                            "frac_of_dfma_peak": round(kp_flops / t / 1e12 / fp64_peak, 4)},
                                   "passes_per_s": round(B / t, 1),
-                                  # dram bytes read + written of one launch, profiles/r2b_ncu_c5_kernels.csv
-                                  "traffic": round(1668.7e6 * B / 65536.0)}
+                                  # dram bytes read + written of one launch, profiles/r2c_ncu_c5_kernels.csv
+                                  "traffic": round(1669.9e6 * B / 65536.0)}
     return roof
 
 
